@@ -1,0 +1,292 @@
+"""CPU oracle for the H-field hot path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs may import this module; the product package
+(``pl-fem-vectoriel_b200/``) never does and has no CPU fallback.
+
+What it is: a NumPy restatement of the arithmetic the reference delegates to
+scikit-fem (which is neither vendored in ``/root/reference`` nor installable
+here), feeding the REAL ``scipy.sparse`` block algebra and the REAL
+``scipy.sparse.linalg.eigsh`` with the reference's exact arguments, followed by
+the reference's post-processing restated line by line:
+
+* ``P2Basis``                 <- ``Basis(mesh, ElementTriP2())``  (`solver_fem.py:126`)
+* ``assemble_form`` / ``asm`` <- ``@BilinearForm`` + ``asm``        (`solver_fem.py:131-156`)
+* ``assemble_hfield_system``  <- `solver_fem.py:122-169`
+* ``solve_vectorial_modes``   <- `solver_fem.py:171-239`
+* ``polarization_from_interp``<- `solver_fem.py:68-107`
+
+PARITY UNPINNED: the reference ships no test, golden vector or stored result
+for this path and scikit-fem (third-party, unpinned,
+README says ``scikit-fem>=6.0``) cannot be run here, so the scikit-fem part of
+this file follows its published algorithm from recall:
+column-sorted ``t``, lexicographically unique facets, DOF = vertex id /
+V + facet id, the 6-point degree-4 Dunavant rule, ``invDF``-transposed
+gradients, COO ``eliminate_zeros`` then ``tocsr``.  The SciPy part is the real
+thing.  The restatement is checked against closed-form facts instead
+(`tests/test_oracle.py`: exact P2 mass/stiffness matrices of a reference
+triangle, partition of unity, mesh area, symmetry, Kyx = Kxyᵀ).
+
+The only deliberate departure from the reference call: ``eigsh`` receives a
+fixed start vector ``v0 = ones`` (SciPy draws a random one otherwise, so the
+reference is not reproducible run to run).
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy.sparse import bmat, coo_matrix
+from scipy.sparse.linalg import eigsh
+
+# 6-point, degree-4 rule on the reference triangle (weights sum to 1/2)
+_A, _B = 0.445948490915965, 0.091576213509771
+_WA, _WB = 0.111690794839005, 0.054975871827661
+QUAD_X = np.array([[_A, _A, 1 - 2 * _A, _B, _B, 1 - 2 * _B],
+                   [_A, 1 - 2 * _A, _A, _B, 1 - 2 * _B, _B]])
+QUAD_W = np.array([_WA, _WA, _WA, _WB, _WB, _WB])
+
+# reference coordinates of the six P2 nodes: 3 vertices, midpoints of (0,1),(1,2),(0,2)
+REF_DOFLOCS = np.array([[0.0, 1.0, 0.0, 0.5, 0.5, 0.0],
+                        [0.0, 0.0, 1.0, 0.0, 0.5, 0.5]])
+
+
+def lbasis(X, i):
+    """Quadratic Lagrange shape function i and its reference gradient at X (2, nq)."""
+    x, y = X
+    if i == 0:
+        return 1.0 - 3.0 * x - 3.0 * y + 2.0 * x ** 2 + 4.0 * x * y + 2.0 * y ** 2, \
+            np.array([-3.0 + 4.0 * x + 4.0 * y, -3.0 + 4.0 * x + 4.0 * y])
+    if i == 1:
+        return 2.0 * x ** 2 - x, np.array([4.0 * x - 1.0, 0.0 * x])
+    if i == 2:
+        return 2.0 * y ** 2 - y, np.array([0.0 * x, 4.0 * y - 1.0])
+    if i == 3:
+        return 4.0 * x - 4.0 * x ** 2 - 4.0 * x * y, np.array([4.0 - 8.0 * x - 4.0 * y, -4.0 * x])
+    if i == 4:
+        return 4.0 * x * y, np.array([4.0 * y, 4.0 * x])
+    if i == 5:
+        return 4.0 * y - 4.0 * x * y - 4.0 * y ** 2, np.array([-4.0 * y, 4.0 - 4.0 * x - 8.0 * y])
+    raise IndexError(i)
+
+
+def reference_tables():
+    """(phi[6,6], dphix[6,6], dphiy[6,6]) — shape function i at quadrature point q."""
+    phi = np.empty((6, 6)); dx = np.empty((6, 6)); dy = np.empty((6, 6))
+    for i in range(6):
+        phi[i], (dx[i], dy[i]) = lbasis(QUAD_X, i)
+    return phi, dx, dy
+
+
+class P2Basis:
+    """DOF tables, affine maps and quadrature data of ``Basis(mesh, ElementTriP2())``."""
+
+    def __init__(self, mesh):
+        p = np.asarray(mesh.p, dtype=np.float64)
+        t = np.asarray(mesh.t, dtype=np.int64)
+        V, T = p.shape[1], t.shape[1]
+        self.p, self.t = p, t
+        # facets: local edges (0,1),(1,2),(0,2); unique sorted vertex pairs, lexicographic
+        e = np.sort(np.hstack([t[[0, 1]], t[[1, 2]], t[[0, 2]]]), axis=0)
+        self.facets, inv = np.unique(e, axis=1, return_inverse=True)
+        self.t2f = np.asarray(inv).reshape(3, T)
+        E = self.facets.shape[1]
+        self.N = V + E
+        self.element_dofs = np.vstack([t, V + self.t2f])
+        # affine map x = A X + b
+        self.A = np.array([[p[0, t[1]] - p[0, t[0]], p[0, t[2]] - p[0, t[0]]],
+                           [p[1, t[1]] - p[1, t[0]], p[1, t[2]] - p[1, t[0]]]])      # (2,2,T)
+        self.b = p[:, t[0]]
+        self.detA = self.A[0, 0] * self.A[1, 1] - self.A[0, 1] * self.A[1, 0]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            self.invA = np.array([[self.A[1, 1], -self.A[0, 1]],
+                                  [-self.A[1, 0], self.A[0, 0]]]) / self.detA
+        # quadrature points in global coordinates, (2, T, 6), and dx (T, 6)
+        self.x = np.array([self.A[i, 0][:, None] * QUAD_X[0][None, :]
+                           + self.A[i, 1][:, None] * QUAD_X[1][None, :]
+                           + self.b[i][:, None] for i in range(2)])
+        self.dx = np.abs(self.detA)[:, None] * QUAD_W[None, :]
+        # global basis: value (T,6) and gradient (2,T,6) per local shape function
+        self.phi, self.grad = [], []
+        for i in range(6):
+            ph, dph = lbasis(QUAD_X, i)
+            self.phi.append(np.broadcast_to(ph, (T, 6)))
+            with np.errstate(invalid="ignore"):
+                self.grad.append(np.array([
+                    self.invA[0, j][:, None] * dph[0][None, :] + self.invA[1, j][:, None] * dph[1][None, :]
+                    for j in range(2)]))
+        # DOF locations: affine image of the reference nodes, later elements overwrite
+        self.doflocs = np.zeros((2, self.N))
+        for k in range(6):
+            X = REF_DOFLOCS[:, k]
+            for i in range(2):
+                self.doflocs[i, self.element_dofs[k]] = self.A[i, 0] * X[0] + self.A[i, 1] * X[1] + self.b[i]
+
+    def boundary_dofs(self) -> np.ndarray:
+        """``basis.get_dofs().all()``: nodal + facet DOFs of facets owned by one element."""
+        count = np.bincount(self.t2f.ravel(), minlength=self.facets.shape[1])
+        bf = np.nonzero(count == 1)[0]
+        V = self.p.shape[1]
+        return np.unique(np.concatenate([self.facets[:, bf].ravel(), V + bf]))
+
+
+def assemble_form(basis: P2Basis, form) -> "scipy.sparse.csr_matrix":
+    """``asm(BilinearForm(form), basis)``: ``form(u, gu, v, gv, x)`` with u trial, v test."""
+    T = basis.t.shape[1]
+    rows = np.empty(36 * T, dtype=np.int64)
+    cols = np.empty(36 * T, dtype=np.int64)
+    data = np.empty(36 * T)
+    for j in range(6):
+        for i in range(6):
+            s = slice(T * (6 * j + i), T * (6 * j + i + 1))
+            rows[s] = basis.element_dofs[i]
+            cols[s] = basis.element_dofs[j]
+            data[s] = np.sum(form(basis.phi[j], basis.grad[j], basis.phi[i], basis.grad[i], basis.x) * basis.dx,
+                             axis=1)
+    K = coo_matrix((data, (rows, cols)), shape=(basis.N, basis.N))
+    K.eliminate_zeros()
+    return K.tocsr()
+
+
+def hfield_forms(eps_fn, faithful_cost: bool = False):
+    """The nine bilinear forms of `solver_fem.py:131-150`, same expression order.
+
+    ε at the quadrature points never changes between the 180 form calls, so it is
+    evaluated once unless ``faithful_cost`` asks for the reference's 180 evaluations
+    (used when this oracle is timed as the CPU baseline); the values are identical.
+    """
+    memo = {}
+
+    def w(x):
+        if faithful_cost:
+            return 1.0 / np.real(eps_fn(*x))
+        if id(x) not in memo:
+            memo[id(x)] = (x, 1.0 / np.real(eps_fn(*x)))
+        return memo[id(x)][1]
+    return dict(
+        kxx=lambda u, gu, v, gv, x: w(x) * gu[1] * gv[1],
+        kyy=lambda u, gu, v, gv, x: w(x) * gu[0] * gv[0],
+        kxy=lambda u, gu, v, gv, x: -w(x) * gu[1] * gv[0],
+        kyx=lambda u, gu, v, gv, x: -w(x) * gu[0] * gv[1],
+        dxx=lambda u, gu, v, gv, x: gu[0] * gv[0],
+        dyy=lambda u, gu, v, gv, x: gu[1] * gv[1],
+        dxy=lambda u, gu, v, gv, x: gu[0] * gv[1],
+        mass=lambda u, gu, v, gv, x: u * v,
+        minv=lambda u, gu, v, gv, x: w(x) * u * v,
+    )
+
+
+def assemble_scalar_matrices(geometry, mesh, faithful_cost: bool = False):
+    basis = P2Basis(mesh)
+    forms = hfield_forms(geometry.epsilon, faithful_cost)
+    return basis, {k: assemble_form(basis, f) for k, f in forms.items()}
+
+
+def assemble_hfield_system(geometry, mesh, faithful_cost: bool = False):
+    """`solver_fem.py:122-169` -> (A, B, basis, Dxx, Dyy, Dxy, M_inv)."""
+    basis, m = assemble_scalar_matrices(geometry, mesh, faithful_cost)
+    alpha_p = 1.0
+    k0sq = geometry.k0 ** 2
+    A_xx = m["kxx"] + alpha_p * m["dxx"] - k0sq * m["mass"]
+    A_yy = m["kyy"] + alpha_p * m["dyy"] - k0sq * m["mass"]
+    A_xy = m["kxy"] + alpha_p * m["dxy"]
+    A_yx = m["kyx"] + alpha_p * m["dxy"].T
+    A = bmat([[A_xx, A_xy], [A_yx, A_yy]], format="csr")
+    B = bmat([[m["minv"], None], [None, m["minv"]]], format="csr")
+    return A, B, basis, m["dxx"], m["dyy"], m["dxy"], m["minv"]
+
+
+def sigma_estimate(geometry) -> float:
+    """LP01 shift of `solver_fem.py:187-193`."""
+    n_core, n_clad, k0 = geometry.n_core, geometry.n_clad, geometry.k0
+    NA = np.sqrt(max(n_core ** 2 - n_clad ** 2, 1e-6))
+    V_geom = k0 * np.mean(geometry.core_radii) * NA
+    b_approx = max((1.0 - 2.405 / max(V_geom, 2.41)) ** 2, 0.05)
+    n_eff_est = np.sqrt(n_clad ** 2 + b_approx * (n_core ** 2 - n_clad ** 2))
+    return (k0 * float(np.clip(n_eff_est, n_clad + 0.05, n_core - 0.005))) ** 2
+
+
+def core_mask(geometry, x, y) -> np.ndarray:
+    m = np.zeros(len(x), dtype=bool)
+    for (cx, cy), r in zip(geometry.positions, geometry.core_radii):
+        m |= (x - cx) ** 2 + (y - cy) ** 2 <= r ** 2
+    return m
+
+
+def polarization_from_interp(vx, vy, x, y, geometry):
+    """`solver_fem.py:68-107`."""
+    in_core = core_mask(geometry, x, y)
+    mask = in_core if np.any(in_core) else np.ones(len(x), dtype=bool)
+    P_x = float(np.sum(vx[mask] ** 2)) + 1e-30
+    P_y = float(np.sum(vy[mask] ** 2)) + 1e-30
+    ratio = P_x / P_y
+    PDL = float(np.clip(10.0 * np.log10(max(P_x, P_y) / min(P_x, P_y)), 0.0, 50.0))
+    pol = ("TE-like" if ratio > 10.0 else "HE-like" if ratio > 2.5 else
+           "Hybrid" if ratio > 0.4 else "EH-like" if ratio > 0.1 else "TM-like")
+    return pol, PDL, P_x, P_y
+
+
+def interior_system(geometry, mesh, faithful_cost: bool = False):
+    A, B, basis, Dxx, Dyy, Dxy, M_inv = assemble_hfield_system(geometry, mesh, faithful_cost)
+    N = basis.N
+    interior = np.setdiff1d(np.arange(N), basis.boundary_dofs())
+    idx = np.concatenate([interior, interior + N])
+    return dict(A=A, B=B, basis=basis, Dxx=Dxx, Dyy=Dyy, Dxy=Dxy, M_inv=M_inv, interior=interior,
+                A_int=A[idx, :][:, idx], B_int=B[idx, :][:, idx])
+
+
+def select_modes(modes_raw, frac_core):
+    """Divergence and radiation filters + sort (`solver_fem.py:228-239`)."""
+    dr = np.array([m["div_ratio"] for m in modes_raw])
+    thr = max(np.median(dr) * 10, dr.min() * 50, 1e-6)
+    phys = [m for m in modes_raw if m["div_ratio"] <= thr]
+    conf_thr = max(5.0 * frac_core, 0.05)
+    guided = [m for m in phys if m["confinement"] >= conf_thr] or phys
+    guided.sort(key=lambda m: m["n_eff"], reverse=True)
+    return guided
+
+
+def solve_vectorial_modes(geometry, mesh, n_modes_target: int = 20, v0="ones",
+                          faithful_cost: bool = False, return_raw: bool = False):
+    """`solver_fem.py:171-239`, verbatim but for the fixed ``v0``."""
+    s = interior_system(geometry, mesh, faithful_cost)
+    basis, interior = s["basis"], s["interior"]
+    A_int, B_int = s["A_int"], s["B_int"]
+    N_solve = len(interior)
+    x_int, y_int = basis.doflocs[0][interior], basis.doflocs[1][interior]
+    sigma = sigma_estimate(geometry)
+    n_req = min(n_modes_target + 12, 2 * N_solve - 4)
+    if isinstance(v0, str) and v0 == "ones":
+        v0 = np.ones(2 * N_solve)
+    beta_sq, evecs = eigsh(A_int, k=n_req, M=B_int, sigma=sigma, which="LM", tol=1e-7,
+                           maxiter=12000, v0=v0)
+
+    in_core = core_mask(geometry, x_int, y_int)
+    frac_core = np.sum(in_core) / N_solve
+    Dxx, Dyy, Dxy = s["Dxx"], s["Dyy"], s["Dxy"]
+    k0, n_core, n_clad = geometry.k0, geometry.n_core, geometry.n_clad
+    modes_raw = []
+    for i in range(len(beta_sq)):
+        b2 = beta_sq[i]
+        if b2 <= 0:
+            continue
+        beta = np.sqrt(b2); ne = beta / k0
+        if ne <= n_clad or ne >= n_core * 1.01:
+            continue
+        vx = evecs[:N_solve, i].copy(); vy = evecs[N_solve:, i].copy()
+        nrm = np.sqrt(np.sum(vx ** 2) + np.sum(vy ** 2)) + 1e-30
+        vx /= nrm; vy /= nrm
+        div_energy = float(vx @ (Dxx[interior, :][:, interior] @ vx)
+                           + 2 * vx @ (Dxy[interior, :][:, interior] @ vy)
+                           + vy @ (Dyy[interior, :][:, interior] @ vy))
+        div_ratio = div_energy / max(b2, 1e-12)
+        e = vx ** 2 + vy ** 2
+        conf = float(np.sum(e[in_core]) / np.sum(e))
+        pol, PDL_dB, P_x, P_y = polarization_from_interp(vx, vy, x_int, y_int, geometry)
+        modes_raw.append({"n_eff": float(ne), "beta": float(beta), "Ex_dofs": vx, "Ey_dofs": vy,
+                          "P_x": P_x, "P_y": P_y, "PDL_dB": PDL_dB, "polarization": pol,
+                          "confinement": conf, "core_overlap": conf, "div_ratio": div_ratio,
+                          "is_vectorial": True, "method": "H-field_V18.10"})
+    modes = select_modes(modes_raw, frac_core)
+    if return_raw:
+        return modes, dict(beta_sq=beta_sq, evecs=evecs, sigma=sigma, modes_raw=modes_raw,
+                           frac_core=frac_core, system=s)
+    return modes
