@@ -1,0 +1,153 @@
+/* plfem.h — C ABI of the B200-native H-field P2 FEM mode solver.
+ *
+ * The reference (KhaoulaAguech/pl-fem-vectoriel) has no FFI: its boundary for this path is the
+ * Python class `TrueVectorialMaxwellSolver` (solver_fem.py:113-239), which delegates the
+ * arithmetic to scikit-fem and SciPy.  This header is what a binding for that class calls
+ * instead; each entry point names the reference lines it replaces.  Plain pointers and sizes
+ * only, `int` status returns (0 = ok), no exceptions cross the boundary; the message of the last
+ * failure is available from plfem_last_error().
+ *
+ * Conventions
+ *   - arrays are C-contiguous like NumPy: p is (2,V) float64, t is (3,T) int64;
+ *   - "reference ordering" of an interior vector is [Hx(interior...), Hy(interior...)]
+ *     (solver_fem.py:181);
+ *   - all output buffers are caller-owned HOST memory unless the name ends in `_dev`.
+ *   - a context is bound to one CUDA device and one stream; contexts are independent and may be
+ *     driven from different host threads.
+ */
+#ifndef PLFEM_H
+#define PLFEM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct plfem_ctx plfem_ctx;
+typedef struct plfem_problem plfem_problem;
+
+enum plfem_status {
+  PLFEM_OK = 0,
+  PLFEM_ERR_CUDA = 1,         /* a CUDA runtime call failed or no usable device */
+  PLFEM_ERR_INVALID = 2,      /* bad argument (null pointer, negative size, index out of range) */
+  PLFEM_ERR_DEGENERATE = 3,   /* the mesh holds zero-area triangles (scikit-fem would divide by zero) */
+  PLFEM_ERR_NOT_READY = 4,    /* call order violated (e.g. export before assemble) */
+  PLFEM_ERR_NO_CONVERGENCE = 5, /* eigensolver hit maxiter (scipy: ArpackNoConvergence) */
+  PLFEM_ERR_SINGULAR = 6,     /* shifted operator numerically singular (scipy: "Factor is exactly singular") */
+  PLFEM_ERR_INTERNAL = 7
+};
+
+/* ---- context ---------------------------------------------------------------------------------- */
+int plfem_ctx_create(int device, plfem_ctx** out);
+void plfem_ctx_destroy(plfem_ctx* ctx);
+const char* plfem_last_error(const plfem_ctx* ctx);
+/* abi / build identification: "plfem <version> sm_100a" */
+const char* plfem_version(void);
+
+/* ---- mesh + DOF tables:  Basis(mesh, ElementTriP2())  (solver_fem.py:126), get_dofs (:179-180) -- */
+typedef struct {
+  int64_t V, T, E, N;          /* vertices, triangles, facets, scalar P2 DOFs (N = V + E) */
+  int64_t n_boundary, n_interior;
+  int64_t nnz_scalar;          /* structural nnz of one scalar N x N matrix */
+  int64_t n_degenerate;        /* zero-area triangles found */
+} plfem_mesh_info;
+
+/* ctx may be NULL: a host-only problem (DOF tables, front plan) that needs no GPU; assembly and
+ * solves on it return PLFEM_ERR_INVALID */
+int plfem_problem_create(plfem_ctx* ctx, const double* p, const int64_t* t, int64_t V, int64_t T,
+                         plfem_problem** out);
+void plfem_problem_destroy(plfem_problem* pb);
+int plfem_problem_info(const plfem_problem* pb, plfem_mesh_info* info);
+/* element_dofs (6,T) int64, doflocs (2,N) float64, boundary (n_boundary) int64, interior (n_interior)
+ * int64; any pointer may be NULL to skip it */
+int plfem_problem_dofs(const plfem_problem* pb, int64_t* element_dofs, double* doflocs,
+                       int64_t* boundary, int64_t* interior);
+
+/* ---- material:  geometry.epsilon(x, y)  (geometry_unified.py:325-347) ------------------------- */
+typedef struct {
+  const double* cores_xy;      /* (n_cores, 2) core centres [um] */
+  const double* cores_r;       /* (n_cores)    core radii   [um] */
+  int32_t n_cores;
+  double eps_core, eps_clad;   /* Re eps = n_core^2, n_clad^2 (evaluated by the caller) */
+  double k0;                   /* 2 pi / lambda [1/um] */
+  double alpha_p;              /* divergence penalty, reference uses 1.0 (solver_fem.py:158) */
+  const double* eps_at_quad;   /* optional (T,6) Re eps sampled by the caller at plfem_quad_points();
+                                  when non-NULL it overrides the disc model */
+} plfem_material;
+
+/* global coordinates of the 6 quadrature points of every element, out_xy is (2,T,6) float64 */
+int plfem_quad_points(const plfem_problem* pb, double* out_xy);
+
+/* ---- assembly:  9 x asm(form, basis) + block build  (solver_fem.py:131-167) -------------------- */
+enum plfem_matrix {
+  PLFEM_MAT_A = 0,      /* 2N x 2N  [[Kxx+aDxx-k0^2 M, Kxy+aDxy],[Kyx+aDxy^T, Kyy+aDyy-k0^2 M]] */
+  PLFEM_MAT_B = 1,      /* 2N x 2N  blockdiag(M_inv, M_inv) */
+  PLFEM_MAT_DXX = 2, PLFEM_MAT_DYY = 3, PLFEM_MAT_DXY = 4, PLFEM_MAT_MINV = 5,  /* N x N, as returned */
+  PLFEM_MAT_KXX = 6, PLFEM_MAT_KYY = 7, PLFEM_MAT_KXY = 8, PLFEM_MAT_KYX = 9, PLFEM_MAT_M = 10,
+  PLFEM_MAT_A_INT = 11, /* A[idx,:][:,idx], idx = [interior, interior+N]  (solver_fem.py:181-182) */
+  PLFEM_MAT_B_INT = 12
+};
+/* assemble all scalar matrices on the device over the full N x N pattern */
+int plfem_assemble(plfem_problem* pb, const plfem_material* mat);
+/* CSR export with SciPy's structure rules (element-level zeros dropped by asm, exact-zero sums
+ * dropped by sparse +/-, sorted indices).  Call with data == NULL to get nnz first.
+ * indptr has rows+1 entries (int64), indices nnz (int64), data nnz (float64). */
+int plfem_export_csr(plfem_problem* pb, int which, int64_t* rows, int64_t* nnz, int64_t* indptr,
+                     int64_t* indices, double* data);
+
+/* ---- CSR SpMV (scipy csr_matvec; solver_fem.py:214 and the M-product inside eigsh) ------------- */
+/* y = M x on the device for an exported matrix; x, y are HOST vectors of length rows.  `repeat`
+ * launches are timed with CUDA events; avg milliseconds per launch is returned in *ms. */
+int plfem_spmv_csr(plfem_ctx* ctx, int64_t rows, int64_t nnz, const int64_t* indptr, const int64_t* indices,
+                   const double* data, const double* x, double* y, int repeat, float* ms);
+
+/* ---- modal solve:  Dirichlet elimination + eigsh + per-mode reductions (solver_fem.py:179-225) - */
+typedef struct {
+  double sigma;        /* shift (solver_fem.py:187-193, computed by the caller) */
+  int32_t k;           /* eigenpairs wanted = min(n_modes+12, 2 N_solve - 4)  (solver_fem.py:196) */
+  int32_t ncv;         /* Lanczos basis size; 0 = scipy's default max(2k+1, 20) */
+  double tol;          /* 1e-7 in the reference */
+  int32_t maxiter;     /* restarts allowed, 12000 in the reference */
+  const double* v0;    /* optional start vector, reference ordering, length 2 N_solve; NULL = ones */
+  int32_t leaf_nodes;  /* nested-dissection leaf size (0 = default) */
+  int32_t max_sn_nodes;/* supernode width limit in nodes (0 = default) */
+  int32_t reuse_symbolic; /* 1 = keep ordering/front plan from the previous solve on this problem */
+  int32_t refine;      /* iterative-refinement steps per operator application: 0 = default (1), n > 0 = n, -1 = none */
+} plfem_solve_opts;
+
+typedef struct {
+  int32_t nconv, n_op, n_restart;   /* converged pairs, operator applications, restarts */
+  int32_t n_fronts, n_levels, max_front_nodes;
+  int64_t factor_entries;           /* doubles read by one forward+backward sweep / 2 */
+  int64_t front_pool_doubles;
+  double factor_flops;
+  double max_residual;              /* max_i ||A x - lambda B x||_2 / (|lambda| ||B x||_2) with the true A, B */
+  float ms_symbolic, ms_assemble, ms_factor, ms_lanczos, ms_metrics, ms_total; /* host wall / CUDA events */
+  int32_t kernel_launches;
+} plfem_solve_stats;
+
+/* Per-mode reductions of solver_fem.py:212-220, computed on the l2-normalised (vx, vy):
+ * metrics is (k, 8): [div_energy, sum_e_core, sum_e, Px_core, Py_core, Px_all, Py_all, norm2_raw] */
+#define PLFEM_NMETRICS 8
+int plfem_solve_modes(plfem_problem* pb, const plfem_material* mat, const plfem_solve_opts* opts,
+                      double* eigvals,    /* (k) ascending, = beta^2 */
+                      double* evecs,      /* (k, 2 N_solve) reference ordering, l2-normalised; may be NULL */
+                      double* metrics,    /* (k, PLFEM_NMETRICS) */
+                      int32_t* core_dof_count, /* number of interior DOFs inside a core (solver_fem.py:200-203) */
+                      plfem_solve_stats* stats);
+
+/* ---- debug / test hooks (host logic checks that need no GPU) ----------------------------------- */
+/* sizes: [n, nfronts, nlevels, strct_len, cmap_len, nchild] */
+int plfem_plan_sizes(plfem_problem* pb, int32_t leaf_nodes, int32_t max_sn_nodes, int64_t sizes[6]);
+int plfem_plan_export(plfem_problem* pb, int32_t* perm, int32_t* first, int32_t* s, int32_t* parent,
+                      int32_t* level, int32_t* sptr, int32_t* strct, int32_t* cmap_ptr, int32_t* cmap,
+                      int64_t* foff);
+
+/* dense symmetric eigensolver used at Lanczos restarts: a is n*n column-major, overwritten by eigenvectors */
+int plfem_debug_symeig(int32_t n, double* a, double* w);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLFEM_H */

@@ -1,0 +1,282 @@
+"""ctypes binding of ``libplfem.so`` (the C ABI declared in ``include/plfem.h``).
+
+There is no CPU implementation behind this module: if the shared library is
+missing it is built with nvcc, and if that fails — or no CUDA device is usable
+when a context is requested — the error propagates.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libplfem.so"
+
+c_i32, c_i64, c_f64 = C.c_int32, C.c_int64, C.c_double
+p_i32, p_i64, p_f64 = C.POINTER(c_i32), C.POINTER(c_i64), C.POINTER(c_f64)
+
+STATUS = {0: "OK", 1: "CUDA", 2: "INVALID", 3: "DEGENERATE", 4: "NOT_READY", 5: "NO_CONVERGENCE",
+          6: "SINGULAR", 7: "INTERNAL"}
+MATRIX = dict(A=0, B=1, Dxx=2, Dyy=3, Dxy=4, M_inv=5, Kxx=6, Kyy=7, Kxy=8, Kyx=9, M=10, A_int=11, B_int=12)
+NMETRICS = 8
+
+#: every symbol include/plfem.h declares (checked by tests/test_cabi.py)
+SYMBOLS = ["plfem_ctx_create", "plfem_ctx_destroy", "plfem_last_error", "plfem_version",
+           "plfem_problem_create", "plfem_problem_destroy", "plfem_problem_info", "plfem_problem_dofs",
+           "plfem_quad_points", "plfem_assemble", "plfem_export_csr", "plfem_spmv_csr", "plfem_solve_modes",
+           "plfem_plan_sizes", "plfem_plan_export", "plfem_debug_symeig"]
+
+
+class MeshInfo(C.Structure):
+    _fields_ = [(n, c_i64) for n in ("V", "T", "E", "N", "n_boundary", "n_interior", "nnz_scalar", "n_degenerate")]
+
+
+class Material(C.Structure):
+    _fields_ = [("cores_xy", p_f64), ("cores_r", p_f64), ("n_cores", c_i32), ("eps_core", c_f64),
+                ("eps_clad", c_f64), ("k0", c_f64), ("alpha_p", c_f64), ("eps_at_quad", p_f64)]
+
+
+class SolveOpts(C.Structure):
+    _fields_ = [("sigma", c_f64), ("k", c_i32), ("ncv", c_i32), ("tol", c_f64), ("maxiter", c_i32),
+                ("v0", p_f64), ("leaf_nodes", c_i32), ("max_sn_nodes", c_i32), ("reuse_symbolic", c_i32),
+                ("refine", c_i32)]
+
+
+class SolveStats(C.Structure):
+    _fields_ = [("nconv", c_i32), ("n_op", c_i32), ("n_restart", c_i32), ("n_fronts", c_i32),
+                ("n_levels", c_i32), ("max_front_nodes", c_i32), ("factor_entries", c_i64),
+                ("front_pool_doubles", c_i64), ("factor_flops", c_f64), ("max_residual", c_f64),
+                ("ms_symbolic", C.c_float), ("ms_assemble", C.c_float), ("ms_factor", C.c_float),
+                ("ms_lanczos", C.c_float), ("ms_metrics", C.c_float), ("ms_total", C.c_float),
+                ("kernel_launches", c_i32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class PlfemError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"plfem [{STATUS.get(status, status)}]: {message}")
+        self.status = status
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Load (building first if needed) the CUDA library.  Never falls back to anything else."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not LIB_PATH.exists():
+            from . import build as _build
+            _build.build()
+        lib = C.CDLL(str(LIB_PATH))
+        vp = C.c_void_p
+        lib.plfem_version.restype = C.c_char_p
+        lib.plfem_last_error.restype = C.c_char_p
+        lib.plfem_last_error.argtypes = [vp]
+        lib.plfem_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+        lib.plfem_ctx_destroy.argtypes = [vp]
+        lib.plfem_ctx_destroy.restype = None
+        lib.plfem_problem_create.argtypes = [vp, p_f64, p_i64, c_i64, c_i64, C.POINTER(vp)]
+        lib.plfem_problem_destroy.argtypes = [vp]
+        lib.plfem_problem_destroy.restype = None
+        lib.plfem_problem_info.argtypes = [vp, C.POINTER(MeshInfo)]
+        lib.plfem_problem_dofs.argtypes = [vp, p_i64, p_f64, p_i64, p_i64]
+        lib.plfem_quad_points.argtypes = [vp, p_f64]
+        lib.plfem_assemble.argtypes = [vp, C.POINTER(Material)]
+        lib.plfem_export_csr.argtypes = [vp, C.c_int, p_i64, p_i64, p_i64, p_i64, p_f64]
+        lib.plfem_spmv_csr.argtypes = [vp, c_i64, c_i64, p_i64, p_i64, p_f64, p_f64, p_f64, C.c_int,
+                                       C.POINTER(C.c_float)]
+        lib.plfem_solve_modes.argtypes = [vp, C.POINTER(Material), C.POINTER(SolveOpts), p_f64, p_f64, p_f64,
+                                          p_i32, C.POINTER(SolveStats)]
+        lib.plfem_plan_sizes.argtypes = [vp, c_i32, c_i32, p_i64]
+        lib.plfem_plan_export.argtypes = [vp] + [p_i32] * 9 + [p_i64]
+        lib.plfem_debug_symeig.argtypes = [c_i32, p_f64, p_f64]
+        _lib = lib
+        return lib
+
+
+def _ptr(a, typ):
+    return a.ctypes.data_as(typ) if a is not None else None
+
+
+class Context:
+    """One CUDA device + stream (``plfem_ctx``).  Contexts are cached per device."""
+    _cache: dict = {}
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = C.c_void_p()
+        st = self.lib.plfem_ctx_create(int(device), C.byref(h))
+        if st != 0:
+            raise PlfemError(st, f"cannot create a CUDA context on device {device} "
+                                 "(this package has no CPU path)")
+        self.handle, self.device = h, int(device)
+
+    @classmethod
+    def get(cls, device: int = 0) -> "Context":
+        if device not in cls._cache:
+            cls._cache[device] = cls(device)
+        return cls._cache[device]
+
+    def check(self, st: int):
+        if st != 0:
+            raise PlfemError(st, self.lib.plfem_last_error(self.handle).decode(errors="replace"))
+
+    def spmv_csr(self, M, x, repeat: int = 1):
+        """y = M @ x on the device for a SciPy CSR matrix; returns (y, avg ms per launch)."""
+        M = M.tocsr()
+        indptr = np.ascontiguousarray(M.indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(M.indices, dtype=np.int64)
+        data = np.ascontiguousarray(M.data, dtype=np.float64)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty(M.shape[0])
+        ms = C.c_float()
+        self.check(self.lib.plfem_spmv_csr(self.handle, M.shape[0], M.nnz, _ptr(indptr, p_i64), _ptr(indices, p_i64),
+                                           _ptr(data, p_f64), _ptr(x, p_f64), _ptr(y, p_f64), repeat, C.byref(ms)))
+        return y, ms.value
+
+    def __del__(self):
+        pass  # contexts live for the process; the driver reclaims them at exit
+
+
+def material_struct(geometry, alpha_p: float = 1.0, eps_at_quad=None):
+    """(Material, keep-alive tuple) from a geometry duck-type (`geometry_unified.py:200-201`)."""
+    pos = np.ascontiguousarray(np.atleast_2d(np.asarray(geometry.positions, dtype=np.float64)))
+    rad = np.ascontiguousarray(np.asarray(geometry.core_radii, dtype=np.float64))
+    m = Material()
+    m.cores_xy, m.cores_r, m.n_cores = _ptr(pos, p_f64), _ptr(rad, p_f64), len(rad)
+    m.eps_core, m.eps_clad = float(geometry.n_core ** 2), float(geometry.n_clad ** 2)
+    m.k0, m.alpha_p = float(geometry.k0), float(alpha_p)
+    keep = [pos, rad]
+    if eps_at_quad is not None:
+        e = np.ascontiguousarray(eps_at_quad, dtype=np.float64)
+        m.eps_at_quad = _ptr(e, p_f64)
+        keep.append(e)
+    return m, keep
+
+
+class Problem:
+    """One mesh: DOF tables, patterns, front plan and device buffers (``plfem_problem``)."""
+
+    def __init__(self, mesh, ctx: "Context | None" = None, host_only: bool = False):
+        self.lib = load()
+        self.ctx = None if host_only else (ctx or Context.get(0))
+        p = np.ascontiguousarray(mesh.p, dtype=np.float64)
+        t = np.ascontiguousarray(mesh.t, dtype=np.int64)
+        if p.ndim != 2 or p.shape[0] != 2 or t.ndim != 2 or t.shape[0] != 3:
+            raise ValueError("mesh.p must be (2,V) and mesh.t (3,T)")
+        h = C.c_void_p()
+        st = self.lib.plfem_problem_create(self.ctx.handle if self.ctx else None, _ptr(p, p_f64), _ptr(t, p_i64),
+                                           p.shape[1], t.shape[1], C.byref(h))
+        if st != 0:
+            msg = self.lib.plfem_last_error(self.ctx.handle).decode() if self.ctx else "invalid mesh"
+            raise PlfemError(st, msg)
+        self.handle = h
+        info = MeshInfo()
+        self.lib.plfem_problem_info(h, C.byref(info))
+        self.info = info
+        self.V, self.T, self.N = info.V, info.T, info.N
+        self.n_interior = info.n_interior
+
+    def _check(self, st):
+        if st != 0:
+            if self.ctx is None:
+                raise PlfemError(st, "host-only problem")
+            self.ctx.check(st)
+
+    def dofs(self):
+        ed = np.empty((6, self.T), dtype=np.int64)
+        loc = np.empty((2, self.N))
+        bnd = np.empty(self.info.n_boundary, dtype=np.int64)
+        itr = np.empty(self.info.n_interior, dtype=np.int64)
+        self._check(self.lib.plfem_problem_dofs(self.handle, _ptr(ed, p_i64), _ptr(loc, p_f64), _ptr(bnd, p_i64),
+                                                _ptr(itr, p_i64)))
+        return ed, loc, bnd, itr
+
+    def quad_points(self):
+        xy = np.empty((2, self.T, 6))
+        self._check(self.lib.plfem_quad_points(self.handle, _ptr(xy, p_f64)))
+        return xy
+
+    def assemble(self, material: Material):
+        self._check(self.lib.plfem_assemble(self.handle, C.byref(material)))
+
+    def export_csr(self, which: str):
+        from scipy.sparse import csr_matrix
+        wid = MATRIX[which]
+        rows, nnz = c_i64(), c_i64()
+        self._check(self.lib.plfem_export_csr(self.handle, wid, C.byref(rows), C.byref(nnz), None, None, None))
+        indptr = np.empty(rows.value + 1, dtype=np.int64)
+        indices = np.empty(nnz.value, dtype=np.int64)
+        data = np.empty(nnz.value)
+        self._check(self.lib.plfem_export_csr(self.handle, wid, C.byref(rows), C.byref(nnz), _ptr(indptr, p_i64),
+                                              _ptr(indices, p_i64), _ptr(data, p_f64)))
+        idx_t = np.int32 if max(rows.value, nnz.value) < 2 ** 31 else np.int64
+        return csr_matrix((data, indices.astype(idx_t), indptr.astype(idx_t)), shape=(rows.value, rows.value))
+
+    def solve_modes(self, material: Material, sigma: float, k: int, ncv: int = 0, tol: float = 1e-7,
+                    maxiter: int = 12000, v0=None, want_vectors: bool = True, leaf_nodes: int = 0,
+                    max_sn_nodes: int = 0, reuse_symbolic: bool = False, refine: int = 0):
+        n2 = 2 * self.n_interior
+        o = SolveOpts(sigma=float(sigma), k=int(k), ncv=int(ncv), tol=float(tol), maxiter=int(maxiter),
+                      leaf_nodes=int(leaf_nodes), max_sn_nodes=int(max_sn_nodes),
+                      reuse_symbolic=int(bool(reuse_symbolic)), refine=int(refine))
+        if v0 is not None:
+            v0 = np.ascontiguousarray(v0, dtype=np.float64)
+            if v0.shape != (n2,):
+                raise ValueError(f"v0 must have length {n2}")
+            o.v0 = _ptr(v0, p_f64)
+        vals = np.empty(k)
+        vecs = np.empty((k, n2)) if want_vectors else None
+        met = np.empty((k, NMETRICS))
+        ncore = c_i32()
+        stats = SolveStats()
+        self._check(self.lib.plfem_solve_modes(self.handle, C.byref(material), C.byref(o), _ptr(vals, p_f64),
+                                               _ptr(vecs, p_f64), _ptr(met, p_f64), C.byref(ncore), C.byref(stats)))
+        return vals, vecs, met, ncore.value, stats
+
+    def plan(self, leaf_nodes: int = 0, max_sn_nodes: int = 0) -> dict:
+        """Front plan as NumPy arrays (host logic; needs no GPU)."""
+        sz = np.zeros(6, dtype=np.int64)
+        self._check(self.lib.plfem_plan_sizes(self.handle, leaf_nodes, max_sn_nodes, _ptr(sz, p_i64)))
+        n, nf, nl, ns, nc, _ = (int(v) for v in sz)
+        a = dict(perm=np.empty(n, np.int32), first=np.empty(nf, np.int32), s=np.empty(nf, np.int32),
+                 parent=np.empty(nf, np.int32), level=np.empty(nf, np.int32), sptr=np.empty(nf + 1, np.int32),
+                 strct=np.empty(ns, np.int32), cmap_ptr=np.empty(nf + 1, np.int32), cmap=np.empty(nc, np.int32))
+        foff = np.empty(nf + 1, np.int64)
+        self._check(self.lib.plfem_plan_export(self.handle, *[_ptr(a[k], p_i32) for k in
+                                               ("perm", "first", "s", "parent", "level", "sptr", "strct", "cmap_ptr",
+                                                "cmap")], _ptr(foff, p_i64)))
+        a.update(foff=foff, n=n, nfronts=nf, nlevels=nl)
+        return a
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.plfem_problem_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def symeig(a: np.ndarray):
+    """Test hook for the restart eigensolver: returns (w ascending, eigenvectors in columns)."""
+    lib = load()
+    n = a.shape[0]
+    buf = np.asfortranarray(a, dtype=np.float64).copy(order="F")
+    w = np.empty(n)
+    st = lib.plfem_debug_symeig(n, buf.ctypes.data_as(p_f64), _ptr(w, p_f64))
+    if st != 0:
+        raise PlfemError(st, "symeig")
+    return w, buf

@@ -1,0 +1,66 @@
+"""Build libplfem.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+CSRC = HERE / "csrc"
+LIB = HERE / "libplfem.so"
+OBJ = HERE / "build"
+
+SOURCES = ["symbolic.cpp", "symeig.cpp", "assembly.cu", "factor.cu", "eigen.cu", "api.cu"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "--expt-relaxed-constexpr"]
+# assembly.cu: products and sums must round like the NumPy oracle, never contract into FMAs
+PER_FILE = {"assembly.cu": ["-fmad=false"]}
+
+
+def nvcc() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found: the CUDA extension cannot be built")
+    return exe
+
+
+def needs_build() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    deps = list(CSRC.glob("*")) + [HERE.parent / "include" / "plfem.h", Path(__file__)]
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return LIB
+    OBJ.mkdir(exist_ok=True)
+    cc = nvcc()
+
+    def compile_one(src: str) -> Path:
+        out = OBJ / (src + ".o")
+        cmd = [cc, *ARCH, *COMMON, *PER_FILE.get(src, []), "-x", "cu", "-c", str(CSRC / src), "-o", str(out)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+        if verbose or r.stderr.strip():
+            sys.stderr.write(r.stderr)
+        return out
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    cmd = [cc, *ARCH, "-shared", "-o", str(LIB), *map(str, objs), "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

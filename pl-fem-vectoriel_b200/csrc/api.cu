@@ -1,0 +1,576 @@
+// C ABI entry points (include/plfem.h): context, problem, assembly/export, SpMV, modal solve.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+#include "common.h"
+
+using namespace plfem;
+
+// ---- device arena -------------------------------------------------------------------------------------
+namespace plfem {
+
+static size_t size_class(size_t bytes) {
+  size_t c = 512;
+  while (c < bytes) c <<= 1;
+  if (c > (size_t(1) << 26)) {  // above 64 MiB: round to 32 MiB multiples instead of doubling
+    const size_t g = size_t(1) << 25;
+    c = (bytes + g - 1) / g * g;
+  }
+  return c;
+}
+
+void* DeviceArena::alloc(size_t bytes) {
+  const size_t c = size_class(bytes);
+  auto it = free_.find(c);
+  void* p = nullptr;
+  if (it != free_.end()) {
+    p = it->second;
+    free_.erase(it);
+  } else {
+    cudaError_t e = cudaMalloc(&p, c);
+    if (e != cudaSuccess) {
+      // give cached blocks back and retry once
+      for (auto& kv : free_) { cudaFree(kv.second); reserved_ -= kv.first; }
+      free_.clear();
+      e = cudaMalloc(&p, c);
+      if (e != cudaSuccess) throw CudaError(std::string("cudaMalloc of ") + std::to_string(c) + " bytes failed: " + cudaGetErrorString(e));
+    }
+    reserved_ += c;
+  }
+  live_[p] = c;
+  return p;
+}
+
+void DeviceArena::release(void* p) {
+  auto it = live_.find(p);
+  if (it == live_.end()) return;
+  free_.emplace(it->second, p);
+  live_.erase(it);
+}
+
+void DeviceArena::destroy() {
+  for (auto& kv : free_) cudaFree(kv.second);
+  for (auto& kv : live_) cudaFree(kv.first);
+  free_.clear(); live_.clear(); reserved_ = 0;
+}
+
+}  // namespace plfem
+
+void* plfem_ctx::pin(size_t bytes) {
+  if (bytes > pinned_bytes) {
+    if (pinned) cudaFreeHost(pinned);
+    pinned = nullptr;
+    size_t nb = std::max<size_t>(bytes, 1 << 20);
+    PLFEM_CUDA(cudaMallocHost(&pinned, nb));
+    pinned_bytes = nb;
+  }
+  return pinned;
+}
+
+// ---- problem ------------------------------------------------------------------------------------------
+struct plfem_problem {
+  plfem_ctx* ctx = nullptr;
+  DofTables dof;
+  std::vector<double> p_host;                 // (2,V)
+  DevBuf<double> d_p;                          // (2,V)
+  DevBuf<int32_t> d_edofs, d_n2e_ptr, d_n2e;
+  DevBuf<double> d_elem, d_cores, d_epsq;
+  // full N x N pattern (export path)
+  Pattern full; DevPattern dfull; bool full_ready = false;
+  DevBuf<double> d_full_vals; DevBuf<uint32_t> d_full_flags;
+  std::vector<double> h_full_vals; std::vector<uint32_t> h_full_flags; bool assembled = false;
+  plfem_material last_mat{};
+  // interior solve path
+  Pattern adj;  bool adj_ready = false;        // interior nodes, interior-index numbering (for dissection)
+  FrontPlan plan; bool plan_ready = false; SymbolicOptions plan_opt;
+  Pattern perm_pat; DevPattern dperm;
+  DevPlan dplan;
+  DevBuf<double> d_vals;                       // NV_SOLVE x nnz
+  DevBuf<int32_t> d_perm;                      // new id -> interior index
+  DevBuf<uint8_t> d_in_core;
+};
+
+namespace {
+
+template <class F>
+int guarded(plfem_ctx* ctx, F&& fn) {
+  try {
+    fn();
+    return PLFEM_OK;
+  } catch (const StatusError& e) {
+    if (ctx) ctx->err = e.what();
+    return e.status;
+  } catch (const CudaError& e) {
+    if (ctx) ctx->err = e.what();
+    return PLFEM_ERR_CUDA;
+  } catch (const std::bad_alloc&) {
+    if (ctx) ctx->err = "host allocation failed";
+    return PLFEM_ERR_INTERNAL;
+  } catch (const std::exception& e) {
+    if (ctx) ctx->err = e.what();
+    return PLFEM_ERR_INTERNAL;
+  }
+}
+
+void need(bool ok, const char* msg) {
+  if (!ok) throw StatusError(PLFEM_ERR_INVALID, msg);
+}
+
+double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+void upload_material(plfem_problem* pb, const plfem_material* mat) {
+  plfem_ctx* ctx = pb->ctx;
+  need(mat != nullptr, "material is NULL");
+  need(mat->n_cores >= 0, "n_cores < 0");
+  need(mat->eps_at_quad || mat->n_cores == 0 || (mat->cores_xy && mat->cores_r), "core arrays are NULL");
+  std::vector<double> cores(3 * (size_t)std::max(mat->n_cores, 1), 0.0);
+  for (int c = 0; c < mat->n_cores && mat->cores_xy; ++c) {
+    cores[3 * c] = mat->cores_xy[2 * c]; cores[3 * c + 1] = mat->cores_xy[2 * c + 1]; cores[3 * c + 2] = mat->cores_r[c];
+  }
+  pb->d_cores.upload(ctx, cores);
+  const double* epsq = nullptr;
+  if (mat->eps_at_quad) { pb->d_epsq.upload(ctx, mat->eps_at_quad, (size_t)6 * pb->dof.T); epsq = pb->d_epsq.p; }
+  pb->d_elem.alloc(ctx, (size_t)12 * pb->dof.T);
+  launch_element_setup(ctx, pb->d_p.p, pb->d_edofs.p, pb->dof.V, pb->dof.T, *mat, pb->d_cores.p, epsq, pb->d_elem.p);
+}
+
+void upload_pattern(plfem_ctx* ctx, const Pattern& P, DevPattern& D) {
+  D.n = P.n; D.nnz = (int64_t)P.col.size();
+  D.rowptr.upload(ctx, P.rowptr); D.col.upload(ctx, P.col); D.old_of_new.upload(ctx, P.old_of_new);
+  D.rowidx.alloc(ctx, std::max<size_t>(P.col.size(), 1));
+  launch_expand_rows(ctx, D);
+}
+
+void ensure_full_pattern(plfem_problem* pb) {
+  if (pb->full_ready) return;
+  std::vector<int32_t> ident(pb->dof.N);
+  for (int64_t i = 0; i < pb->dof.N; ++i) ident[i] = (int32_t)i;
+  build_pattern(pb->dof, ident, (int32_t)pb->dof.N, pb->full);
+  upload_pattern(pb->ctx, pb->full, pb->dfull);
+  pb->full_ready = true;
+}
+
+void ensure_adj(plfem_problem* pb) {
+  if (pb->adj_ready) return;
+  std::vector<int32_t> nid(pb->dof.N, -1);
+  for (size_t i = 0; i < pb->dof.interior.size(); ++i) nid[pb->dof.interior[i]] = (int32_t)i;
+  build_pattern(pb->dof, nid, (int32_t)pb->dof.interior.size(), pb->adj);
+  pb->adj_ready = true;
+}
+
+// returns true when a new plan was built
+bool ensure_plan(plfem_problem* pb, int leaf_nodes, int max_sn_nodes, bool reuse) {
+  SymbolicOptions opt;
+  if (leaf_nodes > 0) opt.leaf_nodes = leaf_nodes;
+  if (max_sn_nodes > 0) opt.max_sn_nodes = max_sn_nodes;
+  need(opt.max_sn_nodes <= 64 && opt.leaf_nodes <= 64, "leaf_nodes and max_sn_nodes must be <= 64");
+  if (pb->plan_ready && reuse && opt.leaf_nodes == pb->plan_opt.leaf_nodes && opt.max_sn_nodes == pb->plan_opt.max_sn_nodes) return false;
+  ensure_adj(pb);
+  const int32_t n = pb->adj.n;
+  std::vector<double> x(n), y(n);
+  for (int32_t i = 0; i < n; ++i) { x[i] = pb->dof.doflocs[pb->dof.interior[i]]; y[i] = pb->dof.doflocs[pb->dof.N + pb->dof.interior[i]]; }
+  build_front_plan(pb->adj, x.data(), y.data(), opt, pb->plan);
+  pb->plan_opt = opt;
+  pb->plan_ready = true;
+  pb->dperm.n = 0;   // device copies are stale
+  return true;
+}
+
+}  // namespace
+
+// ---- C ABI --------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* plfem_version(void) { return "plfem 0.1 sm_100a"; }
+
+int plfem_ctx_create(int device, plfem_ctx** out) {
+  if (!out) return PLFEM_ERR_INVALID;
+  *out = nullptr;
+  auto* ctx = new plfem_ctx();
+  int st = guarded(ctx, [&] {
+    int ndev = 0;
+    PLFEM_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) throw StatusError(PLFEM_ERR_CUDA, "no such CUDA device: " + std::to_string(device));
+    PLFEM_CUDA(cudaSetDevice(device));
+    ctx->device = device;
+    PLFEM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (auto& e : ctx->ev) PLFEM_CUDA(cudaEventCreate(&e));
+  });
+  if (st != PLFEM_OK) {
+    // keep the context alive so the caller can read the message
+    static thread_local std::string last;
+    last = ctx->err;
+    fprintf(stderr, "plfem_ctx_create: %s\n", last.c_str());
+    delete ctx;
+    return st;
+  }
+  *out = ctx;
+  return PLFEM_OK;
+}
+
+void plfem_ctx_destroy(plfem_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  ctx->arena.destroy();
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* plfem_last_error(const plfem_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int plfem_problem_create(plfem_ctx* ctx, const double* p, const int64_t* t, int64_t V, int64_t T, plfem_problem** out) {
+  if (!out) return PLFEM_ERR_INVALID;
+  *out = nullptr;
+  std::unique_ptr<plfem_problem> pb(new plfem_problem());
+  pb->ctx = ctx;
+  int st = guarded(ctx, [&] {
+    need(p && t, "p or t is NULL");
+    need(V >= 3 && T >= 1, "need at least one triangle");
+    need(V + 3 * T < (int64_t(1) << 31), "mesh too large for 32-bit DOF ids");
+    build_dof_tables(p, t, V, T, pb->dof);
+    pb->p_host.assign(p, p + 2 * V);
+    if (!ctx) return;   // host-only problem: DOF tables and front plan only (tests of the host logic)
+    PLFEM_CUDA(cudaSetDevice(ctx->device));
+    pb->d_p.upload(ctx, pb->p_host);
+    pb->d_edofs.upload(ctx, pb->dof.edofs);
+    pb->d_n2e_ptr.upload(ctx, pb->dof.n2e_ptr);
+    pb->d_n2e.upload(ctx, pb->dof.n2e);
+  });
+  if (st != PLFEM_OK) return st;
+  *out = pb.release();
+  return PLFEM_OK;
+}
+
+void plfem_problem_destroy(plfem_problem* pb) {
+  if (!pb) return;
+  if (pb->ctx) cudaSetDevice(pb->ctx->device);
+  delete pb;
+}
+
+int plfem_problem_info(const plfem_problem* pb, plfem_mesh_info* info) {
+  if (!pb || !info) return PLFEM_ERR_INVALID;
+  info->V = pb->dof.V; info->T = pb->dof.T; info->E = pb->dof.E; info->N = pb->dof.N;
+  info->n_boundary = (int64_t)pb->dof.boundary.size();
+  info->n_interior = (int64_t)pb->dof.interior.size();
+  info->nnz_scalar = pb->full_ready ? (int64_t)pb->full.col.size() : -1;
+  info->n_degenerate = pb->dof.n_degenerate;
+  return PLFEM_OK;
+}
+
+int plfem_problem_dofs(const plfem_problem* pb, int64_t* element_dofs, double* doflocs, int64_t* boundary, int64_t* interior) {
+  if (!pb) return PLFEM_ERR_INVALID;
+  const DofTables& d = pb->dof;
+  if (element_dofs)
+    for (int64_t e = 0; e < d.T; ++e)
+      for (int k = 0; k < 6; ++k) element_dofs[k * d.T + e] = d.edofs[6 * e + k];
+  if (doflocs) std::copy(d.doflocs.begin(), d.doflocs.end(), doflocs);
+  if (boundary) std::copy(d.boundary.begin(), d.boundary.end(), boundary);
+  if (interior) std::copy(d.interior.begin(), d.interior.end(), interior);
+  return PLFEM_OK;
+}
+
+int plfem_quad_points(const plfem_problem* pb, double* out_xy) {
+  if (!pb || !out_xy) return PLFEM_ERR_INVALID;
+  const DofTables& d = pb->dof;
+  const RefTables& rt = ref_tables();
+  const double* px = pb->p_host.data();
+  const double* py = px + d.V;
+  for (int64_t e = 0; e < d.T; ++e) {
+    const int32_t v0 = d.edofs[6 * e], v1 = d.edofs[6 * e + 1], v2 = d.edofs[6 * e + 2];
+    const double a00 = px[v1] - px[v0], a01 = px[v2] - px[v0], a10 = py[v1] - py[v0], a11 = py[v2] - py[v0];
+    for (int q = 0; q < 6; ++q) {
+      volatile double t0 = a00 * rt.qx[q], t1 = a01 * rt.qy[q]; volatile double sx = t0 + t1;
+      volatile double t2 = a10 * rt.qx[q], t3 = a11 * rt.qy[q]; volatile double sy = t2 + t3;
+      out_xy[e * 6 + q] = sx + px[v0];
+      out_xy[(d.T + e) * 6 + q] = sy + py[v0];
+    }
+  }
+  return PLFEM_OK;
+}
+
+int plfem_assemble(plfem_problem* pb, const plfem_material* mat) {
+  if (!pb || !pb->ctx) return PLFEM_ERR_INVALID;
+  plfem_ctx* ctx = pb->ctx;
+  return guarded(ctx, [&] {
+    PLFEM_CUDA(cudaSetDevice(ctx->device));
+    if (pb->dof.n_degenerate > 0)
+      throw StatusError(PLFEM_ERR_DEGENERATE, std::to_string(pb->dof.n_degenerate) + " zero-area triangle(s): the affine map is singular");
+    ensure_full_pattern(pb);
+    upload_material(pb, mat);
+    const int64_t nnz = pb->dfull.nnz;
+    pb->d_full_vals.alloc(ctx, (size_t)NV_EXPORT * nnz);
+    pb->d_full_flags.alloc(ctx, (size_t)nnz);
+    launch_assemble(ctx, pb->dfull, pb->d_n2e_ptr.p, pb->d_n2e.p, pb->d_edofs.p, pb->d_elem.p, mat->k0 * mat->k0,
+                    mat->alpha_p, true, pb->d_full_vals.p, pb->d_full_flags.p);
+    pb->h_full_vals.resize((size_t)NV_EXPORT * nnz);
+    pb->h_full_flags.resize((size_t)nnz);
+    pb->d_full_vals.download(pb->h_full_vals.data(), pb->h_full_vals.size());
+    pb->d_full_flags.download(pb->h_full_flags.data(), pb->h_full_flags.size());
+    PLFEM_CUDA(cudaStreamSynchronize(ctx->stream));
+    pb->last_mat = *mat;
+    pb->assembled = true;
+  });
+}
+
+int plfem_export_csr(plfem_problem* pb, int which, int64_t* rows_out, int64_t* nnz_out, int64_t* indptr, int64_t* indices,
+                     double* data) {
+  if (!pb) return PLFEM_ERR_INVALID;
+  plfem_ctx* ctx = pb->ctx;
+  return guarded(ctx, [&] {
+    if (!pb->assembled) throw StatusError(PLFEM_ERR_NOT_READY, "plfem_export_csr called before plfem_assemble");
+    const Pattern& P = pb->full;
+    const int64_t N = pb->dof.N, nnz = (int64_t)P.col.size();
+    const double* v = pb->h_full_vals.data();
+    const uint32_t* fl = pb->h_full_flags.data();
+    const double k0sq = pb->last_mat.k0 * pb->last_mat.k0, al = pb->last_mat.alpha_p;
+    auto val = [&](int k, int64_t z) { return v[(int64_t)k * nnz + z]; };
+    // scalar value + keep rule for block (bi, bj) of A, or for a scalar matrix
+    auto a_block = [&](int bi, int bj, int64_t z, double& out) {
+      volatile double t;
+      if (bi == 0 && bj == 0) { t = val(X_KXX, z) + al * val(X_DXX, z); t = t - k0sq * val(X_M, z); }
+      else if (bi == 1 && bj == 1) { t = val(X_KYY, z) + al * val(X_DYY, z); t = t - k0sq * val(X_M, z); }
+      else if (bi == 0) t = val(X_KXY, z) + al * val(X_DXY, z);
+      else t = val(X_KYX, z) + al * val(X_DYX, z);
+      out = t;
+      return out != 0.0;   // sparse +/- drop exact zeros, NaN is kept
+    };
+    const bool interior_only = (which == PLFEM_MAT_A_INT || which == PLFEM_MAT_B_INT);
+    const bool is_a = (which == PLFEM_MAT_A || which == PLFEM_MAT_A_INT);
+    const bool is_b = (which == PLFEM_MAT_B || which == PLFEM_MAT_B_INT);
+    std::vector<int32_t> imap;  // scalar node -> position among kept nodes
+    int64_t nk = N;
+    if (interior_only) {
+      imap.assign(N, -1);
+      for (size_t i = 0; i < pb->dof.interior.size(); ++i) imap[pb->dof.interior[i]] = (int32_t)i;
+      nk = (int64_t)pb->dof.interior.size();
+    }
+    auto kept = [&](int64_t node) { return interior_only ? imap[node] : (int32_t)node; };
+    int scalar_k = -1;
+    switch (which) {
+      case PLFEM_MAT_DXX: scalar_k = X_DXX; break; case PLFEM_MAT_DYY: scalar_k = X_DYY; break;
+      case PLFEM_MAT_DXY: scalar_k = X_DXY; break; case PLFEM_MAT_MINV: scalar_k = X_MINV; break;
+      case PLFEM_MAT_KXX: scalar_k = X_KXX; break; case PLFEM_MAT_KYY: scalar_k = X_KYY; break;
+      case PLFEM_MAT_KXY: scalar_k = X_KXY; break; case PLFEM_MAT_KYX: scalar_k = X_KYX; break;
+      case PLFEM_MAT_M: scalar_k = X_M; break;
+      default: break;
+    }
+    if (!is_a && !is_b && scalar_k < 0) throw StatusError(PLFEM_ERR_INVALID, "unknown matrix id");
+    const int nblk = (is_a || is_b) ? 2 : 1;
+    const int64_t rows = nblk * nk;
+    if (rows_out) *rows_out = rows;
+    int64_t count = 0;
+    const bool fill = (indptr && indices && data);
+    if (fill) indptr[0] = 0;
+    for (int bi = 0; bi < nblk; ++bi)
+      for (int64_t r = 0; r < N; ++r) {
+        const int32_t kr = kept(r);
+        if (kr < 0) continue;
+        for (int bj = 0; bj < nblk; ++bj) {
+          if (is_b && bi != bj) continue;
+          for (int32_t z = P.rowptr[r]; z < P.rowptr[r + 1]; ++z) {
+            const int32_t kc = kept(P.col[z]);
+            if (kc < 0) continue;
+            double x;
+            bool keep;
+            if (is_a) keep = a_block(bi, bj, z, x);
+            else { const int k = is_b ? X_MINV : scalar_k; x = val(k, z); keep = (fl[z] >> k) & 1u; }
+            if (!keep) continue;
+            if (fill) { indices[count] = bj * nk + kc; data[count] = x; }
+            ++count;
+          }
+        }
+        if (fill) indptr[bi * nk + kr + 1] = count;
+      }
+    if (nnz_out) *nnz_out = count;
+  });
+}
+
+int plfem_spmv_csr(plfem_ctx* ctx, int64_t rows, int64_t nnz, const int64_t* indptr, const int64_t* indices,
+                   const double* data, const double* x, double* y, int repeat, float* ms) {
+  if (!ctx) return PLFEM_ERR_INVALID;
+  return guarded(ctx, [&] {
+    need(indptr && indices && data && x && y, "NULL array");
+    need(rows > 0 && nnz >= 0 && nnz < (int64_t(1) << 31), "bad sizes");
+    PLFEM_CUDA(cudaSetDevice(ctx->device));
+    std::vector<int32_t> rp(rows + 1), ci(nnz);
+    int64_t maxcol = rows;
+    for (int64_t i = 0; i <= rows; ++i) rp[i] = (int32_t)indptr[i];
+    for (int64_t i = 0; i < nnz; ++i) { need(indices[i] >= 0, "negative column"); ci[i] = (int32_t)indices[i]; maxcol = std::max(maxcol, indices[i] + 1); }
+    need(maxcol == rows, "plfem_spmv_csr expects a square matrix");
+    DevBuf<int32_t> d_rp, d_ci; DevBuf<double> d_v, d_x, d_y;
+    d_rp.upload(ctx, rp); d_ci.upload(ctx, ci); d_v.upload(ctx, data, nnz); d_x.upload(ctx, x, rows); d_y.alloc(ctx, rows);
+    const int reps = std::max(repeat, 1);
+    launch_spmv_csr(ctx, rows, d_rp.p, d_ci.p, d_v.p, d_x.p, d_y.p);  // warm-up
+    PLFEM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    for (int i = 0; i < reps; ++i) launch_spmv_csr(ctx, rows, d_rp.p, d_ci.p, d_v.p, d_x.p, d_y.p);
+    PLFEM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    d_y.download(y, rows);
+    PLFEM_CUDA(cudaStreamSynchronize(ctx->stream));
+    float t = 0;
+    PLFEM_CUDA(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]));
+    if (ms) *ms = t / reps;
+  });
+}
+
+int plfem_solve_modes(plfem_problem* pb, const plfem_material* mat, const plfem_solve_opts* o, double* eigvals, double* evecs,
+                      double* metrics, int32_t* core_dof_count, plfem_solve_stats* stats) {
+  if (!pb || !pb->ctx) return PLFEM_ERR_INVALID;
+  plfem_ctx* ctx = pb->ctx;
+  return guarded(ctx, [&] {
+    need(mat && o && eigvals && metrics, "NULL argument");
+    PLFEM_CUDA(cudaSetDevice(ctx->device));
+    if (pb->dof.n_degenerate > 0)
+      throw StatusError(PLFEM_ERR_DEGENERATE, std::to_string(pb->dof.n_degenerate) + " zero-area triangle(s): the affine map is singular");
+    const int64_t n = (int64_t)pb->dof.interior.size();
+    const int k = o->k;
+    need(k >= 1 && k < 2 * n, "k out of range");
+    int ncv = o->ncv > 0 ? o->ncv : std::max(2 * k + 1, 20);
+    ncv = (int)std::min<int64_t>(ncv, 2 * n);
+    need(ncv > k + 1, "ncv must exceed k + 1");
+    ctx->launches = 0;
+    const double t0 = now_ms();
+    cudaStream_t st = ctx->stream;
+
+    // -- symbolic (host) --------------------------------------------------------------------------
+    ensure_plan(pb, o->leaf_nodes, o->max_sn_nodes, o->reuse_symbolic != 0);
+    if (pb->dperm.n == 0) {
+      std::vector<int32_t> new_of_old(pb->dof.N, -1);
+      for (int32_t r = 0; r < pb->plan.n; ++r) new_of_old[pb->dof.interior[pb->plan.perm[r]]] = r;
+      build_pattern(pb->dof, new_of_old, pb->plan.n, pb->perm_pat);
+      upload_pattern(ctx, pb->perm_pat, pb->dperm);
+      build_dev_plan(ctx, pb->plan, pb->dplan);
+      pb->d_perm.upload(ctx, pb->plan.perm);
+    }
+    const double t1 = now_ms();
+
+    // -- assembly ---------------------------------------------------------------------------------
+    PLFEM_CUDA(cudaEventRecord(ctx->ev[0], st));
+    upload_material(pb, mat);
+    const int64_t nnz = pb->dperm.nnz;
+    pb->d_vals.alloc(ctx, (size_t)NV_SOLVE * nnz);
+    launch_assemble(ctx, pb->dperm, pb->d_n2e_ptr.p, pb->d_n2e.p, pb->d_edofs.p, pb->d_elem.p, mat->k0 * mat->k0,
+                    mat->alpha_p, false, pb->d_vals.p, nullptr);
+    // core mask of the permuted interior nodes (solver_fem.py:200-203)
+    {
+      std::vector<uint8_t> mask(n, 0);
+      const double* X = pb->dof.doflocs.data();
+      const double* Y = X + pb->dof.N;
+      int32_t cnt = 0;
+      for (int64_t r = 0; r < n; ++r) {
+        const int32_t node = pb->dof.interior[pb->plan.perm[r]];
+        bool in = false;
+        for (int c = 0; c < mat->n_cores && mat->cores_xy; ++c) {
+          volatile double dx = X[node] - mat->cores_xy[2 * c], dy = Y[node] - mat->cores_xy[2 * c + 1];
+          volatile double dx2 = dx * dx, dy2 = dy * dy, rr = mat->cores_r[c] * mat->cores_r[c];
+          volatile double d2 = dx2 + dy2;
+          if (d2 <= rr) in = true;
+        }
+        mask[r] = in; cnt += in;
+      }
+      if (core_dof_count) *core_dof_count = cnt;
+      pb->d_in_core.upload(ctx, mask);
+    }
+    PLFEM_CUDA(cudaEventRecord(ctx->ev[1], st));
+
+    // -- numeric factorisation of A - sigma B -----------------------------------------------------------
+    launch_front_load(ctx, pb->dperm, pb->dplan, pb->d_vals.p, o->sigma);
+    run_factorization(ctx, pb->dplan);
+    PLFEM_CUDA(cudaEventRecord(ctx->ev[2], st));
+    int32_t fstat[4] = {0, 0, 0, 0};
+    pb->dplan.status.download(fstat, 4);
+    PLFEM_CUDA(cudaStreamSynchronize(st));
+    if (fstat[0]) throw StatusError(PLFEM_ERR_SINGULAR, "a pivot block of A - sigma*B is exactly singular or non-finite");
+
+    // -- eigensolver ----------------------------------------------------------------------------------
+    DevBuf<double> d_v0;
+    const double* v0p = nullptr;
+    if (o->v0) {
+      std::vector<double> v0(2 * n);
+      for (int64_t r = 0; r < n; ++r) { const int32_t ip = pb->plan.perm[r]; v0[2 * r] = o->v0[ip]; v0[2 * r + 1] = o->v0[n + ip]; }
+      d_v0.upload(ctx, v0);
+      v0p = d_v0.p;
+    }
+    DevBuf<double> X;
+    std::vector<double> lambda;
+    EigenResult er;
+    run_eigensolver(ctx, pb->dperm, pb->dplan, pb->d_vals.p, o->sigma, k, ncv, o->tol > 0 ? o->tol : 1e-7,
+                    o->maxiter > 0 ? o->maxiter : 12000, o->refine == 0 ? 1 : std::max(o->refine, 0), v0p, X, lambda, er);
+    PLFEM_CUDA(cudaEventRecord(ctx->ev[3], st));
+
+    // -- per-mode reductions + eigenvectors in reference ordering -------------------------------------------
+    DevBuf<double> d_ev, d_met, d_res;
+    if (evecs) d_ev.alloc(ctx, (size_t)k * 2 * n);
+    d_met.alloc(ctx, (size_t)k * PLFEM_NMETRICS); d_res.alloc(ctx, (size_t)2 * k);
+    run_mode_metrics(ctx, pb->dperm, pb->d_vals.p, pb->d_perm.p, pb->d_in_core.p, X.p, lambda, k, evecs ? d_ev.p : nullptr,
+                     d_met.p, d_res.p);
+    std::vector<double> res(2 * k);
+    d_met.download(metrics, (size_t)k * PLFEM_NMETRICS);
+    d_res.download(res.data(), res.size());
+    if (evecs) d_ev.download(evecs, (size_t)k * 2 * n);
+    PLFEM_CUDA(cudaEventRecord(ctx->ev[4], st));
+    PLFEM_CUDA(cudaStreamSynchronize(st));
+    std::copy(lambda.begin(), lambda.end(), eigvals);
+    const double t2 = now_ms();
+
+    if (stats) {
+      std::memset(stats, 0, sizeof(*stats));
+      stats->nconv = er.nconv; stats->n_op = er.n_op; stats->n_restart = er.n_restart;
+      stats->n_fronts = pb->plan.nfronts; stats->n_levels = pb->plan.nlevels; stats->max_front_nodes = pb->plan.max_front;
+      stats->factor_entries = pb->plan.factor_entries; stats->front_pool_doubles = pb->plan.foff[pb->plan.nfronts];
+      stats->factor_flops = pb->plan.factor_flops;
+      double mr = 0.0;
+      for (int i = 0; i < k; ++i) mr = std::max(mr, res[2 * i] / (std::fabs(lambda[i]) * res[2 * i + 1] + 1e-300));
+      stats->max_residual = mr;
+      stats->ms_symbolic = (float)(t1 - t0);
+      cudaEventElapsedTime(&stats->ms_assemble, ctx->ev[0], ctx->ev[1]);
+      cudaEventElapsedTime(&stats->ms_factor, ctx->ev[1], ctx->ev[2]);
+      cudaEventElapsedTime(&stats->ms_lanczos, ctx->ev[2], ctx->ev[3]);
+      cudaEventElapsedTime(&stats->ms_metrics, ctx->ev[3], ctx->ev[4]);
+      stats->ms_total = (float)(t2 - t0);
+      stats->kernel_launches = ctx->launches;
+    }
+  });
+}
+
+int plfem_plan_sizes(plfem_problem* pb, int32_t leaf_nodes, int32_t max_sn_nodes, int64_t sizes[6]) {
+  if (!pb || !sizes) return PLFEM_ERR_INVALID;
+  return guarded(pb->ctx, [&] {
+    ensure_plan(pb, leaf_nodes, max_sn_nodes, false);
+    const FrontPlan& P = pb->plan;
+    sizes[0] = P.n; sizes[1] = P.nfronts; sizes[2] = P.nlevels; sizes[3] = (int64_t)P.strct.size();
+    sizes[4] = (int64_t)P.cmap.size(); sizes[5] = (int64_t)P.child.size();
+  });
+}
+
+int plfem_plan_export(plfem_problem* pb, int32_t* perm, int32_t* first, int32_t* s, int32_t* parent, int32_t* level,
+                      int32_t* sptr, int32_t* strct, int32_t* cmap_ptr, int32_t* cmap, int64_t* foff) {
+  if (!pb) return PLFEM_ERR_INVALID;
+  return guarded(pb->ctx, [&] {
+    if (!pb->plan_ready) throw StatusError(PLFEM_ERR_NOT_READY, "call plfem_plan_sizes first");
+    const FrontPlan& P = pb->plan;
+    auto cp = [](const auto& v, auto* dst) { if (dst) std::copy(v.begin(), v.end(), dst); };
+    cp(P.perm, perm); cp(P.first, first); cp(P.s, s); cp(P.parent, parent); cp(P.level, level); cp(P.sptr, sptr);
+    cp(P.strct, strct); cp(P.cmap_ptr, cmap_ptr); cp(P.cmap, cmap); cp(P.foff, foff);
+  });
+}
+
+// test hook: dense symmetric eigensolver used at Lanczos restarts
+int plfem_debug_symeig(int32_t n, double* a, double* w) {
+  if (!a || !w || n < 1) return PLFEM_ERR_INVALID;
+  std::vector<double> A(a, a + (size_t)n * n), W;
+  symmetric_eigen(n, A, W);
+  std::copy(A.begin(), A.end(), a);
+  std::copy(W.begin(), W.end(), w);
+  return PLFEM_OK;
+}
+
+}  // extern "C"

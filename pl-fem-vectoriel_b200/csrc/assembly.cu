@@ -1,0 +1,281 @@
+// K1/K2: element geometry + fused gather assembly of the scalar P2 matrices, and the CSR SpMV.
+//
+// Replaces `asm(form, basis)` x 9 and the sparse block adds of solver_fem.py:131-167.
+//
+// Design (B200): the classic "element kernel -> COO -> sort/scatter" pipeline writes and re-reads
+// 36*T*9 triplets (2.3 KB per element) that are not algorithmic traffic.  Here one thread owns one
+// structural non-zero (row node r, column node c).  It walks the elements around r in ascending
+// element id (fixed summation order = deterministic, no atomics), finds c in each of them, and
+// integrates the 10 scalar forms on the fly from an 96-byte per-element record (inverse Jacobian,
+// |det J| and 1/eps at the 6 quadrature points) that lives in L1/L2.  DRAM traffic is the mesh in and
+// each assembled value out, once.
+//
+// Arithmetic follows the oracle operation for operation (no FMA contraction: every product and
+// sum below is an explicit round-to-nearest intrinsic), so an element-level value is exactly zero
+// here iff it is exactly zero there — that decides the CSR structure scikit-fem/SciPy produce.
+#include "common.h"
+
+namespace plfem {
+
+namespace {
+
+__host__ __device__ inline double mul(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dmul_rn(a, b);
+#else
+  volatile double r = a * b; return r;
+#endif
+}
+__host__ __device__ inline double add(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dadd_rn(a, b);
+#else
+  volatile double r = a + b; return r;
+#endif
+}
+
+RefTables make_tables() {
+  // 6-point degree-4 rule on the reference triangle and the P2 shape functions evaluated there,
+  // with the same expression order as the oracle's NumPy code.
+  RefTables t;
+  const double a = 0.445948490915965, b = 0.091576213509771;
+  const double wa = 0.111690794839005, wb = 0.054975871827661;
+  const double a2 = 1 - 2 * a, b2 = 1 - 2 * b;
+  const double X[6] = {a, a, a2, b, b, b2};
+  const double Y[6] = {a, a2, a, b, b2, b};
+  const double W[6] = {wa, wa, wa, wb, wb, wb};
+  for (int q = 0; q < 6; ++q) {
+    const double x = X[q], y = Y[q];
+    t.qx[q] = x; t.qy[q] = y; t.w[q] = W[q];
+    const double xx = mul(x, x), yy = mul(y, y), xy4 = mul(mul(4.0, x), y);
+    // phi
+    t.phi[0 * 6 + q] = add(add(add(add(add(1.0, -mul(3.0, x)), -mul(3.0, y)), mul(2.0, xx)), xy4), mul(2.0, yy));
+    t.phi[1 * 6 + q] = add(mul(2.0, xx), -x);
+    t.phi[2 * 6 + q] = add(mul(2.0, yy), -y);
+    t.phi[3 * 6 + q] = add(add(mul(4.0, x), -mul(4.0, xx)), -xy4);
+    t.phi[4 * 6 + q] = xy4;
+    t.phi[5 * 6 + q] = add(add(mul(4.0, y), -xy4), -mul(4.0, yy));
+    // d/dx
+    t.dx[0 * 6 + q] = add(add(-3.0, mul(4.0, x)), mul(4.0, y));
+    t.dx[1 * 6 + q] = add(mul(4.0, x), -1.0);
+    t.dx[2 * 6 + q] = mul(0.0, x);
+    t.dx[3 * 6 + q] = add(add(4.0, -mul(8.0, x)), -mul(4.0, y));
+    t.dx[4 * 6 + q] = mul(4.0, y);
+    t.dx[5 * 6 + q] = mul(-4.0, y);
+    // d/dy
+    t.dy[0 * 6 + q] = add(add(-3.0, mul(4.0, x)), mul(4.0, y));
+    t.dy[1 * 6 + q] = mul(0.0, x);
+    t.dy[2 * 6 + q] = add(mul(4.0, y), -1.0);
+    t.dy[3 * 6 + q] = mul(-4.0, x);
+    t.dy[4 * 6 + q] = mul(4.0, x);
+    t.dy[5 * 6 + q] = add(add(4.0, -mul(4.0, x)), -mul(8.0, y));
+  }
+  return t;
+}
+
+__constant__ RefTables c_tab;
+bool g_tab_uploaded[64] = {};
+
+void ensure_tables(plfem_ctx* ctx) {
+  if (ctx->device < 64 && g_tab_uploaded[ctx->device]) return;
+  const RefTables& t = ref_tables();
+  PLFEM_CUDA(cudaMemcpyToSymbolAsync(c_tab, &t, sizeof(RefTables), 0, cudaMemcpyHostToDevice, ctx->stream));
+  if (ctx->device < 64) g_tab_uploaded[ctx->device] = true;
+}
+
+constexpr int ELEM_STRIDE = 12;  // doubles per element record: i00 i10 i01 i11 |det| w[6] pad
+
+// ---- K1a: one thread per element -------------------------------------------------------------------
+__global__ void element_setup_kernel(const double* __restrict__ px, const double* __restrict__ py,
+                                     const int32_t* __restrict__ edofs, int64_t T, const double* __restrict__ cores,
+                                     int ncores, double eps_core, double eps_clad,
+                                     const double* __restrict__ eps_at_quad, double* __restrict__ elem) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= T) return;
+  const int32_t v0 = edofs[6 * e], v1 = edofs[6 * e + 1], v2 = edofs[6 * e + 2];
+  const double x0 = px[v0], y0 = py[v0];
+  const double a00 = add(px[v1], -x0), a01 = add(px[v2], -x0);
+  const double a10 = add(py[v1], -y0), a11 = add(py[v2], -y0);
+  const double det = add(mul(a00, a11), -mul(a01, a10));
+  double* r = elem + e * ELEM_STRIDE;
+  r[0] = __ddiv_rn(a11, det);    // invA[0][0]
+  r[1] = __ddiv_rn(-a10, det);   // invA[1][0]
+  r[2] = __ddiv_rn(-a01, det);   // invA[0][1]
+  r[3] = __ddiv_rn(a00, det);    // invA[1][1]
+  r[4] = fabs(det);
+  for (int q = 0; q < 6; ++q) {
+    double eps;
+    if (eps_at_quad) {
+      eps = eps_at_quad[e * 6 + q];
+    } else {
+      const double xq = add(add(mul(a00, c_tab.qx[q]), mul(a01, c_tab.qy[q])), x0);
+      const double yq = add(add(mul(a10, c_tab.qx[q]), mul(a11, c_tab.qy[q])), y0);
+      eps = eps_clad;
+      for (int c = 0; c < ncores; ++c) {
+        const double ddx = add(xq, -cores[3 * c]), ddy = add(yq, -cores[3 * c + 1]), rr = cores[3 * c + 2];
+        if (add(mul(ddx, ddx), mul(ddy, ddy)) <= mul(rr, rr)) eps = eps_core;
+      }
+    }
+    r[5 + q] = __ddiv_rn(1.0, eps);
+  }
+  r[11] = 0.0;
+}
+
+__global__ void expand_rows_kernel(const int32_t* __restrict__ rowptr, int32_t n, int32_t* __restrict__ rowidx) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  for (int32_t z = rowptr[r]; z < rowptr[r + 1]; ++z) rowidx[z] = r;
+}
+
+// ---- K1b/K2 fused: one thread per structural non-zero ---------------------------------------------------
+template <bool EXPORT>
+__global__ void __launch_bounds__(128)
+assemble_kernel(int64_t nnz, const int32_t* __restrict__ rowidx, const int32_t* __restrict__ col,
+                const int32_t* __restrict__ old_of_new, const int32_t* __restrict__ n2e_ptr,
+                const int32_t* __restrict__ n2e, const int32_t* __restrict__ edofs, const double* __restrict__ elem,
+                double k0sq, double alpha, double* __restrict__ vals, uint32_t* __restrict__ flags) {
+  __shared__ double s_phi[36], s_dx[36], s_dy[36], s_w[6];
+  for (int i = threadIdx.x; i < 36; i += blockDim.x) { s_phi[i] = c_tab.phi[i]; s_dx[i] = c_tab.dx[i]; s_dy[i] = c_tab.dy[i]; }
+  if (threadIdx.x < 6) s_w[threadIdx.x] = c_tab.w[threadIdx.x];
+  __syncthreads();
+  const int64_t z = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (z >= nnz) return;
+  const int32_t orow = old_of_new[rowidx[z]];
+  const int32_t ocol = old_of_new[col[z]];
+
+  double g[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) g[k] = 0.0;
+  uint32_t fl = 0;
+
+  for (int32_t q = n2e_ptr[orow]; q < n2e_ptr[orow + 1]; ++q) {
+    const int32_t e = n2e[q];
+    const int32_t* ed = edofs + 6 * (int64_t)e;
+    int li = -1, lj = -1;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int32_t d = ed[k];
+      if (d == orow) li = k;
+      if (d == ocol) lj = k;
+    }
+    if (lj < 0) continue;
+    const double* r = elem + (int64_t)e * ELEM_STRIDE;
+    const double i00 = r[0], i10 = r[1], i01 = r[2], i11 = r[3], adet = r[4];
+    double l[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) l[k] = 0.0;
+#pragma unroll
+    for (int qp = 0; qp < 6; ++qp) {
+      const double w = r[5 + qp];
+      const double dxq = mul(adet, s_w[qp]);
+      // test function v = row node (i), trial function u = column node (j)
+      const double gxi = add(mul(i00, s_dx[li * 6 + qp]), mul(i10, s_dy[li * 6 + qp]));
+      const double gyi = add(mul(i01, s_dx[li * 6 + qp]), mul(i11, s_dy[li * 6 + qp]));
+      const double gxj = add(mul(i00, s_dx[lj * 6 + qp]), mul(i10, s_dy[lj * 6 + qp]));
+      const double gyj = add(mul(i01, s_dx[lj * 6 + qp]), mul(i11, s_dy[lj * 6 + qp]));
+      const double pi = s_phi[li * 6 + qp], pj = s_phi[lj * 6 + qp];
+      l[X_KXX] = add(l[X_KXX], mul(mul(mul(w, gyj), gyi), dxq));
+      l[X_KYY] = add(l[X_KYY], mul(mul(mul(w, gxj), gxi), dxq));
+      l[X_KXY] = add(l[X_KXY], mul(mul(mul(-w, gyj), gxi), dxq));
+      l[X_KYX] = add(l[X_KYX], mul(mul(mul(-w, gxj), gyi), dxq));
+      l[X_DXX] = add(l[X_DXX], mul(mul(gxj, gxi), dxq));
+      l[X_DYY] = add(l[X_DYY], mul(mul(gyj, gyi), dxq));
+      l[X_DXY] = add(l[X_DXY], mul(mul(gxj, gyi), dxq));
+      l[X_DYX] = add(l[X_DYX], mul(mul(gxi, gyj), dxq));   // Dxy(c, r): trial = row node, test = column node
+      l[X_M] = add(l[X_M], mul(mul(pj, pi), dxq));
+      l[X_MINV] = add(l[X_MINV], mul(mul(mul(w, pj), pi), dxq));
+    }
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      g[k] = add(g[k], l[k]);
+      if (EXPORT && l[k] != 0.0) fl |= (1u << k);   // NaN != 0 is true: a NaN entry is stored, as in SciPy
+    }
+  }
+
+  if (EXPORT) {
+#pragma unroll
+    for (int k = 0; k < 10; ++k) vals[(int64_t)k * nnz + z] = g[k];
+    flags[z] = fl;
+  } else {
+    const double km = mul(k0sq, g[X_M]);
+    vals[(int64_t)S_AXX * nnz + z] = add(add(g[X_KXX], mul(alpha, g[X_DXX])), -km);
+    vals[(int64_t)S_AXY * nnz + z] = add(g[X_KXY], mul(alpha, g[X_DXY]));
+    vals[(int64_t)S_AYX * nnz + z] = add(g[X_KYX], mul(alpha, g[X_DYX]));
+    vals[(int64_t)S_AYY * nnz + z] = add(add(g[X_KYY], mul(alpha, g[X_DYY])), -km);
+    vals[(int64_t)S_MINV * nnz + z] = g[X_MINV];
+    vals[(int64_t)S_DXX * nnz + z] = g[X_DXX];
+    vals[(int64_t)S_DXY * nnz + z] = g[X_DXY];
+    vals[(int64_t)S_DYY * nnz + z] = g[X_DYY];
+  }
+}
+
+// ---- K3: CSR SpMV, a group of TPR threads per row ------------------------------------------------------
+template <int TPR>
+__global__ void __launch_bounds__(256)
+spmv_csr_kernel(int64_t rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y) {
+  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t row = gid / TPR;
+  const int lane = (int)(gid % TPR);
+  double acc = 0.0;
+  if (row < rows) {
+    const int32_t b = rowptr[row], e = rowptr[row + 1];
+    for (int32_t k = b + lane; k < e; k += TPR) acc = fma(val[k], __ldg(x + col[k]), acc);
+  }
+#pragma unroll
+  for (int off = TPR / 2; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off, TPR);
+  if (row < rows && lane == 0) y[row] = acc;
+}
+
+}  // namespace
+
+const RefTables& ref_tables() {
+  static const RefTables t = make_tables();
+  return t;
+}
+
+void launch_element_setup(plfem_ctx* ctx, const double* d_p, const int32_t* d_edofs, int64_t V, int64_t T,
+                          const plfem_material& mat, const double* d_cores, const double* d_eps_at_quad,
+                          double* d_elem) {
+  ensure_tables(ctx);
+  const int bs = 128;
+  element_setup_kernel<<<(unsigned)((T + bs - 1) / bs), bs, 0, ctx->stream>>>(
+      d_p, d_p + V, d_edofs, T, d_cores, mat.n_cores, mat.eps_core, mat.eps_clad, d_eps_at_quad, d_elem);
+  PLFEM_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
+void launch_expand_rows(plfem_ctx* ctx, const DevPattern& pat) {
+  const int bs = 256;
+  expand_rows_kernel<<<(pat.n + bs - 1) / bs, bs, 0, ctx->stream>>>(pat.rowptr.p, pat.n, pat.rowidx.p);
+  PLFEM_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
+void launch_assemble(plfem_ctx* ctx, const DevPattern& pat, const int32_t* d_n2e_ptr, const int32_t* d_n2e,
+                     const int32_t* d_edofs, const double* d_elem, double k0sq, double alpha, bool export_mode,
+                     double* d_vals, uint32_t* d_flags) {
+  ensure_tables(ctx);
+  const int bs = 128;
+  const unsigned grid = (unsigned)((pat.nnz + bs - 1) / bs);
+  if (export_mode)
+    assemble_kernel<true><<<grid, bs, 0, ctx->stream>>>(pat.nnz, pat.rowidx.p, pat.col.p, pat.old_of_new.p, d_n2e_ptr,
+                                                        d_n2e, d_edofs, d_elem, k0sq, alpha, d_vals, d_flags);
+  else
+    assemble_kernel<false><<<grid, bs, 0, ctx->stream>>>(pat.nnz, pat.rowidx.p, pat.col.p, pat.old_of_new.p, d_n2e_ptr,
+                                                         d_n2e, d_edofs, d_elem, k0sq, alpha, d_vals, d_flags);
+  PLFEM_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
+void launch_spmv_csr(plfem_ctx* ctx, int64_t rows, const int32_t* rowptr, const int32_t* col, const double* val,
+                     const double* x, double* y) {
+  constexpr int TPR = 8;
+  const int bs = 256;
+  const unsigned grid = (unsigned)((rows * TPR + bs - 1) / bs);
+  spmv_csr_kernel<TPR><<<grid, bs, 0, ctx->stream>>>(rows, rowptr, col, val, x, y);
+  PLFEM_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
+}  // namespace plfem

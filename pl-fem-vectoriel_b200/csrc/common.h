@@ -1,0 +1,163 @@
+// Shared declarations of the CUDA side (context, caching device allocator, problem state).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/plfem.h"
+#include "symbolic.h"
+
+namespace plfem {
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+struct StatusError : std::runtime_error {
+  int status;
+  StatusError(int st, const std::string& m) : std::runtime_error(m), status(st) {}
+};
+
+#define PLFEM_CUDA(call)                                                                              \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess)                                                                            \
+      throw plfem::CudaError(std::string(#call) + " failed: " + cudaGetErrorString(e_) + " at " +      \
+                             __FILE__ + ":" + std::to_string(__LINE__));                              \
+  } while (0)
+
+// Size-class caching allocator: cudaMalloc/cudaFree cost more than a whole assembly pass, and a
+// sweep creates and drops one problem per design.
+class DeviceArena {
+ public:
+  void* alloc(size_t bytes);
+  void release(void* p);
+  void destroy();
+  size_t reserved_bytes() const { return reserved_; }
+
+ private:
+  std::multimap<size_t, void*> free_;
+  std::map<void*, size_t> live_;
+  size_t reserved_ = 0;
+};
+
+}  // namespace plfem
+
+struct plfem_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  plfem::DeviceArena arena;
+  int launches = 0;          // kernels launched since the counter was last reset
+  cudaEvent_t ev[8] = {};
+  void* pinned = nullptr;    // pinned staging buffer for small device->host reads
+  size_t pinned_bytes = 0;
+  void* pin(size_t bytes);
+};
+
+namespace plfem {
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  plfem_ctx* ctx = nullptr;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { free(); }
+  void free() {
+    if (p && ctx) ctx->arena.release(p);
+    p = nullptr; n = 0;
+  }
+  void alloc(plfem_ctx* c, size_t count) {
+    if (p && n >= count && ctx == c) { return; }
+    free();
+    ctx = c; n = count;
+    p = count ? static_cast<T*>(c->arena.alloc(count * sizeof(T))) : nullptr;
+  }
+  void upload(plfem_ctx* c, const T* h, size_t count) {
+    alloc(c, count);
+    if (count) PLFEM_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  }
+  void upload(plfem_ctx* c, const std::vector<T>& h) { upload(c, h.data(), h.size()); }
+  void zero() {
+    if (n) PLFEM_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), ctx->stream));
+  }
+  void download(T* h, size_t count) const {
+    if (count) PLFEM_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+};
+
+// number of scalar value arrays produced by the two assembly modes
+constexpr int NV_EXPORT = 10;  // kxx kyy kxy kyx dxx dyy dxy dyx m minv
+constexpr int NV_SOLVE = 8;    // axx axy ayx ayy minv dxx dxy dyy
+enum { S_AXX = 0, S_AXY, S_AYX, S_AYY, S_MINV, S_DXX, S_DXY, S_DYY };
+enum { X_KXX = 0, X_KYY, X_KXY, X_KYX, X_DXX, X_DYY, X_DXY, X_DYX, X_M, X_MINV };
+
+struct DevPattern {
+  int32_t n = 0;
+  int64_t nnz = 0;
+  DevBuf<int32_t> rowptr, col, rowidx, old_of_new;
+};
+
+struct RefTables {  // shape functions at the quadrature points, [i*6 + q]
+  double phi[36], dx[36], dy[36], w[6], qx[6], qy[6];
+};
+const RefTables& ref_tables();
+
+// ---- kernels (assembly.cu) -----------------------------------------------------------------------
+void launch_element_setup(plfem_ctx* ctx, const double* d_p, const int32_t* d_edofs, int64_t V, int64_t T,
+                          const plfem_material& mat, const double* d_cores /* (nc,3): cx cy r */,
+                          const double* d_eps_at_quad, double* d_elem);
+void launch_expand_rows(plfem_ctx* ctx, const DevPattern& pat);
+void launch_assemble(plfem_ctx* ctx, const DevPattern& pat, const int32_t* d_n2e_ptr, const int32_t* d_n2e,
+                     const int32_t* d_edofs, const double* d_elem, double k0sq, double alpha, bool export_mode,
+                     double* d_vals, uint32_t* d_flags);
+void launch_spmv_csr(plfem_ctx* ctx, int64_t rows, const int32_t* rowptr, const int32_t* col, const double* val,
+                     const double* x, double* y);
+
+// ---- multifrontal factorisation and solves (factor.cu) ------------------------------------------------
+struct DevPlan {
+  int32_t n = 0, nfronts = 0, nlevels = 0;
+  DevBuf<int32_t> first, s, sptr, strct, sn_of, parent, cptr, child, cmap_ptr, cmap, lfront;
+  DevBuf<int64_t> foff;
+  DevBuf<int32_t> uoff;              // offset of each front's update vector (in doubles)
+  std::vector<int32_t> lptr;         // host copy of the level schedule
+  std::vector<int32_t> lmax_m;       // largest pivot block (unknowns) per level
+  // per-level work lists (host-built): tiles for the two GEMMs, slabs for extend-add and the sweeps
+  DevBuf<int4> w_tiles, s_tiles, ea_slabs, fwd_slabs, bwd_slabs;
+  std::vector<int32_t> w_ptr, s_ptr, ea_ptr, fwd_ptr, bwd_ptr;  // [nlevels+1] each
+  DevBuf<double> pool;               // all frontal matrices
+  DevBuf<double> upd;                // per-front update vectors of the forward sweep
+  DevBuf<int32_t> status;            // [0] = 1 when a pivot block was singular
+  int64_t upd_len = 0;
+};
+void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D);
+void launch_front_load(plfem_ctx* ctx, const DevPattern& pat, const DevPlan& D, const double* d_vals, double sigma);
+void run_factorization(plfem_ctx* ctx, const DevPlan& D);
+// solves (A - sigma B) x = b in the permuted interleaved layout, b and x of length 2n (must not alias)
+void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x);
+
+// ---- Lanczos + mode reductions (eigen.cu) ----------------------------------------------------------
+struct EigenResult {
+  std::vector<double> theta;  // Ritz values of OP, wanted ones, sorted by eigenvalue ascending
+  int nconv = 0, n_op = 0, n_restart = 0;
+};
+struct EigenWork;  // opaque
+void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, const DevPlan& D, const double* d_vals, double sigma,
+                     int k, int ncv, double tol, int maxiter, int refine_steps, const double* d_v0 /* permuted, may be null */,
+                     DevBuf<double>& X /* (2n, k) eigenvectors, permuted layout */, std::vector<double>& lambda,
+                     EigenResult& res);
+void run_mode_metrics(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, const int32_t* d_perm_to_interior,
+                      const uint8_t* d_in_core, const double* X, const std::vector<double>& lambda, int k,
+                      double* d_out_evecs /* (k, 2n) reference ordering or null */, double* d_metrics /* (k,8) */,
+                      double* d_resid /* (k,2) */);
+
+void symmetric_eigen(int n, std::vector<double>& a /* n*n col-major in, eigenvectors out */, std::vector<double>& w);
+
+}  // namespace plfem

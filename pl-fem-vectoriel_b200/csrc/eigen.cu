@@ -1,0 +1,411 @@
+// K7-K8: shift-invert thick-restart Lanczos in the B inner product, and the per-mode reductions.
+//
+// Replaces scipy eigsh(A_int, k, M=B_int, sigma, which='LM', tol, maxiter) = ARPACK dsaupd mode 3
+// (solver_fem.py:197) and the per-mode loop of solver_fem.py:206-220.
+//
+// OP = (A - sigma B)^-1 B is self-adjoint in <x,y>_B.  The Krylov basis V and its image BV stay in
+// HBM; every scalar of the recurrence (alpha, beta, the CGS2 coefficients) stays on the device too,
+// so a run of Lanczos steps is a pure stream of launches with no host synchronisation.  The host is
+// only involved at a restart: it reads back <= 2*ncv scalars, diagonalises the ncv x ncv projected
+// matrix (symeig.cpp) and sends the rotation back; the rotation itself (V <- V S) is a device kernel.
+// Thick restart with exact shifts is mathematically what ARPACK's implicit restart does.
+#include "common.h"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+namespace plfem {
+
+namespace {
+
+constexpr int RED_T = 1024;
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  // deterministic CTA reduction (fixed tree), blockDim.x == RED_T or smaller multiple of 32
+  const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  const int nw = blockDim.x / 32;
+  v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
+  if (warp == 0) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  }
+  return v;  // valid in thread 0
+}
+
+// y = B x on the permuted interleaved layout: y[r] (2 comps) = sum_z minv[z] * x[col[z]] (2 comps)
+__global__ void __launch_bounds__(256) spmm_b_kernel(int32_t n, const int32_t* __restrict__ rowptr,
+                                                     const int32_t* __restrict__ col, const double* __restrict__ minv,
+                                                     const double2* __restrict__ x, double2* __restrict__ y) {
+  constexpr int TPR = 4;
+  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t row = gid / TPR;
+  const int lane = (int)(gid % TPR);
+  double ax = 0.0, ay = 0.0;
+  if (row < n) {
+    for (int32_t z = rowptr[row] + lane; z < rowptr[row + 1]; z += TPR) {
+      const double m = minv[z];
+      const double2 v = x[col[z]];
+      ax = fma(m, v.x, ax); ay = fma(m, v.y, ay);
+    }
+  }
+#pragma unroll
+  for (int off = TPR / 2; off > 0; off >>= 1) {
+    ax += __shfl_down_sync(0xffffffffu, ax, off, TPR);
+    ay += __shfl_down_sync(0xffffffffu, ay, off, TPR);
+  }
+  if (row < n && lane == 0) y[row] = make_double2(ax, ay);
+}
+
+// t = b - (A - sigma B) x on the permuted interleaved layout (iterative refinement of the block-LDL^T solve)
+__global__ void __launch_bounds__(256) resid_k_kernel(int32_t n, const int32_t* __restrict__ rowptr,
+                                                      const int32_t* __restrict__ col, const double* __restrict__ vals,
+                                                      int64_t nnz, double sigma, const double2* __restrict__ x,
+                                                      const double2* __restrict__ b, double2* __restrict__ t) {
+  constexpr int TPR = 4;
+  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t row = gid / TPR;
+  const int lane = (int)(gid % TPR);
+  double ax = 0.0, ay = 0.0;
+  if (row < n) {
+    for (int32_t z = rowptr[row] + lane; z < rowptr[row + 1]; z += TPR) {
+      const double sm = sigma * vals[(int64_t)S_MINV * nnz + z];
+      const double2 v = x[col[z]];
+      ax = fma(vals[(int64_t)S_AXX * nnz + z] - sm, v.x, ax);
+      ax = fma(vals[(int64_t)S_AXY * nnz + z], v.y, ax);
+      ay = fma(vals[(int64_t)S_AYX * nnz + z], v.x, ay);
+      ay = fma(vals[(int64_t)S_AYY * nnz + z] - sm, v.y, ay);
+    }
+  }
+#pragma unroll
+  for (int off = TPR / 2; off > 0; off >>= 1) {
+    ax += __shfl_down_sync(0xffffffffu, ax, off, TPR);
+    ay += __shfl_down_sync(0xffffffffu, ay, off, TPR);
+  }
+  if (row < n && lane == 0) { const double2 bb = b[row]; t[row] = make_double2(bb.x - ax, bb.y - ay); }
+}
+
+__global__ void __launch_bounds__(256) add_kernel(double* __restrict__ x, const double* __restrict__ dx, int64_t m) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < m) x[i] += dx[i];
+}
+
+// h[c] = <Q[:,c], r> for c < ncols; one CTA per column
+__global__ void __launch_bounds__(RED_T) dots_kernel(const double* __restrict__ Q, int64_t ld, const double* __restrict__ r,
+                                                     int64_t m, double* __restrict__ h) {
+  __shared__ double sh[32];
+  const double* q = Q + (int64_t)blockIdx.x * ld;
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < m; i += RED_T) acc = fma(q[i], r[i], acc);
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) h[blockIdx.x] = acc;
+}
+
+// r -= V[:, 0..ncols) h
+__global__ void __launch_bounds__(256) update_kernel(const double* __restrict__ V, int64_t ld, const double* __restrict__ h,
+                                                     int ncols, int64_t m, double* __restrict__ r) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  double acc0 = 0.0, acc1 = 0.0;
+  int c = 0;
+  for (; c + 1 < ncols; c += 2) {
+    acc0 = fma(V[(int64_t)c * ld + i], h[c], acc0);
+    acc1 = fma(V[(int64_t)(c + 1) * ld + i], h[c + 1], acc1);
+  }
+  if (c < ncols) acc0 = fma(V[(int64_t)c * ld + i], h[c], acc0);
+  r[i] -= acc0 + acc1;
+}
+
+// beta2 = <r, u>; alpha[j] = h1[j] + h2[j]; beta[j] = sqrt(beta2)     (single CTA)
+__global__ void __launch_bounds__(RED_T) bnorm_kernel(const double* __restrict__ r, const double* __restrict__ u, int64_t m,
+                                                      const double* __restrict__ h1, const double* __restrict__ h2, int j,
+                                                      double* __restrict__ alpha, double* __restrict__ beta) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < m; i += RED_T) acc = fma(r[i], u[i], acc);
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) {
+    beta[j] = sqrt(acc);
+    if (h1) alpha[j] = h1[j] + h2[j];
+  }
+}
+
+// v = r / beta[j], bv = u / beta[j]
+__global__ void __launch_bounds__(256) scale_kernel(const double* __restrict__ r, const double* __restrict__ u, int64_t m,
+                                                    const double* __restrict__ beta, int j, double* __restrict__ v,
+                                                    double* __restrict__ bv) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const double s = 1.0 / beta[j];
+  v[i] = r[i] * s;
+  bv[i] = u[i] * s;
+}
+
+// Out[:, c] = sum_j In[:, j] * S[j, c]  for c < nout (S is nin x nout, column-major, in global memory)
+__global__ void __launch_bounds__(128) rotate_kernel(const double* __restrict__ In, int64_t ld, int nin,
+                                                     const double* __restrict__ S, int nout, int64_t m,
+                                                     double* __restrict__ Out, int64_t ldo) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  for (int c0 = 0; c0 < nout; c0 += 8) {
+    double acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.0;
+    for (int j = 0; j < nin; ++j) {
+      const double v = In[(int64_t)j * ld + i];
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c0 + c < nout) acc[c] = fma(v, __ldg(S + (int64_t)(c0 + c) * nin + j), acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c0 + c < nout) Out[(int64_t)(c0 + c) * ldo + i] = acc[c];
+  }
+}
+
+__global__ void fill_kernel(double* v, int64_t m, double val) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < m) v[i] = val;
+}
+
+// ---- per-mode reductions ----------------------------------------------------------------------------------
+constexpr int NRED = 10;  // norm2, e_core, px_core, py_core, px_all, py_all, div, res2, bx2, unused
+constexpr int MROWS = 2048;  // rows (nodes) per CTA in the mode reduction
+
+__global__ void __launch_bounds__(256) mode_partial_kernel(int32_t n, const int32_t* __restrict__ rowptr,
+                                                           const int32_t* __restrict__ col, const double* __restrict__ vals,
+                                                           int64_t nnz, const uint8_t* __restrict__ in_core,
+                                                           const double2* __restrict__ X, int64_t ldx /* in double2 */,
+                                                           const double* __restrict__ lambda, double* __restrict__ part,
+                                                           int nchunks) {
+  __shared__ double sh[32];
+  const int mode = blockIdx.y, chunk = blockIdx.x;
+  const double2* x = X + (int64_t)mode * ldx;
+  const double lam = lambda[mode];
+  double acc[NRED];
+#pragma unroll
+  for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
+  const int r0 = chunk * MROWS, r1 = min(n, r0 + MROWS);
+  for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+    const double2 v = x[r];
+    const double ex = v.x * v.x, ey = v.y * v.y;
+    acc[0] += ex + ey;
+    acc[4] += ex; acc[5] += ey;
+    if (in_core[r]) { acc[1] += ex + ey; acc[2] += ex; acc[3] += ey; }
+    double dx = 0.0, dy = 0.0, axv = 0.0, ayv = 0.0, bx = 0.0, by = 0.0;
+    for (int32_t z = rowptr[r]; z < rowptr[r + 1]; ++z) {
+      const double2 c = x[col[z]];
+      dx = fma(vals[(int64_t)S_DXX * nnz + z], c.x, dx);
+      dx = fma(2.0 * vals[(int64_t)S_DXY * nnz + z], c.y, dx);
+      dy = fma(vals[(int64_t)S_DYY * nnz + z], c.y, dy);
+      axv = fma(vals[(int64_t)S_AXX * nnz + z], c.x, axv);
+      axv = fma(vals[(int64_t)S_AXY * nnz + z], c.y, axv);
+      ayv = fma(vals[(int64_t)S_AYX * nnz + z], c.x, ayv);
+      ayv = fma(vals[(int64_t)S_AYY * nnz + z], c.y, ayv);
+      const double mi = vals[(int64_t)S_MINV * nnz + z];
+      bx = fma(mi, c.x, bx); by = fma(mi, c.y, by);
+    }
+    acc[6] += v.x * dx + v.y * dy;
+    const double rx = axv - lam * bx, ry = ayv - lam * by;
+    acc[7] += rx * rx + ry * ry;
+    acc[8] += bx * bx + by * by;
+  }
+  for (int k = 0; k < NRED; ++k) {
+    const double t = block_sum(acc[k], sh);
+    if (threadIdx.x == 0) part[((int64_t)mode * nchunks + chunk) * NRED + k] = t;
+  }
+}
+
+// metrics (k, 8): div_energy, sum_e_core, sum_e, Px_core, Py_core, Px_all, Py_all, norm2_raw ; resid (k,2)
+__global__ void mode_final_kernel(const double* __restrict__ part, int nchunks, int k, double* __restrict__ metrics,
+                                  double* __restrict__ resid, double* __restrict__ scale) {
+  const int mode = blockIdx.x * blockDim.x + threadIdx.x;
+  if (mode >= k) return;
+  double t[NRED];
+  for (int q = 0; q < NRED; ++q) t[q] = 0.0;
+  for (int c = 0; c < nchunks; ++c)
+    for (int q = 0; q < NRED; ++q) t[q] += part[((int64_t)mode * nchunks + c) * NRED + q];
+  const double nrm = sqrt(t[0]) + 1e-30;
+  const double inv2 = 1.0 / (nrm * nrm);
+  scale[mode] = 1.0 / nrm;
+  double* o = metrics + (int64_t)mode * PLFEM_NMETRICS;
+  o[0] = t[6] * inv2; o[1] = t[1] * inv2; o[2] = t[0] * inv2; o[3] = t[2] * inv2; o[4] = t[3] * inv2;
+  o[5] = t[4] * inv2; o[6] = t[5] * inv2; o[7] = t[0];
+  resid[2 * mode] = sqrt(t[7]); resid[2 * mode + 1] = sqrt(t[8]);
+}
+
+__global__ void __launch_bounds__(256) write_evecs_kernel(int32_t n, const int32_t* __restrict__ perm,
+                                                          const double2* __restrict__ X, int64_t ldx,
+                                                          const double* __restrict__ scale, double* __restrict__ out) {
+  const int mode = blockIdx.y;
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const double2 v = X[(int64_t)mode * ldx + r];
+  const double s = scale[mode];
+  double* o = out + (int64_t)mode * 2 * n;
+  const int32_t ip = perm[r];
+  o[ip] = v.x * s;
+  o[n + ip] = v.y * s;
+}
+
+}  // namespace
+
+void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, const DevPlan& D, const double* d_vals, double sigma, int k,
+                     int ncv, double tol, int maxiter, int refine_steps, const double* d_v0, DevBuf<double>& X,
+                     std::vector<double>& lambda, EigenResult& res) {
+  const int64_t m = 2 * (int64_t)pat.n;
+  const int64_t ld = m;
+  cudaStream_t st = ctx->stream;
+  const double* minv = d_vals + (int64_t)S_MINV * pat.nnz;
+  DevBuf<double> V[2], BV[2], r, u, h1, h2, alpha, beta, Sdev, rt, rdx;
+  for (int b = 0; b < 2; ++b) { V[b].alloc(ctx, (size_t)ld * (ncv + 1)); BV[b].alloc(ctx, (size_t)ld * (ncv + 1)); }
+  r.alloc(ctx, m); u.alloc(ctx, m);
+  if (refine_steps > 0) { rt.alloc(ctx, m); rdx.alloc(ctx, m); }
+  h1.alloc(ctx, ncv + 1); h2.alloc(ctx, ncv + 1); alpha.alloc(ctx, ncv + 1); beta.alloc(ctx, ncv + 1);
+  Sdev.alloc(ctx, (size_t)ncv * ncv);
+  int cur = 0;
+  const unsigned gm = (unsigned)((m + 255) / 256);
+  const unsigned gspmm = (unsigned)(((int64_t)pat.n * 4 + 255) / 256);
+  auto spmm = [&](const double* x, double* y) {
+    spmm_b_kernel<<<gspmm, 256, 0, st>>>(pat.n, pat.rowptr.p, pat.col.p, minv, (const double2*)x, (double2*)y);
+    ctx->launches++;
+  };
+
+  // OP application: block-LDL^T solve + fixed number of refinement steps with the true operator
+  // (the pivot blocks are not pivoted against each other, so one raw solve carries a backward error
+  // of ~1e-9 relative; each step squares the contraction and the composite stays a fixed symmetric
+  // linear operator, which is what Lanczos needs)
+  auto apply_op = [&](const double* bvec, double* out) {
+    run_solve(ctx, D, bvec, out);
+    for (int it = 0; it < refine_steps; ++it) {
+      resid_k_kernel<<<gspmm, 256, 0, st>>>(pat.n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz, sigma, (const double2*)out,
+                                            (const double2*)bvec, (double2*)rt.p);
+      run_solve(ctx, D, rt.p, rdx.p);
+      add_kernel<<<gm, 256, 0, st>>>(out, rdx.p, m);
+      ctx->launches += 2;
+    }
+  };
+
+  // start vector: v0 / ||v0||_B
+  if (d_v0) PLFEM_CUDA(cudaMemcpyAsync(r.p, d_v0, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  else { fill_kernel<<<gm, 256, 0, st>>>(r.p, m, 1.0); ctx->launches++; }
+  spmm(r.p, u.p);
+  bnorm_kernel<<<1, RED_T, 0, st>>>(r.p, u.p, m, nullptr, nullptr, ncv, alpha.p, beta.p);   // beta[ncv] = ||v0||_B
+  scale_kernel<<<gm, 256, 0, st>>>(r.p, u.p, m, beta.p, ncv, V[cur].p, BV[cur].p);
+  ctx->launches += 2;
+
+  std::vector<double> h_alpha(ncv + 1), h_beta(ncv + 1), theta_keep, b_keep, T, w;
+  std::vector<int> order(ncv);
+  int p = 0;
+  res = EigenResult();
+  const double eps23 = std::pow(2.220446049250313e-16, 2.0 / 3.0);
+  for (;;) {
+    for (int j = p; j < ncv; ++j) {
+      double* Vc = V[cur].p; double* BVc = BV[cur].p;
+      apply_op(BVc + (int64_t)j * ld, r.p);                                   // r = OP v_j
+      res.n_op++;
+      dots_kernel<<<j + 1, RED_T, 0, st>>>(BVc, ld, r.p, m, h1.p);            // CGS pass 1
+      update_kernel<<<gm, 256, 0, st>>>(Vc, ld, h1.p, j + 1, m, r.p);
+      dots_kernel<<<j + 1, RED_T, 0, st>>>(BVc, ld, r.p, m, h2.p);            // CGS pass 2
+      update_kernel<<<gm, 256, 0, st>>>(Vc, ld, h2.p, j + 1, m, r.p);
+      spmm(r.p, u.p);
+      bnorm_kernel<<<1, RED_T, 0, st>>>(r.p, u.p, m, h1.p, h2.p, j, alpha.p, beta.p);
+      scale_kernel<<<gm, 256, 0, st>>>(r.p, u.p, m, beta.p, j, Vc + (int64_t)(j + 1) * ld, BVc + (int64_t)(j + 1) * ld);
+      ctx->launches += 6;
+    }
+    PLFEM_CUDA(cudaGetLastError());
+    alpha.download(h_alpha.data(), ncv);
+    beta.download(h_beta.data(), ncv);
+    PLFEM_CUDA(cudaStreamSynchronize(st));
+    // projected matrix
+    T.assign((size_t)ncv * ncv, 0.0);
+    for (int i = 0; i < p; ++i) { T[(size_t)i * ncv + i] = theta_keep[i]; T[(size_t)p * ncv + i] = T[(size_t)i * ncv + p] = b_keep[i]; }
+    for (int j = p; j < ncv; ++j) {
+      T[(size_t)j * ncv + j] = h_alpha[j];
+      if (j + 1 < ncv) T[(size_t)(j + 1) * ncv + j] = T[(size_t)j * ncv + j + 1] = h_beta[j];
+    }
+    for (double v : T) if (!std::isfinite(v)) throw StatusError(PLFEM_ERR_SINGULAR, "Lanczos recurrence produced a non-finite value (shifted operator singular?)");
+    symmetric_eigen(ncv, T, w);   // T now holds eigenvectors in columns
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return std::fabs(w[a]) > std::fabs(w[b]); });
+    const double bm = h_beta[ncv - 1];
+    int nconv = 0;
+    for (int i = 0; i < k; ++i) {
+      const int c = order[i];
+      const double bound = std::fabs(bm * T[(size_t)c * ncv + (ncv - 1)]);
+      if (bound <= tol * std::max(eps23, std::fabs(w[c]))) nconv++;
+    }
+    res.nconv = nconv;
+    const bool done = nconv >= k;
+    if (done || res.n_restart >= maxiter) {
+      // eigenvectors X = V S[:, wanted], eigenvalues lambda = sigma + 1/theta, ascending in lambda
+      std::vector<int> sel(order.begin(), order.begin() + k);
+      std::sort(sel.begin(), sel.end(), [&](int a, int b) { return sigma + 1.0 / w[a] < sigma + 1.0 / w[b]; });
+      std::vector<double> S((size_t)ncv * k);
+      lambda.resize(k); res.theta.resize(k);
+      for (int i = 0; i < k; ++i) {
+        std::copy(T.begin() + (size_t)sel[i] * ncv, T.begin() + (size_t)(sel[i] + 1) * ncv, S.begin() + (size_t)i * ncv);
+        res.theta[i] = w[sel[i]];
+        lambda[i] = sigma + 1.0 / w[sel[i]];
+      }
+      PLFEM_CUDA(cudaMemcpyAsync(Sdev.p, S.data(), S.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+      X.alloc(ctx, (size_t)m * k);
+      rotate_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(V[cur].p, ld, ncv, Sdev.p, k, m, X.p, m);
+      ctx->launches++;
+      PLFEM_CUDA(cudaStreamSynchronize(st));   // S is a local host buffer
+      if (!done) throw StatusError(PLFEM_ERR_NO_CONVERGENCE, "Lanczos: " + std::to_string(nconv) + " of " + std::to_string(k) + " eigenpairs converged after " + std::to_string(res.n_restart) + " restarts");
+      return;
+    }
+    // thick restart: keep the k wanted Ritz pairs plus some of the next ones (ARPACK's nev adjustment)
+    int keep = k + std::min(nconv, (ncv - k) / 2);
+    keep = std::max(1, std::min(keep, ncv - 2));
+    std::vector<double> S((size_t)ncv * keep);
+    theta_keep.resize(keep); b_keep.resize(keep);
+    for (int i = 0; i < keep; ++i) {
+      const int c = order[i];
+      std::copy(T.begin() + (size_t)c * ncv, T.begin() + (size_t)(c + 1) * ncv, S.begin() + (size_t)i * ncv);
+      theta_keep[i] = w[c];
+      b_keep[i] = bm * T[(size_t)c * ncv + (ncv - 1)];
+    }
+    PLFEM_CUDA(cudaMemcpyAsync(Sdev.p, S.data(), S.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    const int nxt = cur ^ 1;
+    rotate_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(V[cur].p, ld, ncv, Sdev.p, keep, m, V[nxt].p, ld);
+    rotate_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(BV[cur].p, ld, ncv, Sdev.p, keep, m, BV[nxt].p, ld);
+    PLFEM_CUDA(cudaMemcpyAsync(V[nxt].p + (int64_t)keep * ld, V[cur].p + (int64_t)ncv * ld, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    PLFEM_CUDA(cudaMemcpyAsync(BV[nxt].p + (int64_t)keep * ld, BV[cur].p + (int64_t)ncv * ld, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    ctx->launches += 2;
+    PLFEM_CUDA(cudaStreamSynchronize(st));     // S is a local host buffer
+    cur = nxt; p = keep;
+    res.n_restart++;
+  }
+}
+
+void run_mode_metrics(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, const int32_t* d_perm_to_interior,
+                      const uint8_t* d_in_core, const double* X, const std::vector<double>& lambda, int k,
+                      double* d_out_evecs, double* d_metrics, double* d_resid) {
+  cudaStream_t st = ctx->stream;
+  const int n = pat.n;
+  const int nchunks = (n + MROWS - 1) / MROWS;
+  DevBuf<double> part, lam, scale;
+  part.alloc(ctx, (size_t)k * nchunks * NRED);
+  lam.upload(ctx, lambda.data(), k);
+  scale.alloc(ctx, k);
+  mode_partial_kernel<<<dim3(nchunks, k), 256, 0, st>>>(n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz, d_in_core,
+                                                        (const double2*)X, (int64_t)n, lam.p, part.p, nchunks);
+  mode_final_kernel<<<(k + 63) / 64, 64, 0, st>>>(part.p, nchunks, k, d_metrics, d_resid, scale.p);
+  ctx->launches += 2;
+  if (d_out_evecs) {
+    write_evecs_kernel<<<dim3((n + 255) / 256, k), 256, 0, st>>>(n, d_perm_to_interior, (const double2*)X, (int64_t)n,
+                                                                 scale.p, d_out_evecs);
+    ctx->launches++;
+  }
+  PLFEM_CUDA(cudaGetLastError());
+  PLFEM_CUDA(cudaStreamSynchronize(st));   // lambda upload source and the DevBufs above go out of scope
+}
+
+}  // namespace plfem

@@ -1,0 +1,455 @@
+// K4-K6: level-batched multifrontal block-LDL^T factorisation of (A - sigma B) and the two sweeps.
+//
+// Replaces SuperLU `splu` + `solve` inside scipy eigsh (solver_fem.py:197).
+//
+// Design (B200): the shifted operator is symmetric indefinite and only ~45k-2M unknowns, so the
+// work is latency-bound, not flop-bound.  Fronts come from a host nested dissection (symbolic.cpp);
+// every level of the elimination tree is ONE batched launch per stage, all fronts of the level in
+// flight at once:
+//     extend-add  ->  invert pivot block  ->  W^T = (F11^-1 F12)^T  ->  S = F22 - F12^T W
+// A front is a dense column-major (2nf x 2nf) matrix (two unknowns, Hx and Hy, per P2 node).  The
+// pivot block F11 (<= 128 x 128) is inverted explicitly with partial pivoting in shared memory, so
+// the solve phase is pure matrix-vector work on the contiguous left block column [F11^-1 ; W^T]:
+//     forward :  z1 = F11^-1 y1 ,  upd = y2 - W^T y1      (one coalesced GEMV over 2nf rows)
+//     backward:  x1 = z1 - W x2                            (one dot product per column of W^T)
+// Contributions travel child -> parent through per-front update blocks/vectors with precomputed
+// position maps: gather-only, fixed order, no atomics, bit-reproducible run to run.
+#include "common.h"
+
+#include <algorithm>
+
+namespace plfem {
+
+namespace {
+
+constexpr int GT = 64;        // GEMM tile (GT x GT outputs per CTA)
+constexpr int GK = 16;        // GEMM k-step
+constexpr int EA_COLS = 8;    // extend-add slab width in parent node columns
+constexpr int FWD_ROWS = 128; // forward sweep: rows (unknowns) per CTA
+constexpr int BWD_COLS = 16;  // backward sweep: columns (unknowns) per CTA
+constexpr int MAX_PIV = 128;  // largest pivot block (unknowns) the in-shared-memory inverse handles
+
+struct PlanView {
+  const int32_t *first, *s, *sptr, *strct, *cptr, *child, *cmap_ptr, *cmap, *uoff;
+  const int64_t* foff;
+  double* pool;
+};
+
+__device__ __forceinline__ int front_u(const PlanView& P, int f) { return P.sptr[f + 1] - P.sptr[f]; }
+
+// ---- load (A - sigma B) into the fronts: one thread per structural non-zero ---------------------------
+__global__ void front_load_kernel(int64_t nnz, const int32_t* __restrict__ rowidx, const int32_t* __restrict__ col,
+                                  const int32_t* __restrict__ sn_of, PlanView P, const double* __restrict__ vals,
+                                  double sigma) {
+  const int64_t z = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (z >= nnz) return;
+  const int32_t r = rowidx[z], c = col[z];
+  const int32_t f = sn_of[r];
+  const int32_t f0 = P.first[f], s = P.s[f];
+  if (c < f0) return;  // belongs to the front that eliminates c
+  int32_t pc;
+  if (c < f0 + s) {
+    pc = c - f0;
+  } else {
+    int32_t lo = P.sptr[f], hi = P.sptr[f + 1];
+    const int32_t base = lo;
+    while (lo < hi) {
+      const int32_t mid = (lo + hi) >> 1;
+      if (P.strct[mid] < c) lo = mid + 1; else hi = mid;
+    }
+    pc = s + (lo - base);
+  }
+  const int64_t ld = 2 * (int64_t)(s + front_u(P, f));
+  double* F = P.pool + P.foff[f];
+  const int64_t pr = r - f0;
+  const double b = sigma * vals[(int64_t)S_MINV * nnz + z];
+  F[(2 * pc) * ld + 2 * pr] = vals[(int64_t)S_AXX * nnz + z] - b;
+  F[(2 * pc + 1) * ld + 2 * pr] = vals[(int64_t)S_AXY * nnz + z];
+  F[(2 * pc) * ld + 2 * pr + 1] = vals[(int64_t)S_AYX * nnz + z];
+  F[(2 * pc + 1) * ld + 2 * pr + 1] = vals[(int64_t)S_AYY * nnz + z] - b;
+}
+
+// ---- extend-add: parent += children's Schur complements, one CTA per (parent, column slab) --------------
+__global__ void __launch_bounds__(256) extend_add_kernel(const int4* __restrict__ slabs, PlanView P) {
+  const int4 sl = slabs[blockIdx.x];
+  const int f = sl.x, c0 = sl.y, c1 = sl.z;
+  const int sp = P.s[f];
+  const int64_t ldp = 2 * (int64_t)(sp + front_u(P, f));
+  double* Fp = P.pool + P.foff[f];
+  for (int q = P.cptr[f]; q < P.cptr[f + 1]; ++q) {
+    const int ch = P.child[q];
+    const int sc = P.s[ch], uc = front_u(P, ch);
+    const int32_t* cm = P.cmap + P.cmap_ptr[ch];
+    // child columns whose parent position falls in [c0, c1)  (cm is increasing)
+    int lo = 0, hi = uc;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (cm[mid] < c0) lo = mid + 1; else hi = mid; }
+    const int jlo = lo;
+    hi = uc;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (cm[mid] < c1) lo = mid + 1; else hi = mid; }
+    const int jhi = lo;
+    const int64_t ldc = 2 * (int64_t)(sc + uc);
+    const double* Sc = P.pool + P.foff[ch] + (2 * (int64_t)sc) * ldc + 2 * sc;  // F22 of the child
+    const int rows = 2 * uc, cols = 2 * (jhi - jlo);
+    for (int64_t t = threadIdx.x; t < (int64_t)rows * cols; t += blockDim.x) {
+      const int i = (int)(t % rows), j = (int)(t / rows) + 2 * jlo;
+      const int pj = cm[j >> 1], pi = cm[i >> 1];
+      if (pi >= sp && pj < sp) continue;  // F21 of the parent is never read
+      Fp[(2 * (int64_t)pj + (j & 1)) * ldp + 2 * pi + (i & 1)] += Sc[(int64_t)j * ldc + i];
+    }
+    __syncthreads();  // two children may hit the same parent entry: keep child order
+  }
+}
+
+// ---- pivot block inverse: Gauss-Jordan with partial pivoting in shared memory, one CTA per front ------
+__global__ void __launch_bounds__(256) invert_kernel(const int32_t* __restrict__ fronts, PlanView P, int32_t* status) {
+  extern __shared__ double sm[];
+  const int f = fronts[blockIdx.x];
+  const int m = 2 * P.s[f];
+  const int64_t ld = 2 * (int64_t)(P.s[f] + front_u(P, f));
+  double* F = P.pool + P.foff[f];
+  const int lds = m | 1;
+  double* a = sm;                 // m x m, column-major, leading dimension lds
+  double* colk = a + (size_t)lds * m;
+  double* rowk = colk + m;
+  __shared__ int piv[MAX_PIV];
+  __shared__ int src[MAX_PIV];
+  __shared__ int s_p;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int t = tid; t < m * m; t += nt) { const int i = t % m, j = t / m; a[i + j * lds] = F[(int64_t)j * ld + i]; }
+  __syncthreads();
+  for (int k = 0; k < m; ++k) {
+    if (tid < 32) {
+      double best = -1.0; int bi = k;
+      for (int i = k + tid; i < m; i += 32) {
+        const double v = fabs(a[i + k * lds]);
+        if (v > best) { best = v; bi = i; }   // NaN never wins; all-NaN column keeps bi = k
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ob = __shfl_down_sync(0xffffffffu, best, off);
+        const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (tid == 0) {
+        s_p = bi; piv[k] = bi;
+        if (!(best > 0.0) || !isfinite(best)) atomicExch(status, 1);
+      }
+    }
+    __syncthreads();
+    const int p = s_p;
+    const double inv = 1.0 / a[p + k * lds];
+    // row swap k <-> p fused with the copies of the pivot row (scaled) and pivot column
+    for (int j = tid; j < m; j += nt) {
+      const double ak = a[k + j * lds], ap = a[p + j * lds];
+      rowk[j] = ap * inv;
+      if (p != k && j != k) a[p + j * lds] = ak;
+    }
+    for (int i = tid; i < m; i += nt) {
+      double v;
+      if (i == k) v = 0.0;                         // unused
+      else if (i == p) v = a[k + k * lds];         // row p now holds old row k
+      else v = a[i + k * lds];
+      colk[i] = v;
+    }
+    __syncthreads();
+    for (int t = tid; t < m * m; t += nt) {
+      const int i = t % m, j = t / m;
+      double v;
+      if (i == k) v = (j == k) ? inv : rowk[j];
+      else if (j == k) v = -colk[i] * inv;
+      else v = a[i + j * lds] - colk[i] * rowk[j];
+      a[i + j * lds] = v;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    for (int j = 0; j < m; ++j) src[j] = j;
+    for (int k = m - 1; k >= 0; --k) { const int t = src[k]; src[k] = src[piv[k]]; src[piv[k]] = t; }
+  }
+  __syncthreads();
+  for (int t = tid; t < m * m; t += nt) { const int i = t % m, j = t / m; F[(int64_t)j * ld + i] = a[i + src[j] * lds]; }
+}
+
+// ---- tiled FP64 GEMM used for W^T and the Schur update -------------------------------------------------
+// C(i,j) (+)= sign * sum_k A(i,k) * B(k,j); A is k-contiguous (A(i,k) = Ap[i*lda + k]);
+// B is either k-contiguous (B(k,j) = Bp[j*ldb + k]) or j-contiguous (Bp[k*ldb + j]); C(i,j) = Cp[j*ldc + i].
+template <bool B_KCONTIG, bool ACCUM>
+__device__ __forceinline__ void gemm_tile(const double* __restrict__ Ap, int64_t lda, const double* __restrict__ Bp,
+                                          int64_t ldb, double* __restrict__ Cp, int64_t ldc, int M, int N, int K,
+                                          int m0, int n0) {
+  __shared__ double As[GK][GT + 1];
+  __shared__ double Bs[GK][GT + 1];
+  const int tid = threadIdx.x;          // 256 threads, 16 x 16, each 4 x 4 outputs
+  const int tx = tid % 16, ty = tid / 16;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+  for (int k0 = 0; k0 < K; k0 += GK) {
+    // A tile: GT rows x GK k, k fastest in memory
+    for (int t = tid; t < GT * GK; t += 256) {
+      const int kk = t % GK, i = t / GK;
+      const int gi = m0 + i, gk = k0 + kk;
+      As[kk][i] = (gi < M && gk < K) ? Ap[(int64_t)gi * lda + gk] : 0.0;
+    }
+    if (B_KCONTIG) {
+      for (int t = tid; t < GT * GK; t += 256) {
+        const int kk = t % GK, j = t / GK;
+        const int gj = n0 + j, gk = k0 + kk;
+        Bs[kk][j] = (gj < N && gk < K) ? Bp[(int64_t)gj * ldb + gk] : 0.0;
+      }
+    } else {
+      for (int t = tid; t < GT * GK; t += 256) {
+        const int j = t % GT, kk = t / GT;
+        const int gj = n0 + j, gk = k0 + kk;
+        Bs[kk][j] = (gj < N && gk < K) ? Bp[(int64_t)gk * ldb + gj] : 0.0;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) av[a] = As[kk][tx + 16 * a];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bv[b] = Bs[kk][ty + 16 * b];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int gj = n0 + ty + 16 * b;
+    if (gj >= N) continue;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int gi = m0 + tx + 16 * a;
+      if (gi >= M) continue;
+      double* c = Cp + (int64_t)gj * ldc + gi;
+      if (ACCUM) *c -= acc[a][b]; else *c = acc[a][b];
+    }
+  }
+}
+
+// W^T:  F21new(j, i) = sum_k F12(k, j) * F11inv(k, i)      (j over 2u, i over 2s, k over 2s)
+__global__ void __launch_bounds__(256) gemm_w_kernel(const int4* __restrict__ tiles, PlanView P) {
+  const int4 t = tiles[blockIdx.x];
+  const int f = t.x;
+  const int s2 = 2 * P.s[f], u2 = 2 * front_u(P, f);
+  const int64_t ld = s2 + u2;
+  double* F = P.pool + P.foff[f];
+  gemm_tile<true, false>(F + (int64_t)s2 * ld /* F12: A(j,k) at (s2+j)*ld + k */, ld, F /* F11inv(k,i) at i*ld + k */, ld,
+                         F + s2 /* F21(j,i) at i*ld + s2 + j */, ld, u2, s2, s2, t.y, t.z);
+}
+
+// Schur:  F22(a, b) -= sum_k F12(k, a) * F21new(b, k)        (a, b over 2u, k over 2s)
+__global__ void __launch_bounds__(256) gemm_schur_kernel(const int4* __restrict__ tiles, PlanView P) {
+  const int4 t = tiles[blockIdx.x];
+  const int f = t.x;
+  const int s2 = 2 * P.s[f], u2 = 2 * front_u(P, f);
+  const int64_t ld = s2 + u2;
+  double* F = P.pool + P.foff[f];
+  gemm_tile<false, true>(F + (int64_t)s2 * ld, ld, F + s2 /* B(k,b) = F21new(b,k) at k*ld + s2 + b */, ld,
+                         F + (int64_t)s2 * ld + s2, ld, u2, u2, s2, t.y, t.z);
+}
+
+// ---- forward sweep: one CTA per (front, slab of rows) ---------------------------------------------------
+__global__ void __launch_bounds__(FWD_ROWS) forward_kernel(const int4* __restrict__ slabs, PlanView P,
+                                                            const double* __restrict__ rhs, double* __restrict__ z,
+                                                            double* __restrict__ upd) {
+  __shared__ double y1[MAX_PIV];
+  __shared__ double yt[FWD_ROWS];
+  const int4 sl = slabs[blockIdx.x];
+  const int f = sl.x, row0 = sl.y, nrows = sl.z;
+  const int s2 = 2 * P.s[f], u2 = 2 * front_u(P, f);
+  const int64_t ld = s2 + u2;
+  const int tid = threadIdx.x;
+  const int64_t g0 = 2 * (int64_t)P.first[f];
+  for (int i = tid; i < s2; i += FWD_ROWS) y1[i] = rhs[g0 + i];
+  yt[tid] = 0.0;
+  __syncthreads();
+  for (int q = P.cptr[f]; q < P.cptr[f + 1]; ++q) {
+    const int ch = P.child[q];
+    const int uc2 = 2 * front_u(P, ch);
+    const int32_t* cm = P.cmap + P.cmap_ptr[ch];
+    const double* uv = upd + P.uoff[ch];
+    for (int k = tid; k < uc2; k += FWD_ROWS) {
+      const int t = 2 * cm[k >> 1] + (k & 1);
+      if (t < s2) y1[t] += uv[k];
+      else if (t >= row0 && t < row0 + nrows) yt[t - row0] += uv[k];
+    }
+    __syncthreads();
+  }
+  if (tid < nrows) {
+    const int row = row0 + tid;
+    const double* M = P.pool + P.foff[f] + row;
+    double acc0 = 0.0, acc1 = 0.0;
+    int k = 0;
+    for (; k + 1 < s2; k += 2) {
+      acc0 = fma(M[(int64_t)k * ld], y1[k], acc0);
+      acc1 = fma(M[(int64_t)(k + 1) * ld], y1[k + 1], acc1);
+    }
+    if (k < s2) acc0 = fma(M[(int64_t)k * ld], y1[k], acc0);
+    const double acc = acc0 + acc1;
+    if (row < s2) z[g0 + row] = acc;
+    else upd[P.uoff[f] + (row - s2)] = yt[tid] - acc;
+  }
+}
+
+// ---- backward sweep: one CTA per (front, slab of columns), one warp per column --------------------------
+__global__ void __launch_bounds__(256) backward_kernel(const int4* __restrict__ slabs, PlanView P, double* __restrict__ x) {
+  constexpr int CH = 2048;
+  __shared__ double x2[CH];
+  const int4 sl = slabs[blockIdx.x];
+  const int f = sl.x, col0 = sl.y, ncols = sl.z;
+  const int s2 = 2 * P.s[f], u2 = 2 * front_u(P, f);
+  const int64_t ld = s2 + u2;
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int64_t g0 = 2 * (int64_t)P.first[f];
+  const int32_t* st = P.strct + P.sptr[f];
+  const double* W = P.pool + P.foff[f] + s2;   // F21new(j, i) at i*ld + j
+  double acc[BWD_COLS / 8];
+#pragma unroll
+  for (int c = 0; c < BWD_COLS / 8; ++c) acc[c] = 0.0;
+  for (int j0 = 0; j0 < u2; j0 += CH) {
+    const int len = min(CH, u2 - j0);
+    __syncthreads();
+    for (int j = tid; j < len; j += 256) { const int jj = j0 + j; x2[j] = x[2 * (int64_t)st[jj >> 1] + (jj & 1)]; }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < BWD_COLS / 8; ++c) {
+      const int colr = warp + 8 * c;
+      if (colr < ncols) {
+        const double* wc = W + (int64_t)(col0 + colr) * ld + j0;
+        double a = 0.0;
+        for (int j = lane; j < len; j += 32) a = fma(wc[j], x2[j], a);
+        acc[c] += a;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < BWD_COLS / 8; ++c) {
+    double a = acc[c];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) a += __shfl_down_sync(0xffffffffu, a, off);
+    const int colr = warp + 8 * c;
+    if (lane == 0 && colr < ncols) x[g0 + col0 + colr] -= a;
+  }
+}
+
+PlanView view(const DevPlan& D) {
+  PlanView v;
+  v.first = D.first.p; v.s = D.s.p; v.sptr = D.sptr.p; v.strct = D.strct.p; v.cptr = D.cptr.p; v.child = D.child.p;
+  v.cmap_ptr = D.cmap_ptr.p; v.cmap = D.cmap.p; v.uoff = D.uoff.p; v.foff = D.foff.p; v.pool = D.pool.p;
+  return v;
+}
+
+size_t invert_smem(int m) { return ((size_t)(m | 1) * m + 2 * (size_t)m) * sizeof(double); }
+
+}  // namespace
+
+void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
+  if (2 * P.max_s > MAX_PIV) throw StatusError(PLFEM_ERR_INVALID, "max_sn_nodes must be <= 64");
+  D.n = P.n; D.nfronts = P.nfronts; D.nlevels = P.nlevels;
+  D.first.upload(ctx, P.first); D.s.upload(ctx, P.s); D.sptr.upload(ctx, P.sptr); D.strct.upload(ctx, P.strct);
+  D.sn_of.upload(ctx, P.sn_of); D.parent.upload(ctx, P.parent); D.cptr.upload(ctx, P.cptr); D.child.upload(ctx, P.child);
+  D.cmap_ptr.upload(ctx, P.cmap_ptr); D.cmap.upload(ctx, P.cmap); D.lfront.upload(ctx, P.lfront);
+  D.foff.upload(ctx, P.foff);
+  D.lptr = P.lptr;
+  std::vector<int32_t> uoff(P.nfronts + 1, 0);
+  for (int f = 0; f < P.nfronts; ++f) uoff[f + 1] = uoff[f] + 2 * (P.sptr[f + 1] - P.sptr[f]);
+  D.upd_len = uoff[P.nfronts];
+  D.uoff.upload(ctx, uoff);
+  D.upd.alloc(ctx, std::max<int64_t>(D.upd_len, 1));
+
+  std::vector<int4> wt, stl, ea, fw, bw;
+  D.w_ptr.assign(P.nlevels + 1, 0); D.s_ptr = D.ea_ptr = D.fwd_ptr = D.bwd_ptr = D.w_ptr;
+  D.lmax_m.assign(P.nlevels, 0);
+  for (int l = 0; l < P.nlevels; ++l) {
+    for (int q = P.lptr[l]; q < P.lptr[l + 1]; ++q) {
+      const int f = P.lfront[q];
+      const int s = P.s[f], u = P.sptr[f + 1] - P.sptr[f];
+      const int s2 = 2 * s, u2 = 2 * u, nf = s + u;
+      D.lmax_m[l] = std::max(D.lmax_m[l], s2);
+      for (int j0 = 0; j0 < u2; j0 += GT)
+        for (int i0 = 0; i0 < s2; i0 += GT) wt.push_back(make_int4(f, j0, i0, 0));
+      for (int b0 = 0; b0 < u2; b0 += GT)
+        for (int a0 = 0; a0 < u2; a0 += GT) stl.push_back(make_int4(f, a0, b0, 0));
+      if (P.cptr[f + 1] > P.cptr[f])
+        for (int c0 = 0; c0 < nf; c0 += EA_COLS) ea.push_back(make_int4(f, c0, std::min(c0 + EA_COLS, nf), 0));
+      for (int r0 = 0; r0 < s2 + u2; r0 += FWD_ROWS) fw.push_back(make_int4(f, r0, std::min(FWD_ROWS, s2 + u2 - r0), 0));
+      if (u2 > 0)
+        for (int c0 = 0; c0 < s2; c0 += BWD_COLS) bw.push_back(make_int4(f, c0, std::min(BWD_COLS, s2 - c0), 0));
+    }
+    D.w_ptr[l + 1] = (int32_t)wt.size(); D.s_ptr[l + 1] = (int32_t)stl.size(); D.ea_ptr[l + 1] = (int32_t)ea.size();
+    D.fwd_ptr[l + 1] = (int32_t)fw.size(); D.bwd_ptr[l + 1] = (int32_t)bw.size();
+  }
+  D.w_tiles.upload(ctx, wt); D.s_tiles.upload(ctx, stl); D.ea_slabs.upload(ctx, ea);
+  D.fwd_slabs.upload(ctx, fw); D.bwd_slabs.upload(ctx, bw);
+  D.pool.alloc(ctx, (size_t)P.foff[P.nfronts]);
+  D.status.alloc(ctx, 4);
+  // the host vectors above are pageable: make sure the copies are done before they go out of scope
+  PLFEM_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+void launch_front_load(plfem_ctx* ctx, const DevPattern& pat, const DevPlan& D, const double* d_vals, double sigma) {
+  PLFEM_CUDA(cudaMemsetAsync(D.pool.p, 0, D.pool.n * sizeof(double), ctx->stream));
+  PLFEM_CUDA(cudaMemsetAsync(D.status.p, 0, 4 * sizeof(int32_t), ctx->stream));
+  const int bs = 256;
+  front_load_kernel<<<(unsigned)((pat.nnz + bs - 1) / bs), bs, 0, ctx->stream>>>(pat.nnz, pat.rowidx.p, pat.col.p,
+                                                                                 D.sn_of.p, view(D), d_vals, sigma);
+  PLFEM_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
+void run_factorization(plfem_ctx* ctx, const DevPlan& D) {
+  static bool attr_set[64] = {};
+  if (!(ctx->device < 64 && attr_set[ctx->device])) {
+    PLFEM_CUDA(cudaFuncSetAttribute(invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)invert_smem(MAX_PIV)));
+    if (ctx->device < 64) attr_set[ctx->device] = true;
+  }
+  const PlanView v = view(D);
+  for (int l = 0; l < D.nlevels; ++l) {
+    const int nea = D.ea_ptr[l + 1] - D.ea_ptr[l];
+    if (nea > 0) {
+      extend_add_kernel<<<nea, 256, 0, ctx->stream>>>(D.ea_slabs.p + D.ea_ptr[l], v);
+      ctx->launches++;
+    }
+    const int nfl = D.lptr[l + 1] - D.lptr[l];
+    invert_kernel<<<nfl, 256, invert_smem(D.lmax_m[l]), ctx->stream>>>(D.lfront.p + D.lptr[l], v, D.status.p);
+    ctx->launches++;
+    const int nw = D.w_ptr[l + 1] - D.w_ptr[l];
+    if (nw > 0) {
+      gemm_w_kernel<<<nw, 256, 0, ctx->stream>>>(D.w_tiles.p + D.w_ptr[l], v);
+      ctx->launches++;
+    }
+    const int ns = D.s_ptr[l + 1] - D.s_ptr[l];
+    if (ns > 0) {
+      gemm_schur_kernel<<<ns, 256, 0, ctx->stream>>>(D.s_tiles.p + D.s_ptr[l], v);
+      ctx->launches++;
+    }
+  }
+  PLFEM_CUDA(cudaGetLastError());
+}
+
+void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x) {
+  const PlanView v = view(D);
+  for (int l = 0; l < D.nlevels; ++l) {
+    const int nsl = D.fwd_ptr[l + 1] - D.fwd_ptr[l];
+    forward_kernel<<<nsl, FWD_ROWS, 0, ctx->stream>>>(D.fwd_slabs.p + D.fwd_ptr[l], v, b, x, D.upd.p);
+    ctx->launches++;
+  }
+  for (int l = D.nlevels - 1; l >= 0; --l) {
+    const int nsl = D.bwd_ptr[l + 1] - D.bwd_ptr[l];
+    if (nsl == 0) continue;
+    backward_kernel<<<nsl, 256, 0, ctx->stream>>>(D.bwd_slabs.p + D.bwd_ptr[l], v, x);
+    ctx->launches++;
+  }
+  PLFEM_CUDA(cudaGetLastError());
+}
+
+}  // namespace plfem

@@ -1,0 +1,404 @@
+// Host-side symbolic analysis: DOF numbering, sparsity pattern, nested dissection, front plan.
+// See symbolic.h for what each piece replaces in the reference.
+#include "symbolic.h"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <stdexcept>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
+namespace plfem {
+
+// ------------------------------------------------------------------------------------------------
+// DOF tables (scikit-fem ElementTriP2 numbering)
+// ------------------------------------------------------------------------------------------------
+void build_dof_tables(const double* p, const int64_t* t, int64_t V, int64_t T, DofTables& d) {
+  d.V = V; d.T = T;
+  const double* px = p;
+  const double* py = p + V;
+  const int64_t* t0 = t; const int64_t* t1 = t + T; const int64_t* t2 = t + 2 * T;
+  for (int64_t e = 0; e < T; ++e)
+    for (const int64_t* tr : {t0, t1, t2})
+      if (tr[e] < 0 || tr[e] >= V) throw std::runtime_error("mesh.t holds a vertex index outside [0, V)");
+
+  // facets: local edges (0,1),(1,2),(0,2); bucket by min vertex, sort each bucket by max vertex
+  static const int LE[3][2] = {{0, 1}, {1, 2}, {0, 2}};
+  std::vector<int32_t> emin(3 * T), emax(3 * T);
+  std::vector<int32_t> cnt(V + 1, 0);
+  for (int64_t e = 0; e < T; ++e) {
+    const int64_t v[3] = {t0[e], t1[e], t2[e]};
+    for (int k = 0; k < 3; ++k) {
+      int64_t a = v[LE[k][0]], b = v[LE[k][1]];
+      if (a > b) std::swap(a, b);
+      emin[3 * e + k] = (int32_t)a; emax[3 * e + k] = (int32_t)b;
+      cnt[a + 1]++;
+    }
+  }
+  for (int64_t v = 0; v < V; ++v) cnt[v + 1] += cnt[v];
+  std::vector<int32_t> slot(3 * T);           // half-edge ids grouped by min vertex
+  {
+    std::vector<int32_t> fill(cnt.begin(), cnt.end() - 1);
+    for (int64_t h = 0; h < 3 * T; ++h) slot[fill[emin[h]]++] = (int32_t)h;
+  }
+  d.t2f.assign(3 * T, -1);
+  d.facets.clear(); d.facets.reserve(3 * T + 2 * V);
+  std::vector<int32_t> fcount; fcount.reserve(3 * T / 2 + V);
+  for (int64_t v = 0; v < V; ++v) {
+    int32_t b = cnt[v], e = cnt[v + 1];
+    std::sort(slot.begin() + b, slot.begin() + e,
+              [&](int32_t h1, int32_t h2) { return emax[h1] < emax[h2] || (emax[h1] == emax[h2] && h1 < h2); });
+    int32_t last = -1;
+    for (int32_t i = b; i < e; ++i) {
+      int32_t h = slot[i];
+      if (emax[h] != last) {
+        last = emax[h];
+        d.facets.push_back((int32_t)v); d.facets.push_back(last);
+        fcount.push_back(0);
+      }
+      int32_t f = (int32_t)fcount.size() - 1;
+      fcount[f]++;
+      // slot h = 3*e + k  ->  element-major t2f
+      d.t2f[h] = f;
+    }
+  }
+  d.E = (int64_t)fcount.size();
+  d.N = V + d.E;
+
+  d.edofs.resize(6 * T);
+  for (int64_t e = 0; e < T; ++e) {
+    d.edofs[6 * e + 0] = (int32_t)t0[e]; d.edofs[6 * e + 1] = (int32_t)t1[e]; d.edofs[6 * e + 2] = (int32_t)t2[e];
+    for (int k = 0; k < 3; ++k) d.edofs[6 * e + 3 + k] = (int32_t)(V + d.t2f[3 * e + k]);
+  }
+
+  // boundary DOFs: both vertices and the facet DOF of every facet owned by exactly one element
+  std::vector<uint8_t> isb(d.N, 0);
+  for (int64_t f = 0; f < d.E; ++f)
+    if (fcount[f] == 1) { isb[d.facets[2 * f]] = 1; isb[d.facets[2 * f + 1]] = 1; isb[V + f] = 1; }
+  d.boundary.clear(); d.interior.clear();
+  for (int64_t i = 0; i < d.N; ++i) (isb[i] ? d.boundary : d.interior).push_back((int32_t)i);
+
+  // DOF locations: affine image of the reference nodes; loop order (local node outer, element
+  // inner) makes later writes win exactly like the fancy-index assignment it restates.
+  static const double RX[6] = {0.0, 1.0, 0.0, 0.5, 0.5, 0.0};
+  static const double RY[6] = {0.0, 0.0, 1.0, 0.0, 0.5, 0.5};
+  d.doflocs.assign(2 * d.N, 0.0);
+  d.n_degenerate = 0;
+  for (int k = 0; k < 6; ++k)
+    for (int64_t e = 0; e < T; ++e) {
+      const double a00 = px[t1[e]] - px[t0[e]], a01 = px[t2[e]] - px[t0[e]];
+      const double a10 = py[t1[e]] - py[t0[e]], a11 = py[t2[e]] - py[t0[e]];
+      const int32_t g = d.edofs[6 * e + k];
+      d.doflocs[g] = a00 * RX[k] + a01 * RY[k] + px[t0[e]];
+      d.doflocs[d.N + g] = a10 * RX[k] + a11 * RY[k] + py[t0[e]];
+      if (k == 0 && a00 * a11 - a01 * a10 == 0.0) d.n_degenerate++;
+    }
+
+  // node -> elements (ascending element id)
+  d.n2e_ptr.assign(d.N + 1, 0);
+  for (int64_t i = 0; i < 6 * T; ++i) d.n2e_ptr[d.edofs[i] + 1]++;
+  for (int64_t i = 0; i < d.N; ++i) d.n2e_ptr[i + 1] += d.n2e_ptr[i];
+  d.n2e.resize(6 * T);
+  {
+    std::vector<int32_t> fill(d.n2e_ptr.begin(), d.n2e_ptr.end() - 1);
+    for (int64_t e = 0; e < T; ++e)
+      for (int k = 0; k < 6; ++k) d.n2e[fill[d.edofs[6 * e + k]]++] = (int32_t)e;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sparsity pattern in an arbitrary renumbering
+// ------------------------------------------------------------------------------------------------
+void build_pattern(const DofTables& d, const std::vector<int32_t>& new_of_old, int32_t n_new, Pattern& out) {
+  out.n = n_new;
+  out.new_of_old = new_of_old;
+  out.old_of_new.assign(n_new, -1);
+  for (int64_t o = 0; o < d.N; ++o)
+    if (new_of_old[o] >= 0) out.old_of_new[new_of_old[o]] = (int32_t)o;
+  out.rowptr.assign(n_new + 1, 0);
+  out.col.clear();
+  out.col.reserve((size_t)n_new * 12);
+  std::vector<int32_t> stamp(n_new, -1);
+  for (int32_t r = 0; r < n_new; ++r) {
+    const int32_t o = out.old_of_new[r];
+    const size_t b = out.col.size();
+    for (int32_t q = d.n2e_ptr[o]; q < d.n2e_ptr[o + 1]; ++q) {
+      const int32_t* ed = &d.edofs[6 * (int64_t)d.n2e[q]];
+      for (int k = 0; k < 6; ++k) {
+        const int32_t c = new_of_old[ed[k]];
+        if (c >= 0 && stamp[c] != r) { stamp[c] = r; out.col.push_back(c); }
+      }
+    }
+    std::sort(out.col.begin() + b, out.col.end());
+    out.rowptr[r + 1] = (int32_t)out.col.size();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Nested dissection + front plan
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct TreeNode {
+  std::vector<int32_t> own;       // interior indices, elimination order inside the node
+  std::vector<int32_t> children;  // tree node ids
+};
+
+struct Dissector {
+  static constexpr int ND = 4;  // projection directions: x, y, x+y, x-y
+  const Pattern& adj;
+  const double* x;
+  const double* y;
+  const SymbolicOptions& opt;
+  std::vector<TreeNode> nodes;
+  std::vector<int32_t> side;   // per node: stamp of the subset/half it currently belongs to
+  std::vector<int32_t> rank;   // per node: position in the direction list being examined
+  std::vector<uint8_t> insep;  // per node: chosen as separator in the current call
+  int32_t stamp = 0;
+  std::vector<int32_t> lists[ND];  // the node set of the current call, sorted along each direction
+  std::vector<int32_t> tmp, dl, dr;
+
+  Dissector(const Pattern& a, const double* x_, const double* y_, const SymbolicOptions& o)
+      : adj(a), x(x_), y(y_), opt(o), side(a.n, -1), rank(a.n, 0), insep(a.n, 0) {
+    const int32_t n = a.n;
+    std::vector<std::pair<double, int32_t>> kv(n);
+    for (int d = 0; d < ND; ++d) {
+      for (int32_t v = 0; v < n; ++v) kv[v] = {proj(d, v), v};
+      std::sort(kv.begin(), kv.end());
+      lists[d].resize(n);
+      for (int32_t r = 0; r < n; ++r) lists[d][r] = kv[r].second;
+    }
+    tmp.resize(n);
+  }
+
+  double proj(int d, int32_t v) const {
+    switch (d) { case 0: return x[v]; case 1: return y[v]; case 2: return x[v] + y[v]; default: return x[v] - y[v]; }
+  }
+
+  // Dissect the node set stored (in ND different orders) at lists[d][off .. off+n).
+  // Appends the ids of the tree nodes heading the resulting sub-forest to `heads`.
+  void dissect(int32_t off, int32_t n, std::vector<int32_t>& heads) {
+    if (n == 0) return;
+    int32_t* L0 = lists[0].data() + off;
+    if (n <= opt.leaf_nodes) {
+      TreeNode leaf; leaf.own.assign(L0, L0 + n);
+      nodes.push_back(std::move(leaf));
+      heads.push_back((int32_t)nodes.size() - 1);
+      return;
+    }
+    // Candidate cuts: ND directions x every split position in the middle 40%.  Along a direction a
+    // node of rank r is in the left-boundary separator of split h iff r < h <= (highest neighbour
+    // rank), so the separator size for EVERY h comes from one difference array.  Pick the
+    // (direction, h, side) with the smallest separator, mildly penalising imbalance.
+    const int32_t cur = ++stamp;
+    for (int32_t i = 0; i < n; ++i) side[L0[i]] = cur;
+    const int ndir = (n >= opt.search_min_nodes) ? ND : 2;
+    double best_cost = 1e300; int best_dir = 0; int32_t best_h = n / 2; bool best_left = true;
+    const int32_t h0 = std::max<int32_t>(1, (int32_t)(0.3 * n)), h1 = std::min<int32_t>(n - 1, (int32_t)(0.7 * n));
+    for (int d = 0; d < ndir; ++d) {
+      const int32_t* Ld = lists[d].data() + off;
+      for (int32_t r = 0; r < n; ++r) rank[Ld[r]] = r;
+      dl.assign(n + 2, 0); dr.assign(n + 2, 0);
+      for (int32_t r = 0; r < n; ++r) {
+        const int32_t v = Ld[r];
+        int32_t hi = r, lo = r;
+        for (int32_t q = adj.rowptr[v]; q < adj.rowptr[v + 1]; ++q) {
+          const int32_t w = adj.col[q];
+          if (side[w] != cur) continue;
+          const int32_t rw = rank[w];
+          hi = std::max(hi, rw); lo = std::min(lo, rw);
+        }
+        dl[r + 1]++; dl[hi + 1]--;   // left-boundary member for h in (r, hi]
+        dr[lo + 1]++; dr[r + 1]--;   // right-boundary member for h in (lo, r]
+      }
+      int32_t cl = 0, cr = 0;
+      for (int32_t h = 1; h <= h1; ++h) {
+        cl += dl[h]; cr += dr[h];
+        if (h < h0) continue;
+        const double imb = std::fabs(2.0 * h / n - 1.0);
+        const double cost = (std::min(cl, cr) + 1.0) * (1.0 + 1.5 * imb);
+        if (cost < best_cost) { best_cost = cost; best_dir = d; best_h = h; best_left = cl <= cr; }
+      }
+    }
+    const int32_t h = best_h;
+    const int32_t* Lb = lists[best_dir].data() + off;
+    const int32_t sl = ++stamp, sr = ++stamp;
+    for (int32_t i = 0; i < h; ++i) side[Lb[i]] = sl;
+    for (int32_t i = h; i < n; ++i) side[Lb[i]] = sr;
+    std::vector<int32_t> sep;
+    {
+      const int32_t b = best_left ? 0 : h, e = best_left ? h : n, other = best_left ? sr : sl;
+      for (int32_t i = b; i < e; ++i) {
+        const int32_t v = Lb[i];
+        for (int32_t q = adj.rowptr[v]; q < adj.rowptr[v + 1]; ++q)
+          if (side[adj.col[q]] == other) { sep.push_back(v); insep[v] = 1; break; }
+      }
+    }
+    // stable three-way partition of every direction list: [left | right | separator]
+    int32_t nl = 0, nr = 0;
+    for (int d = 0; d < ND; ++d) {
+      int32_t* Ld = lists[d].data() + off;
+      int32_t a = 0, b = 0;
+      for (int32_t i = 0; i < n; ++i) {
+        const int32_t v = Ld[i];
+        if (insep[v]) continue;
+        if (side[v] == sl) Ld[a++] = v; else tmp[b++] = v;
+      }
+      std::copy(tmp.begin(), tmp.begin() + b, Ld + a);
+      nl = a; nr = b;
+    }
+    for (int32_t v : sep) { insep[v] = 0; side[v] = -1; }
+    std::vector<int32_t> kids;
+    dissect(off, nl, kids);
+    dissect(off + nl, nr, kids);
+    if (sep.empty()) {  // disconnected halves: no front of its own, children go up
+      heads.insert(heads.end(), kids.begin(), kids.end());
+      return;
+    }
+    // order the separator along the cut so that chain links are spatially compact
+    const int od = (best_dir == 0) ? 1 : (best_dir == 1 ? 0 : (best_dir == 2 ? 3 : 2));
+    std::sort(sep.begin(), sep.end(), [&](int32_t a, int32_t b) {
+      const double pa = proj(od, a), pb = proj(od, b);
+      return pa < pb || (pa == pb && a < b);
+    });
+    const int32_t ns = (int32_t)sep.size();
+    const int32_t nchunks = (ns + opt.max_sn_nodes - 1) / opt.max_sn_nodes;
+    int32_t prev = -1, pos = 0;
+    for (int32_t k = 0; k < nchunks; ++k) {
+      const int32_t len = ns / nchunks + (k < ns % nchunks ? 1 : 0);
+      TreeNode tn; tn.own.assign(sep.begin() + pos, sep.begin() + pos + len);
+      pos += len;
+      if (k == 0) tn.children = kids; else tn.children = {prev};
+      nodes.push_back(std::move(tn));
+      prev = (int32_t)nodes.size() - 1;
+    }
+    heads.push_back(prev);
+  }
+};
+
+}  // namespace
+
+void build_front_plan(const Pattern& adj, const double* x, const double* y, const SymbolicOptions& opt, FrontPlan& P) {
+  const int32_t n = adj.n;
+  P = FrontPlan();
+  P.n = n;
+  static const bool timing = std::getenv("PLFEM_TIMING") != nullptr;
+  auto clk = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double tA = clk();
+  Dissector D(adj, x, y, opt);
+  const double tB = clk();
+  std::vector<int32_t> roots;
+  D.dissect(0, n, roots);
+  const double tC = clk();
+
+  // post-order numbering of tree nodes -> fronts
+  const int32_t nt = (int32_t)D.nodes.size();
+  std::vector<int32_t> front_of(nt, -1), order; order.reserve(nt);
+  {
+    std::vector<std::pair<int32_t, size_t>> st;
+    for (int32_t r : roots) {
+      st.emplace_back(r, 0);
+      while (!st.empty()) {
+        auto& [v, k] = st.back();
+        if (k < D.nodes[v].children.size()) { int32_t ch = D.nodes[v].children[k++]; st.emplace_back(ch, 0); }
+        else { front_of[v] = (int32_t)order.size(); order.push_back(v); st.pop_back(); }
+      }
+    }
+  }
+  const int32_t nf = (int32_t)order.size();
+  P.nfronts = nf;
+  P.first.resize(nf); P.s.resize(nf); P.parent.assign(nf, -1); P.level.assign(nf, 0);
+  P.perm.resize(n); P.sn_of.resize(n);
+  std::vector<int32_t> new_of(n, -1);
+  int32_t next = 0;
+  for (int32_t f = 0; f < nf; ++f) {
+    const TreeNode& tn = D.nodes[order[f]];
+    P.first[f] = next; P.s[f] = (int32_t)tn.own.size();
+    for (int32_t v : tn.own) { P.perm[next] = v; new_of[v] = next; P.sn_of[next] = f; ++next; }
+    for (int32_t ch : tn.children) P.parent[front_of[ch]] = f;
+  }
+  if (next != n) throw std::runtime_error("nested dissection lost nodes");
+  P.cptr.assign(nf + 1, 0);
+  for (int32_t f = 0; f < nf; ++f) if (P.parent[f] >= 0) P.cptr[P.parent[f] + 1]++;
+  for (int32_t f = 0; f < nf; ++f) P.cptr[f + 1] += P.cptr[f];
+  P.child.resize(P.cptr[nf]);
+  {
+    std::vector<int32_t> fill(P.cptr.begin(), P.cptr.end() - 1);
+    for (int32_t f = 0; f < nf; ++f) if (P.parent[f] >= 0) P.child[fill[P.parent[f]]++] = f;
+  }
+
+  // update sets, bottom-up (post-order guarantees children first)
+  P.sptr.assign(nf + 1, 0);
+  P.strct.clear(); P.strct.reserve((size_t)n * 8);
+  std::vector<int32_t> mark(n, -1);
+  for (int32_t f = 0; f < nf; ++f) {
+    const int32_t last = P.first[f] + P.s[f] - 1;
+    const size_t b = P.strct.size();
+    for (int32_t r = P.first[f]; r <= last; ++r) {
+      const int32_t v = P.perm[r];
+      for (int32_t q = adj.rowptr[v]; q < adj.rowptr[v + 1]; ++q) {
+        const int32_t c = new_of[adj.col[q]];
+        if (c > last && mark[c] != f) { mark[c] = f; P.strct.push_back(c); }
+      }
+    }
+    for (int32_t q = P.cptr[f]; q < P.cptr[f + 1]; ++q) {
+      const int32_t ch = P.child[q];
+      for (int32_t k = P.sptr[ch]; k < P.sptr[ch + 1]; ++k) {
+        const int32_t c = P.strct[k];
+        if (c > last && mark[c] != f) { mark[c] = f; P.strct.push_back(c); }
+        else if (c < P.first[f]) throw std::runtime_error("front plan: child update set escapes its parent");
+      }
+      P.level[f] = std::max(P.level[f], P.level[ch] + 1);
+    }
+    std::sort(P.strct.begin() + b, P.strct.end());
+    P.sptr[f + 1] = (int32_t)P.strct.size();
+    if (P.parent[f] < 0 && P.sptr[f + 1] != (int32_t)b) throw std::runtime_error("front plan: root front has an update set");
+  }
+
+  // child -> parent position maps
+  P.cmap_ptr.assign(nf + 1, 0);
+  for (int32_t f = 0; f < nf; ++f) P.cmap_ptr[f + 1] = P.cmap_ptr[f] + (P.parent[f] >= 0 ? P.sptr[f + 1] - P.sptr[f] : 0);
+  P.cmap.resize(P.cmap_ptr[nf]);
+  for (int32_t f = 0; f < nf; ++f) {
+    const int32_t pa = P.parent[f];
+    if (pa < 0) continue;
+    const int32_t pf = P.first[pa], ps = P.s[pa];
+    const int32_t* pst = P.strct.data() + P.sptr[pa];
+    const int32_t pu = P.sptr[pa + 1] - P.sptr[pa];
+    int32_t w = 0;
+    for (int32_t k = P.sptr[f], o = P.cmap_ptr[f]; k < P.sptr[f + 1]; ++k, ++o) {
+      const int32_t c = P.strct[k];
+      if (c < pf + ps) { P.cmap[o] = c - pf; continue; }
+      while (w < pu && pst[w] < c) ++w;
+      if (w >= pu || pst[w] != c) throw std::runtime_error("front plan: child index missing from parent");
+      P.cmap[o] = ps + w;
+    }
+  }
+
+  const double tD = clk();
+  if (timing) fprintf(stderr, "[plfem] front plan: presort %.2f ms, dissect %.2f ms, fronts/maps %.2f ms\n", tB - tA, tC - tB, tD - tC);
+  // storage offsets, statistics, level schedule
+  P.foff.assign(nf + 1, 0);
+  for (int32_t f = 0; f < nf; ++f) {
+    const int64_t s2 = 2 * (int64_t)P.s[f], u2 = 2 * (int64_t)(P.sptr[f + 1] - P.sptr[f]);
+    const int64_t m = s2 + u2;
+    P.foff[f + 1] = P.foff[f] + m * m;
+    P.factor_entries += s2 * s2 + s2 * u2;
+    P.factor_flops += 2.0 * s2 * s2 * s2 + 2.0 * s2 * s2 * u2 + 2.0 * s2 * u2 * u2;
+    P.max_front = std::max<int32_t>(P.max_front, (int32_t)(m / 2));
+    P.max_s = std::max(P.max_s, P.s[f]);
+    P.nlevels = std::max(P.nlevels, P.level[f] + 1);
+  }
+  P.lptr.assign(P.nlevels + 1, 0);
+  for (int32_t f = 0; f < nf; ++f) P.lptr[P.level[f] + 1]++;
+  for (int32_t l = 0; l < P.nlevels; ++l) P.lptr[l + 1] += P.lptr[l];
+  P.lfront.resize(nf);
+  {
+    std::vector<int32_t> fill(P.lptr.begin(), P.lptr.end() - 1);
+    for (int32_t f = 0; f < nf; ++f) P.lfront[fill[P.level[f]]++] = f;
+  }
+}
+
+}  // namespace plfem

@@ -1,0 +1,140 @@
+// Dense symmetric eigensolver for the projected Lanczos matrix (<= ~200 x 200), host side.
+// Householder tridiagonalisation followed by implicit QL — the classic EISPACK tred2/tql2 pair.
+// ARPACK does the same job with LAPACK dsteqr inside dseigt (scipy eigsh, solver_fem.py:197).
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "common.h"
+
+namespace plfem {
+
+// a: n*n column-major symmetric matrix on entry; on exit its columns are the eigenvectors.
+// w: eigenvalues, ascending.
+void symmetric_eigen(int n, std::vector<double>& a, std::vector<double>& w) {
+  auto V = [&](int i, int j) -> double& { return a[(size_t)j * n + i]; };
+  std::vector<double> d(n), e(n);
+  for (int j = 0; j < n; ++j) d[j] = V(n - 1, j);
+
+  // Householder reduction to tridiagonal form
+  for (int i = n - 1; i > 0; --i) {
+    double scale = 0.0, h = 0.0;
+    for (int k = 0; k < i; ++k) scale += std::fabs(d[k]);
+    if (scale == 0.0) {
+      e[i] = d[i - 1];
+      for (int j = 0; j < i; ++j) { d[j] = V(i - 1, j); V(i, j) = 0.0; V(j, i) = 0.0; }
+    } else {
+      for (int k = 0; k < i; ++k) { d[k] /= scale; h += d[k] * d[k]; }
+      double f = d[i - 1];
+      double g = std::sqrt(h);
+      if (f > 0) g = -g;
+      e[i] = scale * g;
+      h -= f * g;
+      d[i - 1] = f - g;
+      for (int j = 0; j < i; ++j) e[j] = 0.0;
+      for (int j = 0; j < i; ++j) {
+        f = d[j];
+        V(j, i) = f;
+        g = e[j] + V(j, j) * f;
+        for (int k = j + 1; k <= i - 1; ++k) { g += V(k, j) * d[k]; e[k] += V(k, j) * f; }
+        e[j] = g;
+      }
+      f = 0.0;
+      for (int j = 0; j < i; ++j) { e[j] /= h; f += e[j] * d[j]; }
+      const double hh = f / (h + h);
+      for (int j = 0; j < i; ++j) e[j] -= hh * d[j];
+      for (int j = 0; j < i; ++j) {
+        f = d[j]; g = e[j];
+        for (int k = j; k <= i - 1; ++k) V(k, j) -= (f * e[k] + g * d[k]);
+        d[j] = V(i - 1, j);
+        V(i, j) = 0.0;
+      }
+    }
+    d[i] = h;
+  }
+  // accumulate transformations
+  for (int i = 0; i < n - 1; ++i) {
+    V(n - 1, i) = V(i, i);
+    V(i, i) = 1.0;
+    const double h = d[i + 1];
+    if (h != 0.0) {
+      for (int k = 0; k <= i; ++k) d[k] = V(k, i + 1) / h;
+      for (int j = 0; j <= i; ++j) {
+        double g = 0.0;
+        for (int k = 0; k <= i; ++k) g += V(k, i + 1) * V(k, j);
+        for (int k = 0; k <= i; ++k) V(k, j) -= g * d[k];
+      }
+    }
+    for (int k = 0; k <= i; ++k) V(k, i + 1) = 0.0;
+  }
+  for (int j = 0; j < n; ++j) { d[j] = V(n - 1, j); V(n - 1, j) = 0.0; }
+  V(n - 1, n - 1) = 1.0;
+  e[0] = 0.0;
+
+  // implicit QL on the tridiagonal
+  for (int i = 1; i < n; ++i) e[i - 1] = e[i];
+  e[n - 1] = 0.0;
+  double f = 0.0, tst1 = 0.0;
+  const double eps = std::pow(2.0, -52.0);
+  for (int l = 0; l < n; ++l) {
+    tst1 = std::max(tst1, std::fabs(d[l]) + std::fabs(e[l]));
+    int m = l;
+    while (m < n) {
+      if (std::fabs(e[m]) <= eps * tst1) break;
+      ++m;
+    }
+    if (m > l) {
+      int iter = 0;
+      do {
+        ++iter;
+        double g = d[l];
+        double p = (d[l + 1] - g) / (2.0 * e[l]);
+        double r = std::hypot(p, 1.0);
+        if (p < 0) r = -r;
+        d[l] = e[l] / (p + r);
+        d[l + 1] = e[l] * (p + r);
+        const double dl1 = d[l + 1];
+        double h = g - d[l];
+        for (int i = l + 2; i < n; ++i) d[i] -= h;
+        f += h;
+        p = d[m];
+        double c = 1.0, c2 = c, c3 = c;
+        const double el1 = e[l + 1];
+        double s = 0.0, s2 = 0.0;
+        for (int i = m - 1; i >= l; --i) {
+          c3 = c2; c2 = c; s2 = s;
+          g = c * e[i];
+          h = c * p;
+          r = std::hypot(p, e[i]);
+          e[i + 1] = s * r;
+          s = e[i] / r;
+          c = p / r;
+          p = c * d[i] - s * g;
+          d[i + 1] = h + s * (c * g + s * d[i]);
+          for (int k = 0; k < n; ++k) {
+            h = V(k, i + 1);
+            V(k, i + 1) = s * V(k, i) + c * h;
+            V(k, i) = c * V(k, i) - s * h;
+          }
+        }
+        p = -s * s2 * c3 * el1 * e[l] / dl1;
+        e[l] = s * p;
+        d[l] = c * p;
+      } while (std::fabs(e[l]) > eps * tst1 && iter < 200);
+    }
+    d[l] = d[l] + f;
+    e[l] = 0.0;
+  }
+  // sort ascending
+  for (int i = 0; i < n - 1; ++i) {
+    int k = i; double p = d[i];
+    for (int j = i + 1; j < n; ++j) if (d[j] < p) { k = j; p = d[j]; }
+    if (k != i) {
+      d[k] = d[i]; d[i] = p;
+      for (int j = 0; j < n; ++j) std::swap(V(j, i), V(j, k));
+    }
+  }
+  w = d;
+}
+
+}  // namespace plfem

@@ -160,9 +160,7 @@ class MeshGenerator:
 
     @classmethod
     def _generate_mesh(cls, geometry, refinement: float, config: SimulationConfig):
-        pts = lantern_point_cloud(geometry, refinement)
-        tri = Delaunay(pts.T, qhull_options="QJ Pp")
-        mesh = drop_flat_triangles(MeshTri(tri.points.T, tri.simplices.T))
+        mesh = drop_flat_triangles(cls._delaunay_mesh(geometry, refinement))
         it = 0
         while mesh.p.shape[1] < config.mesh_min_points and it < cls.MAX_REFINEMENT_ITERATIONS:
             mesh = mesh.refined()
@@ -170,6 +168,13 @@ class MeshGenerator:
             if mesh.p.shape[1] > config.mesh_target_points * 2.5:
                 break
         return mesh, None
+
+    @staticmethod
+    def _delaunay_mesh(geometry, refinement: float) -> MeshTri:
+        """The reference's mesh before any clean-up (`mesh.py:232-308`)."""
+        pts = lantern_point_cloud(geometry, refinement)
+        tri = Delaunay(pts.T, qhull_options="QJ Pp")
+        return MeshTri(tri.points.T, tri.simplices.T)
 
     @classmethod
     def clear_cache(cls):

@@ -1,0 +1,126 @@
+"""C-ABI library without a GPU: it loads, exports every declared symbol, and its host logic
+(DOF tables, quadrature points, front plan, restart eigensolver) is right.  No compute calls."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from plfem_b200 import _cabi
+from oracle import fem_oracle as O
+import frontal_reference as FR
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _cabi.load()
+    header = open(os.path.join(ROOT, "include", "plfem.h")).read()
+    declared = sorted(set(re.findall(r"\b(plfem_[a-z_0-9]+)\s*\(", header)))
+    assert declared == sorted(_cabi.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.plfem_version()
+
+
+def test_struct_layouts_match_header():
+    # sizes the C compiler produces for the header's structs (LP64)
+    assert ctypes.sizeof(_cabi.MeshInfo) == 64
+    assert ctypes.sizeof(_cabi.Material) == 64
+    assert ctypes.sizeof(_cabi.SolveOpts) == 56
+    assert ctypes.sizeof(_cabi.SolveStats) == 88
+
+
+def test_product_has_no_cpu_path(small_case):
+    g, mesh = small_case
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_cabi.PlfemError):
+        _cabi.Context(0)
+    from plfem_b200.solver_fem import TrueVectorialMaxwellSolver
+    with pytest.raises(_cabi.PlfemError):
+        TrueVectorialMaxwellSolver(g).solve_vectorial_modes(mesh, 4)
+    # no module of the product imports the oracle
+    pkg = os.path.join(ROOT, "pl-fem-vectoriel_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+(oracle|scipy\.sparse\.linalg)|fem_oracle", src, re.M), fn
+
+
+@pytest.mark.parametrize("case", ["small_case", "cfg1"])
+def test_dof_tables_match_oracle(case, request):
+    g, mesh = request.getfixturevalue(case)
+    pb = _cabi.Problem(mesh, host_only=True)
+    ed, loc, bnd, itr = pb.dofs()
+    B = O.P2Basis(mesh)
+    assert pb.N == B.N
+    assert np.array_equal(ed, B.element_dofs)
+    assert np.array_equal(loc, B.doflocs)                      # bit-identical, incl. "last element wins"
+    assert np.array_equal(bnd, B.boundary_dofs())
+    assert np.array_equal(itr, np.setdiff1d(np.arange(B.N), B.boundary_dofs()))
+    assert np.array_equal(pb.quad_points(), B.x)
+    assert pb.info.n_degenerate == 0
+
+
+def test_degenerate_and_invalid_meshes():
+    from plfem_b200.mesh import MeshTri
+    flat = MeshTri(np.array([[0.0, 1.0, 2.0, 0.0], [0.0, 0.0, 0.0, 1.0]]), np.array([[0, 0], [1, 1], [2, 3]]))
+    pb = _cabi.Problem(flat, host_only=True)
+    assert pb.info.n_degenerate == 1
+
+    class Bad:
+        p = np.zeros((2, 3)); t = np.array([[0], [1], [7]])
+    with pytest.raises(_cabi.PlfemError):
+        _cabi.Problem(Bad, host_only=True)
+
+
+def test_restart_eigensolver():
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 7, 45, 105):
+        a = rng.standard_normal((n, n)); a = a + a.T
+        w, v = _cabi.symeig(a)
+        assert np.allclose(w, np.linalg.eigvalsh(a), atol=1e-12 * max(1, n))
+        assert np.abs(a @ v - v * w).max() < 1e-12 * n and np.abs(v.T @ v - np.eye(n)).max() < 1e-13 * n
+    # arrowhead + tridiagonal, the shape it sees after a thick restart
+    n, p = 45, 22
+    a = np.diag(rng.standard_normal(n))
+    a[p, :p] = a[:p, p] = 1e-4 * rng.standard_normal(p)
+    for j in range(p, n - 1):
+        a[j, j + 1] = a[j + 1, j] = rng.standard_normal()
+    w, v = _cabi.symeig(a)
+    assert np.allclose(w, np.linalg.eigvalsh(a), atol=1e-13) and np.abs(a @ v - v * w).max() < 1e-13
+
+
+@pytest.mark.parametrize("leaf,sn", [(24, 64), (8, 16)])
+def test_front_plan_solves_the_shifted_system(small_case, leaf, sn):
+    """The host-built plan (ordering, update sets, child maps), executed with dense NumPy, must solve
+    (A - sigma B) x = b like SuperLU does."""
+    from scipy.sparse.linalg import splu
+    g, mesh = small_case
+    s = O.interior_system(g, mesh)
+    K = (s["A_int"] - O.sigma_estimate(g) * s["B_int"]).tocsr()
+    pb = _cabi.Problem(mesh, host_only=True)
+    pl = pb.plan(leaf, sn)
+    n = pl["n"]
+    assert n == len(s["interior"]) and sorted(pl["perm"]) == list(range(n))
+    # structural invariants
+    first, sz, sptr, strct, parent, level = (pl[k] for k in ("first", "s", "sptr", "strct", "parent", "level"))
+    assert first[0] == 0 and np.array_equal(first[1:], np.cumsum(sz)[:-1]) and sz.sum() == n and sz.max() <= sn
+    for f in range(pl["nfronts"]):
+        st = strct[sptr[f]:sptr[f + 1]]
+        assert (np.diff(st) > 0).all() and (len(st) == 0 or st[0] >= first[f] + sz[f])
+        if parent[f] >= 0:
+            assert parent[f] > f and level[parent[f]] > level[f]
+        else:
+            assert len(st) == 0
+    Kp, idx = FR.permuted_operator(K, pl)
+    fronts, ch = FR.factor(Kp, pl)
+    b = np.random.default_rng(1).standard_normal(2 * n)
+    x = FR.solve(fronts, ch, pl, b)
+    x = x + FR.solve(fronts, ch, pl, b - Kp @ x)               # the one refinement step the product takes
+    xr = splu(Kp.tocsc()).solve(b)
+    assert np.linalg.norm(x - xr) / np.linalg.norm(xr) < 1e-8
+    assert np.linalg.norm(Kp @ x - b) / np.linalg.norm(b) < 1e-9

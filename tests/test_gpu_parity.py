@@ -1,0 +1,145 @@
+"""Parity of the CUDA path (through the C ABI and the drop-in class) against the oracle.
+
+Tolerances (BASELINE.json north_star): identical CSR structure, assembled entries within 1e-12
+relative, n_eff within 1e-8 relative.  "Relative" for an assembled entry is taken against the
+largest magnitude in its row: entries that are pure round-off of cancelling element contributions
+(e.g. the vertex / adjacent-edge mass entries, exactly 0 in exact arithmetic) have no meaningful
+relative error of their own, and SciPy's own summation order for duplicates is unspecified.
+"""
+import numpy as np
+import pytest
+
+from plfem_b200 import _cabi
+from plfem_b200.solver_fem import TrueVectorialMaxwellSolver, ModeRecord
+from oracle import fem_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rowwise_rel_err(M, R):
+    """max over entries of |M - R| / (largest |R| in that row); structures must already match."""
+    d = np.abs(M.data - R.data)
+    rowmax = np.maximum.reduceat(np.abs(R.data), R.indptr[:-1][np.diff(R.indptr) > 0])
+    scale = np.repeat(rowmax, np.diff(R.indptr)[np.diff(R.indptr) > 0])
+    return float((d / scale).max())
+
+
+def same_structure(M, R):
+    return M.shape == R.shape and np.array_equal(M.indptr, R.indptr) and np.array_equal(M.indices, R.indices)
+
+
+@pytest.mark.parametrize("case", ["small_case", "cfg1"])
+def test_assembled_system_matches_oracle(case, request):
+    g, mesh = request.getfixturevalue(case)
+    A, B, basis, Dxx, Dyy, Dxy, M_inv = TrueVectorialMaxwellSolver(g).assemble_hfield_system(mesh)
+    rA, rB, rbasis, rDxx, rDyy, rDxy, rMinv = O.assemble_hfield_system(g, mesh)
+    assert basis.N == rbasis.N and np.array_equal(basis.doflocs, rbasis.doflocs)
+    assert np.array_equal(basis.get_dofs().all(), rbasis.boundary_dofs())
+    for name, M, R in (("A", A, rA), ("B", B, rB), ("Dxx", Dxx, rDxx), ("Dyy", Dyy, rDyy), ("Dxy", Dxy, rDxy),
+                       ("M_inv", M_inv, rMinv)):
+        assert same_structure(M, R), f"{name}: CSR structure differs ({M.nnz} vs {R.nnz} nnz)"
+        err = rowwise_rel_err(M, R)
+        assert err < 1e-12, f"{name}: row-relative deviation {err:.2e}"
+
+
+def test_interior_matrices_and_all_scalar_blocks(small_case):
+    g, mesh = small_case
+    pb = _cabi.Problem(mesh)
+    mat, keep = _cabi.material_struct(g)
+    pb.assemble(mat)
+    s = O.interior_system(g, mesh)
+    for name in ("A_int", "B_int"):
+        M = pb.export_csr(name)
+        assert same_structure(M, s[name]) and rowwise_rel_err(M, s[name]) < 1e-12
+    basis, m = O.assemble_scalar_matrices(g, mesh)
+    for name, key in (("Kxx", "kxx"), ("Kyy", "kyy"), ("Kxy", "kxy"), ("Kyx", "kyx"), ("M", "mass")):
+        M = pb.export_csr(name)
+        assert same_structure(M, m[key]) and rowwise_rel_err(M, m[key]) < 1e-12, name
+
+
+def test_custom_epsilon_callable_uses_host_samples(small_case):
+    g, mesh = small_case
+
+    class Graded:
+        positions, core_radii, n_core, n_clad, k0 = g.positions, g.core_radii, g.n_core, g.n_clad, g.k0
+
+        def epsilon(self, x, y):
+            return (1.0 + 1.3 * np.exp(-(np.asarray(x) ** 2 + np.asarray(y) ** 2) / 30.0)).astype(complex)
+
+    A, B, *_ = TrueVectorialMaxwellSolver(Graded()).assemble_hfield_system(mesh)
+    rA, rB, *_ = O.assemble_hfield_system(Graded(), mesh)
+    assert same_structure(A, rA) and rowwise_rel_err(A, rA) < 1e-12
+    assert same_structure(B, rB) and rowwise_rel_err(B, rB) < 1e-12
+
+
+def test_degenerate_mesh_is_an_error(cfg1):
+    from plfem_b200.mesh import MeshGenerator
+    g, _ = cfg1
+    raw = MeshGenerator._delaunay_mesh(g, 1.0)                 # still holds the 25 flat hull triangles
+    with pytest.raises(_cabi.PlfemError) as e:
+        TrueVectorialMaxwellSolver(g).assemble_hfield_system(raw)
+    assert e.value.status == 3
+
+
+def test_csr_spmv(small_case):
+    g, mesh = small_case
+    s = O.interior_system(g, mesh)
+    x = np.random.default_rng(3).standard_normal(s["A_int"].shape[0])
+    ctx = _cabi.Context.get(0)
+    for M in (s["A_int"], s["B_int"]):
+        y, ms = ctx.spmv_csr(M, x, repeat=3)
+        ref = M @ x
+        assert np.abs(y - ref).max() <= 1e-13 * np.abs(M).dot(np.abs(x)).max() and ms > 0
+
+
+def _compare_modes(g, mesh, n_modes, rtol_neff=1e-8):
+    solver = TrueVectorialMaxwellSolver(g)
+    modes, raw = solver.solve_vectorial_modes(mesh, n_modes, return_raw=True)
+    rmodes, rraw = O.solve_vectorial_modes(g, mesh, n_modes, return_raw=True)
+    st = raw["stats"]
+    assert st["nconv"] >= len(raw["beta_sq"]) and st["max_residual"] < 1e-7
+    # eigenvalues: same k pairs nearest sigma, beta^2 to 2e-8 relative <=> n_eff to 1e-8 relative
+    assert len(raw["beta_sq"]) == len(rraw["beta_sq"])
+    assert np.abs(raw["beta_sq"] / rraw["beta_sq"] - 1).max() < 2 * rtol_neff
+    assert len(modes) == len(rmodes)
+    for m, r in zip(modes, rmodes):
+        assert isinstance(m, ModeRecord) and set(m) == set(r)
+        assert abs(m["n_eff"] / r["n_eff"] - 1) < rtol_neff and abs(m["beta"] / r["beta"] - 1) < rtol_neff
+        assert m.n_eff == m["n_eff"] and m.polarization_state == m["polarization"]
+        assert m["is_vectorial"] is True and m["method"] == "H-field_V18.10"
+        # eigenvectors agree up to sign (the spectrum of these cases is simple)
+        v, rv = np.concatenate([m["Ex_dofs"], m["Ey_dofs"]]), np.concatenate([r["Ex_dofs"], r["Ey_dofs"]])
+        assert abs(abs(v @ rv) - 1) < 1e-6
+        for key in ("confinement", "core_overlap", "P_x", "P_y", "div_ratio"):
+            assert abs(m[key] - r[key]) <= 1e-6 * max(abs(r[key]), 1e-12), key
+        assert abs(m["PDL_dB"] - r["PDL_dB"]) < 1e-5 and m["polarization"] == r["polarization"]
+    return st
+
+
+def test_modes_small_case(small_case):
+    g, mesh = small_case
+    _compare_modes(g, mesh, 4)
+
+
+def test_modes_config1(cfg1):
+    g, mesh = cfg1
+    st = _compare_modes(g, mesh, 10)
+    assert st["kernel_launches"] > 0
+
+
+def test_readme_surface(cfg1):
+    g, mesh = cfg1
+    modes = TrueVectorialMaxwellSolver(g, n_modes=10).solve()
+    assert len(modes) > 0 and all(1.0 < m.n_eff < 1.01 * g.n_core for m in modes)
+    assert [m.n_eff for m in modes] == sorted((m.n_eff for m in modes), reverse=True)
+
+
+def test_start_vector_and_determinism(small_case):
+    g, mesh = small_case
+    s = TrueVectorialMaxwellSolver(g)
+    a = s.solve_vectorial_modes(mesh, 4)
+    b = s.solve_vectorial_modes(mesh, 4)
+    assert all(np.array_equal(x["Ex_dofs"], y["Ex_dofs"]) and x["n_eff"] == y["n_eff"] for x, y in zip(a, b))
+    n2 = 2 * (len(a[0]["Ex_dofs"]))
+    c = s.solve_vectorial_modes(mesh, 4, v0=np.random.default_rng(5).uniform(-1, 1, n2))
+    assert np.allclose([m["n_eff"] for m in a], [m["n_eff"] for m in c], rtol=1e-9)
