@@ -122,7 +122,7 @@ typedef struct {
   int64_t factor_entries;           /* doubles read by one forward+backward sweep / 2 */
   int64_t front_pool_doubles;
   double factor_flops;
-  double max_residual;              /* max_i ||A x - lambda B x||_2 / (|lambda| ||B x||_2) with the true A, B */
+  double max_residual;              /* max_i ||A x - lambda B x||_2 / ||(|A| + |lambda||B|) |x|||_2, true A and B */
   float ms_symbolic, ms_assemble, ms_factor, ms_lanczos, ms_metrics, ms_total; /* host wall / CUDA events */
   int32_t kernel_launches;
 } plfem_solve_stats;
@@ -136,6 +136,14 @@ int plfem_solve_modes(plfem_problem* pb, const plfem_material* mat, const plfem_
                       double* metrics,    /* (k, PLFEM_NMETRICS) */
                       int32_t* core_dof_count, /* number of interior DOFs inside a core (solver_fem.py:200-203) */
                       plfem_solve_stats* stats);
+
+/* ---- measurement hook for bench.py: per-kernel device times (CUDA events on the library's stream, L2
+ * flushed before each repetition) and the algorithmic bytes of the same items; needs a prior solve.
+ * index: 0 assembly (K1), 1 front load + factorisation, 2 forward sweep, 3 backward sweep,
+ *        4 B product (SpMM, 2 right-hand sides), 5 K residual SpMV */
+#define PLFEM_NPROFILE 6
+int plfem_profile_kernels(plfem_problem* pb, const plfem_material* mat, double sigma, int repeat,
+                          double* out_ms, double* out_bytes);
 
 /* ---- debug / test hooks (host logic checks that need no GPU) ----------------------------------- */
 /* sizes: [n, nfronts, nlevels, strct_len, cmap_len, nchild] */

@@ -27,7 +27,7 @@ NMETRICS = 8
 SYMBOLS = ["plfem_ctx_create", "plfem_ctx_destroy", "plfem_last_error", "plfem_version",
            "plfem_problem_create", "plfem_problem_destroy", "plfem_problem_info", "plfem_problem_dofs",
            "plfem_quad_points", "plfem_assemble", "plfem_export_csr", "plfem_spmv_csr", "plfem_solve_modes",
-           "plfem_plan_sizes", "plfem_plan_export", "plfem_debug_symeig"]
+           "plfem_plan_sizes", "plfem_plan_export", "plfem_debug_symeig", "plfem_profile_kernels"]
 
 
 class MeshInfo(C.Structure):
@@ -99,6 +99,7 @@ def load():
         lib.plfem_plan_sizes.argtypes = [vp, c_i32, c_i32, p_i64]
         lib.plfem_plan_export.argtypes = [vp] + [p_i32] * 9 + [p_i64]
         lib.plfem_debug_symeig.argtypes = [c_i32, p_f64, p_f64]
+        lib.plfem_profile_kernels.argtypes = [vp, C.POINTER(Material), c_f64, C.c_int, p_f64, p_f64]
         _lib = lib
         return lib
 
@@ -242,6 +243,16 @@ class Problem:
         self._check(self.lib.plfem_solve_modes(self.handle, C.byref(material), C.byref(o), _ptr(vals, p_f64),
                                                _ptr(vecs, p_f64), _ptr(met, p_f64), C.byref(ncore), C.byref(stats)))
         return vals, vecs, met, ncore.value, stats
+
+    PROFILE_ITEMS = ("assemble", "factorize", "forward_sweep", "backward_sweep", "spmm_B", "spmv_K_residual")
+
+    def profile_kernels(self, material: Material, sigma: float, repeat: int = 20) -> dict:
+        """{item: (avg ms, algorithmic bytes)} measured with CUDA events on the library stream."""
+        ms = np.zeros(len(self.PROFILE_ITEMS))
+        nb = np.zeros(len(self.PROFILE_ITEMS))
+        self._check(self.lib.plfem_profile_kernels(self.handle, C.byref(material), float(sigma), int(repeat),
+                                                   _ptr(ms, p_f64), _ptr(nb, p_f64)))
+        return {k: (float(a), float(b)) for k, a, b in zip(self.PROFILE_ITEMS, ms, nb)}
 
     def plan(self, leaf_nodes: int = 0, max_sn_nodes: int = 0) -> dict:
         """Front plan as NumPy arrays (host logic; needs no GPU)."""

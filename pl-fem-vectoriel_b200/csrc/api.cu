@@ -528,7 +528,7 @@ int plfem_solve_modes(plfem_problem* pb, const plfem_material* mat, const plfem_
       stats->factor_entries = pb->plan.factor_entries; stats->front_pool_doubles = pb->plan.foff[pb->plan.nfronts];
       stats->factor_flops = pb->plan.factor_flops;
       double mr = 0.0;
-      for (int i = 0; i < k; ++i) mr = std::max(mr, res[2 * i] / (std::fabs(lambda[i]) * res[2 * i + 1] + 1e-300));
+      for (int i = 0; i < k; ++i) mr = std::max(mr, res[2 * i] / (res[2 * i + 1] + 1e-300));
       stats->max_residual = mr;
       stats->ms_symbolic = (float)(t1 - t0);
       cudaEventElapsedTime(&stats->ms_assemble, ctx->ev[0], ctx->ev[1]);
@@ -538,6 +538,64 @@ int plfem_solve_modes(plfem_problem* pb, const plfem_material* mat, const plfem_
       stats->ms_total = (float)(t2 - t0);
       stats->kernel_launches = ctx->launches;
     }
+  });
+}
+
+// Per-kernel timings for the roofline report: CUDA events on the library's own stream, L2 flushed
+// (a 256 MiB memset) before every timed repetition.  Needs a completed plfem_solve_modes on pb.
+// out_ms[0] element setup + assembly, [1] front load + factorisation, [2] forward sweep (all levels),
+// [3] backward sweep (all levels), [4] B product (spmm), [5] K residual (refinement spmv); out_bytes
+// holds the algorithmic bytes of the same six items.
+int plfem_profile_kernels(plfem_problem* pb, const plfem_material* mat, double sigma, int repeat, double* out_ms,
+                          double* out_bytes) {
+  if (!pb || !pb->ctx) return PLFEM_ERR_INVALID;
+  plfem_ctx* ctx = pb->ctx;
+  return guarded(ctx, [&] {
+    need(mat && out_ms && out_bytes, "NULL argument");
+    if (pb->dperm.n == 0 || pb->d_vals.p == nullptr) throw StatusError(PLFEM_ERR_NOT_READY, "run plfem_solve_modes first");
+    PLFEM_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int reps = std::max(repeat, 1);
+    const int64_t n = pb->dperm.n, nnz = pb->dperm.nnz, m = 2 * n;
+    DevBuf<double> flush, b, x, t;
+    flush.alloc(ctx, (size_t)32 << 20);   // 256 MiB > 126 MB L2
+    b.alloc(ctx, m); x.alloc(ctx, m); t.alloc(ctx, m);
+    std::vector<double> ones(m, 1.0);
+    b.upload(ctx, ones);
+    auto timed = [&](auto&& body) {
+      double tot = 0.0;
+      for (int r = 0; r < reps; ++r) {
+        PLFEM_CUDA(cudaMemsetAsync(flush.p, r & 0xff, flush.n * sizeof(double), st));
+        PLFEM_CUDA(cudaEventRecord(ctx->ev[5], st));
+        body();
+        PLFEM_CUDA(cudaEventRecord(ctx->ev[6], st));
+        PLFEM_CUDA(cudaStreamSynchronize(st));
+        float ms = 0; PLFEM_CUDA(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]));
+        tot += ms;
+      }
+      return tot / reps;
+    };
+    const DofTables& d = pb->dof;
+    out_ms[0] = timed([&] {
+      launch_element_setup(ctx, pb->d_p.p, pb->d_edofs.p, d.V, d.T, *mat, pb->d_cores.p, nullptr, pb->d_elem.p);
+      launch_assemble(ctx, pb->dperm, pb->d_n2e_ptr.p, pb->d_n2e.p, pb->d_edofs.p, pb->d_elem.p, mat->k0 * mat->k0, mat->alpha_p,
+                      false, pb->d_vals.p, nullptr);
+    });
+    // mesh in (coordinates + 6 DOF ids per element), every assembled value out once
+    out_bytes[0] = 16.0 * d.V + 24.0 * d.T + 8.0 * NV_SOLVE * nnz;
+    out_ms[1] = timed([&] { launch_front_load(ctx, pb->dperm, pb->dplan, pb->d_vals.p, sigma); run_factorization(ctx, pb->dplan); });
+    out_bytes[1] = 8.0 * 5 * nnz + 8.0 * pb->plan.factor_entries;   // read A,B values, write the factor
+    out_ms[2] = timed([&] { run_solve_forward(ctx, pb->dplan, b.p, x.p); });
+    out_bytes[2] = 8.0 * pb->plan.factor_entries + 16.0 * m;
+    out_ms[3] = timed([&] { run_solve_backward(ctx, pb->dplan, x.p); });
+    {
+      double w = 0; for (int f = 0; f < pb->plan.nfronts; ++f) w += 4.0 * pb->plan.s[f] * (pb->plan.sptr[f + 1] - pb->plan.sptr[f]);
+      out_bytes[3] = 8.0 * w + 16.0 * m;
+    }
+    out_ms[4] = timed([&] { launch_spmm_b(ctx, pb->dperm, pb->d_vals.p, b.p, t.p); });
+    out_bytes[4] = 12.0 * nnz + 4.0 * (n + 1) + 32.0 * n;           // values + columns + row pointers + x and y (2 comps)
+    out_ms[5] = timed([&] { launch_resid_k(ctx, pb->dperm, pb->d_vals.p, sigma, x.p, b.p, t.p); });
+    out_bytes[5] = (5 * 8.0 + 4.0) * nnz + 4.0 * (n + 1) + 48.0 * n;
   });
 }
 

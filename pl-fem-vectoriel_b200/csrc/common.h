@@ -142,6 +142,8 @@ void launch_front_load(plfem_ctx* ctx, const DevPattern& pat, const DevPlan& D, 
 void run_factorization(plfem_ctx* ctx, const DevPlan& D);
 // solves (A - sigma B) x = b in the permuted interleaved layout, b and x of length 2n (must not alias)
 void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x);
+void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double* z);
+void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x);
 
 // ---- Lanczos + mode reductions (eigen.cu) ----------------------------------------------------------
 struct EigenResult {
@@ -157,6 +159,10 @@ void run_mode_metrics(plfem_ctx* ctx, const DevPattern& pat, const double* d_val
                       const uint8_t* d_in_core, const double* X, const std::vector<double>& lambda, int k,
                       double* d_out_evecs /* (k, 2n) reference ordering or null */, double* d_metrics /* (k,8) */,
                       double* d_resid /* (k,2) */);
+
+void launch_spmm_b(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, const double* x, double* y);
+void launch_resid_k(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, double sigma, const double* x, const double* b,
+                    double* t);
 
 void symmetric_eigen(int n, std::vector<double>& a /* n*n col-major in, eigenvectors out */, std::vector<double>& w);
 

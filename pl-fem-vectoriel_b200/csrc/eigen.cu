@@ -174,7 +174,7 @@ __global__ void fill_kernel(double* v, int64_t m, double val) {
 }
 
 // ---- per-mode reductions ----------------------------------------------------------------------------------
-constexpr int NRED = 10;  // norm2, e_core, px_core, py_core, px_all, py_all, div, res2, bx2, unused
+constexpr int NRED = 10;  // norm2, e_core, px_core, py_core, px_all, py_all, div, res2, bx2, scale2
 constexpr int MROWS = 2048;  // rows (nodes) per CTA in the mode reduction
 
 __global__ void __launch_bounds__(256) mode_partial_kernel(int32_t n, const int32_t* __restrict__ rowptr,
@@ -197,9 +197,11 @@ __global__ void __launch_bounds__(256) mode_partial_kernel(int32_t n, const int3
     acc[0] += ex + ey;
     acc[4] += ex; acc[5] += ey;
     if (in_core[r]) { acc[1] += ex + ey; acc[2] += ex; acc[3] += ey; }
-    double dx = 0.0, dy = 0.0, axv = 0.0, ayv = 0.0, bx = 0.0, by = 0.0;
+    double dx = 0.0, dy = 0.0, axv = 0.0, ayv = 0.0, bx = 0.0, by = 0.0, nx = 0.0, ny = 0.0;
+    const double alam = fabs(lam);
     for (int32_t z = rowptr[r]; z < rowptr[r + 1]; ++z) {
       const double2 c = x[col[z]];
+      const double acx = fabs(c.x), acy = fabs(c.y);
       dx = fma(vals[(int64_t)S_DXX * nnz + z], c.x, dx);
       dx = fma(2.0 * vals[(int64_t)S_DXY * nnz + z], c.y, dx);
       dy = fma(vals[(int64_t)S_DYY * nnz + z], c.y, dy);
@@ -209,11 +211,15 @@ __global__ void __launch_bounds__(256) mode_partial_kernel(int32_t n, const int3
       ayv = fma(vals[(int64_t)S_AYY * nnz + z], c.y, ayv);
       const double mi = vals[(int64_t)S_MINV * nnz + z];
       bx = fma(mi, c.x, bx); by = fma(mi, c.y, by);
+      // (|A| + |lambda| |B|) |x|: the scale of the componentwise backward error
+      nx += (fabs(vals[(int64_t)S_AXX * nnz + z]) + alam * fabs(mi)) * acx + fabs(vals[(int64_t)S_AXY * nnz + z]) * acy;
+      ny += fabs(vals[(int64_t)S_AYX * nnz + z]) * acx + (fabs(vals[(int64_t)S_AYY * nnz + z]) + alam * fabs(mi)) * acy;
     }
     acc[6] += v.x * dx + v.y * dy;
     const double rx = axv - lam * bx, ry = ayv - lam * by;
     acc[7] += rx * rx + ry * ry;
     acc[8] += bx * bx + by * by;
+    acc[9] += nx * nx + ny * ny;
   }
   for (int k = 0; k < NRED; ++k) {
     const double t = block_sum(acc[k], sh);
@@ -236,7 +242,7 @@ __global__ void mode_final_kernel(const double* __restrict__ part, int nchunks, 
   double* o = metrics + (int64_t)mode * PLFEM_NMETRICS;
   o[0] = t[6] * inv2; o[1] = t[1] * inv2; o[2] = t[0] * inv2; o[3] = t[2] * inv2; o[4] = t[3] * inv2;
   o[5] = t[4] * inv2; o[6] = t[5] * inv2; o[7] = t[0];
-  resid[2 * mode] = sqrt(t[7]); resid[2 * mode + 1] = sqrt(t[8]);
+  resid[2 * mode] = sqrt(t[7]); resid[2 * mode + 1] = sqrt(t[9]);
 }
 
 __global__ void __launch_bounds__(256) write_evecs_kernel(int32_t n, const int32_t* __restrict__ perm,
@@ -254,6 +260,23 @@ __global__ void __launch_bounds__(256) write_evecs_kernel(int32_t n, const int32
 }
 
 }  // namespace
+
+void launch_spmm_b(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, const double* x, double* y) {
+  const unsigned g = (unsigned)(((int64_t)pat.n * 4 + 255) / 256);
+  spmm_b_kernel<<<g, 256, 0, ctx->stream>>>(pat.n, pat.rowptr.p, pat.col.p, d_vals + (int64_t)S_MINV * pat.nnz, (const double2*)x,
+                                            (double2*)y);
+  PLFEM_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
+void launch_resid_k(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, double sigma, const double* x, const double* b,
+                    double* t) {
+  const unsigned g = (unsigned)(((int64_t)pat.n * 4 + 255) / 256);
+  resid_k_kernel<<<g, 256, 0, ctx->stream>>>(pat.n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz, sigma, (const double2*)x,
+                                             (const double2*)b, (double2*)t);
+  PLFEM_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
 
 void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, const DevPlan& D, const double* d_vals, double sigma, int k,
                      int ncv, double tol, int maxiter, int refine_steps, const double* d_v0, DevBuf<double>& X,

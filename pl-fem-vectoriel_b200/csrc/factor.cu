@@ -436,13 +436,18 @@ void run_factorization(plfem_ctx* ctx, const DevPlan& D) {
   PLFEM_CUDA(cudaGetLastError());
 }
 
-void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x) {
+void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double* z) {
   const PlanView v = view(D);
   for (int l = 0; l < D.nlevels; ++l) {
     const int nsl = D.fwd_ptr[l + 1] - D.fwd_ptr[l];
-    forward_kernel<<<nsl, FWD_ROWS, 0, ctx->stream>>>(D.fwd_slabs.p + D.fwd_ptr[l], v, b, x, D.upd.p);
+    forward_kernel<<<nsl, FWD_ROWS, 0, ctx->stream>>>(D.fwd_slabs.p + D.fwd_ptr[l], v, b, z, D.upd.p);
     ctx->launches++;
   }
+  PLFEM_CUDA(cudaGetLastError());
+}
+
+void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x) {
+  const PlanView v = view(D);
   for (int l = D.nlevels - 1; l >= 0; --l) {
     const int nsl = D.bwd_ptr[l + 1] - D.bwd_ptr[l];
     if (nsl == 0) continue;
@@ -450,6 +455,11 @@ void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x) {
     ctx->launches++;
   }
   PLFEM_CUDA(cudaGetLastError());
+}
+
+void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x) {
+  run_solve_forward(ctx, D, b, x);
+  run_solve_backward(ctx, D, x);
 }
 
 }  // namespace plfem

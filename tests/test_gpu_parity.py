@@ -28,6 +28,25 @@ def same_structure(M, R):
     return M.shape == R.shape and np.array_equal(M.indptr, R.indptr) and np.array_equal(M.indices, R.indices)
 
 
+def check_A(A, rA):
+    """A = sums of scalar matrices, where SciPy's sparse +/- drop results that are exactly 0.0.  Whether
+    a cancelling sum of element contributions rounds to exactly 0.0 or to 1e-17 depends on the order in
+    which SciPy happens to add duplicates (an unstable std::sort inside csr sum_duplicates), so the two
+    structures may differ on such pure round-off entries and nowhere else."""
+    assert A.shape == rA.shape
+    D = (A - rA).tocsr()
+    rowmax = np.maximum(abs(rA).max(axis=1).toarray().ravel(), 1e-300)
+    D.eliminate_zeros()
+    rel = np.abs(D.data) / np.repeat(rowmax, np.diff(D.indptr))
+    assert rel.max() < 1e-12, f"A: row-relative deviation {rel.max():.2e}"
+    only = ((A != 0).astype(np.int8) - (rA != 0).astype(np.int8)).tocsr()
+    only.eliminate_zeros()
+    assert only.nnz <= 2e-3 * rA.nnz                       # a few hundred of ~1e6 entries
+    rows = np.repeat(np.arange(A.shape[0]), np.diff(only.indptr))
+    vals = np.abs(np.asarray((A + rA)[rows, only.indices]).ravel())
+    assert (vals <= 1e-13 * rowmax[rows]).all()            # and every one of them is round-off
+
+
 @pytest.mark.parametrize("case", ["small_case", "cfg1"])
 def test_assembled_system_matches_oracle(case, request):
     g, mesh = request.getfixturevalue(case)
@@ -35,11 +54,11 @@ def test_assembled_system_matches_oracle(case, request):
     rA, rB, rbasis, rDxx, rDyy, rDxy, rMinv = O.assemble_hfield_system(g, mesh)
     assert basis.N == rbasis.N and np.array_equal(basis.doflocs, rbasis.doflocs)
     assert np.array_equal(basis.get_dofs().all(), rbasis.boundary_dofs())
-    for name, M, R in (("A", A, rA), ("B", B, rB), ("Dxx", Dxx, rDxx), ("Dyy", Dyy, rDyy), ("Dxy", Dxy, rDxy),
-                       ("M_inv", M_inv, rMinv)):
+    for name, M, R in (("B", B, rB), ("Dxx", Dxx, rDxx), ("Dyy", Dyy, rDyy), ("Dxy", Dxy, rDxy), ("M_inv", M_inv, rMinv)):
         assert same_structure(M, R), f"{name}: CSR structure differs ({M.nnz} vs {R.nnz} nnz)"
         err = rowwise_rel_err(M, R)
         assert err < 1e-12, f"{name}: row-relative deviation {err:.2e}"
+    check_A(A, rA)
 
 
 def test_interior_matrices_and_all_scalar_blocks(small_case):
@@ -48,9 +67,9 @@ def test_interior_matrices_and_all_scalar_blocks(small_case):
     mat, keep = _cabi.material_struct(g)
     pb.assemble(mat)
     s = O.interior_system(g, mesh)
-    for name in ("A_int", "B_int"):
-        M = pb.export_csr(name)
-        assert same_structure(M, s[name]) and rowwise_rel_err(M, s[name]) < 1e-12
+    M = pb.export_csr("B_int")
+    assert same_structure(M, s["B_int"]) and rowwise_rel_err(M, s["B_int"]) < 1e-12
+    check_A(pb.export_csr("A_int"), s["A_int"])
     basis, m = O.assemble_scalar_matrices(g, mesh)
     for name, key in (("Kxx", "kxx"), ("Kyy", "kyy"), ("Kxy", "kxy"), ("Kyx", "kyx"), ("M", "mass")):
         M = pb.export_csr(name)
@@ -68,7 +87,7 @@ def test_custom_epsilon_callable_uses_host_samples(small_case):
 
     A, B, *_ = TrueVectorialMaxwellSolver(Graded()).assemble_hfield_system(mesh)
     rA, rB, *_ = O.assemble_hfield_system(Graded(), mesh)
-    assert same_structure(A, rA) and rowwise_rel_err(A, rA) < 1e-12
+    check_A(A, rA)
     assert same_structure(B, rB) and rowwise_rel_err(B, rB) < 1e-12
 
 
@@ -97,7 +116,7 @@ def _compare_modes(g, mesh, n_modes, rtol_neff=1e-8):
     modes, raw = solver.solve_vectorial_modes(mesh, n_modes, return_raw=True)
     rmodes, rraw = O.solve_vectorial_modes(g, mesh, n_modes, return_raw=True)
     st = raw["stats"]
-    assert st["nconv"] >= len(raw["beta_sq"]) and st["max_residual"] < 1e-7
+    assert st["nconv"] >= len(raw["beta_sq"]) and st["max_residual"] < 1e-10
     # eigenvalues: same k pairs nearest sigma, beta^2 to 2e-8 relative <=> n_eff to 1e-8 relative
     assert len(raw["beta_sq"]) == len(rraw["beta_sq"])
     assert np.abs(raw["beta_sq"] / rraw["beta_sq"] - 1).max() < 2 * rtol_neff
