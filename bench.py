@@ -3,10 +3,12 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg1|cfg2]
 
-A *step* is one modal solve (`solve_vectorial_modes`: DOF tables -> assembly -> Dirichlet
-elimination -> ordering + factorisation of A - sigma*B -> eigensolve -> per-mode reductions) of
-the workload's cross-section; the mesh is given (built on the host before timing, as in the
-reference where `MeshGenerator` runs before the solver).
+A *step* is one batch of ``--inflight`` (default 8) independent modal solves of the workload's
+cross-section, in flight together on one GPU (one host thread + CUDA stream each, the sweep's
+production mode); a modal solve is `solve_vectorial_modes`: DOF tables -> assembly -> Dirichlet
+elimination -> ordering + factorisation of A - sigma*B -> eigensolve -> per-mode reductions.  The mesh
+is given (built on the host before timing, as in the reference where `MeshGenerator` runs first).
+``latency`` in the JSON line is the same solve run alone (inflight = 1).
 
 * ``value``  : solves/s with the mesh and its DOF tables already resident in HBM
                (`plfem_solve_modes` on an existing problem, symbolic analysis NOT reused,
@@ -193,62 +195,87 @@ def run_ours(args):
         torch.cuda.synchronize(local)
 
     # ---- value: mesh + DOF tables resident, everything else inside ----------------------------------
-    pb = _cabi.Problem(mesh, ctx)
-    mat, keep = _cabi.material_struct(g)
+    from plfem_b200.batch import SolverPool
+    B = max(1, args.inflight)
+    pool = SolverPool(device=local, workers=B)
     sigma = sigma_estimate(g)
+    mat, keep = _cabi.material_struct(g)
+
+    by_ctx = {}                                            # one resident problem per worker context
+
+    def resident(c):
+        if id(c) not in by_ctx:
+            by_ctx[id(c)] = _cabi.Problem(mesh, c)         # created during warm-up, outside the timed region
+        return by_ctx[id(c)]
+
+    pb = resident(ctx)
     k = min(n_modes + 12, 2 * pb.n_interior - 4)
 
-    def step_value():
-        return pb.solve_modes(mat, sigma, k, tol=1e-7, maxiter=12000, want_vectors=False, reuse_symbolic=False)
+    def solve_resident(c, _):
+        return resident(c).solve_modes(mat, sigma, k, tol=1e-7, maxiter=12000, want_vectors=False, reuse_symbolic=False)
 
-    for _ in range(args.warmup):
+    def step_value():
+        return pool.map(solve_resident, range(B))
+
+    for _ in range(args.warmup + 2):                       # extra rounds so every worker thread owns a problem
         step_value()
-    launches, phase = 0, {n: 0.0 for n in ("ms_symbolic", "ms_assemble", "ms_factor", "ms_lanczos", "ms_metrics")}
-    records = np.full((args.steps, N_RECORD), np.nan)
+    launches, phase = 0, {n: 0.0 for n in ("ms_symbolic", "ms_assemble", "ms_factor", "ms_lanczos", "ms_metrics", "ms_total")}
+    records = np.full((args.steps * B, N_RECORD), np.nan)
     sync_all()
     t_value = 0.0
     with ClockSampler(local) as clocks:
         for i in range(args.steps):
             flush_l2()
             t0 = time.perf_counter()
-            vals, _, met, ncore, st = step_value()
+            outs = step_value()
             torch.cuda.synchronize(local)
             dt = time.perf_counter() - t0
             t_value += dt
-            launches += st.kernel_launches
-            for n in phase:
-                phase[n] += getattr(st, n)
-            records[i, 0], records[i, 1], records[i, 3] = rank * args.steps + i, 1.0, dt
+            for j, (vals, _, met, ncore, st) in enumerate(outs):
+                launches += st.kernel_launches
+                for n in phase:
+                    phase[n] += getattr(st, n) / B
+                records[i * B + j, 0], records[i * B + j, 1], records[i * B + j, 3] = (rank * args.steps + i) * B + j, 1.0, dt
         if world > 1:          # the sweep's single collective, inside the timed region
             t0 = time.perf_counter()
-            allrec = gather_records(records, world * args.steps, rank, world, local)
+            allrec = gather_records(records, world * args.steps * B, rank, world, local)
             torch.cuda.synchronize(local)
             t_value += time.perf_counter() - t0
-            assert allrec.shape == (world * args.steps, N_RECORD)
+            assert allrec.shape == (world * args.steps * B, N_RECORD)
     stats = st.as_dict()
 
     # ---- e2e: public API, host buffers in, mode records out -----------------------------------------
     def step_e2e():
-        s = TrueVectorialMaxwellSolver(g, device=local)
-        try:
-            return s.solve_vectorial_modes(mesh, n_modes)
-        finally:
-            s.close()
+        return pool.solve_many([(g, mesh, n_modes)] * B)
 
     for _ in range(args.warmup):
-        modes = step_e2e()
+        modes = step_e2e()[0]
     sync_all()
     t_e2e = 0.0
     with ClockSampler(local) as clocks2:
         for i in range(args.steps):
             flush_l2()
             t0 = time.perf_counter()
-            modes = step_e2e()
+            modes = step_e2e()[0]
             torch.cuda.synchronize(local)
             t_e2e += time.perf_counter() - t0
+
+    # ---- latency: one solve alone through the public API ---------------------------------------------
+    lat = []
+    if rank == 0:
+        _cabi.load().plfem_set_host_threads(0)
+        for i in range(3 + min(args.steps, 10)):
+            flush_l2()
+            t0 = time.perf_counter()
+            s1 = TrueVectorialMaxwellSolver(g, device=local)
+            s1.solve_vectorial_modes(mesh, n_modes)
+            lat_stats = dict(s1.last_stats)
+            s1.close()
+            lat.append(time.perf_counter() - t0)
+        lat = lat[3:]
     n_solve = pb.n_interior
-    h2d = mesh.p.nbytes + mesh.t.astype(np.int64).nbytes + 8 * (3 * g.n_cores + 4)
-    d2h = 8 * (k + k * 2 * n_solve + k * _cabi.NMETRICS)
+    h2d = B * (mesh.p.nbytes + mesh.t.astype(np.int64).nbytes + 8 * (3 * g.n_cores + 4))
+    d2h = B * 8 * (k + k * 2 * n_solve + k * _cabi.NMETRICS)
 
     if world > 1:
         tt = torch.tensor([t_value, t_e2e], dtype=torch.float64, device=f"cuda:{local}")
@@ -259,6 +286,7 @@ def run_ours(args):
         launches = int(lt.item())
 
     if rank != 0:
+        pool.close()
         if world > 1:
             dist.destroy_process_group()
         return
@@ -287,22 +315,26 @@ def run_ours(args):
                         "the sweeps are a chain of one launch per elimination-tree level, i.e. latency- not bandwidth-bound"}
 
     cpu = cpu_baseline_sample(args.workload, 2) if world == 1 else None
-    line = {"metric": "modal_solves_per_sec", "value": world * args.steps / t_value, "unit": "solves/s", "n_gpus": world,
+    pool.close()
+    line = {"metric": "modal_solves_per_sec", "value": world * B * args.steps / t_value, "unit": "solves/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_value / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["name"], "mesh": {"V": int(mesh.p.shape[1]), "T": int(mesh.t.shape[1]), "N_p2": int(pb.N),
                                                        "dim": 2 * n_solve, "recipe": "reference point recipe, refinement 1.0, flat hull triangles dropped"},
+                       "step": f"{B} independent modal solves in flight on one GPU (one host thread + stream each)",
                        "k": k, "ncv": max(2 * k + 1, 20), "tol": 1e-7, "start_vector": "ones", "refine_steps": 1,
                        "l2": "flushed (512 MiB write) before every timed step", "timing": "per-step wall clock around the synchronous C-ABI call, "
                        "cuda synchronize on both sides, summed over steps, max over ranks",
                        "SimulationConfig": {"mesh_min_points": 0, "mesh_target_points": 0}},
             "clocks": clocks.summary(),
-            "e2e": {"value": world * args.steps / t_e2e, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "e2e": {"value": world * B * args.steps / t_e2e, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * t_e2e / args.steps, "n_modes_returned": len(modes), "clocks": clocks2.summary()},
             "gpu_launches": int(launches),
+            "latency": {"ms_per_solve_alone_e2e": 1e3 * statistics.mean(lat), "solves_per_s": 1.0 / statistics.mean(lat),
+                        "phases_ms": {n: lat_stats[n] for n in ("ms_symbolic", "ms_assemble", "ms_factor", "ms_lanczos", "ms_metrics")}},
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "phases_ms_per_step": {n: v / args.steps for n, v in phase.items()},
+            "phases_ms_per_solve_in_batch": {n: v / args.steps for n, v in phase.items()},
             "solver": {kk: stats[kk] for kk in ("nconv", "n_op", "n_restart", "n_fronts", "n_levels", "max_front_nodes", "factor_entries",
                                                 "front_pool_doubles", "factor_flops", "max_residual")},
             "kernels": kernels}
@@ -318,6 +350,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg1", choices=sorted(WORKLOADS))
+    ap.add_argument("--inflight", type=int, default=8, help="independent solves in flight per GPU and step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     if args.impl == "reference":

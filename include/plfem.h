@@ -42,6 +42,9 @@ enum plfem_status {
 int plfem_ctx_create(int device, plfem_ctx** out);
 void plfem_ctx_destroy(plfem_ctx* ctx);
 const char* plfem_last_error(const plfem_ctx* ctx);
+/* host threads the symbolic analysis of ONE solve may use (0 = default min(cores, 8)); lower it when several
+ * contexts solve concurrently from different host threads */
+void plfem_set_host_threads(int n);
 /* abi / build identification: "plfem <version> sm_100a" */
 const char* plfem_version(void);
 

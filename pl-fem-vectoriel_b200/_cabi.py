@@ -27,7 +27,7 @@ NMETRICS = 8
 SYMBOLS = ["plfem_ctx_create", "plfem_ctx_destroy", "plfem_last_error", "plfem_version",
            "plfem_problem_create", "plfem_problem_destroy", "plfem_problem_info", "plfem_problem_dofs",
            "plfem_quad_points", "plfem_assemble", "plfem_export_csr", "plfem_spmv_csr", "plfem_solve_modes",
-           "plfem_plan_sizes", "plfem_plan_export", "plfem_debug_symeig", "plfem_profile_kernels"]
+           "plfem_plan_sizes", "plfem_plan_export", "plfem_debug_symeig", "plfem_profile_kernels", "plfem_set_host_threads"]
 
 
 class MeshInfo(C.Structure):
@@ -99,6 +99,8 @@ def load():
         lib.plfem_plan_sizes.argtypes = [vp, c_i32, c_i32, p_i64]
         lib.plfem_plan_export.argtypes = [vp] + [p_i32] * 9 + [p_i64]
         lib.plfem_debug_symeig.argtypes = [c_i32, p_f64, p_f64]
+        lib.plfem_set_host_threads.argtypes = [C.c_int]
+        lib.plfem_set_host_threads.restype = None
         lib.plfem_profile_kernels.argtypes = [vp, C.POINTER(Material), c_f64, C.c_int, p_f64, p_f64]
         _lib = lib
         return lib

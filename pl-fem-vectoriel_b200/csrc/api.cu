@@ -189,6 +189,8 @@ extern "C" {
 
 const char* plfem_version(void) { return "plfem 0.1 sm_100a"; }
 
+void plfem_set_host_threads(int n) { plfem::set_host_threads(n); }
+
 int plfem_ctx_create(int device, plfem_ctx** out) {
   if (!out) return PLFEM_ERR_INVALID;
   *out = nullptr;
@@ -201,6 +203,7 @@ int plfem_ctx_create(int device, plfem_ctx** out) {
     ctx->device = device;
     PLFEM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (auto& e : ctx->ev) PLFEM_CUDA(cudaEventCreate(&e));
+    upload_tables();
   });
   if (st != PLFEM_OK) {
     // keep the context alive so the caller can read the message
@@ -443,9 +446,9 @@ int plfem_solve_modes(plfem_problem* pb, const plfem_material* mat, const plfem_
     // -- symbolic (host) --------------------------------------------------------------------------
     ensure_plan(pb, o->leaf_nodes, o->max_sn_nodes, o->reuse_symbolic != 0);
     if (pb->dperm.n == 0) {
-      std::vector<int32_t> new_of_old(pb->dof.N, -1);
-      for (int32_t r = 0; r < pb->plan.n; ++r) new_of_old[pb->dof.interior[pb->plan.perm[r]]] = r;
-      build_pattern(pb->dof, new_of_old, pb->plan.n, pb->perm_pat);
+      std::vector<int32_t> new_of(pb->plan.n);
+      for (int32_t r = 0; r < pb->plan.n; ++r) new_of[pb->plan.perm[r]] = r;
+      relabel_pattern(pb->adj, pb->plan.perm, new_of, pb->dof.interior, pb->dof.N, pb->perm_pat);
       upload_pattern(ctx, pb->perm_pat, pb->dperm);
       build_dev_plan(ctx, pb->plan, pb->dplan);
       pb->d_perm.upload(ctx, pb->plan.perm);

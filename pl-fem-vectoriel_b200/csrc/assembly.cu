@@ -74,14 +74,6 @@ RefTables make_tables() {
 }
 
 __constant__ RefTables c_tab;
-bool g_tab_uploaded[64] = {};
-
-void ensure_tables(plfem_ctx* ctx) {
-  if (ctx->device < 64 && g_tab_uploaded[ctx->device]) return;
-  const RefTables& t = ref_tables();
-  PLFEM_CUDA(cudaMemcpyToSymbolAsync(c_tab, &t, sizeof(RefTables), 0, cudaMemcpyHostToDevice, ctx->stream));
-  if (ctx->device < 64) g_tab_uploaded[ctx->device] = true;
-}
 
 constexpr int ELEM_STRIDE = 12;  // doubles per element record: i00 i10 i01 i11 |det| w[6] pad
 
@@ -234,10 +226,16 @@ const RefTables& ref_tables() {
   return t;
 }
 
+// Called once per context, synchronously: contexts on other host threads may launch kernels that read
+// the constant bank right after, on their own streams.
+void upload_tables() {
+  const RefTables& t = ref_tables();
+  PLFEM_CUDA(cudaMemcpyToSymbol(c_tab, &t, sizeof(RefTables), 0, cudaMemcpyHostToDevice));
+}
+
 void launch_element_setup(plfem_ctx* ctx, const double* d_p, const int32_t* d_edofs, int64_t V, int64_t T,
                           const plfem_material& mat, const double* d_cores, const double* d_eps_at_quad,
                           double* d_elem) {
-  ensure_tables(ctx);
   const int bs = 128;
   element_setup_kernel<<<(unsigned)((T + bs - 1) / bs), bs, 0, ctx->stream>>>(
       d_p, d_p + V, d_edofs, T, d_cores, mat.n_cores, mat.eps_core, mat.eps_clad, d_eps_at_quad, d_elem);
@@ -255,7 +253,6 @@ void launch_expand_rows(plfem_ctx* ctx, const DevPattern& pat) {
 void launch_assemble(plfem_ctx* ctx, const DevPattern& pat, const int32_t* d_n2e_ptr, const int32_t* d_n2e,
                      const int32_t* d_edofs, const double* d_elem, double k0sq, double alpha, bool export_mode,
                      double* d_vals, uint32_t* d_flags) {
-  ensure_tables(ctx);
   const int bs = 128;
   const unsigned grid = (unsigned)((pat.nnz + bs - 1) / bs);
   if (export_mode)

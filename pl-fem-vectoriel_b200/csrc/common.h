@@ -109,6 +109,7 @@ struct RefTables {  // shape functions at the quadrature points, [i*6 + q]
   double phi[36], dx[36], dy[36], w[6], qx[6], qy[6];
 };
 const RefTables& ref_tables();
+void upload_tables();
 
 // ---- kernels (assembly.cu) -----------------------------------------------------------------------
 void launch_element_setup(plfem_ctx* ctx, const double* d_p, const int32_t* d_edofs, int64_t V, int64_t T,

@@ -302,16 +302,45 @@ void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, const DevPlan& D, co
   // OP application: block-LDL^T solve + fixed number of refinement steps with the true operator
   // (the pivot blocks are not pivoted against each other, so one raw solve carries a backward error
   // of ~1e-9 relative; each step squares the contraction and the composite stays a fixed symmetric
-  // linear operator, which is what Lanczos needs)
-  auto apply_op = [&](const double* bvec, double* out) {
-    run_solve(ctx, D, bvec, out);
-    for (int it = 0; it < refine_steps; ++it) {
-      resid_k_kernel<<<gspmm, 256, 0, st>>>(pat.n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz, sigma, (const double2*)out,
-                                            (const double2*)bvec, (double2*)rt.p);
-      run_solve(ctx, D, rt.p, rdx.p);
-      add_kernel<<<gm, 256, 0, st>>>(out, rdx.p, m);
-      ctx->launches += 2;
+  // linear operator, which is what Lanczos needs).  The whole application — 2 sweeps x levels x
+  // (1 + refine) launches — is captured once into a CUDA graph on fixed buffers (opin -> r) and
+  // replayed, so the CPU issues one launch per operator application instead of ~70.
+  DevBuf<double> opin;
+  opin.alloc(ctx, m);
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  int graph_nodes = 0;
+  {
+    const int before = ctx->launches;
+    PLFEM_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    try {
+      run_solve(ctx, D, opin.p, r.p);
+      for (int it = 0; it < refine_steps; ++it) {
+        resid_k_kernel<<<gspmm, 256, 0, st>>>(pat.n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz, sigma, (const double2*)r.p,
+                                              (const double2*)opin.p, (double2*)rt.p);
+        run_solve(ctx, D, rt.p, rdx.p);
+        add_kernel<<<gm, 256, 0, st>>>(r.p, rdx.p, m);
+        ctx->launches += 2;
+      }
+    } catch (...) {
+      cudaGraph_t dead = nullptr;
+      cudaStreamEndCapture(st, &dead);
+      if (dead) cudaGraphDestroy(dead);
+      throw;
     }
+    PLFEM_CUDA(cudaStreamEndCapture(st, &graph));
+    graph_nodes = ctx->launches - before;
+    ctx->launches = before;
+    PLFEM_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
+  }
+  struct GraphGuard {
+    cudaGraph_t g; cudaGraphExec_t e;
+    ~GraphGuard() { if (e) cudaGraphExecDestroy(e); if (g) cudaGraphDestroy(g); }
+  } guard{graph, gexec};
+  auto apply_op = [&](const double* bvec) {   // r = OP(bvec)
+    PLFEM_CUDA(cudaMemcpyAsync(opin.p, bvec, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    PLFEM_CUDA(cudaGraphLaunch(gexec, st));
+    ctx->launches += graph_nodes;
   };
 
   // start vector: v0 / ||v0||_B
@@ -330,7 +359,7 @@ void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, const DevPlan& D, co
   for (;;) {
     for (int j = p; j < ncv; ++j) {
       double* Vc = V[cur].p; double* BVc = BV[cur].p;
-      apply_op(BVc + (int64_t)j * ld, r.p);                                   // r = OP v_j
+      apply_op(BVc + (int64_t)j * ld);                                        // r = OP v_j
       res.n_op++;
       dots_kernel<<<j + 1, RED_T, 0, st>>>(BVc, ld, r.p, m, h1.p);            // CGS pass 1
       update_kernel<<<gm, 256, 0, st>>>(Vc, ld, h1.p, j + 1, m, r.p);

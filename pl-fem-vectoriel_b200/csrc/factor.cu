@@ -25,8 +25,7 @@ namespace {
 constexpr int GT = 64;        // GEMM tile (GT x GT outputs per CTA)
 constexpr int GK = 16;        // GEMM k-step
 constexpr int EA_COLS = 8;    // extend-add slab width in parent node columns
-constexpr int FWD_ROWS = 128; // forward sweep: rows (unknowns) per CTA
-constexpr int BWD_COLS = 16;  // backward sweep: columns (unknowns) per CTA
+constexpr int BWD_COLS = 8;   // backward sweep: pivot columns per CTA (one warp each)
 constexpr int MAX_PIV = 128;  // largest pivot block (unknowns) the in-shared-memory inverse handles
 
 struct PlanView {
@@ -101,7 +100,9 @@ __global__ void __launch_bounds__(256) extend_add_kernel(const int4* __restrict_
 }
 
 // ---- pivot block inverse: Gauss-Jordan with partial pivoting in shared memory, one CTA per front ------
-__global__ void __launch_bounds__(256) invert_kernel(const int32_t* __restrict__ fronts, PlanView P, int32_t* status) {
+// Thread layout: i = tid % MP (row), jg = tid / MP (column group), MP = m rounded up to 32/64/128, so the
+// rank-1 update of step k needs no integer division and touches shared memory conflict-free.
+__global__ void __launch_bounds__(1024) invert_kernel(const int32_t* __restrict__ fronts, PlanView P, int32_t* status) {
   extern __shared__ double sm[];
   const int f = fronts[blockIdx.x];
   const int m = 2 * P.s[f];
@@ -115,14 +116,17 @@ __global__ void __launch_bounds__(256) invert_kernel(const int32_t* __restrict__
   __shared__ int src[MAX_PIV];
   __shared__ int s_p;
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int t = tid; t < m * m; t += nt) { const int i = t % m, j = t / m; a[i + j * lds] = F[(int64_t)j * ld + i]; }
+  const int MP = (m <= 32) ? 32 : (m <= 64 ? 64 : 128);
+  const int i = tid & (MP - 1), jg = tid / MP, ng = nt / MP;
+  if (i < m)
+    for (int j = jg; j < m; j += ng) a[i + j * lds] = F[(int64_t)j * ld + i];
   __syncthreads();
   for (int k = 0; k < m; ++k) {
     if (tid < 32) {
       double best = -1.0; int bi = k;
-      for (int i = k + tid; i < m; i += 32) {
-        const double v = fabs(a[i + k * lds]);
-        if (v > best) { best = v; bi = i; }   // NaN never wins; all-NaN column keeps bi = k
+      for (int r = k + tid; r < m; r += 32) {
+        const double v = fabs(a[r + k * lds]);
+        if (v > best) { best = v; bi = r; }   // NaN never wins; an all-NaN column keeps bi = k
       }
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) {
@@ -138,27 +142,30 @@ __global__ void __launch_bounds__(256) invert_kernel(const int32_t* __restrict__
     __syncthreads();
     const int p = s_p;
     const double inv = 1.0 / a[p + k * lds];
-    // row swap k <-> p fused with the copies of the pivot row (scaled) and pivot column
-    for (int j = tid; j < m; j += nt) {
+    // row swap k <-> p fused with the copies of the scaled pivot row (first m threads) and of the
+    // pivot column (last m threads)
+    if (tid < m) {
+      const int j = tid;
       const double ak = a[k + j * lds], ap = a[p + j * lds];
       rowk[j] = ap * inv;
       if (p != k && j != k) a[p + j * lds] = ak;
     }
-    for (int i = tid; i < m; i += nt) {
+    if (tid >= nt - m) {
+      const int r = tid - (nt - m);
       double v;
-      if (i == k) v = 0.0;                         // unused
-      else if (i == p) v = a[k + k * lds];         // row p now holds old row k
-      else v = a[i + k * lds];
-      colk[i] = v;
+      if (r == k) v = 0.0;                         // unused
+      else if (r == p) v = a[k + k * lds];         // row p now holds old row k
+      else v = a[r + k * lds];
+      colk[r] = v;
     }
     __syncthreads();
-    for (int t = tid; t < m * m; t += nt) {
-      const int i = t % m, j = t / m;
-      double v;
-      if (i == k) v = (j == k) ? inv : rowk[j];
-      else if (j == k) v = -colk[i] * inv;
-      else v = a[i + j * lds] - colk[i] * rowk[j];
-      a[i + j * lds] = v;
+    if (i < m) {
+      const double ci = colk[i];
+      if (i == k) {
+        for (int j = jg; j < m; j += ng) a[i + j * lds] = (j == k) ? inv : rowk[j];
+      } else {
+        for (int j = jg; j < m; j += ng) a[i + j * lds] = (j == k) ? -ci * inv : a[i + j * lds] - ci * rowk[j];
+      }
     }
     __syncthreads();
   }
@@ -167,7 +174,8 @@ __global__ void __launch_bounds__(256) invert_kernel(const int32_t* __restrict__
     for (int k = m - 1; k >= 0; --k) { const int t = src[k]; src[k] = src[piv[k]]; src[piv[k]] = t; }
   }
   __syncthreads();
-  for (int t = tid; t < m * m; t += nt) { const int i = t % m, j = t / m; F[(int64_t)j * ld + i] = a[i + src[j] * lds]; }
+  if (i < m)
+    for (int j = jg; j < m; j += ng) F[(int64_t)j * ld + i] = a[i + src[j] * lds];
 }
 
 // ---- tiled FP64 GEMM used for W^T and the Schur update -------------------------------------------------
@@ -257,19 +265,23 @@ __global__ void __launch_bounds__(256) gemm_schur_kernel(const int4* __restrict_
                          F + (int64_t)s2 * ld + s2, ld, u2, u2, s2, t.y, t.z);
 }
 
-// ---- forward sweep: one CTA per (front, slab of rows) ---------------------------------------------------
-__global__ void __launch_bounds__(FWD_ROWS) forward_kernel(const int4* __restrict__ slabs, PlanView P,
-                                                            const double* __restrict__ rhs, double* __restrict__ z,
-                                                            double* __restrict__ upd) {
+// ---- forward sweep: one CTA (8 warps) per (front, slab of 32*G rows) ------------------------------------
+// The 8 warps form G row groups x 8/G slices of the k range (the 2s pivot columns), so a big front at the
+// top of the tree, where only a handful of CTAs exist, has 8-16 independent loads in flight per lane
+// instead of a 128-long dependent chain; partial sums meet in shared memory.
+__global__ void __launch_bounds__(256) forward_kernel(const int4* __restrict__ slabs, PlanView P,
+                                                       const double* __restrict__ rhs, double* __restrict__ z,
+                                                       double* __restrict__ upd) {
   __shared__ double y1[MAX_PIV];
-  __shared__ double yt[FWD_ROWS];
+  __shared__ double yt[256];
+  __shared__ double part[8][32];
   const int4 sl = slabs[blockIdx.x];
-  const int f = sl.x, row0 = sl.y, nrows = sl.z;
+  const int f = sl.x, row0 = sl.y, nrows = sl.z, G = sl.w;
   const int s2 = 2 * P.s[f], u2 = 2 * front_u(P, f);
   const int64_t ld = s2 + u2;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t g0 = 2 * (int64_t)P.first[f];
-  for (int i = tid; i < s2; i += FWD_ROWS) y1[i] = rhs[g0 + i];
+  for (int i = tid; i < s2; i += 256) y1[i] = rhs[g0 + i];
   yt[tid] = 0.0;
   __syncthreads();
   for (int q = P.cptr[f]; q < P.cptr[f + 1]; ++q) {
@@ -277,68 +289,62 @@ __global__ void __launch_bounds__(FWD_ROWS) forward_kernel(const int4* __restric
     const int uc2 = 2 * front_u(P, ch);
     const int32_t* cm = P.cmap + P.cmap_ptr[ch];
     const double* uv = upd + P.uoff[ch];
-    for (int k = tid; k < uc2; k += FWD_ROWS) {
+    for (int k = tid; k < uc2; k += 256) {
       const int t = 2 * cm[k >> 1] + (k & 1);
       if (t < s2) y1[t] += uv[k];
       else if (t >= row0 && t < row0 + nrows) yt[t - row0] += uv[k];
     }
-    __syncthreads();
+    __syncthreads();   // children may hit the same entry: keep child order
   }
-  if (tid < nrows) {
-    const int row = row0 + tid;
-    const double* M = P.pool + P.foff[f] + row;
-    double acc0 = 0.0, acc1 = 0.0;
-    int k = 0;
-    for (; k + 1 < s2; k += 2) {
-      acc0 = fma(M[(int64_t)k * ld], y1[k], acc0);
-      acc1 = fma(M[(int64_t)(k + 1) * ld], y1[k + 1], acc1);
+  const int nks = 8 / G, rg = warp % G, ks = warp / G;
+  const int lr = rg * 32 + lane;            // row within the slab
+  double acc = 0.0;
+  if (lr < nrows) {
+    const double* M = P.pool + P.foff[f] + (row0 + lr);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int k = ks;
+    for (; k + 3 * nks < s2; k += 4 * nks) {
+      a0 = fma(M[(int64_t)k * ld], y1[k], a0);
+      a1 = fma(M[(int64_t)(k + nks) * ld], y1[k + nks], a1);
+      a2 = fma(M[(int64_t)(k + 2 * nks) * ld], y1[k + 2 * nks], a2);
+      a3 = fma(M[(int64_t)(k + 3 * nks) * ld], y1[k + 3 * nks], a3);
     }
-    if (k < s2) acc0 = fma(M[(int64_t)k * ld], y1[k], acc0);
-    const double acc = acc0 + acc1;
-    if (row < s2) z[g0 + row] = acc;
-    else upd[P.uoff[f] + (row - s2)] = yt[tid] - acc;
+    for (; k < s2; k += nks) a0 = fma(M[(int64_t)k * ld], y1[k], a0);
+    acc = (a0 + a1) + (a2 + a3);
+  }
+  part[warp][lane] = acc;
+  __syncthreads();
+  if (ks == 0 && lr < nrows) {
+    double t = 0.0;
+    for (int q = 0; q < nks; ++q) t += part[q * G + rg][lane];
+    const int row = row0 + lr;
+    if (row < s2) z[g0 + row] = t;
+    else upd[P.uoff[f] + (row - s2)] = yt[lr] - t;
   }
 }
 
-// ---- backward sweep: one CTA per (front, slab of columns), one warp per column --------------------------
+// ---- backward sweep: one warp per pivot column, 8 columns per CTA ----------------------------------------
 __global__ void __launch_bounds__(256) backward_kernel(const int4* __restrict__ slabs, PlanView P, double* __restrict__ x) {
-  constexpr int CH = 2048;
-  __shared__ double x2[CH];
   const int4 sl = slabs[blockIdx.x];
   const int f = sl.x, col0 = sl.y, ncols = sl.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= ncols) return;
   const int s2 = 2 * P.s[f], u2 = 2 * front_u(P, f);
   const int64_t ld = s2 + u2;
-  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
   const int64_t g0 = 2 * (int64_t)P.first[f];
   const int32_t* st = P.strct + P.sptr[f];
-  const double* W = P.pool + P.foff[f] + s2;   // F21new(j, i) at i*ld + j
-  double acc[BWD_COLS / 8];
-#pragma unroll
-  for (int c = 0; c < BWD_COLS / 8; ++c) acc[c] = 0.0;
-  for (int j0 = 0; j0 < u2; j0 += CH) {
-    const int len = min(CH, u2 - j0);
-    __syncthreads();
-    for (int j = tid; j < len; j += 256) { const int jj = j0 + j; x2[j] = x[2 * (int64_t)st[jj >> 1] + (jj & 1)]; }
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c < BWD_COLS / 8; ++c) {
-      const int colr = warp + 8 * c;
-      if (colr < ncols) {
-        const double* wc = W + (int64_t)(col0 + colr) * ld + j0;
-        double a = 0.0;
-        for (int j = lane; j < len; j += 32) a = fma(wc[j], x2[j], a);
-        acc[c] += a;
-      }
-    }
+  const double* wc = P.pool + P.foff[f] + s2 + (int64_t)(col0 + warp) * ld;   // F21new(j, col) at col*ld + s2 + j
+  double a0 = 0.0, a1 = 0.0;
+  int j = lane;
+  for (; j + 32 < u2; j += 64) {
+    a0 = fma(wc[j], x[2 * (int64_t)st[j >> 1] + (j & 1)], a0);
+    a1 = fma(wc[j + 32], x[2 * (int64_t)st[(j + 32) >> 1] + ((j + 32) & 1)], a1);
   }
+  if (j < u2) a0 = fma(wc[j], x[2 * (int64_t)st[j >> 1] + (j & 1)], a0);
+  double a = a0 + a1;
 #pragma unroll
-  for (int c = 0; c < BWD_COLS / 8; ++c) {
-    double a = acc[c];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) a += __shfl_down_sync(0xffffffffu, a, off);
-    const int colr = warp + 8 * c;
-    if (lane == 0 && colr < ncols) x[g0 + col0 + colr] -= a;
-  }
+  for (int off = 16; off > 0; off >>= 1) a += __shfl_down_sync(0xffffffffu, a, off);
+  if (lane == 0) x[g0 + col0 + warp] -= a;
 }
 
 PlanView view(const DevPlan& D) {
@@ -381,7 +387,11 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
         for (int a0 = 0; a0 < u2; a0 += GT) stl.push_back(make_int4(f, a0, b0, 0));
       if (P.cptr[f + 1] > P.cptr[f])
         for (int c0 = 0; c0 < nf; c0 += EA_COLS) ea.push_back(make_int4(f, c0, std::min(c0 + EA_COLS, nf), 0));
-      for (int r0 = 0; r0 < s2 + u2; r0 += FWD_ROWS) fw.push_back(make_int4(f, r0, std::min(FWD_ROWS, s2 + u2 - r0), 0));
+      {
+        const int rows = s2 + u2;
+        const int G = rows <= 32 ? 1 : (rows <= 64 ? 2 : (rows <= 128 ? 4 : 1));
+        for (int r0 = 0; r0 < rows; r0 += 32 * G) fw.push_back(make_int4(f, r0, std::min(32 * G, rows - r0), G));
+      }
       if (u2 > 0)
         for (int c0 = 0; c0 < s2; c0 += BWD_COLS) bw.push_back(make_int4(f, c0, std::min(BWD_COLS, s2 - c0), 0));
     }
@@ -420,7 +430,7 @@ void run_factorization(plfem_ctx* ctx, const DevPlan& D) {
       ctx->launches++;
     }
     const int nfl = D.lptr[l + 1] - D.lptr[l];
-    invert_kernel<<<nfl, 256, invert_smem(D.lmax_m[l]), ctx->stream>>>(D.lfront.p + D.lptr[l], v, D.status.p);
+    invert_kernel<<<nfl, D.lmax_m[l] > 64 ? 1024 : 256, invert_smem(D.lmax_m[l]), ctx->stream>>>(D.lfront.p + D.lptr[l], v, D.status.p);
     ctx->launches++;
     const int nw = D.w_ptr[l + 1] - D.w_ptr[l];
     if (nw > 0) {
@@ -440,7 +450,7 @@ void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double
   const PlanView v = view(D);
   for (int l = 0; l < D.nlevels; ++l) {
     const int nsl = D.fwd_ptr[l + 1] - D.fwd_ptr[l];
-    forward_kernel<<<nsl, FWD_ROWS, 0, ctx->stream>>>(D.fwd_slabs.p + D.fwd_ptr[l], v, b, z, D.upd.p);
+    forward_kernel<<<nsl, 256, 0, ctx->stream>>>(D.fwd_slabs.p + D.fwd_ptr[l], v, b, z, D.upd.p);
     ctx->launches++;
   }
   PLFEM_CUDA(cudaGetLastError());

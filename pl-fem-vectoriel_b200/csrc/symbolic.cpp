@@ -6,6 +6,9 @@
 #include <cmath>
 #include <numeric>
 #include <stdexcept>
+#include <atomic>
+#include <cstring>
+#include <thread>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -108,9 +111,38 @@ void build_dof_tables(const double* p, const int64_t* t, int64_t V, int64_t T, D
   }
 }
 
+namespace {
+std::atomic<int> g_host_threads{0};
+
+int host_threads() {
+  const int set = g_host_threads.load(std::memory_order_relaxed);
+  if (set > 0) return set;
+  static const int n = [] {
+    if (const char* e = std::getenv("PLFEM_HOST_THREADS")) return std::max(1, atoi(e));
+    const unsigned hc = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min(hc ? hc : 1u, 8u));
+  }();
+  return n;
+}
+
+template <class F>
+void parallel_for(int64_t n, int64_t grain, F&& fn) {
+  const int nt = (int)std::min<int64_t>(host_threads(), std::max<int64_t>(1, n / std::max<int64_t>(grain, 1)));
+  if (nt <= 1) { fn(0, n); return; }
+  std::vector<std::thread> th;
+  const int64_t chunk = (n + nt - 1) / nt;
+  for (int t = 1; t < nt; ++t) th.emplace_back([&, t] { fn(std::min(n, t * chunk), std::min(n, (t + 1) * chunk)); });
+  fn(0, std::min(n, chunk));
+  for (auto& x : th) x.join();
+}
+
+}  // namespace
+
 // ------------------------------------------------------------------------------------------------
 // Sparsity pattern in an arbitrary renumbering
 // ------------------------------------------------------------------------------------------------
+void set_host_threads(int n) { g_host_threads.store(std::max(0, n)); }
+
 void build_pattern(const DofTables& d, const std::vector<int32_t>& new_of_old, int32_t n_new, Pattern& out) {
   out.n = n_new;
   out.new_of_old = new_of_old;
@@ -118,22 +150,70 @@ void build_pattern(const DofTables& d, const std::vector<int32_t>& new_of_old, i
   for (int64_t o = 0; o < d.N; ++o)
     if (new_of_old[o] >= 0) out.old_of_new[new_of_old[o]] = (int32_t)o;
   out.rowptr.assign(n_new + 1, 0);
-  out.col.clear();
-  out.col.reserve((size_t)n_new * 12);
-  std::vector<int32_t> stamp(n_new, -1);
-  for (int32_t r = 0; r < n_new; ++r) {
-    const int32_t o = out.old_of_new[r];
-    const size_t b = out.col.size();
-    for (int32_t q = d.n2e_ptr[o]; q < d.n2e_ptr[o + 1]; ++q) {
-      const int32_t* ed = &d.edofs[6 * (int64_t)d.n2e[q]];
-      for (int k = 0; k < 6; ++k) {
-        const int32_t c = new_of_old[ed[k]];
-        if (c >= 0 && stamp[c] != r) { stamp[c] = r; out.col.push_back(c); }
+  // rows are independent: each worker fills a private column buffer for its row range
+  const int nt = host_threads();
+  std::vector<std::vector<int32_t>> bufs(nt);
+  std::vector<int64_t> lo(nt + 1, n_new);
+  const int64_t chunk = ((int64_t)n_new + nt - 1) / nt;
+  for (int t = 0; t <= nt; ++t) lo[t] = std::min<int64_t>(n_new, t * chunk);
+  auto work = [&](int t) {
+    std::vector<int32_t>& col = bufs[t];
+    col.reserve((size_t)(lo[t + 1] - lo[t]) * 12);
+    std::vector<int32_t> stamp(n_new, -1);
+    for (int32_t r = (int32_t)lo[t]; r < (int32_t)lo[t + 1]; ++r) {
+      const int32_t o = out.old_of_new[r];
+      const size_t b0 = col.size();
+      for (int32_t q = d.n2e_ptr[o]; q < d.n2e_ptr[o + 1]; ++q) {
+        const int32_t* ed = &d.edofs[6 * (int64_t)d.n2e[q]];
+        for (int k = 0; k < 6; ++k) {
+          const int32_t c = new_of_old[ed[k]];
+          if (c >= 0 && stamp[c] != r) { stamp[c] = r; col.push_back(c); }
+        }
       }
+      std::sort(col.begin() + b0, col.end());
+      out.rowptr[r + 1] = (int32_t)(col.size() - b0);
     }
-    std::sort(out.col.begin() + b, out.col.end());
-    out.rowptr[r + 1] = (int32_t)out.col.size();
+  };
+  if (nt > 1 && n_new > 4096) {
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+  } else {
+    lo.assign(nt + 1, n_new); lo[0] = 0;
+    work(0);
   }
+  for (int32_t r = 0; r < n_new; ++r) out.rowptr[r + 1] += out.rowptr[r];
+  out.col.resize(out.rowptr[n_new]);
+  for (int t = 0; t < nt; ++t)
+    if (!bufs[t].empty()) std::copy(bufs[t].begin(), bufs[t].end(), out.col.begin() + out.rowptr[lo[t]]);
+}
+
+// Same pattern in a new numbering of the same node set: new row r is old row old_of[r]; columns are
+// relabelled with new_of and re-sorted.  `full_ids[old]` is the DOF id stored in old_of_new.
+void relabel_pattern(const Pattern& src, const std::vector<int32_t>& old_of, const std::vector<int32_t>& new_of,
+                     const std::vector<int32_t>& full_ids, int64_t N_full, Pattern& out) {
+  const int32_t n = src.n;
+  out.n = n;
+  out.old_of_new.resize(n);
+  out.new_of_old.assign(N_full, -1);
+  out.rowptr.assign(n + 1, 0);
+  for (int32_t r = 0; r < n; ++r) {
+    const int32_t o = old_of[r];
+    out.old_of_new[r] = full_ids[o];
+    out.new_of_old[full_ids[o]] = r;
+    out.rowptr[r + 1] = out.rowptr[r] + (src.rowptr[o + 1] - src.rowptr[o]);
+  }
+  out.col.resize(out.rowptr[n]);
+  parallel_for(n, 2048, [&](int64_t b, int64_t e) {
+    for (int64_t r = b; r < e; ++r) {
+      const int32_t o = old_of[r];
+      int32_t* dst = out.col.data() + out.rowptr[r];
+      const int32_t len = src.rowptr[o + 1] - src.rowptr[o];
+      for (int32_t q = 0; q < len; ++q) dst[q] = new_of[src.col[src.rowptr[o] + q]];
+      std::sort(dst, dst + len);
+    }
+  });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -141,9 +221,43 @@ void build_pattern(const DofTables& d, const std::vector<int32_t>& new_of_old, i
 // ------------------------------------------------------------------------------------------------
 namespace {
 
+// order[r] = index of the r-th smallest key; stable (ties keep ascending index). LSD radix on the
+// order-preserving integer image of the doubles.
+void argsort_doubles(const std::vector<double>& key, std::vector<int32_t>& order) {
+  const int32_t n = (int32_t)key.size();
+  std::vector<uint64_t> k(n), k2(n);
+  std::vector<int32_t> a(n), b(n);
+  for (int32_t i = 0; i < n; ++i) {
+    uint64_t u; std::memcpy(&u, &key[i], 8);
+    k[i] = (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+    a[i] = i;
+  }
+  for (int pass = 0; pass < 8; ++pass) {
+    const int sh = 8 * pass;
+    int32_t cnt[257] = {0};
+    for (int32_t i = 0; i < n; ++i) cnt[((k[i] >> sh) & 0xff) + 1]++;
+    bool single = false;
+    for (int c = 1; c <= 256; ++c) if (cnt[c] == n) single = true;
+    if (single) continue;
+    for (int c = 0; c < 256; ++c) cnt[c + 1] += cnt[c];
+    for (int32_t i = 0; i < n; ++i) { const int32_t d = cnt[(k[i] >> sh) & 0xff]++; k2[d] = k[i]; b[d] = a[i]; }
+    k.swap(k2); a.swap(b);
+  }
+  order.swap(a);
+}
+
 struct TreeNode {
   std::vector<int32_t> own;       // interior indices, elimination order inside the node
-  std::vector<int32_t> children;  // tree node ids
+  std::vector<int32_t> children;  // tree node ids (within the same Forest)
+};
+
+struct Forest {
+  std::vector<TreeNode> nodes;
+  void absorb(Forest&& o, std::vector<int32_t>& heads, const std::vector<int32_t>& oheads) {
+    const int32_t off = (int32_t)nodes.size();
+    for (auto& tn : o.nodes) { for (auto& c : tn.children) c += off; nodes.push_back(std::move(tn)); }
+    for (int32_t h : oheads) heads.push_back(h + off);
+  }
 };
 
 struct Dissector {
@@ -152,25 +266,29 @@ struct Dissector {
   const double* x;
   const double* y;
   const SymbolicOptions& opt;
-  std::vector<TreeNode> nodes;
   std::vector<int32_t> side;   // per node: stamp of the subset/half it currently belongs to
   std::vector<int32_t> rank;   // per node: position in the direction list being examined
   std::vector<uint8_t> insep;  // per node: chosen as separator in the current call
-  int32_t stamp = 0;
+  std::atomic<int32_t> stamp{0};
   std::vector<int32_t> lists[ND];  // the node set of the current call, sorted along each direction
-  std::vector<int32_t> tmp, dl, dr;
+  struct Scratch { std::vector<int32_t> tmp, dl, dr; };
 
   Dissector(const Pattern& a, const double* x_, const double* y_, const SymbolicOptions& o)
       : adj(a), x(x_), y(y_), opt(o), side(a.n, -1), rank(a.n, 0), insep(a.n, 0) {
     const int32_t n = a.n;
-    std::vector<std::pair<double, int32_t>> kv(n);
-    for (int d = 0; d < ND; ++d) {
-      for (int32_t v = 0; v < n; ++v) kv[v] = {proj(d, v), v};
-      std::sort(kv.begin(), kv.end());
-      lists[d].resize(n);
-      for (int32_t r = 0; r < n; ++r) lists[d][r] = kv[r].second;
+    auto one = [&](int d) {
+      std::vector<double> key(n);
+      for (int32_t v = 0; v < n; ++v) key[v] = proj(d, v);
+      argsort_doubles(key, lists[d]);
+    };
+    if (host_threads() >= ND && n > 4096) {
+      std::vector<std::thread> th;
+      for (int d = 1; d < ND; ++d) th.emplace_back(one, d);
+      one(0);
+      for (auto& t : th) t.join();
+    } else {
+      for (int d = 0; d < ND; ++d) one(d);
     }
-    tmp.resize(n);
   }
 
   double proj(int d, int32_t v) const {
@@ -178,14 +296,14 @@ struct Dissector {
   }
 
   // Dissect the node set stored (in ND different orders) at lists[d][off .. off+n).
-  // Appends the ids of the tree nodes heading the resulting sub-forest to `heads`.
-  void dissect(int32_t off, int32_t n, std::vector<int32_t>& heads) {
+  // Appends tree nodes to `F` and the ids of the nodes heading the resulting sub-forest to `heads`.
+  void dissect(int32_t off, int32_t n, Forest& F, std::vector<int32_t>& heads, Scratch& sc, int par_budget) {
     if (n == 0) return;
     int32_t* L0 = lists[0].data() + off;
     if (n <= opt.leaf_nodes) {
       TreeNode leaf; leaf.own.assign(L0, L0 + n);
-      nodes.push_back(std::move(leaf));
-      heads.push_back((int32_t)nodes.size() - 1);
+      F.nodes.push_back(std::move(leaf));
+      heads.push_back((int32_t)F.nodes.size() - 1);
       return;
     }
     // Candidate cuts: ND directions x every split position in the middle 40%.  Along a direction a
@@ -197,9 +315,11 @@ struct Dissector {
     const int ndir = (n >= opt.search_min_nodes) ? ND : 2;
     double best_cost = 1e300; int best_dir = 0; int32_t best_h = n / 2; bool best_left = true;
     const int32_t h0 = std::max<int32_t>(1, (int32_t)(0.3 * n)), h1 = std::min<int32_t>(n - 1, (int32_t)(0.7 * n));
-    for (int d = 0; d < ndir; ++d) {
+    struct Cand { double cost = 1e300; int32_t h = 0; bool left = true; };
+    Cand cand[ND];
+    auto eval_dir = [&](int d, std::vector<int32_t>& rk, std::vector<int32_t>& dl, std::vector<int32_t>& dr) {
       const int32_t* Ld = lists[d].data() + off;
-      for (int32_t r = 0; r < n; ++r) rank[Ld[r]] = r;
+      for (int32_t r = 0; r < n; ++r) rk[Ld[r]] = r;
       dl.assign(n + 2, 0); dr.assign(n + 2, 0);
       for (int32_t r = 0; r < n; ++r) {
         const int32_t v = Ld[r];
@@ -207,21 +327,35 @@ struct Dissector {
         for (int32_t q = adj.rowptr[v]; q < adj.rowptr[v + 1]; ++q) {
           const int32_t w = adj.col[q];
           if (side[w] != cur) continue;
-          const int32_t rw = rank[w];
+          const int32_t rw = rk[w];
           hi = std::max(hi, rw); lo = std::min(lo, rw);
         }
         dl[r + 1]++; dl[hi + 1]--;   // left-boundary member for h in (r, hi]
         dr[lo + 1]++; dr[r + 1]--;   // right-boundary member for h in (lo, r]
       }
       int32_t cl = 0, cr = 0;
+      Cand c;
       for (int32_t h = 1; h <= h1; ++h) {
         cl += dl[h]; cr += dr[h];
         if (h < h0) continue;
         const double imb = std::fabs(2.0 * h / n - 1.0);
         const double cost = (std::min(cl, cr) + 1.0) * (1.0 + 1.5 * imb);
-        if (cost < best_cost) { best_cost = cost; best_dir = d; best_h = h; best_left = cl <= cr; }
+        if (cost < c.cost) { c.cost = cost; c.h = h; c.left = cl <= cr; }
       }
+      cand[d] = c;
+    };
+    if (par_budget >= ndir && ndir > 1 && n >= 4096) {
+      // top of the tree: few, large calls — evaluate the directions concurrently (private rank arrays)
+      std::vector<std::thread> th;
+      std::vector<std::vector<int32_t>> rks(ndir, std::vector<int32_t>()), dls(ndir), drs(ndir);
+      for (int d = 1; d < ndir; ++d) th.emplace_back([&, d] { rks[d].resize(adj.n); eval_dir(d, rks[d], dls[d], drs[d]); });
+      eval_dir(0, rank, sc.dl, sc.dr);
+      for (auto& t : th) t.join();
+    } else {
+      for (int d = 0; d < ndir; ++d) eval_dir(d, rank, sc.dl, sc.dr);
     }
+    for (int d = 0; d < ndir; ++d)
+      if (cand[d].cost < best_cost) { best_cost = cand[d].cost; best_dir = d; best_h = cand[d].h; best_left = cand[d].left; }
     const int32_t h = best_h;
     const int32_t* Lb = lists[best_dir].data() + off;
     const int32_t sl = ++stamp, sr = ++stamp;
@@ -238,21 +372,33 @@ struct Dissector {
     }
     // stable three-way partition of every direction list: [left | right | separator]
     int32_t nl = 0, nr = 0;
+    sc.tmp.resize(n);
     for (int d = 0; d < ND; ++d) {
       int32_t* Ld = lists[d].data() + off;
       int32_t a = 0, b = 0;
       for (int32_t i = 0; i < n; ++i) {
         const int32_t v = Ld[i];
         if (insep[v]) continue;
-        if (side[v] == sl) Ld[a++] = v; else tmp[b++] = v;
+        if (side[v] == sl) Ld[a++] = v; else sc.tmp[b++] = v;
       }
-      std::copy(tmp.begin(), tmp.begin() + b, Ld + a);
+      std::copy(sc.tmp.begin(), sc.tmp.begin() + b, Ld + a);
       nl = a; nr = b;
     }
     for (int32_t v : sep) { insep[v] = 0; side[v] = -1; }
     std::vector<int32_t> kids;
-    dissect(off, nl, kids);
-    dissect(off + nl, nr, kids);
+    if (par_budget > 1 && std::min(nl, nr) >= 1024) {
+      // the two halves are independent: left half on a new thread with its own forest and scratch
+      Forest FL; std::vector<int32_t> hl;
+      std::thread th([&] { Scratch s2; dissect(off, nl, FL, hl, s2, par_budget / 2); });
+      dissect(off + nl, nr, F, kids, sc, par_budget - par_budget / 2);
+      th.join();
+      std::vector<int32_t> right_kids; right_kids.swap(kids);
+      F.absorb(std::move(FL), kids, hl);
+      kids.insert(kids.end(), right_kids.begin(), right_kids.end());
+    } else {
+      dissect(off, nl, F, kids, sc, 1);
+      dissect(off + nl, nr, F, kids, sc, 1);
+    }
     if (sep.empty()) {  // disconnected halves: no front of its own, children go up
       heads.insert(heads.end(), kids.begin(), kids.end());
       return;
@@ -271,8 +417,8 @@ struct Dissector {
       TreeNode tn; tn.own.assign(sep.begin() + pos, sep.begin() + pos + len);
       pos += len;
       if (k == 0) tn.children = kids; else tn.children = {prev};
-      nodes.push_back(std::move(tn));
-      prev = (int32_t)nodes.size() - 1;
+      F.nodes.push_back(std::move(tn));
+      prev = (int32_t)F.nodes.size() - 1;
     }
     heads.push_back(prev);
   }
@@ -290,11 +436,15 @@ void build_front_plan(const Pattern& adj, const double* x, const double* y, cons
   Dissector D(adj, x, y, opt);
   const double tB = clk();
   std::vector<int32_t> roots;
-  D.dissect(0, n, roots);
+  Forest forest;
+  {
+    Dissector::Scratch sc;
+    D.dissect(0, n, forest, roots, sc, host_threads());
+  }
   const double tC = clk();
 
   // post-order numbering of tree nodes -> fronts
-  const int32_t nt = (int32_t)D.nodes.size();
+  const int32_t nt = (int32_t)forest.nodes.size();
   std::vector<int32_t> front_of(nt, -1), order; order.reserve(nt);
   {
     std::vector<std::pair<int32_t, size_t>> st;
@@ -302,7 +452,7 @@ void build_front_plan(const Pattern& adj, const double* x, const double* y, cons
       st.emplace_back(r, 0);
       while (!st.empty()) {
         auto& [v, k] = st.back();
-        if (k < D.nodes[v].children.size()) { int32_t ch = D.nodes[v].children[k++]; st.emplace_back(ch, 0); }
+        if (k < forest.nodes[v].children.size()) { int32_t ch = forest.nodes[v].children[k++]; st.emplace_back(ch, 0); }
         else { front_of[v] = (int32_t)order.size(); order.push_back(v); st.pop_back(); }
       }
     }
@@ -314,7 +464,7 @@ void build_front_plan(const Pattern& adj, const double* x, const double* y, cons
   std::vector<int32_t> new_of(n, -1);
   int32_t next = 0;
   for (int32_t f = 0; f < nf; ++f) {
-    const TreeNode& tn = D.nodes[order[f]];
+    const TreeNode& tn = forest.nodes[order[f]];
     P.first[f] = next; P.s[f] = (int32_t)tn.own.size();
     for (int32_t v : tn.own) { P.perm[next] = v; new_of[v] = next; P.sn_of[next] = f; ++next; }
     for (int32_t ch : tn.children) P.parent[front_of[ch]] = f;

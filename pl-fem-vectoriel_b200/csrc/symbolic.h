@@ -38,10 +38,16 @@ struct Pattern {
 };
 void build_pattern(const DofTables& d, const std::vector<int32_t>& new_of_old, int32_t n_new, Pattern& out);
 
+void relabel_pattern(const Pattern& src, const std::vector<int32_t>& old_of, const std::vector<int32_t>& new_of,
+                     const std::vector<int32_t>& full_ids, int64_t N_full, Pattern& out);
+
+// worker threads the symbolic phase may use per call (0 = default: min(cores, 8) or $PLFEM_HOST_THREADS)
+void set_host_threads(int n);
+
 struct SymbolicOptions {
   int leaf_nodes = 24;   // stop dissecting below this many nodes
   int max_sn_nodes = 64; // split separators into chains of supernodes of at most this many nodes
-  int search_min_nodes = 64; // subsets at least this large try 4 cut directions, smaller ones 1
+  int search_min_nodes = 512; // subsets at least this large try 4 cut directions, smaller ones 1
 };
 
 // Multifrontal plan on the interior nodes, in nested-dissection order.

@@ -97,13 +97,14 @@ def _polarization_label(P_x: float, P_y: float):
 
 class TrueVectorialMaxwellSolver:
     def __init__(self, geometry, use_pml: bool = False, n_modes: Optional[int] = None,
-                 device: int = 0, refinement: float = 1.0, config: Optional[SimulationConfig] = None):
+                 device: int = 0, refinement: float = 1.0, config: Optional[SimulationConfig] = None, ctx=None):
         _cabi.load()                          # fails loudly when the CUDA library cannot be built/loaded
         self.geometry = geometry
         self.k0 = geometry.k0
         self.use_pml = use_pml                # stored, never read — like the reference (`solver_fem.py:119`)
         self.n_modes = n_modes
         self.device = int(device)
+        self._ctx = ctx                       # explicit C-ABI context (one per host thread in a SolverPool)
         self.refinement = refinement
         self.config = config
         self.last_stats: Dict = {}
@@ -116,7 +117,7 @@ class TrueVectorialMaxwellSolver:
         if ent is None or ent[0] is not mesh:
             if len(self._problems) >= 4:
                 self._problems.pop(next(iter(self._problems)))[1].close()
-            ent = (mesh, _cabi.Problem(mesh, _cabi.Context.get(self.device)))
+            ent = (mesh, _cabi.Problem(mesh, self._ctx or _cabi.Context.get(self.device)))
             self._problems[id(mesh)] = ent
         return ent[1]
 
