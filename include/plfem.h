@@ -45,6 +45,8 @@ const char* plfem_last_error(const plfem_ctx* ctx);
 /* host threads the symbolic analysis of ONE solve may use (0 = default min(cores, 8)); lower it when several
  * contexts solve concurrently from different host threads */
 void plfem_set_host_threads(int n);
+/* CTAs per SM of the persistent operator kernel (default 4); use 8 / (contexts sharing the GPU), at least 1 */
+void plfem_ctx_set_coop_ctas(plfem_ctx* ctx, int ctas_per_sm);
 /* abi / build identification: "plfem <version> sm_100a" */
 const char* plfem_version(void);
 
@@ -125,7 +127,7 @@ typedef struct {
   int64_t factor_entries;           /* doubles read by one forward+backward sweep / 2 */
   int64_t front_pool_doubles;
   double factor_flops;
-  double max_residual;              /* max_i ||A x - lambda B x||_2 / ||(|A| + |lambda||B|) |x|||_2, true A and B */
+  double max_residual;              /* normwise backward error: max_i ||A x - lambda B x||_2 / ((||A||_F + |lambda| ||B||_F) ||x||_2) */
   float ms_symbolic, ms_assemble, ms_factor, ms_lanczos, ms_metrics, ms_total; /* host wall / CUDA events */
   int32_t kernel_launches;
 } plfem_solve_stats;
@@ -155,6 +157,8 @@ int plfem_plan_export(plfem_problem* pb, int32_t* perm, int32_t* first, int32_t*
                       int32_t* level, int32_t* sptr, int32_t* strct, int32_t* cmap_ptr, int32_t* cmap,
                       int64_t* foff);
 
+/* x = (A - sigma B)^-1 b with the factors of the last plfem_solve_modes (same sigma), reference ordering */
+int plfem_debug_solve(plfem_problem* pb, double sigma, const double* b, double* x, int refine);
 /* dense symmetric eigensolver used at Lanczos restarts: a is n*n column-major, overwritten by eigenvectors */
 int plfem_debug_symeig(int32_t n, double* a, double* w);
 

@@ -27,7 +27,8 @@ NMETRICS = 8
 SYMBOLS = ["plfem_ctx_create", "plfem_ctx_destroy", "plfem_last_error", "plfem_version",
            "plfem_problem_create", "plfem_problem_destroy", "plfem_problem_info", "plfem_problem_dofs",
            "plfem_quad_points", "plfem_assemble", "plfem_export_csr", "plfem_spmv_csr", "plfem_solve_modes",
-           "plfem_plan_sizes", "plfem_plan_export", "plfem_debug_symeig", "plfem_profile_kernels", "plfem_set_host_threads"]
+           "plfem_plan_sizes", "plfem_plan_export", "plfem_debug_symeig", "plfem_profile_kernels", "plfem_set_host_threads",
+           "plfem_debug_solve", "plfem_ctx_set_coop_ctas"]
 
 
 class MeshInfo(C.Structure):
@@ -99,6 +100,9 @@ def load():
         lib.plfem_plan_sizes.argtypes = [vp, c_i32, c_i32, p_i64]
         lib.plfem_plan_export.argtypes = [vp] + [p_i32] * 9 + [p_i64]
         lib.plfem_debug_symeig.argtypes = [c_i32, p_f64, p_f64]
+        lib.plfem_debug_solve.argtypes = [vp, c_f64, p_f64, p_f64, C.c_int]
+        lib.plfem_ctx_set_coop_ctas.argtypes = [vp, C.c_int]
+        lib.plfem_ctx_set_coop_ctas.restype = None
         lib.plfem_set_host_threads.argtypes = [C.c_int]
         lib.plfem_set_host_threads.restype = None
         lib.plfem_profile_kernels.argtypes = [vp, C.POINTER(Material), c_f64, C.c_int, p_f64, p_f64]
@@ -128,6 +132,9 @@ class Context:
         if device not in cls._cache:
             cls._cache[device] = cls(device)
         return cls._cache[device]
+
+    def set_coop_ctas(self, ctas_per_sm: int):
+        self.lib.plfem_ctx_set_coop_ctas(self.handle, int(ctas_per_sm))
 
     def check(self, st: int):
         if st != 0:
@@ -245,6 +252,13 @@ class Problem:
         self._check(self.lib.plfem_solve_modes(self.handle, C.byref(material), C.byref(o), _ptr(vals, p_f64),
                                                _ptr(vecs, p_f64), _ptr(met, p_f64), C.byref(ncore), C.byref(stats)))
         return vals, vecs, met, ncore.value, stats
+
+    def debug_solve(self, sigma: float, b, refine: int = 1):
+        """x = (A - sigma B)^-1 b with the factors of the last solve (test hook)."""
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.empty_like(b)
+        self._check(self.lib.plfem_debug_solve(self.handle, float(sigma), _ptr(b, p_f64), _ptr(x, p_f64), int(refine)))
+        return x
 
     PROFILE_ITEMS = ("assemble", "factorize", "forward_sweep", "backward_sweep", "spmm_B", "spmv_K_residual")
 

@@ -191,6 +191,8 @@ const char* plfem_version(void) { return "plfem 0.1 sm_100a"; }
 
 void plfem_set_host_threads(int n) { plfem::set_host_threads(n); }
 
+void plfem_ctx_set_coop_ctas(plfem_ctx* ctx, int ctas_per_sm) { if (ctx) ctx->coop_ctas_per_sm = std::max(1, ctas_per_sm); }
+
 int plfem_ctx_create(int device, plfem_ctx** out) {
   if (!out) return PLFEM_ERR_INVALID;
   *out = nullptr;
@@ -599,6 +601,37 @@ int plfem_profile_kernels(plfem_problem* pb, const plfem_material* mat, double s
     out_bytes[4] = 12.0 * nnz + 4.0 * (n + 1) + 32.0 * n;           // values + columns + row pointers + x and y (2 comps)
     out_ms[5] = timed([&] { launch_resid_k(ctx, pb->dperm, pb->d_vals.p, sigma, x.p, b.p, t.p); });
     out_bytes[5] = (5 * 8.0 + 4.0) * nnz + 4.0 * (n + 1) + 48.0 * n;
+  });
+}
+
+// Test hook: x = (A - sigma B)^-1 b with the factors left on the device by the last plfem_solve_modes
+// (same sigma), b and x in reference ordering, `refine` refinement steps.  Lets the tests compare the
+// block-LDL^T factorisation with SuperLU directly.
+int plfem_debug_solve(plfem_problem* pb, double sigma, const double* b, double* x, int refine) {
+  if (!pb || !pb->ctx) return PLFEM_ERR_INVALID;
+  plfem_ctx* ctx = pb->ctx;
+  return guarded(ctx, [&] {
+    need(b && x, "NULL argument");
+    if (pb->dperm.n == 0 || pb->d_vals.p == nullptr) throw StatusError(PLFEM_ERR_NOT_READY, "run plfem_solve_modes first");
+    PLFEM_CUDA(cudaSetDevice(ctx->device));
+    const int64_t n = pb->dperm.n, m = 2 * n;
+    std::vector<double> hb(m), hx(m);
+    for (int64_t r = 0; r < n; ++r) { const int32_t ip = pb->plan.perm[r]; hb[2 * r] = b[ip]; hb[2 * r + 1] = b[n + ip]; }
+    DevBuf<double> db, dx, dt, dd;
+    db.upload(ctx, hb); dx.alloc(ctx, m); dt.alloc(ctx, m); dd.alloc(ctx, m);
+    if (refine >= 100) {   // refine = 100 + r: exercise the per-level kernels instead of the persistent one
+      run_solve(ctx, pb->dplan, db.p, dx.p);
+      for (int it = 0; it < refine - 100; ++it) {
+        launch_resid_k(ctx, pb->dperm, pb->d_vals.p, sigma, dx.p, db.p, dt.p);
+        run_solve(ctx, pb->dplan, dt.p, dd.p);
+        launch_axpy(ctx, dx.p, dd.p, m);
+      }
+    } else {
+      run_operator(ctx, pb->dperm, pb->dplan, pb->d_vals.p, sigma, db.p, dx.p, dt.p, dd.p, refine, ctx->coop_ctas_per_sm);
+    }
+    dx.download(hx.data(), m);
+    PLFEM_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int64_t r = 0; r < n; ++r) { const int32_t ip = pb->plan.perm[r]; x[ip] = hx[2 * r]; x[n + ip] = hx[2 * r + 1]; }
   });
 }
 

@@ -53,6 +53,7 @@ struct plfem_ctx {
   std::string err;
   plfem::DeviceArena arena;
   int launches = 0;          // kernels launched since the counter was last reset
+  int coop_ctas_per_sm = 4;  // grid of the persistent operator kernel (lower it when several contexts share the GPU)
   cudaEvent_t ev[8] = {};
   void* pinned = nullptr;    // pinned staging buffer for small device->host reads
   size_t pinned_bytes = 0;
@@ -128,6 +129,7 @@ struct DevPlan {
   DevBuf<int32_t> first, s, sptr, strct, sn_of, parent, cptr, child, cmap_ptr, cmap, lfront;
   DevBuf<int64_t> foff;
   DevBuf<int32_t> uoff;              // offset of each front's update vector (in doubles)
+  DevBuf<int32_t> d_fwd_ptr, d_bwd_ptr;  // level schedule of the sweeps, on the device (persistent operator kernel)
   std::vector<int32_t> lptr;         // host copy of the level schedule
   std::vector<int32_t> lmax_m;       // largest pivot block (unknowns) per level
   // per-level work lists (host-built): tiles for the two GEMMs, slabs for extend-add and the sweeps
@@ -143,6 +145,8 @@ void launch_front_load(plfem_ctx* ctx, const DevPattern& pat, const DevPlan& D, 
 void run_factorization(plfem_ctx* ctx, const DevPlan& D);
 // solves (A - sigma B) x = b in the permuted interleaved layout, b and x of length 2n (must not alias)
 void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x);
+void run_operator(plfem_ctx* ctx, const DevPattern& pat, const DevPlan& D, const double* d_vals, double sigma, const double* b,
+                  double* x, double* rt, double* rdx, int refine, int ctas_per_sm);
 void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double* z);
 void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x);
 
@@ -165,6 +169,7 @@ void launch_spmm_b(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, 
 void launch_resid_k(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, double sigma, const double* x, const double* b,
                     double* t);
 
+void launch_axpy(plfem_ctx* ctx, double* x, const double* dx, int64_t m);
 void symmetric_eigen(int n, std::vector<double>& a /* n*n col-major in, eigenvectors out */, std::vector<double>& w);
 
 }  // namespace plfem

@@ -13,7 +13,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <numeric>
+#include <string>
 
 namespace plfem {
 
@@ -174,7 +176,7 @@ __global__ void fill_kernel(double* v, int64_t m, double val) {
 }
 
 // ---- per-mode reductions ----------------------------------------------------------------------------------
-constexpr int NRED = 10;  // norm2, e_core, px_core, py_core, px_all, py_all, div, res2, bx2, scale2
+constexpr int NRED = 10;  // norm2, e_core, px_core, py_core, px_all, py_all, div, res2, ||B||_F^2, ||A||_F^2
 constexpr int MROWS = 2048;  // rows (nodes) per CTA in the mode reduction
 
 __global__ void __launch_bounds__(256) mode_partial_kernel(int32_t n, const int32_t* __restrict__ rowptr,
@@ -197,11 +199,9 @@ __global__ void __launch_bounds__(256) mode_partial_kernel(int32_t n, const int3
     acc[0] += ex + ey;
     acc[4] += ex; acc[5] += ey;
     if (in_core[r]) { acc[1] += ex + ey; acc[2] += ex; acc[3] += ey; }
-    double dx = 0.0, dy = 0.0, axv = 0.0, ayv = 0.0, bx = 0.0, by = 0.0, nx = 0.0, ny = 0.0;
-    const double alam = fabs(lam);
+    double dx = 0.0, dy = 0.0, axv = 0.0, ayv = 0.0, bx = 0.0, by = 0.0, fa = 0.0, fb = 0.0;
     for (int32_t z = rowptr[r]; z < rowptr[r + 1]; ++z) {
       const double2 c = x[col[z]];
-      const double acx = fabs(c.x), acy = fabs(c.y);
       dx = fma(vals[(int64_t)S_DXX * nnz + z], c.x, dx);
       dx = fma(2.0 * vals[(int64_t)S_DXY * nnz + z], c.y, dx);
       dy = fma(vals[(int64_t)S_DYY * nnz + z], c.y, dy);
@@ -211,15 +211,17 @@ __global__ void __launch_bounds__(256) mode_partial_kernel(int32_t n, const int3
       ayv = fma(vals[(int64_t)S_AYY * nnz + z], c.y, ayv);
       const double mi = vals[(int64_t)S_MINV * nnz + z];
       bx = fma(mi, c.x, bx); by = fma(mi, c.y, by);
-      // (|A| + |lambda| |B|) |x|: the scale of the componentwise backward error
-      nx += (fabs(vals[(int64_t)S_AXX * nnz + z]) + alam * fabs(mi)) * acx + fabs(vals[(int64_t)S_AXY * nnz + z]) * acy;
-      ny += fabs(vals[(int64_t)S_AYX * nnz + z]) * acx + (fabs(vals[(int64_t)S_AYY * nnz + z]) + alam * fabs(mi)) * acy;
+      // squared Frobenius norms of A and B for the normwise backward error
+      const double a0 = vals[(int64_t)S_AXX * nnz + z], a1 = vals[(int64_t)S_AXY * nnz + z];
+      const double a2 = vals[(int64_t)S_AYX * nnz + z], a3 = vals[(int64_t)S_AYY * nnz + z];
+      fa += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+      fb += 2.0 * mi * mi;
     }
     acc[6] += v.x * dx + v.y * dy;
     const double rx = axv - lam * bx, ry = ayv - lam * by;
     acc[7] += rx * rx + ry * ry;
-    acc[8] += bx * bx + by * by;
-    acc[9] += nx * nx + ny * ny;
+    acc[8] += fb;
+    acc[9] += fa;
   }
   for (int k = 0; k < NRED; ++k) {
     const double t = block_sum(acc[k], sh);
@@ -228,8 +230,8 @@ __global__ void __launch_bounds__(256) mode_partial_kernel(int32_t n, const int3
 }
 
 // metrics (k, 8): div_energy, sum_e_core, sum_e, Px_core, Py_core, Px_all, Py_all, norm2_raw ; resid (k,2)
-__global__ void mode_final_kernel(const double* __restrict__ part, int nchunks, int k, double* __restrict__ metrics,
-                                  double* __restrict__ resid, double* __restrict__ scale) {
+__global__ void mode_final_kernel(const double* __restrict__ part, int nchunks, int k, const double* __restrict__ lambda,
+                                  double* __restrict__ metrics, double* __restrict__ resid, double* __restrict__ scale) {
   const int mode = blockIdx.x * blockDim.x + threadIdx.x;
   if (mode >= k) return;
   double t[NRED];
@@ -242,7 +244,8 @@ __global__ void mode_final_kernel(const double* __restrict__ part, int nchunks, 
   double* o = metrics + (int64_t)mode * PLFEM_NMETRICS;
   o[0] = t[6] * inv2; o[1] = t[1] * inv2; o[2] = t[0] * inv2; o[3] = t[2] * inv2; o[4] = t[3] * inv2;
   o[5] = t[4] * inv2; o[6] = t[5] * inv2; o[7] = t[0];
-  resid[2 * mode] = sqrt(t[7]); resid[2 * mode + 1] = sqrt(t[9]);
+  // ||A x - lambda B x||_2 and (||A||_F + |lambda| ||B||_F) ||x||_2
+  resid[2 * mode] = sqrt(t[7]); resid[2 * mode + 1] = (sqrt(t[9]) + fabs(lambda[mode]) * sqrt(t[8])) * sqrt(t[0]);
 }
 
 __global__ void __launch_bounds__(256) write_evecs_kernel(int32_t n, const int32_t* __restrict__ perm,
@@ -278,6 +281,12 @@ void launch_resid_k(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals,
   ctx->launches++;
 }
 
+void launch_axpy(plfem_ctx* ctx, double* x, const double* dx, int64_t m) {
+  add_kernel<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(x, dx, m);
+  PLFEM_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
 void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, const DevPlan& D, const double* d_vals, double sigma, int k,
                      int ncv, double tol, int maxiter, int refine_steps, const double* d_v0, DevBuf<double>& X,
                      std::vector<double>& lambda, EigenResult& res) {
@@ -288,7 +297,7 @@ void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, const DevPlan& D, co
   DevBuf<double> V[2], BV[2], r, u, h1, h2, alpha, beta, Sdev, rt, rdx;
   for (int b = 0; b < 2; ++b) { V[b].alloc(ctx, (size_t)ld * (ncv + 1)); BV[b].alloc(ctx, (size_t)ld * (ncv + 1)); }
   r.alloc(ctx, m); u.alloc(ctx, m);
-  if (refine_steps > 0) { rt.alloc(ctx, m); rdx.alloc(ctx, m); }
+  rt.alloc(ctx, m); rdx.alloc(ctx, m);
   h1.alloc(ctx, ncv + 1); h2.alloc(ctx, ncv + 1); alpha.alloc(ctx, ncv + 1); beta.alloc(ctx, ncv + 1);
   Sdev.alloc(ctx, (size_t)ncv * ncv);
   int cur = 0;
@@ -305,12 +314,16 @@ void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, const DevPlan& D, co
   // linear operator, which is what Lanczos needs).  The whole application — 2 sweeps x levels x
   // (1 + refine) launches — is captured once into a CUDA graph on fixed buffers (opin -> r) and
   // replayed, so the CPU issues one launch per operator application instead of ~70.
+  // Two ways to issue it: "coop" (default) = one persistent cooperative kernel per application that
+  // walks the level schedule with grid barriers; "graph" = the per-level kernels captured once into a
+  // CUDA graph and replayed (PLFEM_OP_MODE=graph).
+  static const bool use_graph = [] { const char* e = std::getenv("PLFEM_OP_MODE"); return e && std::string(e) == "graph"; }();
   DevBuf<double> opin;
-  opin.alloc(ctx, m);
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
   int graph_nodes = 0;
-  {
+  if (use_graph) {
+    opin.alloc(ctx, m);
     const int before = ctx->launches;
     PLFEM_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     try {
@@ -338,9 +351,13 @@ void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, const DevPlan& D, co
     ~GraphGuard() { if (e) cudaGraphExecDestroy(e); if (g) cudaGraphDestroy(g); }
   } guard{graph, gexec};
   auto apply_op = [&](const double* bvec) {   // r = OP(bvec)
-    PLFEM_CUDA(cudaMemcpyAsync(opin.p, bvec, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    PLFEM_CUDA(cudaGraphLaunch(gexec, st));
-    ctx->launches += graph_nodes;
+    if (use_graph) {
+      PLFEM_CUDA(cudaMemcpyAsync(opin.p, bvec, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      PLFEM_CUDA(cudaGraphLaunch(gexec, st));
+      ctx->launches += graph_nodes;
+    } else {
+      run_operator(ctx, pat, D, d_vals, sigma, bvec, r.p, rt.p, rdx.p, refine_steps, ctx->coop_ctas_per_sm);
+    }
   };
 
   // start vector: v0 / ||v0||_B
@@ -449,7 +466,7 @@ void run_mode_metrics(plfem_ctx* ctx, const DevPattern& pat, const double* d_val
   scale.alloc(ctx, k);
   mode_partial_kernel<<<dim3(nchunks, k), 256, 0, st>>>(n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz, d_in_core,
                                                         (const double2*)X, (int64_t)n, lam.p, part.p, nchunks);
-  mode_final_kernel<<<(k + 63) / 64, 64, 0, st>>>(part.p, nchunks, k, d_metrics, d_resid, scale.p);
+  mode_final_kernel<<<(k + 63) / 64, 64, 0, st>>>(part.p, nchunks, k, lam.p, d_metrics, d_resid, scale.p);
   ctx->launches += 2;
   if (d_out_evecs) {
     write_evecs_kernel<<<dim3((n + 255) / 256, k), 256, 0, st>>>(n, d_perm_to_interior, (const double2*)X, (int64_t)n,

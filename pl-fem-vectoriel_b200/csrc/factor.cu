@@ -16,6 +16,8 @@
 // position maps: gather-only, fixed order, no atomics, bit-reproducible run to run.
 #include "common.h"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 
 namespace plfem {
@@ -265,24 +267,25 @@ __global__ void __launch_bounds__(256) gemm_schur_kernel(const int4* __restrict_
                          F + (int64_t)s2 * ld + s2, ld, u2, u2, s2, t.y, t.z);
 }
 
-// ---- forward sweep: one CTA (8 warps) per (front, slab of 32*G rows) ------------------------------------
+// ---- forward sweep item: one CTA (8 warps) per (front, slab of 32*G rows) -------------------------------
 // The 8 warps form G row groups x 8/G slices of the k range (the 2s pivot columns), so a big front at the
 // top of the tree, where only a handful of CTAs exist, has 8-16 independent loads in flight per lane
 // instead of a 128-long dependent chain; partial sums meet in shared memory.
-__global__ void __launch_bounds__(256) forward_kernel(const int4* __restrict__ slabs, PlanView P,
-                                                       const double* __restrict__ rhs, double* __restrict__ z,
-                                                       double* __restrict__ upd) {
-  __shared__ double y1[MAX_PIV];
-  __shared__ double yt[256];
-  __shared__ double part[8][32];
-  const int4 sl = slabs[blockIdx.x];
+struct SweepSmem {
+  double y1[MAX_PIV];
+  double yt[256];
+  double part[8][32];
+};
+
+__device__ __forceinline__ void forward_item(const int4 sl, const PlanView& P, const double* __restrict__ rhs,
+                                             double* __restrict__ z, double* __restrict__ upd, SweepSmem& sm) {
   const int f = sl.x, row0 = sl.y, nrows = sl.z, G = sl.w;
   const int s2 = 2 * P.s[f], u2 = 2 * front_u(P, f);
   const int64_t ld = s2 + u2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t g0 = 2 * (int64_t)P.first[f];
-  for (int i = tid; i < s2; i += 256) y1[i] = rhs[g0 + i];
-  yt[tid] = 0.0;
+  for (int i = tid; i < s2; i += 256) sm.y1[i] = rhs[g0 + i];
+  sm.yt[tid] = 0.0;
   __syncthreads();
   for (int q = P.cptr[f]; q < P.cptr[f + 1]; ++q) {
     const int ch = P.child[q];
@@ -291,8 +294,8 @@ __global__ void __launch_bounds__(256) forward_kernel(const int4* __restrict__ s
     const double* uv = upd + P.uoff[ch];
     for (int k = tid; k < uc2; k += 256) {
       const int t = 2 * cm[k >> 1] + (k & 1);
-      if (t < s2) y1[t] += uv[k];
-      else if (t >= row0 && t < row0 + nrows) yt[t - row0] += uv[k];
+      if (t < s2) sm.y1[t] += uv[k];
+      else if (t >= row0 && t < row0 + nrows) sm.yt[t - row0] += uv[k];
     }
     __syncthreads();   // children may hit the same entry: keep child order
   }
@@ -304,28 +307,27 @@ __global__ void __launch_bounds__(256) forward_kernel(const int4* __restrict__ s
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     int k = ks;
     for (; k + 3 * nks < s2; k += 4 * nks) {
-      a0 = fma(M[(int64_t)k * ld], y1[k], a0);
-      a1 = fma(M[(int64_t)(k + nks) * ld], y1[k + nks], a1);
-      a2 = fma(M[(int64_t)(k + 2 * nks) * ld], y1[k + 2 * nks], a2);
-      a3 = fma(M[(int64_t)(k + 3 * nks) * ld], y1[k + 3 * nks], a3);
+      a0 = fma(M[(int64_t)k * ld], sm.y1[k], a0);
+      a1 = fma(M[(int64_t)(k + nks) * ld], sm.y1[k + nks], a1);
+      a2 = fma(M[(int64_t)(k + 2 * nks) * ld], sm.y1[k + 2 * nks], a2);
+      a3 = fma(M[(int64_t)(k + 3 * nks) * ld], sm.y1[k + 3 * nks], a3);
     }
-    for (; k < s2; k += nks) a0 = fma(M[(int64_t)k * ld], y1[k], a0);
+    for (; k < s2; k += nks) a0 = fma(M[(int64_t)k * ld], sm.y1[k], a0);
     acc = (a0 + a1) + (a2 + a3);
   }
-  part[warp][lane] = acc;
+  sm.part[warp][lane] = acc;
   __syncthreads();
   if (ks == 0 && lr < nrows) {
     double t = 0.0;
-    for (int q = 0; q < nks; ++q) t += part[q * G + rg][lane];
+    for (int q = 0; q < nks; ++q) t += sm.part[q * G + rg][lane];
     const int row = row0 + lr;
     if (row < s2) z[g0 + row] = t;
-    else upd[P.uoff[f] + (row - s2)] = yt[lr] - t;
+    else upd[P.uoff[f] + (row - s2)] = sm.yt[lr] - t;
   }
 }
 
-// ---- backward sweep: one warp per pivot column, 8 columns per CTA ----------------------------------------
-__global__ void __launch_bounds__(256) backward_kernel(const int4* __restrict__ slabs, PlanView P, double* __restrict__ x) {
-  const int4 sl = slabs[blockIdx.x];
+// ---- backward sweep item: one warp per pivot column, 8 columns per CTA ------------------------------------
+__device__ __forceinline__ void backward_item(const int4 sl, const PlanView& P, double* __restrict__ x) {
   const int f = sl.x, col0 = sl.y, ncols = sl.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp >= ncols) return;
@@ -345,6 +347,87 @@ __global__ void __launch_bounds__(256) backward_kernel(const int4* __restrict__ 
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) a += __shfl_down_sync(0xffffffffu, a, off);
   if (lane == 0) x[g0 + col0 + warp] -= a;
+}
+
+__global__ void __launch_bounds__(256) forward_kernel(const int4* __restrict__ slabs, PlanView P,
+                                                       const double* __restrict__ rhs, double* __restrict__ z,
+                                                       double* __restrict__ upd) {
+  __shared__ SweepSmem sm;
+  forward_item(slabs[blockIdx.x], P, rhs, z, upd, sm);
+}
+
+__global__ void __launch_bounds__(256) backward_kernel(const int4* __restrict__ slabs, PlanView P, double* __restrict__ x) {
+  backward_item(slabs[blockIdx.x], P, x);
+}
+
+// ---- persistent operator kernel: x = refine((A - sigma B)^-1 b) in ONE cooperative launch ----------------
+// A solve is a chain of ~2 x levels small dependent steps; as separate launches (even inside a CUDA graph)
+// each step pays the launch/drain gap and, with several designs in flight, the GPU front end becomes the
+// limiter (~3 us per kernel node).  Here a co-resident grid walks the level schedule itself and meets at a
+// grid barrier between levels: one launch per operator application, no front-end traffic.
+struct OpArgs {
+  PlanView P;
+  const int4* fwd_slabs; const int4* bwd_slabs;
+  const int32_t* fwd_ptr; const int32_t* bwd_ptr;   // [nlevels + 1] on the device
+  int nlevels;
+  const double* b; double* x; double* upd;           // b and x: length 2n, permuted interleaved layout
+  double* rt; double* rdx;                            // refinement work vectors
+  int refine;
+  // K = A - sigma B on the permuted pattern
+  int32_t n; const int32_t* rowptr; const int32_t* col; const double* vals; int64_t nnz; double sigma;
+};
+
+__device__ __forceinline__ void sweep_levels(const OpArgs& a, const double* rhs, double* out, SweepSmem& sm,
+                                             cooperative_groups::grid_group& grid) {
+  for (int l = 0; l < a.nlevels; ++l) {
+    for (int it = a.fwd_ptr[l] + blockIdx.x; it < a.fwd_ptr[l + 1]; it += gridDim.x) {
+      __syncthreads();                       // the previous item's shared-memory reads are done
+      forward_item(a.fwd_slabs[it], a.P, rhs, out, a.upd, sm);
+    }
+    grid.sync();
+  }
+  for (int l = a.nlevels - 1; l >= 0; --l) {
+    if (a.bwd_ptr[l + 1] == a.bwd_ptr[l]) continue;
+    for (int it = a.bwd_ptr[l] + blockIdx.x; it < a.bwd_ptr[l + 1]; it += gridDim.x) backward_item(a.bwd_slabs[it], a.P, out);
+    grid.sync();
+  }
+}
+
+__global__ void __launch_bounds__(256) op_kernel(OpArgs a) {
+  __shared__ SweepSmem sm;
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  sweep_levels(a, a.b, a.x, sm, grid);
+  for (int r = 0; r < a.refine; ++r) {
+    // rt = b - K x, four threads per row
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const int l32 = threadIdx.x & 31;       // whole warps stay in the loop together: the shuffles below use the full mask
+    for (int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; gid - l32 < 4 * (int64_t)a.n; gid += nthreads) {
+      const int64_t row = gid >> 2;
+      const int lane = (int)(gid & 3);
+      double ax = 0.0, ay = 0.0;
+      if (row < a.n) {
+        const double2* xv = (const double2*)a.x;
+        for (int32_t z = a.rowptr[row] + lane; z < a.rowptr[row + 1]; z += 4) {
+          const double smv = a.sigma * a.vals[(int64_t)S_MINV * a.nnz + z];
+          const double2 v = xv[a.col[z]];
+          ax = fma(a.vals[(int64_t)S_AXX * a.nnz + z] - smv, v.x, ax);
+          ax = fma(a.vals[(int64_t)S_AXY * a.nnz + z], v.y, ax);
+          ay = fma(a.vals[(int64_t)S_AYX * a.nnz + z], v.x, ay);
+          ay = fma(a.vals[(int64_t)S_AYY * a.nnz + z] - smv, v.y, ay);
+        }
+      }
+      ax += __shfl_down_sync(0xffffffffu, ax, 2, 4); ay += __shfl_down_sync(0xffffffffu, ay, 2, 4);
+      ax += __shfl_down_sync(0xffffffffu, ax, 1, 4); ay += __shfl_down_sync(0xffffffffu, ay, 1, 4);
+      if (row < a.n && lane == 0) {
+        const double2 bb = ((const double2*)a.b)[row];
+        ((double2*)a.rt)[row] = make_double2(bb.x - ax, bb.y - ay);
+      }
+    }
+    grid.sync();
+    sweep_levels(a, a.rt, a.rdx, sm, grid);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < 2 * (int64_t)a.n; i += nthreads) a.x[i] += a.rdx[i];
+    if (r + 1 < a.refine) grid.sync();
+  }
 }
 
 PlanView view(const DevPlan& D) {
@@ -398,6 +481,7 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
     D.w_ptr[l + 1] = (int32_t)wt.size(); D.s_ptr[l + 1] = (int32_t)stl.size(); D.ea_ptr[l + 1] = (int32_t)ea.size();
     D.fwd_ptr[l + 1] = (int32_t)fw.size(); D.bwd_ptr[l + 1] = (int32_t)bw.size();
   }
+  D.d_fwd_ptr.upload(ctx, D.fwd_ptr); D.d_bwd_ptr.upload(ctx, D.bwd_ptr);
   D.w_tiles.upload(ctx, wt); D.s_tiles.upload(ctx, stl); D.ea_slabs.upload(ctx, ea);
   D.fwd_slabs.upload(ctx, fw); D.bwd_slabs.upload(ctx, bw);
   D.pool.alloc(ctx, (size_t)P.foff[P.nfronts]);
@@ -465,6 +549,31 @@ void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x) {
     ctx->launches++;
   }
   PLFEM_CUDA(cudaGetLastError());
+}
+
+int op_grid_size(plfem_ctx* ctx, int ctas_per_sm) {
+  static int max_per_sm[64] = {}; static int nsm[64] = {};
+  const int dev = ctx->device < 64 ? ctx->device : 0;
+  if (!nsm[dev]) {
+    int occ = 0, sms = 0;
+    PLFEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, op_kernel, 256, 0));
+    PLFEM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    max_per_sm[dev] = std::max(occ, 1); nsm[dev] = sms;
+  }
+  return nsm[dev] * std::max(1, std::min(ctas_per_sm, max_per_sm[dev]));
+}
+
+// x = (A - sigma B)^-1 b with `refine` refinement steps, one cooperative launch (b, x, rt, rdx distinct)
+void run_operator(plfem_ctx* ctx, const DevPattern& pat, const DevPlan& D, const double* d_vals, double sigma, const double* b,
+                  double* x, double* rt, double* rdx, int refine, int ctas_per_sm) {
+  OpArgs a;
+  a.P = view(D);
+  a.fwd_slabs = D.fwd_slabs.p; a.bwd_slabs = D.bwd_slabs.p; a.fwd_ptr = D.d_fwd_ptr.p; a.bwd_ptr = D.d_bwd_ptr.p;
+  a.nlevels = D.nlevels; a.b = b; a.x = x; a.upd = D.upd.p; a.rt = rt; a.rdx = rdx; a.refine = refine;
+  a.n = pat.n; a.rowptr = pat.rowptr.p; a.col = pat.col.p; a.vals = d_vals; a.nnz = pat.nnz; a.sigma = sigma;
+  void* args[] = {&a};
+  PLFEM_CUDA(cudaLaunchCooperativeKernel((const void*)op_kernel, dim3(op_grid_size(ctx, ctas_per_sm)), dim3(256), args, 0, ctx->stream));
+  ctx->launches++;
 }
 
 void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x) {
