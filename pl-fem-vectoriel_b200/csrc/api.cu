@@ -510,6 +510,9 @@ int plfem_solve_modes(plfem_problem* pb, const plfem_material* mat, const plfem_
     run_eigensolver(ctx, pb->dperm, pb->dplan, pb->d_vals.p, o->sigma, k, ncv, o->tol > 0 ? o->tol : 1e-7,
                     o->maxiter > 0 ? o->maxiter : 12000, o->refine == 0 ? 1 : std::max(o->refine, 0), v0p, X, lambda, er);
     PLFEM_CUDA(cudaEventRecord(ctx->ev[3], st));
+    pb->dplan.status.download(fstat, 4);
+    PLFEM_CUDA(cudaStreamSynchronize(st));
+    if (fstat[1]) throw StatusError(PLFEM_ERR_INTERNAL, "operator kernel: a dependency wait timed out");
 
     // -- per-mode reductions + eigenvectors in reference ordering -------------------------------------------
     DevBuf<double> d_ev, d_met, d_res;

@@ -129,7 +129,9 @@ struct DevPlan {
   DevBuf<int32_t> first, s, sptr, strct, sn_of, parent, cptr, child, cmap_ptr, cmap, lfront;
   DevBuf<int64_t> foff;
   DevBuf<int32_t> uoff;              // offset of each front's update vector (in doubles)
-  DevBuf<int32_t> d_fwd_ptr, d_bwd_ptr;  // level schedule of the sweeps, on the device (persistent operator kernel)
+  // persistent operator kernel: backward queue (levels descending), slabs per front, completion counters
+  DevBuf<int4> bwd_q; DevBuf<int32_t> nfs, nbs, fdone, bdone;
+  int n_fwd = 0, n_bwd = 0, epoch = 0;
   std::vector<int32_t> lptr;         // host copy of the level schedule
   std::vector<int32_t> lmax_m;       // largest pivot block (unknowns) per level
   // per-level work lists (host-built): tiles for the two GEMMs, slabs for extend-add and the sweeps
@@ -141,11 +143,11 @@ struct DevPlan {
   int64_t upd_len = 0;
 };
 void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D);
-void launch_front_load(plfem_ctx* ctx, const DevPattern& pat, const DevPlan& D, const double* d_vals, double sigma);
+void launch_front_load(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, double sigma);
 void run_factorization(plfem_ctx* ctx, const DevPlan& D);
 // solves (A - sigma B) x = b in the permuted interleaved layout, b and x of length 2n (must not alias)
 void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x);
-void run_operator(plfem_ctx* ctx, const DevPattern& pat, const DevPlan& D, const double* d_vals, double sigma, const double* b,
+void run_operator(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, double sigma, const double* b,
                   double* x, double* rt, double* rdx, int refine, int ctas_per_sm);
 void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double* z);
 void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x);
@@ -156,7 +158,7 @@ struct EigenResult {
   int nconv = 0, n_op = 0, n_restart = 0;
 };
 struct EigenWork;  // opaque
-void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, const DevPlan& D, const double* d_vals, double sigma,
+void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, double sigma,
                      int k, int ncv, double tol, int maxiter, int refine_steps, const double* d_v0 /* permuted, may be null */,
                      DevBuf<double>& X /* (2n, k) eigenvectors, permuted layout */, std::vector<double>& lambda,
                      EigenResult& res);

@@ -287,7 +287,7 @@ void launch_axpy(plfem_ctx* ctx, double* x, const double* dx, int64_t m) {
   ctx->launches++;
 }
 
-void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, const DevPlan& D, const double* d_vals, double sigma, int k,
+void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, double sigma, int k,
                      int ncv, double tol, int maxiter, int refine_steps, const double* d_v0, DevBuf<double>& X,
                      std::vector<double>& lambda, EigenResult& res) {
   const int64_t m = 2 * (int64_t)pat.n;

@@ -277,14 +277,20 @@ struct SweepSmem {
   double part[8][32];
 };
 
-__device__ __forceinline__ void forward_item(const int4 sl, const PlanView& P, const double* __restrict__ rhs,
-                                             double* __restrict__ z, double* __restrict__ upd, SweepSmem& sm) {
+// CG = true: values produced by other CTAs of the SAME launch (dataflow kernel) are read with ld.global.cg,
+// i.e. from L2, never from a possibly stale L1 line.
+template <bool CG>
+__device__ __forceinline__ double ldx(const double* p) { return CG ? __ldcg(p) : *p; }
+
+template <bool CG>
+__device__ __forceinline__ void forward_item(const int4 sl, const PlanView& P, const double* rhs,
+                                             double* z, double* upd, SweepSmem& sm) {
   const int f = sl.x, row0 = sl.y, nrows = sl.z, G = sl.w;
   const int s2 = 2 * P.s[f], u2 = 2 * front_u(P, f);
   const int64_t ld = s2 + u2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t g0 = 2 * (int64_t)P.first[f];
-  for (int i = tid; i < s2; i += 256) sm.y1[i] = rhs[g0 + i];
+  for (int i = tid; i < s2; i += 256) sm.y1[i] = ldx<CG>(rhs + g0 + i);
   sm.yt[tid] = 0.0;
   __syncthreads();
   for (int q = P.cptr[f]; q < P.cptr[f + 1]; ++q) {
@@ -294,8 +300,8 @@ __device__ __forceinline__ void forward_item(const int4 sl, const PlanView& P, c
     const double* uv = upd + P.uoff[ch];
     for (int k = tid; k < uc2; k += 256) {
       const int t = 2 * cm[k >> 1] + (k & 1);
-      if (t < s2) sm.y1[t] += uv[k];
-      else if (t >= row0 && t < row0 + nrows) sm.yt[t - row0] += uv[k];
+      if (t < s2) sm.y1[t] += ldx<CG>(uv + k);
+      else if (t >= row0 && t < row0 + nrows) sm.yt[t - row0] += ldx<CG>(uv + k);
     }
     __syncthreads();   // children may hit the same entry: keep child order
   }
@@ -327,7 +333,8 @@ __device__ __forceinline__ void forward_item(const int4 sl, const PlanView& P, c
 }
 
 // ---- backward sweep item: one warp per pivot column, 8 columns per CTA ------------------------------------
-__device__ __forceinline__ void backward_item(const int4 sl, const PlanView& P, double* __restrict__ x) {
+template <bool CG>
+__device__ __forceinline__ void backward_item(const int4 sl, const PlanView& P, double* x) {
   const int f = sl.x, col0 = sl.y, ncols = sl.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp >= ncols) return;
@@ -339,65 +346,92 @@ __device__ __forceinline__ void backward_item(const int4 sl, const PlanView& P, 
   double a0 = 0.0, a1 = 0.0;
   int j = lane;
   for (; j + 32 < u2; j += 64) {
-    a0 = fma(wc[j], x[2 * (int64_t)st[j >> 1] + (j & 1)], a0);
-    a1 = fma(wc[j + 32], x[2 * (int64_t)st[(j + 32) >> 1] + ((j + 32) & 1)], a1);
+    a0 = fma(wc[j], ldx<CG>(x + 2 * (int64_t)st[j >> 1] + (j & 1)), a0);
+    a1 = fma(wc[j + 32], ldx<CG>(x + 2 * (int64_t)st[(j + 32) >> 1] + ((j + 32) & 1)), a1);
   }
-  if (j < u2) a0 = fma(wc[j], x[2 * (int64_t)st[j >> 1] + (j & 1)], a0);
+  if (j < u2) a0 = fma(wc[j], ldx<CG>(x + 2 * (int64_t)st[j >> 1] + (j & 1)), a0);
   double a = a0 + a1;
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) a += __shfl_down_sync(0xffffffffu, a, off);
-  if (lane == 0) x[g0 + col0 + warp] -= a;
+  if (lane == 0) x[g0 + col0 + warp] = ldx<CG>(x + g0 + col0 + warp) - a;
 }
 
 __global__ void __launch_bounds__(256) forward_kernel(const int4* __restrict__ slabs, PlanView P,
                                                        const double* __restrict__ rhs, double* __restrict__ z,
                                                        double* __restrict__ upd) {
   __shared__ SweepSmem sm;
-  forward_item(slabs[blockIdx.x], P, rhs, z, upd, sm);
+  forward_item<false>(slabs[blockIdx.x], P, rhs, z, upd, sm);
 }
 
 __global__ void __launch_bounds__(256) backward_kernel(const int4* __restrict__ slabs, PlanView P, double* __restrict__ x) {
-  backward_item(slabs[blockIdx.x], P, x);
+  backward_item<false>(slabs[blockIdx.x], P, x);
 }
 
 // ---- persistent operator kernel: x = refine((A - sigma B)^-1 b) in ONE cooperative launch ----------------
-// A solve is a chain of ~2 x levels small dependent steps; as separate launches (even inside a CUDA graph)
-// each step pays the launch/drain gap and, with several designs in flight, the GPU front end becomes the
-// limiter (~3 us per kernel node).  Here a co-resident grid walks the level schedule itself and meets at a
-// grid barrier between levels: one launch per operator application, no front-end traffic.
+// A solve is a chain of ~2 x levels small dependent steps.  As separate launches (even inside a CUDA graph)
+// every step pays the launch/drain gap, and with several designs in flight the GPU front end becomes the
+// limiter (~3 us per kernel node).  Here a co-resident grid runs the whole operator application: work
+// items (front slabs) sit in one queue ordered children-before-parents; CTA b takes items b, b+G, b+2G...
+// in order and, instead of a grid-wide barrier per level, waits only for the fronts it depends on
+// (per-front completion counters in global memory, dataflow).  Items a CTA waits for always precede it in
+// the queue and every CTA is resident (cooperative launch), so the wait cannot deadlock; a spin limit turns
+// a bug into an error flag instead of a hung GPU.  Grid barriers remain only around the refinement SpMV.
 struct OpArgs {
   PlanView P;
-  const int4* fwd_slabs; const int4* bwd_slabs;
-  const int32_t* fwd_ptr; const int32_t* bwd_ptr;   // [nlevels + 1] on the device
-  int nlevels;
-  const double* b; double* x; double* upd;           // b and x: length 2n, permuted interleaved layout
-  double* rt; double* rdx;                            // refinement work vectors
+  const int4* fwd_q; const int4* bwd_q;      // forward queue (levels ascending), backward queue (levels descending)
+  int n_fwd, n_bwd;
+  const int32_t* parent; const int32_t* nfs; const int32_t* nbs;   // per front: parent, # forward slabs, # backward slabs
+  int32_t* fdone; int32_t* bdone; int32_t* status;
+  int epoch0;                                 // sweeps completed before this launch
+  const double* b; double* x; double* upd;   // b and x: length 2n, permuted interleaved layout
+  double* rt; double* rdx;                    // refinement work vectors
   int refine;
-  // K = A - sigma B on the permuted pattern
   int32_t n; const int32_t* rowptr; const int32_t* col; const double* vals; int64_t nnz; double sigma;
 };
 
-__device__ __forceinline__ void sweep_levels(const OpArgs& a, const double* rhs, double* out, SweepSmem& sm,
-                                             cooperative_groups::grid_group& grid) {
-  for (int l = 0; l < a.nlevels; ++l) {
-    for (int it = a.fwd_ptr[l] + blockIdx.x; it < a.fwd_ptr[l + 1]; it += gridDim.x) {
-      __syncthreads();                       // the previous item's shared-memory reads are done
-      forward_item(a.fwd_slabs[it], a.P, rhs, out, a.upd, sm);
-    }
-    grid.sync();
+__device__ __forceinline__ void wait_count(const int32_t* ctr, int32_t target, int32_t* status) {
+  const volatile int32_t* v = ctr;
+  unsigned spins = 0;
+  while (*v < target) {
+    if (++spins > (1u << 22)) { atomicExch(status + 1, 1); break; }   // ~seconds: report instead of hanging
   }
-  for (int l = a.nlevels - 1; l >= 0; --l) {
-    if (a.bwd_ptr[l + 1] == a.bwd_ptr[l]) continue;
-    for (int it = a.bwd_ptr[l] + blockIdx.x; it < a.bwd_ptr[l + 1]; it += gridDim.x) backward_item(a.bwd_slabs[it], a.P, out);
-    grid.sync();
+}
+
+__device__ __forceinline__ void sweep_dataflow(const OpArgs& a, const double* rhs, double* out, int epoch, SweepSmem& sm) {
+  const PlanView& P = a.P;
+  for (int it = blockIdx.x; it < a.n_fwd; it += gridDim.x) {
+    const int4 sl = a.fwd_q[it];
+    const int f = sl.x;
+    if (threadIdx.x == 0)
+      for (int q = P.cptr[f]; q < P.cptr[f + 1]; ++q) { const int ch = P.child[q]; wait_count(a.fdone + ch, a.nfs[ch] * epoch, a.status); }
+    __syncthreads();                       // children are complete; the previous item's shared-memory reads too
+    forward_item<true>(sl, P, rhs, out, a.upd, sm);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(a.fdone + f, 1);
+  }
+  for (int it = blockIdx.x; it < a.n_bwd; it += gridDim.x) {
+    const int4 sl = a.bwd_q[it];
+    const int f = sl.x;
+    if (threadIdx.x == 0) {
+      wait_count(a.fdone + f, a.nfs[f] * epoch, a.status);               // z of this front is complete
+      const int pa = a.parent[f];
+      if (pa >= 0) { wait_count(a.fdone + pa, a.nfs[pa] * epoch, a.status); wait_count(a.bdone + pa, a.nbs[pa] * epoch, a.status); }
+    }
+    __syncthreads();
+    backward_item<true>(sl, P, out);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(a.bdone + f, 1);
   }
 }
 
 __global__ void __launch_bounds__(256) op_kernel(OpArgs a) {
   __shared__ SweepSmem sm;
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
-  sweep_levels(a, a.b, a.x, sm, grid);
+  sweep_dataflow(a, a.b, a.x, a.epoch0 + 1, sm);
   for (int r = 0; r < a.refine; ++r) {
+    grid.sync();                            // x complete everywhere
     // rt = b - K x, four threads per row
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     const int l32 = threadIdx.x & 31;       // whole warps stay in the loop together: the shuffles below use the full mask
@@ -406,27 +440,27 @@ __global__ void __launch_bounds__(256) op_kernel(OpArgs a) {
       const int lane = (int)(gid & 3);
       double ax = 0.0, ay = 0.0;
       if (row < a.n) {
-        const double2* xv = (const double2*)a.x;
         for (int32_t z = a.rowptr[row] + lane; z < a.rowptr[row + 1]; z += 4) {
           const double smv = a.sigma * a.vals[(int64_t)S_MINV * a.nnz + z];
-          const double2 v = xv[a.col[z]];
-          ax = fma(a.vals[(int64_t)S_AXX * a.nnz + z] - smv, v.x, ax);
-          ax = fma(a.vals[(int64_t)S_AXY * a.nnz + z], v.y, ax);
-          ay = fma(a.vals[(int64_t)S_AYX * a.nnz + z], v.x, ay);
-          ay = fma(a.vals[(int64_t)S_AYY * a.nnz + z] - smv, v.y, ay);
+          const double* xp = a.x + 2 * (int64_t)a.col[z];
+          const double vx = __ldcg(xp), vy = __ldcg(xp + 1);
+          ax = fma(a.vals[(int64_t)S_AXX * a.nnz + z] - smv, vx, ax);
+          ax = fma(a.vals[(int64_t)S_AXY * a.nnz + z], vy, ax);
+          ay = fma(a.vals[(int64_t)S_AYX * a.nnz + z], vx, ay);
+          ay = fma(a.vals[(int64_t)S_AYY * a.nnz + z] - smv, vy, ay);
         }
       }
       ax += __shfl_down_sync(0xffffffffu, ax, 2, 4); ay += __shfl_down_sync(0xffffffffu, ay, 2, 4);
       ax += __shfl_down_sync(0xffffffffu, ax, 1, 4); ay += __shfl_down_sync(0xffffffffu, ay, 1, 4);
       if (row < a.n && lane == 0) {
-        const double2 bb = ((const double2*)a.b)[row];
-        ((double2*)a.rt)[row] = make_double2(bb.x - ax, bb.y - ay);
+        a.rt[2 * row] = a.b[2 * row] - ax;
+        a.rt[2 * row + 1] = a.b[2 * row + 1] - ay;
       }
     }
-    grid.sync();
-    sweep_levels(a, a.rt, a.rdx, sm, grid);
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < 2 * (int64_t)a.n; i += nthreads) a.x[i] += a.rdx[i];
-    if (r + 1 < a.refine) grid.sync();
+    grid.sync();                            // rt complete
+    sweep_dataflow(a, a.rt, a.rdx, a.epoch0 + 2 + r, sm);
+    grid.sync();                            // rdx complete
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < 2 * (int64_t)a.n; i += nthreads) a.x[i] = __ldcg(a.x + i) + __ldcg(a.rdx + i);
   }
 }
 
@@ -481,7 +515,17 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
     D.w_ptr[l + 1] = (int32_t)wt.size(); D.s_ptr[l + 1] = (int32_t)stl.size(); D.ea_ptr[l + 1] = (int32_t)ea.size();
     D.fwd_ptr[l + 1] = (int32_t)fw.size(); D.bwd_ptr[l + 1] = (int32_t)bw.size();
   }
-  D.d_fwd_ptr.upload(ctx, D.fwd_ptr); D.d_bwd_ptr.upload(ctx, D.bwd_ptr);
+  {
+    // queues and counters of the persistent operator kernel
+    std::vector<int4> bq; bq.reserve(bw.size());
+    for (int l = P.nlevels - 1; l >= 0; --l) bq.insert(bq.end(), bw.begin() + D.bwd_ptr[l], bw.begin() + D.bwd_ptr[l + 1]);
+    std::vector<int32_t> nfs(P.nfronts, 0), nbs(P.nfronts, 0);
+    for (const int4& it : fw) nfs[it.x]++;
+    for (const int4& it : bw) nbs[it.x]++;
+    D.bwd_q.upload(ctx, bq); D.nfs.upload(ctx, nfs); D.nbs.upload(ctx, nbs);
+    D.n_fwd = (int)fw.size(); D.n_bwd = (int)bq.size();
+    D.fdone.alloc(ctx, P.nfronts); D.bdone.alloc(ctx, P.nfronts);
+  }
   D.w_tiles.upload(ctx, wt); D.s_tiles.upload(ctx, stl); D.ea_slabs.upload(ctx, ea);
   D.fwd_slabs.upload(ctx, fw); D.bwd_slabs.upload(ctx, bw);
   D.pool.alloc(ctx, (size_t)P.foff[P.nfronts]);
@@ -490,9 +534,12 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
   PLFEM_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
-void launch_front_load(plfem_ctx* ctx, const DevPattern& pat, const DevPlan& D, const double* d_vals, double sigma) {
+void launch_front_load(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, double sigma) {
   PLFEM_CUDA(cudaMemsetAsync(D.pool.p, 0, D.pool.n * sizeof(double), ctx->stream));
   PLFEM_CUDA(cudaMemsetAsync(D.status.p, 0, 4 * sizeof(int32_t), ctx->stream));
+  PLFEM_CUDA(cudaMemsetAsync(D.fdone.p, 0, D.fdone.n * sizeof(int32_t), ctx->stream));
+  PLFEM_CUDA(cudaMemsetAsync(D.bdone.p, 0, D.bdone.n * sizeof(int32_t), ctx->stream));
+  D.epoch = 0;
   const int bs = 256;
   front_load_kernel<<<(unsigned)((pat.nnz + bs - 1) / bs), bs, 0, ctx->stream>>>(pat.nnz, pat.rowidx.p, pat.col.p,
                                                                                  D.sn_of.p, view(D), d_vals, sigma);
@@ -564,12 +611,14 @@ int op_grid_size(plfem_ctx* ctx, int ctas_per_sm) {
 }
 
 // x = (A - sigma B)^-1 b with `refine` refinement steps, one cooperative launch (b, x, rt, rdx distinct)
-void run_operator(plfem_ctx* ctx, const DevPattern& pat, const DevPlan& D, const double* d_vals, double sigma, const double* b,
+void run_operator(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, double sigma, const double* b,
                   double* x, double* rt, double* rdx, int refine, int ctas_per_sm) {
   OpArgs a;
   a.P = view(D);
-  a.fwd_slabs = D.fwd_slabs.p; a.bwd_slabs = D.bwd_slabs.p; a.fwd_ptr = D.d_fwd_ptr.p; a.bwd_ptr = D.d_bwd_ptr.p;
-  a.nlevels = D.nlevels; a.b = b; a.x = x; a.upd = D.upd.p; a.rt = rt; a.rdx = rdx; a.refine = refine;
+  a.fwd_q = D.fwd_slabs.p; a.bwd_q = D.bwd_q.p; a.n_fwd = D.n_fwd; a.n_bwd = D.n_bwd;
+  a.parent = D.parent.p; a.nfs = D.nfs.p; a.nbs = D.nbs.p; a.fdone = D.fdone.p; a.bdone = D.bdone.p; a.status = D.status.p;
+  a.epoch0 = D.epoch; D.epoch += 1 + refine;
+  a.b = b; a.x = x; a.upd = D.upd.p; a.rt = rt; a.rdx = rdx; a.refine = refine;
   a.n = pat.n; a.rowptr = pat.rowptr.p; a.col = pat.col.p; a.vals = d_vals; a.nnz = pat.nnz; a.sigma = sigma;
   void* args[] = {&a};
   PLFEM_CUDA(cudaLaunchCooperativeKernel((const void*)op_kernel, dim3(op_grid_size(ctx, ctas_per_sm)), dim3(256), args, 0, ctx->stream));
