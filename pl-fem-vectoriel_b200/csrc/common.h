@@ -124,18 +124,33 @@ void launch_spmv_csr(plfem_ctx* ctx, int64_t rows, const int32_t* rowptr, const 
                      const double* x, double* y);
 
 // ---- multifrontal factorisation and solves (factor.cu) ------------------------------------------------
+// one forward work item: (front, slab of rows) with everything the kernel needs, so that no plan metadata
+// has to be chased through dependent loads on the critical path
+struct FwdItem {
+  int32_t f, row0, nrows, G, s2, ld;     // ld = 2nf = rows of the front
+  int32_t ch0, ch1, tgt0, tgt1;          // first two children and the number of forward items each must complete
+  int32_t uoff, goff, nchild, tgtx;      // update-vector offset, gather-table offset, children, (unused)
+  int64_t foff, g0;                      // front matrix offset, first unknown of the front
+};
+struct BwdItem {
+  int32_t f, col0, ncols, s2, u2, ld, soff, parent;
+  int32_t tgt_f, tgt_pf, tgt_pb, pad;    // forward items of f, forward / backward items of the parent
+  int64_t foff, g0;
+};
+
 struct DevPlan {
   int32_t n = 0, nfronts = 0, nlevels = 0;
   DevBuf<int32_t> first, s, sptr, strct, sn_of, parent, cptr, child, cmap_ptr, cmap, lfront;
   DevBuf<int64_t> foff;
   DevBuf<int32_t> uoff;              // offset of each front's update vector (in doubles)
   // persistent operator kernel: backward queue (levels descending), slabs per front, completion counters
-  DevBuf<int4> bwd_q; DevBuf<int32_t> nfs, nbs, fdone, bdone;
+  DevBuf<BwdItem> bwd_q; DevBuf<int32_t> fdone, bdone, nfs;
   int n_fwd = 0, n_bwd = 0, epoch = 0;
   std::vector<int32_t> lptr;         // host copy of the level schedule
   std::vector<int32_t> lmax_m;       // largest pivot block (unknowns) per level
   // per-level work lists (host-built): tiles for the two GEMMs, slabs for extend-add and the sweeps
-  DevBuf<int4> w_tiles, s_tiles, ea_slabs, fwd_slabs, bwd_slabs;
+  DevBuf<int4> w_tiles, s_tiles, ea_slabs;
+  DevBuf<FwdItem> fwd_items; DevBuf<BwdItem> bwd_items; DevBuf<int32_t> gsrc;
   std::vector<int32_t> w_ptr, s_ptr, ea_ptr, fwd_ptr, bwd_ptr;  // [nlevels+1] each
   DevBuf<double> pool;               // all frontal matrices
   DevBuf<double> upd;                // per-front update vectors of the forward sweep

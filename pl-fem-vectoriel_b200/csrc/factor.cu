@@ -267,13 +267,17 @@ __global__ void __launch_bounds__(256) gemm_schur_kernel(const int4* __restrict_
                          F + (int64_t)s2 * ld + s2, ld, u2, u2, s2, t.y, t.z);
 }
 
-// ---- forward sweep item: one CTA (8 warps) per (front, slab of 32*G rows) -------------------------------
-// The 8 warps form G row groups x 8/G slices of the k range (the 2s pivot columns), so a big front at the
-// top of the tree, where only a handful of CTAs exist, has 8-16 independent loads in flight per lane
-// instead of a 128-long dependent chain; partial sums meet in shared memory.
+// ---- sweep work items --------------------------------------------------------------------------------------
+// A sweep is a chain of ~2 x levels dependent steps, each a handful of microseconds of which most used to be
+// dependent L2 round trips chasing plan metadata (slab -> front -> children -> maps -> values).  Every item
+// now carries all it needs in one 96-byte record, the child->parent maps are flattened per parent row into
+// two source offsets (first and second child), and everything static — the record, the source offsets, the
+// factor entries the thread will multiply — is loaded BEFORE the item waits for its dependencies, so the
+// critical path of a step is: see the flag, one gather of the freshly written values, FMAs from registers,
+// write, signal.
 struct SweepSmem {
   double y1[MAX_PIV];
-  double yt[256];
+  double yt[128];
   double part[8][32];
 };
 
@@ -281,113 +285,6 @@ struct SweepSmem {
 // i.e. from L2, never from a possibly stale L1 line.
 template <bool CG>
 __device__ __forceinline__ double ldx(const double* p) { return CG ? __ldcg(p) : *p; }
-
-template <bool CG>
-__device__ __forceinline__ void forward_item(const int4 sl, const PlanView& P, const double* rhs,
-                                             double* z, double* upd, SweepSmem& sm) {
-  const int f = sl.x, row0 = sl.y, nrows = sl.z, G = sl.w;
-  const int s2 = 2 * P.s[f], u2 = 2 * front_u(P, f);
-  const int64_t ld = s2 + u2;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t g0 = 2 * (int64_t)P.first[f];
-  for (int i = tid; i < s2; i += 256) sm.y1[i] = ldx<CG>(rhs + g0 + i);
-  sm.yt[tid] = 0.0;
-  __syncthreads();
-  for (int q = P.cptr[f]; q < P.cptr[f + 1]; ++q) {
-    const int ch = P.child[q];
-    const int uc2 = 2 * front_u(P, ch);
-    const int32_t* cm = P.cmap + P.cmap_ptr[ch];
-    const double* uv = upd + P.uoff[ch];
-    for (int k = tid; k < uc2; k += 256) {
-      const int t = 2 * cm[k >> 1] + (k & 1);
-      if (t < s2) sm.y1[t] += ldx<CG>(uv + k);
-      else if (t >= row0 && t < row0 + nrows) sm.yt[t - row0] += ldx<CG>(uv + k);
-    }
-    __syncthreads();   // children may hit the same entry: keep child order
-  }
-  const int nks = 8 / G, rg = warp % G, ks = warp / G;
-  const int lr = rg * 32 + lane;            // row within the slab
-  double acc = 0.0;
-  if (lr < nrows) {
-    const double* M = P.pool + P.foff[f] + (row0 + lr);
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int k = ks;
-    for (; k + 3 * nks < s2; k += 4 * nks) {
-      a0 = fma(M[(int64_t)k * ld], sm.y1[k], a0);
-      a1 = fma(M[(int64_t)(k + nks) * ld], sm.y1[k + nks], a1);
-      a2 = fma(M[(int64_t)(k + 2 * nks) * ld], sm.y1[k + 2 * nks], a2);
-      a3 = fma(M[(int64_t)(k + 3 * nks) * ld], sm.y1[k + 3 * nks], a3);
-    }
-    for (; k < s2; k += nks) a0 = fma(M[(int64_t)k * ld], sm.y1[k], a0);
-    acc = (a0 + a1) + (a2 + a3);
-  }
-  sm.part[warp][lane] = acc;
-  __syncthreads();
-  if (ks == 0 && lr < nrows) {
-    double t = 0.0;
-    for (int q = 0; q < nks; ++q) t += sm.part[q * G + rg][lane];
-    const int row = row0 + lr;
-    if (row < s2) z[g0 + row] = t;
-    else upd[P.uoff[f] + (row - s2)] = sm.yt[lr] - t;
-  }
-}
-
-// ---- backward sweep item: one warp per pivot column, 8 columns per CTA ------------------------------------
-template <bool CG>
-__device__ __forceinline__ void backward_item(const int4 sl, const PlanView& P, double* x) {
-  const int f = sl.x, col0 = sl.y, ncols = sl.z;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp >= ncols) return;
-  const int s2 = 2 * P.s[f], u2 = 2 * front_u(P, f);
-  const int64_t ld = s2 + u2;
-  const int64_t g0 = 2 * (int64_t)P.first[f];
-  const int32_t* st = P.strct + P.sptr[f];
-  const double* wc = P.pool + P.foff[f] + s2 + (int64_t)(col0 + warp) * ld;   // F21new(j, col) at col*ld + s2 + j
-  double a0 = 0.0, a1 = 0.0;
-  int j = lane;
-  for (; j + 32 < u2; j += 64) {
-    a0 = fma(wc[j], ldx<CG>(x + 2 * (int64_t)st[j >> 1] + (j & 1)), a0);
-    a1 = fma(wc[j + 32], ldx<CG>(x + 2 * (int64_t)st[(j + 32) >> 1] + ((j + 32) & 1)), a1);
-  }
-  if (j < u2) a0 = fma(wc[j], ldx<CG>(x + 2 * (int64_t)st[j >> 1] + (j & 1)), a0);
-  double a = a0 + a1;
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) a += __shfl_down_sync(0xffffffffu, a, off);
-  if (lane == 0) x[g0 + col0 + warp] = ldx<CG>(x + g0 + col0 + warp) - a;
-}
-
-__global__ void __launch_bounds__(256) forward_kernel(const int4* __restrict__ slabs, PlanView P,
-                                                       const double* __restrict__ rhs, double* __restrict__ z,
-                                                       double* __restrict__ upd) {
-  __shared__ SweepSmem sm;
-  forward_item<false>(slabs[blockIdx.x], P, rhs, z, upd, sm);
-}
-
-__global__ void __launch_bounds__(256) backward_kernel(const int4* __restrict__ slabs, PlanView P, double* __restrict__ x) {
-  backward_item<false>(slabs[blockIdx.x], P, x);
-}
-
-// ---- persistent operator kernel: x = refine((A - sigma B)^-1 b) in ONE cooperative launch ----------------
-// A solve is a chain of ~2 x levels small dependent steps.  As separate launches (even inside a CUDA graph)
-// every step pays the launch/drain gap, and with several designs in flight the GPU front end becomes the
-// limiter (~3 us per kernel node).  Here a co-resident grid runs the whole operator application: work
-// items (front slabs) sit in one queue ordered children-before-parents; CTA b takes items b, b+G, b+2G...
-// in order and, instead of a grid-wide barrier per level, waits only for the fronts it depends on
-// (per-front completion counters in global memory, dataflow).  Items a CTA waits for always precede it in
-// the queue and every CTA is resident (cooperative launch), so the wait cannot deadlock; a spin limit turns
-// a bug into an error flag instead of a hung GPU.  Grid barriers remain only around the refinement SpMV.
-struct OpArgs {
-  PlanView P;
-  const int4* fwd_q; const int4* bwd_q;      // forward queue (levels ascending), backward queue (levels descending)
-  int n_fwd, n_bwd;
-  const int32_t* parent; const int32_t* nfs; const int32_t* nbs;   // per front: parent, # forward slabs, # backward slabs
-  int32_t* fdone; int32_t* bdone; int32_t* status;
-  int epoch0;                                 // sweeps completed before this launch
-  const double* b; double* x; double* upd;   // b and x: length 2n, permuted interleaved layout
-  double* rt; double* rdx;                    // refinement work vectors
-  int refine;
-  int32_t n; const int32_t* rowptr; const int32_t* col; const double* vals; int64_t nnz; double sigma;
-};
 
 __device__ __forceinline__ void wait_count(const int32_t* ctr, int32_t target, int32_t* status) {
   const volatile int32_t* v = ctr;
@@ -397,32 +294,185 @@ __device__ __forceinline__ void wait_count(const int32_t* ctr, int32_t target, i
   }
 }
 
-__device__ __forceinline__ void sweep_dataflow(const OpArgs& a, const double* rhs, double* out, int epoch, SweepSmem& sm) {
-  const PlanView& P = a.P;
-  for (int it = blockIdx.x; it < a.n_fwd; it += gridDim.x) {
-    const int4 sl = a.fwd_q[it];
-    const int f = sl.x;
-    if (threadIdx.x == 0)
-      for (int q = P.cptr[f]; q < P.cptr[f + 1]; ++q) { const int ch = P.child[q]; wait_count(a.fdone + ch, a.nfs[ch] * epoch, a.status); }
-    __syncthreads();                       // children are complete; the previous item's shared-memory reads too
-    forward_item<true>(sl, P, rhs, out, a.upd, sm);
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(a.fdone + f, 1);
+struct Deps {          // dataflow bookkeeping of the persistent kernel (unused by the per-level kernels)
+  int32_t* fdone; int32_t* bdone; int32_t* status; int epoch; const int32_t* nfs;
+};
+
+constexpr int FQ = 16;  // factor entries per thread preloaded before the wait (forward)
+constexpr int BQ = 8;   // factor entries per lane preloaded before the wait (backward)
+
+// forward: one CTA (8 warps) per (front, slab of 32*G rows).  The 8 warps form G row groups x 8/G slices of
+// the k range (the 2s pivot columns); partial sums meet in shared memory.
+template <bool CG>
+__device__ __forceinline__ void forward_item(const FwdItem& it, const int32_t* __restrict__ gsrc, const PlanView& P,
+                                             const double* rhs, double* z, double* upd, SweepSmem& sm, const Deps& dp) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int s2 = it.s2, nrows = it.nrows, row0 = it.row0, G = it.G, nf2 = it.ld;
+  const int64_t ld = it.ld;
+  const int nks = 8 / G, rg = warp % G, ks = warp / G;
+  const int lr = rg * 32 + lane;            // row within the slab
+  // ---- static prefetch: gather sources and this thread's factor entries
+  const int32_t* g1 = gsrc + it.goff;       // first child: source offset into upd per front row, -1 = none
+  const int32_t* g2 = g1 + nf2;             // second child
+  int i1 = -1, i2 = -1, j1 = -1, j2 = -1;
+  if (tid < s2) { i1 = g1[tid]; i2 = g2[tid]; }
+  const int trow = row0 + (tid - 128);      // threads 128.. handle the slab's update rows (nrows <= 128)
+  if (tid >= 128 && tid - 128 < nrows && trow >= s2) { j1 = g1[trow]; j2 = g2[trow]; }
+  const double* M = P.pool + it.foff + (row0 + lr);
+  double mreg[FQ];
+#pragma unroll
+  for (int q = 0; q < FQ; ++q) {
+    const int k = ks + q * nks;
+    mreg[q] = (lr < nrows && k < s2) ? M[(int64_t)k * ld] : 0.0;
   }
-  for (int it = blockIdx.x; it < a.n_bwd; it += gridDim.x) {
-    const int4 sl = a.bwd_q[it];
-    const int f = sl.x;
-    if (threadIdx.x == 0) {
-      wait_count(a.fdone + f, a.nfs[f] * epoch, a.status);               // z of this front is complete
-      const int pa = a.parent[f];
-      if (pa >= 0) { wait_count(a.fdone + pa, a.nfs[pa] * epoch, a.status); wait_count(a.bdone + pa, a.nbs[pa] * epoch, a.status); }
+  // ---- wait for the children (dataflow mode)
+  if (CG) {
+    if (tid == 0) {
+      if (it.ch0 >= 0) wait_count(dp.fdone + it.ch0, it.tgt0 * dp.epoch, dp.status);
+      if (it.ch1 >= 0) wait_count(dp.fdone + it.ch1, it.tgt1 * dp.epoch, dp.status);
+      for (int q = 2; q < it.nchild; ++q) { const int ch = P.child[P.cptr[it.f] + q]; wait_count(dp.fdone + ch, dp.nfs[ch] * dp.epoch, dp.status); }
     }
     __syncthreads();
-    backward_item<true>(sl, P, out);
+  }
+  // ---- dynamic part: right-hand side + children's updates, fixed order (rhs + first child) + second child
+  if (tid < s2) {
+    double v = ldx<CG>(rhs + it.g0 + tid);
+    if (i1 >= 0) v += ldx<CG>(upd + i1);
+    if (i2 >= 0) v += ldx<CG>(upd + i2);
+    sm.y1[tid] = v;
+  }
+  if (tid >= 128) {
+    double v = 0.0;
+    if (j1 >= 0) v += ldx<CG>(upd + j1);
+    if (j2 >= 0) v += ldx<CG>(upd + j2);
+    sm.yt[tid - 128] = v;
+  }
+  __syncthreads();
+  if (it.nchild > 2) {                       // rare (a separator that does not disconnect): generic path
+    for (int q = P.cptr[it.f] + 2; q < P.cptr[it.f + 1]; ++q) {
+      const int ch = P.child[q];
+      const int uc2 = 2 * front_u(P, ch);
+      const int32_t* cm = P.cmap + P.cmap_ptr[ch];
+      const double* uv = upd + P.uoff[ch];
+      for (int k = tid; k < uc2; k += 256) {
+        const int t = 2 * cm[k >> 1] + (k & 1);
+        if (t < s2) sm.y1[t] += ldx<CG>(uv + k);
+        else if (t >= row0 && t < row0 + nrows) sm.yt[t - row0] += ldx<CG>(uv + k);
+      }
+      __syncthreads();
+    }
+  }
+  double acc = 0.0;
+  if (lr < nrows) {
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int q = 0; q < FQ; q += 2) {
+      const int k = ks + q * nks;
+      if (k < s2) a0 = fma(mreg[q], sm.y1[k], a0);
+      if (k + nks < s2) a1 = fma(mreg[q + 1], sm.y1[k + nks], a1);
+    }
+    for (int k = ks + FQ * nks; k < s2; k += nks) a0 = fma(M[(int64_t)k * ld], sm.y1[k], a0);
+    acc = a0 + a1;
+  }
+  sm.part[warp][lane] = acc;
+  __syncthreads();
+  if (ks == 0 && lr < nrows) {
+    double t = 0.0;
+    for (int q = 0; q < nks; ++q) t += sm.part[q * G + rg][lane];
+    const int row = row0 + lr;
+    if (row < s2) z[it.g0 + row] = t;
+    else upd[it.uoff + (row - s2)] = sm.yt[lr] - t;
+  }
+}
+
+// backward: one warp per pivot column, 8 columns per CTA
+template <bool CG>
+__device__ __forceinline__ void backward_item(const BwdItem& it, const PlanView& P, double* x, const Deps& dp) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u2 = it.u2;
+  const bool active = warp < it.ncols;
+  const int32_t* st = P.strct + it.soff;
+  const double* wc = P.pool + it.foff + it.s2 + (int64_t)(it.col0 + warp) * it.ld;   // F21new(j, col) at col*ld + s2 + j
+  // ---- static prefetch: factor column and gather offsets
+  double wreg[BQ]; int64_t xo[BQ];
+#pragma unroll
+  for (int q = 0; q < BQ; ++q) {
+    const int j = lane + 32 * q;
+    const bool ok = active && j < u2;
+    wreg[q] = ok ? wc[j] : 0.0;
+    xo[q] = ok ? 2 * (int64_t)st[j >> 1] + (j & 1) : -1;
+  }
+  if (CG) {
+    if (threadIdx.x == 0) {
+      wait_count(dp.fdone + it.f, it.tgt_f * dp.epoch, dp.status);             // z of this front is complete
+      if (it.parent >= 0) { wait_count(dp.fdone + it.parent, it.tgt_pf * dp.epoch, dp.status); wait_count(dp.bdone + it.parent, it.tgt_pb * dp.epoch, dp.status); }
+    }
+    __syncthreads();
+  }
+  if (!active) return;
+  double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+  for (int q = 0; q < BQ; q += 2) {
+    if (xo[q] >= 0) a0 = fma(wreg[q], ldx<CG>(x + xo[q]), a0);
+    if (xo[q + 1] >= 0) a1 = fma(wreg[q + 1], ldx<CG>(x + xo[q + 1]), a1);
+  }
+  for (int j = lane + 32 * BQ; j < u2; j += 32) a0 = fma(wc[j], ldx<CG>(x + 2 * (int64_t)st[j >> 1] + (j & 1)), a0);
+  double a = a0 + a1;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) a += __shfl_down_sync(0xffffffffu, a, off);
+  if (lane == 0) { double* xp = x + it.g0 + it.col0 + warp; *xp = ldx<CG>(xp) - a; }
+}
+
+__global__ void __launch_bounds__(256) forward_kernel(const FwdItem* __restrict__ items, const int32_t* __restrict__ gsrc, PlanView P,
+                                                       const double* __restrict__ rhs, double* __restrict__ z,
+                                                       double* __restrict__ upd) {
+  __shared__ SweepSmem sm;
+  const Deps none{nullptr, nullptr, nullptr, 0, nullptr};
+  forward_item<false>(items[blockIdx.x], gsrc, P, rhs, z, upd, sm, none);
+}
+
+__global__ void __launch_bounds__(256) backward_kernel(const BwdItem* __restrict__ items, PlanView P, double* __restrict__ x) {
+  const Deps none{nullptr, nullptr, nullptr, 0, nullptr};
+  backward_item<false>(items[blockIdx.x], P, x, none);
+}
+
+// ---- persistent operator kernel: x = refine((A - sigma B)^-1 b) in ONE cooperative launch ----------------
+// As separate launches (even inside a CUDA graph) every step of a sweep pays the launch/drain gap, and with
+// several designs in flight the GPU front end becomes the limiter (~3 us per kernel node).  Here a
+// co-resident grid runs the whole operator application: items sit in one queue ordered children-before-
+// parents; CTA b takes items b, b+G, b+2G... in order and, instead of a grid-wide barrier per level, waits
+// only for the fronts it depends on (per-front completion counters in global memory, dataflow).  Items a CTA
+// waits for always precede it in the queue and every CTA is resident (cooperative launch), so the wait
+// cannot deadlock; a spin limit turns a bug into an error flag instead of a hung GPU.  Grid barriers remain
+// only around the refinement SpMV.
+struct OpArgs {
+  PlanView P;
+  const FwdItem* fwd_q; const BwdItem* bwd_q;   // forward queue (levels ascending), backward queue (levels descending)
+  const int32_t* gsrc;
+  int n_fwd, n_bwd;
+  int32_t* fdone; int32_t* bdone; int32_t* status; const int32_t* nfs;
+  int epoch0;                                 // sweeps completed before this launch
+  const double* b; double* x; double* upd;   // b and x: length 2n, permuted interleaved layout
+  double* rt; double* rdx;                    // refinement work vectors
+  int refine;
+  int32_t n; const int32_t* rowptr; const int32_t* col; const double* vals; int64_t nnz; double sigma;
+};
+
+__device__ __forceinline__ void sweep_dataflow(const OpArgs& a, const double* rhs, double* out, int epoch, SweepSmem& sm) {
+  const Deps dp{a.fdone, a.bdone, a.status, epoch, a.nfs};
+  for (int i = blockIdx.x; i < a.n_fwd; i += gridDim.x) {
+    const FwdItem it = a.fwd_q[i];
+    forward_item<true>(it, a.gsrc, a.P, rhs, out, a.upd, sm, dp);
+    __threadfence();
+    __syncthreads();                       // all writes of the item are fenced; shared memory is free again
+    if (threadIdx.x == 0) atomicAdd(a.fdone + it.f, 1);
+  }
+  for (int i = blockIdx.x; i < a.n_bwd; i += gridDim.x) {
+    const BwdItem it = a.bwd_q[i];
+    backward_item<true>(it, a.P, out, dp);
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(a.bdone + f, 1);
+    if (threadIdx.x == 0) atomicAdd(a.bdone + it.f, 1);
   }
 }
 
@@ -489,9 +539,34 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
   D.uoff.upload(ctx, uoff);
   D.upd.alloc(ctx, std::max<int64_t>(D.upd_len, 1));
 
-  std::vector<int4> wt, stl, ea, fw, bw;
+  std::vector<int4> wt, stl, ea;
+  std::vector<FwdItem> fw; std::vector<BwdItem> bw;
   D.w_ptr.assign(P.nlevels + 1, 0); D.s_ptr = D.ea_ptr = D.fwd_ptr = D.bwd_ptr = D.w_ptr;
   D.lmax_m.assign(P.nlevels, 0);
+  // flattened child -> parent gather: per front, for every front row (2nf unknowns) the offset into the
+  // update-vector pool it receives from the first and from the second child (-1 = nothing)
+  std::vector<int32_t> goff(P.nfronts + 1, 0);
+  for (int f = 0; f < P.nfronts; ++f) goff[f + 1] = goff[f] + 4 * (P.s[f] + P.sptr[f + 1] - P.sptr[f]);
+  std::vector<int32_t> gsrc(goff[P.nfronts], -1);
+  for (int f = 0; f < P.nfronts; ++f) {
+    const int nf2 = 2 * (P.s[f] + P.sptr[f + 1] - P.sptr[f]);
+    for (int q = P.cptr[f]; q < std::min(P.cptr[f] + 2, P.cptr[f + 1]); ++q) {
+      const int ch = P.child[q];
+      int32_t* g = gsrc.data() + goff[f] + (q - P.cptr[f]) * nf2;
+      for (int k = P.sptr[ch], o = P.cmap_ptr[ch], idx = 0; k < P.sptr[ch + 1]; ++k, ++o, ++idx) {
+        g[2 * P.cmap[o]] = uoff[ch] + 2 * idx;
+        g[2 * P.cmap[o] + 1] = uoff[ch] + 2 * idx + 1;
+      }
+    }
+  }
+  std::vector<int32_t> nfs(P.nfronts, 0), nbs(P.nfronts, 0);
+  for (int f = 0; f < P.nfronts; ++f) {
+    const int s2 = 2 * P.s[f], u2 = 2 * (P.sptr[f + 1] - P.sptr[f]);
+    const int rows = s2 + u2;
+    const int G = rows <= 32 ? 1 : (rows <= 64 ? 2 : (rows <= 128 ? 4 : 1));
+    nfs[f] = (rows + 32 * G - 1) / (32 * G);
+    nbs[f] = u2 > 0 ? (s2 + BWD_COLS - 1) / BWD_COLS : 0;
+  }
   for (int l = 0; l < P.nlevels; ++l) {
     for (int q = P.lptr[l]; q < P.lptr[l + 1]; ++q) {
       const int f = P.lfront[q];
@@ -507,27 +582,42 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
       {
         const int rows = s2 + u2;
         const int G = rows <= 32 ? 1 : (rows <= 64 ? 2 : (rows <= 128 ? 4 : 1));
-        for (int r0 = 0; r0 < rows; r0 += 32 * G) fw.push_back(make_int4(f, r0, std::min(32 * G, rows - r0), G));
+        const int nch = P.cptr[f + 1] - P.cptr[f];
+        for (int r0 = 0; r0 < rows; r0 += 32 * G) {
+          FwdItem it{};
+          it.f = f; it.row0 = r0; it.nrows = std::min(32 * G, rows - r0); it.G = G; it.s2 = s2; it.ld = rows;
+          it.ch0 = nch > 0 ? P.child[P.cptr[f]] : -1; it.ch1 = nch > 1 ? P.child[P.cptr[f] + 1] : -1;
+          it.tgt0 = it.ch0 >= 0 ? nfs[it.ch0] : 0; it.tgt1 = it.ch1 >= 0 ? nfs[it.ch1] : 0;
+          it.uoff = uoff[f]; it.goff = goff[f]; it.nchild = nch; it.tgtx = 0;
+          it.foff = P.foff[f]; it.g0 = 2 * (int64_t)P.first[f];
+          fw.push_back(it);
+        }
       }
       if (u2 > 0)
-        for (int c0 = 0; c0 < s2; c0 += BWD_COLS) bw.push_back(make_int4(f, c0, std::min(BWD_COLS, s2 - c0), 0));
+        for (int c0 = 0; c0 < s2; c0 += BWD_COLS) {
+          BwdItem it{};
+          const int pa = P.parent[f];
+          it.f = f; it.col0 = c0; it.ncols = std::min(BWD_COLS, s2 - c0); it.s2 = s2; it.u2 = u2; it.ld = s2 + u2; it.soff = P.sptr[f];
+          it.parent = pa; it.tgt_f = nfs[f]; it.tgt_pf = pa >= 0 ? nfs[pa] : 0; it.tgt_pb = pa >= 0 ? nbs[pa] : 0;
+          it.foff = P.foff[f]; it.g0 = 2 * (int64_t)P.first[f];
+          bw.push_back(it);
+        }
     }
     D.w_ptr[l + 1] = (int32_t)wt.size(); D.s_ptr[l + 1] = (int32_t)stl.size(); D.ea_ptr[l + 1] = (int32_t)ea.size();
     D.fwd_ptr[l + 1] = (int32_t)fw.size(); D.bwd_ptr[l + 1] = (int32_t)bw.size();
   }
   {
-    // queues and counters of the persistent operator kernel
-    std::vector<int4> bq; bq.reserve(bw.size());
+    // backward queue of the persistent operator kernel: levels descending; completion counters
+    std::vector<BwdItem> bq; bq.reserve(bw.size());
     for (int l = P.nlevels - 1; l >= 0; --l) bq.insert(bq.end(), bw.begin() + D.bwd_ptr[l], bw.begin() + D.bwd_ptr[l + 1]);
-    std::vector<int32_t> nfs(P.nfronts, 0), nbs(P.nfronts, 0);
-    for (const int4& it : fw) nfs[it.x]++;
-    for (const int4& it : bw) nbs[it.x]++;
-    D.bwd_q.upload(ctx, bq); D.nfs.upload(ctx, nfs); D.nbs.upload(ctx, nbs);
+    D.bwd_q.upload(ctx, bq);
     D.n_fwd = (int)fw.size(); D.n_bwd = (int)bq.size();
     D.fdone.alloc(ctx, P.nfronts); D.bdone.alloc(ctx, P.nfronts);
+    D.nfs.upload(ctx, nfs);
   }
+  D.gsrc.upload(ctx, gsrc);
   D.w_tiles.upload(ctx, wt); D.s_tiles.upload(ctx, stl); D.ea_slabs.upload(ctx, ea);
-  D.fwd_slabs.upload(ctx, fw); D.bwd_slabs.upload(ctx, bw);
+  D.fwd_items.upload(ctx, fw); D.bwd_items.upload(ctx, bw);
   D.pool.alloc(ctx, (size_t)P.foff[P.nfronts]);
   D.status.alloc(ctx, 4);
   // the host vectors above are pageable: make sure the copies are done before they go out of scope
@@ -581,7 +671,7 @@ void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double
   const PlanView v = view(D);
   for (int l = 0; l < D.nlevels; ++l) {
     const int nsl = D.fwd_ptr[l + 1] - D.fwd_ptr[l];
-    forward_kernel<<<nsl, 256, 0, ctx->stream>>>(D.fwd_slabs.p + D.fwd_ptr[l], v, b, z, D.upd.p);
+    forward_kernel<<<nsl, 256, 0, ctx->stream>>>(D.fwd_items.p + D.fwd_ptr[l], D.gsrc.p, v, b, z, D.upd.p);
     ctx->launches++;
   }
   PLFEM_CUDA(cudaGetLastError());
@@ -592,7 +682,7 @@ void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x) {
   for (int l = D.nlevels - 1; l >= 0; --l) {
     const int nsl = D.bwd_ptr[l + 1] - D.bwd_ptr[l];
     if (nsl == 0) continue;
-    backward_kernel<<<nsl, 256, 0, ctx->stream>>>(D.bwd_slabs.p + D.bwd_ptr[l], v, x);
+    backward_kernel<<<nsl, 256, 0, ctx->stream>>>(D.bwd_items.p + D.bwd_ptr[l], v, x);
     ctx->launches++;
   }
   PLFEM_CUDA(cudaGetLastError());
@@ -615,8 +705,8 @@ void run_operator(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const doubl
                   double* x, double* rt, double* rdx, int refine, int ctas_per_sm) {
   OpArgs a;
   a.P = view(D);
-  a.fwd_q = D.fwd_slabs.p; a.bwd_q = D.bwd_q.p; a.n_fwd = D.n_fwd; a.n_bwd = D.n_bwd;
-  a.parent = D.parent.p; a.nfs = D.nfs.p; a.nbs = D.nbs.p; a.fdone = D.fdone.p; a.bdone = D.bdone.p; a.status = D.status.p;
+  a.fwd_q = D.fwd_items.p; a.bwd_q = D.bwd_q.p; a.gsrc = D.gsrc.p; a.n_fwd = D.n_fwd; a.n_bwd = D.n_bwd;
+  a.fdone = D.fdone.p; a.bdone = D.bdone.p; a.status = D.status.p; a.nfs = D.nfs.p;
   a.epoch0 = D.epoch; D.epoch += 1 + refine;
   a.b = b; a.x = x; a.upd = D.upd.p; a.rt = rt; a.rdx = rdx; a.refine = refine;
   a.n = pat.n; a.rowptr = pat.rowptr.p; a.col = pat.col.p; a.vals = d_vals; a.nnz = pat.nnz; a.sigma = sigma;
