@@ -111,7 +111,7 @@ int plfem_spmv_csr(plfem_ctx* ctx, int64_t rows, int64_t nnz, const int64_t* ind
 typedef struct {
   double sigma;        /* shift (solver_fem.py:187-193, computed by the caller) */
   int32_t k;           /* eigenpairs wanted = min(n_modes+12, 2 N_solve - 4)  (solver_fem.py:196) */
-  int32_t ncv;         /* Lanczos basis size; 0 = scipy's default max(2k+1, 20) */
+  int32_t ncv;         /* Lanczos basis size; 0 = default: scipy's max(2k+1, 20) for block = 1, 3k for block Lanczos */
   double tol;          /* 1e-7 in the reference */
   int32_t maxiter;     /* restarts allowed, 12000 in the reference */
   const double* v0;    /* optional start vector, reference ordering, length 2 N_solve; NULL = ones */
@@ -119,6 +119,7 @@ typedef struct {
   int32_t max_sn_nodes;/* supernode width limit in nodes (0 = default) */
   int32_t reuse_symbolic; /* 1 = keep ordering/front plan from the previous solve on this problem */
   int32_t refine;      /* iterative-refinement steps per operator application: 0 = default (1), n > 0 = n, -1 = none */
+  int32_t block;       /* Lanczos block size: 0 = default (4 vectors per operator application), 1 = single vector */
 } plfem_solve_opts;
 
 typedef struct {
@@ -130,6 +131,7 @@ typedef struct {
   double max_residual;              /* normwise backward error: max_i ||A x - lambda B x||_2 / ((||A||_F + |lambda| ||B||_F) ||x||_2) */
   float ms_symbolic, ms_assemble, ms_factor, ms_lanczos, ms_metrics, ms_total; /* host wall / CUDA events */
   int32_t kernel_launches;
+  int32_t n_block_op;               /* sequential operator applications (= n_op / block size) */
 } plfem_solve_stats;
 
 /* Per-mode reductions of solver_fem.py:212-220, computed on the l2-normalised (vx, vy):

@@ -43,7 +43,7 @@ class Material(C.Structure):
 class SolveOpts(C.Structure):
     _fields_ = [("sigma", c_f64), ("k", c_i32), ("ncv", c_i32), ("tol", c_f64), ("maxiter", c_i32),
                 ("v0", p_f64), ("leaf_nodes", c_i32), ("max_sn_nodes", c_i32), ("reuse_symbolic", c_i32),
-                ("refine", c_i32)]
+                ("refine", c_i32), ("block", c_i32)]
 
 
 class SolveStats(C.Structure):
@@ -52,7 +52,7 @@ class SolveStats(C.Structure):
                 ("front_pool_doubles", c_i64), ("factor_flops", c_f64), ("max_residual", c_f64),
                 ("ms_symbolic", C.c_float), ("ms_assemble", C.c_float), ("ms_factor", C.c_float),
                 ("ms_lanczos", C.c_float), ("ms_metrics", C.c_float), ("ms_total", C.c_float),
-                ("kernel_launches", c_i32)]
+                ("kernel_launches", c_i32), ("n_block_op", c_i32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -234,11 +234,11 @@ class Problem:
 
     def solve_modes(self, material: Material, sigma: float, k: int, ncv: int = 0, tol: float = 1e-7,
                     maxiter: int = 12000, v0=None, want_vectors: bool = True, leaf_nodes: int = 0,
-                    max_sn_nodes: int = 0, reuse_symbolic: bool = False, refine: int = 0):
+                    max_sn_nodes: int = 0, reuse_symbolic: bool = False, refine: int = 0, block: int = 0):
         n2 = 2 * self.n_interior
         o = SolveOpts(sigma=float(sigma), k=int(k), ncv=int(ncv), tol=float(tol), maxiter=int(maxiter),
                       leaf_nodes=int(leaf_nodes), max_sn_nodes=int(max_sn_nodes),
-                      reuse_symbolic=int(bool(reuse_symbolic)), refine=int(refine))
+                      reuse_symbolic=int(bool(reuse_symbolic)), refine=int(refine), block=int(block))
         if v0 is not None:
             v0 = np.ascontiguousarray(v0, dtype=np.float64)
             if v0.shape != (n2,):

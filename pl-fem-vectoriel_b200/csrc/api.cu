@@ -507,8 +507,16 @@ int plfem_solve_modes(plfem_problem* pb, const plfem_material* mat, const plfem_
     DevBuf<double> X;
     std::vector<double> lambda;
     EigenResult er;
-    run_eigensolver(ctx, pb->dperm, pb->dplan, pb->d_vals.p, o->sigma, k, ncv, o->tol > 0 ? o->tol : 1e-7,
-                    o->maxiter > 0 ? o->maxiter : 12000, o->refine == 0 ? 1 : std::max(o->refine, 0), v0p, X, lambda, er);
+    const int refine = o->refine == 0 ? 1 : std::max(o->refine, 0);
+    const int block = o->block == 0 ? SOLVE_NRHS : o->block;     // 0 = default (block Lanczos), 1 = single vector
+    if (block == SOLVE_NRHS && 2 * n >= 8 * SOLVE_NRHS)
+      run_eigensolver_block(ctx, pb->dperm, pb->dplan, pb->d_vals.p, o->sigma, k, o->ncv > 0 ? o->ncv : 3 * k, o->tol > 0 ? o->tol : 1e-7,
+                            o->maxiter > 0 ? o->maxiter : 12000, refine, v0p, X, lambda, er);
+    else if (block == 1 || 2 * n < 8 * SOLVE_NRHS)
+      run_eigensolver(ctx, pb->dperm, pb->dplan, pb->d_vals.p, o->sigma, k, ncv, o->tol > 0 ? o->tol : 1e-7,
+                      o->maxiter > 0 ? o->maxiter : 12000, refine, v0p, X, lambda, er);
+    else
+      throw StatusError(PLFEM_ERR_INVALID, "block must be 0 (default), 1 or " + std::to_string(SOLVE_NRHS));
     PLFEM_CUDA(cudaEventRecord(ctx->ev[3], st));
     pb->dplan.status.download(fstat, 4);
     PLFEM_CUDA(cudaStreamSynchronize(st));
@@ -531,7 +539,7 @@ int plfem_solve_modes(plfem_problem* pb, const plfem_material* mat, const plfem_
 
     if (stats) {
       std::memset(stats, 0, sizeof(*stats));
-      stats->nconv = er.nconv; stats->n_op = er.n_op; stats->n_restart = er.n_restart;
+      stats->nconv = er.nconv; stats->n_op = er.n_op; stats->n_restart = er.n_restart; stats->n_block_op = er.n_block_op;
       stats->n_fronts = pb->plan.nfronts; stats->n_levels = pb->plan.nlevels; stats->max_front_nodes = pb->plan.max_front;
       stats->factor_entries = pb->plan.factor_entries; stats->front_pool_doubles = pb->plan.foff[pb->plan.nfronts];
       stats->factor_flops = pb->plan.factor_flops;

@@ -161,30 +161,35 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D);
 void launch_front_load(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, double sigma);
 void run_factorization(plfem_ctx* ctx, const DevPlan& D);
 // solves (A - sigma B) x = b in the permuted interleaved layout, b and x of length 2n (must not alias)
-void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x);
+constexpr int SOLVE_NRHS = 4;   // block size of the multi-right-hand-side sweeps (block Lanczos)
+void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x, int nrhs = 1, int64_t ld = 0);
 void run_operator(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, double sigma, const double* b,
                   double* x, double* rt, double* rdx, int refine, int ctas_per_sm);
-void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double* z);
-void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x);
+void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double* z, int nrhs = 1, int64_t ld = 0);
+void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs = 1, int64_t ld = 0);
 
 // ---- Lanczos + mode reductions (eigen.cu) ----------------------------------------------------------
 struct EigenResult {
   std::vector<double> theta;  // Ritz values of OP, wanted ones, sorted by eigenvalue ascending
-  int nconv = 0, n_op = 0, n_restart = 0;
+  int nconv = 0, n_op = 0, n_restart = 0, n_block_op = 0;
 };
 struct EigenWork;  // opaque
 void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, double sigma,
                      int k, int ncv, double tol, int maxiter, int refine_steps, const double* d_v0 /* permuted, may be null */,
                      DevBuf<double>& X /* (2n, k) eigenvectors, permuted layout */, std::vector<double>& lambda,
                      EigenResult& res);
+void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, double sigma, int k, int ncv,
+                           double tol, int maxiter, int refine_steps, const double* d_v0, DevBuf<double>& X,
+                           std::vector<double>& lambda, EigenResult& res);
 void run_mode_metrics(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, const int32_t* d_perm_to_interior,
                       const uint8_t* d_in_core, const double* X, const std::vector<double>& lambda, int k,
                       double* d_out_evecs /* (k, 2n) reference ordering or null */, double* d_metrics /* (k,8) */,
                       double* d_resid /* (k,2) */);
 
-void launch_spmm_b(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, const double* x, double* y);
+void launch_spmm_b(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, const double* x, double* y, int nrhs = 1,
+                   int64_t ld = 0);
 void launch_resid_k(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, double sigma, const double* x, const double* b,
-                    double* t);
+                    double* t, int nrhs = 1, int64_t ld = 0);
 
 void launch_axpy(plfem_ctx* ctx, double* x, const double* dx, int64_t m);
 void symmetric_eigen(int n, std::vector<double>& a /* n*n col-major in, eigenvectors out */, std::vector<double>& w);

@@ -40,56 +40,77 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
   return v;  // valid in thread 0
 }
 
-// y = B x on the permuted interleaved layout: y[r] (2 comps) = sum_z minv[z] * x[col[z]] (2 comps)
+// Y = B X on the permuted interleaved layout, NR right-hand sides (columns of ld2 double2):
+// y[r] (2 comps) = sum_z minv[z] * x[col[z]] (2 comps)
+template <int NR>
 __global__ void __launch_bounds__(256) spmm_b_kernel(int32_t n, const int32_t* __restrict__ rowptr,
                                                      const int32_t* __restrict__ col, const double* __restrict__ minv,
-                                                     const double2* __restrict__ x, double2* __restrict__ y) {
+                                                     const double2* __restrict__ x, double2* __restrict__ y, int64_t ld2) {
   constexpr int TPR = 4;
   const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t row = gid / TPR;
   const int lane = (int)(gid % TPR);
-  double ax = 0.0, ay = 0.0;
+  double ax[NR], ay[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) { ax[r] = 0.0; ay[r] = 0.0; }
   if (row < n) {
     for (int32_t z = rowptr[row] + lane; z < rowptr[row + 1]; z += TPR) {
       const double m = minv[z];
-      const double2 v = x[col[z]];
-      ax = fma(m, v.x, ax); ay = fma(m, v.y, ay);
+      const int32_t c = col[z];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const double2 v = x[r * ld2 + c];
+        ax[r] = fma(m, v.x, ax[r]); ay[r] = fma(m, v.y, ay[r]);
+      }
     }
   }
 #pragma unroll
-  for (int off = TPR / 2; off > 0; off >>= 1) {
-    ax += __shfl_down_sync(0xffffffffu, ax, off, TPR);
-    ay += __shfl_down_sync(0xffffffffu, ay, off, TPR);
+  for (int r = 0; r < NR; ++r) {
+#pragma unroll
+    for (int off = TPR / 2; off > 0; off >>= 1) {
+      ax[r] += __shfl_down_sync(0xffffffffu, ax[r], off, TPR);
+      ay[r] += __shfl_down_sync(0xffffffffu, ay[r], off, TPR);
+    }
+    if (row < n && lane == 0) y[r * ld2 + row] = make_double2(ax[r], ay[r]);
   }
-  if (row < n && lane == 0) y[row] = make_double2(ax, ay);
 }
 
-// t = b - (A - sigma B) x on the permuted interleaved layout (iterative refinement of the block-LDL^T solve)
+// T = Bv - (A - sigma B) X on the permuted interleaved layout (iterative refinement of the block-LDL^T solve)
+template <int NR>
 __global__ void __launch_bounds__(256) resid_k_kernel(int32_t n, const int32_t* __restrict__ rowptr,
                                                       const int32_t* __restrict__ col, const double* __restrict__ vals,
                                                       int64_t nnz, double sigma, const double2* __restrict__ x,
-                                                      const double2* __restrict__ b, double2* __restrict__ t) {
+                                                      const double2* __restrict__ b, double2* __restrict__ t, int64_t ld2) {
   constexpr int TPR = 4;
   const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t row = gid / TPR;
   const int lane = (int)(gid % TPR);
-  double ax = 0.0, ay = 0.0;
+  double ax[NR], ay[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) { ax[r] = 0.0; ay[r] = 0.0; }
   if (row < n) {
     for (int32_t z = rowptr[row] + lane; z < rowptr[row + 1]; z += TPR) {
       const double sm = sigma * vals[(int64_t)S_MINV * nnz + z];
-      const double2 v = x[col[z]];
-      ax = fma(vals[(int64_t)S_AXX * nnz + z] - sm, v.x, ax);
-      ax = fma(vals[(int64_t)S_AXY * nnz + z], v.y, ax);
-      ay = fma(vals[(int64_t)S_AYX * nnz + z], v.x, ay);
-      ay = fma(vals[(int64_t)S_AYY * nnz + z] - sm, v.y, ay);
+      const double kxx = vals[(int64_t)S_AXX * nnz + z] - sm, kxy = vals[(int64_t)S_AXY * nnz + z];
+      const double kyx = vals[(int64_t)S_AYX * nnz + z], kyy = vals[(int64_t)S_AYY * nnz + z] - sm;
+      const int32_t c = col[z];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const double2 v = x[r * ld2 + c];
+        ax[r] = fma(kxx, v.x, ax[r]); ax[r] = fma(kxy, v.y, ax[r]);
+        ay[r] = fma(kyx, v.x, ay[r]); ay[r] = fma(kyy, v.y, ay[r]);
+      }
     }
   }
 #pragma unroll
-  for (int off = TPR / 2; off > 0; off >>= 1) {
-    ax += __shfl_down_sync(0xffffffffu, ax, off, TPR);
-    ay += __shfl_down_sync(0xffffffffu, ay, off, TPR);
+  for (int r = 0; r < NR; ++r) {
+#pragma unroll
+    for (int off = TPR / 2; off > 0; off >>= 1) {
+      ax[r] += __shfl_down_sync(0xffffffffu, ax[r], off, TPR);
+      ay[r] += __shfl_down_sync(0xffffffffu, ay[r], off, TPR);
+    }
+    if (row < n && lane == 0) { const double2 bb = b[r * ld2 + row]; t[r * ld2 + row] = make_double2(bb.x - ax[r], bb.y - ay[r]); }
   }
-  if (row < n && lane == 0) { const double2 bb = b[row]; t[row] = make_double2(bb.x - ax, bb.y - ay); }
 }
 
 __global__ void __launch_bounds__(256) add_kernel(double* __restrict__ x, const double* __restrict__ dx, int64_t m) {
@@ -167,6 +188,131 @@ __global__ void __launch_bounds__(128) rotate_kernel(const double* __restrict__ 
 #pragma unroll
     for (int c = 0; c < 8; ++c)
       if (c0 + c < nout) Out[(int64_t)(c0 + c) * ldo + i] = acc[c];
+  }
+}
+
+// ---- block Lanczos pieces (P = SOLVE_NRHS vectors per block) -------------------------------------------------
+constexpr int P = SOLVE_NRHS;
+
+// H[c + r*ldh] = <Q[:,c], R[:,r]> for c < ncols, r < P; one CTA per column c
+__global__ void __launch_bounds__(RED_T) dots_block_kernel(const double* __restrict__ Q, int64_t ld, const double* __restrict__ R,
+                                                           int64_t m, double* __restrict__ H, int ldh) {
+  __shared__ double sh[32];
+  const double* q = Q + (int64_t)blockIdx.x * ld;
+  double acc[P];
+#pragma unroll
+  for (int r = 0; r < P; ++r) acc[r] = 0.0;
+  for (int64_t i = threadIdx.x; i < m; i += RED_T) {
+    const double qv = q[i];
+#pragma unroll
+    for (int r = 0; r < P; ++r) acc[r] = fma(qv, R[r * ld + i], acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < P; ++r) {
+    const double t = block_sum(acc[r], sh);
+    if (threadIdx.x == 0) H[blockIdx.x + r * ldh] = t;
+  }
+}
+
+// R[:, r] -= V[:, 0..ncols) H[:, r]
+__global__ void __launch_bounds__(256) update_block_kernel(const double* __restrict__ V, int64_t ld, const double* __restrict__ H,
+                                                           int ldh, int ncols, int64_t m, double* __restrict__ R) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  double acc[P];
+#pragma unroll
+  for (int r = 0; r < P; ++r) acc[r] = 0.0;
+  for (int c = 0; c < ncols; ++c) {
+    const double v = V[(int64_t)c * ld + i];
+#pragma unroll
+    for (int r = 0; r < P; ++r) acc[r] = fma(v, __ldg(H + c + r * ldh), acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < P; ++r) R[r * ld + i] -= acc[r];
+}
+
+// Hs[0..ncols, r] = h1 + h2 (the projected-matrix column block kept for the host)
+__global__ void store_h_kernel(const double* __restrict__ h1, const double* __restrict__ h2, int ldh, int ncols, double* __restrict__ Hs, int lds) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncols) return;
+#pragma unroll
+  for (int r = 0; r < P; ++r) Hs[c + r * lds] = h1[c + r * ldh] + h2[c + r * ldh];
+}
+
+// G[r + s*P] = <R[:,r], U[:,s]>, one CTA per r
+__global__ void __launch_bounds__(RED_T) gram_kernel(const double* __restrict__ R, const double* __restrict__ U, int64_t ld, int64_t m,
+                                                     double* __restrict__ G) {
+  __shared__ double sh[32];
+  const double* rr = R + (int64_t)blockIdx.x * ld;
+  double acc[P];
+#pragma unroll
+  for (int s2 = 0; s2 < P; ++s2) acc[s2] = 0.0;
+  for (int64_t i = threadIdx.x; i < m; i += RED_T) {
+    const double v = rr[i];
+#pragma unroll
+    for (int s2 = 0; s2 < P; ++s2) acc[s2] = fma(v, U[s2 * ld + i], acc[s2]);
+  }
+#pragma unroll
+  for (int s2 = 0; s2 < P; ++s2) {
+    const double t = block_sum(acc[s2], sh);
+    if (threadIdx.x == 0) G[blockIdx.x + s2 * P] = t;
+  }
+}
+
+// Cholesky G = L L^T (P x P, symmetrised), Linv = L^-1.  Lout (for the host): L, column-major.  status[2] = 1 on breakdown.
+__global__ void chol_kernel(const double* __restrict__ G, double* __restrict__ Lout, double* __restrict__ Linv, int32_t* status) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double A[P][P], L[P][P], Li[P][P];
+  for (int i = 0; i < P; ++i) for (int j = 0; j < P; ++j) { A[i][j] = 0.5 * (G[i + j * P] + G[j + i * P]); L[i][j] = 0.0; Li[i][j] = 0.0; }
+  double dmax = 0.0;
+  for (int i = 0; i < P; ++i) dmax = fmax(dmax, A[i][i]);
+  for (int j = 0; j < P; ++j) {
+    double d = A[j][j];
+    for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
+    if (!(d > 1e-24 * dmax) || !isfinite(d)) { atomicExch(status + 2, 1); d = 1e-24 * dmax + 1e-300; }
+    L[j][j] = sqrt(d);
+    for (int i = j + 1; i < P; ++i) {
+      double v = A[i][j];
+      for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
+      L[i][j] = v / L[j][j];
+    }
+  }
+  for (int j = 0; j < P; ++j) {           // Li = L^-1 by forward substitution on the identity
+    for (int i = 0; i < P; ++i) {
+      double v = (i == j) ? 1.0 : 0.0;
+      for (int k = 0; k < i; ++k) v -= L[i][k] * Li[k][j];
+      Li[i][j] = v / L[i][i];
+    }
+  }
+  for (int i = 0; i < P; ++i) for (int j = 0; j < P; ++j) { Lout[i + j * P] = L[i][j]; Linv[i + j * P] = Li[i][j]; }
+}
+
+// Vn = R L^-T, BVn = U L^-T   (Vn[:, r] = sum_s R[:, s] * Linv[r, s])
+__global__ void __launch_bounds__(256) scale_block_kernel(const double* __restrict__ R, const double* __restrict__ U, int64_t ld, int64_t m,
+                                                          const double* __restrict__ Linv, double* __restrict__ Vn,
+                                                          double* __restrict__ BVn) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  double rv[P], uv[P];
+#pragma unroll
+  for (int s2 = 0; s2 < P; ++s2) { rv[s2] = R[s2 * ld + i]; uv[s2] = U[s2 * ld + i]; }
+#pragma unroll
+  for (int r = 0; r < P; ++r) {
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int s2 = 0; s2 <= r; ++s2) { const double l = __ldg(Linv + r + s2 * P); a = fma(rv[s2], l, a); b = fma(uv[s2], l, b); }
+    Vn[r * ld + i] = a; BVn[r * ld + i] = b;
+  }
+}
+
+// deterministic pseudo-random start vectors for block columns 1..P-1 (column 0 is the caller's v0 / ones)
+__global__ void start_block_kernel(double* __restrict__ R, int64_t ld, int64_t m) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  for (int r = 1; r < P; ++r) {
+    uint64_t h = (uint64_t)i * 0x9E3779B97F4A7C15ull + (uint64_t)r * 0xBF58476D1CE4E5B9ull + 0x94D049BB133111EBull;
+    h ^= h >> 30; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 27; h *= 0x94D049BB133111EBull; h ^= h >> 31;
+    R[r * ld + i] = (double)(h >> 11) * (2.0 / 9007199254740992.0) - 1.0;
   }
 }
 
@@ -264,19 +410,24 @@ __global__ void __launch_bounds__(256) write_evecs_kernel(int32_t n, const int32
 
 }  // namespace
 
-void launch_spmm_b(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, const double* x, double* y) {
+void launch_spmm_b(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, const double* x, double* y, int nrhs, int64_t ld) {
   const unsigned g = (unsigned)(((int64_t)pat.n * 4 + 255) / 256);
-  spmm_b_kernel<<<g, 256, 0, ctx->stream>>>(pat.n, pat.rowptr.p, pat.col.p, d_vals + (int64_t)S_MINV * pat.nnz, (const double2*)x,
-                                            (double2*)y);
+  const double* minv = d_vals + (int64_t)S_MINV * pat.nnz;
+  if (nrhs == 1) spmm_b_kernel<1><<<g, 256, 0, ctx->stream>>>(pat.n, pat.rowptr.p, pat.col.p, minv, (const double2*)x, (double2*)y, 0);
+  else spmm_b_kernel<SOLVE_NRHS><<<g, 256, 0, ctx->stream>>>(pat.n, pat.rowptr.p, pat.col.p, minv, (const double2*)x, (double2*)y, ld / 2);
   PLFEM_CUDA(cudaGetLastError());
   ctx->launches++;
 }
 
 void launch_resid_k(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, double sigma, const double* x, const double* b,
-                    double* t) {
+                    double* t, int nrhs, int64_t ld) {
   const unsigned g = (unsigned)(((int64_t)pat.n * 4 + 255) / 256);
-  resid_k_kernel<<<g, 256, 0, ctx->stream>>>(pat.n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz, sigma, (const double2*)x,
-                                             (const double2*)b, (double2*)t);
+  if (nrhs == 1)
+    resid_k_kernel<1><<<g, 256, 0, ctx->stream>>>(pat.n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz, sigma, (const double2*)x,
+                                                  (const double2*)b, (double2*)t, 0);
+  else
+    resid_k_kernel<SOLVE_NRHS><<<g, 256, 0, ctx->stream>>>(pat.n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz, sigma, (const double2*)x,
+                                                           (const double2*)b, (double2*)t, ld / 2);
   PLFEM_CUDA(cudaGetLastError());
   ctx->launches++;
 }
@@ -304,8 +455,7 @@ void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const do
   const unsigned gm = (unsigned)((m + 255) / 256);
   const unsigned gspmm = (unsigned)(((int64_t)pat.n * 4 + 255) / 256);
   auto spmm = [&](const double* x, double* y) {
-    spmm_b_kernel<<<gspmm, 256, 0, st>>>(pat.n, pat.rowptr.p, pat.col.p, minv, (const double2*)x, (double2*)y);
-    ctx->launches++;
+    launch_spmm_b(ctx, pat, d_vals, x, y);
   };
 
   // OP application: block-LDL^T solve + fixed number of refinement steps with the true operator
@@ -330,11 +480,9 @@ void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const do
     try {
       run_solve(ctx, D, opin.p, r.p);
       for (int it = 0; it < refine_steps; ++it) {
-        resid_k_kernel<<<gspmm, 256, 0, st>>>(pat.n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz, sigma, (const double2*)r.p,
-                                              (const double2*)opin.p, (double2*)rt.p);
+        launch_resid_k(ctx, pat, d_vals, sigma, r.p, opin.p, rt.p);
         run_solve(ctx, D, rt.p, rdx.p);
-        add_kernel<<<gm, 256, 0, st>>>(r.p, rdx.p, m);
-        ctx->launches += 2;
+        launch_axpy(ctx, r.p, rdx.p, m);
       }
     } catch (...) {
       cudaGraph_t dead = nullptr;
@@ -451,6 +599,173 @@ void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const do
     ctx->launches += 2;
     PLFEM_CUDA(cudaStreamSynchronize(st));     // S is a local host buffer
     cur = nxt; p = keep;
+    res.n_restart++;
+  }
+}
+
+// ---- thick-restart BLOCK Lanczos (block size P) -----------------------------------------------------------
+// Same operator, same inner product, same convergence test as the single-vector version, but every
+// operator application carries P vectors through the sweeps: the factor is read once for P right-hand sides
+// and the number of SEQUENTIAL operator applications — what bounds the latency of this phase, each being a
+// chain of ~70 dependent small kernels — drops from ~57 to ~24 for config 1.  The projected matrix is built
+// from the full-reorthogonalisation coefficients (its upper triangle is exactly what the CGS passes
+// produce), so a thick restart needs no special-casing: the couplings between kept Ritz vectors and the
+// residual block reappear as the first coefficients computed after the restart.
+void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, double sigma, int k, int ncv,
+                           double tol, int maxiter, int refine_steps, const double* d_v0, DevBuf<double>& X,
+                           std::vector<double>& lambda, EigenResult& res) {
+  const int64_t m = 2 * (int64_t)pat.n, ld = m;
+  cudaStream_t st = ctx->stream;
+  const int ncvp = std::max(((std::max(ncv, k + P) + P - 1) / P) * P, 2 * P);
+  const int ldh = ncvp + P;
+  DevBuf<double> V[2], BV[2], R, U, rt, rdx, opin, h1, h2, Hs, G, Lall, Linv, Sdev;
+  for (int b = 0; b < 2; ++b) { V[b].alloc(ctx, (size_t)ld * (ncvp + P)); BV[b].alloc(ctx, (size_t)ld * (ncvp + P)); }
+  R.alloc(ctx, (size_t)m * P); U.alloc(ctx, (size_t)m * P); rt.alloc(ctx, (size_t)m * P); rdx.alloc(ctx, (size_t)m * P);
+  opin.alloc(ctx, (size_t)m * P);
+  h1.alloc(ctx, (size_t)ldh * P); h2.alloc(ctx, (size_t)ldh * P); Hs.alloc(ctx, (size_t)ldh * ncvp);
+  G.alloc(ctx, P * P); Lall.alloc(ctx, (size_t)(ncvp / P + 1) * P * P); Linv.alloc(ctx, P * P);
+  Sdev.alloc(ctx, (size_t)ncvp * ncvp);
+  const unsigned gm = (unsigned)((m + 255) / 256);
+
+  // operator application on P right-hand sides, captured once into a CUDA graph: R = OP(opin)
+  cudaGraph_t graph = nullptr; cudaGraphExec_t gexec = nullptr; int graph_nodes = 0;
+  {
+    const int before = ctx->launches;
+    PLFEM_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    try {
+      run_solve(ctx, D, opin.p, R.p, P, ld);
+      for (int it = 0; it < refine_steps; ++it) {
+        launch_resid_k(ctx, pat, d_vals, sigma, R.p, opin.p, rt.p, P, ld);
+        run_solve(ctx, D, rt.p, rdx.p, P, ld);
+        launch_axpy(ctx, R.p, rdx.p, m * P);
+      }
+    } catch (...) {
+      cudaGraph_t dead = nullptr; cudaStreamEndCapture(st, &dead); if (dead) cudaGraphDestroy(dead);
+      throw;
+    }
+    PLFEM_CUDA(cudaStreamEndCapture(st, &graph));
+    graph_nodes = ctx->launches - before; ctx->launches = before;
+    PLFEM_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
+  }
+  struct GraphGuard { cudaGraph_t g; cudaGraphExec_t e; ~GraphGuard() { if (e) cudaGraphExecDestroy(e); if (g) cudaGraphDestroy(g); } } guard{graph, gexec};
+
+  // B-orthonormalise the block in R: U = B R, G = R^T U = L L^T, Vn = R L^-T, BVn = U L^-T; L kept in slot `slot`
+  auto orthonormalize = [&](double* Vn, double* BVn, int slot) {
+    launch_spmm_b(ctx, pat, d_vals, R.p, U.p, P, ld);
+    gram_kernel<<<P, RED_T, 0, st>>>(R.p, U.p, ld, m, G.p);
+    chol_kernel<<<1, 32, 0, st>>>(G.p, Lall.p + (size_t)slot * P * P, Linv.p, D.status.p);
+    scale_block_kernel<<<gm, 256, 0, st>>>(R.p, U.p, ld, m, Linv.p, Vn, BVn);
+    ctx->launches += 3;
+  };
+
+  // start block: column 0 = v0 (or ones), the others deterministic pseudo-random
+  if (d_v0) PLFEM_CUDA(cudaMemcpyAsync(R.p, d_v0, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  else { fill_kernel<<<gm, 256, 0, st>>>(R.p, m, 1.0); ctx->launches++; }
+  start_block_kernel<<<gm, 256, 0, st>>>(R.p, ld, m);
+  ctx->launches++;
+  int cur = 0;
+  orthonormalize(V[cur].p, BV[cur].p, ncvp / P);     // scratch slot
+
+  std::vector<double> Th((size_t)ncvp * ncvp, 0.0), Hh((size_t)ldh * ncvp), Lh((size_t)(ncvp / P + 1) * P * P), T, w;
+  std::vector<int> order;
+  int nb = P, q = 0;                 // basis vectors present; kept Ritz vectors (their block of Th is diagonal)
+  res = EigenResult();
+  const double eps23 = std::pow(2.220446049250313e-16, 2.0 / 3.0);
+  const int check_from = std::min(ncvp, ((2 * k + P - 1) / P) * P), check_every = 2;
+  int since_check = 0;
+  for (;;) {
+    // ---- one block step: image of the last P basis vectors
+    const int j0 = nb - P;
+    double* Vc = V[cur].p; double* BVc = BV[cur].p;
+    PLFEM_CUDA(cudaMemcpyAsync(opin.p, BVc + (int64_t)j0 * ld, (size_t)m * P * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    PLFEM_CUDA(cudaGraphLaunch(gexec, st));
+    ctx->launches += graph_nodes;
+    res.n_op += P; res.n_block_op++;
+    dots_block_kernel<<<nb, RED_T, 0, st>>>(BVc, ld, R.p, m, h1.p, ldh);
+    update_block_kernel<<<gm, 256, 0, st>>>(Vc, ld, h1.p, ldh, nb, m, R.p);
+    dots_block_kernel<<<nb, RED_T, 0, st>>>(BVc, ld, R.p, m, h2.p, ldh);
+    update_block_kernel<<<gm, 256, 0, st>>>(Vc, ld, h2.p, ldh, nb, m, R.p);
+    store_h_kernel<<<(nb + 127) / 128, 128, 0, st>>>(h1.p, h2.p, ldh, nb, Hs.p + (size_t)j0 * ldh, ldh);
+    ctx->launches += 5;
+    orthonormalize(Vc + (int64_t)nb * ld, BVc + (int64_t)nb * ld, j0 / P);
+    nb += P;
+    ++since_check;
+    const int c = nb - P;            // basis vectors whose images are known
+    const bool full = (c >= ncvp);
+    if (!full && !(c >= check_from && since_check >= check_every)) continue;
+    since_check = 0;
+
+    // ---- convergence check on the c x c projected matrix
+    PLFEM_CUDA(cudaGetLastError());
+    Hs.download(Hh.data(), Hh.size());
+    Lall.download(Lh.data(), Lh.size());
+    int32_t fstat[4];
+    D.status.download(fstat, 4);
+    PLFEM_CUDA(cudaStreamSynchronize(st));
+    if (fstat[2]) throw StatusError(PLFEM_ERR_SINGULAR, "block Lanczos: the residual block lost rank (Cholesky breakdown)");
+    for (int j = q; j < c; ++j)
+      for (int i = 0; i <= j; ++i) Th[(size_t)j * ncvp + i] = Hh[(size_t)j * ldh + i];
+    T.assign((size_t)c * c, 0.0);
+    for (int j = 0; j < c; ++j)
+      for (int i = 0; i <= j; ++i) T[(size_t)j * c + i] = T[(size_t)i * c + j] = Th[(size_t)j * ncvp + i];
+    for (double v : T) if (!std::isfinite(v)) throw StatusError(PLFEM_ERR_SINGULAR, "Lanczos recurrence produced a non-finite value (shifted operator singular?)");
+    symmetric_eigen(c, T, w);        // T now holds eigenvectors in columns
+    order.resize(c);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return std::fabs(w[a]) > std::fabs(w[b]); });
+    const double* L = Lh.data() + (size_t)((c - P) / P) * P * P;     // R_last = V_next L^T
+    auto bound = [&](int col) {
+      double s2 = 0.0;
+      for (int a = 0; a < P; ++a) {
+        double t = 0.0;
+        for (int b = a; b < P; ++b) t += L[b + a * P] * T[(size_t)col * c + (c - P + b)];
+        s2 += t * t;
+      }
+      return std::sqrt(s2);
+    };
+    int nconv = 0;
+    for (int i = 0; i < k; ++i) if (bound(order[i]) <= tol * std::max(eps23, std::fabs(w[order[i]]))) nconv++;
+    res.nconv = nconv;
+    const bool done = nconv >= k;
+    if (done || (full && res.n_restart >= maxiter)) {
+      std::vector<int> sel(order.begin(), order.begin() + k);
+      std::sort(sel.begin(), sel.end(), [&](int a, int b) { return sigma + 1.0 / w[a] < sigma + 1.0 / w[b]; });
+      std::vector<double> S((size_t)c * k);
+      lambda.resize(k); res.theta.resize(k);
+      for (int i = 0; i < k; ++i) {
+        std::copy(T.begin() + (size_t)sel[i] * c, T.begin() + (size_t)(sel[i] + 1) * c, S.begin() + (size_t)i * c);
+        res.theta[i] = w[sel[i]];
+        lambda[i] = sigma + 1.0 / w[sel[i]];
+      }
+      PLFEM_CUDA(cudaMemcpyAsync(Sdev.p, S.data(), S.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+      X.alloc(ctx, (size_t)m * k);
+      rotate_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(V[cur].p, ld, c, Sdev.p, k, m, X.p, m);
+      ctx->launches++;
+      PLFEM_CUDA(cudaStreamSynchronize(st));
+      if (!done) throw StatusError(PLFEM_ERR_NO_CONVERGENCE, "block Lanczos: " + std::to_string(nconv) + " of " + std::to_string(k) + " eigenpairs converged after " + std::to_string(res.n_restart) + " restarts");
+      return;
+    }
+    if (!full) continue;
+    // ---- thick restart: keep the q best Ritz vectors (q = ncvp - P*t so that whole blocks fit again)
+    const int keep = k + std::min(nconv, (ncvp - k) / 2);
+    const int t = std::max(1, (ncvp - keep) / P);
+    q = ncvp - P * t;
+    std::vector<double> S((size_t)ncvp * q);
+    std::fill(Th.begin(), Th.end(), 0.0);
+    for (int i = 0; i < q; ++i) {
+      const int col = order[i];
+      std::copy(T.begin() + (size_t)col * ncvp, T.begin() + (size_t)(col + 1) * ncvp, S.begin() + (size_t)i * ncvp);
+      Th[(size_t)i * ncvp + i] = w[col];
+    }
+    PLFEM_CUDA(cudaMemcpyAsync(Sdev.p, S.data(), S.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    const int nxt = cur ^ 1;
+    rotate_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(V[cur].p, ld, ncvp, Sdev.p, q, m, V[nxt].p, ld);
+    rotate_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(BV[cur].p, ld, ncvp, Sdev.p, q, m, BV[nxt].p, ld);
+    PLFEM_CUDA(cudaMemcpyAsync(V[nxt].p + (int64_t)q * ld, V[cur].p + (int64_t)ncvp * ld, (size_t)m * P * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    PLFEM_CUDA(cudaMemcpyAsync(BV[nxt].p + (int64_t)q * ld, BV[cur].p + (int64_t)ncvp * ld, (size_t)m * P * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    ctx->launches += 2;
+    PLFEM_CUDA(cudaStreamSynchronize(st));   // S is a local host buffer
+    cur = nxt; nb = q + P;
     res.n_restart++;
   }
 }

@@ -275,10 +275,15 @@ __global__ void __launch_bounds__(256) gemm_schur_kernel(const int4* __restrict_
 // factor entries the thread will multiply — is loaded BEFORE the item waits for its dependencies, so the
 // critical path of a step is: see the flag, one gather of the freshly written values, FMAs from registers,
 // write, signal.
+template <int NR>
 struct SweepSmem {
-  double y1[MAX_PIV];
-  double yt[128];
-  double part[8][32];
+  double y1[NR][MAX_PIV];
+  double yt[NR][128];
+  double part[NR][8][32];
+};
+
+struct RhsView {   // NR right-hand sides stored as columns: rhs + r*ldr, out + r*ldo, update pool + r*ldu
+  const double* rhs; int64_t ldr; double* out; int64_t ldo; double* upd; int64_t ldu;
 };
 
 // CG = true: values produced by other CTAs of the SAME launch (dataflow kernel) are read with ld.global.cg,
@@ -303,9 +308,9 @@ constexpr int BQ = 8;   // factor entries per lane preloaded before the wait (ba
 
 // forward: one CTA (8 warps) per (front, slab of 32*G rows).  The 8 warps form G row groups x 8/G slices of
 // the k range (the 2s pivot columns); partial sums meet in shared memory.
-template <bool CG>
+template <bool CG, int NR>
 __device__ __forceinline__ void forward_item(const FwdItem& it, const int32_t* __restrict__ gsrc, const PlanView& P,
-                                             const double* rhs, double* z, double* upd, SweepSmem& sm, const Deps& dp) {
+                                             const RhsView& rv, SweepSmem<NR>& sm, const Deps& dp) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int s2 = it.s2, nrows = it.nrows, row0 = it.row0, G = it.G, nf2 = it.ld;
   const int64_t ld = it.ld;
@@ -335,17 +340,21 @@ __device__ __forceinline__ void forward_item(const FwdItem& it, const int32_t* _
     __syncthreads();
   }
   // ---- dynamic part: right-hand side + children's updates, fixed order (rhs + first child) + second child
-  if (tid < s2) {
-    double v = ldx<CG>(rhs + it.g0 + tid);
-    if (i1 >= 0) v += ldx<CG>(upd + i1);
-    if (i2 >= 0) v += ldx<CG>(upd + i2);
-    sm.y1[tid] = v;
-  }
-  if (tid >= 128) {
-    double v = 0.0;
-    if (j1 >= 0) v += ldx<CG>(upd + j1);
-    if (j2 >= 0) v += ldx<CG>(upd + j2);
-    sm.yt[tid - 128] = v;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const double* up = rv.upd + r * rv.ldu;
+    if (tid < s2) {
+      double v = ldx<CG>(rv.rhs + r * rv.ldr + it.g0 + tid);
+      if (i1 >= 0) v += ldx<CG>(up + i1);
+      if (i2 >= 0) v += ldx<CG>(up + i2);
+      sm.y1[r][tid] = v;
+    }
+    if (tid >= 128) {
+      double v = 0.0;
+      if (j1 >= 0) v += ldx<CG>(up + j1);
+      if (j2 >= 0) v += ldx<CG>(up + j2);
+      sm.yt[r][tid - 128] = v;
+    }
   }
   __syncthreads();
   if (it.nchild > 2) {                       // rare (a separator that does not disconnect): generic path
@@ -353,41 +362,53 @@ __device__ __forceinline__ void forward_item(const FwdItem& it, const int32_t* _
       const int ch = P.child[q];
       const int uc2 = 2 * front_u(P, ch);
       const int32_t* cm = P.cmap + P.cmap_ptr[ch];
-      const double* uv = upd + P.uoff[ch];
-      for (int k = tid; k < uc2; k += 256) {
-        const int t = 2 * cm[k >> 1] + (k & 1);
-        if (t < s2) sm.y1[t] += ldx<CG>(uv + k);
-        else if (t >= row0 && t < row0 + nrows) sm.yt[t - row0] += ldx<CG>(uv + k);
+      for (int r = 0; r < NR; ++r) {
+        const double* uv = rv.upd + r * rv.ldu + P.uoff[ch];
+        for (int k = tid; k < uc2; k += 256) {
+          const int t = 2 * cm[k >> 1] + (k & 1);
+          if (t < s2) sm.y1[r][t] += ldx<CG>(uv + k);
+          else if (t >= row0 && t < row0 + nrows) sm.yt[r][t - row0] += ldx<CG>(uv + k);
+        }
       }
       __syncthreads();
     }
   }
-  double acc = 0.0;
-  if (lr < nrows) {
-    double a0 = 0.0, a1 = 0.0;
+  double acc[NR];
 #pragma unroll
-    for (int q = 0; q < FQ; q += 2) {
+  for (int r = 0; r < NR; ++r) acc[r] = 0.0;
+  if (lr < nrows) {
+#pragma unroll
+    for (int q = 0; q < FQ; ++q) {
       const int k = ks + q * nks;
-      if (k < s2) a0 = fma(mreg[q], sm.y1[k], a0);
-      if (k + nks < s2) a1 = fma(mreg[q + 1], sm.y1[k + nks], a1);
+      if (k < s2) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) acc[r] = fma(mreg[q], sm.y1[r][k], acc[r]);
+      }
     }
-    for (int k = ks + FQ * nks; k < s2; k += nks) a0 = fma(M[(int64_t)k * ld], sm.y1[k], a0);
-    acc = a0 + a1;
+    for (int k = ks + FQ * nks; k < s2; k += nks) {
+      const double mv = M[(int64_t)k * ld];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) acc[r] = fma(mv, sm.y1[r][k], acc[r]);
+    }
   }
-  sm.part[warp][lane] = acc;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) sm.part[r][warp][lane] = acc[r];
   __syncthreads();
   if (ks == 0 && lr < nrows) {
-    double t = 0.0;
-    for (int q = 0; q < nks; ++q) t += sm.part[q * G + rg][lane];
     const int row = row0 + lr;
-    if (row < s2) z[it.g0 + row] = t;
-    else upd[it.uoff + (row - s2)] = sm.yt[lr] - t;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      double t = 0.0;
+      for (int q = 0; q < nks; ++q) t += sm.part[r][q * G + rg][lane];
+      if (row < s2) rv.out[r * rv.ldo + it.g0 + row] = t;
+      else rv.upd[r * rv.ldu + it.uoff + (row - s2)] = sm.yt[r][lr] - t;
+    }
   }
 }
 
 // backward: one warp per pivot column, 8 columns per CTA
-template <bool CG>
-__device__ __forceinline__ void backward_item(const BwdItem& it, const PlanView& P, double* x, const Deps& dp) {
+template <bool CG, int NR>
+__device__ __forceinline__ void backward_item(const BwdItem& it, const PlanView& P, double* x, int64_t ldx_, const Deps& dp) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u2 = it.u2;
   const bool active = warp < it.ncols;
@@ -410,30 +431,43 @@ __device__ __forceinline__ void backward_item(const BwdItem& it, const PlanView&
     __syncthreads();
   }
   if (!active) return;
-  double a0 = 0.0, a1 = 0.0;
+  double a[NR];
 #pragma unroll
-  for (int q = 0; q < BQ; q += 2) {
-    if (xo[q] >= 0) a0 = fma(wreg[q], ldx<CG>(x + xo[q]), a0);
-    if (xo[q + 1] >= 0) a1 = fma(wreg[q + 1], ldx<CG>(x + xo[q + 1]), a1);
+  for (int r = 0; r < NR; ++r) a[r] = 0.0;
+#pragma unroll
+  for (int q = 0; q < BQ; ++q) {
+    if (xo[q] >= 0) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) a[r] = fma(wreg[q], ldx<CG>(x + r * ldx_ + xo[q]), a[r]);
+    }
   }
-  for (int j = lane + 32 * BQ; j < u2; j += 32) a0 = fma(wc[j], ldx<CG>(x + 2 * (int64_t)st[j >> 1] + (j & 1)), a0);
-  double a = a0 + a1;
+  for (int j = lane + 32 * BQ; j < u2; j += 32) {
+    const double wv = wc[j];
+    const int64_t o = 2 * (int64_t)st[j >> 1] + (j & 1);
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) a += __shfl_down_sync(0xffffffffu, a, off);
-  if (lane == 0) { double* xp = x + it.g0 + it.col0 + warp; *xp = ldx<CG>(xp) - a; }
+    for (int r = 0; r < NR; ++r) a[r] = fma(wv, ldx<CG>(x + r * ldx_ + o), a[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    double v = a[r];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if (lane == 0) { double* xp = x + r * ldx_ + it.g0 + it.col0 + warp; *xp = ldx<CG>(xp) - v; }
+  }
 }
 
+template <int NR>
 __global__ void __launch_bounds__(256) forward_kernel(const FwdItem* __restrict__ items, const int32_t* __restrict__ gsrc, PlanView P,
-                                                       const double* __restrict__ rhs, double* __restrict__ z,
-                                                       double* __restrict__ upd) {
-  __shared__ SweepSmem sm;
+                                                       RhsView rv) {
+  __shared__ SweepSmem<NR> sm;
   const Deps none{nullptr, nullptr, nullptr, 0, nullptr};
-  forward_item<false>(items[blockIdx.x], gsrc, P, rhs, z, upd, sm, none);
+  forward_item<false, NR>(items[blockIdx.x], gsrc, P, rv, sm, none);
 }
 
-__global__ void __launch_bounds__(256) backward_kernel(const BwdItem* __restrict__ items, PlanView P, double* __restrict__ x) {
+template <int NR>
+__global__ void __launch_bounds__(256) backward_kernel(const BwdItem* __restrict__ items, PlanView P, double* __restrict__ x, int64_t ldx_) {
   const Deps none{nullptr, nullptr, nullptr, 0, nullptr};
-  backward_item<false>(items[blockIdx.x], P, x, none);
+  backward_item<false, NR>(items[blockIdx.x], P, x, ldx_, none);
 }
 
 // ---- persistent operator kernel: x = refine((A - sigma B)^-1 b) in ONE cooperative launch ----------------
@@ -458,18 +492,19 @@ struct OpArgs {
   int32_t n; const int32_t* rowptr; const int32_t* col; const double* vals; int64_t nnz; double sigma;
 };
 
-__device__ __forceinline__ void sweep_dataflow(const OpArgs& a, const double* rhs, double* out, int epoch, SweepSmem& sm) {
+__device__ __forceinline__ void sweep_dataflow(const OpArgs& a, const double* rhs, double* out, int epoch, SweepSmem<1>& sm) {
   const Deps dp{a.fdone, a.bdone, a.status, epoch, a.nfs};
+  const RhsView rv{rhs, 0, out, 0, a.upd, 0};
   for (int i = blockIdx.x; i < a.n_fwd; i += gridDim.x) {
     const FwdItem it = a.fwd_q[i];
-    forward_item<true>(it, a.gsrc, a.P, rhs, out, a.upd, sm, dp);
+    forward_item<true, 1>(it, a.gsrc, a.P, rv, sm, dp);
     __threadfence();
     __syncthreads();                       // all writes of the item are fenced; shared memory is free again
     if (threadIdx.x == 0) atomicAdd(a.fdone + it.f, 1);
   }
   for (int i = blockIdx.x; i < a.n_bwd; i += gridDim.x) {
     const BwdItem it = a.bwd_q[i];
-    backward_item<true>(it, a.P, out, dp);
+    backward_item<true, 1>(it, a.P, out, 0, dp);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) atomicAdd(a.bdone + it.f, 1);
@@ -477,7 +512,7 @@ __device__ __forceinline__ void sweep_dataflow(const OpArgs& a, const double* rh
 }
 
 __global__ void __launch_bounds__(256) op_kernel(OpArgs a) {
-  __shared__ SweepSmem sm;
+  __shared__ SweepSmem<1> sm;
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   sweep_dataflow(a, a.b, a.x, a.epoch0 + 1, sm);
   for (int r = 0; r < a.refine; ++r) {
@@ -537,7 +572,7 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
   for (int f = 0; f < P.nfronts; ++f) uoff[f + 1] = uoff[f] + 2 * (P.sptr[f + 1] - P.sptr[f]);
   D.upd_len = uoff[P.nfronts];
   D.uoff.upload(ctx, uoff);
-  D.upd.alloc(ctx, std::max<int64_t>(D.upd_len, 1));
+  D.upd.alloc(ctx, (size_t)SOLVE_NRHS * std::max<int64_t>(D.upd_len, 1));
 
   std::vector<int4> wt, stl, ea;
   std::vector<FwdItem> fw; std::vector<BwdItem> bw;
@@ -667,22 +702,27 @@ void run_factorization(plfem_ctx* ctx, const DevPlan& D) {
   PLFEM_CUDA(cudaGetLastError());
 }
 
-void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double* z) {
+// nrhs right-hand sides (1 or 4) stored as columns with stride ld (ignored for nrhs = 1)
+void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double* z, int nrhs, int64_t ld) {
   const PlanView v = view(D);
+  if (nrhs != 1 && nrhs != SOLVE_NRHS) throw StatusError(PLFEM_ERR_INTERNAL, "unsupported number of right-hand sides");
+  const RhsView rv{b, ld, z, ld, D.upd.p, D.upd_len};
   for (int l = 0; l < D.nlevels; ++l) {
     const int nsl = D.fwd_ptr[l + 1] - D.fwd_ptr[l];
-    forward_kernel<<<nsl, 256, 0, ctx->stream>>>(D.fwd_items.p + D.fwd_ptr[l], D.gsrc.p, v, b, z, D.upd.p);
+    if (nrhs == 1) forward_kernel<1><<<nsl, 256, 0, ctx->stream>>>(D.fwd_items.p + D.fwd_ptr[l], D.gsrc.p, v, rv);
+    else forward_kernel<SOLVE_NRHS><<<nsl, 256, 0, ctx->stream>>>(D.fwd_items.p + D.fwd_ptr[l], D.gsrc.p, v, rv);
     ctx->launches++;
   }
   PLFEM_CUDA(cudaGetLastError());
 }
 
-void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x) {
+void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs, int64_t ld) {
   const PlanView v = view(D);
   for (int l = D.nlevels - 1; l >= 0; --l) {
     const int nsl = D.bwd_ptr[l + 1] - D.bwd_ptr[l];
     if (nsl == 0) continue;
-    backward_kernel<<<nsl, 256, 0, ctx->stream>>>(D.bwd_items.p + D.bwd_ptr[l], v, x);
+    if (nrhs == 1) backward_kernel<1><<<nsl, 256, 0, ctx->stream>>>(D.bwd_items.p + D.bwd_ptr[l], v, x, ld);
+    else backward_kernel<SOLVE_NRHS><<<nsl, 256, 0, ctx->stream>>>(D.bwd_items.p + D.bwd_ptr[l], v, x, ld);
     ctx->launches++;
   }
   PLFEM_CUDA(cudaGetLastError());
@@ -715,9 +755,9 @@ void run_operator(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const doubl
   ctx->launches++;
 }
 
-void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x) {
-  run_solve_forward(ctx, D, b, x);
-  run_solve_backward(ctx, D, x);
+void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x, int nrhs, int64_t ld) {
+  run_solve_forward(ctx, D, b, x, nrhs, ld);
+  run_solve_backward(ctx, D, x, nrhs, ld);
 }
 
 }  // namespace plfem

@@ -33,6 +33,6 @@ print("nmodes", len(modes), len(rmodes))
 for m, r in list(zip(modes, rmodes))[:5]:
     v, rv = np.concatenate([m["Ex_dofs"], m["Ey_dofs"]]), np.concatenate([r["Ex_dofs"], r["Ey_dofs"]])
     print(m["n_eff"], r["n_eff"], "dot", abs(v @ rv), "conf", m["confinement"], r["confinement"], "div", m["div_ratio"], r["div_ratio"], m["polarization"], r["polarization"])
-for opts in (dict(refine=-1), dict(refine=2), dict(leaf_nodes=16), dict(leaf_nodes=48), dict(max_sn_nodes=32)):
+for opts in (dict(block=1), dict(block=4, ncv=48), dict(block=4, ncv=64), dict(block=4, ncv=96), dict(refine=-1), dict(refine=2), dict(leaf_nodes=16), dict(leaf_nodes=48)):
     modes2, raw2 = s.solve_vectorial_modes(mesh, nm, return_raw=True, **opts)
     print(opts, "dev", np.abs(raw2["beta_sq"] / rraw["beta_sq"] - 1).max(), json.dumps(raw2["stats"]), flush=True)

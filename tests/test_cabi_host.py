@@ -28,7 +28,7 @@ def test_struct_layouts_match_header():
     # sizes the C compiler produces for the header's structs (LP64)
     assert ctypes.sizeof(_cabi.MeshInfo) == 64
     assert ctypes.sizeof(_cabi.Material) == 64
-    assert ctypes.sizeof(_cabi.SolveOpts) == 56
+    assert ctypes.sizeof(_cabi.SolveOpts) == 64
     assert ctypes.sizeof(_cabi.SolveStats) == 88
 
 

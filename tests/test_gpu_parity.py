@@ -157,6 +157,37 @@ def test_modes_config1(cfg1):
     assert st["kernel_launches"] > 0
 
 
+def test_single_vector_and_block_lanczos_agree(small_case):
+    g, mesh = small_case
+    s = TrueVectorialMaxwellSolver(g)
+    a, ra = s.solve_vectorial_modes(mesh, 4, return_raw=True, block=1)      # ARPACK-like single-vector recurrence
+    b, rb = s.solve_vectorial_modes(mesh, 4, return_raw=True, block=4)      # default: 4 vectors per operator application
+    assert ra["stats"]["n_block_op"] == 0 and rb["stats"]["n_block_op"] > 0
+    assert rb["stats"]["n_block_op"] < ra["stats"]["n_op"]                  # fewer sequential operator applications
+    assert np.abs(ra["beta_sq"] / rb["beta_sq"] - 1).max() < 1e-12
+    assert len(a) == len(b)
+
+
+def test_persistent_operator_kernel_matches_per_level_kernels(small_case):
+    """`plfem_debug_solve`: the cooperative dataflow kernel and the per-level kernels give the same solution,
+    and both agree with SuperLU after one refinement step."""
+    from scipy.sparse.linalg import splu
+    from plfem_b200.solver_fem import sigma_estimate
+    g, mesh = small_case
+    s = O.interior_system(g, mesh)
+    sigma = sigma_estimate(g)
+    K = (s["A_int"] - sigma * s["B_int"]).tocsc()
+    pb = _cabi.Problem(mesh)
+    mat, keep = _cabi.material_struct(g)
+    pb.solve_modes(mat, sigma, 16)
+    b = s["B_int"] @ np.random.default_rng(2).standard_normal(K.shape[0])
+    xr = splu(K).solve(b)
+    x_coop, x_lvl = pb.debug_solve(sigma, b, 1), pb.debug_solve(sigma, b, 101)
+    assert np.linalg.norm(x_coop - xr) / np.linalg.norm(xr) < 1e-9
+    assert np.linalg.norm(x_lvl - xr) / np.linalg.norm(xr) < 1e-9
+    assert np.linalg.norm(x_coop - x_lvl) / np.linalg.norm(xr) < 1e-12
+
+
 def test_readme_surface(cfg1):
     g, mesh = cfg1
     modes = TrueVectorialMaxwellSolver(g, n_modes=10).solve()
