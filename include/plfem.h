@@ -147,8 +147,8 @@ int plfem_solve_modes(plfem_problem* pb, const plfem_material* mat, const plfem_
 /* ---- measurement hook for bench.py: per-kernel device times (CUDA events on the library's stream, L2
  * flushed before each repetition) and the algorithmic bytes of the same items; needs a prior solve.
  * index: 0 assembly (K1), 1 front load + factorisation, 2 forward sweep, 3 backward sweep,
- *        4 B product (SpMM, 2 right-hand sides), 5 K residual SpMV */
-#define PLFEM_NPROFILE 6
+ *        4 B product (SpMM, 2 right-hand sides), 5 K residual SpMV, 6 / 7 forward / backward sweep with 4 right-hand sides */
+#define PLFEM_NPROFILE 8
 int plfem_profile_kernels(plfem_problem* pb, const plfem_material* mat, double sigma, int repeat,
                           double* out_ms, double* out_bytes);
 

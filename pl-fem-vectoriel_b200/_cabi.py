@@ -260,7 +260,8 @@ class Problem:
         self._check(self.lib.plfem_debug_solve(self.handle, float(sigma), _ptr(b, p_f64), _ptr(x, p_f64), int(refine)))
         return x
 
-    PROFILE_ITEMS = ("assemble", "factorize", "forward_sweep", "backward_sweep", "spmm_B", "spmv_K_residual")
+    PROFILE_ITEMS = ("assemble", "factorize", "forward_sweep", "backward_sweep", "spmm_B", "spmv_K_residual",
+                     "forward_sweep_4rhs", "backward_sweep_4rhs")
 
     def profile_kernels(self, material: Material, sigma: float, repeat: int = 20) -> dict:
         """{item: (avg ms, algorithmic bytes)} measured with CUDA events on the library stream."""

@@ -612,6 +612,15 @@ int plfem_profile_kernels(plfem_problem* pb, const plfem_material* mat, double s
     out_bytes[4] = 12.0 * nnz + 4.0 * (n + 1) + 32.0 * n;           // values + columns + row pointers + x and y (2 comps)
     out_ms[5] = timed([&] { launch_resid_k(ctx, pb->dperm, pb->d_vals.p, sigma, x.p, b.p, t.p); });
     out_bytes[5] = (5 * 8.0 + 4.0) * nnz + 4.0 * (n + 1) + 48.0 * n;
+    {
+      DevBuf<double> b4, x4;
+      b4.alloc(ctx, (size_t)m * SOLVE_NRHS); x4.alloc(ctx, (size_t)m * SOLVE_NRHS);
+      for (int r = 0; r < SOLVE_NRHS; ++r) PLFEM_CUDA(cudaMemcpyAsync(b4.p + r * m, b.p, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      out_ms[6] = timed([&] { run_solve_forward(ctx, pb->dplan, b4.p, x4.p, SOLVE_NRHS, m); });
+      out_bytes[6] = out_bytes[2] + 16.0 * m * (SOLVE_NRHS - 1);
+      out_ms[7] = timed([&] { run_solve_backward(ctx, pb->dplan, x4.p, SOLVE_NRHS, m); });
+      out_bytes[7] = out_bytes[3] + 16.0 * m * (SOLVE_NRHS - 1);
+    }
   });
 }
 
