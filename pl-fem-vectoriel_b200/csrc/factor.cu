@@ -101,110 +101,83 @@ __global__ void __launch_bounds__(256) extend_add_kernel(const int4* __restrict_
   }
 }
 
-// ---- pivot block inverse: register-resident Gauss-Jordan with partial pivoting, one CTA per front --------
-// m <= MP unknowns, MP*8 threads: thread (i = tid % MP, jg = tid / MP) keeps row i, columns jg + 8c (c < MP/8)
-// of the working matrix in registers.  A step broadcasts the pivot column and the (scaled) pivot row through
-// double-buffered shared memory, so it costs two block barriers and MP/8 FMAs per thread, instead of the
-// three barriers and ~230 instructions per warp of a shared-memory-resident update.
-template <int MP>
-__global__ void __launch_bounds__(MP * 8) invert_kernel(const int32_t* __restrict__ fronts, PlanView P, int32_t* status) {
-  constexpr int NC = MP / 8;
-  constexpr int NW = MP / 32;                 // warps that hold one column
-  __shared__ double colk[2][MP];
-  __shared__ double rowK[2][MP];              // old row k (goes to row p)
-  __shared__ double rowP[2][MP];              // old row p (becomes the pivot row)
-  __shared__ double candv[2][NW];
-  __shared__ int candi[2][NW];
-  __shared__ int piv[MP];
-  __shared__ int dst[MP];
+// ---- pivot block inverse: Gauss-Jordan with partial pivoting in shared memory, one CTA per front ------
+// Thread layout: i = tid % MP (row), jg = tid / MP (column group), MP = m rounded up to 32/64/128, so the
+// rank-1 update of step k needs no integer division and touches shared memory conflict-free.
+__global__ void __launch_bounds__(1024) invert_kernel(const int32_t* __restrict__ fronts, PlanView P, int32_t* status) {
+  extern __shared__ double sm[];
   const int f = fronts[blockIdx.x];
   const int m = 2 * P.s[f];
   const int64_t ld = 2 * (int64_t)(P.s[f] + front_u(P, f));
   double* F = P.pool + P.foff[f];
-  const int tid = threadIdx.x;
-  const int i = tid % MP, jg = tid / MP;
-  const int lane = tid & 31;
-  double reg[NC];
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    const int j = jg + 8 * c;
-    reg[c] = (i < m && j < m) ? F[(int64_t)j * ld + i] : 0.0;
-  }
+  const int lds = m | 1;
+  double* a = sm;                 // m x m, column-major, leading dimension lds
+  double* colk = a + (size_t)lds * m;
+  double* rowk = colk + m;
+  __shared__ int piv[MAX_PIV];
+  __shared__ int src[MAX_PIV];
+  __shared__ int s_p;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int MP = (m <= 32) ? 32 : (m <= 64 ? 64 : 128);
+  const int i = tid & (MP - 1), jg = tid / MP, ng = nt / MP;
+  if (i < m)
+    for (int j = jg; j < m; j += ng) a[i + j * lds] = F[(int64_t)j * ld + i];
+  __syncthreads();
   for (int k = 0; k < m; ++k) {
-    const int par = k & 1;
-    const int kc = k >> 3, kg = k & 7;
-    // ---- phase 1: owners of column k publish it and search the pivot among rows >= k
-    if (jg == kg) {
-      double v = 0.0;
-#pragma unroll
-      for (int c = 0; c < NC; ++c) if (c == kc) v = reg[c];
-      if (i < m) colk[par][i] = v;
-      double best = (i >= k && i < m) ? fabs(v) : -1.0;       // NaN compares false everywhere: never selected
-      int bi = i;
-      if (!(best >= 0.0)) { best = -1.0; }
+    if (tid < 32) {
+      double best = -1.0; int bi = k;
+      for (int r = k + tid; r < m; r += 32) {
+        const double v = fabs(a[r + k * lds]);
+        if (v > best) { best = v; bi = r; }   // NaN never wins; an all-NaN column keeps bi = k
+      }
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) {
         const double ob = __shfl_down_sync(0xffffffffu, best, off);
         const int oi = __shfl_down_sync(0xffffffffu, bi, off);
         if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
       }
-      if (lane == 0) { candv[par][i / 32] = best; candi[par][i / 32] = bi; }
-    }
-    __syncthreads();
-    double best = candv[par][0]; int p = candi[par][0];
-#pragma unroll
-    for (int w = 1; w < NW; ++w) { const double ob = candv[par][w]; const int oi = candi[par][w]; if (ob > best || (ob == best && oi < p)) { best = ob; p = oi; } }
-    if (tid == 0) { piv[k] = p; if (!(best > 0.0) || !isfinite(best)) atomicExch(status, 1); }
-    if (!(best > 0.0)) p = k;                                   // keep indices valid; the status flag reports it
-    const double inv = 1.0 / colk[par][p];
-    // ---- phase 2: rows k and p publish themselves
-    if (i == k || i == p) {
-      double* dstrow = (i == k) ? rowK[par] : rowP[par];
-#pragma unroll
-      for (int c = 0; c < NC; ++c) { const int j = jg + 8 * c; if (j < m) dstrow[j] = reg[c]; }
-      if (p == k) {
-#pragma unroll
-        for (int c = 0; c < NC; ++c) { const int j = jg + 8 * c; if (j < m) rowP[par][j] = reg[c]; }
+      if (tid == 0) {
+        s_p = bi; piv[k] = bi;
+        if (!(best > 0.0) || !isfinite(best)) atomicExch(status, 1);
       }
     }
     __syncthreads();
-    // ---- phase 3: update from registers
+    const int p = s_p;
+    const double inv = 1.0 / a[p + k * lds];
+    // row swap k <-> p fused with the copies of the scaled pivot row (first m threads) and of the
+    // pivot column (last m threads)
+    if (tid < m) {
+      const int j = tid;
+      const double ak = a[k + j * lds], ap = a[p + j * lds];
+      rowk[j] = ap * inv;
+      if (p != k && j != k) a[p + j * lds] = ak;
+    }
+    if (tid >= nt - m) {
+      const int r = tid - (nt - m);
+      double v;
+      if (r == k) v = 0.0;                         // unused
+      else if (r == p) v = a[k + k * lds];         // row p now holds old row k
+      else v = a[r + k * lds];
+      colk[r] = v;
+    }
+    __syncthreads();
     if (i < m) {
+      const double ci = colk[i];
       if (i == k) {
-#pragma unroll
-        for (int c = 0; c < NC; ++c) { const int j = jg + 8 * c; if (j < m) reg[c] = (j == k) ? inv : rowP[par][j] * inv; }
+        for (int j = jg; j < m; j += ng) a[i + j * lds] = (j == k) ? inv : rowk[j];
       } else {
-        double ci;
-        if (i == p) {                                            // this row now holds old row k
-          ci = colk[par][k];
-#pragma unroll
-          for (int c = 0; c < NC; ++c) { const int j = jg + 8 * c; if (j < m) reg[c] = rowK[par][j]; }
-        } else {
-          ci = colk[par][i];
-        }
-        const double cs = ci * inv;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          const int j = jg + 8 * c;
-          if (j < m) reg[c] = (j == k) ? -cs : reg[c] - cs * rowP[par][j];
-        }
+        for (int j = jg; j < m; j += ng) a[i + j * lds] = (j == k) ? -ci * inv : a[i + j * lds] - ci * rowk[j];
       }
     }
+    __syncthreads();
   }
-  __syncthreads();
   if (tid == 0) {
-    // undo the row pivoting: A^-1 = G P, i.e. column j of the result is column src[j] of G; dst = src^-1
-    int src[MP];
     for (int j = 0; j < m; ++j) src[j] = j;
     for (int k = m - 1; k >= 0; --k) { const int t = src[k]; src[k] = src[piv[k]]; src[piv[k]] = t; }
-    for (int j = 0; j < m; ++j) dst[src[j]] = j;
   }
   __syncthreads();
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    const int j = jg + 8 * c;
-    if (i < m && j < m) F[(int64_t)dst[j] * ld + i] = reg[c];
-  }
+  if (i < m)
+    for (int j = jg; j < m; j += ng) F[(int64_t)j * ld + i] = a[i + src[j] * lds];
 }
 
 // ---- tiled FP64 GEMM used for W^T and the Schur update -------------------------------------------------
@@ -576,6 +549,8 @@ __global__ void __launch_bounds__(256) op_kernel(OpArgs a) {
   }
 }
 
+size_t invert_smem(int m) { return ((size_t)(m | 1) * m + 2 * (size_t)m) * sizeof(double); }
+
 PlanView view(const DevPlan& D) {
   PlanView v;
   v.first = D.first.p; v.s = D.s.p; v.sptr = D.sptr.p; v.strct = D.strct.p; v.cptr = D.cptr.p; v.child = D.child.p;
@@ -699,6 +674,11 @@ void launch_front_load(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const 
 }
 
 void run_factorization(plfem_ctx* ctx, const DevPlan& D) {
+  static bool attr_set[64] = {};
+  if (!(ctx->device < 64 && attr_set[ctx->device])) {
+    PLFEM_CUDA(cudaFuncSetAttribute(invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)invert_smem(MAX_PIV)));
+    if (ctx->device < 64) attr_set[ctx->device] = true;
+  }
   const PlanView v = view(D);
   for (int l = 0; l < D.nlevels; ++l) {
     const int nea = D.ea_ptr[l + 1] - D.ea_ptr[l];
@@ -707,9 +687,7 @@ void run_factorization(plfem_ctx* ctx, const DevPlan& D) {
       ctx->launches++;
     }
     const int nfl = D.lptr[l + 1] - D.lptr[l];
-    if (D.lmax_m[l] <= 32) invert_kernel<32><<<nfl, 256, 0, ctx->stream>>>(D.lfront.p + D.lptr[l], v, D.status.p);
-    else if (D.lmax_m[l] <= 64) invert_kernel<64><<<nfl, 512, 0, ctx->stream>>>(D.lfront.p + D.lptr[l], v, D.status.p);
-    else invert_kernel<128><<<nfl, 1024, 0, ctx->stream>>>(D.lfront.p + D.lptr[l], v, D.status.p);
+    invert_kernel<<<nfl, D.lmax_m[l] > 64 ? 1024 : 256, invert_smem(D.lmax_m[l]), ctx->stream>>>(D.lfront.p + D.lptr[l], v, D.status.p);
     ctx->launches++;
     const int nw = D.w_ptr[l + 1] - D.w_ptr[l];
     if (nw > 0) {
