@@ -162,7 +162,8 @@ def _compare_modes(g, mesh, n_modes, rtol_neff=1e-8, **opts):
         for key in ("confinement", "P_x", "P_y", "div_ratio"):          # traces over the cluster are rotation-invariant
             a, b = sum(mr[i][key] * (mr[i]["beta"] ** 2 if key == "div_ratio" else 1) for i in cl), \
                 sum(rr[i][key] * (rr[i]["beta"] ** 2 if key == "div_ratio" else 1) for i in cl)
-            assert abs(a - b) <= 5e-6 * max(abs(b), 1e-12), key
+            # both sides are Ritz vectors converged to tol = 1e-7 only: small projections carry that error
+            assert abs(a - b) <= 5e-6 * abs(b) + (1e-8 if key == "div_ratio" else 1e-9), key
         if len(cl) == 1:
             m, r = mr[cl[0]], rr[cl[0]]
             assert abs(m["PDL_dB"] - r["PDL_dB"]) < 1e-4 and m["polarization"] == r["polarization"]
