@@ -19,6 +19,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace plfem {
 
@@ -299,6 +300,12 @@ __device__ __forceinline__ void wait_count(const int32_t* ctr, int32_t target, i
   }
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-serialisation attribute may start
+// while its predecessor in the stream is still running; everything before griddep_wait() (the static
+// prefetch) overlaps the predecessor's tail, everything after it sees the predecessor's writes.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 struct Deps {          // dataflow bookkeeping of the persistent kernel (unused by the per-level kernels)
   int32_t* fdone; int32_t* bdone; int32_t* status; int epoch; const int32_t* nfs;
 };
@@ -308,7 +315,7 @@ constexpr int BQ = 8;   // factor entries per lane preloaded before the wait (ba
 
 // forward: one CTA (8 warps) per (front, slab of 32*G rows).  The 8 warps form G row groups x 8/G slices of
 // the k range (the 2s pivot columns); partial sums meet in shared memory.
-template <bool CG, int NR>
+template <bool CG, int NR, bool PDL = false>
 __device__ __forceinline__ void forward_item(const FwdItem& it, const int32_t* __restrict__ gsrc, const PlanView& P,
                                              const RhsView& rv, SweepSmem<NR>& sm, const Deps& dp) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -330,6 +337,7 @@ __device__ __forceinline__ void forward_item(const FwdItem& it, const int32_t* _
     const int k = ks + q * nks;
     mreg[q] = (lr < nrows && k < s2) ? M[(int64_t)k * ld] : 0.0;
   }
+  if (PDL) griddep_wait();                 // the previous level's kernel is complete and visible from here on
   // ---- wait for the children (dataflow mode)
   if (CG) {
     if (tid == 0) {
@@ -407,7 +415,7 @@ __device__ __forceinline__ void forward_item(const FwdItem& it, const int32_t* _
 }
 
 // backward: one warp per pivot column, 8 columns per CTA
-template <bool CG, int NR>
+template <bool CG, int NR, bool PDL = false>
 __device__ __forceinline__ void backward_item(const BwdItem& it, const PlanView& P, double* x, int64_t ldx_, const Deps& dp) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u2 = it.u2;
@@ -423,6 +431,7 @@ __device__ __forceinline__ void backward_item(const BwdItem& it, const PlanView&
     wreg[q] = ok ? wc[j] : 0.0;
     xo[q] = ok ? 2 * (int64_t)st[j >> 1] + (j & 1) : -1;
   }
+  if (PDL) griddep_wait();
   if (CG) {
     if (threadIdx.x == 0) {
       wait_count(dp.fdone + it.f, it.tgt_f * dp.epoch, dp.status);             // z of this front is complete
@@ -456,18 +465,20 @@ __device__ __forceinline__ void backward_item(const BwdItem& it, const PlanView&
   }
 }
 
-template <int NR>
+template <int NR, bool PDL>
 __global__ void __launch_bounds__(256) forward_kernel(const FwdItem* __restrict__ items, const int32_t* __restrict__ gsrc, PlanView P,
                                                        RhsView rv) {
   __shared__ SweepSmem<NR> sm;
+  if (PDL) griddep_launch_dependents();    // let the next level start its static prefetch
   const Deps none{nullptr, nullptr, nullptr, 0, nullptr};
-  forward_item<false, NR>(items[blockIdx.x], gsrc, P, rv, sm, none);
+  forward_item<false, NR, PDL>(items[blockIdx.x], gsrc, P, rv, sm, none);
 }
 
-template <int NR>
-__global__ void __launch_bounds__(256) backward_kernel(const BwdItem* __restrict__ items, PlanView P, double* __restrict__ x, int64_t ldx_) {
+template <int NR, bool PDL>
+__global__ void __launch_bounds__(256) backward_kernel(const BwdItem* __restrict__ items, PlanView P, double* x, int64_t ldx_) {
+  if (PDL) griddep_launch_dependents();
   const Deps none{nullptr, nullptr, nullptr, 0, nullptr};
-  backward_item<false, NR>(items[blockIdx.x], P, x, ldx_, none);
+  backward_item<false, NR, PDL>(items[blockIdx.x], P, x, ldx_, none);
 }
 
 // ---- persistent operator kernel: x = refine((A - sigma B)^-1 b) in ONE cooperative launch ----------------
@@ -703,30 +714,54 @@ void run_factorization(plfem_ctx* ctx, const DevPlan& D) {
   PLFEM_CUDA(cudaGetLastError());
 }
 
+bool use_pdl() {
+  static const bool on = [] { const char* e = std::getenv("PLFEM_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+template <class... KArgs, class... Args>
+void launch_sweep(void (*kernel)(KArgs...), bool pdl, int grid, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  PLFEM_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+}
+
 // nrhs right-hand sides (1 or 4) stored as columns with stride ld (ignored for nrhs = 1)
 void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double* z, int nrhs, int64_t ld) {
   const PlanView v = view(D);
   if (nrhs != 1 && nrhs != SOLVE_NRHS) throw StatusError(PLFEM_ERR_INTERNAL, "unsupported number of right-hand sides");
   const RhsView rv{b, ld, z, ld, D.upd.p, D.upd_len};
+  const bool pdl = use_pdl();
   for (int l = 0; l < D.nlevels; ++l) {
     const int nsl = D.fwd_ptr[l + 1] - D.fwd_ptr[l];
-    if (nrhs == 1) forward_kernel<1><<<nsl, 256, 0, ctx->stream>>>(D.fwd_items.p + D.fwd_ptr[l], D.gsrc.p, v, rv);
-    else forward_kernel<SOLVE_NRHS><<<nsl, 256, 0, ctx->stream>>>(D.fwd_items.p + D.fwd_ptr[l], D.gsrc.p, v, rv);
+    const FwdItem* items = D.fwd_items.p + D.fwd_ptr[l];
+    const int32_t* gs = D.gsrc.p;
+    // the first level follows kernels that are not PDL-aware: plain launch
+    if (nrhs == 1) { if (pdl && l > 0) launch_sweep(forward_kernel<1, true>, true, nsl, ctx->stream, items, gs, v, rv); else launch_sweep(forward_kernel<1, false>, false, nsl, ctx->stream, items, gs, v, rv); }
+    else { if (pdl && l > 0) launch_sweep(forward_kernel<SOLVE_NRHS, true>, true, nsl, ctx->stream, items, gs, v, rv); else launch_sweep(forward_kernel<SOLVE_NRHS, false>, false, nsl, ctx->stream, items, gs, v, rv); }
     ctx->launches++;
   }
-  PLFEM_CUDA(cudaGetLastError());
 }
 
 void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs, int64_t ld) {
   const PlanView v = view(D);
+  const bool pdl = use_pdl();
+  bool first = true;
   for (int l = D.nlevels - 1; l >= 0; --l) {
     const int nsl = D.bwd_ptr[l + 1] - D.bwd_ptr[l];
     if (nsl == 0) continue;
-    if (nrhs == 1) backward_kernel<1><<<nsl, 256, 0, ctx->stream>>>(D.bwd_items.p + D.bwd_ptr[l], v, x, ld);
-    else backward_kernel<SOLVE_NRHS><<<nsl, 256, 0, ctx->stream>>>(D.bwd_items.p + D.bwd_ptr[l], v, x, ld);
+    const BwdItem* items = D.bwd_items.p + D.bwd_ptr[l];
+    // the first backward level follows the last forward kernel, which is PDL-aware only if it was launched so
+    const bool p = pdl && !(first && D.nlevels == 1);
+    if (nrhs == 1) { if (p) launch_sweep(backward_kernel<1, true>, true, nsl, ctx->stream, items, v, x, ld); else launch_sweep(backward_kernel<1, false>, false, nsl, ctx->stream, items, v, x, ld); }
+    else { if (p) launch_sweep(backward_kernel<SOLVE_NRHS, true>, true, nsl, ctx->stream, items, v, x, ld); else launch_sweep(backward_kernel<SOLVE_NRHS, false>, false, nsl, ctx->stream, items, v, x, ld); }
+    first = false;
     ctx->launches++;
   }
-  PLFEM_CUDA(cudaGetLastError());
 }
 
 int op_grid_size(plfem_ctx* ctx, int ctas_per_sm) {
