@@ -3,12 +3,15 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg1|cfg2]
 
-A *step* is one batch of ``--inflight`` (default 8) independent modal solves of the workload's
-cross-section, in flight together on one GPU (one host thread + CUDA stream each, the sweep's
-production mode); a modal solve is `solve_vectorial_modes`: DOF tables -> assembly -> Dirichlet
-elimination -> ordering + factorisation of A - sigma*B -> eigensolve -> per-mode reductions.  The mesh
-is given (built on the host before timing, as in the reference where `MeshGenerator` runs first).
-``latency`` in the JSON line is the same solve run alone (inflight = 1).
+A *step* is one FOREST of ``--inflight`` (default 8) independent modal solves of the workload's
+cross-section: the designs are solved together as one block-diagonal problem by one C-ABI call
+(`plfem_solve_modes_batch`), sharing every kernel launch — the sweep's production mode.  A modal
+solve is `solve_vectorial_modes`: DOF tables -> assembly -> Dirichlet elimination -> ordering +
+factorisation of A - sigma*B -> eigensolve -> per-mode reductions, all of it done per design (nothing
+is reused between the designs of a forest).  ``--workers`` (default 2) host threads each drive their
+own forest, so the host-side symbolic analysis of one forest overlaps the device work of another.
+The mesh is given (built on the host before timing, as in the reference where `MeshGenerator` runs
+first).  ``latency`` in the JSON line is one solve run alone.
 
 * ``value``  : solves/s with the mesh and its DOF tables already resident in HBM
                (`plfem_solve_modes` on an existing problem, symbolic analysis NOT reused,
@@ -22,7 +25,7 @@ is given (built on the host before timing, as in the reference where `MeshGenera
 * ``--impl reference`` : the CPU path (oracle port: NumPy restatement of scikit-fem + the real SciPy
                eigsh/SuperLU) on the host cores, one design per worker process.
 
-L2 is flushed (512 MiB write) before every timed step; steps are timed individually and summed.
+A forest's working set (GBs of front pools) exceeds the 126 MB L2; L2 is also flushed before the timed region.
 """
 from __future__ import annotations
 
@@ -161,8 +164,9 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from plfem_b200 import _cabi
+    from plfem_b200.batch import ForestPool
     from plfem_b200.solver_fem import TrueVectorialMaxwellSolver, sigma_estimate
-    from plfem_b200.sweep import design_record, gather_records, N_RECORD
+    from plfem_b200.sweep import gather_records, N_RECORD
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -182,7 +186,6 @@ def run_ours(args):
 
     w, g, mesh = make_case(args.workload)
     n_modes = w["n_modes"]
-    ctx = _cabi.Context.get(local)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=f"cuda:{local}")
 
     def sync_all():
@@ -195,48 +198,43 @@ def run_ours(args):
         flush.fill_(1)
         torch.cuda.synchronize(local)
 
-    # ---- value: mesh + DOF tables resident, everything else inside ----------------------------------
-    from plfem_b200.batch import SolverPool
+    # ---- value: a step = ONE forest of B designs; mesh + DOF tables resident, everything else inside ------
     B = max(1, args.inflight)
-    pool = SolverPool(device=local, workers=B)
+    pool = ForestPool(device=local, batch=B, workers=max(1, args.workers), want_vectors=False)
     sigma = sigma_estimate(g)
     mat, keep = _cabi.material_struct(g)
-
-    by_ctx = {}                                            # one resident problem per worker context
+    by_ctx = {}                                            # B resident problems per worker context
 
     def resident(c):
         if id(c) not in by_ctx:
-            by_ctx[id(c)] = _cabi.Problem(mesh, c)         # created during warm-up, outside the timed region
+            by_ctx[id(c)] = [_cabi.Problem(mesh, c) for _ in range(B)]   # created during warm-up, outside the timed region
         return by_ctx[id(c)]
 
-    pb = resident(ctx)
-    k = min(n_modes + 12, 2 * pb.n_interior - 4)
+    def forest_resident(_pool, c, _):
+        pbs = resident(c)
+        kk = min(n_modes + 12, 2 * pbs[0].n_interior - 4)
+        return _cabi.solve_modes_batch(c, pbs, [mat] * B, [sigma] * B, [kk] * B, tol=1e-7, maxiter=12000, want_vectors=False,
+                                       reuse_symbolic=False)
 
-    def solve_resident(c, _):
-        return resident(c).solve_modes(mat, sigma, k, tol=1e-7, maxiter=12000, want_vectors=False, reuse_symbolic=False)
-
-    def step_value():
-        return pool.map(solve_resident, range(B))
-
-    for _ in range(args.warmup + 2):                       # extra rounds so every worker thread owns a problem
-        step_value()
-    launches, phase = 0, {n: 0.0 for n in ("ms_symbolic", "ms_assemble", "ms_factor", "ms_lanczos", "ms_metrics", "ms_total")}
+    for _ in range(args.warmup):                           # every worker thread gets its context and problems
+        pool.on_every_worker(lambda p_, c: forest_resident(p_, c, 0))
+    launches, phase = 0, {n: 0.0 for n in ("ms_symbolic", "ms_symbolic_wall", "ms_assemble", "ms_factor", "ms_lanczos", "ms_metrics", "ms_total")}
     records = np.full((args.steps * B, N_RECORD), np.nan)
+    flush_l2()
     sync_all()
-    t_value = 0.0
     with ClockSampler(local) as clocks:
-        for i in range(args.steps):
-            flush_l2()
-            t0 = time.perf_counter()
-            outs = step_value()
-            torch.cuda.synchronize(local)
-            dt = time.perf_counter() - t0
-            t_value += dt
-            for j, (vals, _, met, ncore, st) in enumerate(outs):
-                launches += st.kernel_launches
-                for n in phase:
-                    phase[n] += getattr(st, n) / B
-                records[i * B + j, 0], records[i * B + j, 1], records[i * B + j, 3] = (rank * args.steps + i) * B + j, 1.0, dt
+        t0 = time.perf_counter()
+        outs = pool.map_forests(forest_resident, range(args.steps))      # K forests, pipelined over the worker threads
+        torch.cuda.synchronize(local)
+        t_value = time.perf_counter() - t0
+        for i, forest in enumerate(outs):
+            st = forest[0][4]
+            launches += st.kernel_launches
+            for n in phase:
+                phase[n] += getattr(st, n)
+            for j, f in enumerate(forest):
+                assert f[5] == 0, "a design failed"
+                records[i * B + j, 0], records[i * B + j, 1], records[i * B + j, 3] = (rank * args.steps + i) * B + j, 1.0, st.ms_total * 1e-3 / B
         if world > 1:          # the sweep's single collective, inside the timed region
             t0 = time.perf_counter()
             allrec = gather_records(records, world * args.steps * B, rank, world, local)
@@ -245,24 +243,25 @@ def run_ours(args):
             assert allrec.shape == (world * args.steps * B, N_RECORD)
     stats = st.as_dict()
 
-    # ---- e2e: public API, host buffers in, mode records out -----------------------------------------
-    def step_e2e():
-        return pool.solve_many([(g, mesh, n_modes)] * B)
+    # ---- e2e: public API, host buffers in, mode records (with eigenvectors) out -----------------------------
+    pool_e = ForestPool(device=local, batch=B, workers=max(1, args.workers), want_vectors=True)
+    jobs = [(g, mesh, n_modes)] * B
 
     for _ in range(args.warmup):
-        modes = step_e2e()[0]
+        pool_e.on_every_worker(lambda p_, c: p_.solve_forest(jobs))
+    flush_l2()
     sync_all()
-    t_e2e = 0.0
     with ClockSampler(local) as clocks2:
-        for i in range(args.steps):
-            flush_l2()
-            t0 = time.perf_counter()
-            modes = step_e2e()[0]
-            torch.cuda.synchronize(local)
-            t_e2e += time.perf_counter() - t0
+        t0 = time.perf_counter()
+        all_modes = pool_e.solve_many(jobs * args.steps)
+        torch.cuda.synchronize(local)
+        t_e2e = time.perf_counter() - t0
+    modes = all_modes[0]
+    pool_e.close()
 
     # ---- latency: one solve alone through the public API ---------------------------------------------
     lat = []
+    lat_stats = {}
     if rank == 0:
         _cabi.load().plfem_set_host_threads(0)
         for i in range(3 + min(args.steps, 10)):
@@ -274,7 +273,10 @@ def run_ours(args):
             s1.close()
             lat.append(time.perf_counter() - t0)
         lat = lat[3:]
-    n_solve = pb.n_interior
+    ctx0 = _cabi.Context.get(local)
+    pbs0 = [_cabi.Problem(mesh, ctx0) for _ in range(B)]
+    n_solve = pbs0[0].n_interior
+    k = min(n_modes + 12, 2 * n_solve - 4)
     h2d = B * (mesh.p.nbytes + mesh.t.astype(np.int64).nbytes + 8 * (3 * g.n_cores + 4))
     d2h = B * 8 * (k + k * 2 * n_solve + k * _cabi.NMETRICS)
 
@@ -292,23 +294,23 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- per-kernel roofline (CUDA events on the library's stream, L2 flushed per repetition) ----------
-    pb.solve_modes(mat, sigma, k, tol=1e-7, maxiter=12000, want_vectors=False)      # leaves plan + factors on the device
-    prof = pb.profile_kernels(mat, sigma, repeat=20)
-    nblk = stats.get("n_block_op", 0)
-    n_sweeps = (nblk if nblk else stats["n_op"]) * 2   # 1 refinement step -> 2 block-LDL^T solves per operator application
-    fkey, bkey = ("forward_sweep_4rhs", "backward_sweep_4rhs") if nblk else ("forward_sweep", "backward_sweep")
+    # ---- per-kernel roofline of a forest (CUDA events on the library's stream, L2 flushed per repetition) ----
+    fo = _cabi.solve_modes_batch(ctx0, pbs0, [mat] * B, [sigma] * B, [k] * B, want_vectors=False)   # leaves plan + factors on the device
+    fstats = fo[0][4].as_dict()
+    prof, nb_prof = ctx0.profile_last(repeat=10)
+    nblk = fstats["batch_block_ops"]
+    n_sweeps = nblk * 2        # 1 refinement step -> 2 block-LDL^T solves per operator application
+    fkey, bkey = "forward_sweep_4rhs", "backward_sweep_4rhs"
     share = {k_: 0.0 for k_ in prof}
     share.update({fkey: n_sweeps * prof[fkey][0], bkey: n_sweeps * prof[bkey][0], "factorize": prof["factorize"][0],
-                  "assemble": prof["assemble"][0], "spmm_B": stats["n_op"] * prof["spmm_B"][0] / (4 if nblk else 1),
-                  "spmv_K_residual": stats["n_op"] * prof["spmv_K_residual"][0] / (4 if nblk else 1)})
+                  "assemble": prof["assemble"][0], "spmm_B": nblk * prof["spmm_B"][0], "spmv_K_residual": nblk * prof["spmv_K_residual"][0]})
     dom = max(share, key=share.get)
     kernels = {}
     for name, (ms, nbytes) in prof.items():
         gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else None
         kernels[name] = {"ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak if gbs else None,
-                         "est_ms_per_solve": share[name]}
-    launches_per = stats["n_levels"] if "sweep" in dom else 1
+                         "est_ms_per_forest": share[name]}
+    launches_per = fstats["n_levels"] if "sweep" in dom else 1
     ms_dom, bytes_dom = prof[dom]
     roofline = {"kernel": {"forward_sweep": "forward_kernel<1>", "backward_sweep": "backward_kernel<1>", "forward_sweep_4rhs": "forward_kernel<4>",
                            "backward_sweep_4rhs": "backward_kernel<4>", "factorize": "invert_kernel+gemm",
@@ -316,33 +318,39 @@ def run_ours(args):
                 "bound": "hbm", "achieved": bytes_dom / (ms_dom * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": bytes_dom / (ms_dom * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
                 "per_launch": {"launches_per_sweep": launches_per, "avg_launch_us": 1e3 * ms_dom / launches_per,
-                               "algorithmic_bytes_per_launch": bytes_dom / launches_per},
-                "note": "factor panels of this workload fit the 126 MB L2 but L2 is flushed before each timed sweep; "
-                        "the sweeps are a chain of one launch per elimination-tree level, i.e. latency- not bandwidth-bound"}
+                               "algorithmic_bytes_per_launch": bytes_dom / launches_per, "designs_per_launch": nb_prof},
+                "note": "one sweep = one launch per elimination-tree level carrying the fronts of all designs of the forest; "
+                        "algorithmic bytes = factor entries of the left block columns (8 B each) + the right-hand sides; L2 flushed before each timed sweep"}
 
     cpu = cpu_baseline_sample(args.workload, 2) if world == 1 else None
     pool.close()
+    nst = args.steps
     line = {"metric": "modal_solves_per_sec", "value": world * B * args.steps / t_value, "unit": "solves/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_value / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["name"], "mesh": {"V": int(mesh.p.shape[1]), "T": int(mesh.t.shape[1]), "N_p2": int(pb.N),
+            "config": {"workload": w["name"], "mesh": {"V": int(mesh.p.shape[1]), "T": int(mesh.t.shape[1]), "N_p2": int(pbs0[0].N),
                                                        "dim": 2 * n_solve, "recipe": "reference point recipe, refinement 1.0, flat hull triangles dropped"},
-                       "step": f"{B} independent modal solves in flight on one GPU (one host thread + stream each)",
-                       "k": k, "lanczos": "thick-restart block Lanczos, 4 vectors per operator application, basis 3k", "tol": 1e-7, "start_vector": "ones (+3 fixed pseudo-random)", "refine_steps": 1,
-                       "l2": "flushed (512 MiB write) before every timed step", "timing": "per-step wall clock around the synchronous C-ABI call, "
-                       "cuda synchronize on both sides, summed over steps, max over ranks",
+                       "step": f"one forest of {B} independent modal solves (each with its own symbolic analysis, assembly, factorisation, "
+                               f"eigensolve and reductions) sharing every kernel launch; {pool.workers} host threads/contexts keep "
+                               f"{pool.workers} forests in flight so the host analysis of one overlaps the device work of the other",
+                       "k": k, "lanczos": "thick-restart block Lanczos, 4 vectors per operator application, basis 3k, designs in lockstep", "tol": 1e-7,
+                       "start_vector": "ones (+3 fixed pseudo-random)", "refine_steps": 1,
+                       "l2": f"inputs larger than L2: one forest streams {B * fstats['factor_entries'] * 8 / 1e6:.0f} MB of factor panels per sweep "
+                             f"(front pools {B * fstats['front_pool_doubles'] * 8 / 1e9:.2f} GB); L2 also flushed (512 MiB write) before the timed region",
+                       "timing": "wall clock around the K steps (forests) submitted to the worker threads, cuda synchronize + barrier on both sides, max over ranks",
                        "SimulationConfig": {"mesh_min_points": 0, "mesh_target_points": 0}},
             "clocks": clocks.summary(),
             "e2e": {"value": world * B * args.steps / t_e2e, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * t_e2e / args.steps, "n_modes_returned": len(modes), "clocks": clocks2.summary()},
+                    "ms_per_step": 1e3 * t_e2e / args.steps, "n_modes_returned": len(modes), "clocks": clocks2.summary(),
+                    "path": "ForestPool.solve_many on NumPy meshes: DOF tables + mesh upload, forest solve, eigenvectors + reductions copied back, mode records built"},
             "gpu_launches": int(launches),
             "latency": {"ms_per_solve_alone_e2e": 1e3 * statistics.mean(lat), "solves_per_s": 1.0 / statistics.mean(lat),
                         "phases_ms": {n: lat_stats[n] for n in ("ms_symbolic", "ms_assemble", "ms_factor", "ms_lanczos", "ms_metrics")}},
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "phases_ms_per_solve_in_batch": {n: v / args.steps for n, v in phase.items()},
+            "phases_ms_per_forest": {n: v / nst for n, v in phase.items()},
             "solver": {kk: stats[kk] for kk in ("nconv", "n_op", "n_block_op", "n_restart", "n_fronts", "n_levels", "max_front_nodes", "factor_entries",
-                                                "front_pool_doubles", "factor_flops", "max_residual")},
+                                                "front_pool_doubles", "factor_flops", "max_residual", "batch_size", "batch_block_ops")},
             "kernels": kernels}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -356,7 +364,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg1", choices=sorted(WORKLOADS))
-    ap.add_argument("--inflight", type=int, default=8, help="independent solves in flight per GPU and step")
+    ap.add_argument("--inflight", type=int, default=8, help="designs per forest (= per step)")
+    ap.add_argument("--workers", type=int, default=2, help="host threads / contexts, each working on its own forest")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     if args.impl == "reference":

@@ -132,6 +132,12 @@ typedef struct {
   float ms_symbolic, ms_assemble, ms_factor, ms_lanczos, ms_metrics, ms_total; /* host wall / CUDA events */
   int32_t kernel_launches;
   int32_t n_block_op;               /* sequential operator applications (= n_op / block size) */
+  /* forest (plfem_solve_modes_batch): ms_assemble .. ms_metrics, ms_total and kernel_launches are those of the WHOLE
+   * batch (the designs share every launch); ms_symbolic is this design's own host analysis */
+  int32_t batch_size;               /* designs solved together (1 for plfem_solve_modes) */
+  int32_t batch_block_ops;          /* lockstep operator applications of the batch */
+  float ms_symbolic_wall;           /* host wall time of the analysis of all designs (parallel threads) */
+  int32_t reserved;
 } plfem_solve_stats;
 
 /* Per-mode reductions of solver_fem.py:212-220, computed on the l2-normalised (vx, vy):
@@ -144,6 +150,19 @@ int plfem_solve_modes(plfem_problem* pb, const plfem_material* mat, const plfem_
                       int32_t* core_dof_count, /* number of interior DOFs inside a core (solver_fem.py:200-203) */
                       plfem_solve_stats* stats);
 
+/* ---- forest of designs: the sweep's production mode (dataset generation, README.md:226-243) -----------------
+ * nb independent (mesh, material, shift) designs are solved as ONE block-diagonal problem: their fronts share the
+ * level-batched factorisation and sweep launches and their block-Lanczos iterations advance in lockstep, so a batch
+ * costs about as many (latency-bound) launches as a single design.  Results per design are identical to
+ * plfem_solve_modes on that design alone.  All problems must have been created on `ctx`.  Array arguments have nb
+ * entries; evecs[b] may be NULL.  Returns PLFEM_OK when the batch ran; statuses[b] tells whether design b succeeded
+ * (a singular shift or non-convergence of one design does not affect the others), plfem_last_error() describes the
+ * first failed design.  opts[0].refine/.block and the largest ncv / maxiter apply to the whole batch. */
+int plfem_solve_modes_batch(plfem_ctx* ctx, int32_t nb, plfem_problem* const* pbs, const plfem_material* mats,
+                            const plfem_solve_opts* opts, double* const* eigvals, double* const* evecs,
+                            double* const* metrics, int32_t* core_dof_counts, plfem_solve_stats* stats,
+                            int32_t* statuses);
+
 /* ---- measurement hook for bench.py: per-kernel device times (CUDA events on the library's stream, L2
  * flushed before each repetition) and the algorithmic bytes of the same items; needs a prior solve.
  * index: 0 assembly (K1), 1 front load + factorisation, 2 forward sweep, 3 backward sweep,
@@ -151,6 +170,9 @@ int plfem_solve_modes(plfem_problem* pb, const plfem_material* mat, const plfem_
 #define PLFEM_NPROFILE 8
 int plfem_profile_kernels(plfem_problem* pb, const plfem_material* mat, double sigma, int repeat,
                           double* out_ms, double* out_bytes);
+/* the same on whatever the last solve of this context left on the device — a single design or a forest (every
+ * launch then carries all designs; *batch_size tells how many).  The problems of that solve must still exist. */
+int plfem_profile_last(plfem_ctx* ctx, int repeat, double* out_ms, double* out_bytes, int32_t* batch_size);
 
 /* ---- debug / test hooks (host logic checks that need no GPU) ----------------------------------- */
 /* sizes: [n, nfronts, nlevels, strct_len, cmap_len, nchild] */

@@ -28,7 +28,7 @@ SYMBOLS = ["plfem_ctx_create", "plfem_ctx_destroy", "plfem_last_error", "plfem_v
            "plfem_problem_create", "plfem_problem_destroy", "plfem_problem_info", "plfem_problem_dofs",
            "plfem_quad_points", "plfem_assemble", "plfem_export_csr", "plfem_spmv_csr", "plfem_solve_modes",
            "plfem_plan_sizes", "plfem_plan_export", "plfem_debug_symeig", "plfem_profile_kernels", "plfem_set_host_threads",
-           "plfem_debug_solve", "plfem_ctx_set_coop_ctas"]
+           "plfem_debug_solve", "plfem_ctx_set_coop_ctas", "plfem_solve_modes_batch", "plfem_profile_last"]
 
 
 class MeshInfo(C.Structure):
@@ -52,7 +52,8 @@ class SolveStats(C.Structure):
                 ("front_pool_doubles", c_i64), ("factor_flops", c_f64), ("max_residual", c_f64),
                 ("ms_symbolic", C.c_float), ("ms_assemble", C.c_float), ("ms_factor", C.c_float),
                 ("ms_lanczos", C.c_float), ("ms_metrics", C.c_float), ("ms_total", C.c_float),
-                ("kernel_launches", c_i32), ("n_block_op", c_i32)]
+                ("kernel_launches", c_i32), ("n_block_op", c_i32), ("batch_size", c_i32), ("batch_block_ops", c_i32),
+                ("ms_symbolic_wall", C.c_float), ("reserved", c_i32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -97,6 +98,9 @@ def load():
                                        C.POINTER(C.c_float)]
         lib.plfem_solve_modes.argtypes = [vp, C.POINTER(Material), C.POINTER(SolveOpts), p_f64, p_f64, p_f64,
                                           p_i32, C.POINTER(SolveStats)]
+        lib.plfem_solve_modes_batch.argtypes = [vp, c_i32, C.POINTER(vp), C.POINTER(Material), C.POINTER(SolveOpts),
+                                                C.POINTER(p_f64), C.POINTER(p_f64), C.POINTER(p_f64), p_i32,
+                                                C.POINTER(SolveStats), p_i32]
         lib.plfem_plan_sizes.argtypes = [vp, c_i32, c_i32, p_i64]
         lib.plfem_plan_export.argtypes = [vp] + [p_i32] * 9 + [p_i64]
         lib.plfem_debug_symeig.argtypes = [c_i32, p_f64, p_f64]
@@ -106,6 +110,7 @@ def load():
         lib.plfem_set_host_threads.argtypes = [C.c_int]
         lib.plfem_set_host_threads.restype = None
         lib.plfem_profile_kernels.argtypes = [vp, C.POINTER(Material), c_f64, C.c_int, p_f64, p_f64]
+        lib.plfem_profile_last.argtypes = [vp, C.c_int, p_f64, p_f64, p_i32]
         _lib = lib
         return lib
 
@@ -139,6 +144,13 @@ class Context:
     def check(self, st: int):
         if st != 0:
             raise PlfemError(st, self.lib.plfem_last_error(self.handle).decode(errors="replace"))
+
+    def profile_last(self, repeat: int = 20):
+        """({item: (avg ms, algorithmic bytes)}, batch size) of the device state the last solve on this context left
+        (a single design or a forest), measured with CUDA events on the library stream, L2 flushed per repetition."""
+        ms = np.zeros(len(Problem.PROFILE_ITEMS)); nbytes = np.zeros(len(Problem.PROFILE_ITEMS)); nb = c_i32()
+        self.check(self.lib.plfem_profile_last(self.handle, int(repeat), _ptr(ms, p_f64), _ptr(nbytes, p_f64), C.byref(nb)))
+        return {k: (float(a), float(b)) for k, a, b in zip(Problem.PROFILE_ITEMS, ms, nbytes)}, nb.value
 
     def spmv_csr(self, M, x, repeat: int = 1):
         """y = M @ x on the device for a SciPy CSR matrix; returns (y, avg ms per launch)."""
@@ -296,6 +308,42 @@ class Problem:
             self.close()
         except Exception:
             pass
+
+
+def solve_modes_batch(ctx: "Context", problems, materials, sigmas, ks, tol: float = 1e-7, maxiter: int = 12000,
+                      want_vectors: bool = True, ncv: int = 0, refine: int = 0, reuse_symbolic: bool = False,
+                      leaf_nodes: int = 0, max_sn_nodes: int = 0):
+    """Forest solve (``plfem_solve_modes_batch``): the designs share every kernel launch.
+
+    Returns one ``(eigvals, evecs | None, metrics, n_core_dofs, stats, status)`` per design; ``status`` is 0 or the
+    ``plfem_status`` of that design alone (the other designs are unaffected)."""
+    nb = len(problems)
+    if not (nb == len(materials) == len(sigmas) == len(ks)) or nb == 0:
+        raise ValueError("problems, materials, sigmas and ks must have the same non-zero length")
+    lib = ctx.lib
+    mats = (Material * nb)(*materials)
+    opts = (SolveOpts * nb)()
+    for b in range(nb):
+        opts[b] = SolveOpts(sigma=float(sigmas[b]), k=int(ks[b]), ncv=int(ncv), tol=float(tol), maxiter=int(maxiter),
+                            leaf_nodes=int(leaf_nodes), max_sn_nodes=int(max_sn_nodes),
+                            reuse_symbolic=int(bool(reuse_symbolic)), refine=int(refine), block=0)
+    vals = [np.empty(int(k)) for k in ks]
+    vecs = [np.empty((int(k), 2 * pb.n_interior)) if want_vectors else None for k, pb in zip(ks, problems)]
+    mets = [np.empty((int(k), NMETRICS)) for k in ks]
+    ncore = np.zeros(nb, dtype=np.int32)
+    status = np.zeros(nb, dtype=np.int32)
+    stats = (SolveStats * nb)()
+    handles = (C.c_void_p * nb)(*[pb.handle for pb in problems])
+    pv = (p_f64 * nb)(*[_ptr(a, p_f64) for a in vals])
+    pe = (p_f64 * nb)(*[_ptr(a, p_f64) for a in vecs])
+    pm = (p_f64 * nb)(*[_ptr(a, p_f64) for a in mets])
+    ctx.check(lib.plfem_solve_modes_batch(ctx.handle, nb, handles, mats, opts, pv, pe, pm, _ptr(ncore, p_i32), stats,
+                                          _ptr(status, p_i32)))
+    out = []
+    for b in range(nb):
+        st = SolveStats.from_buffer_copy(stats[b])
+        out.append((vals[b], vecs[b], mets[b], int(ncore[b]), st, int(status[b])))
+    return out
 
 
 def symeig(a: np.ndarray):

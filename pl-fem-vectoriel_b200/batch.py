@@ -1,12 +1,21 @@
-"""Throughput mode: several modal solves in flight on one GPU.
+"""Throughput mode: many modal solves per GPU (the dataset sweep of `README.md:226-243`).
 
-One 7-core cross-section is ~45k unknowns: its kernels are small grids chained level by level, so a
-single solve leaves most of a B200 idle and alternates with host-side symbolic analysis.  A
-``SolverPool`` keeps ``workers`` host threads, each with its own C-ABI context (own CUDA stream and
-device-memory arena); ctypes releases the GIL inside the library, so the symbolic analysis of one
-design overlaps the factorisation and Lanczos sweeps of the others, and kernels from different
-streams share the SMs.  Results are identical to one-at-a-time solves (every solve is deterministic
-and independent).
+One 7-core cross-section is ~45k unknowns: its kernels are small grids chained level by level
+(~2000 dependent launches per solve), so a single solve leaves most of a B200 idle.  Two ways to
+fill it:
+
+``ForestPool`` (production mode)
+    Designs are grouped into *forests* of ``batch`` designs.  A forest is solved by ONE C-ABI call
+    (``plfem_solve_modes_batch``) as one block-diagonal problem: the elimination trees of its designs
+    share the level-batched factorisation and sweep launches and their block-Lanczos iterations
+    advance in lockstep, so a forest costs about as many launches as one design.  ``workers``
+    host threads (default 2), each with its own context (CUDA stream + device arena), work on
+    different forests, so the host-side symbolic analysis of one forest overlaps the device work of
+    another.  Results are identical to one-at-a-time solves.
+
+``SolverPool``
+    One design per host thread and stream (no lockstep): kept for latency-oriented callers that
+    want each result as soon as it is ready.
 """
 from __future__ import annotations
 
@@ -16,7 +25,94 @@ from concurrent.futures import ThreadPoolExecutor
 from typing import Callable, List, Sequence
 
 from . import _cabi
-from .solver_fem import TrueVectorialMaxwellSolver
+from .solver_fem import TrueVectorialMaxwellSolver, modes_from_solution, sigma_estimate
+
+
+class ForestPool:
+    """``solve_many(jobs)`` with jobs = ``(geometry, mesh, n_modes_target)`` -> list of mode lists."""
+
+    def __init__(self, device: int = 0, batch: int = 8, workers: int = 2, want_vectors: bool = True):
+        self.device, self.batch, self.workers = int(device), max(1, int(batch)), max(1, int(workers))
+        self.want_vectors = want_vectors
+        _cabi.load()
+        self._local = threading.local()
+        self._pool = ThreadPoolExecutor(max_workers=self.workers, thread_name_prefix="plfem-forest")
+        self._build = ThreadPoolExecutor(max_workers=min(self.batch, os.cpu_count() or 1), thread_name_prefix="plfem-dof")
+        self.last_stats: List[dict] = []
+
+    def _ctx(self):
+        if not hasattr(self._local, "ctx"):
+            self._local.ctx = _cabi.Context(self.device)     # a fresh context: own stream + arena
+        return self._local.ctx
+
+    # -- one forest ---------------------------------------------------------------------------------
+    def solve_forest(self, jobs: Sequence[tuple], problems=None, return_raw: bool = False):
+        """Solve ``jobs`` as ONE forest on the calling thread's context.  ``problems`` (optional) are resident
+        ``_cabi.Problem`` objects of that context for the jobs' meshes; otherwise they are created (DOF tables on
+        host threads, mesh upload) and released here."""
+        ctx = self._ctx()
+        own = problems is None
+        if own:
+            problems = list(self._build.map(lambda j: _cabi.Problem(j[1], ctx), jobs))
+        try:
+            mats, keep, sigmas, ks = [], [], [], []
+            for (geo, mesh, n_modes), pb in zip(jobs, problems):
+                m, k_ = TrueVectorialMaxwellSolver(geo, device=self.device, ctx=ctx)._material(pb)
+                mats.append(m); keep.append(k_)
+                sigmas.append(sigma_estimate(geo))
+                ks.append(min(n_modes + 12, 2 * pb.n_interior - 4))
+            res = _cabi.solve_modes_batch(ctx, problems, mats, sigmas, ks, tol=1e-7, maxiter=12000,
+                                          want_vectors=self.want_vectors)
+            out, stats = [], []
+            for (geo, mesh, n_modes), pb, (vals, vecs, met, ncore, st, status) in zip(jobs, problems, res):
+                stats.append(st.as_dict())
+                if status != 0:
+                    out.append(_cabi.PlfemError(status, "design failed inside a forest"))
+                    continue
+                guided, raw, frac = modes_from_solution(geo, pb.n_interior, vals, vecs, met, ncore)
+                out.append((guided, dict(beta_sq=vals, evecs=vecs, metrics=met, modes_raw=raw, frac_core=frac,
+                                         stats=stats[-1])) if return_raw else guided)
+            self.last_stats = stats
+            return out
+        finally:
+            if own:
+                for pb in problems:
+                    pb.close()
+
+    # -- many forests, pipelined over the worker threads -------------------------------------------------
+    def solve_many(self, jobs: Sequence[tuple]) -> List[list]:
+        """Mode lists in job order.  A design that fails inside its forest raises here (after all forests ran)."""
+        chunks = [jobs[i:i + self.batch] for i in range(0, len(jobs), self.batch)]
+        out: List[list] = []
+        for part in self._pool.map(self.solve_forest, chunks):
+            out.extend(part)
+        for r in out:
+            if isinstance(r, Exception):
+                raise r
+        return out
+
+    def map_forests(self, fn: Callable, items: Sequence):
+        """Run ``fn(pool, ctx, item)`` on the worker threads (bench hook: resident problems per context)."""
+        return list(self._pool.map(lambda it: fn(self, self._ctx(), it), items))
+
+    def on_every_worker(self, fn: Callable):
+        """Run ``fn(pool, ctx)`` once on EACH worker thread (warm-up: contexts, resident problems)."""
+        gate = threading.Barrier(self.workers)
+
+        def one(_):
+            gate.wait()                                   # every task is held until all threads have taken one
+            return fn(self, self._ctx())
+        return list(self._pool.map(one, range(self.workers)))
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+        self._build.shutdown(wait=True)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
 
 class SolverPool:

@@ -3,7 +3,11 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <atomic>
+#include <exception>
 #include <memory>
+#include <mutex>
+#include <thread>
 
 #include "common.h"
 
@@ -23,6 +27,7 @@ static size_t size_class(size_t bytes) {
 }
 
 void* DeviceArena::alloc(size_t bytes) {
+  std::lock_guard<std::mutex> g(mu_);
   const size_t c = size_class(bytes);
   auto it = free_.find(c);
   void* p = nullptr;
@@ -45,6 +50,7 @@ void* DeviceArena::alloc(size_t bytes) {
 }
 
 void DeviceArena::release(void* p) {
+  std::lock_guard<std::mutex> g(mu_);
   auto it = live_.find(p);
   if (it == live_.end()) return;
   free_.emplace(it->second, p);
@@ -70,6 +76,32 @@ void* plfem_ctx::pin(size_t bytes) {
   return pinned;
 }
 
+namespace plfem {
+// ---- device state of one solve: a single design, or a forest of designs as one block-diagonal problem ------
+struct SolveWork {
+  BatchDims bd;
+  std::vector<int64_t> nnz_off;
+  std::vector<int32_t> front_off;
+  FrontPlan plan;                              // merged front plan
+  Pattern pat;                                 // merged pattern, permuted interior nodes
+  DevPattern dpat;
+  DevPlan dplan;
+  DevBuf<double> d_vals;                       // NV_SOLVE x nnz
+  DevBuf<double> d_sigma;                      // shift of the design each permuted node belongs to
+  DevBuf<int32_t> d_perm;                      // new id -> interior index (local to its design)
+  DevBuf<uint8_t> d_in_core;
+  bool ready = false;
+  int plan_serial = -1;                        // single design: the plan generation these copies were made from
+  // what the measurement hook needs to re-run the assembly of each design (device pointers owned by the problems,
+  // which must outlive the hook call)
+  struct AsmArgs {
+    const double* d_p; const int32_t* d_edofs; const int32_t* d_n2e_ptr; const int32_t* d_n2e; double* d_elem;
+    const double* d_cores; int64_t V, T; plfem_material mat;
+  };
+  std::vector<AsmArgs> asm_args;
+};
+}  // namespace plfem
+
 // ---- problem ------------------------------------------------------------------------------------------
 struct plfem_problem {
   plfem_ctx* ctx = nullptr;
@@ -83,14 +115,12 @@ struct plfem_problem {
   DevBuf<double> d_full_vals; DevBuf<uint32_t> d_full_flags;
   std::vector<double> h_full_vals; std::vector<uint32_t> h_full_flags; bool assembled = false;
   plfem_material last_mat{};
-  // interior solve path
+  // interior solve path (host side; the device side of a solve lives in a SolveWork)
   Pattern adj;  bool adj_ready = false;        // interior nodes, interior-index numbering (for dissection)
   FrontPlan plan; bool plan_ready = false; SymbolicOptions plan_opt;
-  Pattern perm_pat; DevPattern dperm;
-  DevPlan dplan;
-  DevBuf<double> d_vals;                       // NV_SOLVE x nnz
-  DevBuf<int32_t> d_perm;                      // new id -> interior index
-  DevBuf<uint8_t> d_in_core;
+  Pattern perm_pat; bool perm_pat_ready = false;
+  std::shared_ptr<SolveWork> work;             // device state of the last single-design solve (profile / debug hooks, reuse)
+  int plan_serial = 0;                         // bumped whenever the front plan is rebuilt
 };
 
 namespace {
@@ -178,7 +208,8 @@ bool ensure_plan(plfem_problem* pb, int leaf_nodes, int max_sn_nodes, bool reuse
   build_front_plan(pb->adj, x.data(), y.data(), opt, pb->plan);
   pb->plan_opt = opt;
   pb->plan_ready = true;
-  pb->dperm.n = 0;   // device copies are stale
+  pb->perm_pat_ready = false;
+  pb->plan_serial++;  // device copies made from the previous plan are stale
   return true;
 }
 
@@ -426,201 +457,364 @@ int plfem_spmv_csr(plfem_ctx* ctx, int64_t rows, int64_t nnz, const int64_t* ind
   });
 }
 
+// Modal solves of nb designs as ONE forest: per-design symbolic analysis on host threads, then a single
+// chain of launches (assembly slices, one level-batched factorisation, lockstep block Lanczos, reductions).
+// A failure of one design (singular shift, no convergence) is reported in statuses[b] and leaves the others intact.
+static void solve_forest(plfem_ctx* ctx, int nb, plfem_problem* const* pbs, const plfem_material* mats, const plfem_solve_opts* opts,
+                         double* const* eigvals, double* const* evecs, double* const* metrics, int32_t* core_counts,
+                         plfem_solve_stats* stats, int32_t* statuses, std::vector<std::string>& errs, SolveWork& W, bool reuse_work) {
+  PLFEM_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  std::vector<int64_t> nint(nb);
+  int kmax = 0;
+  for (int b = 0; b < nb; ++b) {
+    plfem_problem* pb = pbs[b];
+    need(pb && pb->ctx == ctx, "every problem of a batch must belong to the batch's context");
+    need(eigvals[b] && metrics[b], "NULL output");
+    if (pb->dof.n_degenerate > 0)
+      throw StatusError(PLFEM_ERR_DEGENERATE, std::to_string(pb->dof.n_degenerate) + " zero-area triangle(s): the affine map is singular");
+    nint[b] = (int64_t)pb->dof.interior.size();
+    need(opts[b].k >= 1 && opts[b].k < 2 * nint[b], "k out of range");
+    for (int c = 0; c < b; ++c) need(pbs[c] != pb, "a problem appears twice in the batch");
+    kmax = std::max(kmax, opts[b].k);
+  }
+  const plfem_solve_opts& o0 = opts[0];
+  const int refine = o0.refine == 0 ? 1 : std::max(o0.refine, 0);
+  const int block = o0.block == 0 ? SOLVE_NRHS : o0.block;     // 0 = default (block Lanczos), 1 = single vector
+  need(block == 1 || block == SOLVE_NRHS, "block must be 0 (default), 1 or SOLVE_NRHS");
+  const bool single_vector = (nb == 1) && (block == 1 || 2 * nint[0] < 8 * SOLVE_NRHS);
+  need(nb == 1 || block == SOLVE_NRHS, "a batch of designs needs the block eigensolver");
+  ctx->launches = 0;
+  const double t0 = now_ms();
+
+  // -- symbolic (host), designs in parallel -------------------------------------------------------------
+  std::vector<double> ms_sym(nb, 0.0);
+  std::vector<std::vector<uint8_t>> masks(nb);
+  const bool have_work = reuse_work && W.ready;
+  {
+    const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+    const int outer = std::min(nb, hw);
+    std::atomic<int> next{0};
+    std::exception_ptr err; std::mutex mu;
+    auto work = [&] {
+      if (nb > 1) set_host_threads_local(std::max(1, std::min(8, hw / outer)));
+      for (int b; (b = next.fetch_add(1)) < nb;) {
+        try {
+          const double ta = now_ms();
+          plfem_problem* pb = pbs[b];
+          ensure_plan(pb, opts[b].leaf_nodes, opts[b].max_sn_nodes, opts[b].reuse_symbolic != 0);
+          if (!pb->perm_pat_ready) {
+            std::vector<int32_t> new_of(pb->plan.n);
+            for (int32_t r = 0; r < pb->plan.n; ++r) new_of[pb->plan.perm[r]] = r;
+            relabel_pattern(pb->adj, pb->plan.perm, new_of, pb->dof.interior, pb->dof.N, pb->perm_pat);
+            pb->perm_pat_ready = true;
+          }
+          // core mask of the permuted interior nodes (solver_fem.py:200-203)
+          const plfem_material* mat = &mats[b];
+          const int64_t n = nint[b];
+          std::vector<uint8_t>& mask = masks[b];
+          mask.assign(n, 0);
+          const double* Xc = pb->dof.doflocs.data();
+          const double* Yc = Xc + pb->dof.N;
+          int32_t cnt = 0;
+          for (int64_t r = 0; r < n; ++r) {
+            const int32_t node = pb->dof.interior[pb->plan.perm[r]];
+            bool in = false;
+            for (int c = 0; c < mat->n_cores && mat->cores_xy; ++c) {
+              volatile double dx = Xc[node] - mat->cores_xy[2 * c], dy = Yc[node] - mat->cores_xy[2 * c + 1];
+              volatile double dx2 = dx * dx, dy2 = dy * dy, rr = mat->cores_r[c] * mat->cores_r[c];
+              volatile double d2 = dx2 + dy2;
+              if (d2 <= rr) in = true;
+            }
+            mask[r] = in; cnt += in;
+          }
+          if (core_counts) core_counts[b] = cnt;
+          ms_sym[b] = now_ms() - ta;
+        } catch (...) { std::lock_guard<std::mutex> g(mu); if (!err) err = std::current_exception(); }
+      }
+      set_host_threads_local(0);
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < outer; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    if (err) std::rethrow_exception(err);
+  }
+  if (!have_work) {
+    std::vector<const FrontPlan*> plans(nb); std::vector<const Pattern*> pats(nb);
+    for (int b = 0; b < nb; ++b) { plans[b] = &pbs[b]->plan; pats[b] = &pbs[b]->perm_pat; }
+    std::vector<int32_t> node_off;
+    merge_front_plans(plans, W.plan, node_off, W.front_off);
+    merge_patterns(pats, W.pat, W.nnz_off);
+    W.bd.set(ctx, node_off);
+    upload_pattern(ctx, W.pat, W.dpat);
+    build_dev_plan(ctx, W.plan, W.dplan);
+    W.d_perm.upload(ctx, W.plan.perm);
+    W.ready = true;
+  }
+  const BatchDims& bd = W.bd;
+  const int64_t n_tot = bd.noff[nb];
+  const double t1 = now_ms();
+
+  // -- assembly: one slice of the concatenated value arrays per design ----------------------------------------
+  PLFEM_CUDA(cudaEventRecord(ctx->ev[0], st));
+  const int64_t nnz = W.dpat.nnz;
+  W.d_vals.alloc(ctx, (size_t)NV_SOLVE * nnz);
+  std::vector<double> sig(n_tot);
+  std::vector<uint8_t> mask_all(n_tot);
+  W.asm_args.resize(nb);
+  for (int b = 0; b < nb; ++b) {
+    plfem_problem* pb = pbs[b];
+    upload_material(pb, &mats[b]);
+    W.asm_args[b] = {pb->d_p.p, pb->d_edofs.p, pb->d_n2e_ptr.p, pb->d_n2e.p, pb->d_elem.p, pb->d_cores.p, pb->dof.V, pb->dof.T, mats[b]};
+    W.asm_args[b].mat.cores_xy = nullptr; W.asm_args[b].mat.cores_r = nullptr; W.asm_args[b].mat.eps_at_quad = nullptr;
+    const int64_t z0 = W.nnz_off[b];
+    launch_assemble_slice(ctx, W.nnz_off[b + 1] - z0, W.dpat.rowidx.p + z0, W.dpat.col.p + z0, W.dpat.old_of_new.p, pb->d_n2e_ptr.p,
+                          pb->d_n2e.p, pb->d_edofs.p, pb->d_elem.p, mats[b].k0 * mats[b].k0, mats[b].alpha_p, false,
+                          W.d_vals.p + z0, nnz, nullptr);
+    std::fill(sig.begin() + bd.noff[b], sig.begin() + bd.noff[b + 1], opts[b].sigma);
+    std::copy(masks[b].begin(), masks[b].end(), mask_all.begin() + bd.noff[b]);
+  }
+  W.d_sigma.upload(ctx, sig);
+  W.d_in_core.upload(ctx, mask_all);
+  PLFEM_CUDA(cudaEventRecord(ctx->ev[1], st));
+
+  // -- numeric factorisation of A - sigma B, all designs level by level ----------------------------------------
+  launch_front_load(ctx, W.dpat, W.dplan, W.d_vals.p, W.d_sigma.p);
+  run_factorization(ctx, W.dplan);
+  PLFEM_CUDA(cudaEventRecord(ctx->ev[2], st));
+  int32_t fstat[4] = {0, 0, 0, 0};
+  W.dplan.status.download(fstat, 4);
+  PLFEM_CUDA(cudaStreamSynchronize(st));   // also covers the pageable sig / mask uploads above
+  std::vector<DesignEig> des(nb);
+  for (int b = 0; b < nb; ++b) { des[b].k = opts[b].k; des[b].sigma = opts[b].sigma; des[b].tol = opts[b].tol > 0 ? opts[b].tol : 1e-7; }
+  if (fstat[0]) {
+    const int bad = (int)(std::upper_bound(W.front_off.begin(), W.front_off.end(), fstat[3]) - W.front_off.begin()) - 1;
+    const int bb = std::max(0, std::min(nb - 1, bad));
+    des[bb].status = PLFEM_ERR_SINGULAR; des[bb].err = "a pivot block of A - sigma*B is exactly singular or non-finite";
+  }
+
+  // -- eigensolver ----------------------------------------------------------------------------------
+  DevBuf<double> d_v0;
+  const double* v0p = nullptr;
+  bool any_v0 = false;
+  for (int b = 0; b < nb; ++b) any_v0 |= (opts[b].v0 != nullptr);
+  if (any_v0) {
+    std::vector<double> v0(2 * n_tot, 1.0);
+    for (int b = 0; b < nb; ++b) {
+      if (!opts[b].v0) continue;
+      const int64_t n = nint[b], r0 = bd.noff[b];
+      for (int64_t r = 0; r < n; ++r) { const int32_t ip = pbs[b]->plan.perm[r]; v0[2 * (r0 + r)] = opts[b].v0[ip]; v0[2 * (r0 + r) + 1] = opts[b].v0[n + ip]; }
+    }
+    d_v0.upload(ctx, v0);
+    PLFEM_CUDA(cudaStreamSynchronize(st));
+    v0p = d_v0.p;
+  }
+  DevBuf<double> X;
+  int64_t ldx = 2 * n_tot;
+  EigenResult er;
+  int maxiter = 0, ncv_req = 0;
+  for (int b = 0; b < nb; ++b) { maxiter = std::max(maxiter, opts[b].maxiter > 0 ? opts[b].maxiter : 12000); ncv_req = std::max(ncv_req, opts[b].ncv); }
+  if (des[0].status != PLFEM_OK && nb == 1) {
+    // nothing to iterate on
+  } else if (!single_vector) {
+    run_eigensolver_block(ctx, W.dpat, W.dplan, W.d_vals.p, W.d_sigma.p, bd, des, ncv_req > 0 ? ncv_req : 3 * kmax, maxiter, refine, v0p, X, er);
+  } else {
+    const int64_t n = nint[0];
+    const int k = opts[0].k;
+    int ncv = o0.ncv > 0 ? o0.ncv : std::max(2 * k + 1, 20);
+    ncv = (int)std::min<int64_t>(ncv, 2 * n);
+    need(ncv > k + 1, "ncv must exceed k + 1");
+    try {
+      run_eigensolver(ctx, W.dpat, W.dplan, W.d_vals.p, W.d_sigma.p, o0.sigma, k, ncv, des[0].tol, maxiter, refine, v0p, X, des[0].lambda, er);
+      des[0].nconv = er.nconv;
+    } catch (const StatusError& e) {
+      if (e.status != PLFEM_ERR_NO_CONVERGENCE && e.status != PLFEM_ERR_SINGULAR) throw;
+      des[0].status = e.status; des[0].err = e.what(); des[0].nconv = er.nconv;
+    }
+    des[0].n_block_op = 0; des[0].n_restart = er.n_restart;
+  }
+  PLFEM_CUDA(cudaEventRecord(ctx->ev[3], st));
+  W.dplan.status.download(fstat, 4);
+  PLFEM_CUDA(cudaStreamSynchronize(st));
+  if (fstat[1]) throw StatusError(PLFEM_ERR_INTERNAL, "operator kernel: a dependency wait timed out");
+
+  // -- per-mode reductions + eigenvectors in reference ordering, design by design ---------------------------
+  std::vector<std::vector<double>> resid(nb);
+  std::vector<DevBuf<double>> d_ev(nb), d_met(nb), d_res(nb);
+  for (int b = 0; b < nb; ++b) {
+    const int k = des[b].k;
+    if (des[b].lambda.size() != (size_t)k) continue;     // failed before any Ritz pair existed
+    const int64_t n = nint[b];
+    if (evecs[b]) d_ev[b].alloc(ctx, (size_t)k * 2 * n);
+    d_met[b].alloc(ctx, (size_t)k * PLFEM_NMETRICS); d_res[b].alloc(ctx, (size_t)2 * k);
+    run_mode_metrics(ctx, W.dpat, W.d_vals.p, W.d_perm.p, W.d_in_core.p, X.p, ldx, bd.noff[b], (int32_t)n, des[b].lambda, k,
+                     evecs[b] ? d_ev[b].p : nullptr, d_met[b].p, d_res[b].p);
+    resid[b].resize(2 * k);
+    d_met[b].download(metrics[b], (size_t)k * PLFEM_NMETRICS);
+    d_res[b].download(resid[b].data(), resid[b].size());
+    if (evecs[b]) d_ev[b].download(evecs[b], (size_t)k * 2 * n);
+  }
+  PLFEM_CUDA(cudaEventRecord(ctx->ev[4], st));
+  PLFEM_CUDA(cudaStreamSynchronize(st));
+  const double t2 = now_ms();
+
+  float ms_asm = 0, ms_fac = 0, ms_lan = 0, ms_met = 0;
+  cudaEventElapsedTime(&ms_asm, ctx->ev[0], ctx->ev[1]);
+  cudaEventElapsedTime(&ms_fac, ctx->ev[1], ctx->ev[2]);
+  cudaEventElapsedTime(&ms_lan, ctx->ev[2], ctx->ev[3]);
+  cudaEventElapsedTime(&ms_met, ctx->ev[3], ctx->ev[4]);
+  for (int b = 0; b < nb; ++b) {
+    statuses[b] = des[b].status;
+    errs[b] = des[b].err;
+    if (des[b].lambda.size() == (size_t)des[b].k) std::copy(des[b].lambda.begin(), des[b].lambda.end(), eigvals[b]);
+    if (!stats) continue;
+    plfem_solve_stats* s = &stats[b];
+    std::memset(s, 0, sizeof(*s));
+    const FrontPlan& P = pbs[b]->plan;
+    s->nconv = des[b].nconv; s->n_op = single_vector ? er.n_op : des[b].n_block_op * SOLVE_NRHS;
+    s->n_restart = des[b].n_restart; s->n_block_op = des[b].n_block_op;
+    s->n_fronts = P.nfronts; s->n_levels = P.nlevels; s->max_front_nodes = P.max_front;
+    s->factor_entries = P.factor_entries; s->front_pool_doubles = P.foff[P.nfronts]; s->factor_flops = P.factor_flops;
+    double mr = 0.0;
+    for (size_t i = 0; i + 1 < resid[b].size(); i += 2) mr = std::max(mr, resid[b][i] / (resid[b][i + 1] + 1e-300));
+    s->max_residual = mr;
+    s->ms_symbolic = (float)ms_sym[b];
+    s->ms_assemble = ms_asm; s->ms_factor = ms_fac; s->ms_lanczos = ms_lan; s->ms_metrics = ms_met;
+    s->ms_total = (float)(t2 - t0);
+    s->kernel_launches = ctx->launches;
+    s->batch_size = nb; s->batch_block_ops = er.n_block_op; s->ms_symbolic_wall = (float)(t1 - t0);
+  }
+}
+
 int plfem_solve_modes(plfem_problem* pb, const plfem_material* mat, const plfem_solve_opts* o, double* eigvals, double* evecs,
                       double* metrics, int32_t* core_dof_count, plfem_solve_stats* stats) {
   if (!pb || !pb->ctx) return PLFEM_ERR_INVALID;
   plfem_ctx* ctx = pb->ctx;
   return guarded(ctx, [&] {
     need(mat && o && eigvals && metrics, "NULL argument");
-    PLFEM_CUDA(cudaSetDevice(ctx->device));
-    if (pb->dof.n_degenerate > 0)
-      throw StatusError(PLFEM_ERR_DEGENERATE, std::to_string(pb->dof.n_degenerate) + " zero-area triangle(s): the affine map is singular");
-    const int64_t n = (int64_t)pb->dof.interior.size();
-    const int k = o->k;
-    need(k >= 1 && k < 2 * n, "k out of range");
-    int ncv = o->ncv > 0 ? o->ncv : std::max(2 * k + 1, 20);
-    ncv = (int)std::min<int64_t>(ncv, 2 * n);
-    need(ncv > k + 1, "ncv must exceed k + 1");
-    ctx->launches = 0;
-    const double t0 = now_ms();
-    cudaStream_t st = ctx->stream;
+    SymbolicOptions want;
+    if (o->leaf_nodes > 0) want.leaf_nodes = o->leaf_nodes;
+    if (o->max_sn_nodes > 0) want.max_sn_nodes = o->max_sn_nodes;
+    const bool reuse = o->reuse_symbolic != 0 && pb->work && pb->work->ready && pb->plan_ready &&
+                       pb->work->plan_serial == pb->plan_serial && want.leaf_nodes == pb->plan_opt.leaf_nodes &&
+                       want.max_sn_nodes == pb->plan_opt.max_sn_nodes;
+    if (!reuse) pb->work = std::make_shared<SolveWork>();
+    ctx->last_work = pb->work;
+    int32_t status = 0;
+    std::vector<std::string> errs(1);
+    plfem_problem* pbs[1] = {pb};
+    double* ev[1] = {eigvals}; double* vc[1] = {evecs}; double* mt[1] = {metrics};
+    solve_forest(ctx, 1, pbs, mat, o, ev, vc, mt, core_dof_count, stats, &status, errs, *pb->work, reuse);
+    pb->work->plan_serial = pb->plan_serial;
+    if (status != PLFEM_OK) throw StatusError(status, errs[0]);
+  });
+}
 
-    // -- symbolic (host) --------------------------------------------------------------------------
-    ensure_plan(pb, o->leaf_nodes, o->max_sn_nodes, o->reuse_symbolic != 0);
-    if (pb->dperm.n == 0) {
-      std::vector<int32_t> new_of(pb->plan.n);
-      for (int32_t r = 0; r < pb->plan.n; ++r) new_of[pb->plan.perm[r]] = r;
-      relabel_pattern(pb->adj, pb->plan.perm, new_of, pb->dof.interior, pb->dof.N, pb->perm_pat);
-      upload_pattern(ctx, pb->perm_pat, pb->dperm);
-      build_dev_plan(ctx, pb->plan, pb->dplan);
-      pb->d_perm.upload(ctx, pb->plan.perm);
-    }
-    const double t1 = now_ms();
-
-    // -- assembly ---------------------------------------------------------------------------------
-    PLFEM_CUDA(cudaEventRecord(ctx->ev[0], st));
-    upload_material(pb, mat);
-    const int64_t nnz = pb->dperm.nnz;
-    pb->d_vals.alloc(ctx, (size_t)NV_SOLVE * nnz);
-    launch_assemble(ctx, pb->dperm, pb->d_n2e_ptr.p, pb->d_n2e.p, pb->d_edofs.p, pb->d_elem.p, mat->k0 * mat->k0,
-                    mat->alpha_p, false, pb->d_vals.p, nullptr);
-    // core mask of the permuted interior nodes (solver_fem.py:200-203)
-    {
-      std::vector<uint8_t> mask(n, 0);
-      const double* X = pb->dof.doflocs.data();
-      const double* Y = X + pb->dof.N;
-      int32_t cnt = 0;
-      for (int64_t r = 0; r < n; ++r) {
-        const int32_t node = pb->dof.interior[pb->plan.perm[r]];
-        bool in = false;
-        for (int c = 0; c < mat->n_cores && mat->cores_xy; ++c) {
-          volatile double dx = X[node] - mat->cores_xy[2 * c], dy = Y[node] - mat->cores_xy[2 * c + 1];
-          volatile double dx2 = dx * dx, dy2 = dy * dy, rr = mat->cores_r[c] * mat->cores_r[c];
-          volatile double d2 = dx2 + dy2;
-          if (d2 <= rr) in = true;
-        }
-        mask[r] = in; cnt += in;
-      }
-      if (core_dof_count) *core_dof_count = cnt;
-      pb->d_in_core.upload(ctx, mask);
-    }
-    PLFEM_CUDA(cudaEventRecord(ctx->ev[1], st));
-
-    // -- numeric factorisation of A - sigma B -----------------------------------------------------------
-    launch_front_load(ctx, pb->dperm, pb->dplan, pb->d_vals.p, o->sigma);
-    run_factorization(ctx, pb->dplan);
-    PLFEM_CUDA(cudaEventRecord(ctx->ev[2], st));
-    int32_t fstat[4] = {0, 0, 0, 0};
-    pb->dplan.status.download(fstat, 4);
-    PLFEM_CUDA(cudaStreamSynchronize(st));
-    if (fstat[0]) throw StatusError(PLFEM_ERR_SINGULAR, "a pivot block of A - sigma*B is exactly singular or non-finite");
-
-    // -- eigensolver ----------------------------------------------------------------------------------
-    DevBuf<double> d_v0;
-    const double* v0p = nullptr;
-    if (o->v0) {
-      std::vector<double> v0(2 * n);
-      for (int64_t r = 0; r < n; ++r) { const int32_t ip = pb->plan.perm[r]; v0[2 * r] = o->v0[ip]; v0[2 * r + 1] = o->v0[n + ip]; }
-      d_v0.upload(ctx, v0);
-      v0p = d_v0.p;
-    }
-    DevBuf<double> X;
-    std::vector<double> lambda;
-    EigenResult er;
-    const int refine = o->refine == 0 ? 1 : std::max(o->refine, 0);
-    const int block = o->block == 0 ? SOLVE_NRHS : o->block;     // 0 = default (block Lanczos), 1 = single vector
-    if (block == SOLVE_NRHS && 2 * n >= 8 * SOLVE_NRHS)
-      run_eigensolver_block(ctx, pb->dperm, pb->dplan, pb->d_vals.p, o->sigma, k, o->ncv > 0 ? o->ncv : 3 * k, o->tol > 0 ? o->tol : 1e-7,
-                            o->maxiter > 0 ? o->maxiter : 12000, refine, v0p, X, lambda, er);
-    else if (block == 1 || 2 * n < 8 * SOLVE_NRHS)
-      run_eigensolver(ctx, pb->dperm, pb->dplan, pb->d_vals.p, o->sigma, k, ncv, o->tol > 0 ? o->tol : 1e-7,
-                      o->maxiter > 0 ? o->maxiter : 12000, refine, v0p, X, lambda, er);
-    else
-      throw StatusError(PLFEM_ERR_INVALID, "block must be 0 (default), 1 or " + std::to_string(SOLVE_NRHS));
-    PLFEM_CUDA(cudaEventRecord(ctx->ev[3], st));
-    pb->dplan.status.download(fstat, 4);
-    PLFEM_CUDA(cudaStreamSynchronize(st));
-    if (fstat[1]) throw StatusError(PLFEM_ERR_INTERNAL, "operator kernel: a dependency wait timed out");
-
-    // -- per-mode reductions + eigenvectors in reference ordering -------------------------------------------
-    DevBuf<double> d_ev, d_met, d_res;
-    if (evecs) d_ev.alloc(ctx, (size_t)k * 2 * n);
-    d_met.alloc(ctx, (size_t)k * PLFEM_NMETRICS); d_res.alloc(ctx, (size_t)2 * k);
-    run_mode_metrics(ctx, pb->dperm, pb->d_vals.p, pb->d_perm.p, pb->d_in_core.p, X.p, lambda, k, evecs ? d_ev.p : nullptr,
-                     d_met.p, d_res.p);
-    std::vector<double> res(2 * k);
-    d_met.download(metrics, (size_t)k * PLFEM_NMETRICS);
-    d_res.download(res.data(), res.size());
-    if (evecs) d_ev.download(evecs, (size_t)k * 2 * n);
-    PLFEM_CUDA(cudaEventRecord(ctx->ev[4], st));
-    PLFEM_CUDA(cudaStreamSynchronize(st));
-    std::copy(lambda.begin(), lambda.end(), eigvals);
-    const double t2 = now_ms();
-
-    if (stats) {
-      std::memset(stats, 0, sizeof(*stats));
-      stats->nconv = er.nconv; stats->n_op = er.n_op; stats->n_restart = er.n_restart; stats->n_block_op = er.n_block_op;
-      stats->n_fronts = pb->plan.nfronts; stats->n_levels = pb->plan.nlevels; stats->max_front_nodes = pb->plan.max_front;
-      stats->factor_entries = pb->plan.factor_entries; stats->front_pool_doubles = pb->plan.foff[pb->plan.nfronts];
-      stats->factor_flops = pb->plan.factor_flops;
-      double mr = 0.0;
-      for (int i = 0; i < k; ++i) mr = std::max(mr, res[2 * i] / (res[2 * i + 1] + 1e-300));
-      stats->max_residual = mr;
-      stats->ms_symbolic = (float)(t1 - t0);
-      cudaEventElapsedTime(&stats->ms_assemble, ctx->ev[0], ctx->ev[1]);
-      cudaEventElapsedTime(&stats->ms_factor, ctx->ev[1], ctx->ev[2]);
-      cudaEventElapsedTime(&stats->ms_lanczos, ctx->ev[2], ctx->ev[3]);
-      cudaEventElapsedTime(&stats->ms_metrics, ctx->ev[3], ctx->ev[4]);
-      stats->ms_total = (float)(t2 - t0);
-      stats->kernel_launches = ctx->launches;
-    }
+int plfem_solve_modes_batch(plfem_ctx* ctx, int32_t nb, plfem_problem* const* pbs, const plfem_material* mats,
+                            const plfem_solve_opts* opts, double* const* eigvals, double* const* evecs, double* const* metrics,
+                            int32_t* core_dof_counts, plfem_solve_stats* stats, int32_t* statuses) {
+  if (!ctx) return PLFEM_ERR_INVALID;
+  return guarded(ctx, [&] {
+    need(nb >= 1 && pbs && mats && opts && eigvals && evecs && metrics && statuses, "NULL argument");
+    auto Wp = std::make_shared<SolveWork>();
+    ctx->last_work = Wp;         // kept for plfem_profile_last; replaced (and its buffers recycled) by the next solve
+    SolveWork& W = *Wp;
+    std::vector<std::string> errs(nb);
+    for (int b = 0; b < nb; ++b) statuses[b] = PLFEM_ERR_INTERNAL;
+    solve_forest(ctx, nb, pbs, mats, opts, eigvals, evecs, metrics, core_dof_counts, stats, statuses, errs, W, false);
+    ctx->err.clear();
+    for (int b = 0; b < nb; ++b)
+      if (statuses[b] != PLFEM_OK) { ctx->err = "design " + std::to_string(b) + ": " + errs[b]; break; }
   });
 }
 
 // Per-kernel timings for the roofline report: CUDA events on the library's own stream, L2 flushed
-// (a 256 MiB memset) before every timed repetition.  Needs a completed plfem_solve_modes on pb.
+// (a 256 MiB memset) before every timed repetition, on the device state the last solve of this context left
+// behind (a single design or a forest: every launch then carries all its designs).
 // out_ms[0] element setup + assembly, [1] front load + factorisation, [2] forward sweep (all levels),
-// [3] backward sweep (all levels), [4] B product (spmm), [5] K residual (refinement spmv); out_bytes
-// holds the algorithmic bytes of the same six items.
+// [3] backward sweep (all levels), [4] B product (spmm), [5] K residual (refinement spmv), [6] / [7] the sweeps
+// with SOLVE_NRHS right-hand sides; out_bytes holds the algorithmic bytes of the same items.
+static void profile_work(plfem_ctx* ctx, SolveWork& W, int repeat, double* out_ms, double* out_bytes) {
+  if (!W.ready || W.d_vals.p == nullptr || W.asm_args.empty()) throw StatusError(PLFEM_ERR_NOT_READY, "run a modal solve first");
+  PLFEM_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int reps = std::max(repeat, 1);
+  const int nb = W.bd.nb;
+  const int64_t n = W.dpat.n, nnz = W.dpat.nnz, m = 2 * n;
+  DevBuf<double> flush, b, x, t;
+  flush.alloc(ctx, (size_t)32 << 20);   // 256 MiB > 126 MB L2
+  b.alloc(ctx, m); x.alloc(ctx, m); t.alloc(ctx, m);
+  std::vector<double> ones(m, 1.0);
+  b.upload(ctx, ones);
+  auto timed = [&](auto&& body) {
+    double tot = 0.0;
+    for (int r = 0; r < reps; ++r) {
+      PLFEM_CUDA(cudaMemsetAsync(flush.p, r & 0xff, flush.n * sizeof(double), st));
+      PLFEM_CUDA(cudaEventRecord(ctx->ev[5], st));
+      body();
+      PLFEM_CUDA(cudaEventRecord(ctx->ev[6], st));
+      PLFEM_CUDA(cudaStreamSynchronize(st));
+      float ms = 0; PLFEM_CUDA(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]));
+      tot += ms;
+    }
+    return tot / reps;
+  };
+  out_ms[0] = timed([&] {
+    for (int d = 0; d < nb; ++d) {
+      const SolveWork::AsmArgs& a = W.asm_args[d];
+      const int64_t z0 = W.nnz_off[d];
+      launch_element_setup(ctx, a.d_p, a.d_edofs, a.V, a.T, a.mat, a.d_cores, nullptr, a.d_elem);
+      launch_assemble_slice(ctx, W.nnz_off[d + 1] - z0, W.dpat.rowidx.p + z0, W.dpat.col.p + z0, W.dpat.old_of_new.p, a.d_n2e_ptr, a.d_n2e,
+                            a.d_edofs, a.d_elem, a.mat.k0 * a.mat.k0, a.mat.alpha_p, false, W.d_vals.p + z0, nnz, nullptr);
+    }
+  });
+  // mesh in (coordinates + 6 DOF ids per element), every assembled value out once
+  out_bytes[0] = 8.0 * NV_SOLVE * nnz;
+  for (const SolveWork::AsmArgs& a : W.asm_args) out_bytes[0] += 16.0 * a.V + 24.0 * a.T;
+  out_ms[1] = timed([&] { launch_front_load(ctx, W.dpat, W.dplan, W.d_vals.p, W.d_sigma.p); run_factorization(ctx, W.dplan); });
+  out_bytes[1] = 8.0 * 5 * nnz + 8.0 * W.plan.factor_entries;   // read A,B values, write the factor
+  out_ms[2] = timed([&] { run_solve_forward(ctx, W.dplan, b.p, x.p); });
+  out_bytes[2] = 8.0 * W.plan.factor_entries + 16.0 * m;
+  out_ms[3] = timed([&] { run_solve_backward(ctx, W.dplan, x.p); });
+  {
+    double w = 0; for (int f = 0; f < W.plan.nfronts; ++f) w += 4.0 * W.plan.s[f] * (W.plan.sptr[f + 1] - W.plan.sptr[f]);
+    out_bytes[3] = 8.0 * w + 16.0 * m;
+  }
+  out_ms[4] = timed([&] { launch_spmm_b(ctx, W.dpat, W.d_vals.p, b.p, t.p); });
+  out_bytes[4] = 12.0 * nnz + 4.0 * (n + 1) + 32.0 * n;           // values + columns + row pointers + x and y (2 comps)
+  out_ms[5] = timed([&] { launch_resid_k(ctx, W.dpat, W.d_vals.p, W.d_sigma.p, x.p, b.p, t.p); });
+  out_bytes[5] = (5 * 8.0 + 4.0) * nnz + 4.0 * (n + 1) + 48.0 * n;
+  {
+    DevBuf<double> b4, x4;
+    b4.alloc(ctx, (size_t)m * SOLVE_NRHS); x4.alloc(ctx, (size_t)m * SOLVE_NRHS);
+    for (int r = 0; r < SOLVE_NRHS; ++r) PLFEM_CUDA(cudaMemcpyAsync(b4.p + r * m, b.p, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    out_ms[6] = timed([&] { run_solve_forward(ctx, W.dplan, b4.p, x4.p, SOLVE_NRHS, m); });
+    out_bytes[6] = out_bytes[2] + 16.0 * m * (SOLVE_NRHS - 1);
+    out_ms[7] = timed([&] { run_solve_backward(ctx, W.dplan, x4.p, SOLVE_NRHS, m); });
+    out_bytes[7] = out_bytes[3] + 16.0 * m * (SOLVE_NRHS - 1);
+  }
+}
+
 int plfem_profile_kernels(plfem_problem* pb, const plfem_material* mat, double sigma, int repeat, double* out_ms,
                           double* out_bytes) {
   if (!pb || !pb->ctx) return PLFEM_ERR_INVALID;
   plfem_ctx* ctx = pb->ctx;
   return guarded(ctx, [&] {
     need(mat && out_ms && out_bytes, "NULL argument");
-    if (pb->dperm.n == 0 || pb->d_vals.p == nullptr) throw StatusError(PLFEM_ERR_NOT_READY, "run plfem_solve_modes first");
-    PLFEM_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    const int reps = std::max(repeat, 1);
-    const int64_t n = pb->dperm.n, nnz = pb->dperm.nnz, m = 2 * n;
-    DevBuf<double> flush, b, x, t;
-    flush.alloc(ctx, (size_t)32 << 20);   // 256 MiB > 126 MB L2
-    b.alloc(ctx, m); x.alloc(ctx, m); t.alloc(ctx, m);
-    std::vector<double> ones(m, 1.0);
-    b.upload(ctx, ones);
-    auto timed = [&](auto&& body) {
-      double tot = 0.0;
-      for (int r = 0; r < reps; ++r) {
-        PLFEM_CUDA(cudaMemsetAsync(flush.p, r & 0xff, flush.n * sizeof(double), st));
-        PLFEM_CUDA(cudaEventRecord(ctx->ev[5], st));
-        body();
-        PLFEM_CUDA(cudaEventRecord(ctx->ev[6], st));
-        PLFEM_CUDA(cudaStreamSynchronize(st));
-        float ms = 0; PLFEM_CUDA(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]));
-        tot += ms;
-      }
-      return tot / reps;
-    };
-    const DofTables& d = pb->dof;
-    out_ms[0] = timed([&] {
-      launch_element_setup(ctx, pb->d_p.p, pb->d_edofs.p, d.V, d.T, *mat, pb->d_cores.p, nullptr, pb->d_elem.p);
-      launch_assemble(ctx, pb->dperm, pb->d_n2e_ptr.p, pb->d_n2e.p, pb->d_edofs.p, pb->d_elem.p, mat->k0 * mat->k0, mat->alpha_p,
-                      false, pb->d_vals.p, nullptr);
-    });
-    // mesh in (coordinates + 6 DOF ids per element), every assembled value out once
-    out_bytes[0] = 16.0 * d.V + 24.0 * d.T + 8.0 * NV_SOLVE * nnz;
-    out_ms[1] = timed([&] { launch_front_load(ctx, pb->dperm, pb->dplan, pb->d_vals.p, sigma); run_factorization(ctx, pb->dplan); });
-    out_bytes[1] = 8.0 * 5 * nnz + 8.0 * pb->plan.factor_entries;   // read A,B values, write the factor
-    out_ms[2] = timed([&] { run_solve_forward(ctx, pb->dplan, b.p, x.p); });
-    out_bytes[2] = 8.0 * pb->plan.factor_entries + 16.0 * m;
-    out_ms[3] = timed([&] { run_solve_backward(ctx, pb->dplan, x.p); });
-    {
-      double w = 0; for (int f = 0; f < pb->plan.nfronts; ++f) w += 4.0 * pb->plan.s[f] * (pb->plan.sptr[f + 1] - pb->plan.sptr[f]);
-      out_bytes[3] = 8.0 * w + 16.0 * m;
-    }
-    out_ms[4] = timed([&] { launch_spmm_b(ctx, pb->dperm, pb->d_vals.p, b.p, t.p); });
-    out_bytes[4] = 12.0 * nnz + 4.0 * (n + 1) + 32.0 * n;           // values + columns + row pointers + x and y (2 comps)
-    out_ms[5] = timed([&] { launch_resid_k(ctx, pb->dperm, pb->d_vals.p, sigma, x.p, b.p, t.p); });
-    out_bytes[5] = (5 * 8.0 + 4.0) * nnz + 4.0 * (n + 1) + 48.0 * n;
-    {
-      DevBuf<double> b4, x4;
-      b4.alloc(ctx, (size_t)m * SOLVE_NRHS); x4.alloc(ctx, (size_t)m * SOLVE_NRHS);
-      for (int r = 0; r < SOLVE_NRHS; ++r) PLFEM_CUDA(cudaMemcpyAsync(b4.p + r * m, b.p, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
-      out_ms[6] = timed([&] { run_solve_forward(ctx, pb->dplan, b4.p, x4.p, SOLVE_NRHS, m); });
-      out_bytes[6] = out_bytes[2] + 16.0 * m * (SOLVE_NRHS - 1);
-      out_ms[7] = timed([&] { run_solve_backward(ctx, pb->dplan, x4.p, SOLVE_NRHS, m); });
-      out_bytes[7] = out_bytes[3] + 16.0 * m * (SOLVE_NRHS - 1);
-    }
+    (void)sigma;   // material and shift of the last solve are still on the device
+    if (!pb->work) throw StatusError(PLFEM_ERR_NOT_READY, "run plfem_solve_modes first");
+    profile_work(ctx, *pb->work, repeat, out_ms, out_bytes);
+  });
+}
+
+int plfem_profile_last(plfem_ctx* ctx, int repeat, double* out_ms, double* out_bytes, int32_t* batch_size) {
+  if (!ctx) return PLFEM_ERR_INVALID;
+  return guarded(ctx, [&] {
+    need(out_ms && out_bytes, "NULL argument");
+    if (!ctx->last_work) throw StatusError(PLFEM_ERR_NOT_READY, "no solve has run on this context");
+    profile_work(ctx, *ctx->last_work, repeat, out_ms, out_bytes);
+    if (batch_size) *batch_size = ctx->last_work->bd.nb;
   });
 }
 
@@ -632,22 +826,24 @@ int plfem_debug_solve(plfem_problem* pb, double sigma, const double* b, double* 
   plfem_ctx* ctx = pb->ctx;
   return guarded(ctx, [&] {
     need(b && x, "NULL argument");
-    if (pb->dperm.n == 0 || pb->d_vals.p == nullptr) throw StatusError(PLFEM_ERR_NOT_READY, "run plfem_solve_modes first");
+    if (!pb->work || !pb->work->ready || pb->work->d_vals.p == nullptr) throw StatusError(PLFEM_ERR_NOT_READY, "run plfem_solve_modes first");
+    SolveWork& W = *pb->work;
+    (void)sigma;   // the factors and W.d_sigma belong to the last solve
     PLFEM_CUDA(cudaSetDevice(ctx->device));
-    const int64_t n = pb->dperm.n, m = 2 * n;
+    const int64_t n = W.dpat.n, m = 2 * n;
     std::vector<double> hb(m), hx(m);
     for (int64_t r = 0; r < n; ++r) { const int32_t ip = pb->plan.perm[r]; hb[2 * r] = b[ip]; hb[2 * r + 1] = b[n + ip]; }
     DevBuf<double> db, dx, dt, dd;
     db.upload(ctx, hb); dx.alloc(ctx, m); dt.alloc(ctx, m); dd.alloc(ctx, m);
     if (refine >= 100) {   // refine = 100 + r: exercise the per-level kernels instead of the persistent one
-      run_solve(ctx, pb->dplan, db.p, dx.p);
+      run_solve(ctx, W.dplan, db.p, dx.p);
       for (int it = 0; it < refine - 100; ++it) {
-        launch_resid_k(ctx, pb->dperm, pb->d_vals.p, sigma, dx.p, db.p, dt.p);
-        run_solve(ctx, pb->dplan, dt.p, dd.p);
+        launch_resid_k(ctx, W.dpat, W.d_vals.p, W.d_sigma.p, dx.p, db.p, dt.p);
+        run_solve(ctx, W.dplan, dt.p, dd.p);
         launch_axpy(ctx, dx.p, dd.p, m);
       }
     } else {
-      run_operator(ctx, pb->dperm, pb->dplan, pb->d_vals.p, sigma, db.p, dx.p, dt.p, dd.p, refine, ctx->coop_ctas_per_sm);
+      run_operator(ctx, W.dpat, W.dplan, W.d_vals.p, W.d_sigma.p, db.p, dx.p, dt.p, dd.p, refine, ctx->coop_ctas_per_sm);
     }
     dx.download(hx.data(), m);
     PLFEM_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(128)
 assemble_kernel(int64_t nnz, const int32_t* __restrict__ rowidx, const int32_t* __restrict__ col,
                 const int32_t* __restrict__ old_of_new, const int32_t* __restrict__ n2e_ptr,
                 const int32_t* __restrict__ n2e, const int32_t* __restrict__ edofs, const double* __restrict__ elem,
-                double k0sq, double alpha, double* __restrict__ vals, uint32_t* __restrict__ flags) {
+                double k0sq, double alpha, double* __restrict__ vals, int64_t vstride, uint32_t* __restrict__ flags) {
   __shared__ double s_phi[36], s_dx[36], s_dy[36], s_w[6];
   for (int i = threadIdx.x; i < 36; i += blockDim.x) { s_phi[i] = c_tab.phi[i]; s_dx[i] = c_tab.dx[i]; s_dy[i] = c_tab.dy[i]; }
   if (threadIdx.x < 6) s_w[threadIdx.x] = c_tab.w[threadIdx.x];
@@ -186,18 +186,18 @@ assemble_kernel(int64_t nnz, const int32_t* __restrict__ rowidx, const int32_t* 
 
   if (EXPORT) {
 #pragma unroll
-    for (int k = 0; k < 10; ++k) vals[(int64_t)k * nnz + z] = g[k];
+    for (int k = 0; k < 10; ++k) vals[(int64_t)k * vstride + z] = g[k];
     flags[z] = fl;
   } else {
     const double km = mul(k0sq, g[X_M]);
-    vals[(int64_t)S_AXX * nnz + z] = add(add(g[X_KXX], mul(alpha, g[X_DXX])), -km);
-    vals[(int64_t)S_AXY * nnz + z] = add(g[X_KXY], mul(alpha, g[X_DXY]));
-    vals[(int64_t)S_AYX * nnz + z] = add(g[X_KYX], mul(alpha, g[X_DYX]));
-    vals[(int64_t)S_AYY * nnz + z] = add(add(g[X_KYY], mul(alpha, g[X_DYY])), -km);
-    vals[(int64_t)S_MINV * nnz + z] = g[X_MINV];
-    vals[(int64_t)S_DXX * nnz + z] = g[X_DXX];
-    vals[(int64_t)S_DXY * nnz + z] = g[X_DXY];
-    vals[(int64_t)S_DYY * nnz + z] = g[X_DYY];
+    vals[(int64_t)S_AXX * vstride + z] = add(add(g[X_KXX], mul(alpha, g[X_DXX])), -km);
+    vals[(int64_t)S_AXY * vstride + z] = add(g[X_KXY], mul(alpha, g[X_DXY]));
+    vals[(int64_t)S_AYX * vstride + z] = add(g[X_KYX], mul(alpha, g[X_DYX]));
+    vals[(int64_t)S_AYY * vstride + z] = add(add(g[X_KYY], mul(alpha, g[X_DYY])), -km);
+    vals[(int64_t)S_MINV * vstride + z] = g[X_MINV];
+    vals[(int64_t)S_DXX * vstride + z] = g[X_DXX];
+    vals[(int64_t)S_DXY * vstride + z] = g[X_DXY];
+    vals[(int64_t)S_DYY * vstride + z] = g[X_DYY];
   }
 }
 
@@ -250,19 +250,28 @@ void launch_expand_rows(plfem_ctx* ctx, const DevPattern& pat) {
   ctx->launches++;
 }
 
+// one design's slice of a (possibly concatenated) pattern: nnz entries starting at rowidx/col, values written to
+// vals[k * vstride + z]; row/column ids index old_of_new, whose entries are DOF ids of THIS design's mesh
+void launch_assemble_slice(plfem_ctx* ctx, int64_t nnz, const int32_t* d_rowidx, const int32_t* d_col, const int32_t* d_old_of_new,
+                           const int32_t* d_n2e_ptr, const int32_t* d_n2e, const int32_t* d_edofs, const double* d_elem,
+                           double k0sq, double alpha, bool export_mode, double* d_vals, int64_t vstride, uint32_t* d_flags) {
+  const int bs = 128;
+  const unsigned grid = (unsigned)((nnz + bs - 1) / bs);
+  if (export_mode)
+    assemble_kernel<true><<<grid, bs, 0, ctx->stream>>>(nnz, d_rowidx, d_col, d_old_of_new, d_n2e_ptr, d_n2e, d_edofs, d_elem, k0sq,
+                                                        alpha, d_vals, vstride, d_flags);
+  else
+    assemble_kernel<false><<<grid, bs, 0, ctx->stream>>>(nnz, d_rowidx, d_col, d_old_of_new, d_n2e_ptr, d_n2e, d_edofs, d_elem, k0sq,
+                                                         alpha, d_vals, vstride, d_flags);
+  PLFEM_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
 void launch_assemble(plfem_ctx* ctx, const DevPattern& pat, const int32_t* d_n2e_ptr, const int32_t* d_n2e,
                      const int32_t* d_edofs, const double* d_elem, double k0sq, double alpha, bool export_mode,
                      double* d_vals, uint32_t* d_flags) {
-  const int bs = 128;
-  const unsigned grid = (unsigned)((pat.nnz + bs - 1) / bs);
-  if (export_mode)
-    assemble_kernel<true><<<grid, bs, 0, ctx->stream>>>(pat.nnz, pat.rowidx.p, pat.col.p, pat.old_of_new.p, d_n2e_ptr,
-                                                        d_n2e, d_edofs, d_elem, k0sq, alpha, d_vals, d_flags);
-  else
-    assemble_kernel<false><<<grid, bs, 0, ctx->stream>>>(pat.nnz, pat.rowidx.p, pat.col.p, pat.old_of_new.p, d_n2e_ptr,
-                                                         d_n2e, d_edofs, d_elem, k0sq, alpha, d_vals, d_flags);
-  PLFEM_CUDA(cudaGetLastError());
-  ctx->launches++;
+  launch_assemble_slice(ctx, pat.nnz, pat.rowidx.p, pat.col.p, pat.old_of_new.p, d_n2e_ptr, d_n2e, d_edofs, d_elem, k0sq, alpha,
+                        export_mode, d_vals, pat.nnz, d_flags);
 }
 
 void launch_spmv_csr(plfem_ctx* ctx, int64_t rows, const int32_t* rowptr, const int32_t* col, const double* val,

@@ -2,9 +2,12 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -40,10 +43,13 @@ class DeviceArena {
   size_t reserved_bytes() const { return reserved_; }
 
  private:
+  std::mutex mu_;   // problems of one context may be created from several host threads
   std::multimap<size_t, void*> free_;
   std::map<void*, size_t> live_;
   size_t reserved_ = 0;
 };
+
+struct SolveWork;   // device state of one solve (api.cu)
 
 }  // namespace plfem
 
@@ -55,6 +61,7 @@ struct plfem_ctx {
   int launches = 0;          // kernels launched since the counter was last reset
   int coop_ctas_per_sm = 4;  // grid of the persistent operator kernel (lower it when several contexts share the GPU)
   cudaEvent_t ev[8] = {};
+  std::shared_ptr<plfem::SolveWork> last_work;   // what the last solve left on the device (measurement hook)
   void* pinned = nullptr;    // pinned staging buffer for small device->host reads
   size_t pinned_bytes = 0;
   void* pin(size_t bytes);
@@ -120,6 +127,9 @@ void launch_expand_rows(plfem_ctx* ctx, const DevPattern& pat);
 void launch_assemble(plfem_ctx* ctx, const DevPattern& pat, const int32_t* d_n2e_ptr, const int32_t* d_n2e,
                      const int32_t* d_edofs, const double* d_elem, double k0sq, double alpha, bool export_mode,
                      double* d_vals, uint32_t* d_flags);
+void launch_assemble_slice(plfem_ctx* ctx, int64_t nnz, const int32_t* d_rowidx, const int32_t* d_col, const int32_t* d_old_of_new,
+                           const int32_t* d_n2e_ptr, const int32_t* d_n2e, const int32_t* d_edofs, const double* d_elem,
+                           double k0sq, double alpha, bool export_mode, double* d_vals, int64_t vstride, uint32_t* d_flags);
 void launch_spmv_csr(plfem_ctx* ctx, int64_t rows, const int32_t* rowptr, const int32_t* col, const double* val,
                      const double* x, double* y);
 
@@ -158,12 +168,13 @@ struct DevPlan {
   int64_t upd_len = 0;
 };
 void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D);
-void launch_front_load(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, double sigma);
+// d_sigma_node: the shift of the design each (permuted) node belongs to — a forest of designs is one problem
+void launch_front_load(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, const double* d_sigma_node);
 void run_factorization(plfem_ctx* ctx, const DevPlan& D);
 // solves (A - sigma B) x = b in the permuted interleaved layout, b and x of length 2n (must not alias)
 constexpr int SOLVE_NRHS = 4;   // block size of the multi-right-hand-side sweeps (block Lanczos)
 void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x, int nrhs = 1, int64_t ld = 0);
-void run_operator(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, double sigma, const double* b,
+void run_operator(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, const double* d_sigma_node, const double* b,
                   double* x, double* rt, double* rdx, int refine, int ctas_per_sm);
 void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double* z, int nrhs = 1, int64_t ld = 0);
 void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs = 1, int64_t ld = 0);
@@ -173,23 +184,44 @@ struct EigenResult {
   std::vector<double> theta;  // Ritz values of OP, wanted ones, sorted by eigenvalue ascending
   int nconv = 0, n_op = 0, n_restart = 0, n_block_op = 0;
 };
-struct EigenWork;  // opaque
-void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, double sigma,
+// A forest of independent designs laid out as one block-diagonal problem: design b owns the permuted nodes
+// [noff[b], noff[b+1]) and the vector rows [moff[b], moff[b+1]) (two unknowns per node).
+struct BatchDims {
+  int nb = 1;
+  std::vector<int32_t> noff;
+  std::vector<int64_t> moff;
+  DevBuf<int64_t> d_moff;
+  int64_t mmax = 0;              // rows of the largest design
+  void set(plfem_ctx* ctx, const std::vector<int32_t>& node_off) {
+    nb = (int)node_off.size() - 1; noff = node_off; moff.resize(nb + 1); mmax = 0;
+    for (int b = 0; b <= nb; ++b) moff[b] = 2 * (int64_t)noff[b];
+    for (int b = 0; b < nb; ++b) mmax = std::max(mmax, moff[b + 1] - moff[b]);
+    d_moff.upload(ctx, moff);
+  }
+};
+struct DesignEig {               // one design's eigenproblem inside a forest
+  int k = 0; double sigma = 0.0, tol = 1e-7;
+  int status = 0; std::string err;       // PLFEM_OK or why THIS design failed (the others are unaffected)
+  std::vector<double> lambda, theta;     // ascending in lambda
+  int nconv = 0, n_block_op = 0, n_restart = 0;
+};
+void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, const double* d_sigma_node, double sigma,
                      int k, int ncv, double tol, int maxiter, int refine_steps, const double* d_v0 /* permuted, may be null */,
                      DevBuf<double>& X /* (2n, k) eigenvectors, permuted layout */, std::vector<double>& lambda,
                      EigenResult& res);
-void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, double sigma, int k, int ncv,
-                           double tol, int maxiter, int refine_steps, const double* d_v0, DevBuf<double>& X,
-                           std::vector<double>& lambda, EigenResult& res);
+// X is (moff[nb] x max k), leading dimension moff[nb]; per-design results and failures in `des`
+void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, const double* d_sigma_node,
+                           const BatchDims& bd, std::vector<DesignEig>& des, int ncv, int maxiter, int refine_steps,
+                           const double* d_v0, DevBuf<double>& X, EigenResult& res);
 void run_mode_metrics(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, const int32_t* d_perm_to_interior,
-                      const uint8_t* d_in_core, const double* X, const std::vector<double>& lambda, int k,
-                      double* d_out_evecs /* (k, 2n) reference ordering or null */, double* d_metrics /* (k,8) */,
-                      double* d_resid /* (k,2) */);
+                      const uint8_t* d_in_core, const double* X, int64_t ldx /* doubles */, int32_t row0, int32_t n,
+                      const std::vector<double>& lambda, int k, double* d_out_evecs /* (k, 2n) reference ordering or null */,
+                      double* d_metrics /* (k,8) */, double* d_resid /* (k,2) */);
 
 void launch_spmm_b(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, const double* x, double* y, int nrhs = 1,
                    int64_t ld = 0);
-void launch_resid_k(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, double sigma, const double* x, const double* b,
-                    double* t, int nrhs = 1, int64_t ld = 0);
+void launch_resid_k(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, const double* d_sigma_node, const double* x,
+                    const double* b, double* t, int nrhs = 1, int64_t ld = 0);
 
 void launch_axpy(plfem_ctx* ctx, double* x, const double* dx, int64_t m);
 void symmetric_eigen(int n, std::vector<double>& a /* n*n col-major in, eigenvectors out */, std::vector<double>& w);

@@ -14,8 +14,12 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <atomic>
+#include <exception>
+#include <mutex>
 #include <numeric>
 #include <string>
+#include <thread>
 
 namespace plfem {
 
@@ -79,8 +83,9 @@ __global__ void __launch_bounds__(256) spmm_b_kernel(int32_t n, const int32_t* _
 template <int NR>
 __global__ void __launch_bounds__(256) resid_k_kernel(int32_t n, const int32_t* __restrict__ rowptr,
                                                       const int32_t* __restrict__ col, const double* __restrict__ vals,
-                                                      int64_t nnz, double sigma, const double2* __restrict__ x,
-                                                      const double2* __restrict__ b, double2* __restrict__ t, int64_t ld2) {
+                                                      int64_t nnz, const double* __restrict__ sigma_node,
+                                                      const double2* __restrict__ x, const double2* __restrict__ b,
+                                                      double2* __restrict__ t, int64_t ld2) {
   constexpr int TPR = 4;
   const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t row = gid / TPR;
@@ -89,6 +94,7 @@ __global__ void __launch_bounds__(256) resid_k_kernel(int32_t n, const int32_t* 
 #pragma unroll
   for (int r = 0; r < NR; ++r) { ax[r] = 0.0; ay[r] = 0.0; }
   if (row < n) {
+    const double sigma = sigma_node[row];
     for (int32_t z = rowptr[row] + lane; z < rowptr[row + 1]; z += TPR) {
       const double sm = sigma * vals[(int64_t)S_MINV * nnz + z];
       const double kxx = vals[(int64_t)S_AXX * nnz + z] - sm, kxy = vals[(int64_t)S_AXY * nnz + z];
@@ -191,18 +197,24 @@ __global__ void __launch_bounds__(128) rotate_kernel(const double* __restrict__ 
   }
 }
 
-// ---- block Lanczos pieces (P = SOLVE_NRHS vectors per block) -------------------------------------------------
+// ---- block Lanczos pieces (P = SOLVE_NRHS vectors per block), batched over the designs of a forest ------------
+// All vectors are concatenations over the designs: design b owns rows [moff[b], moff[b+1]).  Everything that
+// couples rows — inner products, the small Cholesky, the coefficient matrices — is per design (blockIdx.y);
+// with one design the kernels do exactly what the single-design versions did.
 constexpr int P = SOLVE_NRHS;
 
-// H[c + r*ldh] = <Q[:,c], R[:,r]> for c < ncols, r < P; one CTA per column c
+// H_b[c + r*ldh] = <Q_b[:,c], R_b[:,r]> for c < ncols, r < P; one CTA per (column c, design b)
 __global__ void __launch_bounds__(RED_T) dots_block_kernel(const double* __restrict__ Q, int64_t ld, const double* __restrict__ R,
-                                                           int64_t m, double* __restrict__ H, int ldh) {
+                                                           const int64_t* __restrict__ moff, double* __restrict__ H, int ldh,
+                                                           int64_t hstride) {
   __shared__ double sh[32];
+  const int b = blockIdx.y;
+  const int64_t m0 = moff[b], m1 = moff[b + 1];
   const double* q = Q + (int64_t)blockIdx.x * ld;
   double acc[P];
 #pragma unroll
   for (int r = 0; r < P; ++r) acc[r] = 0.0;
-  for (int64_t i = threadIdx.x; i < m; i += RED_T) {
+  for (int64_t i = m0 + threadIdx.x; i < m1; i += RED_T) {
     const double qv = q[i];
 #pragma unroll
     for (int r = 0; r < P; ++r) acc[r] = fma(qv, R[r * ld + i], acc[r]);
@@ -210,44 +222,51 @@ __global__ void __launch_bounds__(RED_T) dots_block_kernel(const double* __restr
 #pragma unroll
   for (int r = 0; r < P; ++r) {
     const double t = block_sum(acc[r], sh);
-    if (threadIdx.x == 0) H[blockIdx.x + r * ldh] = t;
+    if (threadIdx.x == 0) H[b * hstride + blockIdx.x + r * ldh] = t;
   }
 }
 
-// R[:, r] -= V[:, 0..ncols) H[:, r]
+// R_b[:, r] -= V_b[:, 0..ncols) H_b[:, r]
 __global__ void __launch_bounds__(256) update_block_kernel(const double* __restrict__ V, int64_t ld, const double* __restrict__ H,
-                                                           int ldh, int ncols, int64_t m, double* __restrict__ R) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= m) return;
+                                                           int ldh, int64_t hstride, int ncols, const int64_t* __restrict__ moff,
+                                                           double* __restrict__ R) {
+  const int b = blockIdx.y;
+  const int64_t i = moff[b] + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= moff[b + 1]) return;
+  const double* Hb = H + b * hstride;
   double acc[P];
 #pragma unroll
   for (int r = 0; r < P; ++r) acc[r] = 0.0;
   for (int c = 0; c < ncols; ++c) {
     const double v = V[(int64_t)c * ld + i];
 #pragma unroll
-    for (int r = 0; r < P; ++r) acc[r] = fma(v, __ldg(H + c + r * ldh), acc[r]);
+    for (int r = 0; r < P; ++r) acc[r] = fma(v, __ldg(Hb + c + r * ldh), acc[r]);
   }
 #pragma unroll
   for (int r = 0; r < P; ++r) R[r * ld + i] -= acc[r];
 }
 
-// Hs[0..ncols, r] = h1 + h2 (the projected-matrix column block kept for the host)
-__global__ void store_h_kernel(const double* __restrict__ h1, const double* __restrict__ h2, int ldh, int ncols, double* __restrict__ Hs, int lds) {
+// Hs_b[0..ncols, r] = h1 + h2 (the projected-matrix column block kept for the host)
+__global__ void store_h_kernel(const double* __restrict__ h1, const double* __restrict__ h2, int ldh, int64_t hstride, int ncols,
+                               double* __restrict__ Hs, int lds, int64_t sstride) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
   if (c >= ncols) return;
 #pragma unroll
-  for (int r = 0; r < P; ++r) Hs[c + r * lds] = h1[c + r * ldh] + h2[c + r * ldh];
+  for (int r = 0; r < P; ++r) Hs[b * sstride + c + r * lds] = h1[b * hstride + c + r * ldh] + h2[b * hstride + c + r * ldh];
 }
 
-// G[r + s*P] = <R[:,r], U[:,s]>, one CTA per r
-__global__ void __launch_bounds__(RED_T) gram_kernel(const double* __restrict__ R, const double* __restrict__ U, int64_t ld, int64_t m,
-                                                     double* __restrict__ G) {
+// G_b[r + s*P] = <R_b[:,r], U_b[:,s]>, one CTA per (r, design)
+__global__ void __launch_bounds__(RED_T) gram_kernel(const double* __restrict__ R, const double* __restrict__ U, int64_t ld,
+                                                     const int64_t* __restrict__ moff, double* __restrict__ G) {
   __shared__ double sh[32];
+  const int b = blockIdx.y;
+  const int64_t m0 = moff[b], m1 = moff[b + 1];
   const double* rr = R + (int64_t)blockIdx.x * ld;
   double acc[P];
 #pragma unroll
   for (int s2 = 0; s2 < P; ++s2) acc[s2] = 0.0;
-  for (int64_t i = threadIdx.x; i < m; i += RED_T) {
+  for (int64_t i = m0 + threadIdx.x; i < m1; i += RED_T) {
     const double v = rr[i];
 #pragma unroll
     for (int s2 = 0; s2 < P; ++s2) acc[s2] = fma(v, U[s2 * ld + i], acc[s2]);
@@ -255,13 +274,18 @@ __global__ void __launch_bounds__(RED_T) gram_kernel(const double* __restrict__ 
 #pragma unroll
   for (int s2 = 0; s2 < P; ++s2) {
     const double t = block_sum(acc[s2], sh);
-    if (threadIdx.x == 0) G[blockIdx.x + s2 * P] = t;
+    if (threadIdx.x == 0) G[b * P * P + blockIdx.x + s2 * P] = t;
   }
 }
 
-// Cholesky G = L L^T (P x P, symmetrised), Linv = L^-1.  Lout (for the host): L, column-major.  status[2] = 1 on breakdown.
-__global__ void chol_kernel(const double* __restrict__ G, double* __restrict__ Lout, double* __restrict__ Linv, int32_t* status) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// Cholesky G_b = L L^T (P x P, symmetrised), Linv = L^-1, one CTA per design.  Lout (for the host): L, column-major,
+// slot `slot` of design b.  cstat[b] = 1 on breakdown (the residual block of that design lost rank).
+__global__ void chol_kernel(const double* __restrict__ G, double* __restrict__ Lall, int nslots, int slot, double* __restrict__ Linv,
+                            int32_t* __restrict__ cstat) {
+  if (threadIdx.x != 0) return;
+  const int b = blockIdx.x;
+  G += b * P * P; Linv += b * P * P;
+  double* Lout = Lall + ((size_t)b * nslots + slot) * P * P;
   double A[P][P], L[P][P], Li[P][P];
   for (int i = 0; i < P; ++i) for (int j = 0; j < P; ++j) { A[i][j] = 0.5 * (G[i + j * P] + G[j + i * P]); L[i][j] = 0.0; Li[i][j] = 0.0; }
   double dmax = 0.0;
@@ -269,7 +293,7 @@ __global__ void chol_kernel(const double* __restrict__ G, double* __restrict__ L
   for (int j = 0; j < P; ++j) {
     double d = A[j][j];
     for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
-    if (!(d > 1e-24 * dmax) || !isfinite(d)) { atomicExch(status + 2, 1); d = 1e-24 * dmax + 1e-300; }
+    if (!(d > 1e-24 * dmax) || !isfinite(d)) { cstat[b] = 1; d = 1e-24 * dmax + 1e-300; }
     L[j][j] = sqrt(d);
     for (int i = j + 1; i < P; ++i) {
       double v = A[i][j];
@@ -287,30 +311,35 @@ __global__ void chol_kernel(const double* __restrict__ G, double* __restrict__ L
   for (int i = 0; i < P; ++i) for (int j = 0; j < P; ++j) { Lout[i + j * P] = L[i][j]; Linv[i + j * P] = Li[i][j]; }
 }
 
-// Vn = R L^-T, BVn = U L^-T   (Vn[:, r] = sum_s R[:, s] * Linv[r, s])
-__global__ void __launch_bounds__(256) scale_block_kernel(const double* __restrict__ R, const double* __restrict__ U, int64_t ld, int64_t m,
-                                                          const double* __restrict__ Linv, double* __restrict__ Vn,
-                                                          double* __restrict__ BVn) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= m) return;
+// Vn_b = R_b L_b^-T, BVn_b = U_b L_b^-T   (Vn[:, r] = sum_s R[:, s] * Linv[r, s])
+__global__ void __launch_bounds__(256) scale_block_kernel(const double* __restrict__ R, const double* __restrict__ U, int64_t ld,
+                                                          const int64_t* __restrict__ moff, const double* __restrict__ Linv,
+                                                          double* __restrict__ Vn, double* __restrict__ BVn) {
+  const int b = blockIdx.y;
+  const int64_t i = moff[b] + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= moff[b + 1]) return;
+  const double* Lb = Linv + b * P * P;
   double rv[P], uv[P];
 #pragma unroll
   for (int s2 = 0; s2 < P; ++s2) { rv[s2] = R[s2 * ld + i]; uv[s2] = U[s2 * ld + i]; }
 #pragma unroll
   for (int r = 0; r < P; ++r) {
-    double a = 0.0, b = 0.0;
+    double a = 0.0, c = 0.0;
 #pragma unroll
-    for (int s2 = 0; s2 <= r; ++s2) { const double l = __ldg(Linv + r + s2 * P); a = fma(rv[s2], l, a); b = fma(uv[s2], l, b); }
-    Vn[r * ld + i] = a; BVn[r * ld + i] = b;
+    for (int s2 = 0; s2 <= r; ++s2) { const double l = __ldg(Lb + r + s2 * P); a = fma(rv[s2], l, a); c = fma(uv[s2], l, c); }
+    Vn[r * ld + i] = a; BVn[r * ld + i] = c;
   }
 }
 
-// deterministic pseudo-random start vectors for block columns 1..P-1 (column 0 is the caller's v0 / ones)
-__global__ void start_block_kernel(double* __restrict__ R, int64_t ld, int64_t m) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= m) return;
+// deterministic pseudo-random start vectors for block columns 1..P-1 (column 0 is the caller's v0 / ones); the
+// sequence depends on the row index WITHIN the design, so a design starts the same alone or in a forest
+__global__ void start_block_kernel(double* __restrict__ R, int64_t ld, const int64_t* __restrict__ moff) {
+  const int b = blockIdx.y;
+  const int64_t il = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t i = moff[b] + il;
+  if (i >= moff[b + 1]) return;
   for (int r = 1; r < P; ++r) {
-    uint64_t h = (uint64_t)i * 0x9E3779B97F4A7C15ull + (uint64_t)r * 0xBF58476D1CE4E5B9ull + 0x94D049BB133111EBull;
+    uint64_t h = (uint64_t)il * 0x9E3779B97F4A7C15ull + (uint64_t)r * 0xBF58476D1CE4E5B9ull + 0x94D049BB133111EBull;
     h ^= h >> 30; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 27; h *= 0x94D049BB133111EBull; h ^= h >> 31;
     R[r * ld + i] = (double)(h >> 11) * (2.0 / 9007199254740992.0) - 1.0;
   }
@@ -325,7 +354,7 @@ __global__ void fill_kernel(double* v, int64_t m, double val) {
 constexpr int NRED = 10;  // norm2, e_core, px_core, py_core, px_all, py_all, div, res2, ||B||_F^2, ||A||_F^2
 constexpr int MROWS = 2048;  // rows (nodes) per CTA in the mode reduction
 
-__global__ void __launch_bounds__(256) mode_partial_kernel(int32_t n, const int32_t* __restrict__ rowptr,
+__global__ void __launch_bounds__(256) mode_partial_kernel(int32_t row0, int32_t row1, const int32_t* __restrict__ rowptr,
                                                            const int32_t* __restrict__ col, const double* __restrict__ vals,
                                                            int64_t nnz, const uint8_t* __restrict__ in_core,
                                                            const double2* __restrict__ X, int64_t ldx /* in double2 */,
@@ -338,7 +367,7 @@ __global__ void __launch_bounds__(256) mode_partial_kernel(int32_t n, const int3
   double acc[NRED];
 #pragma unroll
   for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
-  const int r0 = chunk * MROWS, r1 = min(n, r0 + MROWS);
+  const int r0 = row0 + chunk * MROWS, r1 = min(row1, r0 + MROWS);   // rows of ONE design of the forest
   for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
     const double2 v = x[r];
     const double ex = v.x * v.x, ey = v.y * v.y;
@@ -394,16 +423,16 @@ __global__ void mode_final_kernel(const double* __restrict__ part, int nchunks, 
   resid[2 * mode] = sqrt(t[7]); resid[2 * mode + 1] = (sqrt(t[9]) + fabs(lambda[mode]) * sqrt(t[8])) * sqrt(t[0]);
 }
 
-__global__ void __launch_bounds__(256) write_evecs_kernel(int32_t n, const int32_t* __restrict__ perm,
+__global__ void __launch_bounds__(256) write_evecs_kernel(int32_t row0, int32_t n, const int32_t* __restrict__ perm,
                                                           const double2* __restrict__ X, int64_t ldx,
                                                           const double* __restrict__ scale, double* __restrict__ out) {
   const int mode = blockIdx.y;
   const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
-  const double2 v = X[(int64_t)mode * ldx + r];
+  const double2 v = X[(int64_t)mode * ldx + row0 + r];
   const double s = scale[mode];
   double* o = out + (int64_t)mode * 2 * n;
-  const int32_t ip = perm[r];
+  const int32_t ip = perm[row0 + r];
   o[ip] = v.x * s;
   o[n + ip] = v.y * s;
 }
@@ -419,14 +448,14 @@ void launch_spmm_b(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, 
   ctx->launches++;
 }
 
-void launch_resid_k(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, double sigma, const double* x, const double* b,
-                    double* t, int nrhs, int64_t ld) {
+void launch_resid_k(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, const double* d_sigma_node, const double* x,
+                    const double* b, double* t, int nrhs, int64_t ld) {
   const unsigned g = (unsigned)(((int64_t)pat.n * 4 + 255) / 256);
   if (nrhs == 1)
-    resid_k_kernel<1><<<g, 256, 0, ctx->stream>>>(pat.n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz, sigma, (const double2*)x,
+    resid_k_kernel<1><<<g, 256, 0, ctx->stream>>>(pat.n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz, d_sigma_node, (const double2*)x,
                                                   (const double2*)b, (double2*)t, 0);
   else
-    resid_k_kernel<SOLVE_NRHS><<<g, 256, 0, ctx->stream>>>(pat.n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz, sigma, (const double2*)x,
+    resid_k_kernel<SOLVE_NRHS><<<g, 256, 0, ctx->stream>>>(pat.n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz, d_sigma_node, (const double2*)x,
                                                            (const double2*)b, (double2*)t, ld / 2);
   PLFEM_CUDA(cudaGetLastError());
   ctx->launches++;
@@ -438,8 +467,8 @@ void launch_axpy(plfem_ctx* ctx, double* x, const double* dx, int64_t m) {
   ctx->launches++;
 }
 
-void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, double sigma, int k,
-                     int ncv, double tol, int maxiter, int refine_steps, const double* d_v0, DevBuf<double>& X,
+void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, const double* d_sigma_node, double sigma,
+                     int k, int ncv, double tol, int maxiter, int refine_steps, const double* d_v0, DevBuf<double>& X,
                      std::vector<double>& lambda, EigenResult& res) {
   const int64_t m = 2 * (int64_t)pat.n;
   const int64_t ld = m;
@@ -480,7 +509,7 @@ void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const do
     try {
       run_solve(ctx, D, opin.p, r.p);
       for (int it = 0; it < refine_steps; ++it) {
-        launch_resid_k(ctx, pat, d_vals, sigma, r.p, opin.p, rt.p);
+        launch_resid_k(ctx, pat, d_vals, d_sigma_node, r.p, opin.p, rt.p);
         run_solve(ctx, D, rt.p, rdx.p);
         launch_axpy(ctx, r.p, rdx.p, m);
       }
@@ -505,7 +534,7 @@ void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const do
       PLFEM_CUDA(cudaGraphLaunch(gexec, st));
       ctx->launches += graph_nodes;
     } else {
-      run_operator(ctx, pat, D, d_vals, sigma, bvec, r.p, rt.p, rdx.p, refine_steps, ctx->coop_ctas_per_sm);
+      run_operator(ctx, pat, D, d_vals, d_sigma_node, bvec, r.p, rt.p, rdx.p, refine_steps, ctx->coop_ctas_per_sm);
     }
   };
 
@@ -603,7 +632,7 @@ void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const do
   }
 }
 
-// ---- thick-restart BLOCK Lanczos (block size P) -----------------------------------------------------------
+// ---- thick-restart BLOCK Lanczos (block size P) on a forest of designs ---------------------------------------
 // Same operator, same inner product, same convergence test as the single-vector version, but every
 // operator application carries P vectors through the sweeps: the factor is read once for P right-hand sides
 // and the number of SEQUENTIAL operator applications — what bounds the latency of this phase, each being a
@@ -611,21 +640,57 @@ void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const do
 // from the full-reorthogonalisation coefficients (its upper triangle is exactly what the CGS passes
 // produce), so a thick restart needs no special-casing: the couplings between kept Ritz vectors and the
 // residual block reappear as the first coefficients computed after the restart.
-void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, double sigma, int k, int ncv,
-                           double tol, int maxiter, int refine_steps, const double* d_v0, DevBuf<double>& X,
-                           std::vector<double>& lambda, EigenResult& res) {
-  const int64_t m = 2 * (int64_t)pat.n, ld = m;
+//
+// Forest: the designs of a batch are independent eigenproblems on disjoint row ranges of the same vectors.
+// They advance in lockstep — ONE chain of launches serves all of them, which is what turns a latency-bound
+// solve into a throughput-bound one — each with its own inner products, projected matrix, convergence test
+// and restart rotation.  A design that converges has its Ritz vectors extracted at once; it keeps being
+// carried along (its rows cannot influence any other design) until the last one is done.
+namespace {
+template <class F>
+void for_each_design(int nb, F&& fn) {
+  const int nt = std::min<int>(nb, std::max(1u, std::thread::hardware_concurrency()));
+  if (nt <= 1) { for (int b = 0; b < nb; ++b) fn(b); return; }
+  std::atomic<int> next{0};
+  std::exception_ptr err; std::mutex mu;
+  auto work = [&] {
+    for (int b; (b = next.fetch_add(1)) < nb;) {
+      try { fn(b); } catch (...) { std::lock_guard<std::mutex> g(mu); if (!err) err = std::current_exception(); }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nt; ++t) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+  if (err) std::rethrow_exception(err);
+}
+}  // namespace
+
+void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, const double* d_sigma_node,
+                           const BatchDims& bd, std::vector<DesignEig>& des, int ncv, int maxiter, int refine_steps,
+                           const double* d_v0, DevBuf<double>& X, EigenResult& res) {
+  const int B = bd.nb;
+  const int64_t m = bd.moff[B], ld = m;
+  const int64_t* moff = bd.d_moff.p;
   cudaStream_t st = ctx->stream;
-  const int ncvp = std::max(((std::max(ncv, k + P) + P - 1) / P) * P, 2 * P);
-  const int ldh = ncvp + P;
+  int kmax = 0;
+  for (const DesignEig& d : des) kmax = std::max(kmax, d.k);
+  const int ncvp = std::max(((std::max(ncv, kmax + P) + P - 1) / P) * P, 2 * P);
+  for (int b = 0; b < B; ++b)
+    if (bd.moff[b + 1] - bd.moff[b] < ncvp + P) throw StatusError(PLFEM_ERR_INVALID, "a design of the batch is smaller than the Lanczos basis");
+  const int ldh = ncvp + P, nslots = ncvp / P + 1;
+  const int64_t hstride = (int64_t)ldh * P, sstride = (int64_t)ldh * ncvp;
   DevBuf<double> V[2], BV[2], R, U, rt, rdx, opin, h1, h2, Hs, G, Lall, Linv, Sdev;
+  DevBuf<int32_t> cstat;
   for (int b = 0; b < 2; ++b) { V[b].alloc(ctx, (size_t)ld * (ncvp + P)); BV[b].alloc(ctx, (size_t)ld * (ncvp + P)); }
   R.alloc(ctx, (size_t)m * P); U.alloc(ctx, (size_t)m * P); rt.alloc(ctx, (size_t)m * P); rdx.alloc(ctx, (size_t)m * P);
   opin.alloc(ctx, (size_t)m * P);
-  h1.alloc(ctx, (size_t)ldh * P); h2.alloc(ctx, (size_t)ldh * P); Hs.alloc(ctx, (size_t)ldh * ncvp);
-  G.alloc(ctx, P * P); Lall.alloc(ctx, (size_t)(ncvp / P + 1) * P * P); Linv.alloc(ctx, P * P);
+  h1.alloc(ctx, (size_t)B * hstride); h2.alloc(ctx, (size_t)B * hstride); Hs.alloc(ctx, (size_t)B * sstride);
+  G.alloc(ctx, (size_t)B * P * P); Lall.alloc(ctx, (size_t)B * nslots * P * P); Linv.alloc(ctx, (size_t)B * P * P);
   Sdev.alloc(ctx, (size_t)ncvp * ncvp);
+  cstat.alloc(ctx, B); cstat.zero();
   const unsigned gm = (unsigned)((m + 255) / 256);
+  const dim3 grows((unsigned)((bd.mmax + 255) / 256), B);
 
   // operator application on P right-hand sides, captured once into a CUDA graph: R = OP(opin)
   cudaGraph_t graph = nullptr; cudaGraphExec_t gexec = nullptr; int graph_nodes = 0;
@@ -635,7 +700,7 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
     try {
       run_solve(ctx, D, opin.p, R.p, P, ld);
       for (int it = 0; it < refine_steps; ++it) {
-        launch_resid_k(ctx, pat, d_vals, sigma, R.p, opin.p, rt.p, P, ld);
+        launch_resid_k(ctx, pat, d_vals, d_sigma_node, R.p, opin.p, rt.p, P, ld);
         run_solve(ctx, D, rt.p, rdx.p, P, ld);
         launch_axpy(ctx, R.p, rdx.p, m * P);
       }
@@ -649,30 +714,41 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
   }
   struct GraphGuard { cudaGraph_t g; cudaGraphExec_t e; ~GraphGuard() { if (e) cudaGraphExecDestroy(e); if (g) cudaGraphDestroy(g); } } guard{graph, gexec};
 
-  // B-orthonormalise the block in R: U = B R, G = R^T U = L L^T, Vn = R L^-T, BVn = U L^-T; L kept in slot `slot`
+  // B-orthonormalise the block in R, per design: U = B R, G = R^T U = L L^T, Vn = R L^-T, BVn = U L^-T; L kept in slot `slot`
   auto orthonormalize = [&](double* Vn, double* BVn, int slot) {
     launch_spmm_b(ctx, pat, d_vals, R.p, U.p, P, ld);
-    gram_kernel<<<P, RED_T, 0, st>>>(R.p, U.p, ld, m, G.p);
-    chol_kernel<<<1, 32, 0, st>>>(G.p, Lall.p + (size_t)slot * P * P, Linv.p, D.status.p);
-    scale_block_kernel<<<gm, 256, 0, st>>>(R.p, U.p, ld, m, Linv.p, Vn, BVn);
+    gram_kernel<<<dim3(P, B), RED_T, 0, st>>>(R.p, U.p, ld, moff, G.p);
+    chol_kernel<<<B, 32, 0, st>>>(G.p, Lall.p, nslots, slot, Linv.p, cstat.p);
+    scale_block_kernel<<<grows, 256, 0, st>>>(R.p, U.p, ld, moff, Linv.p, Vn, BVn);
     ctx->launches += 3;
   };
 
   // start block: column 0 = v0 (or ones), the others deterministic pseudo-random
   if (d_v0) PLFEM_CUDA(cudaMemcpyAsync(R.p, d_v0, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
   else { fill_kernel<<<gm, 256, 0, st>>>(R.p, m, 1.0); ctx->launches++; }
-  start_block_kernel<<<gm, 256, 0, st>>>(R.p, ld, m);
+  start_block_kernel<<<grows, 256, 0, st>>>(R.p, ld, moff);
   ctx->launches++;
   int cur = 0;
   orthonormalize(V[cur].p, BV[cur].p, ncvp / P);     // scratch slot
 
-  std::vector<double> Th((size_t)ncvp * ncvp, 0.0), Hh((size_t)ldh * ncvp), Lh((size_t)(ncvp / P + 1) * P * P), T, w;
-  std::vector<int> order;
+  struct Host {                      // per-design host state of the projected problem
+    std::vector<double> Th, T, w, S;
+    std::vector<int> order;
+    bool done = false, newly = false;
+    int q_want = 0;
+  };
+  std::vector<Host> hs(B);
+  for (Host& h : hs) h.Th.assign((size_t)ncvp * ncvp, 0.0);
+  std::vector<double> Hh((size_t)B * sstride), Lh((size_t)B * nslots * P * P);
+  std::vector<int32_t> cs(B, 0);
   int nb = P, q = 0;                 // basis vectors present; kept Ritz vectors (their block of Th is diagonal)
+  int ndone = 0;
   res = EigenResult();
+  X.alloc(ctx, (size_t)m * kmax);
   const double eps23 = std::pow(2.220446049250313e-16, 2.0 / 3.0);
-  const int check_from = std::min(ncvp, ((2 * k + P - 1) / P) * P), check_every = 2;
+  const int check_every = 2;
   int since_check = 0;
+  auto check_from = [&](int k) { return std::min(ncvp, ((2 * k + P - 1) / P) * P); };
   for (;;) {
     // ---- one block step: image of the last P basis vectors
     const int j0 = nb - P;
@@ -681,111 +757,150 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
     PLFEM_CUDA(cudaGraphLaunch(gexec, st));
     ctx->launches += graph_nodes;
     res.n_op += P; res.n_block_op++;
-    dots_block_kernel<<<nb, RED_T, 0, st>>>(BVc, ld, R.p, m, h1.p, ldh);
-    update_block_kernel<<<gm, 256, 0, st>>>(Vc, ld, h1.p, ldh, nb, m, R.p);
-    dots_block_kernel<<<nb, RED_T, 0, st>>>(BVc, ld, R.p, m, h2.p, ldh);
-    update_block_kernel<<<gm, 256, 0, st>>>(Vc, ld, h2.p, ldh, nb, m, R.p);
-    store_h_kernel<<<(nb + 127) / 128, 128, 0, st>>>(h1.p, h2.p, ldh, nb, Hs.p + (size_t)j0 * ldh, ldh);
+    dots_block_kernel<<<dim3(nb, B), RED_T, 0, st>>>(BVc, ld, R.p, moff, h1.p, ldh, hstride);
+    update_block_kernel<<<grows, 256, 0, st>>>(Vc, ld, h1.p, ldh, hstride, nb, moff, R.p);
+    dots_block_kernel<<<dim3(nb, B), RED_T, 0, st>>>(BVc, ld, R.p, moff, h2.p, ldh, hstride);
+    update_block_kernel<<<grows, 256, 0, st>>>(Vc, ld, h2.p, ldh, hstride, nb, moff, R.p);
+    store_h_kernel<<<dim3((nb + 127) / 128, B), 128, 0, st>>>(h1.p, h2.p, ldh, hstride, nb, Hs.p + (size_t)j0 * ldh, ldh, sstride);
     ctx->launches += 5;
     orthonormalize(Vc + (int64_t)nb * ld, BVc + (int64_t)nb * ld, j0 / P);
     nb += P;
     ++since_check;
     const int c = nb - P;            // basis vectors whose images are known
     const bool full = (c >= ncvp);
-    if (!full && !(c >= check_from && since_check >= check_every)) continue;
+    bool due = false;
+    for (int b = 0; b < B; ++b) if (!hs[b].done && c >= check_from(des[b].k)) due = true;
+    if (!full && !(due && since_check >= check_every)) continue;
     since_check = 0;
 
-    // ---- convergence check on the c x c projected matrix
+    // ---- convergence check on the c x c projected matrix of every unfinished design
     PLFEM_CUDA(cudaGetLastError());
     Hs.download(Hh.data(), Hh.size());
     Lall.download(Lh.data(), Lh.size());
-    int32_t fstat[4];
-    D.status.download(fstat, 4);
+    cstat.download(cs.data(), B);
     PLFEM_CUDA(cudaStreamSynchronize(st));
-    if (fstat[2]) throw StatusError(PLFEM_ERR_SINGULAR, "block Lanczos: the residual block lost rank (Cholesky breakdown)");
-    for (int j = q; j < c; ++j)
-      for (int i = 0; i <= j; ++i) Th[(size_t)j * ncvp + i] = Hh[(size_t)j * ldh + i];
-    T.assign((size_t)c * c, 0.0);
-    for (int j = 0; j < c; ++j)
-      for (int i = 0; i <= j; ++i) T[(size_t)j * c + i] = T[(size_t)i * c + j] = Th[(size_t)j * ncvp + i];
-    for (double v : T) if (!std::isfinite(v)) throw StatusError(PLFEM_ERR_SINGULAR, "Lanczos recurrence produced a non-finite value (shifted operator singular?)");
-    symmetric_eigen(c, T, w);        // T now holds eigenvectors in columns
-    order.resize(c);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return std::fabs(w[a]) > std::fabs(w[b]); });
-    const double* L = Lh.data() + (size_t)((c - P) / P) * P * P;     // R_last = V_next L^T
-    auto bound = [&](int col) {
-      double s2 = 0.0;
-      for (int a = 0; a < P; ++a) {
-        double t = 0.0;
-        for (int b = a; b < P; ++b) t += L[b + a * P] * T[(size_t)col * c + (c - P + b)];
-        s2 += t * t;
+    const bool last_chance = full && res.n_restart >= maxiter;
+    for_each_design(B, [&](int b) {
+      Host& h = hs[b]; DesignEig& de = des[b];
+      h.newly = false;
+      if (h.done) return;
+      if (cs[b]) {
+        de.status = PLFEM_ERR_SINGULAR; de.err = "block Lanczos: the residual block lost rank (Cholesky breakdown)";
+        h.done = true; return;
       }
-      return std::sqrt(s2);
-    };
-    int nconv = 0;
-    for (int i = 0; i < k; ++i) if (bound(order[i]) <= tol * std::max(eps23, std::fabs(w[order[i]]))) nconv++;
-    res.nconv = nconv;
-    const bool done = nconv >= k;
-    if (done || (full && res.n_restart >= maxiter)) {
-      std::vector<int> sel(order.begin(), order.begin() + k);
-      std::sort(sel.begin(), sel.end(), [&](int a, int b) { return sigma + 1.0 / w[a] < sigma + 1.0 / w[b]; });
-      std::vector<double> S((size_t)c * k);
-      lambda.resize(k); res.theta.resize(k);
-      for (int i = 0; i < k; ++i) {
-        std::copy(T.begin() + (size_t)sel[i] * c, T.begin() + (size_t)(sel[i] + 1) * c, S.begin() + (size_t)i * c);
-        res.theta[i] = w[sel[i]];
-        lambda[i] = sigma + 1.0 / w[sel[i]];
+      const double* Hb = Hh.data() + (size_t)b * sstride;
+      for (int j = q; j < c; ++j)
+        for (int i = 0; i <= j; ++i) h.Th[(size_t)j * ncvp + i] = Hb[(size_t)j * ldh + i];
+      h.T.assign((size_t)c * c, 0.0);
+      for (int j = 0; j < c; ++j)
+        for (int i = 0; i <= j; ++i) h.T[(size_t)j * c + i] = h.T[(size_t)i * c + j] = h.Th[(size_t)j * ncvp + i];
+      for (double v : h.T)
+        if (!std::isfinite(v)) {
+          de.status = PLFEM_ERR_SINGULAR; de.err = "Lanczos recurrence produced a non-finite value (shifted operator singular?)";
+          h.done = true; return;
+        }
+      symmetric_eigen(c, h.T, h.w);        // T now holds eigenvectors in columns
+      h.order.resize(c);
+      std::iota(h.order.begin(), h.order.end(), 0);
+      std::stable_sort(h.order.begin(), h.order.end(), [&](int a, int bb) { return std::fabs(h.w[a]) > std::fabs(h.w[bb]); });
+      const double* L = Lh.data() + ((size_t)b * nslots + (c - P) / P) * P * P;     // R_last = V_next L^T
+      auto bound = [&](int col) {
+        double s2 = 0.0;
+        for (int a = 0; a < P; ++a) {
+          double t = 0.0;
+          for (int bb = a; bb < P; ++bb) t += L[bb + a * P] * h.T[(size_t)col * c + (c - P + bb)];
+          s2 += t * t;
+        }
+        return std::sqrt(s2);
+      };
+      const int k = de.k;
+      int nconv = 0;
+      for (int i = 0; i < k; ++i) if (bound(h.order[i]) <= de.tol * std::max(eps23, std::fabs(h.w[h.order[i]]))) nconv++;
+      de.nconv = nconv;
+      if (nconv >= k || last_chance) {
+        std::vector<int> sel(h.order.begin(), h.order.begin() + k);
+        std::sort(sel.begin(), sel.end(), [&](int a, int bb) { return de.sigma + 1.0 / h.w[a] < de.sigma + 1.0 / h.w[bb]; });
+        h.S.assign((size_t)c * k, 0.0);
+        de.lambda.resize(k); de.theta.resize(k);
+        for (int i = 0; i < k; ++i) {
+          std::copy(h.T.begin() + (size_t)sel[i] * c, h.T.begin() + (size_t)(sel[i] + 1) * c, h.S.begin() + (size_t)i * c);
+          de.theta[i] = h.w[sel[i]];
+          de.lambda[i] = de.sigma + 1.0 / h.w[sel[i]];
+        }
+        de.n_block_op = res.n_block_op; de.n_restart = res.n_restart;
+        if (nconv < k) {
+          de.status = PLFEM_ERR_NO_CONVERGENCE;
+          de.err = "block Lanczos: " + std::to_string(nconv) + " of " + std::to_string(k) + " eigenpairs converged after " + std::to_string(res.n_restart) + " restarts";
+        }
+        h.done = true; h.newly = true;
+      } else if (full) {
+        // thick restart: this design wants its q best Ritz vectors (q = ncvp - P*t so that whole blocks fit again)
+        const int keep = k + std::min(nconv, (ncvp - k) / 2);
+        const int t = std::max(1, (ncvp - keep) / P);
+        h.q_want = ncvp - P * t;
+      }
+    });
+    // eigenvectors of the designs that just finished: X_b = V_b S_b
+    for (int b = 0; b < B; ++b) {
+      if (!hs[b].newly) continue;
+      const int k = des[b].k;
+      PLFEM_CUDA(cudaMemcpyAsync(Sdev.p, hs[b].S.data(), hs[b].S.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+      const int64_t mb = bd.moff[b + 1] - bd.moff[b];
+      rotate_kernel<<<(unsigned)((mb + 127) / 128), 128, 0, st>>>(V[cur].p + bd.moff[b], ld, c, Sdev.p, k, mb, X.p + bd.moff[b], m);
+      ctx->launches++;
+      PLFEM_CUDA(cudaStreamSynchronize(st));   // Sdev is reused by the next design
+    }
+    ndone = 0;
+    for (const Host& h : hs) ndone += h.done;
+    if (ndone == B) return;
+    if (!full) continue;
+    // ---- thick restart, all designs together: the largest q any unfinished design asks for
+    q = 0;
+    for (int b = 0; b < B; ++b) if (!hs[b].done) q = std::max(q, hs[b].q_want);
+    const int nxt = cur ^ 1;
+    for (int b = 0; b < B; ++b) {
+      Host& h = hs[b];
+      std::vector<double> S((size_t)ncvp * q, 0.0);
+      if (h.done) {
+        for (int i = 0; i < q; ++i) S[(size_t)i * ncvp + i] = 1.0;        // finished: carried along, values stay finite
+      } else {
+        std::fill(h.Th.begin(), h.Th.end(), 0.0);
+        for (int i = 0; i < q; ++i) {
+          const int col = h.order[i];
+          std::copy(h.T.begin() + (size_t)col * ncvp, h.T.begin() + (size_t)(col + 1) * ncvp, S.begin() + (size_t)i * ncvp);
+          h.Th[(size_t)i * ncvp + i] = h.w[col];
+        }
       }
       PLFEM_CUDA(cudaMemcpyAsync(Sdev.p, S.data(), S.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-      X.alloc(ctx, (size_t)m * k);
-      rotate_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(V[cur].p, ld, c, Sdev.p, k, m, X.p, m);
-      ctx->launches++;
-      PLFEM_CUDA(cudaStreamSynchronize(st));
-      if (!done) throw StatusError(PLFEM_ERR_NO_CONVERGENCE, "block Lanczos: " + std::to_string(nconv) + " of " + std::to_string(k) + " eigenpairs converged after " + std::to_string(res.n_restart) + " restarts");
-      return;
+      const int64_t mb = bd.moff[b + 1] - bd.moff[b], o = bd.moff[b];
+      rotate_kernel<<<(unsigned)((mb + 127) / 128), 128, 0, st>>>(V[cur].p + o, ld, ncvp, Sdev.p, q, mb, V[nxt].p + o, ld);
+      rotate_kernel<<<(unsigned)((mb + 127) / 128), 128, 0, st>>>(BV[cur].p + o, ld, ncvp, Sdev.p, q, mb, BV[nxt].p + o, ld);
+      ctx->launches += 2;
+      PLFEM_CUDA(cudaStreamSynchronize(st));   // S is a local host buffer, Sdev is reused
     }
-    if (!full) continue;
-    // ---- thick restart: keep the q best Ritz vectors (q = ncvp - P*t so that whole blocks fit again)
-    const int keep = k + std::min(nconv, (ncvp - k) / 2);
-    const int t = std::max(1, (ncvp - keep) / P);
-    q = ncvp - P * t;
-    std::vector<double> S((size_t)ncvp * q);
-    std::fill(Th.begin(), Th.end(), 0.0);
-    for (int i = 0; i < q; ++i) {
-      const int col = order[i];
-      std::copy(T.begin() + (size_t)col * ncvp, T.begin() + (size_t)(col + 1) * ncvp, S.begin() + (size_t)i * ncvp);
-      Th[(size_t)i * ncvp + i] = w[col];
-    }
-    PLFEM_CUDA(cudaMemcpyAsync(Sdev.p, S.data(), S.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-    const int nxt = cur ^ 1;
-    rotate_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(V[cur].p, ld, ncvp, Sdev.p, q, m, V[nxt].p, ld);
-    rotate_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(BV[cur].p, ld, ncvp, Sdev.p, q, m, BV[nxt].p, ld);
     PLFEM_CUDA(cudaMemcpyAsync(V[nxt].p + (int64_t)q * ld, V[cur].p + (int64_t)ncvp * ld, (size_t)m * P * sizeof(double), cudaMemcpyDeviceToDevice, st));
     PLFEM_CUDA(cudaMemcpyAsync(BV[nxt].p + (int64_t)q * ld, BV[cur].p + (int64_t)ncvp * ld, (size_t)m * P * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    ctx->launches += 2;
-    PLFEM_CUDA(cudaStreamSynchronize(st));   // S is a local host buffer
     cur = nxt; nb = q + P;
     res.n_restart++;
   }
 }
 
+// per-mode reductions of ONE design of the forest: rows [row0, row0 + n) of the concatenated pattern / vectors
 void run_mode_metrics(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, const int32_t* d_perm_to_interior,
-                      const uint8_t* d_in_core, const double* X, const std::vector<double>& lambda, int k,
-                      double* d_out_evecs, double* d_metrics, double* d_resid) {
+                      const uint8_t* d_in_core, const double* X, int64_t ldx, int32_t row0, int32_t n,
+                      const std::vector<double>& lambda, int k, double* d_out_evecs, double* d_metrics, double* d_resid) {
   cudaStream_t st = ctx->stream;
-  const int n = pat.n;
   const int nchunks = (n + MROWS - 1) / MROWS;
   DevBuf<double> part, lam, scale;
   part.alloc(ctx, (size_t)k * nchunks * NRED);
   lam.upload(ctx, lambda.data(), k);
   scale.alloc(ctx, k);
-  mode_partial_kernel<<<dim3(nchunks, k), 256, 0, st>>>(n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz, d_in_core,
-                                                        (const double2*)X, (int64_t)n, lam.p, part.p, nchunks);
+  mode_partial_kernel<<<dim3(nchunks, k), 256, 0, st>>>(row0, row0 + n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz, d_in_core,
+                                                        (const double2*)X, ldx / 2, lam.p, part.p, nchunks);
   mode_final_kernel<<<(k + 63) / 64, 64, 0, st>>>(part.p, nchunks, k, lam.p, d_metrics, d_resid, scale.p);
   ctx->launches += 2;
   if (d_out_evecs) {
-    write_evecs_kernel<<<dim3((n + 255) / 256, k), 256, 0, st>>>(n, d_perm_to_interior, (const double2*)X, (int64_t)n,
+    write_evecs_kernel<<<dim3((n + 255) / 256, k), 256, 0, st>>>(row0, n, d_perm_to_interior, (const double2*)X, ldx / 2,
                                                                  scale.p, d_out_evecs);
     ctx->launches++;
   }

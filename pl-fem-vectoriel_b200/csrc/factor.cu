@@ -42,7 +42,7 @@ __device__ __forceinline__ int front_u(const PlanView& P, int f) { return P.sptr
 // ---- load (A - sigma B) into the fronts: one thread per structural non-zero ---------------------------
 __global__ void front_load_kernel(int64_t nnz, const int32_t* __restrict__ rowidx, const int32_t* __restrict__ col,
                                   const int32_t* __restrict__ sn_of, PlanView P, const double* __restrict__ vals,
-                                  double sigma) {
+                                  const double* __restrict__ sigma_node) {
   const int64_t z = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (z >= nnz) return;
   const int32_t r = rowidx[z], c = col[z];
@@ -64,7 +64,7 @@ __global__ void front_load_kernel(int64_t nnz, const int32_t* __restrict__ rowid
   const int64_t ld = 2 * (int64_t)(s + front_u(P, f));
   double* F = P.pool + P.foff[f];
   const int64_t pr = r - f0;
-  const double b = sigma * vals[(int64_t)S_MINV * nnz + z];
+  const double b = sigma_node[r] * vals[(int64_t)S_MINV * nnz + z];   // one shift per design of the forest
   F[(2 * pc) * ld + 2 * pr] = vals[(int64_t)S_AXX * nnz + z] - b;
   F[(2 * pc + 1) * ld + 2 * pr] = vals[(int64_t)S_AXY * nnz + z];
   F[(2 * pc) * ld + 2 * pr + 1] = vals[(int64_t)S_AYX * nnz + z];
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(1024) invert_kernel(const int32_t* __restrict_
       }
       if (tid == 0) {
         s_p = bi; piv[k] = bi;
-        if (!(best > 0.0) || !isfinite(best)) atomicExch(status, 1);
+        if (!(best > 0.0) || !isfinite(best)) { atomicExch(status, 1); atomicExch(status + 3, f); }
       }
     }
     __syncthreads();
@@ -500,7 +500,7 @@ struct OpArgs {
   const double* b; double* x; double* upd;   // b and x: length 2n, permuted interleaved layout
   double* rt; double* rdx;                    // refinement work vectors
   int refine;
-  int32_t n; const int32_t* rowptr; const int32_t* col; const double* vals; int64_t nnz; double sigma;
+  int32_t n; const int32_t* rowptr; const int32_t* col; const double* vals; int64_t nnz; const double* sigma_node;
 };
 
 __device__ __forceinline__ void sweep_dataflow(const OpArgs& a, const double* rhs, double* out, int epoch, SweepSmem<1>& sm) {
@@ -536,8 +536,9 @@ __global__ void __launch_bounds__(256) op_kernel(OpArgs a) {
       const int lane = (int)(gid & 3);
       double ax = 0.0, ay = 0.0;
       if (row < a.n) {
+        const double sig = a.sigma_node[row];
         for (int32_t z = a.rowptr[row] + lane; z < a.rowptr[row + 1]; z += 4) {
-          const double smv = a.sigma * a.vals[(int64_t)S_MINV * a.nnz + z];
+          const double smv = sig * a.vals[(int64_t)S_MINV * a.nnz + z];
           const double* xp = a.x + 2 * (int64_t)a.col[z];
           const double vx = __ldcg(xp), vy = __ldcg(xp + 1);
           ax = fma(a.vals[(int64_t)S_AXX * a.nnz + z] - smv, vx, ax);
@@ -671,7 +672,7 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
   PLFEM_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
-void launch_front_load(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, double sigma) {
+void launch_front_load(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, const double* d_sigma_node) {
   PLFEM_CUDA(cudaMemsetAsync(D.pool.p, 0, D.pool.n * sizeof(double), ctx->stream));
   PLFEM_CUDA(cudaMemsetAsync(D.status.p, 0, 4 * sizeof(int32_t), ctx->stream));
   PLFEM_CUDA(cudaMemsetAsync(D.fdone.p, 0, D.fdone.n * sizeof(int32_t), ctx->stream));
@@ -679,7 +680,7 @@ void launch_front_load(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const 
   D.epoch = 0;
   const int bs = 256;
   front_load_kernel<<<(unsigned)((pat.nnz + bs - 1) / bs), bs, 0, ctx->stream>>>(pat.nnz, pat.rowidx.p, pat.col.p,
-                                                                                 D.sn_of.p, view(D), d_vals, sigma);
+                                                                                 D.sn_of.p, view(D), d_vals, d_sigma_node);
   PLFEM_CUDA(cudaGetLastError());
   ctx->launches++;
 }
@@ -777,7 +778,7 @@ int op_grid_size(plfem_ctx* ctx, int ctas_per_sm) {
 }
 
 // x = (A - sigma B)^-1 b with `refine` refinement steps, one cooperative launch (b, x, rt, rdx distinct)
-void run_operator(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, double sigma, const double* b,
+void run_operator(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, const double* d_sigma_node, const double* b,
                   double* x, double* rt, double* rdx, int refine, int ctas_per_sm) {
   OpArgs a;
   a.P = view(D);
@@ -785,7 +786,7 @@ void run_operator(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const doubl
   a.fdone = D.fdone.p; a.bdone = D.bdone.p; a.status = D.status.p; a.nfs = D.nfs.p;
   a.epoch0 = D.epoch; D.epoch += 1 + refine;
   a.b = b; a.x = x; a.upd = D.upd.p; a.rt = rt; a.rdx = rdx; a.refine = refine;
-  a.n = pat.n; a.rowptr = pat.rowptr.p; a.col = pat.col.p; a.vals = d_vals; a.nnz = pat.nnz; a.sigma = sigma;
+  a.n = pat.n; a.rowptr = pat.rowptr.p; a.col = pat.col.p; a.vals = d_vals; a.nnz = pat.nnz; a.sigma_node = d_sigma_node;
   void* args[] = {&a};
   PLFEM_CUDA(cudaLaunchCooperativeKernel((const void*)op_kernel, dim3(op_grid_size(ctx, ctas_per_sm)), dim3(256), args, 0, ctx->stream));
   ctx->launches++;

@@ -113,8 +113,10 @@ void build_dof_tables(const double* p, const int64_t* t, int64_t V, int64_t T, D
 
 namespace {
 std::atomic<int> g_host_threads{0};
+thread_local int tl_host_threads = 0;   // per-thread override: a forest analyses its designs on separate threads
 
 int host_threads() {
+  if (tl_host_threads > 0) return tl_host_threads;
   const int set = g_host_threads.load(std::memory_order_relaxed);
   if (set > 0) return set;
   static const int n = [] {
@@ -142,6 +144,7 @@ void parallel_for(int64_t n, int64_t grain, F&& fn) {
 // Sparsity pattern in an arbitrary renumbering
 // ------------------------------------------------------------------------------------------------
 void set_host_threads(int n) { g_host_threads.store(std::max(0, n)); }
+void set_host_threads_local(int n) { tl_host_threads = std::max(0, n); }
 
 void build_pattern(const DofTables& d, const std::vector<int32_t>& new_of_old, int32_t n_new, Pattern& out) {
   out.n = n_new;
@@ -548,6 +551,76 @@ void build_front_plan(const Pattern& adj, const double* x, const double* y, cons
   {
     std::vector<int32_t> fill(P.lptr.begin(), P.lptr.end() - 1);
     for (int32_t f = 0; f < nf; ++f) P.lfront[fill[P.level[f]]++] = f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forest batching: several designs as one block-diagonal problem
+// ------------------------------------------------------------------------------------------------
+void merge_front_plans(const std::vector<const FrontPlan*>& parts, FrontPlan& M, std::vector<int32_t>& node_off,
+                       std::vector<int32_t>& front_off) {
+  const int nb = (int)parts.size();
+  M = FrontPlan();
+  node_off.assign(nb + 1, 0); front_off.assign(nb + 1, 0);
+  int64_t n_tot = 0, nf_tot = 0, ns_tot = 0, nc_tot = 0, nch_tot = 0;
+  for (int b = 0; b < nb; ++b) {
+    const FrontPlan& P = *parts[b];
+    n_tot += P.n; nf_tot += P.nfronts; ns_tot += (int64_t)P.strct.size(); nc_tot += (int64_t)P.cmap.size(); nch_tot += (int64_t)P.child.size();
+    node_off[b + 1] = (int32_t)n_tot; front_off[b + 1] = (int32_t)nf_tot;
+    M.nlevels = std::max(M.nlevels, P.nlevels);
+    M.max_front = std::max(M.max_front, P.max_front); M.max_s = std::max(M.max_s, P.max_s);
+    M.factor_entries += P.factor_entries; M.factor_flops += P.factor_flops;
+  }
+  if (n_tot >= (int64_t(1) << 30) || ns_tot >= (int64_t(1) << 30)) throw std::runtime_error("batch too large for 32-bit plan indices");
+  M.n = (int32_t)n_tot; M.nfronts = (int32_t)nf_tot;
+  M.perm.reserve(n_tot); M.sn_of.reserve(n_tot);
+  M.first.reserve(nf_tot); M.s.reserve(nf_tot); M.parent.reserve(nf_tot); M.level.reserve(nf_tot);
+  M.sptr.assign(1, 0); M.cptr.assign(1, 0); M.cmap_ptr.assign(1, 0); M.foff.assign(1, 0);
+  M.sptr.reserve(nf_tot + 1); M.cptr.reserve(nf_tot + 1); M.cmap_ptr.reserve(nf_tot + 1); M.foff.reserve(nf_tot + 1);
+  M.strct.reserve(ns_tot); M.cmap.reserve(nc_tot); M.child.reserve(nch_tot);
+  for (int b = 0; b < nb; ++b) {
+    const FrontPlan& P = *parts[b];
+    const int32_t no = node_off[b], fo = front_off[b];
+    const int32_t so = M.sptr.back(), co = M.cptr.back(), mo = M.cmap_ptr.back();
+    const int64_t po = M.foff.back();
+    M.perm.insert(M.perm.end(), P.perm.begin(), P.perm.end());
+    for (int32_t v : P.sn_of) M.sn_of.push_back(v + fo);
+    for (int32_t f = 0; f < P.nfronts; ++f) {
+      M.first.push_back(P.first[f] + no); M.s.push_back(P.s[f]);
+      M.parent.push_back(P.parent[f] >= 0 ? P.parent[f] + fo : -1); M.level.push_back(P.level[f]);
+      M.sptr.push_back(P.sptr[f + 1] + so); M.cptr.push_back(P.cptr[f + 1] + co);
+      M.cmap_ptr.push_back(P.cmap_ptr[f + 1] + mo); M.foff.push_back(P.foff[f + 1] + po);
+    }
+    for (int32_t v : P.strct) M.strct.push_back(v + no);
+    for (int32_t v : P.child) M.child.push_back(v + fo);
+    M.cmap.insert(M.cmap.end(), P.cmap.begin(), P.cmap.end());
+  }
+  M.lptr.assign(M.nlevels + 1, 0);
+  for (int32_t f = 0; f < M.nfronts; ++f) M.lptr[M.level[f] + 1]++;
+  for (int32_t l = 0; l < M.nlevels; ++l) M.lptr[l + 1] += M.lptr[l];
+  M.lfront.resize(M.nfronts);
+  std::vector<int32_t> fill(M.lptr.begin(), M.lptr.end() - 1);
+  for (int32_t f = 0; f < M.nfronts; ++f) M.lfront[fill[M.level[f]]++] = f;
+}
+
+void merge_patterns(const std::vector<const Pattern*>& parts, Pattern& M, std::vector<int64_t>& nnz_off) {
+  const int nb = (int)parts.size();
+  M = Pattern();
+  nnz_off.assign(nb + 1, 0);
+  int64_t n_tot = 0;
+  for (int b = 0; b < nb; ++b) { n_tot += parts[b]->n; nnz_off[b + 1] = nnz_off[b] + (int64_t)parts[b]->col.size(); }
+  if (nnz_off[nb] >= (int64_t(1) << 31) || n_tot >= (int64_t(1) << 30)) throw std::runtime_error("batch too large for 32-bit pattern indices");
+  M.n = (int32_t)n_tot;
+  M.rowptr.assign(1, 0); M.rowptr.reserve(n_tot + 1);
+  M.col.reserve(nnz_off[nb]); M.old_of_new.reserve(n_tot);
+  int32_t no = 0;
+  for (int b = 0; b < nb; ++b) {
+    const Pattern& P = *parts[b];
+    const int32_t zo = (int32_t)nnz_off[b];
+    for (int32_t r = 0; r < P.n; ++r) M.rowptr.push_back(P.rowptr[r + 1] + zo);
+    for (int32_t c : P.col) M.col.push_back(c + no);
+    M.old_of_new.insert(M.old_of_new.end(), P.old_of_new.begin(), P.old_of_new.end());
+    no += P.n;
   }
 }
 

@@ -43,6 +43,8 @@ void relabel_pattern(const Pattern& src, const std::vector<int32_t>& old_of, con
 
 // worker threads the symbolic phase may use per call (0 = default: min(cores, 8) or $PLFEM_HOST_THREADS)
 void set_host_threads(int n);
+// the same for the calling thread only (0 = follow the global setting)
+void set_host_threads_local(int n);
 
 struct SymbolicOptions {
   int leaf_nodes = 24;   // stop dissecting below this many nodes
@@ -76,5 +78,13 @@ struct FrontPlan {
 
 // adjacency = pattern of interior nodes in *interior index* numbering (identity order over DofTables::interior)
 void build_front_plan(const Pattern& adj, const double* x, const double* y, const SymbolicOptions& opt, FrontPlan& out);
+
+// Forest of several independent designs as ONE plan / ONE block-diagonal pattern: node ids, front ids and all
+// offsets of design b are shifted behind those of designs 0..b-1; level l of the result is the union of the
+// designs' levels l.  node_off / front_off get nb+1 entries.  `perm` of the result keeps each design's LOCAL
+// interior indices, `old_of_new` of the merged pattern each design's LOCAL DOF ids.
+void merge_front_plans(const std::vector<const FrontPlan*>& parts, FrontPlan& out, std::vector<int32_t>& node_off,
+                       std::vector<int32_t>& front_off);
+void merge_patterns(const std::vector<const Pattern*>& parts, Pattern& out, std::vector<int64_t>& nnz_off);
 
 }  // namespace plfem

@@ -95,6 +95,46 @@ def _polarization_label(P_x: float, P_y: float):
     return pol, PDL
 
 
+def modes_from_solution(geo, N_solve: int, beta_sq, evecs, met, n_core_dofs: int):
+    """Window filter, per-mode records, divergence / radiation filters and sort (`solver_fem.py:200-239`) from
+    the eigenvalues, the l2-normalised eigenvectors (may be None: records then carry no DOF arrays) and the
+    (k, 8) reductions the device computed.  Returns (modes_guided, modes_raw, frac_core)."""
+    frac_core = n_core_dofs / N_solve
+    n_core, n_clad, k0 = geo.n_core, geo.n_clad, geo.k0
+    modes_raw = []
+    for i in range(len(beta_sq)):
+        b2 = beta_sq[i]
+        if b2 <= 0:
+            continue
+        beta = np.sqrt(b2)
+        ne = beta / k0
+        if ne <= n_clad or ne >= n_core * 1.01:
+            continue
+        div_energy, e_core, e_all, px_c, py_c, px_a, py_a, _ = met[i]
+        use_core = n_core_dofs > 0                       # `solver_fem.py:93`
+        P_x = float(px_c if use_core else px_a) + 1e-30
+        P_y = float(py_c if use_core else py_a) + 1e-30
+        pol, PDL_dB = _polarization_label(P_x, P_y)
+        conf = float(e_core / e_all)
+        modes_raw.append(ModeRecord({
+            "n_eff": float(ne), "beta": float(beta),
+            # rows of a buffer this solve owns (fresh per call, like the reference's eigsh output)
+            "Ex_dofs": evecs[i, :N_solve] if evecs is not None else None,
+            "Ey_dofs": evecs[i, N_solve:] if evecs is not None else None,
+            "P_x": P_x, "P_y": P_y, "PDL_dB": PDL_dB, "polarization": pol,
+            "confinement": conf, "core_overlap": conf,
+            "div_ratio": float(div_energy) / max(b2, 1e-12),
+            "is_vectorial": True, "method": "H-field_V18.10"}))
+
+    dr = np.array([m["div_ratio"] for m in modes_raw])
+    dr_thresh = max(np.median(dr) * 10, dr.min() * 50, 1e-6)      # raises on empty input, like the reference
+    modes_phys = [m for m in modes_raw if m["div_ratio"] <= dr_thresh]
+    conf_thr = max(5.0 * frac_core, 0.05)
+    modes_guided = [m for m in modes_phys if m["confinement"] >= conf_thr] or modes_phys
+    modes_guided.sort(key=lambda m: m["n_eff"], reverse=True)
+    return modes_guided, modes_raw, frac_core
+
+
 class TrueVectorialMaxwellSolver:
     def __init__(self, geometry, use_pml: bool = False, n_modes: Optional[int] = None,
                  device: int = 0, refinement: float = 1.0, config: Optional[SimulationConfig] = None, ctx=None):
@@ -154,38 +194,7 @@ class TrueVectorialMaxwellSolver:
         beta_sq, evecs, met, n_core_dofs, stats = pb.solve_modes(mat, sigma, n_req, tol=1e-7, maxiter=12000, v0=v0,
                                                                  **solver_opts)
         self.last_stats = stats.as_dict()
-        frac_core = n_core_dofs / N_solve
-
-        n_core, n_clad = geo.n_core, geo.n_clad
-        modes_raw = []
-        for i in range(len(beta_sq)):
-            b2 = beta_sq[i]
-            if b2 <= 0:
-                continue
-            beta = np.sqrt(b2)
-            ne = beta / self.k0
-            if ne <= n_clad or ne >= n_core * 1.01:
-                continue
-            div_energy, e_core, e_all, px_c, py_c, px_a, py_a, _ = met[i]
-            use_core = n_core_dofs > 0                       # `solver_fem.py:93`
-            P_x = float(px_c if use_core else px_a) + 1e-30
-            P_y = float(py_c if use_core else py_a) + 1e-30
-            pol, PDL_dB = _polarization_label(P_x, P_y)
-            conf = float(e_core / e_all)
-            modes_raw.append(ModeRecord({
-                "n_eff": float(ne), "beta": float(beta),
-                "Ex_dofs": evecs[i, :N_solve].copy(), "Ey_dofs": evecs[i, N_solve:].copy(),
-                "P_x": P_x, "P_y": P_y, "PDL_dB": PDL_dB, "polarization": pol,
-                "confinement": conf, "core_overlap": conf,
-                "div_ratio": float(div_energy) / max(b2, 1e-12),
-                "is_vectorial": True, "method": "H-field_V18.10"}))
-
-        dr = np.array([m["div_ratio"] for m in modes_raw])
-        dr_thresh = max(np.median(dr) * 10, dr.min() * 50, 1e-6)      # raises on empty input, like the reference
-        modes_phys = [m for m in modes_raw if m["div_ratio"] <= dr_thresh]
-        conf_thr = max(5.0 * frac_core, 0.05)
-        modes_guided = [m for m in modes_phys if m["confinement"] >= conf_thr] or modes_phys
-        modes_guided.sort(key=lambda m: m["n_eff"], reverse=True)
+        modes_guided, modes_raw, frac_core = modes_from_solution(geo, N_solve, beta_sq, evecs, met, n_core_dofs)
         if return_raw:
             return modes_guided, dict(beta_sq=beta_sq, evecs=evecs, metrics=met, sigma=sigma,
                                       modes_raw=modes_raw, frac_core=frac_core, stats=self.last_stats)

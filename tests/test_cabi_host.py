@@ -29,7 +29,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_cabi.MeshInfo) == 64
     assert ctypes.sizeof(_cabi.Material) == 64
     assert ctypes.sizeof(_cabi.SolveOpts) == 64
-    assert ctypes.sizeof(_cabi.SolveStats) == 88
+    assert ctypes.sizeof(_cabi.SolveStats) == 104
 
 
 def test_product_has_no_cpu_path(small_case):

@@ -231,3 +231,69 @@ def test_start_vector_and_determinism(small_case):
     n2 = 2 * (len(a[0]["Ex_dofs"]))
     c = s.solve_vectorial_modes(mesh, 4, v0=np.random.default_rng(5).uniform(-1, 1, n2))
     assert np.allclose([m["n_eff"] for m in a], [m["n_eff"] for m in c], rtol=1e-9)
+
+
+# ---- forest of designs: plfem_solve_modes_batch ----------------------------------------------------------------
+def _forest_jobs(small_case):
+    import plfem_b200 as P
+    g, mesh = small_case
+    g2 = P.MCFGeometry(3, 6.0, 1.2, P.IPDipCauchy.n(1490), 1.0, 1.49)          # same mesh recipe, another band
+    g3 = P.MCFGeometry(4, 5.0, 1.0, 1.53, 1.0, 1.55)                           # another layout, another mesh
+    mesh3, _ = P.MeshGenerator.generate(g3, refinement=0.4)
+    return [(g, mesh, 4), (g2, mesh, 4), (g3, mesh3, 6)]
+
+
+def test_forest_matches_single_solves(small_case):
+    """Designs solved together as one block-diagonal problem give what each gives alone."""
+    from plfem_b200.batch import ForestPool
+    jobs = _forest_jobs(small_case)
+    with ForestPool(batch=len(jobs), workers=1) as pool:
+        forest = pool.solve_forest(jobs, return_raw=True)
+        stats = pool.last_stats
+    assert all(s["batch_size"] == len(jobs) for s in stats)
+    assert len({s["kernel_launches"] for s in stats}) == 1              # the designs share every launch
+    for (g, mesh, n), (modes, raw) in zip(jobs, forest):
+        alone, araw = TrueVectorialMaxwellSolver(g).solve_vectorial_modes(mesh, n, return_raw=True)
+        assert raw["stats"]["nconv"] >= len(raw["beta_sq"]) and raw["stats"]["max_residual"] < 1e-9
+        assert np.abs(raw["beta_sq"] / araw["beta_sq"] - 1).max() < 1e-9   # lockstep may stop a step later: same pairs
+        assert len(modes) == len(alone)
+        for m, a in zip(modes, alone):
+            assert abs(m["n_eff"] / a["n_eff"] - 1) < 1e-9 and m["polarization"] == a["polarization"]
+            assert abs(m["confinement"] - a["confinement"]) < 1e-6
+
+
+def test_forest_of_identical_designs_is_bit_identical_to_single(small_case):
+    from plfem_b200.batch import ForestPool
+    g, mesh = small_case
+    alone, araw = TrueVectorialMaxwellSolver(g).solve_vectorial_modes(mesh, 4, return_raw=True)
+    with ForestPool(batch=3, workers=1) as pool:
+        forest = pool.solve_forest([(g, mesh, 4)] * 3, return_raw=True)
+    for modes, raw in forest:
+        assert np.array_equal(raw["beta_sq"], araw["beta_sq"])
+        assert np.array_equal(raw["evecs"], araw["evecs"]) and np.array_equal(raw["metrics"], araw["metrics"])
+
+
+def test_forest_matches_oracle_config1(cfg1):
+    """Two copies of config 1 at different bands in one forest, each against the oracle's eigsh."""
+    import plfem_b200 as P
+    from plfem_b200.batch import ForestPool
+    g, mesh = cfg1
+    g2 = P.MCFGeometry(7, 8.0, 1.5, P.IPDipCauchy.n(1600), 1.0, 1.60)
+    jobs = [(g, mesh, 10), (g2, mesh, 10)]
+    with ForestPool(batch=2, workers=1) as pool:
+        forest = pool.solve_forest(jobs, return_raw=True)
+    for (gg, mm, n), (modes, raw) in zip(jobs, forest):
+        rmodes, rraw = O.solve_vectorial_modes(gg, mm, n, return_raw=True)
+        assert np.abs(raw["beta_sq"] / rraw["beta_sq"] - 1).max() < 2e-8      # n_eff to 1e-8 relative
+        assert len(modes) == len(rmodes)
+
+
+def test_pool_solve_many_keeps_job_order(small_case):
+    from plfem_b200.batch import ForestPool
+    jobs = _forest_jobs(small_case) * 2
+    with ForestPool(batch=2, workers=2) as pool:
+        out = pool.solve_many(jobs)
+    assert len(out) == len(jobs)
+    for (g, mesh, n), modes in zip(jobs, out):
+        alone = TrueVectorialMaxwellSolver(g).solve_vectorial_modes(mesh, n)
+        assert [m["n_eff"] for m in modes] == pytest.approx([m["n_eff"] for m in alone], rel=1e-9)
