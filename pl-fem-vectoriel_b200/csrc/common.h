@@ -137,15 +137,30 @@ void launch_spmv_csr(plfem_ctx* ctx, int64_t rows, const int32_t* rowptr, const 
 // one forward work item: (front, slab of rows) with everything the kernel needs, so that no plan metadata
 // has to be chased through dependent loads on the critical path
 struct FwdItem {
-  int32_t f, row0, nrows, G, s2, ld;     // ld = 2nf = rows of the front
+  int32_t f, row0, nrows, G, s2, ld;     // ld = leading dimension of the front's packed left block column
   int32_t ch0, ch1, tgt0, tgt1;          // first two children and the number of forward items each must complete
-  int32_t uoff, goff, nchild, tgtx;      // update-vector offset, gather-table offset, children, (unused)
-  int64_t foff, g0;                      // front matrix offset, first unknown of the front
+  int32_t uoff, goff, nchild, nf2;       // update-vector offset, gather-table offset, children, rows of the front
+  int64_t foff, g0;                      // packed panel offset, first unknown of the front
 };
 struct BwdItem {
-  int32_t f, col0, ncols, s2, u2, ld, soff, parent;
-  int32_t tgt_f, tgt_pf, tgt_pb, pad;    // forward items of f, forward / backward items of the parent
-  int64_t foff, g0;
+  int32_t f, col0, ncols, s2, u2, ld, soff, parent;   // ld = leading dimension of the row-major copy of W
+  int32_t tgt_f, tgt_pf, tgt_pb, G;      // forward items of f, forward / backward items of the parent; column groups
+  int64_t foff, g0;                      // offset of the W copy, first unknown of the front
+};
+
+// Throughput path of the sweeps: one WARP per task, no CTA-wide synchronisation.  A forward task is a chunk of
+// <= 128 rows of a front's packed left block column [F11^-1 ; W^T] (lanes over rows), a backward task the
+// <= 128 pivot columns of a front against its row-major copy of W (lanes over pivot columns): both are
+// coalesced matrix-vector products with the contraction index staged through shared memory in tiles.
+struct FwdTask {
+  int32_t s2, rows, r0, nr;              // pivot unknowns, rows of the front, first row / rows of this chunk
+  int32_t ldp, goff, uoff, nch;          // panel leading dimension, gather tables, update-vector offset, children
+  int64_t lo, g0;                        // panel offset, first unknown of the front
+};
+struct BwdTask {
+  int32_t s2, u2, c0, nc;                // pivot / update unknowns, first column / columns of this chunk
+  int32_t s2p, soff, pad0, pad1;         // leading dimension of the W copy, offset of the update set in strct
+  int64_t wo, g0;                        // offset of the W copy, first unknown of the front
 };
 
 struct DevPlan {
@@ -162,7 +177,13 @@ struct DevPlan {
   DevBuf<int4> w_tiles, s_tiles, ea_slabs;
   DevBuf<FwdItem> fwd_items; DevBuf<BwdItem> bwd_items; DevBuf<int32_t> gsrc;
   std::vector<int32_t> w_ptr, s_ptr, ea_ptr, fwd_ptr, bwd_ptr;  // [nlevels+1] each
-  DevBuf<double> pool;               // all frontal matrices
+  // per-level launch lists: CTA items of the large fronts + warp tasks of the small ones
+  DevBuf<FwdItem> fwdb_items; DevBuf<BwdItem> bwdb_items;
+  DevBuf<FwdTask> fwd_tasks; DevBuf<BwdTask> bwd_tasks;
+  std::vector<int32_t> fwdb_ptr, bwdb_ptr, fwd_tptr, bwd_tptr;     // [nlevels+1] each
+  DevBuf<int64_t> lo, wo; DevBuf<int32_t> ldp; // packed panels: [F11^-1 ; W^T] (ldp x 2s) and W row-major (s2p x 2u)
+  DevBuf<double> fac;                // packed factor panels: the only matrix data the sweeps read
+  DevBuf<double> pool;               // all frontal matrices (factorisation workspace)
   DevBuf<double> upd;                // per-front update vectors of the forward sweep
   DevBuf<int32_t> status;            // [0] = 1 when a pivot block was singular
   int64_t upd_len = 0;

@@ -28,7 +28,6 @@ namespace {
 constexpr int GT = 64;        // GEMM tile (GT x GT outputs per CTA)
 constexpr int GK = 16;        // GEMM k-step
 constexpr int EA_COLS = 8;    // extend-add slab width in parent node columns
-constexpr int BWD_COLS = 8;   // backward sweep: pivot columns per CTA (one warp each)
 constexpr int MAX_PIV = 128;  // largest pivot block (unknowns) the in-shared-memory inverse handles
 
 struct PlanView {
@@ -278,9 +277,8 @@ __global__ void __launch_bounds__(256) gemm_schur_kernel(const int4* __restrict_
 // write, signal.
 template <int NR>
 struct SweepSmem {
-  double y1[NR][MAX_PIV];
-  double yt[NR][128];
-  double part[NR][8][32];
+  double y[MAX_PIV][NR];          // assembled pivot part of the right-hand sides, [k][rhs] (one 16/32-byte read per k)
+  double part[8][2][NR][32];      // partial sums: [warp][row of the thread][rhs][lane]
 };
 
 struct RhsView {   // NR right-hand sides stored as columns: rhs + r*ldr, out + r*ldo, update pool + r*ldu
@@ -310,32 +308,63 @@ struct Deps {          // dataflow bookkeeping of the persistent kernel (unused 
   int32_t* fdone; int32_t* bdone; int32_t* status; int epoch; const int32_t* nfs;
 };
 
-constexpr int FQ = 16;  // factor entries per thread preloaded before the wait (forward)
-constexpr int BQ = 8;   // factor entries per lane preloaded before the wait (backward)
+constexpr int FQ = 16;  // factor entries per thread in flight before the wait
 
-// forward: one CTA (8 warps) per (front, slab of 32*G rows).  The 8 warps form G row groups x 8/G slices of
-// the k range (the 2s pivot columns); partial sums meet in shared memory.
-template <bool CG, int NR, bool PDL = false>
-__device__ __forceinline__ void forward_item(const FwdItem& it, const int32_t* __restrict__ gsrc, const PlanView& P,
-                                             const RhsView& rv, SweepSmem<NR>& sm, const Deps& dp) {
+// NR doubles of one row of a [.][NR] shared array: a single 128-bit load per pair of right-hand sides
+template <int NR>
+__device__ __forceinline__ void lds_row(const double (*a)[NR], int k, double (&v)[NR]) {
+  if constexpr (NR % 2 == 0) {
+    const double2* p = reinterpret_cast<const double2*>(a[k]);
+#pragma unroll
+    for (int r = 0; r < NR / 2; ++r) { const double2 t = p[r]; v[2 * r] = t.x; v[2 * r + 1] = t.y; }
+  } else {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) v[r] = a[k][r];
+  }
+}
+
+// forward: one CTA (8 warps) per (front, slab of 32*G*R rows) of the packed left block column.  The 8 warps form G
+// row groups x 8/G slices of the k range (the 2s pivot columns), every thread owns R rows 32 apart; partial sums
+// meet in shared memory.  The loops are lean on purpose — ncu showed the previous version issue-bound at ~80 warp
+// instructions per loaded factor entry: loop bounds are warp-uniform, rows past the end of the slab read row 0
+// (and are discarded) instead of predicating every load, the assembled right-hand sides are read with one 128-bit
+// shared load per pair, pointers advance by a constant stride.
+template <bool CG, int NR, int R, bool PDL>
+__device__ __forceinline__ void forward_item_r(const FwdItem& it, const int32_t* __restrict__ gsrc, const PlanView& P,
+                                               const RhsView& rv, SweepSmem<NR>& sm, const Deps& dp) {
+  constexpr int FQR = FQ / R;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int s2 = it.s2, nrows = it.nrows, row0 = it.row0, G = it.G, nf2 = it.ld;
+  const int s2 = it.s2, nrows = it.nrows, row0 = it.row0, G = it.G & 0xff, nf2 = it.nf2;
   const int64_t ld = it.ld;
   const int nks = 8 / G, rg = warp % G, ks = warp / G;
-  const int lr = rg * 32 + lane;            // row within the slab
   // ---- static prefetch: gather sources and this thread's factor entries
   const int32_t* g1 = gsrc + it.goff;       // first child: source offset into upd per front row, -1 = none
   const int32_t* g2 = g1 + nf2;             // second child
-  int i1 = -1, i2 = -1, j1 = -1, j2 = -1;
+  int i1 = -1, i2 = -1;
   if (tid < s2) { i1 = g1[tid]; i2 = g2[tid]; }
-  const int trow = row0 + (tid - 128);      // threads 128.. handle the slab's update rows (nrows <= 128)
-  if (tid >= 128 && tid - 128 < nrows && trow >= s2) { j1 = g1[trow]; j2 = g2[trow]; }
-  const double* M = P.pool + it.foff + (row0 + lr);
-  double mreg[FQ];
+  int lr[R]; bool ok[R]; int j1[R], j2[R];
 #pragma unroll
-  for (int q = 0; q < FQ; ++q) {
-    const int k = ks + q * nks;
-    mreg[q] = (lr < nrows && k < s2) ? M[(int64_t)k * ld] : 0.0;
+  for (int q = 0; q < R; ++q) {
+    lr[q] = (rg * R + q) * 32 + lane;
+    ok[q] = lr[q] < nrows;
+    j1[q] = j2[q] = -1;
+    if (ks == 0 && ok[q] && row0 + lr[q] >= s2) { j1[q] = g1[row0 + lr[q]]; j2[q] = g2[row0 + lr[q]]; }
+  }
+  const int nk = (s2 - ks + nks - 1) / nks;          // k's of this warp's slice: ks, ks + nks, ...  (warp-uniform)
+  const int64_t step = (int64_t)nks * ld;
+  const double* p[R];
+#pragma unroll
+  for (int q = 0; q < R; ++q) p[q] = P.pool + it.foff + row0 + (ok[q] ? lr[q] : 0) + (int64_t)ks * ld;
+  double m[FQR][R];
+#pragma unroll
+  for (int i = 0; i < FQR; ++i) {
+    if (i < nk) {
+#pragma unroll
+      for (int q = 0; q < R; ++q) m[i][q] = p[q][i * step];
+    } else {
+#pragma unroll
+      for (int q = 0; q < R; ++q) m[i][q] = 0.0;
+    }
   }
   if (PDL) griddep_wait();                 // the previous level's kernel is complete and visible from here on
   // ---- wait for the children (dataflow mode)
@@ -348,80 +377,234 @@ __device__ __forceinline__ void forward_item(const FwdItem& it, const int32_t* _
     __syncthreads();
   }
   // ---- dynamic part: right-hand side + children's updates, fixed order (rhs + first child) + second child
+  if (tid < s2) {
 #pragma unroll
-  for (int r = 0; r < NR; ++r) {
-    const double* up = rv.upd + r * rv.ldu;
-    if (tid < s2) {
+    for (int r = 0; r < NR; ++r) {
+      const double* up = rv.upd + r * rv.ldu;
       double v = ldx<CG>(rv.rhs + r * rv.ldr + it.g0 + tid);
       if (i1 >= 0) v += ldx<CG>(up + i1);
       if (i2 >= 0) v += ldx<CG>(up + i2);
-      sm.y1[r][tid] = v;
-    }
-    if (tid >= 128) {
-      double v = 0.0;
-      if (j1 >= 0) v += ldx<CG>(up + j1);
-      if (j2 >= 0) v += ldx<CG>(up + j2);
-      sm.yt[r][tid - 128] = v;
+      sm.y[tid][r] = v;
     }
   }
+  double yt[R][NR];                          // what the children send to this thread's update rows (final-stage threads)
+#pragma unroll
+  for (int q = 0; q < R; ++q)
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const double* up = rv.upd + r * rv.ldu;
+      double v = 0.0;
+      if (j1[q] >= 0) v += ldx<CG>(up + j1[q]);
+      if (j2[q] >= 0) v += ldx<CG>(up + j2[q]);
+      yt[q][r] = v;
+    }
   __syncthreads();
   if (it.nchild > 2) {                       // rare (a separator that does not disconnect): generic path
-    for (int q = P.cptr[it.f] + 2; q < P.cptr[it.f + 1]; ++q) {
-      const int ch = P.child[q];
+    for (int c = P.cptr[it.f] + 2; c < P.cptr[it.f + 1]; ++c) {
+      const int ch = P.child[c];
       const int uc2 = 2 * front_u(P, ch);
       const int32_t* cm = P.cmap + P.cmap_ptr[ch];
       for (int r = 0; r < NR; ++r) {
         const double* uv = rv.upd + r * rv.ldu + P.uoff[ch];
         for (int k = tid; k < uc2; k += 256) {
           const int t = 2 * cm[k >> 1] + (k & 1);
-          if (t < s2) sm.y1[r][t] += ldx<CG>(uv + k);
-          else if (t >= row0 && t < row0 + nrows) sm.yt[r][t - row0] += ldx<CG>(uv + k);
+          if (t < s2) sm.y[t][r] += ldx<CG>(uv + k);
+        }
+        if (ks == 0) {
+          for (int k = 0; k < uc2; ++k) {
+            const int t = 2 * cm[k >> 1] + (k & 1);
+#pragma unroll
+            for (int q = 0; q < R; ++q) if (ok[q] && t == row0 + lr[q] && t >= s2) yt[q][r] += ldx<CG>(uv + k);
+          }
         }
       }
       __syncthreads();
     }
   }
-  double acc[NR];
+  double acc[R][NR];
 #pragma unroll
-  for (int r = 0; r < NR; ++r) acc[r] = 0.0;
-  if (lr < nrows) {
+  for (int q = 0; q < R; ++q)
 #pragma unroll
-    for (int q = 0; q < FQ; ++q) {
-      const int k = ks + q * nks;
-      if (k < s2) {
+    for (int r = 0; r < NR; ++r) acc[q][r] = 0.0;
 #pragma unroll
-        for (int r = 0; r < NR; ++r) acc[r] = fma(mreg[q], sm.y1[r][k], acc[r]);
-      }
-    }
-    for (int k = ks + FQ * nks; k < s2; k += nks) {
-      const double mv = M[(int64_t)k * ld];
+  for (int i = 0; i < FQR; ++i) {
+    if (i < nk) {
+      double y[NR];
+      lds_row<NR>(sm.y, ks + i * nks, y);
 #pragma unroll
-      for (int r = 0; r < NR; ++r) acc[r] = fma(mv, sm.y1[r][k], acc[r]);
+      for (int q = 0; q < R; ++q)
+#pragma unroll
+        for (int r = 0; r < NR; ++r) acc[q][r] = fma(m[i][q], y[r], acc[q][r]);
     }
   }
+#pragma unroll 4
+  for (int i = FQR; i < nk; ++i) {
+    double mv[R], y[NR];
 #pragma unroll
-  for (int r = 0; r < NR; ++r) sm.part[r][warp][lane] = acc[r];
+    for (int q = 0; q < R; ++q) mv[q] = p[q][i * step];
+    lds_row<NR>(sm.y, ks + i * nks, y);
+#pragma unroll
+    for (int q = 0; q < R; ++q)
+#pragma unroll
+      for (int r = 0; r < NR; ++r) acc[q][r] = fma(mv[q], y[r], acc[q][r]);
+  }
+#pragma unroll
+  for (int q = 0; q < R; ++q)
+#pragma unroll
+    for (int r = 0; r < NR; ++r) sm.part[warp][q][r][lane] = acc[q][r];
   __syncthreads();
-  if (ks == 0 && lr < nrows) {
-    const int row = row0 + lr;
+  if (ks == 0) {
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      double t = 0.0;
-      for (int q = 0; q < nks; ++q) t += sm.part[r][q * G + rg][lane];
-      if (row < s2) rv.out[r * rv.ldo + it.g0 + row] = t;
-      else rv.upd[r * rv.ldu + it.uoff + (row - s2)] = sm.yt[r][lr] - t;
+    for (int q = 0; q < R; ++q) {
+      if (!ok[q]) continue;
+      const int row = row0 + lr[q];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        double t = 0.0;
+        for (int c = 0; c < nks; ++c) t += sm.part[c * G + rg][q][r][lane];
+        if (row < s2) rv.out[r * rv.ldo + it.g0 + row] = t;
+        else rv.upd[r * rv.ldu + it.uoff + (row - s2)] = yt[q][r] - t;
+      }
     }
   }
 }
 
-// backward: one warp per pivot column, 8 columns per CTA
 template <bool CG, int NR, bool PDL = false>
-__device__ __forceinline__ void backward_item(const BwdItem& it, const PlanView& P, double* x, int64_t ldx_, const Deps& dp) {
+__device__ __forceinline__ void forward_item(const FwdItem& it, const int32_t* __restrict__ gsrc, const PlanView& P,
+                                             const RhsView& rv, SweepSmem<NR>& sm, const Deps& dp) {
+  if ((it.G >> 8) == 2) forward_item_r<CG, NR, 2, PDL>(it, gsrc, P, rv, sm, dp);
+  else forward_item_r<CG, NR, 1, PDL>(it, gsrc, P, rv, sm, dp);
+}
+
+// backward: one CTA per (front, chunk of 32*R pivot columns) against the row-major copy of W (lanes over pivot
+// columns, coalesced rows).  The update unknowns x2 are gathered ONCE per CTA into shared memory — the gather costs
+// as many loads as the factor chunk itself, so it must not be repeated per column — and the 8 warps take slices of
+// the j range (the 2u update unknowns); partial sums meet in shared memory.  Same lean loops as the forward item.
+constexpr int JT = 512;    // update unknowns staged per pass (one pass for all fronts met so far)
+template <int NR>
+struct BwdSmem {
+  double xs[JT][NR];
+  double part[8][2][NR][32];
+};
+
+template <bool CG, int NR, int R, bool PDL>
+__device__ __forceinline__ void backward_item_r(const BwdItem& it, const PlanView& P, double* x, int64_t ldx_, BwdSmem<NR>& sm,
+                                                const Deps& dp) {
+  constexpr int FQR = FQ / R;
+  constexpr int nks = 8;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int u2 = it.u2, ks = warp;
+  const int64_t s2p = it.ld;
+  const int32_t* st = P.strct + it.soff;
+  int lc[R]; bool ok[R];
+#pragma unroll
+  for (int q = 0; q < R; ++q) { lc[q] = q * 32 + lane; ok[q] = lc[q] < it.ncols; }
+  // ---- static prefetch: gather offsets of the first pass and this thread's factor entries
+  int64_t o0 = -1, o1 = -1;
+  if (tid < u2) o0 = 2 * (int64_t)st[tid >> 1] + (tid & 1);
+  if (tid + 256 < u2) o1 = 2 * (int64_t)st[(tid + 256) >> 1] + (tid & 1);
+  const double* p[R];
+#pragma unroll
+  for (int q = 0; q < R; ++q) p[q] = P.pool + it.foff + it.col0 + (ok[q] ? lc[q] : 0) + (int64_t)ks * s2p;
+  const int64_t step = (int64_t)nks * s2p;
+  const int n0 = (min(u2, JT) - ks + nks - 1) / nks;   // j's of this warp's slice in the first pass (warp-uniform)
+  double m[FQR][R];
+#pragma unroll
+  for (int i = 0; i < FQR; ++i) {
+    if (i < n0) {
+#pragma unroll
+      for (int q = 0; q < R; ++q) m[i][q] = p[q][i * step];
+    } else {
+#pragma unroll
+      for (int q = 0; q < R; ++q) m[i][q] = 0.0;
+    }
+  }
+  if (PDL) griddep_wait();
+  if (CG) {
+    if (tid == 0) {
+      wait_count(dp.fdone + it.f, it.tgt_f * dp.epoch, dp.status);             // z of this front is complete
+      if (it.parent >= 0) { wait_count(dp.fdone + it.parent, it.tgt_pf * dp.epoch, dp.status); wait_count(dp.bdone + it.parent, it.tgt_pb * dp.epoch, dp.status); }
+    }
+    __syncthreads();
+  }
+  double acc[R][NR];
+#pragma unroll
+  for (int q = 0; q < R; ++q)
+#pragma unroll
+    for (int r = 0; r < NR; ++r) acc[q][r] = 0.0;
+  for (int j0 = 0; j0 < u2; j0 += JT) {
+    const int jn = min(JT, u2 - j0);
+    if (j0 > 0) {                             // fronts with more than JT update unknowns: further passes
+      __syncthreads();
+      o0 = o1 = -1;
+      if (tid < jn) o0 = 2 * (int64_t)st[(j0 + tid) >> 1] + (tid & 1);
+      if (tid + 256 < jn) o1 = 2 * (int64_t)st[(j0 + tid + 256) >> 1] + (tid & 1);
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      if (o0 >= 0) sm.xs[tid][r] = ldx<CG>(x + r * ldx_ + o0);
+      if (o1 >= 0) sm.xs[tid + 256][r] = ldx<CG>(x + r * ldx_ + o1);
+    }
+    __syncthreads();
+    const int nk = (jn - ks + nks - 1) / nks;
+    int i = 0;
+    if (j0 == 0) {
+#pragma unroll
+      for (int ii = 0; ii < FQR; ++ii) {
+        if (ii < nk) {
+          double xv[NR];
+          lds_row<NR>(sm.xs, ks + ii * nks, xv);
+#pragma unroll
+          for (int q = 0; q < R; ++q)
+#pragma unroll
+            for (int r = 0; r < NR; ++r) acc[q][r] = fma(m[ii][q], xv[r], acc[q][r]);
+        }
+      }
+      i = FQR;
+    }
+    const double* const* pp = p;
+#pragma unroll 4
+    for (; i < nk; ++i) {
+      double mv[R], xv[NR];
+#pragma unroll
+      for (int q = 0; q < R; ++q) mv[q] = pp[q][(int64_t)j0 * s2p + i * step];
+      lds_row<NR>(sm.xs, ks + i * nks, xv);
+#pragma unroll
+      for (int q = 0; q < R; ++q)
+#pragma unroll
+        for (int r = 0; r < NR; ++r) acc[q][r] = fma(mv[q], xv[r], acc[q][r]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < R; ++q)
+#pragma unroll
+    for (int r = 0; r < NR; ++r) sm.part[warp][q][r][lane] = acc[q][r];
+  __syncthreads();
+  // final stage: warp w sums the partials of right-hand side w % NR for row q = w / NR (all 8 warps share the work)
+  for (int job = warp; job < R * NR; job += 8) {
+    const int q = job / NR, r = job % NR;
+    if (q * 32 + lane < it.ncols) {
+      double t = 0.0;
+#pragma unroll
+      for (int c = 0; c < nks; ++c) t += sm.part[c][q][r][lane];
+      double* xp = x + r * ldx_ + it.g0 + it.col0 + q * 32 + lane;
+      *xp = ldx<CG>(xp) - t;
+    }
+  }
+}
+
+// backward, fronts with MANY update unknowns: one warp per pivot column of W^T in the packed left block column
+// (lanes over the update unknowns), 8 columns per CTA.  Parallel over all 2s x 2u entries, every factor entry in
+// flight before the dependency wait — the shape the latency-bound upper levels of the tree need.
+constexpr int BWD_COLS = 8;
+constexpr int BQ = 8;   // factor entries per lane preloaded before the wait
+template <bool CG, int NR, bool PDL>
+__device__ __forceinline__ void backward_item_cols(const BwdItem& it, const PlanView& P, double* x, int64_t ldx_, const Deps& dp) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u2 = it.u2;
   const bool active = warp < it.ncols;
   const int32_t* st = P.strct + it.soff;
-  const double* wc = P.pool + it.foff + it.s2 + (int64_t)(it.col0 + warp) * it.ld;   // F21new(j, col) at col*ld + s2 + j
+  const double* wc = P.pool + it.foff + it.s2 + (int64_t)(it.col0 + warp) * it.ld;   // W^T(j, col) at col*ld + s2 + j
   // ---- static prefetch: factor column and gather offsets
   double wreg[BQ]; int64_t xo[BQ];
 #pragma unroll
@@ -465,20 +648,263 @@ __device__ __forceinline__ void backward_item(const BwdItem& it, const PlanView&
   }
 }
 
+template <bool CG, int NR, bool PDL = false>
+__device__ __forceinline__ void backward_item(const BwdItem& it, const PlanView& P, double* x, int64_t ldx_, BwdSmem<NR>& sm,
+                                              const Deps& dp) {
+  if (it.G == 0) backward_item_cols<CG, NR, PDL>(it, P, x, ldx_, dp);
+  else if (it.G == 2) backward_item_r<CG, NR, 2, PDL>(it, P, x, ldx_, sm, dp);
+  else backward_item_r<CG, NR, 1, PDL>(it, P, x, ldx_, sm, dp);
+}
+
+// ---- warp-per-task sweeps for SMALL fronts -------------------------------------------------------------------
+// The CTA-cooperative items above minimise the latency of one large front (k-split, everything prefetched) and are
+// what the top of the tree needs.  The bottom of the tree — most fronts of a design, and thousands per launch in a
+// forest of designs — are small: a CTA of 256 mostly idle threads per front wastes the SM's thread slots and the
+// launch ends up bound by CTA turnover, not by memory.  A small front is served by one WARP per task instead, which
+// never synchronises with another warp: a forward task is a chunk of 32*R rows of the packed left block column
+// [F11^-1 ; W^T] (lanes over rows), a backward task 32*R pivot columns against the row-major copy of W (lanes over
+// pivot columns); both are coalesced matrix-vector products whose contraction index is staged through shared
+// memory in tiles, with 16 factor entries per lane in flight.  Which path a front takes depends only on its own
+// size, so a design gives bit-identical results alone and inside a forest.
+constexpr int KT = 64;     // contraction-index tile staged in shared memory (per warp)
+
+// acc += M[:, 0..kn) * vs[0..kn): 8 factor entries per lane in flight; `pre` holds the first batch when PRE
+template <int NR, int R, bool PRE>
+__device__ __forceinline__ void warp_gemv_tile(const double* __restrict__ Mk, int64_t ldm, int kn, const bool (&valid)[R],
+                                               const double (*vs)[NR], double (&acc)[R][NR], const double (&pre)[8 / R][R]) {
+  constexpr int U = 8 / R;
+  for (int kk0 = 0; kk0 < kn; kk0 += U) {
+    double m[U][R];
+    if (PRE && kk0 == 0) {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int q = 0; q < R; ++q) m[u][q] = pre[u][q];
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int q = 0; q < R; ++q) m[u][q] = (kk0 + u < kn && valid[q]) ? Mk[(int64_t)(kk0 + u) * ldm + 32 * q] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (kk0 + u < kn) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const double y = vs[kk0 + u][r];
+#pragma unroll
+          for (int q = 0; q < R; ++q) acc[q][r] = fma(m[u][q], y, acc[q][r]);
+        }
+      }
+    }
+  }
+}
+
+template <int NR, int R, bool PDL>
+__device__ __forceinline__ void forward_task(const FwdTask& t, const int32_t* __restrict__ gsrc, const double* __restrict__ fac,
+                                             const RhsView& rv, double (*ys)[NR], int lane) {
+  constexpr int U = 8 / R;
+  const int s2 = t.s2, nf2 = t.rows;
+  const int64_t ldp = t.ldp;
+  const int32_t* g = gsrc + t.goff;
+  const double* L = fac + t.lo + t.r0 + lane;
+  bool valid[R];
+#pragma unroll
+  for (int q = 0; q < R; ++q) valid[q] = lane + 32 * q < t.nr;
+  // static prefetch: the first batch of factor entries is on its way before the inputs are touched
+  double pre[U][R];
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+#pragma unroll
+    for (int q = 0; q < R; ++q) pre[u][q] = (u < s2 && valid[q]) ? L[(int64_t)u * ldp + 32 * q] : 0.0;
+  if (PDL) griddep_wait();                 // the previous level is complete and visible from here on
+  double acc[R][NR];
+#pragma unroll
+  for (int q = 0; q < R; ++q)
+#pragma unroll
+    for (int r = 0; r < NR; ++r) acc[q][r] = 0.0;
+  for (int k0 = 0; k0 < s2; k0 += KT) {
+    const int kn = min(KT, s2 - k0);
+    // right-hand side + children's updates of the pivot unknowns k0.., fixed order (rhs + child 0) + child 1 ...
+    for (int h = lane; h < kn; h += 32) {
+      const int k = k0 + h;
+      double v[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) v[r] = rv.rhs[r * rv.ldr + t.g0 + k];
+      for (int c = 0; c < t.nch; ++c) {
+        const int i = g[c * nf2 + k];
+        if (i >= 0) {
+#pragma unroll
+          for (int r = 0; r < NR; ++r) v[r] += rv.upd[r * rv.ldu + i];
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < NR; ++r) ys[h][r] = v[r];
+    }
+    __syncwarp();
+    if (k0 == 0) warp_gemv_tile<NR, R, true>(L, ldp, kn, valid, ys, acc, pre);
+    else warp_gemv_tile<NR, R, false>(L + (int64_t)k0 * ldp, ldp, kn, valid, ys, acc, pre);
+    __syncwarp();
+  }
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+    if (!valid[q]) continue;
+    const int row = t.r0 + lane + 32 * q;
+    if (row < s2) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) rv.out[r * rv.ldo + t.g0 + row] = acc[q][r];
+    } else {
+      double yt[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) yt[r] = 0.0;
+      for (int c = 0; c < t.nch; ++c) {
+        const int i = g[c * nf2 + row];
+        if (i >= 0) {
+#pragma unroll
+          for (int r = 0; r < NR; ++r) yt[r] += rv.upd[r * rv.ldu + i];
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < NR; ++r) rv.upd[r * rv.ldu + t.uoff + (row - s2)] = yt[r] - acc[q][r];
+    }
+  }
+}
+
+template <int NR, int R, bool PDL>
+__device__ __forceinline__ void backward_task(const BwdTask& t, const int32_t* __restrict__ strct, const double* __restrict__ fac,
+                                              double* x, int64_t ldx_, double (*xs)[NR], int lane) {
+  constexpr int U = 8 / R;
+  const int u2 = t.u2;
+  const int64_t s2p = t.s2p;
+  const int32_t* st = strct + t.soff;
+  const double* W = fac + t.wo + t.c0 + lane;
+  bool valid[R];
+#pragma unroll
+  for (int q = 0; q < R; ++q) valid[q] = lane + 32 * q < t.nc;
+  double pre[U][R];
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+#pragma unroll
+    for (int q = 0; q < R; ++q) pre[u][q] = (u < u2 && valid[q]) ? W[(int64_t)u * s2p + 32 * q] : 0.0;
+  // gather offsets of the first tile are static too
+  int64_t o0 = -1, o1 = -1;
+  if (lane < u2) o0 = 2 * (int64_t)st[lane >> 1] + (lane & 1);
+  if (lane + 32 < u2) o1 = 2 * (int64_t)st[(lane + 32) >> 1] + (lane & 1);
+  if (PDL) griddep_wait();
+  double acc[R][NR];
+#pragma unroll
+  for (int q = 0; q < R; ++q)
+#pragma unroll
+    for (int r = 0; r < NR; ++r) acc[q][r] = 0.0;
+  for (int j0 = 0; j0 < u2; j0 += KT) {
+    const int jn = min(KT, u2 - j0);
+    if (j0 == 0) {
+      if (o0 >= 0) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) xs[lane][r] = x[r * ldx_ + o0];
+      }
+      if (o1 >= 0) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) xs[lane + 32][r] = x[r * ldx_ + o1];
+      }
+    } else {
+      for (int h = lane; h < jn; h += 32) {
+        const int j = j0 + h;
+        const int64_t o = 2 * (int64_t)st[j >> 1] + (j & 1);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) xs[h][r] = x[r * ldx_ + o];
+      }
+    }
+    __syncwarp();
+    if (j0 == 0) warp_gemv_tile<NR, R, true>(W, s2p, jn, valid, xs, acc, pre);
+    else warp_gemv_tile<NR, R, false>(W + (int64_t)j0 * s2p, s2p, jn, valid, xs, acc, pre);
+    __syncwarp();
+  }
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+    if (!valid[q]) continue;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      double* xp = x + r * ldx_ + t.g0 + t.c0 + lane + 32 * q;
+      *xp = *xp - acc[q][r];
+    }
+  }
+}
+
+// large fronts: one CTA-cooperative item per CTA
 template <int NR, bool PDL>
-__global__ void __launch_bounds__(256) forward_kernel(const FwdItem* __restrict__ items, const int32_t* __restrict__ gsrc, PlanView P,
+__global__ void __launch_bounds__(256, 4) forward_kernel(const FwdItem* __restrict__ items, const int32_t* __restrict__ gsrc, PlanView P,
                                                        RhsView rv) {
   __shared__ SweepSmem<NR> sm;
-  if (PDL) griddep_launch_dependents();    // let the next level start its static prefetch
+  if (PDL) griddep_launch_dependents();    // let the next launch start its static prefetch
   const Deps none{nullptr, nullptr, nullptr, 0, nullptr};
   forward_item<false, NR, PDL>(items[blockIdx.x], gsrc, P, rv, sm, none);
 }
 
 template <int NR, bool PDL>
-__global__ void __launch_bounds__(256) backward_kernel(const BwdItem* __restrict__ items, PlanView P, double* x, int64_t ldx_) {
+__global__ void __launch_bounds__(256, 4) backward_kernel(const BwdItem* __restrict__ items, PlanView P, double* x, int64_t ldx_) {
+  __shared__ BwdSmem<NR> sm;
   if (PDL) griddep_launch_dependents();
   const Deps none{nullptr, nullptr, nullptr, 0, nullptr};
-  backward_item<false, NR, PDL>(items[blockIdx.x], P, x, ldx_, none);
+  backward_item<false, NR, PDL>(items[blockIdx.x], P, x, ldx_, sm, none);
+}
+
+// small fronts: eight warp tasks per CTA, 32 warps resident per SM
+template <int NR, bool PDL>
+__global__ void __launch_bounds__(256, 4) forward_small_kernel(const FwdTask* __restrict__ tasks, int ntasks, const int32_t* __restrict__ gsrc,
+                                                                const double* __restrict__ fac, RhsView rv) {
+  __shared__ __align__(16) double tile[8][KT][NR];
+  if (PDL) griddep_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int id = (int)blockIdx.x * 8 + warp;
+  if (id >= ntasks) return;
+  const FwdTask t = tasks[id];
+  if (t.nr <= 32) forward_task<NR, 1, PDL>(t, gsrc, fac, rv, tile[warp], lane);
+  else forward_task<NR, 2, PDL>(t, gsrc, fac, rv, tile[warp], lane);
+}
+
+template <int NR, bool PDL>
+__global__ void __launch_bounds__(256, 4) backward_small_kernel(const BwdTask* __restrict__ tasks, int ntasks, const int32_t* __restrict__ strct,
+                                                                 const double* __restrict__ fac, double* x, int64_t ldx_) {
+  __shared__ __align__(16) double tile[8][KT][NR];
+  if (PDL) griddep_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int id = (int)blockIdx.x * 8 + warp;
+  if (id >= ntasks) return;
+  const BwdTask t = tasks[id];
+  if (t.nc <= 32) backward_task<NR, 1, PDL>(t, strct, fac, x, ldx_, tile[warp], lane);
+  else backward_task<NR, 2, PDL>(t, strct, fac, x, ldx_, tile[warp], lane);
+}
+
+// ---- pack: the solve phase reads only the left block column of a front (and W a second time, row-major) ----
+// Copy both into dense, 32-byte aligned panels; the front pool is factorisation workspace only.
+__global__ void __launch_bounds__(256) pack_kernel(PlanView P, const int64_t* __restrict__ lo, const int64_t* __restrict__ wo,
+                                                   const int32_t* __restrict__ ldp, double* __restrict__ fac) {
+  __shared__ double tile[32][33];
+  const int f = blockIdx.x;
+  const int s2 = 2 * P.s[f], u2 = 2 * front_u(P, f);
+  const int64_t ld = s2 + u2, lp = ldp[f];
+  const double* src = P.pool + P.foff[f];
+  double* dst = fac + lo[f];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = warp; k < s2; k += 8)
+    for (int i = lane; i < ld; i += 32) dst[k * lp + i] = src[k * ld + i];
+  if (u2 == 0) return;
+  double* dw = fac + wo[f];
+  const int64_t s2p = (s2 + 3) & ~3;
+  for (int c0 = 0; c0 < s2; c0 += 32)
+    for (int j0 = 0; j0 < u2; j0 += 32) {
+      __syncthreads();
+      for (int w = warp; w < 32; w += 8) {              // column c0+w of W^T, rows j0..j0+31
+        const int c = c0 + w, j = j0 + lane;
+        tile[w][lane] = (c < s2 && j < u2) ? src[(int64_t)c * ld + s2 + j] : 0.0;
+      }
+      __syncthreads();
+      for (int w = warp; w < 32; w += 8) {              // row j0+w of the copy, columns c0..c0+31
+        const int j = j0 + w, c = c0 + lane;
+        if (j < u2 && c < s2) dw[(int64_t)j * s2p + c] = tile[lane][w];
+      }
+    }
 }
 
 // ---- persistent operator kernel: x = refine((A - sigma B)^-1 b) in ONE cooperative launch ----------------
@@ -503,19 +929,24 @@ struct OpArgs {
   int32_t n; const int32_t* rowptr; const int32_t* col; const double* vals; int64_t nnz; const double* sigma_node;
 };
 
-__device__ __forceinline__ void sweep_dataflow(const OpArgs& a, const double* rhs, double* out, int epoch, SweepSmem<1>& sm) {
+union OpSmem {
+  SweepSmem<1> f;
+  BwdSmem<1> b;
+};
+
+__device__ __forceinline__ void sweep_dataflow(const OpArgs& a, const double* rhs, double* out, int epoch, OpSmem& sm) {
   const Deps dp{a.fdone, a.bdone, a.status, epoch, a.nfs};
   const RhsView rv{rhs, 0, out, 0, a.upd, 0};
   for (int i = blockIdx.x; i < a.n_fwd; i += gridDim.x) {
     const FwdItem it = a.fwd_q[i];
-    forward_item<true, 1>(it, a.gsrc, a.P, rv, sm, dp);
+    forward_item<true, 1>(it, a.gsrc, a.P, rv, sm.f, dp);
     __threadfence();
     __syncthreads();                       // all writes of the item are fenced; shared memory is free again
     if (threadIdx.x == 0) atomicAdd(a.fdone + it.f, 1);
   }
   for (int i = blockIdx.x; i < a.n_bwd; i += gridDim.x) {
     const BwdItem it = a.bwd_q[i];
-    backward_item<true, 1>(it, a.P, out, 0, dp);
+    backward_item<true, 1>(it, a.P, out, 0, sm.b, dp);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) atomicAdd(a.bdone + it.f, 1);
@@ -523,7 +954,7 @@ __device__ __forceinline__ void sweep_dataflow(const OpArgs& a, const double* rh
 }
 
 __global__ void __launch_bounds__(256) op_kernel(OpArgs a) {
-  __shared__ SweepSmem<1> sm;
+  __shared__ OpSmem sm;
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   sweep_dataflow(a, a.b, a.x, a.epoch0 + 1, sm);
   for (int r = 0; r < a.refine; ++r) {
@@ -561,6 +992,13 @@ __global__ void __launch_bounds__(256) op_kernel(OpArgs a) {
   }
 }
 
+PlanView view(const DevPlan& D);
+PlanView sweep_view(const DevPlan& D) {   // the sweeps read the packed panels, never the front pool
+  PlanView v = view(D);
+  v.pool = D.fac.p;
+  return v;
+}
+
 size_t invert_smem(int m) { return ((size_t)(m | 1) * m + 2 * (size_t)m) * sizeof(double); }
 
 PlanView view(const DevPlan& D) {
@@ -572,6 +1010,12 @@ PlanView view(const DevPlan& D) {
 
 
 }  // namespace
+
+// fronts with at most this many pivot / update unknowns take the warp-per-task path of the sweeps (0: none does)
+int small_front_limit(const char* env, int dflt) {
+  const char* e = std::getenv(env);
+  return e ? std::max(0, atoi(e)) : dflt;
+}
 
 void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
   if (2 * P.max_s > MAX_PIV) throw StatusError(PLFEM_ERR_INVALID, "max_sn_nodes must be <= 64");
@@ -587,18 +1031,38 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
   D.uoff.upload(ctx, uoff);
   D.upd.alloc(ctx, (size_t)SOLVE_NRHS * std::max<int64_t>(D.upd_len, 1));
 
+  // packed panels of the solve phase
+  std::vector<int64_t> lo(P.nfronts + 1, 0), wo(P.nfronts, 0);
+  std::vector<int32_t> ldp(P.nfronts, 0);
+  {
+    int64_t off = 0;
+    for (int f = 0; f < P.nfronts; ++f) {
+      const int64_t s2 = 2 * (int64_t)P.s[f], u2 = 2 * (int64_t)(P.sptr[f + 1] - P.sptr[f]);
+      ldp[f] = (int32_t)((s2 + u2 + 3) & ~int64_t(3));
+      lo[f] = off; off += (int64_t)ldp[f] * s2;
+      wo[f] = off; off += ((s2 + 3) & ~int64_t(3)) * u2;
+    }
+    lo[P.nfronts] = off;
+    D.fac.alloc(ctx, (size_t)std::max<int64_t>(off, 1));
+    D.lo.upload(ctx, lo); D.wo.upload(ctx, wo); D.ldp.upload(ctx, ldp);
+  }
   std::vector<int4> wt, stl, ea;
   std::vector<FwdItem> fw; std::vector<BwdItem> bw;
+  std::vector<FwdItem> fwb; std::vector<BwdItem> bwb;     // per-level launches: CTA items of large fronts ...
+  std::vector<FwdTask> ft; std::vector<BwdTask> bt;       // ... and warp tasks of small ones
+  D.fwd_tptr.assign(P.nlevels + 1, 0); D.bwd_tptr = D.fwdb_ptr = D.bwdb_ptr = D.fwd_tptr;
+  const int small_s2 = small_front_limit("PLFEM_SMALL_S2", 0), small_u2 = small_front_limit("PLFEM_SMALL_U2", 0);
   D.w_ptr.assign(P.nlevels + 1, 0); D.s_ptr = D.ea_ptr = D.fwd_ptr = D.bwd_ptr = D.w_ptr;
   D.lmax_m.assign(P.nlevels, 0);
   // flattened child -> parent gather: per front, for every front row (2nf unknowns) the offset into the
   // update-vector pool it receives from the first and from the second child (-1 = nothing)
   std::vector<int32_t> goff(P.nfronts + 1, 0);
-  for (int f = 0; f < P.nfronts; ++f) goff[f + 1] = goff[f] + 4 * (P.s[f] + P.sptr[f + 1] - P.sptr[f]);
+  for (int f = 0; f < P.nfronts; ++f)   // one table per child, at least two (the CTA path reads two unconditionally)
+    goff[f + 1] = goff[f] + 2 * std::max(2, P.cptr[f + 1] - P.cptr[f]) * (P.s[f] + P.sptr[f + 1] - P.sptr[f]);
   std::vector<int32_t> gsrc(goff[P.nfronts], -1);
   for (int f = 0; f < P.nfronts; ++f) {
     const int nf2 = 2 * (P.s[f] + P.sptr[f + 1] - P.sptr[f]);
-    for (int q = P.cptr[f]; q < std::min(P.cptr[f] + 2, P.cptr[f + 1]); ++q) {
+    for (int q = P.cptr[f]; q < P.cptr[f + 1]; ++q) {
       const int ch = P.child[q];
       int32_t* g = gsrc.data() + goff[f] + (q - P.cptr[f]) * nf2;
       for (int k = P.sptr[ch], o = P.cmap_ptr[ch], idx = 0; k < P.sptr[ch + 1]; ++k, ++o, ++idx) {
@@ -607,13 +1071,14 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
       }
     }
   }
+  const int bwd_rows_u2 = small_front_limit("PLFEM_BWD_ROWS_U2", 128);
   std::vector<int32_t> nfs(P.nfronts, 0), nbs(P.nfronts, 0);
   for (int f = 0; f < P.nfronts; ++f) {
     const int s2 = 2 * P.s[f], u2 = 2 * (P.sptr[f + 1] - P.sptr[f]);
     const int rows = s2 + u2;
-    const int G = rows <= 32 ? 1 : (rows <= 64 ? 2 : (rows <= 128 ? 4 : 1));
-    nfs[f] = (rows + 32 * G - 1) / (32 * G);
-    nbs[f] = u2 > 0 ? (s2 + BWD_COLS - 1) / BWD_COLS : 0;
+    nfs[f] = rows <= 128 ? 1 : (rows + 63) / 64;     // forward CTA items: one slab of <= 128 rows, else slabs of 64
+    // backward CTA items: few update unknowns -> chunks of 64 pivot columns sharing one gather, many -> 8 columns each
+    nbs[f] = u2 == 0 ? 0 : (u2 <= bwd_rows_u2 ? (s2 + 63) / 64 : (s2 + BWD_COLS - 1) / BWD_COLS);
   }
   for (int l = 0; l < P.nlevels; ++l) {
     for (int q = P.lptr[l]; q < P.lptr[l + 1]; ++q) {
@@ -629,31 +1094,64 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
         for (int c0 = 0; c0 < nf; c0 += EA_COLS) ea.push_back(make_int4(f, c0, std::min(c0 + EA_COLS, nf), 0));
       {
         const int rows = s2 + u2;
-        const int G = rows <= 32 ? 1 : (rows <= 64 ? 2 : (rows <= 128 ? 4 : 1));
+        // row groups x rows per thread: <= 32 rows (1,1), <= 64 (1,2), <= 128 (2,2), larger fronts in slabs of 64 rows (1,2)
+        const int G = (rows > 64 && rows <= 128) ? 2 : 1, Rr = rows <= 32 ? 1 : 2;
         const int nch = P.cptr[f + 1] - P.cptr[f];
-        for (int r0 = 0; r0 < rows; r0 += 32 * G) {
+        const bool fsmall = s2 <= small_s2;
+        for (int r0 = 0; r0 < rows; r0 += 32 * G * Rr) {
           FwdItem it{};
-          it.f = f; it.row0 = r0; it.nrows = std::min(32 * G, rows - r0); it.G = G; it.s2 = s2; it.ld = rows;
+          it.f = f; it.row0 = r0; it.nrows = std::min(32 * G * Rr, rows - r0); it.G = G | (Rr << 8); it.s2 = s2; it.ld = ldp[f];
           it.ch0 = nch > 0 ? P.child[P.cptr[f]] : -1; it.ch1 = nch > 1 ? P.child[P.cptr[f] + 1] : -1;
           it.tgt0 = it.ch0 >= 0 ? nfs[it.ch0] : 0; it.tgt1 = it.ch1 >= 0 ? nfs[it.ch1] : 0;
-          it.uoff = uoff[f]; it.goff = goff[f]; it.nchild = nch; it.tgtx = 0;
-          it.foff = P.foff[f]; it.g0 = 2 * (int64_t)P.first[f];
+          it.uoff = uoff[f]; it.goff = goff[f]; it.nchild = nch; it.nf2 = rows;
+          it.foff = lo[f]; it.g0 = 2 * (int64_t)P.first[f];
           fw.push_back(it);
+          if (!fsmall) fwb.push_back(it);
+        }
+        if (fsmall) {
+          // rows per warp: at most 64 factor entries per lane, so a task is a handful of memory round trips
+          const int R = (s2 <= 32 && rows > 32) ? 2 : 1;
+          for (int r0 = 0; r0 < rows; r0 += 32 * R) {
+            FwdTask t{};
+            t.s2 = s2; t.rows = rows; t.r0 = r0; t.nr = std::min(32 * R, rows - r0); t.ldp = ldp[f]; t.goff = goff[f]; t.uoff = uoff[f];
+            t.nch = nch; t.lo = lo[f]; t.g0 = 2 * (int64_t)P.first[f];
+            ft.push_back(t);
+          }
         }
       }
-      if (u2 > 0)
-        for (int c0 = 0; c0 < s2; c0 += BWD_COLS) {
+      if (u2 > 0) {
+        const bool bsmall = s2 <= small_s2 && u2 <= small_u2;
+        const bool rows_style = u2 <= bwd_rows_u2;
+        const int Gb = rows_style ? (s2 <= 32 ? 1 : 2) : 0;   // pivot columns per thread; 0 = one warp per column
+        const int cw = rows_style ? 32 * Gb : BWD_COLS;
+        for (int c0 = 0; c0 < s2; c0 += cw) {
           BwdItem it{};
           const int pa = P.parent[f];
-          it.f = f; it.col0 = c0; it.ncols = std::min(BWD_COLS, s2 - c0); it.s2 = s2; it.u2 = u2; it.ld = s2 + u2; it.soff = P.sptr[f];
-          it.parent = pa; it.tgt_f = nfs[f]; it.tgt_pf = pa >= 0 ? nfs[pa] : 0; it.tgt_pb = pa >= 0 ? nbs[pa] : 0;
-          it.foff = P.foff[f]; it.g0 = 2 * (int64_t)P.first[f];
+          it.f = f; it.col0 = c0; it.ncols = std::min(cw, s2 - c0); it.s2 = s2; it.u2 = u2; it.soff = P.sptr[f];
+          it.ld = rows_style ? ((s2 + 3) & ~3) : ldp[f];
+          it.parent = pa; it.tgt_f = nfs[f]; it.tgt_pf = pa >= 0 ? nfs[pa] : 0; it.tgt_pb = pa >= 0 ? nbs[pa] : 0; it.G = Gb;
+          it.foff = rows_style ? wo[f] : lo[f]; it.g0 = 2 * (int64_t)P.first[f];
           bw.push_back(it);
+          if (!bsmall) bwb.push_back(it);
         }
+        if (bsmall) {
+          const int R = (s2 > 32 && u2 <= 32) ? 2 : 1;
+          for (int c0 = 0; c0 < s2; c0 += 32 * R) {
+            BwdTask t{};
+            t.s2 = s2; t.u2 = u2; t.c0 = c0; t.nc = std::min(32 * R, s2 - c0); t.s2p = (s2 + 3) & ~3; t.soff = P.sptr[f];
+            t.wo = wo[f]; t.g0 = 2 * (int64_t)P.first[f];
+            bt.push_back(t);
+          }
+        }
+      }
     }
     D.w_ptr[l + 1] = (int32_t)wt.size(); D.s_ptr[l + 1] = (int32_t)stl.size(); D.ea_ptr[l + 1] = (int32_t)ea.size();
     D.fwd_ptr[l + 1] = (int32_t)fw.size(); D.bwd_ptr[l + 1] = (int32_t)bw.size();
+    D.fwd_tptr[l + 1] = (int32_t)ft.size(); D.bwd_tptr[l + 1] = (int32_t)bt.size();
+    D.fwdb_ptr[l + 1] = (int32_t)fwb.size(); D.bwdb_ptr[l + 1] = (int32_t)bwb.size();
   }
+  D.fwd_tasks.upload(ctx, ft); D.bwd_tasks.upload(ctx, bt);
+  D.fwdb_items.upload(ctx, fwb); D.bwdb_items.upload(ctx, bwb);
   {
     // backward queue of the persistent operator kernel: levels descending; completion counters
     std::vector<BwdItem> bq; bq.reserve(bw.size());
@@ -712,6 +1210,8 @@ void run_factorization(plfem_ctx* ctx, const DevPlan& D) {
       ctx->launches++;
     }
   }
+  pack_kernel<<<D.nfronts, 256, 0, ctx->stream>>>(v, D.lo.p, D.wo.p, D.ldp.p, D.fac.p);
+  ctx->launches++;
   PLFEM_CUDA(cudaGetLastError());
 }
 
@@ -731,37 +1231,54 @@ void launch_sweep(void (*kernel)(KArgs...), bool pdl, int grid, cudaStream_t st,
   PLFEM_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
 }
 
-// nrhs right-hand sides (1 or 4) stored as columns with stride ld (ignored for nrhs = 1)
+// nrhs right-hand sides (1 or 4) stored as columns with stride ld (ignored for nrhs = 1).  Per level: one launch for
+// the CTA items of the large fronts, one for the warp tasks of the small ones (most levels have only one kind).
 void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double* z, int nrhs, int64_t ld) {
-  const PlanView v = view(D);
+  const PlanView v = sweep_view(D);
   if (nrhs != 1 && nrhs != SOLVE_NRHS) throw StatusError(PLFEM_ERR_INTERNAL, "unsupported number of right-hand sides");
   const RhsView rv{b, ld, z, ld, D.upd.p, D.upd_len};
   const bool pdl = use_pdl();
+  bool first = true;     // the first launch follows kernels that are not PDL-aware: plain launch
+  const int32_t* gs = D.gsrc.p;
   for (int l = 0; l < D.nlevels; ++l) {
-    const int nsl = D.fwd_ptr[l + 1] - D.fwd_ptr[l];
-    const FwdItem* items = D.fwd_items.p + D.fwd_ptr[l];
-    const int32_t* gs = D.gsrc.p;
-    // the first level follows kernels that are not PDL-aware: plain launch
-    if (nrhs == 1) { if (pdl && l > 0) launch_sweep(forward_kernel<1, true>, true, nsl, ctx->stream, items, gs, v, rv); else launch_sweep(forward_kernel<1, false>, false, nsl, ctx->stream, items, gs, v, rv); }
-    else { if (pdl && l > 0) launch_sweep(forward_kernel<SOLVE_NRHS, true>, true, nsl, ctx->stream, items, gs, v, rv); else launch_sweep(forward_kernel<SOLVE_NRHS, false>, false, nsl, ctx->stream, items, gs, v, rv); }
-    ctx->launches++;
+    const int nbig = D.fwdb_ptr[l + 1] - D.fwdb_ptr[l], nt = D.fwd_tptr[l + 1] - D.fwd_tptr[l];
+    if (nbig > 0) {
+      const FwdItem* items = D.fwdb_items.p + D.fwdb_ptr[l];
+      const bool p = pdl && !first;
+      if (nrhs == 1) { if (p) launch_sweep(forward_kernel<1, true>, true, nbig, ctx->stream, items, gs, v, rv); else launch_sweep(forward_kernel<1, false>, false, nbig, ctx->stream, items, gs, v, rv); }
+      else { if (p) launch_sweep(forward_kernel<SOLVE_NRHS, true>, true, nbig, ctx->stream, items, gs, v, rv); else launch_sweep(forward_kernel<SOLVE_NRHS, false>, false, nbig, ctx->stream, items, gs, v, rv); }
+      first = false; ctx->launches++;
+    }
+    if (nt > 0) {
+      const FwdTask* tasks = D.fwd_tasks.p + D.fwd_tptr[l];
+      const int grid = (nt + 7) / 8;
+      const bool p = pdl && !first;
+      if (nrhs == 1) { if (p) launch_sweep(forward_small_kernel<1, true>, true, grid, ctx->stream, tasks, nt, gs, D.fac.p, rv); else launch_sweep(forward_small_kernel<1, false>, false, grid, ctx->stream, tasks, nt, gs, D.fac.p, rv); }
+      else { if (p) launch_sweep(forward_small_kernel<SOLVE_NRHS, true>, true, grid, ctx->stream, tasks, nt, gs, D.fac.p, rv); else launch_sweep(forward_small_kernel<SOLVE_NRHS, false>, false, grid, ctx->stream, tasks, nt, gs, D.fac.p, rv); }
+      first = false; ctx->launches++;
+    }
   }
 }
 
+// must follow run_solve_forward on the same stream (its launches may be PDL-chained to the forward ones)
 void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs, int64_t ld) {
-  const PlanView v = view(D);
+  const PlanView v = sweep_view(D);
   const bool pdl = use_pdl();
-  bool first = true;
   for (int l = D.nlevels - 1; l >= 0; --l) {
-    const int nsl = D.bwd_ptr[l + 1] - D.bwd_ptr[l];
-    if (nsl == 0) continue;
-    const BwdItem* items = D.bwd_items.p + D.bwd_ptr[l];
-    // the first backward level follows the last forward kernel, which is PDL-aware only if it was launched so
-    const bool p = pdl && !(first && D.nlevels == 1);
-    if (nrhs == 1) { if (p) launch_sweep(backward_kernel<1, true>, true, nsl, ctx->stream, items, v, x, ld); else launch_sweep(backward_kernel<1, false>, false, nsl, ctx->stream, items, v, x, ld); }
-    else { if (p) launch_sweep(backward_kernel<SOLVE_NRHS, true>, true, nsl, ctx->stream, items, v, x, ld); else launch_sweep(backward_kernel<SOLVE_NRHS, false>, false, nsl, ctx->stream, items, v, x, ld); }
-    first = false;
-    ctx->launches++;
+    const int nbig = D.bwdb_ptr[l + 1] - D.bwdb_ptr[l], nt = D.bwd_tptr[l + 1] - D.bwd_tptr[l];
+    if (nbig > 0) {
+      const BwdItem* items = D.bwdb_items.p + D.bwdb_ptr[l];
+      if (nrhs == 1) { if (pdl) launch_sweep(backward_kernel<1, true>, true, nbig, ctx->stream, items, v, x, ld); else launch_sweep(backward_kernel<1, false>, false, nbig, ctx->stream, items, v, x, ld); }
+      else { if (pdl) launch_sweep(backward_kernel<SOLVE_NRHS, true>, true, nbig, ctx->stream, items, v, x, ld); else launch_sweep(backward_kernel<SOLVE_NRHS, false>, false, nbig, ctx->stream, items, v, x, ld); }
+      ctx->launches++;
+    }
+    if (nt > 0) {
+      const BwdTask* tasks = D.bwd_tasks.p + D.bwd_tptr[l];
+      const int grid = (nt + 7) / 8;
+      if (nrhs == 1) { if (pdl) launch_sweep(backward_small_kernel<1, true>, true, grid, ctx->stream, tasks, nt, D.strct.p, D.fac.p, x, ld); else launch_sweep(backward_small_kernel<1, false>, false, grid, ctx->stream, tasks, nt, D.strct.p, D.fac.p, x, ld); }
+      else { if (pdl) launch_sweep(backward_small_kernel<SOLVE_NRHS, true>, true, grid, ctx->stream, tasks, nt, D.strct.p, D.fac.p, x, ld); else launch_sweep(backward_small_kernel<SOLVE_NRHS, false>, false, grid, ctx->stream, tasks, nt, D.strct.p, D.fac.p, x, ld); }
+      ctx->launches++;
+    }
   }
 }
 
@@ -781,7 +1298,7 @@ int op_grid_size(plfem_ctx* ctx, int ctas_per_sm) {
 void run_operator(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, const double* d_sigma_node, const double* b,
                   double* x, double* rt, double* rdx, int refine, int ctas_per_sm) {
   OpArgs a;
-  a.P = view(D);
+  a.P = sweep_view(D);
   a.fwd_q = D.fwd_items.p; a.bwd_q = D.bwd_q.p; a.gsrc = D.gsrc.p; a.n_fwd = D.n_fwd; a.n_bwd = D.n_bwd;
   a.fdone = D.fdone.p; a.bdone = D.bdone.p; a.status = D.status.p; a.nfs = D.nfs.p;
   a.epoch0 = D.epoch; D.epoch += 1 + refine;
