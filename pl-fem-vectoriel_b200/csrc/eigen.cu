@@ -197,32 +197,100 @@ __global__ void __launch_bounds__(128) rotate_kernel(const double* __restrict__ 
   }
 }
 
+// Out_b[:, c] = sum_j In_b[:, j] * S_b[j, c]  for c < nout, every design of the forest in one launch (S_b at S + b*sstride)
+__global__ void __launch_bounds__(128) rotate_forest_kernel(const double* __restrict__ In, int64_t ld, int nin,
+                                                            const double* __restrict__ S, int64_t sstride, int nout,
+                                                            const int64_t* __restrict__ moff, double* __restrict__ Out, int64_t ldo) {
+  const int b = blockIdx.y;
+  const int64_t i = moff[b] + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= moff[b + 1]) return;
+  const double* Sb = S + b * sstride;
+  for (int c0 = 0; c0 < nout; c0 += 8) {
+    double acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.0;
+    for (int j = 0; j < nin; ++j) {
+      const double v = In[(int64_t)j * ld + i];
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c0 + c < nout) acc[c] = fma(v, __ldg(Sb + (int64_t)(c0 + c) * nin + j), acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c0 + c < nout) Out[(int64_t)(c0 + c) * ldo + i] = acc[c];
+  }
+}
+
 // ---- block Lanczos pieces (P = SOLVE_NRHS vectors per block), batched over the designs of a forest ------------
 // All vectors are concatenations over the designs: design b owns rows [moff[b], moff[b+1]).  Everything that
 // couples rows — inner products, the small Cholesky, the coefficient matrices — is per design (blockIdx.y);
 // with one design the kernels do exactly what the single-design versions did.
 constexpr int P = SOLVE_NRHS;
 
-// H_b[c + r*ldh] = <Q_b[:,c], R_b[:,r]> for c < ncols, r < P; one CTA per (column c, design b)
-__global__ void __launch_bounds__(RED_T) dots_block_kernel(const double* __restrict__ Q, int64_t ld, const double* __restrict__ R,
-                                                           const int64_t* __restrict__ moff, double* __restrict__ H, int ldh,
-                                                           int64_t hstride) {
-  __shared__ double sh[32];
-  const int b = blockIdx.y;
-  const int64_t m0 = moff[b], m1 = moff[b + 1];
-  const double* q = Q + (int64_t)blockIdx.x * ld;
-  double acc[P];
+// Deterministic CTA reduction of N accumulators at once: shuffles inside the warps, one trip through shared memory,
+// one barrier.  sh holds N * (blockDim.x / 32) doubles; thread t < N returns the total of accumulator t.
+template <int N>
+__device__ __forceinline__ double block_sum_n(double (&acc)[N], double* sh) {
+  const int lane = threadIdx.x % 32, warp = threadIdx.x / 32, nw = blockDim.x / 32;
 #pragma unroll
-  for (int r = 0; r < P; ++r) acc[r] = 0.0;
-  for (int64_t i = m0 + threadIdx.x; i < m1; i += RED_T) {
-    const double qv = q[i];
+  for (int a = 0; a < N; ++a) {
+    double v = acc[a];
 #pragma unroll
-    for (int r = 0; r < P; ++r) acc[r] = fma(qv, R[r * ld + i], acc[r]);
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if (lane == 0) sh[a * nw + warp] = v;
   }
+  __syncthreads();
+  double t = 0.0;
+  if ((int)threadIdx.x < N)
+    for (int w = 0; w < nw; ++w) t += sh[threadIdx.x * nw + w];
+  return t;
+}
+
+constexpr int DCOLS = 8;    // basis columns per CTA of the projection kernel: the block R is read once per 8 columns
+constexpr int RSPLIT = 8;   // row slices per design (fixed: the summation order does not depend on the forest)
+
+// Hp_b[s][c + r*ldh] = <Q_b[rows of slice s, c], R_b[rows of slice s, r]> for c < ncols, r < P;
+// one CTA per (group of DCOLS columns, row slice s, design b)
+__global__ void __launch_bounds__(256) dots_block_kernel(const double* __restrict__ Q, int64_t ld, const double* __restrict__ R,
+                                                         const int64_t* __restrict__ moff, int ncols, double* __restrict__ Hp, int ldh,
+                                                         int64_t hstride) {
+  __shared__ double sh[DCOLS * P * 8];
+  const int b = blockIdx.z, sl = blockIdx.y, c0 = blockIdx.x * DCOLS;
+  const int64_t m0 = moff[b], mlen = moff[b + 1] - m0;
+  const int64_t chunk = (mlen + RSPLIT - 1) / RSPLIT;
+  const int64_t i0 = m0 + sl * chunk, i1 = min(m0 + mlen, i0 + chunk);
+  const int nc = min(DCOLS, ncols - c0);
+  const double* q = Q + (int64_t)c0 * ld;
+  double acc[DCOLS * P];
+#pragma unroll
+  for (int a = 0; a < DCOLS * P; ++a) acc[a] = 0.0;
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += 256) {
+    double rv[P], qv[DCOLS];
+#pragma unroll
+    for (int r = 0; r < P; ++r) rv[r] = R[r * ld + i];
+#pragma unroll
+    for (int c = 0; c < DCOLS; ++c) qv[c] = c < nc ? q[c * ld + i] : 0.0;
+#pragma unroll
+    for (int c = 0; c < DCOLS; ++c)
+#pragma unroll
+      for (int r = 0; r < P; ++r) acc[c * P + r] = fma(qv[c], rv[r], acc[c * P + r]);
+  }
+  const double t = block_sum_n<DCOLS * P>(acc, sh);
+  const int c = threadIdx.x / P, r = threadIdx.x % P;
+  if ((int)threadIdx.x < DCOLS * P && c < nc) Hp[(b * RSPLIT + sl) * hstride + c0 + c + r * ldh] = t;
+}
+
+// H_b = sum over the row slices of Hp_b (fixed order)
+__global__ void sum_slices_kernel(const double* __restrict__ Hp, int ldh, int64_t hstride, int ncols, double* __restrict__ H) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (c >= ncols) return;
 #pragma unroll
   for (int r = 0; r < P; ++r) {
-    const double t = block_sum(acc[r], sh);
-    if (threadIdx.x == 0) H[b * hstride + blockIdx.x + r * ldh] = t;
+    double t = 0.0;
+#pragma unroll
+    for (int sl = 0; sl < RSPLIT; ++sl) t += Hp[(b * RSPLIT + sl) * hstride + c + r * ldh];
+    H[b * hstride + c + r * ldh] = t;
   }
 }
 
@@ -256,36 +324,45 @@ __global__ void store_h_kernel(const double* __restrict__ h1, const double* __re
   for (int r = 0; r < P; ++r) Hs[b * sstride + c + r * lds] = h1[b * hstride + c + r * ldh] + h2[b * hstride + c + r * ldh];
 }
 
-// G_b[r + s*P] = <R_b[:,r], U_b[:,s]>, one CTA per (r, design)
-__global__ void __launch_bounds__(RED_T) gram_kernel(const double* __restrict__ R, const double* __restrict__ U, int64_t ld,
-                                                     const int64_t* __restrict__ moff, double* __restrict__ G) {
-  __shared__ double sh[32];
-  const int b = blockIdx.y;
-  const int64_t m0 = moff[b], m1 = moff[b + 1];
-  const double* rr = R + (int64_t)blockIdx.x * ld;
-  double acc[P];
+// Gp_b[s][r + q*P] = <R_b[slice s, r], U_b[slice s, q]>, one CTA per (row slice, design): R and U are read once
+__global__ void __launch_bounds__(256) gram_kernel(const double* __restrict__ R, const double* __restrict__ U, int64_t ld,
+                                                   const int64_t* __restrict__ moff, double* __restrict__ Gp) {
+  __shared__ double sh[P * P * 8];
+  const int b = blockIdx.y, sl = blockIdx.x;
+  const int64_t m0 = moff[b], mlen = moff[b + 1] - m0;
+  const int64_t chunk = (mlen + RSPLIT - 1) / RSPLIT;
+  const int64_t i0 = m0 + sl * chunk, i1 = min(m0 + mlen, i0 + chunk);
+  double acc[P * P];
 #pragma unroll
-  for (int s2 = 0; s2 < P; ++s2) acc[s2] = 0.0;
-  for (int64_t i = m0 + threadIdx.x; i < m1; i += RED_T) {
-    const double v = rr[i];
+  for (int a = 0; a < P * P; ++a) acc[a] = 0.0;
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += 256) {
+    double rv[P], uv[P];
 #pragma unroll
-    for (int s2 = 0; s2 < P; ++s2) acc[s2] = fma(v, U[s2 * ld + i], acc[s2]);
+    for (int r = 0; r < P; ++r) { rv[r] = R[r * ld + i]; uv[r] = U[r * ld + i]; }
+#pragma unroll
+    for (int q = 0; q < P; ++q)
+#pragma unroll
+      for (int r = 0; r < P; ++r) acc[r + q * P] = fma(rv[r], uv[q], acc[r + q * P]);
   }
-#pragma unroll
-  for (int s2 = 0; s2 < P; ++s2) {
-    const double t = block_sum(acc[s2], sh);
-    if (threadIdx.x == 0) G[b * P * P + blockIdx.x + s2 * P] = t;
-  }
+  const double t = block_sum_n<P * P>(acc, sh);
+  if ((int)threadIdx.x < P * P) Gp[(b * RSPLIT + sl) * P * P + threadIdx.x] = t;
 }
 
-// Cholesky G_b = L L^T (P x P, symmetrised), Linv = L^-1, one CTA per design.  Lout (for the host): L, column-major,
-// slot `slot` of design b.  cstat[b] = 1 on breakdown (the residual block of that design lost rank).
-__global__ void chol_kernel(const double* __restrict__ G, double* __restrict__ Lall, int nslots, int slot, double* __restrict__ Linv,
+// Cholesky G_b = L L^T (P x P, G_b = sum of the slices of Gp_b, symmetrised), Linv = L^-1, one CTA per design.  Lout (for
+// the host): L, column-major, slot `slot` of design b.  cstat[b] = 1 on breakdown (the residual block of that design
+// lost rank).
+__global__ void chol_kernel(const double* __restrict__ Gp, double* __restrict__ Lall, int nslots, int slot, double* __restrict__ Linv,
                             int32_t* __restrict__ cstat) {
   if (threadIdx.x != 0) return;
   const int b = blockIdx.x;
-  G += b * P * P; Linv += b * P * P;
+  Linv += b * P * P;
   double* Lout = Lall + ((size_t)b * nslots + slot) * P * P;
+  double G[P * P];
+  for (int a = 0; a < P * P; ++a) {
+    double t = 0.0;
+    for (int sl = 0; sl < RSPLIT; ++sl) t += Gp[(b * RSPLIT + sl) * P * P + a];
+    G[a] = t;
+  }
   double A[P][P], L[P][P], Li[P][P];
   for (int i = 0; i < P; ++i) for (int j = 0; j < P; ++j) { A[i][j] = 0.5 * (G[i + j * P] + G[j + i * P]); L[i][j] = 0.0; Li[i][j] = 0.0; }
   double dmax = 0.0;
@@ -686,8 +763,10 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
   R.alloc(ctx, (size_t)m * P); U.alloc(ctx, (size_t)m * P); rt.alloc(ctx, (size_t)m * P); rdx.alloc(ctx, (size_t)m * P);
   opin.alloc(ctx, (size_t)m * P);
   h1.alloc(ctx, (size_t)B * hstride); h2.alloc(ctx, (size_t)B * hstride); Hs.alloc(ctx, (size_t)B * sstride);
-  G.alloc(ctx, (size_t)B * P * P); Lall.alloc(ctx, (size_t)B * nslots * P * P); Linv.alloc(ctx, (size_t)B * P * P);
-  Sdev.alloc(ctx, (size_t)ncvp * ncvp);
+  DevBuf<double> hp;                                   // per-slice partial projections
+  hp.alloc(ctx, (size_t)B * RSPLIT * hstride);
+  G.alloc(ctx, (size_t)B * RSPLIT * P * P); Lall.alloc(ctx, (size_t)B * nslots * P * P); Linv.alloc(ctx, (size_t)B * P * P);
+  Sdev.alloc(ctx, (size_t)B * ncvp * ncvp);
   cstat.alloc(ctx, B); cstat.zero();
   const unsigned gm = (unsigned)((m + 255) / 256);
   const dim3 grows((unsigned)((bd.mmax + 255) / 256), B);
@@ -717,7 +796,7 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
   // B-orthonormalise the block in R, per design: U = B R, G = R^T U = L L^T, Vn = R L^-T, BVn = U L^-T; L kept in slot `slot`
   auto orthonormalize = [&](double* Vn, double* BVn, int slot) {
     launch_spmm_b(ctx, pat, d_vals, R.p, U.p, P, ld);
-    gram_kernel<<<dim3(P, B), RED_T, 0, st>>>(R.p, U.p, ld, moff, G.p);
+    gram_kernel<<<dim3(RSPLIT, B), 256, 0, st>>>(R.p, U.p, ld, moff, G.p);
     chol_kernel<<<B, 32, 0, st>>>(G.p, Lall.p, nslots, slot, Linv.p, cstat.p);
     scale_block_kernel<<<grows, 256, 0, st>>>(R.p, U.p, ld, moff, Linv.p, Vn, BVn);
     ctx->launches += 3;
@@ -757,12 +836,15 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
     PLFEM_CUDA(cudaGraphLaunch(gexec, st));
     ctx->launches += graph_nodes;
     res.n_op += P; res.n_block_op++;
-    dots_block_kernel<<<dim3(nb, B), RED_T, 0, st>>>(BVc, ld, R.p, moff, h1.p, ldh, hstride);
+    const dim3 gdots((nb + DCOLS - 1) / DCOLS, RSPLIT, B), gsum((nb + 127) / 128, B);
+    dots_block_kernel<<<gdots, 256, 0, st>>>(BVc, ld, R.p, moff, nb, hp.p, ldh, hstride);          // CGS pass 1
+    sum_slices_kernel<<<gsum, 128, 0, st>>>(hp.p, ldh, hstride, nb, h1.p);
     update_block_kernel<<<grows, 256, 0, st>>>(Vc, ld, h1.p, ldh, hstride, nb, moff, R.p);
-    dots_block_kernel<<<dim3(nb, B), RED_T, 0, st>>>(BVc, ld, R.p, moff, h2.p, ldh, hstride);
+    dots_block_kernel<<<gdots, 256, 0, st>>>(BVc, ld, R.p, moff, nb, hp.p, ldh, hstride);          // CGS pass 2
+    sum_slices_kernel<<<gsum, 128, 0, st>>>(hp.p, ldh, hstride, nb, h2.p);
     update_block_kernel<<<grows, 256, 0, st>>>(Vc, ld, h2.p, ldh, hstride, nb, moff, R.p);
-    store_h_kernel<<<dim3((nb + 127) / 128, B), 128, 0, st>>>(h1.p, h2.p, ldh, hstride, nb, Hs.p + (size_t)j0 * ldh, ldh, sstride);
-    ctx->launches += 5;
+    store_h_kernel<<<gsum, 128, 0, st>>>(h1.p, h2.p, ldh, hstride, nb, Hs.p + (size_t)j0 * ldh, ldh, sstride);
+    ctx->launches += 7;
     orthonormalize(Vc + (int64_t)nb * ld, BVc + (int64_t)nb * ld, j0 / P);
     nb += P;
     ++since_check;
@@ -858,25 +940,29 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
     q = 0;
     for (int b = 0; b < B; ++b) if (!hs[b].done) q = std::max(q, hs[b].q_want);
     const int nxt = cur ^ 1;
-    for (int b = 0; b < B; ++b) {
-      Host& h = hs[b];
-      std::vector<double> S((size_t)ncvp * q, 0.0);
-      if (h.done) {
-        for (int i = 0; i < q; ++i) S[(size_t)i * ncvp + i] = 1.0;        // finished: carried along, values stay finite
-      } else {
-        std::fill(h.Th.begin(), h.Th.end(), 0.0);
-        for (int i = 0; i < q; ++i) {
-          const int col = h.order[i];
-          std::copy(h.T.begin() + (size_t)col * ncvp, h.T.begin() + (size_t)(col + 1) * ncvp, S.begin() + (size_t)i * ncvp);
-          h.Th[(size_t)i * ncvp + i] = h.w[col];
+    {
+      const int64_t sst = (int64_t)ncvp * q;
+      std::vector<double> S((size_t)B * sst, 0.0);
+      for (int b = 0; b < B; ++b) {
+        Host& h = hs[b];
+        double* Sb = S.data() + (size_t)b * sst;
+        if (h.done) {
+          for (int i = 0; i < q; ++i) Sb[(size_t)i * ncvp + i] = 1.0;        // finished: carried along, values stay finite
+        } else {
+          std::fill(h.Th.begin(), h.Th.end(), 0.0);
+          for (int i = 0; i < q; ++i) {
+            const int col = h.order[i];
+            std::copy(h.T.begin() + (size_t)col * ncvp, h.T.begin() + (size_t)(col + 1) * ncvp, Sb + (size_t)i * ncvp);
+            h.Th[(size_t)i * ncvp + i] = h.w[col];
+          }
         }
       }
       PLFEM_CUDA(cudaMemcpyAsync(Sdev.p, S.data(), S.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-      const int64_t mb = bd.moff[b + 1] - bd.moff[b], o = bd.moff[b];
-      rotate_kernel<<<(unsigned)((mb + 127) / 128), 128, 0, st>>>(V[cur].p + o, ld, ncvp, Sdev.p, q, mb, V[nxt].p + o, ld);
-      rotate_kernel<<<(unsigned)((mb + 127) / 128), 128, 0, st>>>(BV[cur].p + o, ld, ncvp, Sdev.p, q, mb, BV[nxt].p + o, ld);
+      const dim3 grot((unsigned)((bd.mmax + 127) / 128), B);
+      rotate_forest_kernel<<<grot, 128, 0, st>>>(V[cur].p, ld, ncvp, Sdev.p, sst, q, moff, V[nxt].p, ld);
+      rotate_forest_kernel<<<grot, 128, 0, st>>>(BV[cur].p, ld, ncvp, Sdev.p, sst, q, moff, BV[nxt].p, ld);
       ctx->launches += 2;
-      PLFEM_CUDA(cudaStreamSynchronize(st));   // S is a local host buffer, Sdev is reused
+      PLFEM_CUDA(cudaStreamSynchronize(st));   // S is a local host buffer
     }
     PLFEM_CUDA(cudaMemcpyAsync(V[nxt].p + (int64_t)q * ld, V[cur].p + (int64_t)ncvp * ld, (size_t)m * P * sizeof(double), cudaMemcpyDeviceToDevice, st));
     PLFEM_CUDA(cudaMemcpyAsync(BV[nxt].p + (int64_t)q * ld, BV[cur].p + (int64_t)ncvp * ld, (size_t)m * P * sizeof(double), cudaMemcpyDeviceToDevice, st));

@@ -1051,7 +1051,11 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
   std::vector<FwdItem> fwb; std::vector<BwdItem> bwb;     // per-level launches: CTA items of large fronts ...
   std::vector<FwdTask> ft; std::vector<BwdTask> bt;       // ... and warp tasks of small ones
   D.fwd_tptr.assign(P.nlevels + 1, 0); D.bwd_tptr = D.fwdb_ptr = D.bwdb_ptr = D.fwd_tptr;
+  // which fronts take the warp-per-task path: by default the LEAVES of the elimination tree (no children to gather
+  // from, hundreds per design, ~75 x 30 entries each: a 256-thread CTA per leaf is bound by CTA turnover); the limits
+  // widen it to every front with at most that many pivot / update unknowns
   const int small_s2 = small_front_limit("PLFEM_SMALL_S2", 0), small_u2 = small_front_limit("PLFEM_SMALL_U2", 0);
+  const bool leaf_warp = small_front_limit("PLFEM_LEAF_WARP", 1) != 0;
   D.w_ptr.assign(P.nlevels + 1, 0); D.s_ptr = D.ea_ptr = D.fwd_ptr = D.bwd_ptr = D.w_ptr;
   D.lmax_m.assign(P.nlevels, 0);
   // flattened child -> parent gather: per front, for every front row (2nf unknowns) the offset into the
@@ -1097,7 +1101,7 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
         // row groups x rows per thread: <= 32 rows (1,1), <= 64 (1,2), <= 128 (2,2), larger fronts in slabs of 64 rows (1,2)
         const int G = (rows > 64 && rows <= 128) ? 2 : 1, Rr = rows <= 32 ? 1 : 2;
         const int nch = P.cptr[f + 1] - P.cptr[f];
-        const bool fsmall = s2 <= small_s2;
+        const bool fsmall = s2 <= small_s2 || (leaf_warp && nch == 0 && s2 <= 64);
         for (int r0 = 0; r0 < rows; r0 += 32 * G * Rr) {
           FwdItem it{};
           it.f = f; it.row0 = r0; it.nrows = std::min(32 * G * Rr, rows - r0); it.G = G | (Rr << 8); it.s2 = s2; it.ld = ldp[f];
@@ -1120,7 +1124,7 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
         }
       }
       if (u2 > 0) {
-        const bool bsmall = s2 <= small_s2 && u2 <= small_u2;
+        const bool bsmall = (s2 <= small_s2 && u2 <= small_u2) || (leaf_warp && P.cptr[f + 1] == P.cptr[f] && s2 <= 64 && u2 <= 128);
         const bool rows_style = u2 <= bwd_rows_u2;
         const int Gb = rows_style ? (s2 <= 32 ? 1 : 2) : 0;   // pivot columns per thread; 0 = one warp per column
         const int cw = rows_style ? 32 * Gb : BWD_COLS;
