@@ -3,12 +3,12 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg1|cfg2]
 
-A *step* is one FOREST of ``--inflight`` (default 8) independent modal solves of the workload's
+A *step* is one FOREST of ``--inflight`` (default 16) independent modal solves of the workload's
 cross-section: the designs are solved together as one block-diagonal problem by one C-ABI call
 (`plfem_solve_modes_batch`), sharing every kernel launch — the sweep's production mode.  A modal
 solve is `solve_vectorial_modes`: DOF tables -> assembly -> Dirichlet elimination -> ordering +
 factorisation of A - sigma*B -> eigensolve -> per-mode reductions, all of it done per design (nothing
-is reused between the designs of a forest).  ``--workers`` (default 2) host threads each drive their
+is reused between the designs of a forest).  ``--workers`` (default 3) host threads each drive their
 own forest, so the host-side symbolic analysis of one forest overlaps the device work of another.
 The mesh is given (built on the host before timing, as in the reference where `MeshGenerator` runs
 first).  ``latency`` in the JSON line is one solve run alone.
@@ -364,8 +364,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg1", choices=sorted(WORKLOADS))
-    ap.add_argument("--inflight", type=int, default=8, help="designs per forest (= per step)")
-    ap.add_argument("--workers", type=int, default=2, help="host threads / contexts, each working on its own forest")
+    ap.add_argument("--inflight", type=int, default=16, help="designs per forest (= per step)")
+    ap.add_argument("--workers", type=int, default=3, help="host threads / contexts, each working on its own forest")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     if args.impl == "reference":

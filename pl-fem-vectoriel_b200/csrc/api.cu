@@ -789,9 +789,9 @@ static void profile_work(plfem_ctx* ctx, SolveWork& W, int repeat, double* out_m
     DevBuf<double> b4, x4;
     b4.alloc(ctx, (size_t)m * SOLVE_NRHS); x4.alloc(ctx, (size_t)m * SOLVE_NRHS);
     for (int r = 0; r < SOLVE_NRHS; ++r) PLFEM_CUDA(cudaMemcpyAsync(b4.p + r * m, b.p, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    out_ms[6] = timed([&] { run_solve_forward(ctx, W.dplan, b4.p, x4.p, SOLVE_NRHS, m); });
+    out_ms[6] = timed([&] { run_solve_forward(ctx, W.dplan, b4.p, x4.p, SOLVE_NRHS); });
     out_bytes[6] = out_bytes[2] + 16.0 * m * (SOLVE_NRHS - 1);
-    out_ms[7] = timed([&] { run_solve_backward(ctx, W.dplan, x4.p, SOLVE_NRHS, m); });
+    out_ms[7] = timed([&] { run_solve_backward(ctx, W.dplan, x4.p, SOLVE_NRHS); });
     out_bytes[7] = out_bytes[3] + 16.0 * m * (SOLVE_NRHS - 1);
   }
 }

@@ -192,13 +192,14 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D);
 // d_sigma_node: the shift of the design each (permuted) node belongs to — a forest of designs is one problem
 void launch_front_load(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, const double* d_sigma_node);
 void run_factorization(plfem_ctx* ctx, const DevPlan& D);
-// solves (A - sigma B) x = b in the permuted interleaved layout, b and x of length 2n (must not alias)
+// solves (A - sigma B) x = b in the permuted layout (Hx, Hy of a node adjacent), b and x of length 2n (must not alias);
+// with nrhs = SOLVE_NRHS the right-hand sides are interleaved: entry i of right-hand side r at b[i * nrhs + r]
 constexpr int SOLVE_NRHS = 4;   // block size of the multi-right-hand-side sweeps (block Lanczos)
-void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x, int nrhs = 1, int64_t ld = 0);
+void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x, int nrhs = 1);
 void run_operator(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, const double* d_sigma_node, const double* b,
                   double* x, double* rt, double* rdx, int refine, int ctas_per_sm);
-void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double* z, int nrhs = 1, int64_t ld = 0);
-void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs = 1, int64_t ld = 0);
+void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double* z, int nrhs = 1);
+void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs = 1);
 
 // ---- Lanczos + mode reductions (eigen.cu) ----------------------------------------------------------
 struct EigenResult {
@@ -241,8 +242,9 @@ void run_mode_metrics(plfem_ctx* ctx, const DevPattern& pat, const double* d_val
 
 void launch_spmm_b(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, const double* x, double* y, int nrhs = 1,
                    int64_t ld = 0);
+// t = b - (A - sigma B) x, x / b / t with nrhs interleaved right-hand sides
 void launch_resid_k(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, const double* d_sigma_node, const double* x,
-                    const double* b, double* t, int nrhs = 1, int64_t ld = 0);
+                    const double* b, double* t, int nrhs = 1);
 
 void launch_axpy(plfem_ctx* ctx, double* x, const double* dx, int64_t m);
 void symmetric_eigen(int n, std::vector<double>& a /* n*n col-major in, eigenvectors out */, std::vector<double>& w);

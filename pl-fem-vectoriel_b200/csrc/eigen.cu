@@ -79,13 +79,15 @@ __global__ void __launch_bounds__(256) spmm_b_kernel(int32_t n, const int32_t* _
   }
 }
 
-// T = Bv - (A - sigma B) X on the permuted interleaved layout (iterative refinement of the block-LDL^T solve)
+// T = Bv - (A - sigma B) X (iterative refinement of the block-LDL^T solve).  X, Bv and T hold NR interleaved right-hand
+// sides in the permuted layout: unknown i of right-hand side r at x[i*NR + r], i.e. the 2*NR values of a node are one
+// contiguous 16*NR-byte record
 template <int NR>
 __global__ void __launch_bounds__(256) resid_k_kernel(int32_t n, const int32_t* __restrict__ rowptr,
                                                       const int32_t* __restrict__ col, const double* __restrict__ vals,
                                                       int64_t nnz, const double* __restrict__ sigma_node,
-                                                      const double2* __restrict__ x, const double2* __restrict__ b,
-                                                      double2* __restrict__ t, int64_t ld2) {
+                                                      const double* __restrict__ x, const double* __restrict__ b,
+                                                      double* __restrict__ t) {
   constexpr int TPR = 4;
   const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t row = gid / TPR;
@@ -99,12 +101,12 @@ __global__ void __launch_bounds__(256) resid_k_kernel(int32_t n, const int32_t* 
       const double sm = sigma * vals[(int64_t)S_MINV * nnz + z];
       const double kxx = vals[(int64_t)S_AXX * nnz + z] - sm, kxy = vals[(int64_t)S_AXY * nnz + z];
       const double kyx = vals[(int64_t)S_AYX * nnz + z], kyy = vals[(int64_t)S_AYY * nnz + z] - sm;
-      const int32_t c = col[z];
+      const double* xc = x + 2 * (int64_t)col[z] * NR;
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
-        const double2 v = x[r * ld2 + c];
-        ax[r] = fma(kxx, v.x, ax[r]); ax[r] = fma(kxy, v.y, ax[r]);
-        ay[r] = fma(kyx, v.x, ay[r]); ay[r] = fma(kyy, v.y, ay[r]);
+        const double vx = xc[r], vy = xc[NR + r];
+        ax[r] = fma(kxx, vx, ax[r]); ax[r] = fma(kxy, vy, ax[r]);
+        ay[r] = fma(kyx, vx, ay[r]); ay[r] = fma(kyy, vy, ay[r]);
       }
     }
   }
@@ -115,8 +117,29 @@ __global__ void __launch_bounds__(256) resid_k_kernel(int32_t n, const int32_t* 
       ax[r] += __shfl_down_sync(0xffffffffu, ax[r], off, TPR);
       ay[r] += __shfl_down_sync(0xffffffffu, ay[r], off, TPR);
     }
-    if (row < n && lane == 0) { const double2 bb = b[r * ld2 + row]; t[r * ld2 + row] = make_double2(bb.x - ax[r], bb.y - ay[r]); }
+    if (row < n && lane == 0) {
+      const int64_t o = 2 * row * NR + r;
+      t[o] = b[o] - ax[r];
+      t[o + NR] = b[o + NR] - ay[r];
+    }
   }
+}
+
+// block of P columns (leading dimension ld) -> interleaved right-hand sides
+__global__ void __launch_bounds__(256) interleave_kernel(const double* __restrict__ in, int64_t ld, int64_t m, double* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= m) return;
+#pragma unroll
+  for (int r = 0; r < SOLVE_NRHS; ++r) out[i * SOLVE_NRHS + r] = in[r * ld + i];
+}
+
+// out (P columns, leading dimension ld) = interleaved x (+ interleaved dx when given)
+__global__ void __launch_bounds__(256) deinterleave_add_kernel(const double* __restrict__ x, const double* __restrict__ dx, int64_t ld,
+                                                               int64_t m, double* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= m) return;
+#pragma unroll
+  for (int r = 0; r < SOLVE_NRHS; ++r) out[r * ld + i] = x[i * SOLVE_NRHS + r] + (dx ? dx[i * SOLVE_NRHS + r] : 0.0);
 }
 
 __global__ void __launch_bounds__(256) add_kernel(double* __restrict__ x, const double* __restrict__ dx, int64_t m) {
@@ -526,14 +549,12 @@ void launch_spmm_b(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, 
 }
 
 void launch_resid_k(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, const double* d_sigma_node, const double* x,
-                    const double* b, double* t, int nrhs, int64_t ld) {
+                    const double* b, double* t, int nrhs) {
   const unsigned g = (unsigned)(((int64_t)pat.n * 4 + 255) / 256);
   if (nrhs == 1)
-    resid_k_kernel<1><<<g, 256, 0, ctx->stream>>>(pat.n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz, d_sigma_node, (const double2*)x,
-                                                  (const double2*)b, (double2*)t, 0);
+    resid_k_kernel<1><<<g, 256, 0, ctx->stream>>>(pat.n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz, d_sigma_node, x, b, t);
   else
-    resid_k_kernel<SOLVE_NRHS><<<g, 256, 0, ctx->stream>>>(pat.n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz, d_sigma_node, (const double2*)x,
-                                                           (const double2*)b, (double2*)t, ld / 2);
+    resid_k_kernel<SOLVE_NRHS><<<g, 256, 0, ctx->stream>>>(pat.n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz, d_sigma_node, x, b, t);
   PLFEM_CUDA(cudaGetLastError());
   ctx->launches++;
 }
@@ -762,6 +783,8 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
   for (int b = 0; b < 2; ++b) { V[b].alloc(ctx, (size_t)ld * (ncvp + P)); BV[b].alloc(ctx, (size_t)ld * (ncvp + P)); }
   R.alloc(ctx, (size_t)m * P); U.alloc(ctx, (size_t)m * P); rt.alloc(ctx, (size_t)m * P); rdx.alloc(ctx, (size_t)m * P);
   opin.alloc(ctx, (size_t)m * P);
+  DevBuf<double> xi;                                    // interleaved solution of the block solve
+  xi.alloc(ctx, (size_t)m * P);
   h1.alloc(ctx, (size_t)B * hstride); h2.alloc(ctx, (size_t)B * hstride); Hs.alloc(ctx, (size_t)B * sstride);
   DevBuf<double> hp;                                   // per-slice partial projections
   hp.alloc(ctx, (size_t)B * RSPLIT * hstride);
@@ -777,12 +800,15 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
     const int before = ctx->launches;
     PLFEM_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     try {
-      run_solve(ctx, D, opin.p, R.p, P, ld);
+      // interleaved right-hand sides inside the solve: opin -> xi (+ refinement) -> R (columns again)
+      run_solve(ctx, D, opin.p, xi.p, P);
       for (int it = 0; it < refine_steps; ++it) {
-        launch_resid_k(ctx, pat, d_vals, d_sigma_node, R.p, opin.p, rt.p, P, ld);
-        run_solve(ctx, D, rt.p, rdx.p, P, ld);
-        launch_axpy(ctx, R.p, rdx.p, m * P);
+        launch_resid_k(ctx, pat, d_vals, d_sigma_node, xi.p, opin.p, rt.p, P);
+        run_solve(ctx, D, rt.p, rdx.p, P);
+        if (it + 1 < refine_steps) launch_axpy(ctx, xi.p, rdx.p, m * P);
       }
+      deinterleave_add_kernel<<<gm, 256, 0, st>>>(xi.p, refine_steps > 0 ? rdx.p : nullptr, ld, m, R.p);
+      ctx->launches++;
     } catch (...) {
       cudaGraph_t dead = nullptr; cudaStreamEndCapture(st, &dead); if (dead) cudaGraphDestroy(dead);
       throw;
@@ -825,14 +851,15 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
   res = EigenResult();
   X.alloc(ctx, (size_t)m * kmax);
   const double eps23 = std::pow(2.220446049250313e-16, 2.0 / 3.0);
-  const int check_every = 2;
+  static const int check_every = [] { const char* e = std::getenv("PLFEM_CHECK_EVERY"); return e ? std::max(1, atoi(e)) : 2; }();
   int since_check = 0;
   auto check_from = [&](int k) { return std::min(ncvp, ((2 * k + P - 1) / P) * P); };
   for (;;) {
     // ---- one block step: image of the last P basis vectors
     const int j0 = nb - P;
     double* Vc = V[cur].p; double* BVc = BV[cur].p;
-    PLFEM_CUDA(cudaMemcpyAsync(opin.p, BVc + (int64_t)j0 * ld, (size_t)m * P * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    interleave_kernel<<<gm, 256, 0, st>>>(BVc + (int64_t)j0 * ld, ld, m, opin.p);
+    ctx->launches++;
     PLFEM_CUDA(cudaGraphLaunch(gexec, st));
     ctx->launches += graph_nodes;
     res.n_op += P; res.n_block_op++;

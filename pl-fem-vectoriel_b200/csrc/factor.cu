@@ -281,14 +281,41 @@ struct SweepSmem {
   double part[8][2][NR][32];      // partial sums: [warp][row of the thread][rhs][lane]
 };
 
-struct RhsView {   // NR right-hand sides stored as columns: rhs + r*ldr, out + r*ldo, update pool + r*ldu
-  const double* rhs; int64_t ldr; double* out; int64_t ldo; double* upd; int64_t ldu;
+// The NR right-hand sides of a sweep are INTERLEAVED: entry i of all of them is rhs[i*NR .. i*NR+NR), one 32-byte
+// sector for NR = 4.  Every gather of the sweeps (children's updates, ancestors' unknowns) fetches all right-hand
+// sides of an index at once, so this costs one sector and two 128-bit loads per index instead of four of each.
+struct RhsView {
+  const double* rhs; double* out; double* upd;
 };
 
 // CG = true: values produced by other CTAs of the SAME launch (dataflow kernel) are read with ld.global.cg,
 // i.e. from L2, never from a possibly stale L1 line.
 template <bool CG>
 __device__ __forceinline__ double ldx(const double* p) { return CG ? __ldcg(p) : *p; }
+
+// all NR right-hand sides of entry idx of an interleaved vector block
+template <bool CG, int NR>
+__device__ __forceinline__ void ldv(const double* base, int64_t idx, double (&v)[NR]) {
+  if constexpr (NR % 2 == 0) {
+    const double2* p = reinterpret_cast<const double2*>(base + idx * NR);
+#pragma unroll
+    for (int r = 0; r < NR / 2; ++r) { const double2 t = CG ? __ldcg(p + r) : p[r]; v[2 * r] = t.x; v[2 * r + 1] = t.y; }
+  } else {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) v[r] = ldx<CG>(base + idx * NR + r);
+  }
+}
+template <int NR>
+__device__ __forceinline__ void stv(double* base, int64_t idx, const double (&v)[NR]) {
+  if constexpr (NR % 2 == 0) {
+    double2* p = reinterpret_cast<double2*>(base + idx * NR);
+#pragma unroll
+    for (int r = 0; r < NR / 2; ++r) p[r] = make_double2(v[2 * r], v[2 * r + 1]);
+  } else {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) base[idx * NR + r] = v[r];
+  }
+}
 
 __device__ __forceinline__ void wait_count(const int32_t* ctr, int32_t target, int32_t* status) {
   const volatile int32_t* v = ctr;
@@ -378,26 +405,38 @@ __device__ __forceinline__ void forward_item_r(const FwdItem& it, const int32_t*
   }
   // ---- dynamic part: right-hand side + children's updates, fixed order (rhs + first child) + second child
   if (tid < s2) {
+    double v[NR], w[NR];
+    ldv<CG, NR>(rv.rhs, it.g0 + tid, v);
+    if (i1 >= 0) {
+      ldv<CG, NR>(rv.upd, i1, w);
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      const double* up = rv.upd + r * rv.ldu;
-      double v = ldx<CG>(rv.rhs + r * rv.ldr + it.g0 + tid);
-      if (i1 >= 0) v += ldx<CG>(up + i1);
-      if (i2 >= 0) v += ldx<CG>(up + i2);
-      sm.y[tid][r] = v;
+      for (int r = 0; r < NR; ++r) v[r] += w[r];
     }
+    if (i2 >= 0) {
+      ldv<CG, NR>(rv.upd, i2, w);
+#pragma unroll
+      for (int r = 0; r < NR; ++r) v[r] += w[r];
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) sm.y[tid][r] = v[r];
   }
   double yt[R][NR];                          // what the children send to this thread's update rows (final-stage threads)
 #pragma unroll
-  for (int q = 0; q < R; ++q)
+  for (int q = 0; q < R; ++q) {
+    double w[NR];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      const double* up = rv.upd + r * rv.ldu;
-      double v = 0.0;
-      if (j1[q] >= 0) v += ldx<CG>(up + j1[q]);
-      if (j2[q] >= 0) v += ldx<CG>(up + j2[q]);
-      yt[q][r] = v;
+    for (int r = 0; r < NR; ++r) yt[q][r] = 0.0;
+    if (j1[q] >= 0) {
+      ldv<CG, NR>(rv.upd, j1[q], w);
+#pragma unroll
+      for (int r = 0; r < NR; ++r) yt[q][r] += w[r];
     }
+    if (j2[q] >= 0) {
+      ldv<CG, NR>(rv.upd, j2[q], w);
+#pragma unroll
+      for (int r = 0; r < NR; ++r) yt[q][r] += w[r];
+    }
+  }
   __syncthreads();
   if (it.nchild > 2) {                       // rare (a separator that does not disconnect): generic path
     for (int c = P.cptr[it.f] + 2; c < P.cptr[it.f + 1]; ++c) {
@@ -405,16 +444,16 @@ __device__ __forceinline__ void forward_item_r(const FwdItem& it, const int32_t*
       const int uc2 = 2 * front_u(P, ch);
       const int32_t* cm = P.cmap + P.cmap_ptr[ch];
       for (int r = 0; r < NR; ++r) {
-        const double* uv = rv.upd + r * rv.ldu + P.uoff[ch];
+        const double* uv = rv.upd + (int64_t)P.uoff[ch] * NR + r;      // entry k of right-hand side r at uv[k * NR]
         for (int k = tid; k < uc2; k += 256) {
           const int t = 2 * cm[k >> 1] + (k & 1);
-          if (t < s2) sm.y[t][r] += ldx<CG>(uv + k);
+          if (t < s2) sm.y[t][r] += ldx<CG>(uv + (int64_t)k * NR);
         }
         if (ks == 0) {
           for (int k = 0; k < uc2; ++k) {
             const int t = 2 * cm[k >> 1] + (k & 1);
 #pragma unroll
-            for (int q = 0; q < R; ++q) if (ok[q] && t == row0 + lr[q] && t >= s2) yt[q][r] += ldx<CG>(uv + k);
+            for (int q = 0; q < R; ++q) if (ok[q] && t == row0 + lr[q] && t >= s2) yt[q][r] += ldx<CG>(uv + (int64_t)k * NR);
           }
         }
       }
@@ -458,13 +497,15 @@ __device__ __forceinline__ void forward_item_r(const FwdItem& it, const int32_t*
     for (int q = 0; q < R; ++q) {
       if (!ok[q]) continue;
       const int row = row0 + lr[q];
+      double o[NR];
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
         double t = 0.0;
         for (int c = 0; c < nks; ++c) t += sm.part[c * G + rg][q][r][lane];
-        if (row < s2) rv.out[r * rv.ldo + it.g0 + row] = t;
-        else rv.upd[r * rv.ldu + it.uoff + (row - s2)] = yt[q][r] - t;
+        o[r] = row < s2 ? t : yt[q][r] - t;
       }
+      if (row < s2) stv<NR>(rv.out, it.g0 + row, o);
+      else stv<NR>(rv.upd, (int64_t)it.uoff + (row - s2), o);
     }
   }
 }
@@ -488,7 +529,7 @@ struct BwdSmem {
 };
 
 template <bool CG, int NR, int R, bool PDL>
-__device__ __forceinline__ void backward_item_r(const BwdItem& it, const PlanView& P, double* x, int64_t ldx_, BwdSmem<NR>& sm,
+__device__ __forceinline__ void backward_item_r(const BwdItem& it, const PlanView& P, double* x, BwdSmem<NR>& sm,
                                                 const Deps& dp) {
   constexpr int FQR = FQ / R;
   constexpr int nks = 8;
@@ -540,10 +581,17 @@ __device__ __forceinline__ void backward_item_r(const BwdItem& it, const PlanVie
       if (tid < jn) o0 = 2 * (int64_t)st[(j0 + tid) >> 1] + (tid & 1);
       if (tid + 256 < jn) o1 = 2 * (int64_t)st[(j0 + tid + 256) >> 1] + (tid & 1);
     }
+    if (o0 >= 0) {
+      double v[NR];
+      ldv<CG, NR>(x, o0, v);
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      if (o0 >= 0) sm.xs[tid][r] = ldx<CG>(x + r * ldx_ + o0);
-      if (o1 >= 0) sm.xs[tid + 256][r] = ldx<CG>(x + r * ldx_ + o1);
+      for (int r = 0; r < NR; ++r) sm.xs[tid][r] = v[r];
+    }
+    if (o1 >= 0) {
+      double v[NR];
+      ldv<CG, NR>(x, o1, v);
+#pragma unroll
+      for (int r = 0; r < NR; ++r) sm.xs[tid + 256][r] = v[r];
     }
     __syncthreads();
     const int nk = (jn - ks + nks - 1) / nks;
@@ -587,7 +635,7 @@ __device__ __forceinline__ void backward_item_r(const BwdItem& it, const PlanVie
       double t = 0.0;
 #pragma unroll
       for (int c = 0; c < nks; ++c) t += sm.part[c][q][r][lane];
-      double* xp = x + r * ldx_ + it.g0 + it.col0 + q * 32 + lane;
+      double* xp = x + (it.g0 + it.col0 + q * 32 + lane) * NR + r;
       *xp = ldx<CG>(xp) - t;
     }
   }
@@ -599,7 +647,7 @@ __device__ __forceinline__ void backward_item_r(const BwdItem& it, const PlanVie
 constexpr int BWD_COLS = 8;
 constexpr int BQ = 8;   // factor entries per lane preloaded before the wait
 template <bool CG, int NR, bool PDL>
-__device__ __forceinline__ void backward_item_cols(const BwdItem& it, const PlanView& P, double* x, int64_t ldx_, const Deps& dp) {
+__device__ __forceinline__ void backward_item_cols(const BwdItem& it, const PlanView& P, double* x, const Deps& dp) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u2 = it.u2;
   const bool active = warp < it.ncols;
@@ -629,31 +677,35 @@ __device__ __forceinline__ void backward_item_cols(const BwdItem& it, const Plan
 #pragma unroll
   for (int q = 0; q < BQ; ++q) {
     if (xo[q] >= 0) {
+      double xv[NR];
+      ldv<CG, NR>(x, xo[q], xv);
 #pragma unroll
-      for (int r = 0; r < NR; ++r) a[r] = fma(wreg[q], ldx<CG>(x + r * ldx_ + xo[q]), a[r]);
+      for (int r = 0; r < NR; ++r) a[r] = fma(wreg[q], xv[r], a[r]);
     }
   }
   for (int j = lane + 32 * BQ; j < u2; j += 32) {
     const double wv = wc[j];
     const int64_t o = 2 * (int64_t)st[j >> 1] + (j & 1);
+    double xv[NR];
+    ldv<CG, NR>(x, o, xv);
 #pragma unroll
-    for (int r = 0; r < NR; ++r) a[r] = fma(wv, ldx<CG>(x + r * ldx_ + o), a[r]);
+    for (int r = 0; r < NR; ++r) a[r] = fma(wv, xv[r], a[r]);
   }
 #pragma unroll
   for (int r = 0; r < NR; ++r) {
     double v = a[r];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-    if (lane == 0) { double* xp = x + r * ldx_ + it.g0 + it.col0 + warp; *xp = ldx<CG>(xp) - v; }
+    if (lane == 0) { double* xp = x + (it.g0 + it.col0 + warp) * NR + r; *xp = ldx<CG>(xp) - v; }
   }
 }
 
 template <bool CG, int NR, bool PDL = false>
-__device__ __forceinline__ void backward_item(const BwdItem& it, const PlanView& P, double* x, int64_t ldx_, BwdSmem<NR>& sm,
+__device__ __forceinline__ void backward_item(const BwdItem& it, const PlanView& P, double* x, BwdSmem<NR>& sm,
                                               const Deps& dp) {
-  if (it.G == 0) backward_item_cols<CG, NR, PDL>(it, P, x, ldx_, dp);
-  else if (it.G == 2) backward_item_r<CG, NR, 2, PDL>(it, P, x, ldx_, sm, dp);
-  else backward_item_r<CG, NR, 1, PDL>(it, P, x, ldx_, sm, dp);
+  if (it.G == 0) backward_item_cols<CG, NR, PDL>(it, P, x, dp);
+  else if (it.G == 2) backward_item_r<CG, NR, 2, PDL>(it, P, x, sm, dp);
+  else backward_item_r<CG, NR, 1, PDL>(it, P, x, sm, dp);
 }
 
 // ---- warp-per-task sweeps for SMALL fronts -------------------------------------------------------------------
@@ -728,14 +780,14 @@ __device__ __forceinline__ void forward_task(const FwdTask& t, const int32_t* __
     // right-hand side + children's updates of the pivot unknowns k0.., fixed order (rhs + child 0) + child 1 ...
     for (int h = lane; h < kn; h += 32) {
       const int k = k0 + h;
-      double v[NR];
-#pragma unroll
-      for (int r = 0; r < NR; ++r) v[r] = rv.rhs[r * rv.ldr + t.g0 + k];
+      double v[NR], w[NR];
+      ldv<false, NR>(rv.rhs, t.g0 + k, v);
       for (int c = 0; c < t.nch; ++c) {
         const int i = g[c * nf2 + k];
         if (i >= 0) {
+          ldv<false, NR>(rv.upd, i, w);
 #pragma unroll
-          for (int r = 0; r < NR; ++r) v[r] += rv.upd[r * rv.ldu + i];
+          for (int r = 0; r < NR; ++r) v[r] += w[r];
         }
       }
 #pragma unroll
@@ -751,28 +803,29 @@ __device__ __forceinline__ void forward_task(const FwdTask& t, const int32_t* __
     if (!valid[q]) continue;
     const int row = t.r0 + lane + 32 * q;
     if (row < s2) {
-#pragma unroll
-      for (int r = 0; r < NR; ++r) rv.out[r * rv.ldo + t.g0 + row] = acc[q][r];
+      stv<NR>(rv.out, t.g0 + row, acc[q]);
     } else {
-      double yt[NR];
+      double yt[NR], w[NR];
 #pragma unroll
       for (int r = 0; r < NR; ++r) yt[r] = 0.0;
       for (int c = 0; c < t.nch; ++c) {
         const int i = g[c * nf2 + row];
         if (i >= 0) {
+          ldv<false, NR>(rv.upd, i, w);
 #pragma unroll
-          for (int r = 0; r < NR; ++r) yt[r] += rv.upd[r * rv.ldu + i];
+          for (int r = 0; r < NR; ++r) yt[r] += w[r];
         }
       }
 #pragma unroll
-      for (int r = 0; r < NR; ++r) rv.upd[r * rv.ldu + t.uoff + (row - s2)] = yt[r] - acc[q][r];
+      for (int r = 0; r < NR; ++r) yt[r] -= acc[q][r];
+      stv<NR>(rv.upd, (int64_t)t.uoff + (row - s2), yt);
     }
   }
 }
 
 template <int NR, int R, bool PDL>
 __device__ __forceinline__ void backward_task(const BwdTask& t, const int32_t* __restrict__ strct, const double* __restrict__ fac,
-                                              double* x, int64_t ldx_, double (*xs)[NR], int lane) {
+                                              double* x, double (*xs)[NR], int lane) {
   constexpr int U = 8 / R;
   const int u2 = t.u2;
   const int64_t s2p = t.s2p;
@@ -800,19 +853,25 @@ __device__ __forceinline__ void backward_task(const BwdTask& t, const int32_t* _
     const int jn = min(KT, u2 - j0);
     if (j0 == 0) {
       if (o0 >= 0) {
+        double v[NR];
+        ldv<false, NR>(x, o0, v);
 #pragma unroll
-        for (int r = 0; r < NR; ++r) xs[lane][r] = x[r * ldx_ + o0];
+        for (int r = 0; r < NR; ++r) xs[lane][r] = v[r];
       }
       if (o1 >= 0) {
+        double v[NR];
+        ldv<false, NR>(x, o1, v);
 #pragma unroll
-        for (int r = 0; r < NR; ++r) xs[lane + 32][r] = x[r * ldx_ + o1];
+        for (int r = 0; r < NR; ++r) xs[lane + 32][r] = v[r];
       }
     } else {
       for (int h = lane; h < jn; h += 32) {
         const int j = j0 + h;
         const int64_t o = 2 * (int64_t)st[j >> 1] + (j & 1);
+        double v[NR];
+        ldv<false, NR>(x, o, v);
 #pragma unroll
-        for (int r = 0; r < NR; ++r) xs[h][r] = x[r * ldx_ + o];
+        for (int r = 0; r < NR; ++r) xs[h][r] = v[r];
       }
     }
     __syncwarp();
@@ -823,11 +882,11 @@ __device__ __forceinline__ void backward_task(const BwdTask& t, const int32_t* _
 #pragma unroll
   for (int q = 0; q < R; ++q) {
     if (!valid[q]) continue;
+    double v[NR];
+    ldv<false, NR>(x, t.g0 + t.c0 + lane + 32 * q, v);
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      double* xp = x + r * ldx_ + t.g0 + t.c0 + lane + 32 * q;
-      *xp = *xp - acc[q][r];
-    }
+    for (int r = 0; r < NR; ++r) v[r] -= acc[q][r];
+    stv<NR>(x, t.g0 + t.c0 + lane + 32 * q, v);
   }
 }
 
@@ -842,11 +901,11 @@ __global__ void __launch_bounds__(256, 4) forward_kernel(const FwdItem* __restri
 }
 
 template <int NR, bool PDL>
-__global__ void __launch_bounds__(256, 4) backward_kernel(const BwdItem* __restrict__ items, PlanView P, double* x, int64_t ldx_) {
+__global__ void __launch_bounds__(256, 4) backward_kernel(const BwdItem* __restrict__ items, PlanView P, double* x) {
   __shared__ BwdSmem<NR> sm;
   if (PDL) griddep_launch_dependents();
   const Deps none{nullptr, nullptr, nullptr, 0, nullptr};
-  backward_item<false, NR, PDL>(items[blockIdx.x], P, x, ldx_, sm, none);
+  backward_item<false, NR, PDL>(items[blockIdx.x], P, x, sm, none);
 }
 
 // small fronts: eight warp tasks per CTA, 32 warps resident per SM
@@ -865,15 +924,15 @@ __global__ void __launch_bounds__(256, 4) forward_small_kernel(const FwdTask* __
 
 template <int NR, bool PDL>
 __global__ void __launch_bounds__(256, 4) backward_small_kernel(const BwdTask* __restrict__ tasks, int ntasks, const int32_t* __restrict__ strct,
-                                                                 const double* __restrict__ fac, double* x, int64_t ldx_) {
+                                                                 const double* __restrict__ fac, double* x) {
   __shared__ __align__(16) double tile[8][KT][NR];
   if (PDL) griddep_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int id = (int)blockIdx.x * 8 + warp;
   if (id >= ntasks) return;
   const BwdTask t = tasks[id];
-  if (t.nc <= 32) backward_task<NR, 1, PDL>(t, strct, fac, x, ldx_, tile[warp], lane);
-  else backward_task<NR, 2, PDL>(t, strct, fac, x, ldx_, tile[warp], lane);
+  if (t.nc <= 32) backward_task<NR, 1, PDL>(t, strct, fac, x, tile[warp], lane);
+  else backward_task<NR, 2, PDL>(t, strct, fac, x, tile[warp], lane);
 }
 
 // ---- pack: the solve phase reads only the left block column of a front (and W a second time, row-major) ----
@@ -936,7 +995,7 @@ union OpSmem {
 
 __device__ __forceinline__ void sweep_dataflow(const OpArgs& a, const double* rhs, double* out, int epoch, OpSmem& sm) {
   const Deps dp{a.fdone, a.bdone, a.status, epoch, a.nfs};
-  const RhsView rv{rhs, 0, out, 0, a.upd, 0};
+  const RhsView rv{rhs, out, a.upd};
   for (int i = blockIdx.x; i < a.n_fwd; i += gridDim.x) {
     const FwdItem it = a.fwd_q[i];
     forward_item<true, 1>(it, a.gsrc, a.P, rv, sm.f, dp);
@@ -946,7 +1005,7 @@ __device__ __forceinline__ void sweep_dataflow(const OpArgs& a, const double* rh
   }
   for (int i = blockIdx.x; i < a.n_bwd; i += gridDim.x) {
     const BwdItem it = a.bwd_q[i];
-    backward_item<true, 1>(it, a.P, out, 0, sm.b, dp);
+    backward_item<true, 1>(it, a.P, out, sm.b, dp);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) atomicAdd(a.bdone + it.f, 1);
@@ -1235,12 +1294,12 @@ void launch_sweep(void (*kernel)(KArgs...), bool pdl, int grid, cudaStream_t st,
   PLFEM_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
 }
 
-// nrhs right-hand sides (1 or 4) stored as columns with stride ld (ignored for nrhs = 1).  Per level: one launch for
-// the CTA items of the large fronts, one for the warp tasks of the small ones (most levels have only one kind).
-void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double* z, int nrhs, int64_t ld) {
+// nrhs right-hand sides (1 or SOLVE_NRHS), INTERLEAVED: entry i of right-hand side r at b[i * nrhs + r].  Per level: one
+// launch for the CTA items of the large fronts, one for the warp tasks of the small ones (most levels have one kind).
+void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double* z, int nrhs) {
   const PlanView v = sweep_view(D);
   if (nrhs != 1 && nrhs != SOLVE_NRHS) throw StatusError(PLFEM_ERR_INTERNAL, "unsupported number of right-hand sides");
-  const RhsView rv{b, ld, z, ld, D.upd.p, D.upd_len};
+  const RhsView rv{b, z, D.upd.p};
   const bool pdl = use_pdl();
   bool first = true;     // the first launch follows kernels that are not PDL-aware: plain launch
   const int32_t* gs = D.gsrc.p;
@@ -1265,22 +1324,22 @@ void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double
 }
 
 // must follow run_solve_forward on the same stream (its launches may be PDL-chained to the forward ones)
-void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs, int64_t ld) {
+void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs) {
   const PlanView v = sweep_view(D);
   const bool pdl = use_pdl();
   for (int l = D.nlevels - 1; l >= 0; --l) {
     const int nbig = D.bwdb_ptr[l + 1] - D.bwdb_ptr[l], nt = D.bwd_tptr[l + 1] - D.bwd_tptr[l];
     if (nbig > 0) {
       const BwdItem* items = D.bwdb_items.p + D.bwdb_ptr[l];
-      if (nrhs == 1) { if (pdl) launch_sweep(backward_kernel<1, true>, true, nbig, ctx->stream, items, v, x, ld); else launch_sweep(backward_kernel<1, false>, false, nbig, ctx->stream, items, v, x, ld); }
-      else { if (pdl) launch_sweep(backward_kernel<SOLVE_NRHS, true>, true, nbig, ctx->stream, items, v, x, ld); else launch_sweep(backward_kernel<SOLVE_NRHS, false>, false, nbig, ctx->stream, items, v, x, ld); }
+      if (nrhs == 1) { if (pdl) launch_sweep(backward_kernel<1, true>, true, nbig, ctx->stream, items, v, x); else launch_sweep(backward_kernel<1, false>, false, nbig, ctx->stream, items, v, x); }
+      else { if (pdl) launch_sweep(backward_kernel<SOLVE_NRHS, true>, true, nbig, ctx->stream, items, v, x); else launch_sweep(backward_kernel<SOLVE_NRHS, false>, false, nbig, ctx->stream, items, v, x); }
       ctx->launches++;
     }
     if (nt > 0) {
       const BwdTask* tasks = D.bwd_tasks.p + D.bwd_tptr[l];
       const int grid = (nt + 7) / 8;
-      if (nrhs == 1) { if (pdl) launch_sweep(backward_small_kernel<1, true>, true, grid, ctx->stream, tasks, nt, D.strct.p, D.fac.p, x, ld); else launch_sweep(backward_small_kernel<1, false>, false, grid, ctx->stream, tasks, nt, D.strct.p, D.fac.p, x, ld); }
-      else { if (pdl) launch_sweep(backward_small_kernel<SOLVE_NRHS, true>, true, grid, ctx->stream, tasks, nt, D.strct.p, D.fac.p, x, ld); else launch_sweep(backward_small_kernel<SOLVE_NRHS, false>, false, grid, ctx->stream, tasks, nt, D.strct.p, D.fac.p, x, ld); }
+      if (nrhs == 1) { if (pdl) launch_sweep(backward_small_kernel<1, true>, true, grid, ctx->stream, tasks, nt, D.strct.p, D.fac.p, x); else launch_sweep(backward_small_kernel<1, false>, false, grid, ctx->stream, tasks, nt, D.strct.p, D.fac.p, x); }
+      else { if (pdl) launch_sweep(backward_small_kernel<SOLVE_NRHS, true>, true, grid, ctx->stream, tasks, nt, D.strct.p, D.fac.p, x); else launch_sweep(backward_small_kernel<SOLVE_NRHS, false>, false, grid, ctx->stream, tasks, nt, D.strct.p, D.fac.p, x); }
       ctx->launches++;
     }
   }
@@ -1313,9 +1372,9 @@ void run_operator(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const doubl
   ctx->launches++;
 }
 
-void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x, int nrhs, int64_t ld) {
-  run_solve_forward(ctx, D, b, x, nrhs, ld);
-  run_solve_backward(ctx, D, x, nrhs, ld);
+void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x, int nrhs) {
+  run_solve_forward(ctx, D, b, x, nrhs);
+  run_solve_backward(ctx, D, x, nrhs);
 }
 
 }  // namespace plfem

@@ -150,23 +150,77 @@ def solve_design_gpu(d: Dict, device: int = 0, refinement: float = 1.0):
     return g, mesh, modes, st, time.perf_counter() - t0
 
 
+def solve_forest_gpu(ds: Sequence[Dict], pool, refinement: float = 1.0) -> List:
+    """Default worker of the forest mode: meshes on the host, ONE forest solve on the GPU for all of ``ds``.
+    Returns one ``(geometry, mesh, modes, stats, seconds)`` or ``Exception`` per design."""
+    import time
+    from .solver_fem import sigma_estimate
+    prepared, out = [], [None] * len(ds)
+    for j, d in enumerate(ds):
+        try:
+            g = design_geometry(d)
+            mesh, _ = MeshGenerator.generate(g, refinement)
+            prepared.append((j, g, mesh, d.get("n_modes", 10)))
+        except Exception as e:                              # noqa: BLE001 — a bad design must not stop the forest
+            out[j] = e
+    if prepared:
+        t0 = time.perf_counter()
+        res = pool.solve_forest([(g, mesh, n) for _, g, mesh, n in prepared])
+        secs = (time.perf_counter() - t0) / len(prepared)
+        for (j, g, mesh, _), modes, st in zip(prepared, res, pool.last_stats):
+            if isinstance(modes, Exception):
+                out[j] = modes
+            else:
+                n_dofs = 2 * len(modes[0]["Ex_dofs"]) if modes and modes[0]["Ex_dofs"] is not None else np.nan
+                out[j] = (g, mesh, modes, dict(st, sigma=sigma_estimate(g), n_dofs=n_dofs), secs)
+    return out
+
+
 def run_sweep(designs: Sequence[Dict], rank: int = 0, world: int = 1, device: int = 0,
-              solve_fn: Optional[Callable] = None, gather: bool = True) -> np.ndarray:
+              solve_fn: Optional[Callable] = None, gather: bool = True, forest: int = 0,
+              forest_fn: Optional[Callable] = None) -> np.ndarray:
     """Solve this rank's shard and return ALL records, (len(designs), 86), on every rank.
+
+    ``forest = B > 0`` is the production mode on GPUs: the shard is cut into forests of ``B`` designs, each solved by
+    one `plfem_solve_modes_batch` call (``forest_fn(list of designs) -> list of results or Exceptions``; default
+    `solve_forest_gpu` on a `ForestPool`).  ``forest = 0`` solves design by design with ``solve_fn``.
 
     A failed design yields a record with ``success = 0`` and never poisons the others
     (the reference wraps each sample in try/except, `main.py:346,384-386`).
     With ``world > 1`` ``torch.distributed`` must be initialised (NCCL on GPUs, gloo in CPU tests).
     """
-    solve_fn = solve_fn or (lambda d: solve_design_gpu(d, device))
     mine = shard(len(designs), rank, world)
     local = np.full((len(mine), N_RECORD), np.nan)
-    for j, i in enumerate(mine):
+    if forest > 0:
+        pool = None
+        if forest_fn is None:
+            from .batch import ForestPool
+            pool = ForestPool(device=device, batch=forest, workers=1)
+            forest_fn = lambda ds: solve_forest_gpu(ds, pool)                     # noqa: E731
         try:
-            g, mesh, modes, st, secs = solve_fn(designs[i])
-            local[j] = design_record(i, designs[i], g, mesh, modes, st, secs, True)
-        except Exception:                                   # noqa: BLE001 — record and move on
-            local[j] = design_record(i, designs[i], None, None, [], None, 0.0, False)
+            for j0 in range(0, len(mine), forest):
+                idx = mine[j0:j0 + forest]
+                try:
+                    results = forest_fn([designs[i] for i in idx])
+                except Exception as e:                      # noqa: BLE001 — the whole forest failed
+                    results = [e] * len(idx)
+                for j, i, r in zip(range(j0, j0 + len(idx)), idx, results):
+                    if isinstance(r, Exception) or r is None:
+                        local[j] = design_record(i, designs[i], None, None, [], None, 0.0, False)
+                    else:
+                        g, mesh, modes, st, secs = r
+                        local[j] = design_record(i, designs[i], g, mesh, modes, st, secs, True)
+        finally:
+            if pool is not None:
+                pool.close()
+    else:
+        solve_fn = solve_fn or (lambda d: solve_design_gpu(d, device))
+        for j, i in enumerate(mine):
+            try:
+                g, mesh, modes, st, secs = solve_fn(designs[i])
+                local[j] = design_record(i, designs[i], g, mesh, modes, st, secs, True)
+            except Exception:                                   # noqa: BLE001 — record and move on
+                local[j] = design_record(i, designs[i], None, None, [], None, 0.0, False)
     if world == 1 or not gather:
         out = np.full((len(designs), N_RECORD), np.nan)
         out[mine] = local

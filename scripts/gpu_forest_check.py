@@ -18,7 +18,7 @@ for nb in sizes:
     for rep in range(3):
         t0 = time.perf_counter()
         out = _cabi.solve_modes_batch(ctx, pbs[:nb], [mat] * nb, [sigma] * nb, [k] * nb, want_vectors=False,
-                                      leaf_nodes=int(os.environ.get('LEAF', 0)), max_sn_nodes=int(os.environ.get('MAXSN', 0)))
+                                      ncv=int(os.environ.get('NCV', 0)), leaf_nodes=int(os.environ.get('LEAF', 0)), max_sn_nodes=int(os.environ.get('MAXSN', 0)))
         dt = time.perf_counter() - t0
     st = out[0][4].as_dict()
     vals = out[0][0]

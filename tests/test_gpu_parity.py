@@ -297,3 +297,16 @@ def test_pool_solve_many_keeps_job_order(small_case):
     for (g, mesh, n), modes in zip(jobs, out):
         alone = TrueVectorialMaxwellSolver(g).solve_vectorial_modes(mesh, n)
         assert [m["n_eff"] for m in modes] == pytest.approx([m["n_eff"] for m in alone], rel=1e-9)
+
+
+def test_sweep_forest_mode_matches_design_by_design():
+    """Config 3 (S/C/L/U bands on the 7-core PL): the sweep driver in forest mode and design by design."""
+    from plfem_b200 import sweep
+    designs = sweep.band_sweep_designs()
+    a = sweep.run_sweep(designs, forest=4)
+    b = sweep.run_sweep(designs)
+    f = {k: i for i, k in enumerate(sweep.RECORD_FIELDS)}
+    assert list(a[:, f["success"]]) == [1, 1, 1, 1] and list(b[:, f["success"]]) == [1, 1, 1, 1]
+    for key in ("n_modes_found", "n_eff_max", "n_eff_min", "n_eff_mean", "confinement_mean", "n_dofs", "sigma_shift", "wavelength_nm"):
+        assert np.allclose(a[:, f[key]], b[:, f[key]], rtol=1e-8, atol=0), key
+    assert np.allclose(a[:, f["PDL_mean_dB"]], b[:, f["PDL_mean_dB"]], atol=1e-4)

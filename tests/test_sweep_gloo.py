@@ -47,6 +47,34 @@ def _designs():
     return ds
 
 
+def _oracle_forest(ds):
+    """Forest worker stand-in: one result or Exception per design (what `solve_forest_gpu` returns)."""
+    out = []
+    for d in ds:
+        try:
+            out.append(_oracle_worker(d))
+        except Exception as e:                                      # noqa: BLE001
+            out.append(e)
+    return out
+
+
+def test_forest_mode_gives_the_same_records():
+    single = sweep.run_sweep(_designs(), 0, 1, solve_fn=_oracle_worker)
+    f = {k: i for i, k in enumerate(sweep.RECORD_FIELDS)}
+    keep = [i for i in range(sweep.N_RECORD) if i != f["solver_time_s"]]
+    for B in (1, 2, 5, 8):
+        rec = sweep.run_sweep(_designs(), 0, 1, forest=B, forest_fn=_oracle_forest)
+        assert np.array_equal(rec[:, keep], single[:, keep], equal_nan=True), B
+    calls = []
+    rec = sweep.run_sweep(_designs(), 1, 2, forest=2, forest_fn=lambda ds: calls.append(len(ds)) or _oracle_forest(ds), gather=False)
+    assert calls == [2] and list(rec[:, f["success"]][[1, 3]]) == [1, 0]     # rank 1 of 2 owns designs 1 and 3: one forest
+
+    def broken(ds):
+        raise RuntimeError("whole forest failed")
+    rec = sweep.run_sweep(_designs(), 0, 1, forest=3, forest_fn=broken)
+    assert list(rec[:, f["success"]]) == [0, 0, 0, 0, 0]
+
+
 def _rank_main(rank, world, port, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
