@@ -118,7 +118,8 @@ typedef struct {
   int32_t leaf_nodes;  /* nested-dissection leaf size (0 = default) */
   int32_t max_sn_nodes;/* supernode width limit in nodes (0 = default) */
   int32_t reuse_symbolic; /* 1 = keep ordering/front plan from the previous solve on this problem */
-  int32_t refine;      /* iterative-refinement steps per operator application: 0 = default (1), n > 0 = n, -1 = none */
+  int32_t refine;      /* iterative-refinement steps per operator application: 0 = chosen by probing one raw solve
+                          (1 for the reference's meshes), n > 0 = n, -1 = none */
   int32_t block;       /* Lanczos block size: 0 = default (4 vectors per operator application), 1 = single vector */
 } plfem_solve_opts;
 
@@ -137,7 +138,7 @@ typedef struct {
   int32_t batch_size;               /* designs solved together (1 for plfem_solve_modes) */
   int32_t batch_block_ops;          /* lockstep operator applications of the batch */
   float ms_symbolic_wall;           /* host wall time of the analysis of all designs (parallel threads) */
-  int32_t reserved;
+  int32_t refine_steps;             /* refinement steps per operator application actually used */
 } plfem_solve_stats;
 
 /* Per-mode reductions of solver_fem.py:212-220, computed on the l2-normalised (vx, vy):

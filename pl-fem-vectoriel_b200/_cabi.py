@@ -53,7 +53,7 @@ class SolveStats(C.Structure):
                 ("ms_symbolic", C.c_float), ("ms_assemble", C.c_float), ("ms_factor", C.c_float),
                 ("ms_lanczos", C.c_float), ("ms_metrics", C.c_float), ("ms_total", C.c_float),
                 ("kernel_launches", c_i32), ("n_block_op", c_i32), ("batch_size", c_i32), ("batch_block_ops", c_i32),
-                ("ms_symbolic_wall", C.c_float), ("reserved", c_i32)]
+                ("ms_symbolic_wall", C.c_float), ("refine_steps", c_i32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -479,7 +479,8 @@ static void solve_forest(plfem_ctx* ctx, int nb, plfem_problem* const* pbs, cons
     kmax = std::max(kmax, opts[b].k);
   }
   const plfem_solve_opts& o0 = opts[0];
-  const int refine = o0.refine == 0 ? 1 : std::max(o0.refine, 0);
+  const int refine = o0.refine == 0 ? 1 : std::max(o0.refine, 0);     // single-vector path
+  const int refine_block = o0.refine == 0 ? -1 : std::max(o0.refine, 0);   // block path: 0 in the options = choose by probing
   const int block = o0.block == 0 ? SOLVE_NRHS : o0.block;     // 0 = default (block Lanczos), 1 = single vector
   need(block == 1 || block == SOLVE_NRHS, "block must be 0 (default), 1 or SOLVE_NRHS");
   const bool single_vector = (nb == 1) && (block == 1 || 2 * nint[0] < 8 * SOLVE_NRHS);
@@ -618,7 +619,7 @@ static void solve_forest(plfem_ctx* ctx, int nb, plfem_problem* const* pbs, cons
   if (des[0].status != PLFEM_OK && nb == 1) {
     // nothing to iterate on
   } else if (!single_vector) {
-    run_eigensolver_block(ctx, W.dpat, W.dplan, W.d_vals.p, W.d_sigma.p, bd, des, ncv_req > 0 ? ncv_req : 3 * kmax, maxiter, refine, v0p, X, er);
+    run_eigensolver_block(ctx, W.dpat, W.dplan, W.d_vals.p, W.d_sigma.p, bd, des, ncv_req > 0 ? ncv_req : 3 * kmax, maxiter, refine_block, v0p, X, er);
   } else {
     const int64_t n = nint[0];
     const int k = opts[0].k;
@@ -684,6 +685,7 @@ static void solve_forest(plfem_ctx* ctx, int nb, plfem_problem* const* pbs, cons
     s->ms_total = (float)(t2 - t0);
     s->kernel_launches = ctx->launches;
     s->batch_size = nb; s->batch_block_ops = er.n_block_op; s->ms_symbolic_wall = (float)(t1 - t0);
+    s->refine_steps = single_vector ? refine : er.refine_steps;
   }
 }
 

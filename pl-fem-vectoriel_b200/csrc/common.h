@@ -205,6 +205,7 @@ void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs = 
 struct EigenResult {
   std::vector<double> theta;  // Ritz values of OP, wanted ones, sorted by eigenvalue ascending
   int nconv = 0, n_op = 0, n_restart = 0, n_block_op = 0;
+  int refine_steps = 0;       // refinement steps per operator application actually used
 };
 // A forest of independent designs laid out as one block-diagonal problem: design b owns the permuted nodes
 // [noff[b], noff[b+1]) and the vector rows [moff[b], moff[b+1]) (two unknowns per node).
@@ -226,6 +227,7 @@ struct DesignEig {               // one design's eigenproblem inside a forest
   int status = 0; std::string err;       // PLFEM_OK or why THIS design failed (the others are unaffected)
   std::vector<double> lambda, theta;     // ascending in lambda
   int nconv = 0, n_block_op = 0, n_restart = 0;
+  double solve_residual = 0.0;           // |dx| / |x| of the first refinement correction of a raw block-LDL^T solve (probe)
 };
 void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, const double* d_sigma_node, double sigma,
                      int k, int ncv, double tol, int maxiter, int refine_steps, const double* d_v0 /* permuted, may be null */,

@@ -125,6 +125,22 @@ __global__ void __launch_bounds__(256) resid_k_kernel(int32_t n, const int32_t* 
   }
 }
 
+// out[b][slice] = (sum a^2, sum b^2) over the rows of design b of two interleaved blocks of P right-hand sides
+__global__ void __launch_bounds__(256) sq_norms_kernel(const double* __restrict__ a, const double* __restrict__ bvec,
+                                                       const int64_t* __restrict__ moff, double* __restrict__ out) {
+  __shared__ double sh[64];
+  const int b = blockIdx.y, sl = blockIdx.x;
+  const int64_t m0 = moff[b] * SOLVE_NRHS, mlen = (moff[b + 1] - moff[b]) * SOLVE_NRHS;
+  const int64_t chunk = (mlen + gridDim.x - 1) / gridDim.x;
+  const int64_t i0 = m0 + sl * chunk, i1 = min(m0 + mlen, i0 + chunk);
+  double sa = 0.0, sb = 0.0;
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += 256) { sa = fma(a[i], a[i], sa); sb = fma(bvec[i], bvec[i], sb); }
+  sa = block_sum(sa, sh);
+  __syncthreads();
+  sb = block_sum(sb, sh + 32);
+  if (threadIdx.x == 0) { out[(b * gridDim.x + sl) * 2] = sa; out[(b * gridDim.x + sl) * 2 + 1] = sb; }
+}
+
 // block of P columns (leading dimension ld) -> interleaved right-hand sides
 __global__ void __launch_bounds__(256) interleave_kernel(const double* __restrict__ in, int64_t ld, int64_t m, double* __restrict__ out) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -796,18 +812,19 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
 
   // operator application on P right-hand sides, captured once into a CUDA graph: R = OP(opin)
   cudaGraph_t graph = nullptr; cudaGraphExec_t gexec = nullptr; int graph_nodes = 0;
-  {
+  struct GraphGuard { cudaGraph_t* g; cudaGraphExec_t* e; ~GraphGuard() { if (*e) cudaGraphExecDestroy(*e); if (*g) cudaGraphDestroy(*g); } } guard{&graph, &gexec};
+  auto capture_operator = [&](int rsteps) {
     const int before = ctx->launches;
     PLFEM_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     try {
       // interleaved right-hand sides inside the solve: opin -> xi (+ refinement) -> R (columns again)
       run_solve(ctx, D, opin.p, xi.p, P);
-      for (int it = 0; it < refine_steps; ++it) {
+      for (int it = 0; it < rsteps; ++it) {
         launch_resid_k(ctx, pat, d_vals, d_sigma_node, xi.p, opin.p, rt.p, P);
         run_solve(ctx, D, rt.p, rdx.p, P);
-        if (it + 1 < refine_steps) launch_axpy(ctx, xi.p, rdx.p, m * P);
+        if (it + 1 < rsteps) launch_axpy(ctx, xi.p, rdx.p, m * P);
       }
-      deinterleave_add_kernel<<<gm, 256, 0, st>>>(xi.p, refine_steps > 0 ? rdx.p : nullptr, ld, m, R.p);
+      deinterleave_add_kernel<<<gm, 256, 0, st>>>(xi.p, rsteps > 0 ? rdx.p : nullptr, ld, m, R.p);
       ctx->launches++;
     } catch (...) {
       cudaGraph_t dead = nullptr; cudaStreamEndCapture(st, &dead); if (dead) cudaGraphDestroy(dead);
@@ -816,8 +833,7 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
     PLFEM_CUDA(cudaStreamEndCapture(st, &graph));
     graph_nodes = ctx->launches - before; ctx->launches = before;
     PLFEM_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
-  }
-  struct GraphGuard { cudaGraph_t g; cudaGraphExec_t e; ~GraphGuard() { if (e) cudaGraphExecDestroy(e); if (g) cudaGraphDestroy(g); } } guard{graph, gexec};
+  };
 
   // B-orthonormalise the block in R, per design: U = B R, G = R^T U = L L^T, Vn = R L^-T, BVn = U L^-T; L kept in slot `slot`
   auto orthonormalize = [&](double* Vn, double* BVn, int slot) {
@@ -836,6 +852,44 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
   int cur = 0;
   orthonormalize(V[cur].p, BV[cur].p, ncvp / P);     // scratch slot
 
+  // How many refinement steps does the block-LDL^T solve need?  Pivoting is confined to the pivot blocks, so the
+  // quality of a raw solve depends on the mesh and the shift: probe it on the start block with one refinement step
+  // (rho = |dx| / |x| per design — the size of the first correction, a scale-free estimate of the contraction; the
+  // residual norm itself is dominated by the 1e9-size rows of sliver elements) and take the step count that brings
+  // rho^(steps+1) below the Lanczos tolerance with a wide margin.  A design whose raw solve is useless (rho >= 0.05)
+  // is reported as singular instead of iterating forever.
+  int rsteps = refine_steps;
+  if (refine_steps < 0) {
+    DevBuf<double> nrm;
+    nrm.alloc(ctx, (size_t)B * RSPLIT * 2);
+    interleave_kernel<<<gm, 256, 0, st>>>(BV[cur].p, ld, m, opin.p);
+    run_solve(ctx, D, opin.p, xi.p, P);
+    launch_resid_k(ctx, pat, d_vals, d_sigma_node, xi.p, opin.p, rt.p, P);
+    run_solve(ctx, D, rt.p, rdx.p, P);                  // the first correction: |dx| / |x| estimates the contraction
+    sq_norms_kernel<<<dim3(RSPLIT, B), 256, 0, st>>>(rdx.p, xi.p, moff, nrm.p);
+    ctx->launches += 2;
+    std::vector<double> hn((size_t)B * RSPLIT * 2);
+    nrm.download(hn.data(), hn.size());
+    PLFEM_CUDA(cudaStreamSynchronize(st));
+    rsteps = 1;
+    for (int b = 0; b < B; ++b) {
+      double nr = 0.0, nbv = 0.0;
+      for (int sl = 0; sl < RSPLIT; ++sl) { nr += hn[((size_t)b * RSPLIT + sl) * 2]; nbv += hn[((size_t)b * RSPLIT + sl) * 2 + 1]; }
+      const double rho = std::sqrt(nr / nbv);
+      des[b].solve_residual = rho;
+      if (des[b].status != PLFEM_OK) continue;
+      if (!(rho < 0.05)) {
+        des[b].status = PLFEM_ERR_SINGULAR;
+        des[b].err = "the block-LDL^T solve of A - sigma*B is too inaccurate for this mesh and shift (first refinement correction |dx|/|x| = " + std::to_string(rho) +
+                     "): a pivot block is numerically singular";
+        continue;
+      }
+      rsteps = std::max(rsteps, rho <= 1e-4 ? 1 : (rho <= 2e-3 ? 2 : (rho <= 1e-2 ? 3 : 5)));
+    }
+  }
+  res.refine_steps = rsteps;
+  capture_operator(rsteps);
+
   struct Host {                      // per-design host state of the projected problem
     std::vector<double> Th, T, w, S;
     std::vector<int> order;
@@ -844,11 +898,13 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
   };
   std::vector<Host> hs(B);
   for (Host& h : hs) h.Th.assign((size_t)ncvp * ncvp, 0.0);
+  for (int b = 0; b < B; ++b) hs[b].done = des[b].status != PLFEM_OK;     // failed before the iteration: carried along only
+  { int nd = 0; for (const Host& h : hs) nd += h.done; if (nd == B) return; }
   std::vector<double> Hh((size_t)B * sstride), Lh((size_t)B * nslots * P * P);
   std::vector<int32_t> cs(B, 0);
   int nb = P, q = 0;                 // basis vectors present; kept Ritz vectors (their block of Th is diagonal)
   int ndone = 0;
-  res = EigenResult();
+  { const int keep = res.refine_steps; res = EigenResult(); res.refine_steps = keep; }
   X.alloc(ctx, (size_t)m * kmax);
   const double eps23 = std::pow(2.220446049250313e-16, 2.0 / 3.0);
   static const int check_every = [] { const char* e = std::getenv("PLFEM_CHECK_EVERY"); return e ? std::max(1, atoi(e)) : 2; }();

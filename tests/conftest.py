@@ -47,3 +47,12 @@ def small_case():
     g = P.MCFGeometry(3, 6.0, 1.2, 1.53, 1.0, 1.55)
     mesh, _ = P.MeshGenerator.generate(g, refinement=0.4)
     return g, mesh
+
+
+@pytest.fixture(scope="session")
+def cfg2():
+    """Config 2 of BASELINE.json: 19-core MCF cross-section, C-band (Cauchy IP-Dip index at 1550 nm), n_modes = 40."""
+    import plfem_b200 as P
+    g = P.MCFGeometry(19, 8.0, 1.5, P.IPDipCauchy.n(1550), 1.0, 1.55)
+    mesh, _ = P.MeshGenerator.generate(g)
+    return g, mesh

@@ -24,12 +24,24 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in lib.plfem_version()
 
 
-def test_struct_layouts_match_header():
-    # sizes the C compiler produces for the header's structs (LP64)
+def test_struct_layouts_match_header(tmp_path):
+    """The ctypes mirrors have the sizes gcc gives the header's structs (the header must also compile as plain C)."""
+    import shutil
+    import subprocess
     assert ctypes.sizeof(_cabi.MeshInfo) == 64
     assert ctypes.sizeof(_cabi.Material) == 64
     assert ctypes.sizeof(_cabi.SolveOpts) == 64
     assert ctypes.sizeof(_cabi.SolveStats) == 104
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "plfem.h"\nint main(void){printf("%zu %zu %zu %zu\\n", sizeof(plfem_mesh_info), '
+                   'sizeof(plfem_material), sizeof(plfem_solve_opts), sizeof(plfem_solve_stats)); return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    sizes = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [ctypes.sizeof(c) for c in (_cabi.MeshInfo, _cabi.Material, _cabi.SolveOpts, _cabi.SolveStats)]
 
 
 def test_product_has_no_cpu_path(small_case):
