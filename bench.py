@@ -312,11 +312,21 @@ def run_ours(args):
                          "est_ms_per_forest": share[name]}
     launches_per = fstats["n_levels"] if "sweep" in dom else 1
     ms_dom, bytes_dom = prof[dom]
-    roofline = {"kernel": {"forward_sweep": "forward_kernel<1>", "backward_sweep": "backward_kernel<1>", "forward_sweep_4rhs": "forward_kernel<4>",
-                           "backward_sweep_4rhs": "backward_kernel<4>", "factorize": "invert_kernel+gemm",
+    traffic = None          # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (same forest size)
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["sweeps"].get(dom)
+        if tr and nb_prof == 16:
+            traffic = tr["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"kernel": {"forward_sweep": "forward_small_kernel<1> (leaf fronts) + forward_kernel<1> (one launch per level)",
+                           "backward_sweep": "backward_kernel<1> (one launch per level) + backward_small_kernel<1> (leaf fronts)",
+                           "forward_sweep_4rhs": "forward_small_kernel<4> (leaf fronts) + forward_kernel<4> (one launch per level)",
+                           "backward_sweep_4rhs": "backward_kernel<4> (one launch per level) + backward_small_kernel<4> (leaf fronts)",
+                           "factorize": "invert_kernel+gemm",
                            "assemble": "assemble_kernel", "spmm_B": "spmm_b_kernel", "spmv_K_residual": "resid_k_kernel"}[dom],
                 "bound": "hbm", "achieved": bytes_dom / (ms_dom * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": bytes_dom / (ms_dom * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": bytes_dom / (ms_dom * 1e-3) / 1e9 / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "per_launch": {"launches_per_sweep": launches_per, "avg_launch_us": 1e3 * ms_dom / launches_per,
                                "algorithmic_bytes_per_launch": bytes_dom / launches_per, "designs_per_launch": nb_prof},
                 "note": "one sweep = one launch per elimination-tree level carrying the fronts of all designs of the forest; "
