@@ -18,6 +18,7 @@
 #ifndef PLFEM_H
 #define PLFEM_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -163,6 +164,13 @@ int plfem_solve_modes_batch(plfem_ctx* ctx, int32_t nb, plfem_problem* const* pb
                             const plfem_solve_opts* opts, double* const* eigvals, double* const* evecs,
                             double* const* metrics, int32_t* core_dof_counts, plfem_solve_stats* stats,
                             int32_t* statuses);
+
+/* ---- page-locked host memory for result buffers --------------------------------------------------------------
+ * The eigenvectors of a forest are >100 MB; copying them into pageable memory runs at a few GB/s (driver staging
+ * copies + first-touch page faults).  Buffers obtained here are page-locked (cudaHostAlloc, portable), so the
+ * device->host copies of plfem_solve_modes / plfem_solve_modes_batch run at link speed.  Free with plfem_host_free. */
+int plfem_host_alloc(size_t bytes, void** out);
+void plfem_host_free(void* p);
 
 /* ---- measurement hook for bench.py: per-kernel device times (CUDA events on the library's stream, L2
  * flushed before each repetition) and the algorithmic bytes of the same items; needs a prior solve.

@@ -28,7 +28,7 @@ SYMBOLS = ["plfem_ctx_create", "plfem_ctx_destroy", "plfem_last_error", "plfem_v
            "plfem_problem_create", "plfem_problem_destroy", "plfem_problem_info", "plfem_problem_dofs",
            "plfem_quad_points", "plfem_assemble", "plfem_export_csr", "plfem_spmv_csr", "plfem_solve_modes",
            "plfem_plan_sizes", "plfem_plan_export", "plfem_debug_symeig", "plfem_profile_kernels", "plfem_set_host_threads",
-           "plfem_debug_solve", "plfem_ctx_set_coop_ctas", "plfem_solve_modes_batch", "plfem_profile_last"]
+           "plfem_debug_solve", "plfem_ctx_set_coop_ctas", "plfem_solve_modes_batch", "plfem_profile_last", "plfem_host_alloc", "plfem_host_free"]
 
 
 class MeshInfo(C.Structure):
@@ -111,12 +111,65 @@ def load():
         lib.plfem_set_host_threads.restype = None
         lib.plfem_profile_kernels.argtypes = [vp, C.POINTER(Material), c_f64, C.c_int, p_f64, p_f64]
         lib.plfem_profile_last.argtypes = [vp, C.c_int, p_f64, p_f64, p_i32]
+        lib.plfem_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+        lib.plfem_host_free.argtypes = [vp]
+        lib.plfem_host_free.restype = None
         _lib = lib
         return lib
 
 
 def _ptr(a, typ):
     return a.ctypes.data_as(typ) if a is not None else None
+
+
+class PinnedPool:
+    """Recycling pool of page-locked host blocks for the big result arrays (eigenvectors).
+
+    ``empty(shape)`` returns a float64 NumPy array backed by a pinned block; when the array (and every view of it —
+    the mode records hold views) is garbage-collected the block goes back to the pool.  Device->host copies into such
+    arrays run at link speed and touch no fresh pages.  Above ``cap_bytes`` of blocks in use the pool hands out ordinary
+    ``np.empty`` arrays, so a caller that keeps thousands of results alive does not pin all of host memory."""
+
+    def __init__(self, cap_bytes: int = 4 << 30):
+        self.cap, self.in_use = int(cap_bytes), 0
+        self.free: dict = {}
+        self.lock = threading.Lock()
+
+    @staticmethod
+    def _size_class(nbytes: int) -> int:
+        c = 1 << 16
+        while c < nbytes:
+            c <<= 1
+        return c
+
+    def _give_back(self, ptr: int, size: int):
+        with self.lock:
+            self.free.setdefault(size, []).append(ptr)
+            self.in_use -= size
+
+    def empty(self, shape) -> np.ndarray:
+        import weakref
+        n = int(np.prod(shape))
+        size = self._size_class(8 * max(n, 1))
+        with self.lock:
+            if self.in_use + size > self.cap:
+                return np.empty(shape)
+            lst = self.free.get(size)
+            ptr = lst.pop() if lst else None
+            self.in_use += size
+        if ptr is None:
+            h = C.c_void_p()
+            if load().plfem_host_alloc(size, C.byref(h)) != 0 or not h.value:
+                with self.lock:
+                    self.in_use -= size
+                return np.empty(shape)
+            ptr = h.value
+        buf = (c_f64 * n).from_address(ptr)
+        weakref.finalize(buf, self._give_back, ptr, size)      # runs when the last array / view over buf dies
+        return np.ctypeslib.as_array(buf).reshape(shape)
+
+
+PINNED = PinnedPool()
 
 
 class Context:
@@ -257,7 +310,7 @@ class Problem:
                 raise ValueError(f"v0 must have length {n2}")
             o.v0 = _ptr(v0, p_f64)
         vals = np.empty(k)
-        vecs = np.empty((k, n2)) if want_vectors else None
+        vecs = PINNED.empty((k, n2)) if want_vectors else None
         met = np.empty((k, NMETRICS))
         ncore = c_i32()
         stats = SolveStats()
@@ -328,7 +381,7 @@ def solve_modes_batch(ctx: "Context", problems, materials, sigmas, ks, tol: floa
                             leaf_nodes=int(leaf_nodes), max_sn_nodes=int(max_sn_nodes),
                             reuse_symbolic=int(bool(reuse_symbolic)), refine=int(refine), block=0)
     vals = [np.empty(int(k)) for k in ks]
-    vecs = [np.empty((int(k), 2 * pb.n_interior)) if want_vectors else None for k, pb in zip(ks, problems)]
+    vecs = [PINNED.empty((int(k), 2 * pb.n_interior)) if want_vectors else None for k, pb in zip(ks, problems)]
     mets = [np.empty((int(k), NMETRICS)) for k in ks]
     ncore = np.zeros(nb, dtype=np.int32)
     status = np.zeros(nb, dtype=np.int32)

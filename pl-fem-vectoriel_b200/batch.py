@@ -91,6 +91,15 @@ class ForestPool:
                 raise r
         return out
 
+    def solve_iter(self, jobs: Sequence[tuple]):
+        """Like ``solve_many`` but yields the mode list (or the Exception) of one job at a time, in job order, while
+        later forests are still being solved — a consumer that reduces each result (a dataset record) and drops it
+        keeps only a few forests of eigenvectors alive, and their page-locked buffers are recycled."""
+        chunks = [jobs[i:i + self.batch] for i in range(0, len(jobs), self.batch)]
+        for part in self._pool.map(self.solve_forest, chunks):
+            while part:
+                yield part.pop(0)
+
     def map_forests(self, fn: Callable, items: Sequence):
         """Run ``fn(pool, ctx, item)`` on the worker threads (bench hook: resident problems per context)."""
         return list(self._pool.map(lambda it: fn(self, self._ctx(), it), items))

@@ -875,6 +875,16 @@ int plfem_plan_export(plfem_problem* pb, int32_t* perm, int32_t* first, int32_t*
   });
 }
 
+int plfem_host_alloc(size_t bytes, void** out) {
+  if (!out) return PLFEM_ERR_INVALID;
+  *out = nullptr;
+  return cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocPortable) == cudaSuccess ? PLFEM_OK : PLFEM_ERR_CUDA;
+}
+
+void plfem_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 // test hook: dense symmetric eigensolver used at Lanczos restarts
 int plfem_debug_symeig(int32_t n, double* a, double* w) {
   if (!a || !w || n < 1) return PLFEM_ERR_INVALID;
