@@ -3,12 +3,12 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg1|cfg2]
 
-A *step* is one FOREST of ``--inflight`` (default 16) independent modal solves of the workload's
-cross-section: the designs are solved together as one block-diagonal problem by one C-ABI call
+A *step* is ``--workers`` (default 6) FORESTS of ``--inflight`` (default 12) independent modal solves of the workload's
+cross-section each (72 solves): the designs of a forest are solved together as one block-diagonal problem by one C-ABI call
 (`plfem_solve_modes_batch`), sharing every kernel launch — the sweep's production mode.  A modal
 solve is `solve_vectorial_modes`: DOF tables -> assembly -> Dirichlet elimination -> ordering +
 factorisation of A - sigma*B -> eigensolve -> per-mode reductions, all of it done per design (nothing
-is reused between the designs of a forest).  ``--workers`` (default 3) host threads each drive their
+is reused between the designs of a forest).  ``--workers`` (default 6) host threads each drive their
 own forest, so the host-side symbolic analysis of one forest overlaps the device work of another.
 The mesh is given (built on the host before timing, as in the reference where `MeshGenerator` runs
 first).  ``latency`` in the JSON line is one solve run alone.
@@ -200,7 +200,9 @@ def run_ours(args):
 
     # ---- value: a step = ONE forest of B designs; mesh + DOF tables resident, everything else inside ------
     B = max(1, args.inflight)
-    pool = ForestPool(device=local, batch=B, workers=max(1, args.workers), want_vectors=False)
+    NW = max(1, args.workers)
+    NF = args.steps * NW                                   # forests in the timed region: a step = one forest per worker thread
+    pool = ForestPool(device=local, batch=B, workers=NW, want_vectors=False)
     sigma = sigma_estimate(g)
     mat, keep = _cabi.material_struct(g)
     by_ctx = {}                                            # B resident problems per worker context
@@ -219,12 +221,12 @@ def run_ours(args):
     for _ in range(args.warmup):                           # every worker thread gets its context and problems
         pool.on_every_worker(lambda p_, c: forest_resident(p_, c, 0))
     launches, phase = 0, {n: 0.0 for n in ("ms_symbolic", "ms_symbolic_wall", "ms_assemble", "ms_factor", "ms_lanczos", "ms_metrics", "ms_total")}
-    records = np.full((args.steps * B, N_RECORD), np.nan)
+    records = np.full((NF * B, N_RECORD), np.nan)
     flush_l2()
     sync_all()
     with ClockSampler(local) as clocks:
         t0 = time.perf_counter()
-        outs = pool.map_forests(forest_resident, range(args.steps))      # K forests, pipelined over the worker threads
+        outs = pool.map_forests(forest_resident, range(NF))              # K x workers forests, pipelined over the worker threads
         torch.cuda.synchronize(local)
         t_value = time.perf_counter() - t0
         for i, forest in enumerate(outs):
@@ -234,13 +236,13 @@ def run_ours(args):
                 phase[n] += getattr(st, n)
             for j, f in enumerate(forest):
                 assert f[5] == 0, "a design failed"
-                records[i * B + j, 0], records[i * B + j, 1], records[i * B + j, 3] = (rank * args.steps + i) * B + j, 1.0, st.ms_total * 1e-3 / B
+                records[i * B + j, 0], records[i * B + j, 1], records[i * B + j, 3] = (rank * NF + i) * B + j, 1.0, st.ms_total * 1e-3 / B
         if world > 1:          # the sweep's single collective, inside the timed region
             t0 = time.perf_counter()
-            allrec = gather_records(records, world * args.steps * B, rank, world, local)
+            allrec = gather_records(records, world * NF * B, rank, world, local)
             torch.cuda.synchronize(local)
             t_value += time.perf_counter() - t0
-            assert allrec.shape == (world * args.steps * B, N_RECORD)
+            assert allrec.shape == (world * NF * B, N_RECORD)
     stats = st.as_dict()
 
     # ---- e2e: public API, host buffers in, mode records (with eigenvectors) out -----------------------------
@@ -254,12 +256,12 @@ def run_ours(args):
     with ClockSampler(local) as clocks2:
         t0 = time.perf_counter()
         n_rec = 0
-        for modes in pool_e.solve_iter(jobs * args.steps):     # records consumed as they arrive (a dataset writer would
+        for modes in pool_e.solve_iter(jobs * NF):     # records consumed as they arrive (a dataset writer would
             assert not isinstance(modes, Exception), modes     # reduce each to its 86-slot row here)
             n_rec += len(modes) > 0
         torch.cuda.synchronize(local)
         t_e2e = time.perf_counter() - t0
-        assert n_rec == B * args.steps
+        assert n_rec == B * NF
     pool_e.close()
 
     # ---- latency: one solve alone through the public API ---------------------------------------------
@@ -280,8 +282,8 @@ def run_ours(args):
     pbs0 = [_cabi.Problem(mesh, ctx0) for _ in range(B)]
     n_solve = pbs0[0].n_interior
     k = min(n_modes + 12, 2 * n_solve - 4)
-    h2d = B * (mesh.p.nbytes + mesh.t.astype(np.int64).nbytes + 8 * (3 * g.n_cores + 4))
-    d2h = B * 8 * (k + k * 2 * n_solve + k * _cabi.NMETRICS)
+    h2d = NW * B * (mesh.p.nbytes + mesh.t.astype(np.int64).nbytes + 8 * (3 * g.n_cores + 4))
+    d2h = NW * B * 8 * (k + k * 2 * n_solve + k * _cabi.NMETRICS)
 
     if world > 1:
         tt = torch.tensor([t_value, t_e2e], dtype=torch.float64, device=f"cuda:{local}")
@@ -318,8 +320,8 @@ def run_ours(args):
     traffic = None          # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (same forest size)
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["sweeps"].get(dom)
-        if tr and nb_prof == 16:
-            traffic = tr["dram_bytes_per_launch"]
+        if tr:      # captured on a forest of 16 designs: scale to this forest (traffic is proportional to the designs)
+            traffic = tr["dram_bytes_per_launch"] * nb_prof / 16.0
     except Exception:
         pass
     roofline = {"kernel": {"forward_sweep": "forward_small_kernel<1> (leaf fronts) + forward_kernel<1> (one launch per level)",
@@ -338,14 +340,15 @@ def run_ours(args):
     cpu = cpu_baseline_sample(args.workload, 2) if world == 1 else None
     pool.close()
     nst = args.steps
-    line = {"metric": "modal_solves_per_sec", "value": world * B * args.steps / t_value, "unit": "solves/s", "n_gpus": world,
+    line = {"metric": "modal_solves_per_sec", "value": world * B * NF / t_value, "unit": "solves/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_value / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["name"], "mesh": {"V": int(mesh.p.shape[1]), "T": int(mesh.t.shape[1]), "N_p2": int(pbs0[0].N),
                                                        "dim": 2 * n_solve, "recipe": "reference point recipe, refinement 1.0, flat hull triangles dropped"},
-                       "step": f"one forest of {B} independent modal solves (each with its own symbolic analysis, assembly, factorisation, "
-                               f"eigensolve and reductions) sharing every kernel launch; {pool.workers} host threads/contexts keep "
-                               f"{pool.workers} forests in flight so the host analysis of one overlaps the device work of the other",
+                       "step": f"{NW} forests (one per host thread / context) of {B} independent modal solves each = {NW * B} solves; the designs "
+                               f"of a forest (each with its own symbolic analysis, assembly, factorisation, eigensolve and reductions) share "
+                               f"every kernel launch, the {NW} forests in flight overlap host analysis and device work",
+                       "designs_per_forest": B, "forests_in_flight": NW, "solves_per_step": NW * B,
                        "k": k, "lanczos": "thick-restart block Lanczos, 4 vectors per operator application, basis 3k, designs in lockstep", "tol": 1e-7,
                        "start_vector": "ones (+3 fixed pseudo-random)", "refine_steps": 1,
                        "l2": f"inputs larger than L2: one forest streams {B * fstats['factor_entries'] * 8 / 1e6:.0f} MB of factor panels per sweep "
@@ -353,7 +356,7 @@ def run_ours(args):
                        "timing": "wall clock around the K steps (forests) submitted to the worker threads, cuda synchronize + barrier on both sides, max over ranks",
                        "SimulationConfig": {"mesh_min_points": 0, "mesh_target_points": 0}},
             "clocks": clocks.summary(),
-            "e2e": {"value": world * B * args.steps / t_e2e, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "e2e": {"value": world * B * NF / t_e2e, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * t_e2e / args.steps, "n_modes_returned": len(modes), "clocks": clocks2.summary(),
                     "path": "ForestPool.solve_iter on NumPy meshes: DOF tables + mesh upload, forest solve, eigenvectors + reductions copied back into page-locked result arrays, mode records built and consumed one by one"},
             "gpu_launches": int(launches),
@@ -361,7 +364,7 @@ def run_ours(args):
                         "phases_ms": {n: lat_stats[n] for n in ("ms_symbolic", "ms_assemble", "ms_factor", "ms_lanczos", "ms_metrics")}},
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "phases_ms_per_forest": {n: v / nst for n, v in phase.items()},
+            "phases_ms_per_forest": {n: v / NF for n, v in phase.items()},
             "solver": {kk: stats[kk] for kk in ("nconv", "n_op", "n_block_op", "n_restart", "n_fronts", "n_levels", "max_front_nodes", "factor_entries",
                                                 "front_pool_doubles", "factor_flops", "max_residual", "batch_size", "batch_block_ops")},
             "kernels": kernels}
@@ -377,8 +380,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg1", choices=sorted(WORKLOADS))
-    ap.add_argument("--inflight", type=int, default=16, help="designs per forest (= per step)")
-    ap.add_argument("--workers", type=int, default=3, help="host threads / contexts, each working on its own forest")
+    ap.add_argument("--inflight", type=int, default=12, help="designs per forest (= per step)")
+    ap.add_argument("--workers", type=int, default=6, help="host threads / contexts, each working on its own forest")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     if args.impl == "reference":
