@@ -120,7 +120,8 @@ typedef struct {
   int32_t max_sn_nodes;/* supernode width limit in nodes (0 = default) */
   int32_t reuse_symbolic; /* 1 = keep ordering/front plan from the previous solve on this problem */
   int32_t refine;      /* iterative-refinement steps per operator application: 0 = chosen by probing one raw solve
-                          (1 for the reference's meshes), n > 0 = n, -1 = none */
+                          (1 for the reference's meshes), n > 0 = n, -1 = none.  Environment PLFEM_RELAX_AT=x (default
+                          0 = off) applies one step fewer once every wanted Ritz pair is within x of convergence */
   int32_t block;       /* Lanczos block size: 0 = default (4 vectors per operator application), 1 = single vector */
 } plfem_solve_opts;
 

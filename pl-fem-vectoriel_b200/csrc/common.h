@@ -206,6 +206,7 @@ struct EigenResult {
   std::vector<double> theta;  // Ritz values of OP, wanted ones, sorted by eigenvalue ascending
   int nconv = 0, n_op = 0, n_restart = 0, n_block_op = 0;
   int refine_steps = 0;       // refinement steps per operator application actually used
+  int relaxed_from = -1;      // block step from which the relaxed operator (one refinement step fewer) was applied
 };
 // A forest of independent designs laid out as one block-diagonal problem: design b owns the permuted nodes
 // [noff[b], noff[b+1]) and the vector rows [moff[b], moff[b+1]) (two unknowns per node).

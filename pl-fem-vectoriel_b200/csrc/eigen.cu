@@ -811,9 +811,13 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
   const dim3 grows((unsigned)((bd.mmax + 255) / 256), B);
 
   // operator application on P right-hand sides, captured once into a CUDA graph: R = OP(opin)
-  cudaGraph_t graph = nullptr; cudaGraphExec_t gexec = nullptr; int graph_nodes = 0;
-  struct GraphGuard { cudaGraph_t* g; cudaGraphExec_t* e; ~GraphGuard() { if (*e) cudaGraphExecDestroy(*e); if (*g) cudaGraphDestroy(*g); } } guard{&graph, &gexec};
-  auto capture_operator = [&](int rsteps) {
+  // Two versions: the accurate one (rsteps refinement steps) and a RELAXED one with one step fewer.  Inexact-Krylov
+  // theory (Bouras/Fraysse, Simoncini/Szyld) allows the error of an operator application to grow like
+  // eps / |current Ritz residual|: once every wanted Ritz pair is within `relax_at` of convergence the remaining
+  // applications use the relaxed operator (PLFEM_RELAX_AT, 0 = never).
+  cudaGraph_t graph = nullptr, graph_lo = nullptr; cudaGraphExec_t gexec = nullptr, gexec_lo = nullptr; int graph_nodes = 0, graph_nodes_lo = 0;
+  struct GraphGuard { cudaGraph_t* g; cudaGraphExec_t* e; ~GraphGuard() { if (*e) cudaGraphExecDestroy(*e); if (*g) cudaGraphDestroy(*g); } } guard{&graph, &gexec}, guard_lo{&graph_lo, &gexec_lo};
+  auto capture_operator = [&](int rsteps, cudaGraph_t& graph, cudaGraphExec_t& gexec, int& graph_nodes) {
     const int before = ctx->launches;
     PLFEM_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     try {
@@ -888,13 +892,17 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
     }
   }
   res.refine_steps = rsteps;
-  capture_operator(rsteps);
+  capture_operator(rsteps, graph, gexec, graph_nodes);
+  static const double relax_at = [] { const char* e = std::getenv("PLFEM_RELAX_AT"); return e ? atof(e) : 0.0; }();
+  bool relaxed = false;
+  if (relax_at > 0.0 && rsteps >= 1) capture_operator(rsteps - 1, graph_lo, gexec_lo, graph_nodes_lo);
 
   struct Host {                      // per-design host state of the projected problem
     std::vector<double> Th, T, w, S;
     std::vector<int> order;
     bool done = false, newly = false;
     int q_want = 0;
+    double worst = 1e300;            // largest relative residual bound among the wanted Ritz pairs at the last check
   };
   std::vector<Host> hs(B);
   for (Host& h : hs) h.Th.assign((size_t)ncvp * ncvp, 0.0);
@@ -916,8 +924,8 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
     double* Vc = V[cur].p; double* BVc = BV[cur].p;
     interleave_kernel<<<gm, 256, 0, st>>>(BVc + (int64_t)j0 * ld, ld, m, opin.p);
     ctx->launches++;
-    PLFEM_CUDA(cudaGraphLaunch(gexec, st));
-    ctx->launches += graph_nodes;
+    PLFEM_CUDA(cudaGraphLaunch(relaxed ? gexec_lo : gexec, st));
+    ctx->launches += relaxed ? graph_nodes_lo : graph_nodes;
     res.n_op += P; res.n_block_op++;
     const dim3 gdots((nb + DCOLS - 1) / DCOLS, RSPLIT, B), gsum((nb + 127) / 128, B);
     dots_block_kernel<<<gdots, 256, 0, st>>>(BVc, ld, R.p, moff, nb, hp.p, ldh, hstride);          // CGS pass 1
@@ -980,7 +988,13 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
       };
       const int k = de.k;
       int nconv = 0;
-      for (int i = 0; i < k; ++i) if (bound(h.order[i]) <= de.tol * std::max(eps23, std::fabs(h.w[h.order[i]]))) nconv++;
+      double worst = 0.0;
+      for (int i = 0; i < k; ++i) {
+        const double bnd = bound(h.order[i]), ref = std::max(eps23, std::fabs(h.w[h.order[i]]));
+        if (bnd <= de.tol * ref) nconv++;
+        worst = std::max(worst, bnd / ref);
+      }
+      h.worst = worst;
       de.nconv = nconv;
       if (nconv >= k || last_chance) {
         std::vector<int> sel(h.order.begin(), h.order.begin() + k);
@@ -1018,6 +1032,11 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
     ndone = 0;
     for (const Host& h : hs) ndone += h.done;
     if (ndone == B) return;
+    if (!relaxed && gexec_lo) {
+      double w = 0.0;
+      for (const Host& h : hs) if (!h.done) w = std::max(w, h.worst);
+      if (w <= relax_at) { relaxed = true; res.relaxed_from = res.n_block_op; }
+    }
     if (!full) continue;
     // ---- thick restart, all designs together: the largest q any unfinished design asks for
     q = 0;

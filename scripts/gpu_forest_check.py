@@ -28,4 +28,4 @@ for nb in sizes:
     dev = max(float(np.abs(o[0] / ref - 1).max()) for o in out)
     print(f"nb={nb:3d} wall={1e3*dt:8.2f} ms  per-solve={1e3*dt/nb:7.2f} ms  {nb/dt:7.1f} solves/s | sym_wall={st['ms_symbolic_wall']:.1f} "
           f"sym_own={st['ms_symbolic']:.1f} asm={st['ms_assemble']:.2f} fac={st['ms_factor']:.2f} lan={st['ms_lanczos']:.2f} "
-          f"met={st['ms_metrics']:.2f} entries={st['factor_entries']} levels={st['n_levels']} fronts={st['n_fronts']} launches={st['kernel_launches']} block_ops={st['batch_block_ops']} ok={ok} dev={dev:.1e}", flush=True)
+          f"met={st['ms_metrics']:.2f} entries={st['factor_entries']} levels={st['n_levels']} fronts={st['n_fronts']} launches={st['kernel_launches']} block_ops={st['batch_block_ops']} ok={ok} dev={dev:.1e} resid={st['max_residual']:.1e}", flush=True)
