@@ -324,10 +324,10 @@ def run_ours(args):
             traffic = tr["dram_bytes_per_launch"] * nb_prof / 16.0
     except Exception:
         pass
-    roofline = {"kernel": {"forward_sweep": "forward_small_kernel<1> (leaf fronts) + forward_kernel<1> (one launch per level)",
-                           "backward_sweep": "backward_kernel<1> (one launch per level) + backward_small_kernel<1> (leaf fronts)",
-                           "forward_sweep_4rhs": "forward_small_kernel<4> (leaf fronts) + forward_kernel<4> (one launch per level)",
-                           "backward_sweep_4rhs": "backward_kernel<4> (one launch per level) + backward_small_kernel<4> (leaf fronts)",
+    roofline = {"kernel": {"forward_sweep": "forward_subtree_kernel<1> (leaf fronts) + forward_kernel<1> (one launch per level)",
+                           "backward_sweep": "backward_kernel<1> (one launch per level) + backward_subtree_kernel<1> (leaf fronts)",
+                           "forward_sweep_4rhs": "forward_subtree_kernel<4> (leaf fronts) + forward_kernel<4> (one launch per level)",
+                           "backward_sweep_4rhs": "backward_kernel<4> (one launch per level) + backward_subtree_kernel<4> (leaf fronts)",
                            "factorize": "invert_kernel+gemm",
                            "assemble": "assemble_kernel", "spmm_B": "spmm_b_kernel", "spmv_K_residual": "resid_k_kernel"}[dom],
                 "bound": "hbm", "achieved": bytes_dom / (ms_dom * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

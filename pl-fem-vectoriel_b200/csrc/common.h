@@ -177,10 +177,12 @@ struct DevPlan {
   DevBuf<int4> w_tiles, s_tiles, ea_slabs;
   DevBuf<FwdItem> fwd_items; DevBuf<BwdItem> bwd_items; DevBuf<int32_t> gsrc;
   std::vector<int32_t> w_ptr, s_ptr, ea_ptr, fwd_ptr, bwd_ptr;  // [nlevels+1] each
-  // per-level launch lists: CTA items of the large fronts + warp tasks of the small ones
+  // per-level launch lists (CTA items of the fronts above the bottom subtrees) + the subtrees' warp tasks
   DevBuf<FwdItem> fwdb_items; DevBuf<BwdItem> bwdb_items;
+  std::vector<int32_t> fwdb_ptr, bwdb_ptr;     // [nlevels+1] each
   DevBuf<FwdTask> fwd_tasks; DevBuf<BwdTask> bwd_tasks;
-  std::vector<int32_t> fwdb_ptr, bwdb_ptr, fwd_tptr, bwd_tptr;     // [nlevels+1] each
+  DevBuf<int2> subs; DevBuf<int32_t> sub_fptr, sub_bptr;   // per subtree: {first level range, levels}; task ranges per level
+  int n_subs = 0;
   DevBuf<int64_t> lo, wo; DevBuf<int32_t> ldp; // packed panels: [F11^-1 ; W^T] (ldp x 2s) and W row-major (s2p x 2u)
   DevBuf<double> fac;                // packed factor panels: the only matrix data the sweeps read
   DevBuf<double> pool;               // all frontal matrices (factorisation workspace)

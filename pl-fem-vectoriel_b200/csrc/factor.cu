@@ -908,31 +908,48 @@ __global__ void __launch_bounds__(256, 4) backward_kernel(const BwdItem* __restr
   backward_item<false, NR, PDL>(items[blockIdx.x], P, x, sm, none);
 }
 
-// small fronts: eight warp tasks per CTA, 32 warps resident per SM
+// Bottom of the elimination forest: ONE CTA per subtree of small fronts (the fronts below level `subtree_levels`).  The
+// 8 warps run the warp tasks of the subtree level by level — leaves first on the way up, the subtree's root first on the
+// way down — with a CTA barrier between levels: the update vectors / unknowns a level produces are consumed by the same
+// CTA (global memory, visible after the barrier), so levels 0..H-1 of a sweep cost one launch instead of H, and the
+// dependent round trips of a small front overlap with those of its siblings and cousins in the same CTA.
+// sub[b] = {first entry of the subtree's level ranges in ptr, number of levels}; tasks of level l: ptr[o+l] .. ptr[o+l+1].
 template <int NR, bool PDL>
-__global__ void __launch_bounds__(256, 4) forward_small_kernel(const FwdTask* __restrict__ tasks, int ntasks, const int32_t* __restrict__ gsrc,
-                                                                const double* __restrict__ fac, RhsView rv) {
+__global__ void __launch_bounds__(256, 4) forward_subtree_kernel(const int2* __restrict__ sub, const int32_t* __restrict__ ptr,
+                                                                  const FwdTask* __restrict__ tasks, const int32_t* __restrict__ gsrc,
+                                                                  const double* __restrict__ fac, RhsView rv) {
   __shared__ __align__(16) double tile[8][KT][NR];
   if (PDL) griddep_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int id = (int)blockIdx.x * 8 + warp;
-  if (id >= ntasks) return;
-  const FwdTask t = tasks[id];
-  if (t.nr <= 32) forward_task<NR, 1, PDL>(t, gsrc, fac, rv, tile[warp], lane);
-  else forward_task<NR, 2, PDL>(t, gsrc, fac, rv, tile[warp], lane);
+  const int2 sb = sub[blockIdx.x];
+  for (int l = 0; l < sb.y; ++l) {
+    const int t1 = ptr[sb.x + l + 1];
+    for (int id = ptr[sb.x + l] + warp; id < t1; id += 8) {
+      const FwdTask t = tasks[id];
+      if (t.nr <= 32) forward_task<NR, 1, PDL>(t, gsrc, fac, rv, tile[warp], lane);
+      else forward_task<NR, 2, PDL>(t, gsrc, fac, rv, tile[warp], lane);
+    }
+    if (l + 1 < sb.y) __syncthreads();
+  }
 }
 
 template <int NR, bool PDL>
-__global__ void __launch_bounds__(256, 4) backward_small_kernel(const BwdTask* __restrict__ tasks, int ntasks, const int32_t* __restrict__ strct,
-                                                                 const double* __restrict__ fac, double* x) {
+__global__ void __launch_bounds__(256, 4) backward_subtree_kernel(const int2* __restrict__ sub, const int32_t* __restrict__ ptr,
+                                                                   const BwdTask* __restrict__ tasks, const int32_t* __restrict__ strct,
+                                                                   const double* __restrict__ fac, double* x) {
   __shared__ __align__(16) double tile[8][KT][NR];
   if (PDL) griddep_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int id = (int)blockIdx.x * 8 + warp;
-  if (id >= ntasks) return;
-  const BwdTask t = tasks[id];
-  if (t.nc <= 32) backward_task<NR, 1, PDL>(t, strct, fac, x, tile[warp], lane);
-  else backward_task<NR, 2, PDL>(t, strct, fac, x, tile[warp], lane);
+  const int2 sb = sub[blockIdx.x];
+  for (int l = sb.y - 1; l >= 0; --l) {
+    const int t1 = ptr[sb.x + l + 1];
+    for (int id = ptr[sb.x + l] + warp; id < t1; id += 8) {
+      const BwdTask t = tasks[id];
+      if (t.nc <= 32) backward_task<NR, 1, PDL>(t, strct, fac, x, tile[warp], lane);
+      else backward_task<NR, 2, PDL>(t, strct, fac, x, tile[warp], lane);
+    }
+    if (l > 0) __syncthreads();
+  }
 }
 
 // ---- pack: the solve phase reads only the left block column of a front (and W a second time, row-major) ----
@@ -1107,14 +1124,12 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
   }
   std::vector<int4> wt, stl, ea;
   std::vector<FwdItem> fw; std::vector<BwdItem> bw;
-  std::vector<FwdItem> fwb; std::vector<BwdItem> bwb;     // per-level launches: CTA items of large fronts ...
-  std::vector<FwdTask> ft; std::vector<BwdTask> bt;       // ... and warp tasks of small ones
-  D.fwd_tptr.assign(P.nlevels + 1, 0); D.bwd_tptr = D.fwdb_ptr = D.bwdb_ptr = D.fwd_tptr;
-  // which fronts take the warp-per-task path: by default the LEAVES of the elimination tree (no children to gather
-  // from, hundreds per design, ~75 x 30 entries each: a 256-thread CTA per leaf is bound by CTA turnover); the limits
-  // widen it to every front with at most that many pivot / update unknowns
-  const int small_s2 = small_front_limit("PLFEM_SMALL_S2", 0), small_u2 = small_front_limit("PLFEM_SMALL_U2", 0);
-  const bool leaf_warp = small_front_limit("PLFEM_LEAF_WARP", 1) != 0;
+  std::vector<FwdItem> fwb; std::vector<BwdItem> bwb;     // per-level launches: CTA items of the fronts above the subtrees
+  D.fwdb_ptr.assign(P.nlevels + 1, 0); D.bwdb_ptr = D.fwdb_ptr;
+  // The fronts below level H (PLFEM_SUBTREE_LEVELS, default 1: the leaves — hundreds per design, ~75 x 30 entries each; a
+  // 256-thread CTA per leaf is bound by CTA turnover) are served by warp tasks, one CTA per maximal subtree of such fronts.
+  const int H = small_front_limit("PLFEM_SUBTREE_LEVELS", 1);
+  auto in_sub = [&](int f) { return P.level[f] < H; };
   D.w_ptr.assign(P.nlevels + 1, 0); D.s_ptr = D.ea_ptr = D.fwd_ptr = D.bwd_ptr = D.w_ptr;
   D.lmax_m.assign(P.nlevels, 0);
   // flattened child -> parent gather: per front, for every front row (2nf unknowns) the offset into the
@@ -1160,7 +1175,7 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
         // row groups x rows per thread: <= 32 rows (1,1), <= 64 (1,2), <= 128 (2,2), larger fronts in slabs of 64 rows (1,2)
         const int G = (rows > 64 && rows <= 128) ? 2 : 1, Rr = rows <= 32 ? 1 : 2;
         const int nch = P.cptr[f + 1] - P.cptr[f];
-        const bool fsmall = s2 <= small_s2 || (leaf_warp && nch == 0 && s2 <= 64);
+        const bool fsmall = in_sub(f);
         for (int r0 = 0; r0 < rows; r0 += 32 * G * Rr) {
           FwdItem it{};
           it.f = f; it.row0 = r0; it.nrows = std::min(32 * G * Rr, rows - r0); it.G = G | (Rr << 8); it.s2 = s2; it.ld = ldp[f];
@@ -1171,19 +1186,9 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
           fw.push_back(it);
           if (!fsmall) fwb.push_back(it);
         }
-        if (fsmall) {
-          // rows per warp: at most 64 factor entries per lane, so a task is a handful of memory round trips
-          const int R = (s2 <= 32 && rows > 32) ? 2 : 1;
-          for (int r0 = 0; r0 < rows; r0 += 32 * R) {
-            FwdTask t{};
-            t.s2 = s2; t.rows = rows; t.r0 = r0; t.nr = std::min(32 * R, rows - r0); t.ldp = ldp[f]; t.goff = goff[f]; t.uoff = uoff[f];
-            t.nch = nch; t.lo = lo[f]; t.g0 = 2 * (int64_t)P.first[f];
-            ft.push_back(t);
-          }
-        }
       }
       if (u2 > 0) {
-        const bool bsmall = (s2 <= small_s2 && u2 <= small_u2) || (leaf_warp && P.cptr[f + 1] == P.cptr[f] && s2 <= 64 && u2 <= 128);
+        const bool bsmall = in_sub(f);
         const bool rows_style = u2 <= bwd_rows_u2;
         const int Gb = rows_style ? (s2 <= 32 ? 1 : 2) : 0;   // pivot columns per thread; 0 = one warp per column
         const int cw = rows_style ? 32 * Gb : BWD_COLS;
@@ -1197,24 +1202,70 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
           bw.push_back(it);
           if (!bsmall) bwb.push_back(it);
         }
-        if (bsmall) {
-          const int R = (s2 > 32 && u2 <= 32) ? 2 : 1;
-          for (int c0 = 0; c0 < s2; c0 += 32 * R) {
-            BwdTask t{};
-            t.s2 = s2; t.u2 = u2; t.c0 = c0; t.nc = std::min(32 * R, s2 - c0); t.s2p = (s2 + 3) & ~3; t.soff = P.sptr[f];
-            t.wo = wo[f]; t.g0 = 2 * (int64_t)P.first[f];
-            bt.push_back(t);
-          }
-        }
       }
     }
     D.w_ptr[l + 1] = (int32_t)wt.size(); D.s_ptr[l + 1] = (int32_t)stl.size(); D.ea_ptr[l + 1] = (int32_t)ea.size();
     D.fwd_ptr[l + 1] = (int32_t)fw.size(); D.bwd_ptr[l + 1] = (int32_t)bw.size();
-    D.fwd_tptr[l + 1] = (int32_t)ft.size(); D.bwd_tptr[l + 1] = (int32_t)bt.size();
     D.fwdb_ptr[l + 1] = (int32_t)fwb.size(); D.bwdb_ptr[l + 1] = (int32_t)bwb.size();
   }
-  D.fwd_tasks.upload(ctx, ft); D.bwd_tasks.upload(ctx, bt);
   D.fwdb_items.upload(ctx, fwb); D.bwdb_items.upload(ctx, bwb);
+  {
+    // subtree task lists.  Fronts are numbered in post-order: the subtree of root r is the contiguous range ending at r.
+    std::vector<int32_t> size(P.nfronts, 1);
+    for (int f = 0; f < P.nfronts; ++f) if (P.parent[f] >= 0) size[P.parent[f]] += size[f];
+    std::vector<FwdTask> ft; std::vector<BwdTask> bt;
+    std::vector<int32_t> fptr(1, 0), bptr(1, 0);
+    std::vector<int2> subs;
+    // a CTA serves a GROUP of neighbouring subtrees, level by level, so that its 8 warps have tasks at the widest level
+    std::vector<std::vector<int32_t>> by_level;
+    auto close_group = [&] {
+      if (by_level.empty()) return;
+      subs.push_back(make_int2((int)fptr.size() - 1, (int)by_level.size()));
+      for (const std::vector<int32_t>& fl : by_level) {
+        for (int f : fl) {
+          const int s2 = 2 * P.s[f], u2 = 2 * (P.sptr[f + 1] - P.sptr[f]), rows = s2 + u2;
+          const int nch = P.cptr[f + 1] - P.cptr[f];
+          // rows per warp: at most 64 factor entries per lane in flight order, so a task is a handful of round trips
+          const int Rf = (s2 <= 32 && rows > 32) ? 2 : 1;
+          for (int r0 = 0; r0 < rows; r0 += 32 * Rf) {
+            FwdTask t{};
+            t.s2 = s2; t.rows = rows; t.r0 = r0; t.nr = std::min(32 * Rf, rows - r0); t.ldp = ldp[f]; t.goff = goff[f]; t.uoff = uoff[f];
+            t.nch = nch; t.lo = lo[f]; t.g0 = 2 * (int64_t)P.first[f];
+            ft.push_back(t);
+          }
+          if (u2 > 0) {
+            const int Rb = (s2 > 32 && u2 <= 32) ? 2 : 1;
+            for (int c0 = 0; c0 < s2; c0 += 32 * Rb) {
+              BwdTask t{};
+              t.s2 = s2; t.u2 = u2; t.c0 = c0; t.nc = std::min(32 * Rb, s2 - c0); t.s2p = (s2 + 3) & ~3; t.soff = P.sptr[f];
+              t.wo = wo[f]; t.g0 = 2 * (int64_t)P.first[f];
+              bt.push_back(t);
+            }
+          }
+        }
+        fptr.push_back((int32_t)ft.size()); bptr.push_back((int32_t)bt.size());
+      }
+      by_level.clear();
+    };
+    int widest = 0;     // forward tasks of the current group at its widest level
+    for (int r = 0; r < P.nfronts; ++r) {
+      if (!in_sub(r) || (P.parent[r] >= 0 && in_sub(P.parent[r]))) continue;     // not the root of a maximal subtree
+      const int nl = P.level[r] + 1;
+      if ((int)by_level.size() < nl) by_level.resize(nl);
+      for (int f = r - size[r] + 1; f <= r; ++f) by_level[P.level[f]].push_back(f);
+      widest = 0;
+      for (const std::vector<int32_t>& fl : by_level) {
+        int nt = 0;
+        for (int f : fl) { const int s2 = 2 * P.s[f], rows = s2 + 2 * (P.sptr[f + 1] - P.sptr[f]); nt += (rows + ((s2 <= 32 && rows > 32) ? 63 : 31)) / ((s2 <= 32 && rows > 32) ? 64 : 32); }
+        widest = std::max(widest, nt);
+      }
+      if (widest >= 8) close_group();
+    }
+    close_group();
+    D.n_subs = (int)subs.size();
+    D.fwd_tasks.upload(ctx, ft); D.bwd_tasks.upload(ctx, bt);
+    D.sub_fptr.upload(ctx, fptr); D.sub_bptr.upload(ctx, bptr); D.subs.upload(ctx, subs);
+  }
   {
     // backward queue of the persistent operator kernel: levels descending; completion counters
     std::vector<BwdItem> bq; bq.reserve(bw.size());
@@ -1294,8 +1345,8 @@ void launch_sweep(void (*kernel)(KArgs...), bool pdl, int grid, cudaStream_t st,
   PLFEM_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
 }
 
-// nrhs right-hand sides (1 or SOLVE_NRHS), INTERLEAVED: entry i of right-hand side r at b[i * nrhs + r].  Per level: one
-// launch for the CTA items of the large fronts, one for the warp tasks of the small ones (most levels have one kind).
+// nrhs right-hand sides (1 or SOLVE_NRHS), INTERLEAVED: entry i of right-hand side r at b[i * nrhs + r].  One launch for the
+// bottom subtrees, then one launch per remaining level (CTA items).
 void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double* z, int nrhs) {
   const PlanView v = sweep_view(D);
   if (nrhs != 1 && nrhs != SOLVE_NRHS) throw StatusError(PLFEM_ERR_INTERNAL, "unsupported number of right-hand sides");
@@ -1303,23 +1354,19 @@ void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double
   const bool pdl = use_pdl();
   bool first = true;     // the first launch follows kernels that are not PDL-aware: plain launch
   const int32_t* gs = D.gsrc.p;
+  if (D.n_subs > 0) {
+    if (nrhs == 1) launch_sweep(forward_subtree_kernel<1, false>, false, D.n_subs, ctx->stream, D.subs.p, D.sub_fptr.p, D.fwd_tasks.p, gs, D.fac.p, rv);
+    else launch_sweep(forward_subtree_kernel<SOLVE_NRHS, false>, false, D.n_subs, ctx->stream, D.subs.p, D.sub_fptr.p, D.fwd_tasks.p, gs, D.fac.p, rv);
+    first = false; ctx->launches++;
+  }
   for (int l = 0; l < D.nlevels; ++l) {
-    const int nbig = D.fwdb_ptr[l + 1] - D.fwdb_ptr[l], nt = D.fwd_tptr[l + 1] - D.fwd_tptr[l];
-    if (nbig > 0) {
-      const FwdItem* items = D.fwdb_items.p + D.fwdb_ptr[l];
-      const bool p = pdl && !first;
-      if (nrhs == 1) { if (p) launch_sweep(forward_kernel<1, true>, true, nbig, ctx->stream, items, gs, v, rv); else launch_sweep(forward_kernel<1, false>, false, nbig, ctx->stream, items, gs, v, rv); }
-      else { if (p) launch_sweep(forward_kernel<SOLVE_NRHS, true>, true, nbig, ctx->stream, items, gs, v, rv); else launch_sweep(forward_kernel<SOLVE_NRHS, false>, false, nbig, ctx->stream, items, gs, v, rv); }
-      first = false; ctx->launches++;
-    }
-    if (nt > 0) {
-      const FwdTask* tasks = D.fwd_tasks.p + D.fwd_tptr[l];
-      const int grid = (nt + 7) / 8;
-      const bool p = pdl && !first;
-      if (nrhs == 1) { if (p) launch_sweep(forward_small_kernel<1, true>, true, grid, ctx->stream, tasks, nt, gs, D.fac.p, rv); else launch_sweep(forward_small_kernel<1, false>, false, grid, ctx->stream, tasks, nt, gs, D.fac.p, rv); }
-      else { if (p) launch_sweep(forward_small_kernel<SOLVE_NRHS, true>, true, grid, ctx->stream, tasks, nt, gs, D.fac.p, rv); else launch_sweep(forward_small_kernel<SOLVE_NRHS, false>, false, grid, ctx->stream, tasks, nt, gs, D.fac.p, rv); }
-      first = false; ctx->launches++;
-    }
+    const int nbig = D.fwdb_ptr[l + 1] - D.fwdb_ptr[l];
+    if (nbig == 0) continue;
+    const FwdItem* items = D.fwdb_items.p + D.fwdb_ptr[l];
+    const bool p = pdl && !first;
+    if (nrhs == 1) { if (p) launch_sweep(forward_kernel<1, true>, true, nbig, ctx->stream, items, gs, v, rv); else launch_sweep(forward_kernel<1, false>, false, nbig, ctx->stream, items, gs, v, rv); }
+    else { if (p) launch_sweep(forward_kernel<SOLVE_NRHS, true>, true, nbig, ctx->stream, items, gs, v, rv); else launch_sweep(forward_kernel<SOLVE_NRHS, false>, false, nbig, ctx->stream, items, gs, v, rv); }
+    first = false; ctx->launches++;
   }
 }
 
@@ -1328,20 +1375,17 @@ void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs) {
   const PlanView v = sweep_view(D);
   const bool pdl = use_pdl();
   for (int l = D.nlevels - 1; l >= 0; --l) {
-    const int nbig = D.bwdb_ptr[l + 1] - D.bwdb_ptr[l], nt = D.bwd_tptr[l + 1] - D.bwd_tptr[l];
-    if (nbig > 0) {
-      const BwdItem* items = D.bwdb_items.p + D.bwdb_ptr[l];
-      if (nrhs == 1) { if (pdl) launch_sweep(backward_kernel<1, true>, true, nbig, ctx->stream, items, v, x); else launch_sweep(backward_kernel<1, false>, false, nbig, ctx->stream, items, v, x); }
-      else { if (pdl) launch_sweep(backward_kernel<SOLVE_NRHS, true>, true, nbig, ctx->stream, items, v, x); else launch_sweep(backward_kernel<SOLVE_NRHS, false>, false, nbig, ctx->stream, items, v, x); }
-      ctx->launches++;
-    }
-    if (nt > 0) {
-      const BwdTask* tasks = D.bwd_tasks.p + D.bwd_tptr[l];
-      const int grid = (nt + 7) / 8;
-      if (nrhs == 1) { if (pdl) launch_sweep(backward_small_kernel<1, true>, true, grid, ctx->stream, tasks, nt, D.strct.p, D.fac.p, x); else launch_sweep(backward_small_kernel<1, false>, false, grid, ctx->stream, tasks, nt, D.strct.p, D.fac.p, x); }
-      else { if (pdl) launch_sweep(backward_small_kernel<SOLVE_NRHS, true>, true, grid, ctx->stream, tasks, nt, D.strct.p, D.fac.p, x); else launch_sweep(backward_small_kernel<SOLVE_NRHS, false>, false, grid, ctx->stream, tasks, nt, D.strct.p, D.fac.p, x); }
-      ctx->launches++;
-    }
+    const int nbig = D.bwdb_ptr[l + 1] - D.bwdb_ptr[l];
+    if (nbig == 0) continue;
+    const BwdItem* items = D.bwdb_items.p + D.bwdb_ptr[l];
+    if (nrhs == 1) { if (pdl) launch_sweep(backward_kernel<1, true>, true, nbig, ctx->stream, items, v, x); else launch_sweep(backward_kernel<1, false>, false, nbig, ctx->stream, items, v, x); }
+    else { if (pdl) launch_sweep(backward_kernel<SOLVE_NRHS, true>, true, nbig, ctx->stream, items, v, x); else launch_sweep(backward_kernel<SOLVE_NRHS, false>, false, nbig, ctx->stream, items, v, x); }
+    ctx->launches++;
+  }
+  if (D.n_subs > 0) {
+    if (nrhs == 1) { if (pdl) launch_sweep(backward_subtree_kernel<1, true>, true, D.n_subs, ctx->stream, D.subs.p, D.sub_bptr.p, D.bwd_tasks.p, D.strct.p, D.fac.p, x); else launch_sweep(backward_subtree_kernel<1, false>, false, D.n_subs, ctx->stream, D.subs.p, D.sub_bptr.p, D.bwd_tasks.p, D.strct.p, D.fac.p, x); }
+    else { if (pdl) launch_sweep(backward_subtree_kernel<SOLVE_NRHS, true>, true, D.n_subs, ctx->stream, D.subs.p, D.sub_bptr.p, D.bwd_tasks.p, D.strct.p, D.fac.p, x); else launch_sweep(backward_subtree_kernel<SOLVE_NRHS, false>, false, D.n_subs, ctx->stream, D.subs.p, D.sub_bptr.p, D.bwd_tasks.p, D.strct.p, D.fac.p, x); }
+    ctx->launches++;
   }
 }
 
