@@ -215,7 +215,7 @@ def run_ours(args):
     def forest_resident(_pool, c, _):
         pbs = resident(c)
         kk = min(n_modes + 12, 2 * pbs[0].n_interior - 4)
-        return _cabi.solve_modes_batch(c, pbs, [mat] * B, [sigma] * B, [kk] * B, tol=1e-7, maxiter=12000, want_vectors=False,
+        return _cabi.solve_modes_batch(c, pbs, [mat] * B, [sigma] * B, [kk] * B, tol=_cabi.EIG_TOL, maxiter=12000, want_vectors=False,
                                        reuse_symbolic=False)
 
     for _ in range(args.warmup):                           # every worker thread gets its context and problems

@@ -61,7 +61,7 @@ class ForestPool:
                 mats.append(m); keep.append(k_)
                 sigmas.append(sigma_estimate(geo))
                 ks.append(min(n_modes + 12, 2 * pb.n_interior - 4))
-            res = _cabi.solve_modes_batch(ctx, problems, mats, sigmas, ks, tol=1e-7, maxiter=12000,
+            res = _cabi.solve_modes_batch(ctx, problems, mats, sigmas, ks, tol=_cabi.EIG_TOL, maxiter=12000,
                                           want_vectors=self.want_vectors)
             out, stats = [], []
             for (geo, mesh, n_modes), pb, (vals, vecs, met, ncore, st, status) in zip(jobs, problems, res):

@@ -205,7 +205,7 @@ bool ensure_plan(plfem_problem* pb, int leaf_nodes, int max_sn_nodes, bool reuse
   const int32_t n = pb->adj.n;
   std::vector<double> x(n), y(n);
   for (int32_t i = 0; i < n; ++i) { x[i] = pb->dof.doflocs[pb->dof.interior[i]]; y[i] = pb->dof.doflocs[pb->dof.N + pb->dof.interior[i]]; }
-  build_front_plan(pb->adj, x.data(), y.data(), opt, pb->plan);
+  build_front_plan(pb->dof, pb->adj, x.data(), y.data(), opt, pb->plan);
   pb->plan_opt = opt;
   pb->plan_ready = true;
   pb->perm_pat_ready = false;

@@ -557,7 +557,6 @@ __global__ void __launch_bounds__(256) write_evecs_kernel(int32_t row0, int32_t 
 
 void launch_spmm_b(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, const double* x, double* y, int nrhs, int64_t ld) {
   const unsigned g = (unsigned)(((int64_t)pat.n * 4 + 255) / 256);
-  const double* minv = d_vals + (int64_t)S_MINV * pat.nnz;
   if (nrhs == 1) spmm_b_kernel<1><<<g, 256, 0, ctx->stream>>>(pat.n, pat.rowptr.p, pat.col.p, minv, (const double2*)x, (double2*)y, 0);
   else spmm_b_kernel<SOLVE_NRHS><<<g, 256, 0, ctx->stream>>>(pat.n, pat.rowptr.p, pat.col.p, minv, (const double2*)x, (double2*)y, ld / 2);
   PLFEM_CUDA(cudaGetLastError());
@@ -596,7 +595,6 @@ void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const do
   Sdev.alloc(ctx, (size_t)ncv * ncv);
   int cur = 0;
   const unsigned gm = (unsigned)((m + 255) / 256);
-  const unsigned gspmm = (unsigned)(((int64_t)pat.n * 4 + 255) / 256);
   auto spmm = [&](const double* x, double* y) {
     launch_spmm_b(ctx, pat, d_vals, x, y);
   };
@@ -903,6 +901,7 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
     bool done = false, newly = false;
     int q_want = 0;
     double worst = 1e300;            // largest relative residual bound among the wanted Ritz pairs at the last check
+    int best_nconv = -1, stalled = 0; // restarts since the number of converged pairs last grew
   };
   std::vector<Host> hs(B);
   for (Host& h : hs) h.Th.assign((size_t)ncvp * ncvp, 0.0);
@@ -1012,6 +1011,14 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
           de.err = "block Lanczos: " + std::to_string(nconv) + " of " + std::to_string(k) + " eigenpairs converged after " + std::to_string(res.n_restart) + " restarts";
         }
         h.done = true; h.newly = true;
+      } else if (full && (nconv > h.best_nconv ? (h.best_nconv = nconv, h.stalled = 0) : ++h.stalled) >= 8) {
+        // eight restarts without a single newly converged pair: the operator is too inaccurate for the recurrence to make
+        // progress (a raw solve the probe judged acceptable but is not) — report it instead of spinning to maxiter
+        de.status = PLFEM_ERR_NO_CONVERGENCE;
+        de.err = "block Lanczos stagnated: " + std::to_string(nconv) + " of " + std::to_string(k) + " eigenpairs after " +
+                 std::to_string(res.n_restart) + " restarts, none newly converged in the last 8 (inaccurate factorisation of A - sigma*B?)";
+        de.n_block_op = res.n_block_op; de.n_restart = res.n_restart;
+        h.done = true;
       } else if (full) {
         // thick restart: this design wants its q best Ritz vectors (q = ncvp - P*t so that whole blocks fit again)
         const int keep = k + std::min(nconv, (ncvp - k) / 2);

@@ -77,7 +77,9 @@ struct FrontPlan {
 };
 
 // adjacency = pattern of interior nodes in *interior index* numbering (identity order over DofTables::interior)
-void build_front_plan(const Pattern& adj, const double* x, const double* y, const SymbolicOptions& opt, FrontPlan& out);
+// dof: the mesh's DOF tables (the dissection runs on its P1 vertex graph and is lifted to the P2 nodes)
+void build_front_plan(const DofTables& dof, const Pattern& adj, const double* x, const double* y, const SymbolicOptions& opt,
+                      FrontPlan& out);
 
 // Forest of several independent designs as ONE plan / ONE block-diagonal pattern: node ids, front ids and all
 // offsets of design b are shifted behind those of designs 0..b-1; level l of the result is the union of the

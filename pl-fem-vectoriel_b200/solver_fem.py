@@ -191,7 +191,7 @@ class TrueVectorialMaxwellSolver:
         N_solve = pb.n_interior
         sigma = sigma_estimate(geo)
         n_req = min(n_modes_target + 12, 2 * N_solve - 4)
-        beta_sq, evecs, met, n_core_dofs, stats = pb.solve_modes(mat, sigma, n_req, tol=1e-7, maxiter=12000, v0=v0,
+        beta_sq, evecs, met, n_core_dofs, stats = pb.solve_modes(mat, sigma, n_req, tol=_cabi.EIG_TOL, maxiter=12000, v0=v0,
                                                                  **solver_opts)
         self.last_stats = stats.as_dict()
         modes_guided, modes_raw, frac_core = modes_from_solution(geo, N_solve, beta_sq, evecs, met, n_core_dofs)

@@ -359,7 +359,7 @@ def test_useless_factorisation_is_reported_not_iterated():
     try:
         vals, _, _, _, st = pb.solve_modes(mat, sigma, 22, want_vectors=False)
     except _cabi.PlfemError as e:
-        assert e.status == 6
+        assert e.status in (5, 6)            # SINGULAR from the probe, or NO_CONVERGENCE from the stagnation guard
         return
     assert st.n_block_op < 200
     s = O.interior_system(g, mesh)
@@ -383,7 +383,7 @@ def test_failed_design_does_not_poison_its_forest(small_case):
     alone, araw = TrueVectorialMaxwellSolver(g).solve_vectorial_modes(mesh, 4, return_raw=True)
     with ForestPool(batch=3, workers=1) as pool:
         out = pool.solve_forest([(g, mesh, 4), (g7, bad_mesh, 10), (g, mesh, 4)], return_raw=True)
-    assert isinstance(out[1], _cabi.PlfemError) and out[1].status == 6
+    assert isinstance(out[1], _cabi.PlfemError) and out[1].status in (5, 6)
     for modes, raw in (out[0], out[2]):
         assert np.abs(raw["beta_sq"] / araw["beta_sq"] - 1).max() < 1e-9 and len(modes) == len(alone)
         assert raw["stats"]["max_residual"] < 1e-9
