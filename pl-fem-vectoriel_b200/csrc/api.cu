@@ -545,13 +545,18 @@ static void solve_forest(plfem_ctx* ctx, int nb, plfem_problem* const* pbs, cons
     std::vector<const FrontPlan*> plans(nb); std::vector<const Pattern*> pats(nb);
     for (int b = 0; b < nb; ++b) { plans[b] = &pbs[b]->plan; pats[b] = &pbs[b]->perm_pat; }
     std::vector<int32_t> node_off;
+    static const bool timing = std::getenv("PLFEM_TIMING") != nullptr;
+    const double ta = now_ms();
     merge_front_plans(plans, W.plan, node_off, W.front_off);
     merge_patterns(pats, W.pat, W.nnz_off);
+    const double tb = now_ms();
     W.bd.set(ctx, node_off);
     upload_pattern(ctx, W.pat, W.dpat);
+    const double tc = now_ms();
     build_dev_plan(ctx, W.plan, W.dplan);
     W.d_perm.upload(ctx, W.plan.perm);
     W.ready = true;
+    if (timing) fprintf(stderr, "[plfem] forest of %d: merge %.2f ms, pattern upload %.2f ms, device plan %.2f ms\n", nb, tb - ta, tc - tb, now_ms() - tc);
   }
   const BatchDims& bd = W.bd;
   const int64_t n_tot = bd.noff[nb];

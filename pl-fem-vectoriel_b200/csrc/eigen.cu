@@ -557,6 +557,7 @@ __global__ void __launch_bounds__(256) write_evecs_kernel(int32_t row0, int32_t 
 
 void launch_spmm_b(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, const double* x, double* y, int nrhs, int64_t ld) {
   const unsigned g = (unsigned)(((int64_t)pat.n * 4 + 255) / 256);
+  const double* minv = d_vals + (int64_t)S_MINV * pat.nnz;
   if (nrhs == 1) spmm_b_kernel<1><<<g, 256, 0, ctx->stream>>>(pat.n, pat.rowptr.p, pat.col.p, minv, (const double2*)x, (double2*)y, 0);
   else spmm_b_kernel<SOLVE_NRHS><<<g, 256, 0, ctx->stream>>>(pat.n, pat.rowptr.p, pat.col.p, minv, (const double2*)x, (double2*)y, ld / 2);
   PLFEM_CUDA(cudaGetLastError());
@@ -586,7 +587,6 @@ void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const do
   const int64_t m = 2 * (int64_t)pat.n;
   const int64_t ld = m;
   cudaStream_t st = ctx->stream;
-  const double* minv = d_vals + (int64_t)S_MINV * pat.nnz;
   DevBuf<double> V[2], BV[2], r, u, h1, h2, alpha, beta, Sdev, rt, rdx;
   for (int b = 0; b < 2; ++b) { V[b].alloc(ctx, (size_t)ld * (ncv + 1)); BV[b].alloc(ctx, (size_t)ld * (ncv + 1)); }
   r.alloc(ctx, m); u.alloc(ctx, m);
