@@ -319,9 +319,11 @@ def run_ours(args):
     ms_dom, bytes_dom = prof[dom]
     traffic = None          # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (same forest size)
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["sweeps"].get(dom)
-        if tr:      # captured on a forest of 16 designs: scale to this forest (traffic is proportional to the designs)
-            traffic = tr["dram_bytes_per_launch"] * nb_prof / 16.0
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        tr = tj["sweeps"].get(dom)
+        if tr:      # whole-sweep DRAM bytes of the captured forest, scaled to this forest (traffic is proportional to the
+            #         designs) and spread over the same launches `achieved` is quoted per
+            traffic = tr["dram_bytes"] * nb_prof / float(tj.get("designs", 12)) / launches_per
     except Exception:
         pass
     roofline = {"kernel": {"forward_sweep": "forward_subtree_kernel<1> (leaf fronts) + forward_kernel<1> (one launch per level)",

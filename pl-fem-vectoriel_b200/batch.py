@@ -31,13 +31,19 @@ from .solver_fem import TrueVectorialMaxwellSolver, modes_from_solution, sigma_e
 class ForestPool:
     """``solve_many(jobs)`` with jobs = ``(geometry, mesh, n_modes_target)`` -> list of mode lists."""
 
-    def __init__(self, device: int = 0, batch: int = 8, workers: int = 2, want_vectors: bool = True):
+    def __init__(self, device: int = 0, batch: int = 8, workers: int = 2, want_vectors: bool = True, host_threads: int = 0):
         self.device, self.batch, self.workers = int(device), max(1, int(batch)), max(1, int(workers))
         self.want_vectors = want_vectors
-        _cabi.load()
+        lib = _cabi.load()
+        # host threads per forest: the cores this process may count on (its share of the node under torchrun), spread
+        # over the forests in flight with some oversubscription — hundreds of runnable threads per core cost more than
+        # the idle cores they could fill
+        cores = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
+        self.host_threads = host_threads or max(1, min(self.batch, -(-3 * cores // (2 * self.workers))))
+        lib.plfem_set_host_threads(self.host_threads)
         self._local = threading.local()
         self._pool = ThreadPoolExecutor(max_workers=self.workers, thread_name_prefix="plfem-forest")
-        self._build = ThreadPoolExecutor(max_workers=min(self.batch, os.cpu_count() or 1), thread_name_prefix="plfem-dof")
+        self._build = ThreadPoolExecutor(max_workers=max(1, min(self.batch, cores)), thread_name_prefix="plfem-dof")
         self.last_stats: List[dict] = []
 
     def _ctx(self):
@@ -116,6 +122,7 @@ class ForestPool:
     def close(self):
         self._pool.shutdown(wait=True)
         self._build.shutdown(wait=True)
+        _cabi.load().plfem_set_host_threads(0)
 
     def __enter__(self):
         return self

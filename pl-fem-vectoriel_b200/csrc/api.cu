@@ -493,7 +493,7 @@ static void solve_forest(plfem_ctx* ctx, int nb, plfem_problem* const* pbs, cons
   std::vector<std::vector<uint8_t>> masks(nb);
   const bool have_work = reuse_work && W.ready;
   {
-    const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+    const int hw = host_thread_budget();      // threads this call may occupy (lowered when several forests / ranks share the host)
     const int outer = std::min(nb, hw);
     std::atomic<int> next{0};
     std::exception_ptr err; std::mutex mu;

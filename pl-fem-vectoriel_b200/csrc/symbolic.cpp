@@ -145,6 +145,12 @@ void parallel_for(int64_t n, int64_t grain, F&& fn) {
 // ------------------------------------------------------------------------------------------------
 void set_host_threads(int n) { g_host_threads.store(std::max(0, n)); }
 void set_host_threads_local(int n) { tl_host_threads = std::max(0, n); }
+int host_thread_budget() {
+  const int set = g_host_threads.load(std::memory_order_relaxed);
+  if (set > 0) return set;
+  if (const char* e = std::getenv("PLFEM_HOST_THREADS")) return std::max(1, atoi(e));
+  return (int)std::max(1u, std::thread::hardware_concurrency());
+}
 
 void build_pattern(const DofTables& d, const std::vector<int32_t>& new_of_old, int32_t n_new, Pattern& out) {
   out.n = n_new;

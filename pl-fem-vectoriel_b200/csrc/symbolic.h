@@ -45,6 +45,9 @@ void relabel_pattern(const Pattern& src, const std::vector<int32_t>& old_of, con
 void set_host_threads(int n);
 // the same for the calling thread only (0 = follow the global setting)
 void set_host_threads_local(int n);
+// threads one call (a solve, or the analysis of a whole forest) may occupy: the plfem_set_host_threads value,
+// $PLFEM_HOST_THREADS, or every hardware thread
+int host_thread_budget();
 
 struct SymbolicOptions {
   int leaf_nodes = 24;   // stop dissecting below this many nodes

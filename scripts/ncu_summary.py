@@ -1,3 +1,4 @@
+import os
 """Compact per-launch table (and per-sweep DRAM traffic) from an `ncu --set full` report.
 
     python scripts/ncu_summary.py report.ncu-rep out.csv [traffic.json]
@@ -34,7 +35,8 @@ def main(rep, out, traffic=None):
     if traffic:
         for t in tot.values():
             t["dram_bytes_per_launch"] = t["dram_bytes"] / max(t["launches"], 1)
-        json.dump({"source": rep, "note": "one sweep pair of a 16-design forest of config 1, ncu --set full (cold caches, serialised)",
+        json.dump({"source": rep, "designs": int(os.environ.get("DESIGNS", "12")),
+                   "note": "one sweep pair of a forest of config-1 designs, ncu --set full (cold caches, serialised)",
                    "sweeps": tot}, open(traffic, "w"), indent=1)
     print(json.dumps(tot))
 
