@@ -83,7 +83,6 @@ struct SolveWork {
   std::vector<int64_t> nnz_off;
   std::vector<int32_t> front_off;
   FrontPlan plan;                              // merged front plan
-  Pattern pat;                                 // merged pattern, permuted interior nodes
   DevPattern dpat;
   DevPlan dplan;
   DevBuf<double> d_vals;                       // NV_SOLVE x nnz
@@ -118,7 +117,6 @@ struct plfem_problem {
   // interior solve path (host side; the device side of a solve lives in a SolveWork)
   Pattern adj;  bool adj_ready = false;        // interior nodes, interior-index numbering (for dissection)
   FrontPlan plan; bool plan_ready = false; SymbolicOptions plan_opt;
-  Pattern perm_pat; bool perm_pat_ready = false;
   std::shared_ptr<SolveWork> work;             // device state of the last single-design solve (profile / debug hooks, reuse)
   int plan_serial = 0;                         // bumped whenever the front plan is rebuilt
 };
@@ -201,14 +199,14 @@ bool ensure_plan(plfem_problem* pb, int leaf_nodes, int max_sn_nodes, bool reuse
   if (max_sn_nodes > 0) opt.max_sn_nodes = max_sn_nodes;
   need(opt.max_sn_nodes <= 64 && opt.leaf_nodes <= 64, "leaf_nodes and max_sn_nodes must be <= 64");
   if (pb->plan_ready && reuse && opt.leaf_nodes == pb->plan_opt.leaf_nodes && opt.max_sn_nodes == pb->plan_opt.max_sn_nodes) return false;
-  ensure_adj(pb);
-  const int32_t n = pb->adj.n;
+  const bool need_adj = front_plan_needs_adjacency(pb->dof);
+  if (need_adj) ensure_adj(pb);
+  const int32_t n = (int32_t)pb->dof.interior.size();
   std::vector<double> x(n), y(n);
   for (int32_t i = 0; i < n; ++i) { x[i] = pb->dof.doflocs[pb->dof.interior[i]]; y[i] = pb->dof.doflocs[pb->dof.N + pb->dof.interior[i]]; }
-  build_front_plan(pb->dof, pb->adj, x.data(), y.data(), opt, pb->plan);
+  build_front_plan(pb->dof, need_adj ? &pb->adj : nullptr, x.data(), y.data(), opt, pb->plan);
   pb->plan_opt = opt;
   pb->plan_ready = true;
-  pb->perm_pat_ready = false;
   pb->plan_serial++;  // device copies made from the previous plan are stale
   return true;
 }
@@ -351,7 +349,7 @@ int plfem_assemble(plfem_problem* pb, const plfem_material* mat) {
     pb->h_full_flags.resize((size_t)nnz);
     pb->d_full_vals.download(pb->h_full_vals.data(), pb->h_full_vals.size());
     pb->d_full_flags.download(pb->h_full_flags.data(), pb->h_full_flags.size());
-    PLFEM_CUDA(cudaStreamSynchronize(ctx->stream));
+    PLFEM_CUDA(stream_wait(ctx->stream));
     pb->last_mat = *mat;
     pb->assembled = true;
   });
@@ -450,7 +448,7 @@ int plfem_spmv_csr(plfem_ctx* ctx, int64_t rows, int64_t nnz, const int64_t* ind
     for (int i = 0; i < reps; ++i) launch_spmv_csr(ctx, rows, d_rp.p, d_ci.p, d_v.p, d_x.p, d_y.p);
     PLFEM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     d_y.download(y, rows);
-    PLFEM_CUDA(cudaStreamSynchronize(ctx->stream));
+    PLFEM_CUDA(stream_wait(ctx->stream));
     float t = 0;
     PLFEM_CUDA(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]));
     if (ms) *ms = t / reps;
@@ -504,12 +502,6 @@ static void solve_forest(plfem_ctx* ctx, int nb, plfem_problem* const* pbs, cons
           const double ta = now_ms();
           plfem_problem* pb = pbs[b];
           ensure_plan(pb, opts[b].leaf_nodes, opts[b].max_sn_nodes, opts[b].reuse_symbolic != 0);
-          if (!pb->perm_pat_ready) {
-            std::vector<int32_t> new_of(pb->plan.n);
-            for (int32_t r = 0; r < pb->plan.n; ++r) new_of[pb->plan.perm[r]] = r;
-            relabel_pattern(pb->adj, pb->plan.perm, new_of, pb->dof.interior, pb->dof.N, pb->perm_pat);
-            pb->perm_pat_ready = true;
-          }
           // core mask of the permuted interior nodes (solver_fem.py:200-203)
           const plfem_material* mat = &mats[b];
           const int64_t n = nint[b];
@@ -542,21 +534,31 @@ static void solve_forest(plfem_ctx* ctx, int nb, plfem_problem* const* pbs, cons
     if (err) std::rethrow_exception(err);
   }
   if (!have_work) {
-    std::vector<const FrontPlan*> plans(nb); std::vector<const Pattern*> pats(nb);
-    for (int b = 0; b < nb; ++b) { plans[b] = &pbs[b]->plan; pats[b] = &pbs[b]->perm_pat; }
+    std::vector<const FrontPlan*> plans(nb);
+    for (int b = 0; b < nb; ++b) plans[b] = &pbs[b]->plan;
     std::vector<int32_t> node_off;
     static const bool timing = std::getenv("PLFEM_TIMING") != nullptr;
     const double ta = now_ms();
     merge_front_plans(plans, W.plan, node_off, W.front_off);
-    merge_patterns(pats, W.pat, W.nnz_off);
     const double tb = now_ms();
     W.bd.set(ctx, node_off);
-    upload_pattern(ctx, W.pat, W.dpat);
+    {
+      // sparsity pattern in elimination order: built on the device from the resident element tables
+      std::vector<PatternSource> src(nb);
+      std::vector<int32_t> old_of_new((size_t)node_off[nb]);
+      for (int b = 0; b < nb; ++b) {
+        const plfem_problem* pb = pbs[b];
+        src[b] = {pb->d_n2e_ptr.p, pb->d_n2e.p, pb->d_edofs.p, pb->dof.N};
+        int32_t* o = old_of_new.data() + node_off[b];
+        for (int32_t r = 0; r < pb->plan.n; ++r) o[r] = pb->dof.interior[pb->plan.perm[r]];
+      }
+      build_device_pattern(ctx, nb, src.data(), node_off, old_of_new, W.dpat, W.nnz_off);
+    }
     const double tc = now_ms();
     build_dev_plan(ctx, W.plan, W.dplan);
     W.d_perm.upload(ctx, W.plan.perm);
     W.ready = true;
-    if (timing) fprintf(stderr, "[plfem] forest of %d: merge %.2f ms, pattern upload %.2f ms, device plan %.2f ms\n", nb, tb - ta, tc - tb, now_ms() - tc);
+    if (timing) fprintf(stderr, "[plfem] forest of %d: merge %.2f ms, device pattern %.2f ms, device plan %.2f ms\n", nb, tb - ta, tc - tb, now_ms() - tc);
   }
   const BatchDims& bd = W.bd;
   const int64_t n_tot = bd.noff[nb];
@@ -591,7 +593,7 @@ static void solve_forest(plfem_ctx* ctx, int nb, plfem_problem* const* pbs, cons
   PLFEM_CUDA(cudaEventRecord(ctx->ev[2], st));
   int32_t fstat[4] = {0, 0, 0, 0};
   W.dplan.status.download(fstat, 4);
-  PLFEM_CUDA(cudaStreamSynchronize(st));   // also covers the pageable sig / mask uploads above
+  PLFEM_CUDA(stream_wait(st));   // also covers the pageable sig / mask uploads above
   std::vector<DesignEig> des(nb);
   for (int b = 0; b < nb; ++b) { des[b].k = opts[b].k; des[b].sigma = opts[b].sigma; des[b].tol = opts[b].tol > 0 ? opts[b].tol : 1e-7; }
   if (fstat[0]) {
@@ -613,7 +615,7 @@ static void solve_forest(plfem_ctx* ctx, int nb, plfem_problem* const* pbs, cons
       for (int64_t r = 0; r < n; ++r) { const int32_t ip = pbs[b]->plan.perm[r]; v0[2 * (r0 + r)] = opts[b].v0[ip]; v0[2 * (r0 + r) + 1] = opts[b].v0[n + ip]; }
     }
     d_v0.upload(ctx, v0);
-    PLFEM_CUDA(cudaStreamSynchronize(st));
+    PLFEM_CUDA(stream_wait(st));
     v0p = d_v0.p;
   }
   DevBuf<double> X;
@@ -642,7 +644,7 @@ static void solve_forest(plfem_ctx* ctx, int nb, plfem_problem* const* pbs, cons
   }
   PLFEM_CUDA(cudaEventRecord(ctx->ev[3], st));
   W.dplan.status.download(fstat, 4);
-  PLFEM_CUDA(cudaStreamSynchronize(st));
+  PLFEM_CUDA(stream_wait(st));
   if (fstat[1]) throw StatusError(PLFEM_ERR_INTERNAL, "operator kernel: a dependency wait timed out");
 
   // -- per-mode reductions + eigenvectors in reference ordering, design by design ---------------------------
@@ -662,7 +664,7 @@ static void solve_forest(plfem_ctx* ctx, int nb, plfem_problem* const* pbs, cons
     if (evecs[b]) d_ev[b].download(evecs[b], (size_t)k * 2 * n);
   }
   PLFEM_CUDA(cudaEventRecord(ctx->ev[4], st));
-  PLFEM_CUDA(cudaStreamSynchronize(st));
+  PLFEM_CUDA(stream_wait(st));
   const double t2 = now_ms();
 
   float ms_asm = 0, ms_fac = 0, ms_lan = 0, ms_met = 0;
@@ -761,7 +763,7 @@ static void profile_work(plfem_ctx* ctx, SolveWork& W, int repeat, double* out_m
       PLFEM_CUDA(cudaEventRecord(ctx->ev[5], st));
       body();
       PLFEM_CUDA(cudaEventRecord(ctx->ev[6], st));
-      PLFEM_CUDA(cudaStreamSynchronize(st));
+      PLFEM_CUDA(stream_wait(st));
       float ms = 0; PLFEM_CUDA(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]));
       tot += ms;
     }
@@ -853,7 +855,7 @@ int plfem_debug_solve(plfem_problem* pb, double sigma, const double* b, double* 
       run_operator(ctx, W.dpat, W.dplan, W.d_vals.p, W.d_sigma.p, db.p, dx.p, dt.p, dd.p, refine, ctx->coop_ctas_per_sm);
     }
     dx.download(hx.data(), m);
-    PLFEM_CUDA(cudaStreamSynchronize(ctx->stream));
+    PLFEM_CUDA(stream_wait(ctx->stream));
     for (int64_t r = 0; r < n; ++r) { const int32_t ip = pb->plan.perm[r]; x[ip] = hx[2 * r]; x[n + ip] = hx[2 * r + 1]; }
   });
 }

@@ -13,6 +13,8 @@
 // Arithmetic follows the oracle operation for operation (no FMA contraction: every product and
 // sum below is an explicit round-to-nearest intrinsic), so an element-level value is exactly zero
 // here iff it is exactly zero there — that decides the CSR structure scikit-fem/SciPy produce.
+#include <cub/device/device_scan.cuh>
+
 #include "common.h"
 
 namespace plfem {
@@ -117,6 +119,58 @@ __global__ void expand_rows_kernel(const int32_t* __restrict__ rowptr, int32_t n
   const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   for (int32_t z = rowptr[r]; z < rowptr[r + 1]; ++z) rowidx[z] = r;
+}
+
+
+// ---- sparsity pattern of the interior nodes in elimination order, built on the device ---------------------------
+// Row R (a node in elimination order) holds the nodes that share an element with it — the union over the elements
+// around its DOF of their 6 DOFs, dropped when eliminated by the Dirichlet condition, sorted ascending.  One thread per
+// row keeps the row in a small sorted list (a P2 row of a triangulation has 3*valence + 1 entries for a vertex, 9 for an
+// edge node); COUNT pass -> inclusive scan -> FILL pass.  Identical to the host `build_pattern` (symbolic.cpp), which the
+// export path still uses; here it saves ~5 ms of host time per design, which is what a forest pool is short of.
+constexpr int PATTERN_MAXROW = 128;
+
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+pattern_rows_kernel(int32_t r0, int32_t n, const int32_t* __restrict__ old_of_new, const int32_t* __restrict__ n2e_ptr,
+                    const int32_t* __restrict__ n2e, const int32_t* __restrict__ edofs, const int32_t* __restrict__ new_of_dof,
+                    int32_t* __restrict__ rowptr, int32_t* __restrict__ col, int32_t* __restrict__ rowidx, int32_t* __restrict__ err) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int32_t R = r0 + r;
+  const int32_t o = old_of_new[R];
+  int32_t list[PATTERN_MAXROW];
+  int len = 0;
+  for (int32_t q = n2e_ptr[o]; q < n2e_ptr[o + 1]; ++q) {
+    const int32_t* ed = edofs + 6 * (int64_t)n2e[q];
+    for (int k = 0; k < 6; ++k) {
+      const int32_t c = new_of_dof[ed[k]];
+      if (c < 0) continue;
+      int i = len;
+      while (i > 0 && list[i - 1] > c) --i;
+      if (i > 0 && list[i - 1] == c) continue;
+      if (len == PATTERN_MAXROW) { atomicExch(err, 1); continue; }
+      for (int j = len; j > i; --j) list[j] = list[j - 1];
+      list[i] = c;
+      ++len;
+    }
+  }
+  if (!FILL) {
+    rowptr[R + 1] = len;
+  } else {
+    const int32_t z0 = rowptr[R];
+    for (int i = 0; i < len; ++i) { col[z0 + i] = list[i]; rowidx[z0 + i] = R; }
+  }
+}
+
+__global__ void scatter_new_of_dof_kernel(int32_t r0, int32_t n, const int32_t* __restrict__ old_of_new, int32_t* __restrict__ new_of_dof) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) new_of_dof[old_of_new[r0 + r]] = r0 + r;
+}
+
+__global__ void gather_offsets_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ node_off, int nb1, int32_t* __restrict__ out) {
+  const int i = threadIdx.x;
+  if (i < nb1) out[i] = rowptr[node_off[i]];
 }
 
 // ---- K1b/K2 fused: one thread per structural non-zero ---------------------------------------------------
@@ -248,6 +302,63 @@ void launch_expand_rows(plfem_ctx* ctx, const DevPattern& pat) {
   expand_rows_kernel<<<(pat.n + bs - 1) / bs, bs, 0, ctx->stream>>>(pat.rowptr.p, pat.n, pat.rowidx.p);
   PLFEM_CUDA(cudaGetLastError());
   ctx->launches++;
+}
+
+void build_device_pattern(plfem_ctx* ctx, int nb, const PatternSource* src, const std::vector<int32_t>& node_off,
+                          const std::vector<int32_t>& old_of_new, DevPattern& D, std::vector<int64_t>& nnz_off) {
+  cudaStream_t st = ctx->stream;
+  const int32_t n_tot = node_off[nb];
+  D.n = n_tot;
+  D.old_of_new.upload(ctx, old_of_new);
+  D.rowptr.alloc(ctx, (size_t)n_tot + 1);
+  int64_t dof_tot = 0;
+  std::vector<int64_t> dof_off(nb + 1, 0);
+  for (int b = 0; b < nb; ++b) dof_off[b + 1] = dof_off[b] + src[b].N;
+  dof_tot = dof_off[nb];
+  DevBuf<int32_t> new_of_dof, d_noff, d_zoff, d_err;
+  new_of_dof.alloc(ctx, (size_t)dof_tot);
+  PLFEM_CUDA(cudaMemsetAsync(new_of_dof.p, 0xFF, (size_t)dof_tot * sizeof(int32_t), st));      // -1: not an interior node
+  PLFEM_CUDA(cudaMemsetAsync(D.rowptr.p, 0, sizeof(int32_t), st));
+  d_err.alloc(ctx, 1);
+  PLFEM_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int32_t), st));
+  d_noff.upload(ctx, node_off);
+  d_zoff.alloc(ctx, (size_t)nb + 1);
+  const int bs = 128;
+  for (int b = 0; b < nb; ++b) {
+    const int32_t r0 = node_off[b], n = node_off[b + 1] - node_off[b];
+    if (n == 0) continue;
+    scatter_new_of_dof_kernel<<<(n + 255) / 256, 256, 0, st>>>(r0, n, D.old_of_new.p, new_of_dof.p + dof_off[b]);
+    pattern_rows_kernel<false><<<(n + bs - 1) / bs, bs, 0, st>>>(r0, n, D.old_of_new.p, src[b].n2e_ptr, src[b].n2e, src[b].edofs,
+                                                                new_of_dof.p + dof_off[b], D.rowptr.p, nullptr, nullptr, d_err.p);
+    ctx->launches += 2;
+  }
+  PLFEM_CUDA(cudaGetLastError());
+  size_t tmp_bytes = 0;
+  PLFEM_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, D.rowptr.p, D.rowptr.p, n_tot + 1, st));
+  DevBuf<uint8_t> tmp;
+  tmp.alloc(ctx, std::max<size_t>(tmp_bytes, 1));
+  PLFEM_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tmp_bytes, D.rowptr.p, D.rowptr.p, n_tot + 1, st));
+  gather_offsets_kernel<<<1, 32 * ((nb + 1 + 31) / 32), 0, st>>>(D.rowptr.p, d_noff.p, nb + 1, d_zoff.p);
+  ctx->launches += 2;
+  std::vector<int32_t> zoff(nb + 1), err(1);
+  d_zoff.download(zoff.data(), zoff.size());
+  d_err.download(err.data(), 1);
+  PLFEM_CUDA(stream_wait(st));
+  if (err[0]) throw StatusError(PLFEM_ERR_INVALID, "a mesh node has more than " + std::to_string(PATTERN_MAXROW) + " neighbours");
+  nnz_off.assign(nb + 1, 0);
+  for (int b = 0; b <= nb; ++b) nnz_off[b] = zoff[b];
+  D.nnz = nnz_off[nb];
+  D.col.alloc(ctx, std::max<size_t>((size_t)D.nnz, 1));
+  D.rowidx.alloc(ctx, std::max<size_t>((size_t)D.nnz, 1));
+  for (int b = 0; b < nb; ++b) {
+    const int32_t r0 = node_off[b], n = node_off[b + 1] - node_off[b];
+    if (n == 0) continue;
+    pattern_rows_kernel<true><<<(n + bs - 1) / bs, bs, 0, st>>>(r0, n, D.old_of_new.p, src[b].n2e_ptr, src[b].n2e, src[b].edofs,
+                                                               new_of_dof.p + dof_off[b], D.rowptr.p, D.col.p, D.rowidx.p, d_err.p);
+    ctx->launches++;
+  }
+  PLFEM_CUDA(cudaGetLastError());
+  // the scratch buffers return to the context's arena here; it serves this stream only, so reuse is stream-ordered
 }
 
 // one design's slice of a (possibly concatenated) pattern: nnz entries starting at rowidx/col, values written to

@@ -2,9 +2,13 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <time.h>
+
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -32,6 +36,26 @@ struct StatusError : std::runtime_error {
       throw plfem::CudaError(std::string(#call) + " failed: " + cudaGetErrorString(e_) + " at " +      \
                              __FILE__ + ":" + std::to_string(__LINE__));                              \
   } while (0)
+
+// Wait for a stream without burning a core: spin for a few tens of microseconds (most waits in the Lanczos loop are that
+// short), then poll between short naps.  A forest pool keeps several host threads per GPU waiting on their streams while
+// other threads run the symbolic analysis of the next forests, and under torchrun the ranks share the node's cores:
+// cudaStreamSynchronize's default busy-wait costs a core per waiting thread (measured: 6.6 ms of CPU per solve), and the
+// driver's interrupt-based blocking wait (cudaDeviceScheduleBlockingSync) costs ~0.3 ms per wake-up (measured: +9 ms per
+// solo solve).  PLFEM_SYNC=spin restores the plain busy-wait.
+inline cudaError_t stream_wait(cudaStream_t st) {
+  static const bool spin = [] { const char* e = std::getenv("PLFEM_SYNC"); return e && e[0] == 's'; }();
+  if (spin) return cudaStreamSynchronize(st);
+  using clk = std::chrono::steady_clock;
+  const auto t0 = clk::now();
+  for (;;) {
+    const cudaError_t e = cudaStreamQuery(st);
+    if (e != cudaErrorNotReady) return e;
+    if (clk::now() - t0 < std::chrono::microseconds(40)) continue;
+    timespec ts{0, 30000};
+    nanosleep(&ts, nullptr);
+  }
+}
 
 // Size-class caching allocator: cudaMalloc/cudaFree cost more than a whole assembly pass, and a
 // sweep creates and drops one problem per design.
@@ -97,7 +121,9 @@ struct DevBuf {
     if (n) PLFEM_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), ctx->stream));
   }
   void download(T* h, size_t count) const {
-    if (count) PLFEM_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!count) return;
+    PLFEM_CUDA(stream_wait(ctx->stream));     // a copy into pageable memory waits for the stream inside the driver: wait politely first
+    PLFEM_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
   }
 };
 
@@ -124,6 +150,12 @@ void launch_element_setup(plfem_ctx* ctx, const double* d_p, const int32_t* d_ed
                           const plfem_material& mat, const double* d_cores /* (nc,3): cx cy r */,
                           const double* d_eps_at_quad, double* d_elem);
 void launch_expand_rows(plfem_ctx* ctx, const DevPattern& pat);
+// device tables of one design's mesh (element DOFs, node -> elements) and its DOF count
+struct PatternSource { const int32_t* n2e_ptr; const int32_t* n2e; const int32_t* edofs; int64_t N; };
+// Pattern of a forest built on the device: rows node_off[b]..node_off[b+1] are design b's interior nodes in elimination
+// order, old_of_new[R] the DOF id (in its own mesh) of row R; columns are global row ids.  Fills D and nnz_off[nb+1].
+void build_device_pattern(plfem_ctx* ctx, int nb, const PatternSource* src, const std::vector<int32_t>& node_off,
+                          const std::vector<int32_t>& old_of_new, DevPattern& D, std::vector<int64_t>& nnz_off);
 void launch_assemble(plfem_ctx* ctx, const DevPattern& pat, const int32_t* d_n2e_ptr, const int32_t* d_n2e,
                      const int32_t* d_edofs, const double* d_elem, double k0sq, double alpha, bool export_mode,
                      double* d_vals, uint32_t* d_flags);

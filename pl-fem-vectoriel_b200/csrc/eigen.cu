@@ -680,7 +680,7 @@ void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const do
     PLFEM_CUDA(cudaGetLastError());
     alpha.download(h_alpha.data(), ncv);
     beta.download(h_beta.data(), ncv);
-    PLFEM_CUDA(cudaStreamSynchronize(st));
+    PLFEM_CUDA(stream_wait(st));
     // projected matrix
     T.assign((size_t)ncv * ncv, 0.0);
     for (int i = 0; i < p; ++i) { T[(size_t)i * ncv + i] = theta_keep[i]; T[(size_t)p * ncv + i] = T[(size_t)i * ncv + p] = b_keep[i]; }
@@ -716,7 +716,7 @@ void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const do
       X.alloc(ctx, (size_t)m * k);
       rotate_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(V[cur].p, ld, ncv, Sdev.p, k, m, X.p, m);
       ctx->launches++;
-      PLFEM_CUDA(cudaStreamSynchronize(st));   // S is a local host buffer
+      PLFEM_CUDA(stream_wait(st));   // S is a local host buffer
       if (!done) throw StatusError(PLFEM_ERR_NO_CONVERGENCE, "Lanczos: " + std::to_string(nconv) + " of " + std::to_string(k) + " eigenpairs converged after " + std::to_string(res.n_restart) + " restarts");
       return;
     }
@@ -738,7 +738,7 @@ void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const do
     PLFEM_CUDA(cudaMemcpyAsync(V[nxt].p + (int64_t)keep * ld, V[cur].p + (int64_t)ncv * ld, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
     PLFEM_CUDA(cudaMemcpyAsync(BV[nxt].p + (int64_t)keep * ld, BV[cur].p + (int64_t)ncv * ld, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
     ctx->launches += 2;
-    PLFEM_CUDA(cudaStreamSynchronize(st));     // S is a local host buffer
+    PLFEM_CUDA(stream_wait(st));     // S is a local host buffer
     cur = nxt; p = keep;
     res.n_restart++;
   }
@@ -872,7 +872,7 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
     ctx->launches += 2;
     std::vector<double> hn((size_t)B * RSPLIT * 2);
     nrm.download(hn.data(), hn.size());
-    PLFEM_CUDA(cudaStreamSynchronize(st));
+    PLFEM_CUDA(stream_wait(st));
     rsteps = 1;
     for (int b = 0; b < B; ++b) {
       double nr = 0.0, nbv = 0.0;
@@ -950,7 +950,7 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
     Hs.download(Hh.data(), Hh.size());
     Lall.download(Lh.data(), Lh.size());
     cstat.download(cs.data(), B);
-    PLFEM_CUDA(cudaStreamSynchronize(st));
+    PLFEM_CUDA(stream_wait(st));
     const bool last_chance = full && res.n_restart >= maxiter;
     for_each_design(B, [&](int b) {
       Host& h = hs[b]; DesignEig& de = des[b];
@@ -1034,7 +1034,7 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
       const int64_t mb = bd.moff[b + 1] - bd.moff[b];
       rotate_kernel<<<(unsigned)((mb + 127) / 128), 128, 0, st>>>(V[cur].p + bd.moff[b], ld, c, Sdev.p, k, mb, X.p + bd.moff[b], m);
       ctx->launches++;
-      PLFEM_CUDA(cudaStreamSynchronize(st));   // Sdev is reused by the next design
+      PLFEM_CUDA(stream_wait(st));   // Sdev is reused by the next design
     }
     ndone = 0;
     for (const Host& h : hs) ndone += h.done;
@@ -1071,7 +1071,7 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
       rotate_forest_kernel<<<grot, 128, 0, st>>>(V[cur].p, ld, ncvp, Sdev.p, sst, q, moff, V[nxt].p, ld);
       rotate_forest_kernel<<<grot, 128, 0, st>>>(BV[cur].p, ld, ncvp, Sdev.p, sst, q, moff, BV[nxt].p, ld);
       ctx->launches += 2;
-      PLFEM_CUDA(cudaStreamSynchronize(st));   // S is a local host buffer
+      PLFEM_CUDA(stream_wait(st));   // S is a local host buffer
     }
     PLFEM_CUDA(cudaMemcpyAsync(V[nxt].p + (int64_t)q * ld, V[cur].p + (int64_t)ncvp * ld, (size_t)m * P * sizeof(double), cudaMemcpyDeviceToDevice, st));
     PLFEM_CUDA(cudaMemcpyAsync(BV[nxt].p + (int64_t)q * ld, BV[cur].p + (int64_t)ncvp * ld, (size_t)m * P * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -1100,7 +1100,7 @@ void run_mode_metrics(plfem_ctx* ctx, const DevPattern& pat, const double* d_val
     ctx->launches++;
   }
   PLFEM_CUDA(cudaGetLastError());
-  PLFEM_CUDA(cudaStreamSynchronize(st));   // lambda upload source and the DevBufs above go out of scope
+  PLFEM_CUDA(stream_wait(st));   // lambda upload source and the DevBufs above go out of scope
 }
 
 }  // namespace plfem

@@ -1281,7 +1281,7 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
   D.pool.alloc(ctx, (size_t)P.foff[P.nfronts]);
   D.status.alloc(ctx, 4);
   // the host vectors above are pageable: make sure the copies are done before they go out of scope
-  PLFEM_CUDA(cudaStreamSynchronize(ctx->stream));
+  PLFEM_CUDA(stream_wait(ctx->stream));
 }
 
 void launch_front_load(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, const double* d_sigma_node) {

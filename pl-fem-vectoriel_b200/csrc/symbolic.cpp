@@ -198,33 +198,6 @@ void build_pattern(const DofTables& d, const std::vector<int32_t>& new_of_old, i
     if (!bufs[t].empty()) std::copy(bufs[t].begin(), bufs[t].end(), out.col.begin() + out.rowptr[lo[t]]);
 }
 
-// Same pattern in a new numbering of the same node set: new row r is old row old_of[r]; columns are
-// relabelled with new_of and re-sorted.  `full_ids[old]` is the DOF id stored in old_of_new.
-void relabel_pattern(const Pattern& src, const std::vector<int32_t>& old_of, const std::vector<int32_t>& new_of,
-                     const std::vector<int32_t>& full_ids, int64_t N_full, Pattern& out) {
-  const int32_t n = src.n;
-  out.n = n;
-  out.old_of_new.resize(n);
-  out.new_of_old.assign(N_full, -1);
-  out.rowptr.assign(n + 1, 0);
-  for (int32_t r = 0; r < n; ++r) {
-    const int32_t o = old_of[r];
-    out.old_of_new[r] = full_ids[o];
-    out.new_of_old[full_ids[o]] = r;
-    out.rowptr[r + 1] = out.rowptr[r] + (src.rowptr[o + 1] - src.rowptr[o]);
-  }
-  out.col.resize(out.rowptr[n]);
-  parallel_for(n, 2048, [&](int64_t b, int64_t e) {
-    for (int64_t r = b; r < e; ++r) {
-      const int32_t o = old_of[r];
-      int32_t* dst = out.col.data() + out.rowptr[r];
-      const int32_t len = src.rowptr[o + 1] - src.rowptr[o];
-      for (int32_t q = 0; q < len; ++q) dst[q] = new_of[src.col[src.rowptr[o] + q]];
-      std::sort(dst, dst + len);
-    }
-  });
-}
-
 // ------------------------------------------------------------------------------------------------
 // Nested dissection + front plan
 // ------------------------------------------------------------------------------------------------
@@ -277,15 +250,16 @@ struct Dissector {
   const double* y;
   const SymbolicOptions& opt;
   std::vector<int32_t> side;   // per node: stamp of the subset/half it currently belongs to
-  std::vector<int32_t> rank;   // per node: position in the direction list being examined
+  struct Rk { int32_t r[4]; };
+  std::vector<Rk> rank4;       // per node: position in each direction list of the subset being examined
   std::vector<uint8_t> insep;  // per node: chosen as separator in the current call
   std::atomic<int32_t> stamp{0};
   std::vector<int32_t> lists[ND];  // the node set of the current call, sorted along each direction
   bool split_chains = true;        // cut separators into chains of <= max_sn_nodes supernodes here (false: the caller does)
-  struct Scratch { std::vector<int32_t> tmp, dl, dr; };
+  struct Scratch { std::vector<int32_t> tmp, dl[ND], dr[ND]; };
 
   Dissector(const Pattern& a, const double* x_, const double* y_, const SymbolicOptions& o)
-      : adj(a), x(x_), y(y_), opt(o), side(a.n, -1), rank(a.n, 0), insep(a.n, 0) {
+      : adj(a), x(x_), y(y_), opt(o), side(a.n, -1), rank4(a.n, Rk{{0, 0, 0, 0}}), insep(a.n, 0) {
     const int32_t n = a.n;
     auto one = [&](int d) {
       std::vector<double> key(n);
@@ -328,42 +302,43 @@ struct Dissector {
     const int32_t h0 = std::max<int32_t>(1, (int32_t)(0.3 * n)), h1 = std::min<int32_t>(n - 1, (int32_t)(0.7 * n));
     struct Cand { double cost = 1e300; int32_t h = 0; bool left = true; };
     Cand cand[ND];
-    auto eval_dir = [&](int d, std::vector<int32_t>& rk, std::vector<int32_t>& dl, std::vector<int32_t>& dr) {
-      const int32_t* Ld = lists[d].data() + off;
-      for (int32_t r = 0; r < n; ++r) rk[Ld[r]] = r;
-      dl.assign(n + 2, 0); dr.assign(n + 2, 0);
-      for (int32_t r = 0; r < n; ++r) {
-        const int32_t v = Ld[r];
-        int32_t hi = r, lo = r;
+    {
+      // ranks of every node along every direction, then ONE pass over the adjacency: the extreme neighbour ranks along
+      // all directions at once
+      for (int d = 0; d < ndir; ++d) {
+        const int32_t* Ld = lists[d].data() + off;
+        for (int32_t r = 0; r < n; ++r) rank4[Ld[r]].r[d] = r;
+        sc.dl[d].assign(n + 2, 0); sc.dr[d].assign(n + 2, 0);
+      }
+      for (int32_t i = 0; i < n; ++i) {
+        const int32_t v = L0[i];
+        const Rk rv = rank4[v];
+        int32_t hi[ND], lo[ND];
+        for (int d = 0; d < ND; ++d) hi[d] = lo[d] = rv.r[d];
         for (int32_t q = adj.rowptr[v]; q < adj.rowptr[v + 1]; ++q) {
           const int32_t w = adj.col[q];
           if (side[w] != cur) continue;
-          const int32_t rw = rk[w];
-          hi = std::max(hi, rw); lo = std::min(lo, rw);
+          const Rk rw = rank4[w];
+          for (int d = 0; d < ND; ++d) { hi[d] = std::max(hi[d], rw.r[d]); lo[d] = std::min(lo[d], rw.r[d]); }
         }
-        dl[r + 1]++; dl[hi + 1]--;   // left-boundary member for h in (r, hi]
-        dr[lo + 1]++; dr[r + 1]--;   // right-boundary member for h in (lo, r]
+        for (int d = 0; d < ndir; ++d) {
+          sc.dl[d][rv.r[d] + 1]++; sc.dl[d][hi[d] + 1]--;   // left-boundary member for h in (r, hi]
+          sc.dr[d][lo[d] + 1]++; sc.dr[d][rv.r[d] + 1]--;   // right-boundary member for h in (lo, r]
+        }
       }
-      int32_t cl = 0, cr = 0;
-      Cand c;
-      for (int32_t h = 1; h <= h1; ++h) {
-        cl += dl[h]; cr += dr[h];
-        if (h < h0) continue;
-        const double imb = std::fabs(2.0 * h / n - 1.0);
-        const double cost = (std::min(cl, cr) + 1.0) * (1.0 + 1.5 * imb);
-        if (cost < c.cost) { c.cost = cost; c.h = h; c.left = cl <= cr; }
+      for (int d = 0; d < ndir; ++d) {
+        const int32_t* dl = sc.dl[d].data(); const int32_t* dr = sc.dr[d].data();
+        int32_t cl = 0, cr = 0;
+        Cand c;
+        for (int32_t h = 1; h <= h1; ++h) {
+          cl += dl[h]; cr += dr[h];
+          if (h < h0) continue;
+          const double imb = std::fabs(2.0 * h / n - 1.0);
+          const double cost = (std::min(cl, cr) + 1.0) * (1.0 + 1.5 * imb);
+          if (cost < c.cost) { c.cost = cost; c.h = h; c.left = cl <= cr; }
+        }
+        cand[d] = c;
       }
-      cand[d] = c;
-    };
-    if (par_budget >= ndir && ndir > 1 && n >= 4096) {
-      // top of the tree: few, large calls — evaluate the directions concurrently (private rank arrays)
-      std::vector<std::thread> th;
-      std::vector<std::vector<int32_t>> rks(ndir, std::vector<int32_t>()), dls(ndir), drs(ndir);
-      for (int d = 1; d < ndir; ++d) th.emplace_back([&, d] { rks[d].resize(adj.n); eval_dir(d, rks[d], dls[d], drs[d]); });
-      eval_dir(0, rank, sc.dl, sc.dr);
-      for (auto& t : th) t.join();
-    } else {
-      for (int d = 0; d < ndir; ++d) eval_dir(d, rank, sc.dl, sc.dr);
     }
     for (int d = 0; d < ndir; ++d)
       if (cand[d].cost < best_cost) { best_cost = cand[d].cost; best_dir = d; best_h = cand[d].h; best_left = cand[d].left; }
@@ -446,12 +421,15 @@ namespace {
 // a mesh edge are adjacent, so their tree nodes lie on one root path), which keeps every pair of P2 nodes that share an
 // element on a common root path — the tree stays a valid elimination tree of the P2 graph.  Edge nodes without an
 // interior endpoint (chords between boundary vertices) are eliminated last, in a tree node above all roots.
-void dissect_vertex_graph(const DofTables& d, const Pattern& adj, const double* x, const double* y, const SymbolicOptions& opt,
-                          Forest& out, std::vector<int32_t>& out_roots) {
+void dissect_vertex_graph(const DofTables& d, const std::vector<int32_t>& interior, const double* x, const double* y,
+                          const SymbolicOptions& opt, Forest& out, std::vector<int32_t>& out_roots) {
   const int64_t V = d.V, N = d.N;
-  const int32_t n = adj.n;                       // interior P2 nodes; adj.old_of_new[i] = DOF id of interior index i
+  const int32_t n = (int32_t)interior.size();    // interior P2 nodes; interior[i] = DOF id of interior index i
+  static const bool timing = std::getenv("PLFEM_TIMING") != nullptr;
+  auto clk = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = clk();
   std::vector<int32_t> int_of(N, -1);
-  for (int32_t i = 0; i < n; ++i) int_of[adj.old_of_new[i]] = i;
+  for (int32_t i = 0; i < n; ++i) int_of[interior[i]] = i;
   // interior vertices and their graph (two vertices are adjacent iff they share an element)
   std::vector<int32_t> vid(V, -1), vdof;
   for (int64_t v = 0; v < V; ++v) if (int_of[v] >= 0) { vid[v] = (int32_t)vdof.size(); vdof.push_back((int32_t)v); }
@@ -464,7 +442,6 @@ void dissect_vertex_graph(const DofTables& d, const Pattern& adj, const double* 
     vadj.col.reserve((size_t)nv * 8);
     for (int32_t a = 0; a < nv; ++a) {
       const int32_t va = vdof[a];
-      const size_t b0 = vadj.col.size();
       stamp[a] = a; vadj.col.push_back(a);
       for (int32_t q = d.n2e_ptr[va]; q < d.n2e_ptr[va + 1]; ++q) {
         const int32_t* ed = &d.edofs[6 * (int64_t)d.n2e[q]];
@@ -473,8 +450,7 @@ void dissect_vertex_graph(const DofTables& d, const Pattern& adj, const double* 
           if (c >= 0 && stamp[c] != a) { stamp[c] = a; vadj.col.push_back(c); }
         }
       }
-      std::sort(vadj.col.begin() + b0, vadj.col.end());
-      vadj.rowptr[a + 1] = (int32_t)vadj.col.size();
+      vadj.rowptr[a + 1] = (int32_t)vadj.col.size();     // (rows stay unsorted: the dissection only asks "any/extreme neighbour")
     }
   }
   std::vector<double> vx(nv), vy(nv);
@@ -483,12 +459,16 @@ void dissect_vertex_graph(const DofTables& d, const Pattern& adj, const double* 
   vopt.leaf_nodes = std::max(1, opt.leaf_nodes / 4);           // a vertex brings ~3 edge nodes along
   vopt.search_min_nodes = std::max(1, opt.search_min_nodes / 4);
   Forest vf; std::vector<int32_t> vroots;
+  const double t1 = clk();
+  double t1b;
   {
     Dissector D(vadj, vx.data(), vy.data(), vopt);
+    t1b = clk();
     D.split_chains = false;
     Dissector::Scratch sc;
     D.dissect(0, nv, vf, vroots, sc, host_threads());
   }
+  const double t2 = clk();
   // depth of every tree node, tree node of every vertex
   const int32_t nt = (int32_t)vf.nodes.size();
   std::vector<int32_t> depth(nt, 0), tn_of(nv, -1);
@@ -561,6 +541,7 @@ void dissect_vertex_graph(const DofTables& d, const Pattern& adj, const double* 
     head[t] = prev;
   }
   for (int32_t r : vroots) out_roots.push_back(head[r]);
+  if (timing) fprintf(stderr, "[plfem] vertex dissection: graph %.2f ms, presort %.2f ms, dissect %.2f ms, lift %.2f ms (nv=%d)\n", t1 - t0, t1b - t1, t2 - t1b, clk() - t2, nv);
   if (!orphans.empty()) {
     TreeNode tn; tn.own = orphans; tn.children = out_roots;
     // keep the supernode limit: chain if needed
@@ -577,24 +558,30 @@ void dissect_vertex_graph(const DofTables& d, const Pattern& adj, const double* 
 
 }  // namespace
 
-void build_front_plan(const DofTables& dof, const Pattern& adj, const double* x, const double* y, const SymbolicOptions& opt, FrontPlan& P) {
-  const int32_t n = adj.n;
+bool front_plan_needs_adjacency(const DofTables& dof) {
+  static const bool p2_graph = [] { const char* e = std::getenv("PLFEM_DISSECT_P2"); return e && e[0] == '1'; }();
+  return p2_graph || dof.V == 0;
+}
+
+void build_front_plan(const DofTables& dof, const Pattern* adj_p, const double* x, const double* y, const SymbolicOptions& opt, FrontPlan& P) {
+  const int32_t n = (int32_t)dof.interior.size();
   P = FrontPlan();
   P.n = n;
   static const bool timing = std::getenv("PLFEM_TIMING") != nullptr;
-  static const bool p2_graph = [] { const char* e = std::getenv("PLFEM_DISSECT_P2"); return e && e[0] == '1'; }();
+  const bool p2_graph = front_plan_needs_adjacency(dof);
+  if (p2_graph && !adj_p) throw std::runtime_error("front plan: the P2-graph dissection needs the adjacency pattern");
   auto clk = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double tA = clk();
   double tB = tA;
   std::vector<int32_t> roots;
   Forest forest;
-  if (p2_graph || dof.V == 0) {       // dissect the P2 node graph itself (the first implementation; kept for comparison)
-    Dissector D(adj, x, y, opt);
+  if (p2_graph) {       // dissect the P2 node graph itself (the first implementation; kept for comparison)
+    Dissector D(*adj_p, x, y, opt);
     tB = clk();
     Dissector::Scratch sc;
     D.dissect(0, n, forest, roots, sc, host_threads());
   } else {
-    dissect_vertex_graph(dof, adj, x, y, opt, forest, roots);
+    dissect_vertex_graph(dof, dof.interior, x, y, opt, forest, roots);
   }
   const double tC = clk();
 
@@ -634,18 +621,35 @@ void build_front_plan(const DofTables& dof, const Pattern& adj, const double* x,
     for (int32_t f = 0; f < nf; ++f) if (P.parent[f] >= 0) P.child[fill[P.parent[f]]++] = f;
   }
 
-  // update sets, bottom-up (post-order guarantees children first)
+  // update sets, bottom-up (post-order guarantees children first).  Neighbours of a node = the nodes of its elements
+  // (read from the element tables: the node adjacency pattern is never built on this path).
   P.sptr.assign(nf + 1, 0);
   P.strct.clear(); P.strct.reserve((size_t)n * 8);
   std::vector<int32_t> mark(n, -1);
+  std::vector<int32_t> new_of_dof;
+  if (!adj_p) {
+    new_of_dof.assign(dof.N, -1);
+    for (int32_t r = 0; r < n; ++r) new_of_dof[dof.interior[P.perm[r]]] = r;
+  }
   for (int32_t f = 0; f < nf; ++f) {
     const int32_t last = P.first[f] + P.s[f] - 1;
     const size_t b = P.strct.size();
     for (int32_t r = P.first[f]; r <= last; ++r) {
       const int32_t v = P.perm[r];
-      for (int32_t q = adj.rowptr[v]; q < adj.rowptr[v + 1]; ++q) {
-        const int32_t c = new_of[adj.col[q]];
-        if (c > last && mark[c] != f) { mark[c] = f; P.strct.push_back(c); }
+      if (adj_p) {
+        for (int32_t q = adj_p->rowptr[v]; q < adj_p->rowptr[v + 1]; ++q) {
+          const int32_t c = new_of[adj_p->col[q]];
+          if (c > last && mark[c] != f) { mark[c] = f; P.strct.push_back(c); }
+        }
+      } else {
+        const int32_t o = dof.interior[v];
+        for (int32_t q = dof.n2e_ptr[o]; q < dof.n2e_ptr[o + 1]; ++q) {
+          const int32_t* ed = &dof.edofs[6 * (int64_t)dof.n2e[q]];
+          for (int k = 0; k < 6; ++k) {
+            const int32_t c = new_of_dof[ed[k]];
+            if (c > last && mark[c] != f) { mark[c] = f; P.strct.push_back(c); }
+          }
+        }
       }
     }
     for (int32_t q = P.cptr[f]; q < P.cptr[f + 1]; ++q) {
@@ -753,27 +757,6 @@ void merge_front_plans(const std::vector<const FrontPlan*>& parts, FrontPlan& M,
   M.lfront.resize(M.nfronts);
   std::vector<int32_t> fill(M.lptr.begin(), M.lptr.end() - 1);
   for (int32_t f = 0; f < M.nfronts; ++f) M.lfront[fill[M.level[f]]++] = f;
-}
-
-void merge_patterns(const std::vector<const Pattern*>& parts, Pattern& M, std::vector<int64_t>& nnz_off) {
-  const int nb = (int)parts.size();
-  M = Pattern();
-  nnz_off.assign(nb + 1, 0);
-  int64_t n_tot = 0;
-  for (int b = 0; b < nb; ++b) { n_tot += parts[b]->n; nnz_off[b + 1] = nnz_off[b] + (int64_t)parts[b]->col.size(); }
-  if (nnz_off[nb] >= (int64_t(1) << 31) || n_tot >= (int64_t(1) << 30)) throw std::runtime_error("batch too large for 32-bit pattern indices");
-  M.n = (int32_t)n_tot;
-  M.rowptr.assign(1, 0); M.rowptr.reserve(n_tot + 1);
-  M.col.reserve(nnz_off[nb]); M.old_of_new.reserve(n_tot);
-  int32_t no = 0;
-  for (int b = 0; b < nb; ++b) {
-    const Pattern& P = *parts[b];
-    const int32_t zo = (int32_t)nnz_off[b];
-    for (int32_t r = 0; r < P.n; ++r) M.rowptr.push_back(P.rowptr[r + 1] + zo);
-    for (int32_t c : P.col) M.col.push_back(c + no);
-    M.old_of_new.insert(M.old_of_new.end(), P.old_of_new.begin(), P.old_of_new.end());
-    no += P.n;
-  }
 }
 
 }  // namespace plfem

@@ -38,9 +38,6 @@ struct Pattern {
 };
 void build_pattern(const DofTables& d, const std::vector<int32_t>& new_of_old, int32_t n_new, Pattern& out);
 
-void relabel_pattern(const Pattern& src, const std::vector<int32_t>& old_of, const std::vector<int32_t>& new_of,
-                     const std::vector<int32_t>& full_ids, int64_t N_full, Pattern& out);
-
 // worker threads the symbolic phase may use per call (0 = default: min(cores, 8) or $PLFEM_HOST_THREADS)
 void set_host_threads(int n);
 // the same for the calling thread only (0 = follow the global setting)
@@ -79,9 +76,12 @@ struct FrontPlan {
   int32_t max_front = 0, max_s = 0; // in nodes
 };
 
-// adjacency = pattern of interior nodes in *interior index* numbering (identity order over DofTables::interior)
-// dof: the mesh's DOF tables (the dissection runs on its P1 vertex graph and is lifted to the P2 nodes)
-void build_front_plan(const DofTables& dof, const Pattern& adj, const double* x, const double* y, const SymbolicOptions& opt,
+// dof: the mesh's DOF tables (the dissection runs on its P1 vertex graph and is lifted to the P2 nodes; node
+//      neighbourhoods are read from the element tables); x, y: coordinates of the interior nodes (interior index order)
+// adj: only when front_plan_needs_adjacency(dof) (the P2-graph dissection, PLFEM_DISSECT_P2=1): pattern of the interior
+//      nodes in *interior index* numbering (identity order over DofTables::interior); otherwise may be NULL
+bool front_plan_needs_adjacency(const DofTables& dof);
+void build_front_plan(const DofTables& dof, const Pattern* adj, const double* x, const double* y, const SymbolicOptions& opt,
                       FrontPlan& out);
 
 // Forest of several independent designs as ONE plan / ONE block-diagonal pattern: node ids, front ids and all
@@ -90,6 +90,5 @@ void build_front_plan(const DofTables& dof, const Pattern& adj, const double* x,
 // interior indices, `old_of_new` of the merged pattern each design's LOCAL DOF ids.
 void merge_front_plans(const std::vector<const FrontPlan*>& parts, FrontPlan& out, std::vector<int32_t>& node_off,
                        std::vector<int32_t>& front_off);
-void merge_patterns(const std::vector<const Pattern*>& parts, Pattern& out, std::vector<int64_t>& nnz_off);
 
 }  // namespace plfem
