@@ -205,6 +205,7 @@ struct DevPlan {
   int n_fwd = 0, n_bwd = 0, epoch = 0;
   std::vector<int32_t> lptr;         // host copy of the level schedule
   std::vector<int32_t> lmax_m;       // largest pivot block (unknowns) per level
+  std::vector<int32_t> lsplit, lmax_small;   // per level: fronts with a pivot block <= 64 unknowns (listed first in lfront), their largest block
   // per-level work lists (host-built): tiles for the two GEMMs, slabs for extend-add and the sweeps
   DevBuf<int4> w_tiles, s_tiles, ea_slabs;
   DevBuf<FwdItem> fwd_items; DevBuf<BwdItem> bwd_items; DevBuf<int32_t> gsrc;

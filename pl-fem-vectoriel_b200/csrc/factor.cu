@@ -1098,7 +1098,20 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
   D.n = P.n; D.nfronts = P.nfronts; D.nlevels = P.nlevels;
   D.first.upload(ctx, P.first); D.s.upload(ctx, P.s); D.sptr.upload(ctx, P.sptr); D.strct.upload(ctx, P.strct);
   D.sn_of.upload(ctx, P.sn_of); D.parent.upload(ctx, P.parent); D.cptr.upload(ctx, P.cptr); D.child.upload(ctx, P.child);
-  D.cmap_ptr.upload(ctx, P.cmap_ptr); D.cmap.upload(ctx, P.cmap); D.lfront.upload(ctx, P.lfront);
+  D.cmap_ptr.upload(ctx, P.cmap_ptr); D.cmap.upload(ctx, P.cmap);
+  {
+    // fronts of a level in two size classes (pivot block <= 64 unknowns first): the pivot-block inverse runs 256-thread
+    // CTAs on the first class and 1024-thread CTAs on the second — one oversized leaf must not put a thousand threads on
+    // each of the thousands of 48 x 48 blocks of its level
+    std::vector<int32_t> lf(P.lfront);
+    D.lsplit.assign(P.nlevels, 0); D.lmax_small.assign(P.nlevels, 0);
+    for (int l = 0; l < P.nlevels; ++l) {
+      auto mid = std::stable_partition(lf.begin() + P.lptr[l], lf.begin() + P.lptr[l + 1], [&](int32_t f) { return 2 * P.s[f] <= 64; });
+      D.lsplit[l] = (int32_t)(mid - (lf.begin() + P.lptr[l]));
+      for (auto it = lf.begin() + P.lptr[l]; it != mid; ++it) D.lmax_small[l] = std::max(D.lmax_small[l], 2 * P.s[*it]);
+    }
+    D.lfront.upload(ctx, lf);
+  }
   D.foff.upload(ctx, P.foff);
   D.lptr = P.lptr;
   std::vector<int32_t> uoff(P.nfronts + 1, 0);
@@ -1311,8 +1324,17 @@ void run_factorization(plfem_ctx* ctx, const DevPlan& D) {
       ctx->launches++;
     }
     const int nfl = D.lptr[l + 1] - D.lptr[l];
-    invert_kernel<<<nfl, D.lmax_m[l] > 64 ? 1024 : 256, invert_smem(D.lmax_m[l]), ctx->stream>>>(D.lfront.p + D.lptr[l], v, D.status.p);
-    ctx->launches++;
+    // two size classes in separate launches only where the level is throughput-bound (thousands of small blocks, as at the
+    // bottom of a forest); a latency-bound level runs both classes in one launch, concurrently
+    const int nsmall = D.lsplit[l];
+    if (nsmall >= 1500 && nfl > nsmall) {
+      invert_kernel<<<nsmall, 256, invert_smem(D.lmax_small[l]), ctx->stream>>>(D.lfront.p + D.lptr[l], v, D.status.p);
+      invert_kernel<<<nfl - nsmall, 1024, invert_smem(D.lmax_m[l]), ctx->stream>>>(D.lfront.p + D.lptr[l] + nsmall, v, D.status.p);
+      ctx->launches += 2;
+    } else {
+      invert_kernel<<<nfl, D.lmax_m[l] > 64 ? 1024 : 256, invert_smem(D.lmax_m[l]), ctx->stream>>>(D.lfront.p + D.lptr[l], v, D.status.p);
+      ctx->launches++;
+    }
     const int nw = D.w_ptr[l + 1] - D.w_ptr[l];
     if (nw > 0) {
       gemm_w_kernel<<<nw, 256, 0, ctx->stream>>>(D.w_tiles.p + D.w_ptr[l], v);
