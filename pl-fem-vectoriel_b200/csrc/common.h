@@ -51,8 +51,9 @@ inline cudaError_t stream_wait(cudaStream_t st) {
   for (;;) {
     const cudaError_t e = cudaStreamQuery(st);
     if (e != cudaErrorNotReady) return e;
-    if (clk::now() - t0 < std::chrono::microseconds(40)) continue;
-    timespec ts{0, 30000};
+    const auto waited = std::chrono::duration_cast<std::chrono::nanoseconds>(clk::now() - t0).count();
+    if (waited < 40000) continue;
+    timespec ts{0, (long)std::min<int64_t>(100000, std::max<int64_t>(30000, waited / 16))};   // naps grow with the wait, <= 0.1 ms
     nanosleep(&ts, nullptr);
   }
 }
