@@ -124,42 +124,69 @@ __global__ void expand_rows_kernel(const int32_t* __restrict__ rowptr, int32_t n
 
 // ---- sparsity pattern of the interior nodes in elimination order, built on the device ---------------------------
 // Row R (a node in elimination order) holds the nodes that share an element with it — the union over the elements
-// around its DOF of their 6 DOFs, dropped when eliminated by the Dirichlet condition, sorted ascending.  One thread per
-// row keeps the row in a small sorted list (a P2 row of a triangulation has 3*valence + 1 entries for a vertex, 9 for an
-// edge node); COUNT pass -> inclusive scan -> FILL pass.  Identical to the host `build_pattern` (symbolic.cpp), which the
-// export path still uses; here it saves ~5 ms of host time per design, which is what a forest pool is short of.
-constexpr int PATTERN_MAXROW = 128;
+// around its DOF of their 6 DOFs, dropped when eliminated by the Dirichlet condition, sorted ascending.  One WARP per
+// row: the 6 x (elements around the node) candidate columns go to shared memory, duplicates are struck out (a candidate
+// survives if no earlier one has its value), and a survivor's position in the row is the number of smaller survivors —
+// a few dozen broadcast reads per lane, no per-thread list.  COUNT pass -> inclusive scan -> FILL pass.  Identical to the
+// host `build_pattern` (symbolic.cpp), which the export path still uses; here it saves ~5 ms of host time per design,
+// which is what a forest pool is short of.
+constexpr int PATTERN_MAXCAND = 768;     // 6 x 128 elements around one node (a core centre is the hub of a whole ring)
+constexpr int PATTERN_WARPS = 8;
 
 template <bool FILL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32 * PATTERN_WARPS)
 pattern_rows_kernel(int32_t r0, int32_t n, const int32_t* __restrict__ old_of_new, const int32_t* __restrict__ n2e_ptr,
                     const int32_t* __restrict__ n2e, const int32_t* __restrict__ edofs, const int32_t* __restrict__ new_of_dof,
                     int32_t* __restrict__ rowptr, int32_t* __restrict__ col, int32_t* __restrict__ rowidx, int32_t* __restrict__ err) {
-  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
+  __shared__ int32_t s_cand[PATTERN_WARPS][PATTERN_MAXCAND];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int32_t r = blockIdx.x * PATTERN_WARPS + w;
+  if (r >= n) return;                                   // whole warps leave together
+  int32_t* cand = s_cand[w];
   const int32_t R = r0 + r;
   const int32_t o = old_of_new[R];
-  int32_t list[PATTERN_MAXROW];
-  int len = 0;
-  for (int32_t q = n2e_ptr[o]; q < n2e_ptr[o + 1]; ++q) {
-    const int32_t* ed = edofs + 6 * (int64_t)n2e[q];
-    for (int k = 0; k < 6; ++k) {
-      const int32_t c = new_of_dof[ed[k]];
-      if (c < 0) continue;
-      int i = len;
-      while (i > 0 && list[i - 1] > c) --i;
-      if (i > 0 && list[i - 1] == c) continue;
-      if (len == PATTERN_MAXROW) { atomicExch(err, 1); continue; }
-      for (int j = len; j > i; --j) list[j] = list[j - 1];
-      list[i] = c;
-      ++len;
+  const int32_t q0 = n2e_ptr[o];
+  int nc = 6 * (n2e_ptr[o + 1] - q0);
+  if (nc > PATTERN_MAXCAND) { if (lane == 0) atomicExch(err, 1); nc = PATTERN_MAXCAND; }
+  for (int i = lane; i < nc; i += 32) cand[i] = new_of_dof[edofs[6 * (int64_t)n2e[q0 + i / 6] + i % 6]];
+  __syncwarp();
+  // strike out duplicates: decided from the untouched list, written after everyone has read (bit t of `dup` = candidate
+  // lane + 32 t is a repetition of an earlier one)
+  uint32_t dup = 0;
+  for (int t = 0; 32 * t < nc; ++t) {
+    const int i = lane + 32 * t;
+    if (i < nc) {
+      const int32_t c = cand[i];
+      bool d = false;
+      for (int j = 0; j < i; ++j) d |= (cand[j] == c);
+      dup |= (uint32_t)d << t;
+    }
+  }
+  __syncwarp();
+  for (int t = 0; 32 * t < nc; ++t) {
+    const int i = lane + 32 * t;
+    if (i < nc && ((dup >> t) & 1u)) cand[i] = -1;
+  }
+  __syncwarp();
+  int mine = 0;
+  const int32_t z0 = FILL ? rowptr[R] : 0;
+  for (int t = 0; 32 * t < nc; ++t) {
+    const int i = lane + 32 * t;
+    if (i >= nc) continue;
+    const int32_t c = cand[i];
+    if (c < 0) continue;                                  // eliminated by the Dirichlet condition, or a duplicate
+    ++mine;
+    if (FILL) {
+      int rank = 0;
+      for (int j = 0; j < nc; ++j) { const int32_t cj = cand[j]; rank += (cj >= 0 && cj < c); }
+      col[z0 + rank] = c;
+      rowidx[z0 + rank] = R;
     }
   }
   if (!FILL) {
-    rowptr[R + 1] = len;
-  } else {
-    const int32_t z0 = rowptr[R];
-    for (int i = 0; i < len; ++i) { col[z0 + i] = list[i]; rowidx[z0 + i] = R; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, off);
+    if (lane == 0) rowptr[R + 1] = mine;
   }
 }
 
@@ -323,12 +350,11 @@ void build_device_pattern(plfem_ctx* ctx, int nb, const PatternSource* src, cons
   PLFEM_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int32_t), st));
   d_noff.upload(ctx, node_off);
   d_zoff.alloc(ctx, (size_t)nb + 1);
-  const int bs = 128;
   for (int b = 0; b < nb; ++b) {
     const int32_t r0 = node_off[b], n = node_off[b + 1] - node_off[b];
     if (n == 0) continue;
     scatter_new_of_dof_kernel<<<(n + 255) / 256, 256, 0, st>>>(r0, n, D.old_of_new.p, new_of_dof.p + dof_off[b]);
-    pattern_rows_kernel<false><<<(n + bs - 1) / bs, bs, 0, st>>>(r0, n, D.old_of_new.p, src[b].n2e_ptr, src[b].n2e, src[b].edofs,
+    pattern_rows_kernel<false><<<(n + PATTERN_WARPS - 1) / PATTERN_WARPS, 32 * PATTERN_WARPS, 0, st>>>(r0, n, D.old_of_new.p, src[b].n2e_ptr, src[b].n2e, src[b].edofs,
                                                                 new_of_dof.p + dof_off[b], D.rowptr.p, nullptr, nullptr, d_err.p);
     ctx->launches += 2;
   }
@@ -339,12 +365,12 @@ void build_device_pattern(plfem_ctx* ctx, int nb, const PatternSource* src, cons
   tmp.alloc(ctx, std::max<size_t>(tmp_bytes, 1));
   PLFEM_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tmp_bytes, D.rowptr.p, D.rowptr.p, n_tot + 1, st));
   gather_offsets_kernel<<<1, 32 * ((nb + 1 + 31) / 32), 0, st>>>(D.rowptr.p, d_noff.p, nb + 1, d_zoff.p);
-  ctx->launches += 2;
+  ctx->launches += 3;      // the scan is two kernels (tile-state init + scan)
   std::vector<int32_t> zoff(nb + 1), err(1);
   d_zoff.download(zoff.data(), zoff.size());
   d_err.download(err.data(), 1);
   PLFEM_CUDA(stream_wait(st));
-  if (err[0]) throw StatusError(PLFEM_ERR_INVALID, "a mesh node has more than " + std::to_string(PATTERN_MAXROW) + " neighbours");
+  if (err[0]) throw StatusError(PLFEM_ERR_INVALID, "a mesh node belongs to more than " + std::to_string(PATTERN_MAXCAND / 6) + " elements");
   nnz_off.assign(nb + 1, 0);
   for (int b = 0; b <= nb; ++b) nnz_off[b] = zoff[b];
   D.nnz = nnz_off[nb];
@@ -353,7 +379,7 @@ void build_device_pattern(plfem_ctx* ctx, int nb, const PatternSource* src, cons
   for (int b = 0; b < nb; ++b) {
     const int32_t r0 = node_off[b], n = node_off[b + 1] - node_off[b];
     if (n == 0) continue;
-    pattern_rows_kernel<true><<<(n + bs - 1) / bs, bs, 0, st>>>(r0, n, D.old_of_new.p, src[b].n2e_ptr, src[b].n2e, src[b].edofs,
+    pattern_rows_kernel<true><<<(n + PATTERN_WARPS - 1) / PATTERN_WARPS, 32 * PATTERN_WARPS, 0, st>>>(r0, n, D.old_of_new.p, src[b].n2e_ptr, src[b].n2e, src[b].edofs,
                                                                new_of_dof.p + dof_off[b], D.rowptr.p, D.col.p, D.rowidx.p, d_err.p);
     ctx->launches++;
   }
