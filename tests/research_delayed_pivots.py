@@ -9,8 +9,11 @@ parent front (delayed), where more of their couplings are fully summed.
 
     python tests/research_delayed_pivots.py cfg1|<nx> [u]
 
-prints, per threshold u, the raw solve error against SuperLU, the refinement contraction, the number of delayed
-unknowns (total, per level, largest front growth).  Results are summarised in DESIGN.md ("next round").
+prints, per threshold, the raw solve error against SuperLU, the refinement contraction, the number of delayed
+unknowns (total, per level, largest front growth): u < 1 = classical threshold test (1x1 / 2x2 pivots), u >= 1 = tau of the
+growth-based selection (largest row of W).  Results are summarised in DESIGN.md 4.4a.  NOTE: this prototype forms the Schur
+complement from BOTH off-diagonal blocks (F_RE E^-1 F_ER), which is why it does not show the asymmetry amplification of the
+product's one-block form — see ``frontal_reference_delayed.py`` for that finding and for the static-shape version.
 """
 import sys
 import time

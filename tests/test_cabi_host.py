@@ -136,3 +136,38 @@ def test_front_plan_solves_the_shifted_system(small_case, leaf, sn):
     xr = splu(Kp.tocsc()).solve(b)
     assert np.linalg.norm(x - xr) / np.linalg.norm(xr) < 1e-8
     assert np.linalg.norm(Kp @ x - b) / np.linalg.norm(b) < 1e-9
+
+
+def test_next_factorisation_spec():
+    """Executable specification of the next factorisation on a coarse structured mesh, where the product's
+    algebra loses six digits: symmetrised pivot-block inverses recover most of them, delayed pivots in static slots the
+    rest — with a handful of handed-up unknowns and no front near its slot capacity."""
+    import plfem_b200 as P
+    import frontal_reference_delayed as FD
+    from scipy.sparse.linalg import splu
+    nx = 40
+    g = P.MCFGeometry(7, 8.0, 1.5, 1.535, 1.0, 1.55)
+    xs = np.linspace(-32.0, 32.0, nx + 1)
+    X, Y = np.meshgrid(xs, xs, indexing="xy")
+    idx = np.arange((nx + 1) ** 2).reshape(nx + 1, nx + 1)
+    a, b, c, d = idx[:-1, :-1].ravel(), idx[:-1, 1:].ravel(), idx[1:, :-1].ravel(), idx[1:, 1:].ravel()
+    mesh = P.MeshTri(np.vstack([X.ravel(), Y.ravel()]), np.hstack([np.vstack([a, b, d]), np.vstack([a, d, c])]))
+    s = O.interior_system(g, mesh)
+    K = (s["A_int"] - O.sigma_estimate(g) * s["B_int"]).tocsr()
+    pl = _cabi.Problem(mesh, host_only=True).plan()
+    Kp, _ = FR.permuted_operator(K, pl)
+    rhs = np.random.default_rng(1).standard_normal(Kp.shape[0])
+    xr = splu(Kp.tocsc()).solve(rhs)
+
+    def err(x):
+        return np.linalg.norm(x - xr) / np.linalg.norm(xr)
+    fr, ch = FR.factor(Kp, pl)
+    e_product = err(FR.solve(fr, ch, pl, rhs))                       # 3e-7 when this was written
+    fr, ch = FD.factor(Kp, pl, tau=1e30, symmetrise=True)
+    e_sym = err(FD.solve(fr, ch, pl, rhs))                           # 3e-11
+    fr, ch = FD.factor(Kp, pl, tau=30.0, symmetrise=True)
+    e_full = err(FD.solve(fr, ch, pl, rhs))                          # 7e-13
+    n_delayed = [len(f["dl"]) for f in fr]
+    assert e_sym < 1e-9 and e_sym < 1e-2 * e_product
+    assert e_full < 1e-11
+    assert 0 < sum(n_delayed) < 0.01 * Kp.shape[0] and max(n_delayed) < FD.DC
