@@ -8,8 +8,10 @@ import pytest
 
 import plfem_b200 as P
 from plfem_b200.mesh import MeshGenerator, MeshTri, signed_double_area
+from plfem_b200.sweep import design_geometry, lhs_designs
 
 G = os.path.join(os.path.dirname(__file__), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def digest(a):
@@ -101,3 +103,17 @@ def test_cauchy_indices():
     # SURVEY.md 8(d) config 3
     for lam, n in ((1490, 1.529816), (1550, 1.529516), (1600, 1.529291), (1650, 1.529087)):
         assert abs(P.IPDipCauchy.n(lam) - n) < 1e-6
+
+
+def test_hub_vertices_fit_the_device_pattern_builder(cfg1, cfg2):
+    """The recipe makes every core centre the hub of a whole ring of points (34 triangles around one vertex in config 1).
+    The device-side pattern builder (`pattern_rows_kernel`, assembly.cu) holds the 6 x valence candidate columns of a row
+    in shared memory, PATTERN_MAXCAND = 768, i.e. valence <= 128: the recipe's meshes must stay well inside that."""
+    import re
+    src = open(os.path.join(ROOT, "pl-fem-vectoriel_b200", "csrc", "assembly.cu")).read()
+    cap = int(re.search(r"PATTERN_MAXCAND\s*=\s*(\d+)", src).group(1)) // 6
+    sample = [cfg1[1], cfg2[1]]
+    for d in lhs_designs(24, seed=7)[:8]:
+        sample.append(P.MeshGenerator.generate(design_geometry(d))[0])
+    worst = max(int(np.bincount(np.asarray(m.t).ravel()).max()) for m in sample)
+    assert 16 <= worst <= cap // 2, worst
