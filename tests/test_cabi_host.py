@@ -168,6 +168,14 @@ def test_next_factorisation_spec():
     fr, ch = FD.factor(Kp, pl, tau=30.0, symmetrise=True)
     e_full = err(FD.solve(fr, ch, pl, rhs))                          # 7e-13
     n_delayed = [len(f["dl"]) for f in fr]
+    # the same with the product's own inverse algorithm (Gauss-Jordan as in invert_kernel) and its symmetrised write-back
+    fr_gj, ch_gj = FR.factor(Kp, pl, inverse=lambda A: FR.gauss_jordan_inverse(A, symmetrise=True))
+    e_gj = err(FR.solve(fr_gj, ch_gj, pl, rhs))
+    A0 = np.random.default_rng(2).standard_normal((37, 37))
+    A0 = A0 + A0.T
+    A0[np.diag_indices(37)] *= 1e-3                                  # forces row swaps
+    assert np.abs(FR.gauss_jordan_inverse(A0) - np.linalg.inv(A0)).max() < 1e-11 * np.abs(np.linalg.inv(A0)).max()
+    assert e_gj < 1e-9 and e_gj < 1e-2 * e_product
     assert e_sym < 1e-9 and e_sym < 1e-2 * e_product
     assert e_full < 1e-11
     assert 0 < sum(n_delayed) < 0.01 * Kp.shape[0] and max(n_delayed) < FD.DC
