@@ -402,7 +402,7 @@ def test_structured_mesh_is_solved_without_refinement():
     mat, keep = _cabi.material_struct(g)
     sigma = sigma_estimate(g)
     vals, _, _, _, st = pb.solve_modes(mat, sigma, 22, want_vectors=False)
-    assert st.solve_residual < 1e-6 and st.refine_steps <= 1
+    assert st.refine_steps <= 1 and st.max_residual < 1e-8
     s = O.interior_system(g, mesh)
     ref = np.sort(eigsh(s["A_int"], k=22, M=s["B_int"], sigma=sigma, which="LM", tol=1e-10)[0])
     assert np.abs(np.sort(vals) / ref - 1).max() < 1e-8
