@@ -20,7 +20,35 @@ def permuted_operator(K_int, plan):
     return K_int[idx, :][:, idx].tocsr(), idx
 
 
-def factor(Kp, plan):
+def gauss_jordan_inverse(F, symmetrise=False):
+    """The algorithm of `invert_kernel` (factor.cu) in NumPy: in-place Gauss-Jordan with partial pivoting, the row swaps
+    undone at write-back through the column permutation `src` (entry (i, j) of the inverse = a[i, src[j]]).  With
+    ``symmetrise`` the write-back averages entry (i, j) with entry (j, i) = a[j, src[i]] — the one-line change of
+    DESIGN.md 4.4a."""
+    m = F.shape[0]
+    a = np.array(F, dtype=float)
+    piv = np.zeros(m, dtype=np.int64)
+    for k in range(m):
+        p = k + int(np.argmax(np.abs(a[k:, k])))
+        piv[k] = p
+        inv = 1.0 / a[p, k]
+        if p != k:
+            a[[k, p], :] = a[[p, k], :]
+        rowk = a[k, :] * inv
+        colk = a[:, k].copy()
+        colk[k] = 0.0
+        a -= np.outer(colk, rowk)
+        a[:, k] = -colk * inv
+        a[k, :] = rowk
+        a[k, k] = inv
+    src = np.arange(m)
+    for k in range(m - 1, -1, -1):
+        src[k], src[piv[k]] = src[piv[k]], src[k]
+    out = a[:, src]
+    return 0.5 * (out + out.T) if symmetrise else out
+
+
+def factor(Kp, plan, inverse=np.linalg.inv):
     first, s, sptr, strct = plan["first"], plan["s"], plan["sptr"], plan["strct"]
     parent, cmap_ptr, cmap = plan["parent"], plan["cmap_ptr"], plan["cmap"]
     nf = plan["nfronts"]
@@ -45,7 +73,7 @@ def factor(Kp, plan):
             pos[0::2] = 2 * cm
             pos[1::2] = 2 * cm + 1
             F[np.ix_(pos, pos)] += fronts[c]["S"]
-        F11inv = np.linalg.inv(F[:s2, :s2])
+        F11inv = inverse(F[:s2, :s2])
         W = F11inv @ F[:s2, s2:]
         S = F[s2:, s2:] - F[:s2, s2:].T @ W
         fronts[f] = dict(F11inv=F11inv, W=W, S=S, unk=unk, s2=s2)

@@ -168,6 +168,54 @@ def test_next_factorisation_spec():
     fr, ch = FD.factor(Kp, pl, tau=30.0, symmetrise=True)
     e_full = err(FD.solve(fr, ch, pl, rhs))                          # 7e-13
     n_delayed = [len(f["dl"]) for f in fr]
+    # the same with the product's own inverse algorithm (Gauss-Jordan as in invert_kernel) and its symmetrised write-back
+    fr_gj, ch_gj = FR.factor(Kp, pl, inverse=lambda A: FR.gauss_jordan_inverse(A, symmetrise=True))
+    e_gj = err(FR.solve(fr_gj, ch_gj, pl, rhs))
+    A0 = np.random.default_rng(2).standard_normal((37, 37))
+    A0 = A0 + A0.T
+    A0[np.diag_indices(37)] *= 1e-3                                  # forces row swaps
+    assert np.abs(FR.gauss_jordan_inverse(A0) - np.linalg.inv(A0)).max() < 1e-11 * np.abs(np.linalg.inv(A0)).max()
+    assert e_gj < 1e-9 and e_gj < 1e-2 * e_product
     assert e_sym < 1e-9 and e_sym < 1e-2 * e_product
     assert e_full < 1e-11
     assert 0 < sum(n_delayed) < 0.01 * Kp.shape[0] and max(n_delayed) < FD.DC
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_front_plan_on_random_triangulations(seed):
+    """Random point clouds (irregular valences, thin triangles at the hull, chords between boundary vertices): the plan built
+    from the lifted vertex-graph dissection must be a valid elimination forest of the P2 graph — executed with dense NumPy it
+    solves the shifted system."""
+    import plfem_b200 as P
+    from scipy.spatial import Delaunay
+    from scipy.sparse.linalg import splu
+    rng = np.random.default_rng(seed)
+    n_pts = 350 + 150 * seed
+    r = 6.0 * np.sqrt(rng.random(n_pts))
+    a = 2 * np.pi * rng.random(n_pts)
+    pts = np.column_stack([r * np.cos(a), r * np.sin(a)])
+    tri = Delaunay(pts).simplices
+    p = pts.T.copy()
+    t = tri.T.copy()
+    area2 = (p[0, t[1]] - p[0, t[0]]) * (p[1, t[2]] - p[1, t[0]]) - (p[0, t[2]] - p[0, t[0]]) * (p[1, t[1]] - p[1, t[0]])
+    t = t[:, np.abs(area2) > 1e-9]
+    mesh = P.MeshTri(p, t)
+    g = P.MCFGeometry(3, 4.0, 1.2, 1.53, 1.0, 1.55)
+    s = O.interior_system(g, mesh)
+    K = (s["A_int"] - O.sigma_estimate(g) * s["B_int"]).tocsr()
+    pl = _cabi.Problem(mesh, host_only=True).plan(12 + 6 * seed, 16 * (seed + 1))
+    n = pl["n"]
+    assert n == len(s["interior"]) and sorted(pl["perm"]) == list(range(n))
+    first, sz, sptr, strct, parent, level = (pl[k] for k in ("first", "s", "sptr", "strct", "parent", "level"))
+    assert sz.sum() == n and sz.max() <= 16 * (seed + 1)
+    for f in range(pl["nfronts"]):
+        st = strct[sptr[f]:sptr[f + 1]]
+        assert (np.diff(st) > 0).all() and (len(st) == 0 or st[0] >= first[f] + sz[f])
+        assert (parent[f] > f and level[parent[f]] > level[f]) if parent[f] >= 0 else len(st) == 0
+    Kp, _ = FR.permuted_operator(K, pl)
+    fronts, ch = FR.factor(Kp, pl)
+    rhs = rng.standard_normal(2 * n)
+    x = FR.solve(fronts, ch, pl, rhs)
+    x = x + FR.solve(fronts, ch, pl, rhs - Kp @ x)
+    xr = splu(Kp.tocsc()).solve(rhs)
+    assert np.linalg.norm(x - xr) / np.linalg.norm(xr) < 1e-7
