@@ -219,3 +219,22 @@ def test_front_plan_on_random_triangulations(seed):
     x = x + FR.solve(fronts, ch, pl, rhs - Kp @ x)
     xr = splu(Kp.tocsc()).solve(rhs)
     assert np.linalg.norm(x - xr) / np.linalg.norm(xr) < 1e-7
+
+
+def test_front_plan_is_the_frozen_one(cfg1, small_case):
+    """The numerical results on the GPU (and their bit-for-bit reproducibility) depend on the front plan.  Host-side speed
+    work on the symbolic phase must not change it silently: these digests were taken from the plan the GPU parity tests of
+    round 1 ran with.  An intended change of the ordering regenerates tests/golden/front_plan.json (same code as below)."""
+    import hashlib
+    import json
+
+    def digest(mesh, opts):
+        pl = _cabi.Problem(mesh, host_only=True).plan(*opts)
+        h = hashlib.sha256()
+        for k in ("perm", "first", "s", "parent", "level", "sptr", "strct", "cmap_ptr", "cmap", "foff"):
+            h.update(np.ascontiguousarray(pl[k]).tobytes())
+        return h.hexdigest()
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "front_plan.json")))
+    assert digest(cfg1[1], (0, 0)) == gold["cfg1_default"]
+    assert digest(cfg1[1], (8, 16)) == gold["cfg1_leaf8_sn16"]
+    assert digest(small_case[1], (0, 0)) == gold["small_default"]
