@@ -13,12 +13,14 @@ own forest, so the host-side symbolic analysis of one forest overlaps the device
 The mesh is given (built on the host before timing, as in the reference where `MeshGenerator` runs
 first).  ``latency`` in the JSON line is one solve run alone.
 
-* ``value``  : solves/s with the mesh and its DOF tables already resident in HBM
-               (`plfem_solve_modes` on an existing problem, symbolic analysis NOT reused,
+* ``value``  : solves/s with the meshes and their DOF tables already resident in HBM
+               (`plfem_solve_modes_batch` on existing problems, symbolic analysis NOT reused,
                eigenvectors left on the device).
-* ``e2e``    : the same metric through the public drop-in class with HOST buffers in and out
-               (`TrueVectorialMaxwellSolver(g).solve_vectorial_modes(mesh, n)` on NumPy arrays: mesh
-               upload, solve, eigenvectors + metrics copied back, mode records built).
+* ``e2e``    : the same metric through the public forest API with HOST buffers in and out
+               (`ForestPool.solve_iter` on (geometry, NumPy mesh, n_modes) jobs: DOF tables, mesh upload,
+               forest solve, eigenvectors + metrics copied back, mode records built and consumed);
+               ``latency`` is `TrueVectorialMaxwellSolver(g).solve_vectorial_modes(mesh, n)` alone.
+* ``host``   : process CPU time per solve inside the two timed regions (what limits N > 1 on one node).
 * N > 1      : one process per GPU (torchrun), every rank solves the same workload (weak scaling,
                independent designs, no data-path collective); the 86-slot records are exchanged with
                ONE all_gather inside the timed region; time = max over ranks.
