@@ -873,7 +873,7 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
     std::vector<double> hn((size_t)B * RSPLIT * 2);
     nrm.download(hn.data(), hn.size());
     PLFEM_CUDA(stream_wait(st));
-    rsteps = 1;
+    rsteps = 0;
     for (int b = 0; b < B; ++b) {
       double nr = 0.0, nbv = 0.0;
       for (int sl = 0; sl < RSPLIT; ++sl) { nr += hn[((size_t)b * RSPLIT + sl) * 2]; nbv += hn[((size_t)b * RSPLIT + sl) * 2 + 1]; }
@@ -886,7 +886,9 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
                      "): a pivot block is numerically singular";
         continue;
       }
-      rsteps = std::max(rsteps, rho <= 1e-4 ? 1 : (rho <= 2e-3 ? 2 : (rho <= 1e-2 ? 3 : 5)));
+      // rho <= 1e-9: the raw solve is already three decades below the Lanczos tolerance (symmetrised pivot-block inverses
+      // give 1e-10 on the reference's meshes): no refinement solve at all
+      rsteps = std::max(rsteps, rho <= 1e-9 ? 0 : (rho <= 1e-4 ? 1 : (rho <= 2e-3 ? 2 : (rho <= 1e-2 ? 3 : 5))));
     }
   }
   res.refine_steps = rsteps;

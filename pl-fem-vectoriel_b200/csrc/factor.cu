@@ -176,8 +176,12 @@ __global__ void __launch_bounds__(1024) invert_kernel(const int32_t* __restrict_
     for (int k = m - 1; k >= 0; --k) { const int t = src[k]; src[k] = src[piv[k]]; src[piv[k]] = t; }
   }
   __syncthreads();
+  // The inverse of a symmetric block is symmetric; the computed one only to cond x eps, and the Schur complement
+  // S = F22 - F12^T (F11^-1 F12) is formed from the upper block alone, so that antisymmetric part would land in S, then in
+  // the parent's pivot block, amplified by |W|^2 level by level (it, not the block-local pivoting, cost
+  // the raw solve six digits and made structured meshes diverge).  Write back the average with the transpose.
   if (i < m)
-    for (int j = jg; j < m; j += ng) F[(int64_t)j * ld + i] = a[i + src[j] * lds];
+    for (int j = jg; j < m; j += ng) F[(int64_t)j * ld + i] = 0.5 * (a[i + src[j] * lds] + a[j + src[i] * lds]);
 }
 
 // ---- tiled FP64 GEMM used for W^T and the Schur update -------------------------------------------------

@@ -368,22 +368,41 @@ def test_useless_factorisation_is_reported_not_iterated():
 
 
 def test_failed_design_does_not_poison_its_forest(small_case):
-    """A design whose factorisation is useless (coarse structured mesh, see above) is reported alone; the other designs
-    of the same forest give exactly their single-solve results."""
-    import plfem_b200 as P
+    """A design whose factorisation is useless (a non-finite core index: every pivot block of its tree is NaN) is reported
+    alone; the other designs of the same forest give exactly their single-solve results."""
+    import copy
     from plfem_b200.batch import ForestPool
     g, mesh = small_case
-    nx = 96
-    xs = np.linspace(-32.0, 32.0, nx + 1)
-    X, Y = np.meshgrid(xs, xs, indexing="xy")
-    idx = np.arange((nx + 1) ** 2).reshape(nx + 1, nx + 1)
-    a, b, c, d = idx[:-1, :-1].ravel(), idx[:-1, 1:].ravel(), idx[1:, :-1].ravel(), idx[1:, 1:].ravel()
-    bad_mesh = P.MeshTri(np.vstack([X.ravel(), Y.ravel()]), np.hstack([np.vstack([a, b, d]), np.vstack([a, d, c])]))
-    g7 = P.MCFGeometry(7, 8.0, 1.5, 1.535, 1.0, 1.55)
+    g_bad = copy.copy(g)
+    g_bad.n_core = float("nan")
     alone, araw = TrueVectorialMaxwellSolver(g).solve_vectorial_modes(mesh, 4, return_raw=True)
     with ForestPool(batch=3, workers=1) as pool:
-        out = pool.solve_forest([(g, mesh, 4), (g7, bad_mesh, 10), (g, mesh, 4)], return_raw=True)
+        out = pool.solve_forest([(g, mesh, 4), (g_bad, mesh, 4), (g, mesh, 4)], return_raw=True)
     assert isinstance(out[1], _cabi.PlfemError) and out[1].status in (5, 6)
     for modes, raw in (out[0], out[2]):
         assert np.abs(raw["beta_sq"] / araw["beta_sq"] - 1).max() < 1e-9 and len(modes) == len(alone)
         assert raw["stats"]["max_residual"] < 1e-9
+
+
+@pytest.mark.gpu
+def test_structured_mesh_is_solved_without_refinement():
+    """120 x 120 structured cells: the mesh family on which the factorisation diverged before the pivot-block inverses were
+    symmetrised.  Eigenvalues against the oracle; the probe must find the raw solve accurate."""
+    import plfem_b200 as P
+    from plfem_b200.solver_fem import sigma_estimate
+    from scipy.sparse.linalg import eigsh
+    g = P.MCFGeometry(7, 8.0, 1.5, 1.535, 1.0, 1.55)
+    nx = 120
+    xs = np.linspace(-32.0, 32.0, nx + 1)
+    X, Y = np.meshgrid(xs, xs, indexing="xy")
+    idx = np.arange((nx + 1) ** 2).reshape(nx + 1, nx + 1)
+    a, b, c, d = idx[:-1, :-1].ravel(), idx[:-1, 1:].ravel(), idx[1:, :-1].ravel(), idx[1:, 1:].ravel()
+    mesh = P.MeshTri(np.vstack([X.ravel(), Y.ravel()]), np.hstack([np.vstack([a, b, d]), np.vstack([a, d, c])]))
+    pb = _cabi.Problem(mesh)
+    mat, keep = _cabi.material_struct(g)
+    sigma = sigma_estimate(g)
+    vals, _, _, _, st = pb.solve_modes(mat, sigma, 22, want_vectors=False)
+    assert st.refine_steps <= 1 and st.max_residual < 1e-8
+    s = O.interior_system(g, mesh)
+    ref = np.sort(eigsh(s["A_int"], k=22, M=s["B_int"], sigma=sigma, which="LM", tol=1e-10)[0])
+    assert np.abs(np.sort(vals) / ref - 1).max() < 1e-8
