@@ -112,23 +112,43 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+_ONE_THREAD = {"OMP_NUM_THREADS": "1", "OPENBLAS_NUM_THREADS": "1", "MKL_NUM_THREADS": "1", "NUMEXPR_NUM_THREADS": "1"}
+
+
+def _blas_threads():
+    """Threads the BLAS pools of THIS process actually run with (threadpoolctl), for the record."""
+    try:
+        from threadpoolctl import threadpool_info
+        return sorted({int(p.get("num_threads", 0)) for p in threadpool_info()}) or [1]
+    except Exception:
+        return None
+
+
 def _cpu_solve(args):
+    """One modal solve with the oracle port.  The caller pins the BLAS/OpenMP pools to ONE thread per process through
+    the environment BEFORE this process imports NumPy (`run_reference` sets it in the parent of the spawned workers,
+    `cpu_baseline_sample` runs a subprocess): SuperLU and ARPACK are single-threaded, a BLAS pool per worker process only
+    oversubscribes the host."""
     name, faithful = args
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
     from oracle import fem_oracle as O
     w, g, mesh = make_case(name)
     t = time.perf_counter()
     modes = O.solve_vectorial_modes(g, mesh, w["n_modes"], faithful_cost=faithful)
-    return time.perf_counter() - t, len(modes)
+    return time.perf_counter() - t, len(modes), _blas_threads()
 
 
 def cpu_baseline_sample(name: str, n_solves: int = 2):
     """Oracle port timed on one host core: the reference's own work per solve (epsilon re-evaluated in
-    each of the 180 form calls like scikit-fem does, SuperLU + ARPACK through SciPy)."""
-    times = [_cpu_solve((name, True))[0] for _ in range(n_solves)]
-    return {"value": 1.0 / statistics.mean(times), "unit": "solves/s", "cores": 1, "kind": "port",
+    each of the 180 form calls like scikit-fem does, SuperLU + ARPACK through SciPy).  Runs in a fresh
+    subprocess whose environment pins every BLAS/OpenMP pool to one thread before NumPy is imported."""
+    code = ("import sys, json; sys.path.insert(0, %r); import bench; "
+            "r = [bench._cpu_solve((%r, True)) for _ in range(%d)]; print(json.dumps(r))" % (ROOT, name, n_solves))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **_ONE_THREAD), capture_output=True, text=True, check=True)
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    times = [r[0] for r in res]
+    return {"value": 1.0 / statistics.mean(times), "unit": "solves/s", "cores": 1, "kind": "port", "blas_threads": res[0][2],
             "sample": f"{n_solves} full modal solves of {name} with oracle/fem_oracle.py (NumPy restatement of scikit-fem "
-                      f"assembly + real scipy eigsh/SuperLU), {statistics.mean(times):.2f} s each, "
+                      f"assembly + real scipy eigsh/SuperLU), one process, one thread, {statistics.mean(times):.2f} s each, "
                       f"host has {os.cpu_count()} cores"}
 
 
@@ -137,13 +157,15 @@ def run_reference(args):
     if rank != 0:
         return
     import multiprocessing as mp
-    name = args.workload
-    cores = max(1, min(os.cpu_count() or 1, 16))
+    name = args.workload if args.workload in WORKLOADS else "cfg1"
+    cores = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     w, g, mesh = make_case(name)
+    os.environ.update(_ONE_THREAD)          # inherited by the spawned workers BEFORE they import NumPy
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
+        threads = pool.map(_cpu_solve, [(name, True)] * cores)[0][2] if args.warmup == 0 else None
         for _ in range(args.warmup):
-            pool.map(_cpu_solve, [(name, True)] * cores)
+            threads = pool.map(_cpu_solve, [(name, True)] * cores)[0][2]
         t0 = time.perf_counter()
         for _ in range(args.steps):
             pool.map(_cpu_solve, [(name, True)] * cores)
@@ -154,9 +176,10 @@ def run_reference(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["name"], "mesh": {"V": int(mesh.p.shape[1]), "T": int(mesh.t.shape[1])},
                        "step": f"{cores} independent modal solves, one per worker process"},
-            "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port",
-                             "sample": f"each step = {cores} concurrent full modal solves (one process per core, "
-                                       "OMP_NUM_THREADS=1; SuperLU/ARPACK are single-threaded)"},
+            "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port", "blas_threads_per_process": threads,
+                             "sample": f"each step = {cores} concurrent full modal solves, one single-threaded process per host core "
+                                       f"({cores} of {os.cpu_count()} cores usable; OMP/OPENBLAS/MKL_NUM_THREADS=1 set before the workers "
+                                       "import NumPy; SuperLU/ARPACK are single-threaded)"},
             "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -177,7 +200,8 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("PLFEM_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
+        # NCCL_DEBUG stays as the launcher set it; NCCL's log goes to stderr so that stdout carries only the JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     peaks = {}
     try:
@@ -306,7 +330,7 @@ def run_ours(args):
     fstats = fo[0][4].as_dict()
     prof, nb_prof = ctx0.profile_last(repeat=10)
     nblk = fstats["batch_block_ops"]
-    n_sweeps = nblk * 2        # 1 refinement step -> 2 block-LDL^T solves per operator application
+    n_sweeps = nblk * (1 + int(fstats["refine_steps"]))        # block-LDL^T solves per operator application: 1 + refinement steps
     fkey, bkey = "forward_sweep_4rhs", "backward_sweep_4rhs"
     share = {k_: 0.0 for k_ in prof}
     share.update({fkey: n_sweeps * prof[fkey][0], bkey: n_sweeps * prof[bkey][0], "factorize": prof["factorize"][0],
@@ -353,8 +377,8 @@ def run_ours(args):
                                f"of a forest (each with its own symbolic analysis, assembly, factorisation, eigensolve and reductions) share "
                                f"every kernel launch, the {NW} forests in flight overlap host analysis and device work",
                        "designs_per_forest": B, "forests_in_flight": NW, "solves_per_step": NW * B,
-                       "k": k, "lanczos": "thick-restart block Lanczos, 4 vectors per operator application, basis 3k, designs in lockstep", "tol": 1e-7,
-                       "start_vector": "ones (+3 fixed pseudo-random)", "refine_steps": 1,
+                       "k": k, "lanczos": "thick-restart block Lanczos, 4 vectors per operator application, basis 3k, designs in lockstep", "tol": _cabi.EIG_TOL,
+                       "start_vector": "ones (+3 fixed pseudo-random)", "refine_steps": int(fstats["refine_steps"]),
                        "l2": f"inputs larger than L2: one forest streams {B * fstats['factor_entries'] * 8 / 1e6:.0f} MB of factor panels per sweep "
                              f"(front pools {B * fstats['front_pool_doubles'] * 8 / 1e9:.2f} GB); L2 also flushed (512 MiB write) before the timed region",
                        "timing": "wall clock around the K steps (forests) submitted to the worker threads, cuda synchronize + barrier on both sides, max over ranks",

@@ -141,6 +141,7 @@ typedef struct {
   int32_t batch_block_ops;          /* lockstep operator applications of the batch */
   float ms_symbolic_wall;           /* host wall time of the analysis of all designs (parallel threads) */
   int32_t refine_steps;             /* refinement steps per operator application actually used */
+  double probe_rho;                 /* |dx|/|x| of the first refinement correction of a raw block-LDL^T solve (this design) */
 } plfem_solve_stats;
 
 /* Per-mode reductions of solver_fem.py:212-220, computed on the l2-normalised (vx, vy):

@@ -59,7 +59,7 @@ class SolveStats(C.Structure):
                 ("ms_symbolic", C.c_float), ("ms_assemble", C.c_float), ("ms_factor", C.c_float),
                 ("ms_lanczos", C.c_float), ("ms_metrics", C.c_float), ("ms_total", C.c_float),
                 ("kernel_launches", c_i32), ("n_block_op", c_i32), ("batch_size", c_i32), ("batch_block_ops", c_i32),
-                ("ms_symbolic_wall", C.c_float), ("refine_steps", c_i32)]
+                ("ms_symbolic_wall", C.c_float), ("refine_steps", c_i32), ("probe_rho", c_f64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -81,9 +81,13 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        if not LIB_PATH.exists():
-            from . import build as _build
-            _build.build()
+        from . import build as _build
+        if not LIB_PATH.exists() or _build.needs_build():     # never load a library older than its sources
+            try:
+                _build.build()
+            except RuntimeError:
+                if not LIB_PATH.exists():
+                    raise                                     # no nvcc and no library: nothing to run
         lib = C.CDLL(str(LIB_PATH))
         vp = C.c_void_p
         lib.plfem_version.restype = C.c_char_p
@@ -190,6 +194,8 @@ class Context:
             raise PlfemError(st, f"cannot create a CUDA context on device {device} "
                                  "(this package has no CPU path)")
         self.handle, self.device = h, int(device)
+        import weakref
+        self._problems = weakref.WeakSet()      # live problems of this context (closed with it: their buffers are in its arena)
 
     @classmethod
     def get(cls, device: int = 0) -> "Context":
@@ -224,8 +230,20 @@ class Context:
                                            _ptr(data, p_f64), _ptr(x, p_f64), _ptr(y, p_f64), repeat, C.byref(ms)))
         return y, ms.value
 
+    def close(self):
+        """Destroy the context: stream, events, pinned staging and every block of its device arena.  Problems created on
+        it must be closed first (their buffers live in the arena)."""
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            for pb in list(self._problems):
+                pb.close()
+            self.lib.plfem_ctx_destroy(h)
+            for k, v in list(Context._cache.items()):
+                if v is self:
+                    del Context._cache[k]
+
     def __del__(self):
-        pass  # contexts live for the process; the driver reclaims them at exit
+        pass  # cached contexts live for the process; pools close the ones they create (ForestPool.close)
 
 
 def material_struct(geometry, alpha_p: float = 1.0, eps_at_quad=None):
@@ -261,6 +279,8 @@ class Problem:
             msg = self.lib.plfem_last_error(self.ctx.handle).decode() if self.ctx else "invalid mesh"
             raise PlfemError(st, msg)
         self.handle = h
+        if self.ctx is not None:
+            self.ctx._problems.add(self)
         info = MeshInfo()
         self.lib.plfem_problem_info(h, C.byref(info))
         self.info = info

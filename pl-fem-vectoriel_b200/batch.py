@@ -42,6 +42,8 @@ class ForestPool:
         self.host_threads = host_threads or max(1, min(self.batch, -(-3 * cores // (2 * self.workers))))
         lib.plfem_set_host_threads(self.host_threads)
         self._local = threading.local()
+        self._contexts: list = []                     # every context a worker thread created (destroyed in close())
+        self._ctx_lock = threading.Lock()
         self._pool = ThreadPoolExecutor(max_workers=self.workers, thread_name_prefix="plfem-forest")
         self._build = ThreadPoolExecutor(max_workers=max(1, min(self.batch, cores)), thread_name_prefix="plfem-dof")
         self.last_stats: List[dict] = []
@@ -49,6 +51,8 @@ class ForestPool:
     def _ctx(self):
         if not hasattr(self._local, "ctx"):
             self._local.ctx = _cabi.Context(self.device)     # a fresh context: own stream + arena
+            with self._ctx_lock:
+                self._contexts.append(self._local.ctx)
         return self._local.ctx
 
     # -- one forest ---------------------------------------------------------------------------------
@@ -61,23 +65,38 @@ class ForestPool:
         if own:
             problems = list(self._build.map(lambda j: _cabi.Problem(j[1], ctx), jobs))
         try:
-            mats, keep, sigmas, ks = [], [], [], []
-            for (geo, mesh, n_modes), pb in zip(jobs, problems):
-                m, k_ = TrueVectorialMaxwellSolver(geo, device=self.device, ctx=ctx)._material(pb)
-                mats.append(m); keep.append(k_)
-                sigmas.append(sigma_estimate(geo))
-                ks.append(min(n_modes + 12, 2 * pb.n_interior - 4))
-            res = _cabi.solve_modes_batch(ctx, problems, mats, sigmas, ks, tol=_cabi.EIG_TOL, maxiter=12000,
-                                          want_vectors=self.want_vectors)
-            out, stats = [], []
-            for (geo, mesh, n_modes), pb, (vals, vecs, met, ncore, st, status) in zip(jobs, problems, res):
-                stats.append(st.as_dict())
-                if status != 0:
-                    out.append(_cabi.PlfemError(status, "design failed inside a forest"))
+            # A design whose host-side preparation fails (its epsilon callable raises, k out of range ...) is reported alone
+            # and left out of the forest; the others are solved as usual (the C layer does the same for device-side
+            # failures through statuses[b]).
+            out: list = [None] * len(jobs)
+            stats: list = [None] * len(jobs)
+            live, mats, keep, sigmas, ks = [], [], [], [], []
+            for j, ((geo, mesh, n_modes), pb) in enumerate(zip(jobs, problems)):
+                try:
+                    m, k_ = TrueVectorialMaxwellSolver(geo, device=self.device, ctx=ctx)._material(pb)
+                    sg, kk = sigma_estimate(geo), min(n_modes + 12, 2 * pb.n_interior - 4)
+                    if kk < 1:
+                        raise ValueError("mesh too small for the requested number of modes")
+                except Exception as e:                      # noqa: BLE001
+                    out[j] = e
                     continue
-                guided, raw, frac = modes_from_solution(geo, pb.n_interior, vals, vecs, met, ncore)
-                out.append((guided, dict(beta_sq=vals, evecs=vecs, metrics=met, modes_raw=raw, frac_core=frac,
-                                         stats=stats[-1])) if return_raw else guided)
+                live.append(j); mats.append(m); keep.append(k_); sigmas.append(sg); ks.append(kk)
+            if live:
+                res = _cabi.solve_modes_batch(ctx, [problems[j] for j in live], mats, sigmas, ks, tol=_cabi.EIG_TOL,
+                                              maxiter=12000, want_vectors=self.want_vectors)
+                for j, (vals, vecs, met, ncore, st, status) in zip(live, res):
+                    geo, pb = jobs[j][0], problems[j]
+                    stats[j] = st.as_dict()
+                    if status != 0:
+                        out[j] = _cabi.PlfemError(status, "design failed inside a forest")
+                        continue
+                    try:      # e.g. no eigenvalue inside the n_eff window: the reference raises here too (`solver_fem.py:228`)
+                        guided, raw, frac = modes_from_solution(geo, pb.n_interior, vals, vecs, met, ncore)
+                    except Exception as e:                  # noqa: BLE001
+                        out[j] = e
+                        continue
+                    out[j] = (guided, dict(beta_sq=vals, evecs=vecs, metrics=met, modes_raw=raw, frac_core=frac,
+                                           stats=stats[j])) if return_raw else guided
             self.last_stats = stats
             return out
         finally:
@@ -122,6 +141,10 @@ class ForestPool:
     def close(self):
         self._pool.shutdown(wait=True)
         self._build.shutdown(wait=True)
+        with self._ctx_lock:
+            ctxs, self._contexts = self._contexts, []
+        for c in ctxs:                                 # stream, events and the device arena (GBs per forest) go back
+            c.close()
         _cabi.load().plfem_set_host_threads(0)
 
     def __enter__(self):
@@ -138,11 +161,15 @@ class SolverPool:
         cores = os.cpu_count() or 1
         lib.plfem_set_host_threads(host_threads_per_solve or max(1, min(8, cores // max(self.workers, 1))))
         self._local = threading.local()
+        self._contexts: list = []
+        self._ctx_lock = threading.Lock()
         self._pool = ThreadPoolExecutor(max_workers=self.workers, thread_name_prefix="plfem")
 
     def _ctx(self):
         if not hasattr(self._local, "ctx"):
             self._local.ctx = _cabi.Context(self.device)     # a fresh context: own stream + arena
+            with self._ctx_lock:
+                self._contexts.append(self._local.ctx)
             # persistent operator kernels of all workers must be co-resident: share the 8 CTA slots per SM
             self._local.ctx.set_coop_ctas(max(1, min(4, 8 // max(self.workers, 1))))
         return self._local.ctx
@@ -165,6 +192,10 @@ class SolverPool:
 
     def close(self):
         self._pool.shutdown(wait=True)
+        with self._ctx_lock:
+            ctxs, self._contexts = self._contexts, []
+        for c in ctxs:
+            c.close()
         _cabi.load().plfem_set_host_threads(0)
 
     def __enter__(self):

@@ -252,6 +252,7 @@ void plfem_ctx_destroy(plfem_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  ctx->last_work.reset();        // its buffers go back to the arena before the arena frees everything
   ctx->arena.destroy();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -673,6 +674,19 @@ static void solve_forest(plfem_ctx* ctx, int nb, plfem_problem* const* pbs, cons
   cudaEventElapsedTime(&ms_lan, ctx->ev[2], ctx->ev[3]);
   cudaEventElapsedTime(&ms_met, ctx->ev[3], ctx->ev[4]);
   for (int b = 0; b < nb; ++b) {
+    // The Lanczos convergence test assumes an exact operator; the block-LDL^T solve (+ the refinement steps the probe chose)
+    // is not.  The TRUE normwise backward error ||A x - lambda B x|| / ((||A||_F + |lambda| ||B||_F) ||x||) of every returned
+    // pair is therefore checked against the tolerance before a design is reported as PLFEM_OK.
+    double mr = 0.0;
+    for (size_t i = 0; i + 1 < resid[b].size(); i += 2) {
+      const double r = resid[b][i] / (resid[b][i + 1] + 1e-300);
+      mr = (r > mr || !(r == r)) ? r : mr;          // a NaN residual must not pass
+    }
+    if (des[b].status == PLFEM_OK && !resid[b].empty() && !(mr <= 0.1 * des[b].tol)) {
+      des[b].status = PLFEM_ERR_NO_CONVERGENCE;
+      des[b].err = "returned eigenpairs miss the backward-error bar: max ||A x - lambda B x|| / ((||A|| + |lambda| ||B||) ||x||) = " +
+                   std::to_string(mr) + " > 0.1 * tol (the factorisation of A - sigma*B is less accurate than the refinement probe estimated)";
+    }
     statuses[b] = des[b].status;
     errs[b] = des[b].err;
     if (des[b].lambda.size() == (size_t)des[b].k) std::copy(des[b].lambda.begin(), des[b].lambda.end(), eigvals[b]);
@@ -684,8 +698,6 @@ static void solve_forest(plfem_ctx* ctx, int nb, plfem_problem* const* pbs, cons
     s->n_restart = des[b].n_restart; s->n_block_op = des[b].n_block_op;
     s->n_fronts = P.nfronts; s->n_levels = P.nlevels; s->max_front_nodes = P.max_front;
     s->factor_entries = P.factor_entries; s->front_pool_doubles = P.foff[P.nfronts]; s->factor_flops = P.factor_flops;
-    double mr = 0.0;
-    for (size_t i = 0; i + 1 < resid[b].size(); i += 2) mr = std::max(mr, resid[b][i] / (resid[b][i + 1] + 1e-300));
     s->max_residual = mr;
     s->ms_symbolic = (float)ms_sym[b];
     s->ms_assemble = ms_asm; s->ms_factor = ms_fac; s->ms_lanczos = ms_lan; s->ms_metrics = ms_met;
@@ -693,6 +705,7 @@ static void solve_forest(plfem_ctx* ctx, int nb, plfem_problem* const* pbs, cons
     s->kernel_launches = ctx->launches;
     s->batch_size = nb; s->batch_block_ops = er.n_block_op; s->ms_symbolic_wall = (float)(t1 - t0);
     s->refine_steps = single_vector ? refine : er.refine_steps;
+    s->probe_rho = des[b].solve_residual;
   }
 }
 

@@ -31,7 +31,7 @@ def test_struct_layouts_match_header(tmp_path):
     assert ctypes.sizeof(_cabi.MeshInfo) == 64
     assert ctypes.sizeof(_cabi.Material) == 64
     assert ctypes.sizeof(_cabi.SolveOpts) == 64
-    assert ctypes.sizeof(_cabi.SolveStats) == 104
+    assert ctypes.sizeof(_cabi.SolveStats) == 112
     gcc = shutil.which("gcc")
     if gcc is None:
         pytest.skip("no C compiler")
