@@ -46,8 +46,6 @@ const char* plfem_last_error(const plfem_ctx* ctx);
 /* host threads the symbolic analysis of ONE call (a solve, or a whole forest) may use (0 = default: min(cores, 8) for a
  * single solve, every core for a forest); lower it when several contexts / processes share the host */
 void plfem_set_host_threads(int n);
-/* CTAs per SM of the persistent operator kernel (default 4); use 8 / (contexts sharing the GPU), at least 1 */
-void plfem_ctx_set_coop_ctas(plfem_ctx* ctx, int ctas_per_sm);
 /* abi / build identification: "plfem <version> sm_100a" */
 const char* plfem_version(void);
 

@@ -34,7 +34,7 @@ SYMBOLS = ["plfem_ctx_create", "plfem_ctx_destroy", "plfem_last_error", "plfem_v
            "plfem_problem_create", "plfem_problem_destroy", "plfem_problem_info", "plfem_problem_dofs",
            "plfem_quad_points", "plfem_assemble", "plfem_export_csr", "plfem_spmv_csr", "plfem_solve_modes",
            "plfem_plan_sizes", "plfem_plan_export", "plfem_debug_symeig", "plfem_profile_kernels", "plfem_set_host_threads",
-           "plfem_debug_solve", "plfem_ctx_set_coop_ctas", "plfem_solve_modes_batch", "plfem_profile_last", "plfem_host_alloc", "plfem_host_free"]
+           "plfem_debug_solve", "plfem_solve_modes_batch", "plfem_profile_last", "plfem_host_alloc", "plfem_host_free"]
 
 
 class MeshInfo(C.Structure):
@@ -115,8 +115,6 @@ def load():
         lib.plfem_plan_export.argtypes = [vp] + [p_i32] * 9 + [p_i64]
         lib.plfem_debug_symeig.argtypes = [c_i32, p_f64, p_f64]
         lib.plfem_debug_solve.argtypes = [vp, c_f64, p_f64, p_f64, C.c_int]
-        lib.plfem_ctx_set_coop_ctas.argtypes = [vp, C.c_int]
-        lib.plfem_ctx_set_coop_ctas.restype = None
         lib.plfem_set_host_threads.argtypes = [C.c_int]
         lib.plfem_set_host_threads.restype = None
         lib.plfem_profile_kernels.argtypes = [vp, C.POINTER(Material), c_f64, C.c_int, p_f64, p_f64]
@@ -202,9 +200,6 @@ class Context:
         if device not in cls._cache:
             cls._cache[device] = cls(device)
         return cls._cache[device]
-
-    def set_coop_ctas(self, ctas_per_sm: int):
-        self.lib.plfem_ctx_set_coop_ctas(self.handle, int(ctas_per_sm))
 
     def check(self, st: int):
         if st != 0:

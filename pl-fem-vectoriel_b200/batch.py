@@ -170,8 +170,6 @@ class SolverPool:
             self._local.ctx = _cabi.Context(self.device)     # a fresh context: own stream + arena
             with self._ctx_lock:
                 self._contexts.append(self._local.ctx)
-            # persistent operator kernels of all workers must be co-resident: share the 8 CTA slots per SM
-            self._local.ctx.set_coop_ctas(max(1, min(4, 8 // max(self.workers, 1))))
         return self._local.ctx
 
     def _solve(self, job):

@@ -220,8 +220,6 @@ const char* plfem_version(void) { return "plfem 0.1 sm_100a"; }
 
 void plfem_set_host_threads(int n) { plfem::set_host_threads(n); }
 
-void plfem_ctx_set_coop_ctas(plfem_ctx* ctx, int ctas_per_sm) { if (ctx) ctx->coop_ctas_per_sm = std::max(1, ctas_per_sm); }
-
 int plfem_ctx_create(int device, plfem_ctx** out) {
   if (!out) return PLFEM_ERR_INVALID;
   *out = nullptr;
@@ -646,7 +644,7 @@ static void solve_forest(plfem_ctx* ctx, int nb, plfem_problem* const* pbs, cons
   PLFEM_CUDA(cudaEventRecord(ctx->ev[3], st));
   W.dplan.status.download(fstat, 4);
   PLFEM_CUDA(stream_wait(st));
-  if (fstat[1]) throw StatusError(PLFEM_ERR_INTERNAL, "operator kernel: a dependency wait timed out");
+  if (fstat[1]) throw StatusError(PLFEM_ERR_INTERNAL, "a sweep kernel gave up waiting for a bulk copy of its factor stream");
 
   // -- per-mode reductions + eigenvectors in reference ordering, design by design ---------------------------
   std::vector<std::vector<double>> resid(nb);
@@ -857,15 +855,12 @@ int plfem_debug_solve(plfem_problem* pb, double sigma, const double* b, double* 
     for (int64_t r = 0; r < n; ++r) { const int32_t ip = pb->plan.perm[r]; hb[2 * r] = b[ip]; hb[2 * r + 1] = b[n + ip]; }
     DevBuf<double> db, dx, dt, dd;
     db.upload(ctx, hb); dx.alloc(ctx, m); dt.alloc(ctx, m); dd.alloc(ctx, m);
-    if (refine >= 100) {   // refine = 100 + r: exercise the per-level kernels instead of the persistent one
-      run_solve(ctx, W.dplan, db.p, dx.p);
-      for (int it = 0; it < refine - 100; ++it) {
-        launch_resid_k(ctx, W.dpat, W.d_vals.p, W.d_sigma.p, dx.p, db.p, dt.p);
-        run_solve(ctx, W.dplan, dt.p, dd.p);
-        launch_axpy(ctx, dx.p, dd.p, m);
-      }
-    } else {
-      run_operator(ctx, W.dpat, W.dplan, W.d_vals.p, W.d_sigma.p, db.p, dx.p, dt.p, dd.p, refine, ctx->coop_ctas_per_sm);
+    const int steps = refine >= 100 ? refine - 100 : refine;     // (100 + r is accepted for old callers)
+    run_solve(ctx, W.dplan, db.p, dx.p);
+    for (int it = 0; it < steps; ++it) {
+      launch_resid_k(ctx, W.dpat, W.d_vals.p, W.d_sigma.p, dx.p, db.p, dt.p);
+      run_solve(ctx, W.dplan, dt.p, dd.p);
+      launch_axpy(ctx, dx.p, dd.p, m);
     }
     dx.download(hx.data(), m);
     PLFEM_CUDA(stream_wait(ctx->stream));

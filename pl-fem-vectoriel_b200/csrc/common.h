@@ -84,7 +84,6 @@ struct plfem_ctx {
   std::string err;
   plfem::DeviceArena arena;
   int launches = 0;          // kernels launched since the counter was last reset
-  int coop_ctas_per_sm = 4;  // grid of the persistent operator kernel (lower it when several contexts share the GPU)
   cudaEvent_t ev[8] = {};
   std::shared_ptr<plfem::SolveWork> last_work;   // what the last solve left on the device (measurement hook)
   void* pinned = nullptr;    // pinned staging buffer for small device->host reads
@@ -181,19 +180,25 @@ struct BwdItem {
   int64_t foff, g0;                      // offset of the W copy, first unknown of the front
 };
 
-// Throughput path of the sweeps: one WARP per task, no CTA-wide synchronisation.  A forward task is a chunk of
-// <= 128 rows of a front's packed left block column [F11^-1 ; W^T] (lanes over rows), a backward task the
-// <= 128 pivot columns of a front against its row-major copy of W (lanes over pivot columns): both are
-// coalesced matrix-vector products with the contraction index staged through shared memory in tiles.
-struct FwdTask {
-  int32_t s2, rows, r0, nr;              // pivot unknowns, rows of the front, first row / rows of this chunk
-  int32_t ldp, goff, uoff, nch;          // panel leading dimension, gather tables, update-vector offset, children
-  int64_t lo, g0;                        // panel offset, first unknown of the front
+// ---- TMA-streamed bottom subtrees of the sweeps (sweep_stream.cu) --------------------------------------------------
+constexpr int ST_CHUNK_DOUBLES = 512;   // one bulk copy / ring stage: 4 KB
+constexpr int ST_NLOC = 320;            // unknowns of a subtree's local vector: its pivots + the update set of its root
+struct StreamSub {                      // one bottom subtree = one warp
+  int64_t foff, boff;                   // chunk-aligned offsets (doubles) of its forward / backward stream
+  int32_t fchunks, bchunks;
+  int32_t nfronts, front0;              // its fronts (post-order) in the descriptor array
+  int32_t g0, nI, next;                 // first unknown of its contiguous pivot range, pivot unknowns, unknowns of the root's update set
+  int32_t uoff, soff;                   // the root's update vector in the update pool, the root's update set in strct
+  int32_t pad;
 };
-struct BwdTask {
-  int32_t s2, u2, c0, nc;                // pivot / update unknowns, first column / columns of this chunk
-  int32_t s2p, soff, pad0, pad1;         // leading dimension of the W copy, offset of the update set in strct
-  int64_t wo, g0;                        // offset of the W copy, first unknown of the front
+struct StreamPackRec {                  // where one front of a subtree starts in the two streams (cursor before its items)
+  int32_t f, sub, fchunk, fpos, bchunk, bpos, lm_off, pad;
+};
+struct StreamPlan {
+  int n_subs = 0, n_fronts = 0;
+  int64_t fwd_doubles = 0, bwd_doubles = 0;   // stream lengths including chunk padding
+  DevBuf<StreamSub> subs; DevBuf<int4> fronts; DevBuf<StreamPackRec> recs; DevBuf<uint16_t> lmaps;
+  DevBuf<double> sfwd, sbwd;
 };
 
 struct DevPlan {
@@ -201,22 +206,18 @@ struct DevPlan {
   DevBuf<int32_t> first, s, sptr, strct, sn_of, parent, cptr, child, cmap_ptr, cmap, lfront;
   DevBuf<int64_t> foff;
   DevBuf<int32_t> uoff;              // offset of each front's update vector (in doubles)
-  // persistent operator kernel: backward queue (levels descending), slabs per front, completion counters
-  DevBuf<BwdItem> bwd_q; DevBuf<int32_t> fdone, bdone, nfs;
-  int n_fwd = 0, n_bwd = 0, epoch = 0;
   std::vector<int32_t> lptr;         // host copy of the level schedule
   std::vector<int32_t> lmax_m;       // largest pivot block (unknowns) per level
   std::vector<int32_t> lsplit, lmax_small;   // per level: fronts with a pivot block <= 64 unknowns (listed first in lfront), their largest block
   // per-level work lists (host-built): tiles for the two GEMMs, slabs for extend-add and the sweeps
   DevBuf<int4> w_tiles, s_tiles, ea_slabs;
-  DevBuf<FwdItem> fwd_items; DevBuf<BwdItem> bwd_items; DevBuf<int32_t> gsrc;
+  DevBuf<int32_t> gsrc;
   std::vector<int32_t> w_ptr, s_ptr, ea_ptr, fwd_ptr, bwd_ptr;  // [nlevels+1] each
   // per-level launch lists (CTA items of the fronts above the bottom subtrees) + the subtrees' warp tasks
   DevBuf<FwdItem> fwdb_items; DevBuf<BwdItem> bwdb_items;
   std::vector<int32_t> fwdb_ptr, bwdb_ptr;     // [nlevels+1] each
-  DevBuf<FwdTask> fwd_tasks; DevBuf<BwdTask> bwd_tasks;
-  DevBuf<int2> subs; DevBuf<int32_t> sub_fptr, sub_bptr;   // per subtree: {first level range, levels}; task ranges per level
-  int n_subs = 0;
+  StreamPlan st;                     // bottom subtrees: TMA-streamed, one warp each
+  DevBuf<uint8_t> in_sub;            // front covered by a bottom subtree
   DevBuf<int64_t> lo, wo; DevBuf<int32_t> ldp; // packed panels: [F11^-1 ; W^T] (ldp x 2s) and W row-major (s2p x 2u)
   DevBuf<double> fac;                // packed factor panels: the only matrix data the sweeps read
   DevBuf<double> pool;               // all frontal matrices (factorisation workspace)
@@ -225,6 +226,10 @@ struct DevPlan {
   int64_t upd_len = 0;
 };
 void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D);
+void build_stream_plan(plfem_ctx* ctx, const FrontPlan& P, const std::vector<int32_t>& uoff, std::vector<uint8_t>& in_sub, StreamPlan& S);
+void launch_stream_pack(plfem_ctx* ctx, const DevPlan& D);
+void launch_stream_forward(plfem_ctx* ctx, const DevPlan& D, const double* rhs, double* out, int nrhs, bool pdl);
+void launch_stream_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs, bool pdl);
 // d_sigma_node: the shift of the design each (permuted) node belongs to — a forest of designs is one problem
 void launch_front_load(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, const double* d_sigma_node);
 void run_factorization(plfem_ctx* ctx, const DevPlan& D);
@@ -232,8 +237,6 @@ void run_factorization(plfem_ctx* ctx, const DevPlan& D);
 // with nrhs = SOLVE_NRHS the right-hand sides are interleaved: entry i of right-hand side r at b[i * nrhs + r]
 constexpr int SOLVE_NRHS = 4;   // block size of the multi-right-hand-side sweeps (block Lanczos)
 void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x, int nrhs = 1);
-void run_operator(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, const double* d_sigma_node, const double* b,
-                  double* x, double* rt, double* rdx, int refine, int ctas_per_sm);
 void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double* z, int nrhs = 1);
 void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs = 1);
 

@@ -605,11 +605,7 @@ void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const do
   // linear operator, which is what Lanczos needs).  The whole application — 2 sweeps x levels x
   // (1 + refine) launches — is captured once into a CUDA graph on fixed buffers (opin -> r) and
   // replayed, so the CPU issues one launch per operator application instead of ~70.
-  // Two ways to issue it: "graph" (default) = the per-level kernels captured once into a CUDA graph and
-  // replayed; "coop" (PLFEM_OP_MODE=coop) = one persistent cooperative kernel per application whose CTAs
-  // walk a dependency-ordered queue (dataflow).  Measured on B200 (config 1): equal for one solve alone,
-  // the graph is ~20 % faster with 8 solves in flight (spinning CTAs of 8 persistent kernels compete).
-  static const bool use_graph = [] { const char* e = std::getenv("PLFEM_OP_MODE"); return !(e && std::string(e) == "coop"); }();
+  const bool use_graph = true;
   DevBuf<double> opin;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
@@ -645,8 +641,6 @@ void run_eigensolver(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const do
       PLFEM_CUDA(cudaMemcpyAsync(opin.p, bvec, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
       PLFEM_CUDA(cudaGraphLaunch(gexec, st));
       ctx->launches += graph_nodes;
-    } else {
-      run_operator(ctx, pat, D, d_vals, d_sigma_node, bvec, r.p, rt.p, rdx.p, refine_steps, ctx->coop_ctas_per_sm);
     }
   };
 

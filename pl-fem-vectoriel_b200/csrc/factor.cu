@@ -16,8 +16,6 @@
 // position maps: gather-only, fixed order, no atomics, bit-reproducible run to run.
 #include "common.h"
 
-#include <cooperative_groups.h>
-
 #include <algorithm>
 #include <cstdlib>
 
@@ -712,188 +710,6 @@ __device__ __forceinline__ void backward_item(const BwdItem& it, const PlanView&
   else backward_item_r<CG, NR, 1, PDL>(it, P, x, sm, dp);
 }
 
-// ---- warp-per-task sweeps for SMALL fronts -------------------------------------------------------------------
-// The CTA-cooperative items above minimise the latency of one large front (k-split, everything prefetched) and are
-// what the top of the tree needs.  The bottom of the tree — most fronts of a design, and thousands per launch in a
-// forest of designs — are small: a CTA of 256 mostly idle threads per front wastes the SM's thread slots and the
-// launch ends up bound by CTA turnover, not by memory.  A small front is served by one WARP per task instead, which
-// never synchronises with another warp: a forward task is a chunk of 32*R rows of the packed left block column
-// [F11^-1 ; W^T] (lanes over rows), a backward task 32*R pivot columns against the row-major copy of W (lanes over
-// pivot columns); both are coalesced matrix-vector products whose contraction index is staged through shared
-// memory in tiles, with 16 factor entries per lane in flight.  Which path a front takes depends only on its own
-// size, so a design gives bit-identical results alone and inside a forest.
-constexpr int KT = 64;     // contraction-index tile staged in shared memory (per warp)
-
-// acc += M[:, 0..kn) * vs[0..kn): 8 factor entries per lane in flight; `pre` holds the first batch when PRE
-template <int NR, int R, bool PRE>
-__device__ __forceinline__ void warp_gemv_tile(const double* __restrict__ Mk, int64_t ldm, int kn, const bool (&valid)[R],
-                                               const double (*vs)[NR], double (&acc)[R][NR], const double (&pre)[8 / R][R]) {
-  constexpr int U = 8 / R;
-  for (int kk0 = 0; kk0 < kn; kk0 += U) {
-    double m[U][R];
-    if (PRE && kk0 == 0) {
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int q = 0; q < R; ++q) m[u][q] = pre[u][q];
-    } else {
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int q = 0; q < R; ++q) m[u][q] = (kk0 + u < kn && valid[q]) ? Mk[(int64_t)(kk0 + u) * ldm + 32 * q] : 0.0;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (kk0 + u < kn) {
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-          const double y = vs[kk0 + u][r];
-#pragma unroll
-          for (int q = 0; q < R; ++q) acc[q][r] = fma(m[u][q], y, acc[q][r]);
-        }
-      }
-    }
-  }
-}
-
-template <int NR, int R, bool PDL>
-__device__ __forceinline__ void forward_task(const FwdTask& t, const int32_t* __restrict__ gsrc, const double* __restrict__ fac,
-                                             const RhsView& rv, double (*ys)[NR], int lane) {
-  constexpr int U = 8 / R;
-  const int s2 = t.s2, nf2 = t.rows;
-  const int64_t ldp = t.ldp;
-  const int32_t* g = gsrc + t.goff;
-  const double* L = fac + t.lo + t.r0 + lane;
-  bool valid[R];
-#pragma unroll
-  for (int q = 0; q < R; ++q) valid[q] = lane + 32 * q < t.nr;
-  // static prefetch: the first batch of factor entries is on its way before the inputs are touched
-  double pre[U][R];
-#pragma unroll
-  for (int u = 0; u < U; ++u)
-#pragma unroll
-    for (int q = 0; q < R; ++q) pre[u][q] = (u < s2 && valid[q]) ? L[(int64_t)u * ldp + 32 * q] : 0.0;
-  if (PDL) griddep_wait();                 // the previous level is complete and visible from here on
-  double acc[R][NR];
-#pragma unroll
-  for (int q = 0; q < R; ++q)
-#pragma unroll
-    for (int r = 0; r < NR; ++r) acc[q][r] = 0.0;
-  for (int k0 = 0; k0 < s2; k0 += KT) {
-    const int kn = min(KT, s2 - k0);
-    // right-hand side + children's updates of the pivot unknowns k0.., fixed order (rhs + child 0) + child 1 ...
-    for (int h = lane; h < kn; h += 32) {
-      const int k = k0 + h;
-      double v[NR], w[NR];
-      ldv<false, NR>(rv.rhs, t.g0 + k, v);
-      for (int c = 0; c < t.nch; ++c) {
-        const int i = g[c * nf2 + k];
-        if (i >= 0) {
-          ldv<false, NR>(rv.upd, i, w);
-#pragma unroll
-          for (int r = 0; r < NR; ++r) v[r] += w[r];
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < NR; ++r) ys[h][r] = v[r];
-    }
-    __syncwarp();
-    if (k0 == 0) warp_gemv_tile<NR, R, true>(L, ldp, kn, valid, ys, acc, pre);
-    else warp_gemv_tile<NR, R, false>(L + (int64_t)k0 * ldp, ldp, kn, valid, ys, acc, pre);
-    __syncwarp();
-  }
-#pragma unroll
-  for (int q = 0; q < R; ++q) {
-    if (!valid[q]) continue;
-    const int row = t.r0 + lane + 32 * q;
-    if (row < s2) {
-      stv<NR>(rv.out, t.g0 + row, acc[q]);
-    } else {
-      double yt[NR], w[NR];
-#pragma unroll
-      for (int r = 0; r < NR; ++r) yt[r] = 0.0;
-      for (int c = 0; c < t.nch; ++c) {
-        const int i = g[c * nf2 + row];
-        if (i >= 0) {
-          ldv<false, NR>(rv.upd, i, w);
-#pragma unroll
-          for (int r = 0; r < NR; ++r) yt[r] += w[r];
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < NR; ++r) yt[r] -= acc[q][r];
-      stv<NR>(rv.upd, (int64_t)t.uoff + (row - s2), yt);
-    }
-  }
-}
-
-template <int NR, int R, bool PDL>
-__device__ __forceinline__ void backward_task(const BwdTask& t, const int32_t* __restrict__ strct, const double* __restrict__ fac,
-                                              double* x, double (*xs)[NR], int lane) {
-  constexpr int U = 8 / R;
-  const int u2 = t.u2;
-  const int64_t s2p = t.s2p;
-  const int32_t* st = strct + t.soff;
-  const double* W = fac + t.wo + t.c0 + lane;
-  bool valid[R];
-#pragma unroll
-  for (int q = 0; q < R; ++q) valid[q] = lane + 32 * q < t.nc;
-  double pre[U][R];
-#pragma unroll
-  for (int u = 0; u < U; ++u)
-#pragma unroll
-    for (int q = 0; q < R; ++q) pre[u][q] = (u < u2 && valid[q]) ? W[(int64_t)u * s2p + 32 * q] : 0.0;
-  // gather offsets of the first tile are static too
-  int64_t o0 = -1, o1 = -1;
-  if (lane < u2) o0 = 2 * (int64_t)st[lane >> 1] + (lane & 1);
-  if (lane + 32 < u2) o1 = 2 * (int64_t)st[(lane + 32) >> 1] + (lane & 1);
-  if (PDL) griddep_wait();
-  double acc[R][NR];
-#pragma unroll
-  for (int q = 0; q < R; ++q)
-#pragma unroll
-    for (int r = 0; r < NR; ++r) acc[q][r] = 0.0;
-  for (int j0 = 0; j0 < u2; j0 += KT) {
-    const int jn = min(KT, u2 - j0);
-    if (j0 == 0) {
-      if (o0 >= 0) {
-        double v[NR];
-        ldv<false, NR>(x, o0, v);
-#pragma unroll
-        for (int r = 0; r < NR; ++r) xs[lane][r] = v[r];
-      }
-      if (o1 >= 0) {
-        double v[NR];
-        ldv<false, NR>(x, o1, v);
-#pragma unroll
-        for (int r = 0; r < NR; ++r) xs[lane + 32][r] = v[r];
-      }
-    } else {
-      for (int h = lane; h < jn; h += 32) {
-        const int j = j0 + h;
-        const int64_t o = 2 * (int64_t)st[j >> 1] + (j & 1);
-        double v[NR];
-        ldv<false, NR>(x, o, v);
-#pragma unroll
-        for (int r = 0; r < NR; ++r) xs[h][r] = v[r];
-      }
-    }
-    __syncwarp();
-    if (j0 == 0) warp_gemv_tile<NR, R, true>(W, s2p, jn, valid, xs, acc, pre);
-    else warp_gemv_tile<NR, R, false>(W + (int64_t)j0 * s2p, s2p, jn, valid, xs, acc, pre);
-    __syncwarp();
-  }
-#pragma unroll
-  for (int q = 0; q < R; ++q) {
-    if (!valid[q]) continue;
-    double v[NR];
-    ldv<false, NR>(x, t.g0 + t.c0 + lane + 32 * q, v);
-#pragma unroll
-    for (int r = 0; r < NR; ++r) v[r] -= acc[q][r];
-    stv<NR>(x, t.g0 + t.c0 + lane + 32 * q, v);
-  }
-}
-
 // large fronts: one CTA-cooperative item per CTA
 template <int NR, bool PDL>
 __global__ void __launch_bounds__(256, 4) forward_kernel(const FwdItem* __restrict__ items, const int32_t* __restrict__ gsrc, PlanView P,
@@ -912,56 +728,14 @@ __global__ void __launch_bounds__(256, 4) backward_kernel(const BwdItem* __restr
   backward_item<false, NR, PDL>(items[blockIdx.x], P, x, sm, none);
 }
 
-// Bottom of the elimination forest: ONE CTA per subtree of small fronts (the fronts below level `subtree_levels`).  The
-// 8 warps run the warp tasks of the subtree level by level — leaves first on the way up, the subtree's root first on the
-// way down — with a CTA barrier between levels: the update vectors / unknowns a level produces are consumed by the same
-// CTA (global memory, visible after the barrier), so levels 0..H-1 of a sweep cost one launch instead of H, and the
-// dependent round trips of a small front overlap with those of its siblings and cousins in the same CTA.
-// sub[b] = {first entry of the subtree's level ranges in ptr, number of levels}; tasks of level l: ptr[o+l] .. ptr[o+l+1].
-template <int NR, bool PDL>
-__global__ void __launch_bounds__(256, 4) forward_subtree_kernel(const int2* __restrict__ sub, const int32_t* __restrict__ ptr,
-                                                                  const FwdTask* __restrict__ tasks, const int32_t* __restrict__ gsrc,
-                                                                  const double* __restrict__ fac, RhsView rv) {
-  __shared__ __align__(16) double tile[8][KT][NR];
-  if (PDL) griddep_launch_dependents();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int2 sb = sub[blockIdx.x];
-  for (int l = 0; l < sb.y; ++l) {
-    const int t1 = ptr[sb.x + l + 1];
-    for (int id = ptr[sb.x + l] + warp; id < t1; id += 8) {
-      const FwdTask t = tasks[id];
-      if (t.nr <= 32) forward_task<NR, 1, PDL>(t, gsrc, fac, rv, tile[warp], lane);
-      else forward_task<NR, 2, PDL>(t, gsrc, fac, rv, tile[warp], lane);
-    }
-    if (l + 1 < sb.y) __syncthreads();
-  }
-}
-
-template <int NR, bool PDL>
-__global__ void __launch_bounds__(256, 4) backward_subtree_kernel(const int2* __restrict__ sub, const int32_t* __restrict__ ptr,
-                                                                   const BwdTask* __restrict__ tasks, const int32_t* __restrict__ strct,
-                                                                   const double* __restrict__ fac, double* x) {
-  __shared__ __align__(16) double tile[8][KT][NR];
-  if (PDL) griddep_launch_dependents();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int2 sb = sub[blockIdx.x];
-  for (int l = sb.y - 1; l >= 0; --l) {
-    const int t1 = ptr[sb.x + l + 1];
-    for (int id = ptr[sb.x + l] + warp; id < t1; id += 8) {
-      const BwdTask t = tasks[id];
-      if (t.nc <= 32) backward_task<NR, 1, PDL>(t, strct, fac, x, tile[warp], lane);
-      else backward_task<NR, 2, PDL>(t, strct, fac, x, tile[warp], lane);
-    }
-    if (l > 0) __syncthreads();
-  }
-}
-
 // ---- pack: the solve phase reads only the left block column of a front (and W a second time, row-major) ----
 // Copy both into dense, 32-byte aligned panels; the front pool is factorisation workspace only.
 __global__ void __launch_bounds__(256) pack_kernel(PlanView P, const int64_t* __restrict__ lo, const int64_t* __restrict__ wo,
-                                                   const int32_t* __restrict__ ldp, double* __restrict__ fac) {
+                                                   const int32_t* __restrict__ ldp, const uint8_t* __restrict__ in_sub,
+                                                   double* __restrict__ fac) {
   __shared__ double tile[32][33];
   const int f = blockIdx.x;
+  if (in_sub[f]) return;          // packed into the streams of the bottom subtrees instead
   const int s2 = 2 * P.s[f], u2 = 2 * front_u(P, f);
   const int64_t ld = s2 + u2, lp = ldp[f];
   const double* src = P.pool + P.foff[f];
@@ -987,91 +761,6 @@ __global__ void __launch_bounds__(256) pack_kernel(PlanView P, const int64_t* __
     }
 }
 
-// ---- persistent operator kernel: x = refine((A - sigma B)^-1 b) in ONE cooperative launch ----------------
-// As separate launches (even inside a CUDA graph) every step of a sweep pays the launch/drain gap, and with
-// several designs in flight the GPU front end becomes the limiter (~3 us per kernel node).  Here a
-// co-resident grid runs the whole operator application: items sit in one queue ordered children-before-
-// parents; CTA b takes items b, b+G, b+2G... in order and, instead of a grid-wide barrier per level, waits
-// only for the fronts it depends on (per-front completion counters in global memory, dataflow).  Items a CTA
-// waits for always precede it in the queue and every CTA is resident (cooperative launch), so the wait
-// cannot deadlock; a spin limit turns a bug into an error flag instead of a hung GPU.  Grid barriers remain
-// only around the refinement SpMV.
-struct OpArgs {
-  PlanView P;
-  const FwdItem* fwd_q; const BwdItem* bwd_q;   // forward queue (levels ascending), backward queue (levels descending)
-  const int32_t* gsrc;
-  int n_fwd, n_bwd;
-  int32_t* fdone; int32_t* bdone; int32_t* status; const int32_t* nfs;
-  int epoch0;                                 // sweeps completed before this launch
-  const double* b; double* x; double* upd;   // b and x: length 2n, permuted interleaved layout
-  double* rt; double* rdx;                    // refinement work vectors
-  int refine;
-  int32_t n; const int32_t* rowptr; const int32_t* col; const double* vals; int64_t nnz; const double* sigma_node;
-};
-
-union OpSmem {
-  SweepSmem<1> f;
-  BwdSmem<1> b;
-};
-
-__device__ __forceinline__ void sweep_dataflow(const OpArgs& a, const double* rhs, double* out, int epoch, OpSmem& sm) {
-  const Deps dp{a.fdone, a.bdone, a.status, epoch, a.nfs};
-  const RhsView rv{rhs, out, a.upd};
-  for (int i = blockIdx.x; i < a.n_fwd; i += gridDim.x) {
-    const FwdItem it = a.fwd_q[i];
-    forward_item<true, 1>(it, a.gsrc, a.P, rv, sm.f, dp);
-    __threadfence();
-    __syncthreads();                       // all writes of the item are fenced; shared memory is free again
-    if (threadIdx.x == 0) atomicAdd(a.fdone + it.f, 1);
-  }
-  for (int i = blockIdx.x; i < a.n_bwd; i += gridDim.x) {
-    const BwdItem it = a.bwd_q[i];
-    backward_item<true, 1>(it, a.P, out, sm.b, dp);
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(a.bdone + it.f, 1);
-  }
-}
-
-__global__ void __launch_bounds__(256) op_kernel(OpArgs a) {
-  __shared__ OpSmem sm;
-  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
-  sweep_dataflow(a, a.b, a.x, a.epoch0 + 1, sm);
-  for (int r = 0; r < a.refine; ++r) {
-    grid.sync();                            // x complete everywhere
-    // rt = b - K x, four threads per row
-    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-    const int l32 = threadIdx.x & 31;       // whole warps stay in the loop together: the shuffles below use the full mask
-    for (int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; gid - l32 < 4 * (int64_t)a.n; gid += nthreads) {
-      const int64_t row = gid >> 2;
-      const int lane = (int)(gid & 3);
-      double ax = 0.0, ay = 0.0;
-      if (row < a.n) {
-        const double sig = a.sigma_node[row];
-        for (int32_t z = a.rowptr[row] + lane; z < a.rowptr[row + 1]; z += 4) {
-          const double smv = sig * a.vals[(int64_t)S_MINV * a.nnz + z];
-          const double* xp = a.x + 2 * (int64_t)a.col[z];
-          const double vx = __ldcg(xp), vy = __ldcg(xp + 1);
-          ax = fma(a.vals[(int64_t)S_AXX * a.nnz + z] - smv, vx, ax);
-          ax = fma(a.vals[(int64_t)S_AXY * a.nnz + z], vy, ax);
-          ay = fma(a.vals[(int64_t)S_AYX * a.nnz + z], vx, ay);
-          ay = fma(a.vals[(int64_t)S_AYY * a.nnz + z] - smv, vy, ay);
-        }
-      }
-      ax += __shfl_down_sync(0xffffffffu, ax, 2, 4); ay += __shfl_down_sync(0xffffffffu, ay, 2, 4);
-      ax += __shfl_down_sync(0xffffffffu, ax, 1, 4); ay += __shfl_down_sync(0xffffffffu, ay, 1, 4);
-      if (row < a.n && lane == 0) {
-        a.rt[2 * row] = a.b[2 * row] - ax;
-        a.rt[2 * row + 1] = a.b[2 * row + 1] - ay;
-      }
-    }
-    grid.sync();                            // rt complete
-    sweep_dataflow(a, a.rt, a.rdx, a.epoch0 + 2 + r, sm);
-    grid.sync();                            // rdx complete
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < 2 * (int64_t)a.n; i += nthreads) a.x[i] = __ldcg(a.x + i) + __ldcg(a.rdx + i);
-  }
-}
-
 PlanView view(const DevPlan& D);
 PlanView sweep_view(const DevPlan& D) {   // the sweeps read the packed panels, never the front pool
   PlanView v = view(D);
@@ -1090,12 +779,6 @@ PlanView view(const DevPlan& D) {
 
 
 }  // namespace
-
-// fronts with at most this many pivot / update unknowns take the warp-per-task path of the sweeps (0: none does)
-int small_front_limit(const char* env, int dflt) {
-  const char* e = std::getenv(env);
-  return e ? std::max(0, atoi(e)) : dflt;
-}
 
 void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
   if (2 * P.max_s > MAX_PIV) throw StatusError(PLFEM_ERR_INVALID, "max_sn_nodes must be <= 64");
@@ -1124,7 +807,12 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
   D.uoff.upload(ctx, uoff);
   D.upd.alloc(ctx, (size_t)SOLVE_NRHS * std::max<int64_t>(D.upd_len, 1));
 
-  // packed panels of the solve phase
+  // bottom subtrees: TMA-streamed, one warp each (sweep_stream.cu); everything above them: one launch per level
+  std::vector<uint8_t> in_sub;
+  build_stream_plan(ctx, P, uoff, in_sub, D.st);
+  D.in_sub.upload(ctx, in_sub);
+
+  // packed panels of the solve phase (fronts above the bottom subtrees)
   std::vector<int64_t> lo(P.nfronts + 1, 0), wo(P.nfronts, 0);
   std::vector<int32_t> ldp(P.nfronts, 0);
   {
@@ -1132,30 +820,26 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
     for (int f = 0; f < P.nfronts; ++f) {
       const int64_t s2 = 2 * (int64_t)P.s[f], u2 = 2 * (int64_t)(P.sptr[f + 1] - P.sptr[f]);
       ldp[f] = (int32_t)((s2 + u2 + 3) & ~int64_t(3));
-      lo[f] = off; off += (int64_t)ldp[f] * s2;
-      wo[f] = off; off += ((s2 + 3) & ~int64_t(3)) * u2;
+      lo[f] = off; if (!in_sub[f]) off += (int64_t)ldp[f] * s2;
+      wo[f] = off; if (!in_sub[f]) off += ((s2 + 3) & ~int64_t(3)) * u2;
     }
     lo[P.nfronts] = off;
     D.fac.alloc(ctx, (size_t)std::max<int64_t>(off, 1));
     D.lo.upload(ctx, lo); D.wo.upload(ctx, wo); D.ldp.upload(ctx, ldp);
   }
   std::vector<int4> wt, stl, ea;
-  std::vector<FwdItem> fw; std::vector<BwdItem> bw;
   std::vector<FwdItem> fwb; std::vector<BwdItem> bwb;     // per-level launches: CTA items of the fronts above the subtrees
   D.fwdb_ptr.assign(P.nlevels + 1, 0); D.bwdb_ptr = D.fwdb_ptr;
-  // The fronts below level H (PLFEM_SUBTREE_LEVELS, default 1: the leaves — hundreds per design, ~75 x 30 entries each; a
-  // 256-thread CTA per leaf is bound by CTA turnover) are served by warp tasks, one CTA per maximal subtree of such fronts.
-  const int H = small_front_limit("PLFEM_SUBTREE_LEVELS", 1);
-  auto in_sub = [&](int f) { return P.level[f] < H; };
-  D.w_ptr.assign(P.nlevels + 1, 0); D.s_ptr = D.ea_ptr = D.fwd_ptr = D.bwd_ptr = D.w_ptr;
+  D.w_ptr.assign(P.nlevels + 1, 0); D.s_ptr = D.ea_ptr = D.w_ptr;
   D.lmax_m.assign(P.nlevels, 0);
-  // flattened child -> parent gather: per front, for every front row (2nf unknowns) the offset into the
+  // flattened child -> parent gather: per front above the subtrees, for every front row (2nf unknowns) the offset into the
   // update-vector pool it receives from the first and from the second child (-1 = nothing)
   std::vector<int32_t> goff(P.nfronts + 1, 0);
   for (int f = 0; f < P.nfronts; ++f)   // one table per child, at least two (the CTA path reads two unconditionally)
-    goff[f + 1] = goff[f] + 2 * std::max(2, P.cptr[f + 1] - P.cptr[f]) * (P.s[f] + P.sptr[f + 1] - P.sptr[f]);
+    goff[f + 1] = goff[f] + (in_sub[f] ? 0 : 2 * std::max(2, P.cptr[f + 1] - P.cptr[f]) * (P.s[f] + P.sptr[f + 1] - P.sptr[f]));
   std::vector<int32_t> gsrc(goff[P.nfronts], -1);
   for (int f = 0; f < P.nfronts; ++f) {
+    if (in_sub[f]) continue;
     const int nf2 = 2 * (P.s[f] + P.sptr[f + 1] - P.sptr[f]);
     for (int q = P.cptr[f]; q < P.cptr[f + 1]; ++q) {
       const int ch = P.child[q];
@@ -1166,15 +850,7 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
       }
     }
   }
-  const int bwd_rows_u2 = small_front_limit("PLFEM_BWD_ROWS_U2", 128);
-  std::vector<int32_t> nfs(P.nfronts, 0), nbs(P.nfronts, 0);
-  for (int f = 0; f < P.nfronts; ++f) {
-    const int s2 = 2 * P.s[f], u2 = 2 * (P.sptr[f + 1] - P.sptr[f]);
-    const int rows = s2 + u2;
-    nfs[f] = rows <= 128 ? 1 : (rows + 63) / 64;     // forward CTA items: one slab of <= 128 rows, else slabs of 64
-    // backward CTA items: few update unknowns -> chunks of 64 pivot columns sharing one gather, many -> 8 columns each
-    nbs[f] = u2 == 0 ? 0 : (u2 <= bwd_rows_u2 ? (s2 + 63) / 64 : (s2 + BWD_COLS - 1) / BWD_COLS);
-  }
+  static const int bwd_rows_u2 = [] { const char* e = std::getenv("PLFEM_BWD_ROWS_U2"); return e ? std::max(0, atoi(e)) : 128; }();
   for (int l = 0; l < P.nlevels; ++l) {
     for (int q = P.lptr[l]; q < P.lptr[l + 1]; ++q) {
       const int f = P.lfront[q];
@@ -1187,114 +863,41 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
         for (int a0 = 0; a0 < u2; a0 += GT) stl.push_back(make_int4(f, a0, b0, 0));
       if (P.cptr[f + 1] > P.cptr[f])
         for (int c0 = 0; c0 < nf; c0 += EA_COLS) ea.push_back(make_int4(f, c0, std::min(c0 + EA_COLS, nf), 0));
+      if (in_sub[f]) continue;
       {
         const int rows = s2 + u2;
         // row groups x rows per thread: <= 32 rows (1,1), <= 64 (1,2), <= 128 (2,2), larger fronts in slabs of 64 rows (1,2)
         const int G = (rows > 64 && rows <= 128) ? 2 : 1, Rr = rows <= 32 ? 1 : 2;
         const int nch = P.cptr[f + 1] - P.cptr[f];
-        const bool fsmall = in_sub(f);
         for (int r0 = 0; r0 < rows; r0 += 32 * G * Rr) {
           FwdItem it{};
           it.f = f; it.row0 = r0; it.nrows = std::min(32 * G * Rr, rows - r0); it.G = G | (Rr << 8); it.s2 = s2; it.ld = ldp[f];
           it.ch0 = nch > 0 ? P.child[P.cptr[f]] : -1; it.ch1 = nch > 1 ? P.child[P.cptr[f] + 1] : -1;
-          it.tgt0 = it.ch0 >= 0 ? nfs[it.ch0] : 0; it.tgt1 = it.ch1 >= 0 ? nfs[it.ch1] : 0;
           it.uoff = uoff[f]; it.goff = goff[f]; it.nchild = nch; it.nf2 = rows;
           it.foff = lo[f]; it.g0 = 2 * (int64_t)P.first[f];
-          fw.push_back(it);
-          if (!fsmall) fwb.push_back(it);
+          fwb.push_back(it);
         }
       }
       if (u2 > 0) {
-        const bool bsmall = in_sub(f);
         const bool rows_style = u2 <= bwd_rows_u2;
         const int Gb = rows_style ? (s2 <= 32 ? 1 : 2) : 0;   // pivot columns per thread; 0 = one warp per column
         const int cw = rows_style ? 32 * Gb : BWD_COLS;
         for (int c0 = 0; c0 < s2; c0 += cw) {
           BwdItem it{};
-          const int pa = P.parent[f];
           it.f = f; it.col0 = c0; it.ncols = std::min(cw, s2 - c0); it.s2 = s2; it.u2 = u2; it.soff = P.sptr[f];
           it.ld = rows_style ? ((s2 + 3) & ~3) : ldp[f];
-          it.parent = pa; it.tgt_f = nfs[f]; it.tgt_pf = pa >= 0 ? nfs[pa] : 0; it.tgt_pb = pa >= 0 ? nbs[pa] : 0; it.G = Gb;
+          it.parent = P.parent[f]; it.G = Gb;
           it.foff = rows_style ? wo[f] : lo[f]; it.g0 = 2 * (int64_t)P.first[f];
-          bw.push_back(it);
-          if (!bsmall) bwb.push_back(it);
+          bwb.push_back(it);
         }
       }
     }
     D.w_ptr[l + 1] = (int32_t)wt.size(); D.s_ptr[l + 1] = (int32_t)stl.size(); D.ea_ptr[l + 1] = (int32_t)ea.size();
-    D.fwd_ptr[l + 1] = (int32_t)fw.size(); D.bwd_ptr[l + 1] = (int32_t)bw.size();
     D.fwdb_ptr[l + 1] = (int32_t)fwb.size(); D.bwdb_ptr[l + 1] = (int32_t)bwb.size();
   }
   D.fwdb_items.upload(ctx, fwb); D.bwdb_items.upload(ctx, bwb);
-  {
-    // subtree task lists.  Fronts are numbered in post-order: the subtree of root r is the contiguous range ending at r.
-    std::vector<int32_t> size(P.nfronts, 1);
-    for (int f = 0; f < P.nfronts; ++f) if (P.parent[f] >= 0) size[P.parent[f]] += size[f];
-    std::vector<FwdTask> ft; std::vector<BwdTask> bt;
-    std::vector<int32_t> fptr(1, 0), bptr(1, 0);
-    std::vector<int2> subs;
-    // a CTA serves a GROUP of neighbouring subtrees, level by level, so that its 8 warps have tasks at the widest level
-    std::vector<std::vector<int32_t>> by_level;
-    auto close_group = [&] {
-      if (by_level.empty()) return;
-      subs.push_back(make_int2((int)fptr.size() - 1, (int)by_level.size()));
-      for (const std::vector<int32_t>& fl : by_level) {
-        for (int f : fl) {
-          const int s2 = 2 * P.s[f], u2 = 2 * (P.sptr[f + 1] - P.sptr[f]), rows = s2 + u2;
-          const int nch = P.cptr[f + 1] - P.cptr[f];
-          // rows per warp: at most 64 factor entries per lane in flight order, so a task is a handful of round trips
-          const int Rf = (s2 <= 32 && rows > 32) ? 2 : 1;
-          for (int r0 = 0; r0 < rows; r0 += 32 * Rf) {
-            FwdTask t{};
-            t.s2 = s2; t.rows = rows; t.r0 = r0; t.nr = std::min(32 * Rf, rows - r0); t.ldp = ldp[f]; t.goff = goff[f]; t.uoff = uoff[f];
-            t.nch = nch; t.lo = lo[f]; t.g0 = 2 * (int64_t)P.first[f];
-            ft.push_back(t);
-          }
-          if (u2 > 0) {
-            const int Rb = (s2 > 32 && u2 <= 32) ? 2 : 1;
-            for (int c0 = 0; c0 < s2; c0 += 32 * Rb) {
-              BwdTask t{};
-              t.s2 = s2; t.u2 = u2; t.c0 = c0; t.nc = std::min(32 * Rb, s2 - c0); t.s2p = (s2 + 3) & ~3; t.soff = P.sptr[f];
-              t.wo = wo[f]; t.g0 = 2 * (int64_t)P.first[f];
-              bt.push_back(t);
-            }
-          }
-        }
-        fptr.push_back((int32_t)ft.size()); bptr.push_back((int32_t)bt.size());
-      }
-      by_level.clear();
-    };
-    int widest = 0;     // forward tasks of the current group at its widest level
-    for (int r = 0; r < P.nfronts; ++r) {
-      if (!in_sub(r) || (P.parent[r] >= 0 && in_sub(P.parent[r]))) continue;     // not the root of a maximal subtree
-      const int nl = P.level[r] + 1;
-      if ((int)by_level.size() < nl) by_level.resize(nl);
-      for (int f = r - size[r] + 1; f <= r; ++f) by_level[P.level[f]].push_back(f);
-      widest = 0;
-      for (const std::vector<int32_t>& fl : by_level) {
-        int nt = 0;
-        for (int f : fl) { const int s2 = 2 * P.s[f], rows = s2 + 2 * (P.sptr[f + 1] - P.sptr[f]); nt += (rows + ((s2 <= 32 && rows > 32) ? 63 : 31)) / ((s2 <= 32 && rows > 32) ? 64 : 32); }
-        widest = std::max(widest, nt);
-      }
-      if (widest >= 8) close_group();
-    }
-    close_group();
-    D.n_subs = (int)subs.size();
-    D.fwd_tasks.upload(ctx, ft); D.bwd_tasks.upload(ctx, bt);
-    D.sub_fptr.upload(ctx, fptr); D.sub_bptr.upload(ctx, bptr); D.subs.upload(ctx, subs);
-  }
-  {
-    // backward queue of the persistent operator kernel: levels descending; completion counters
-    std::vector<BwdItem> bq; bq.reserve(bw.size());
-    for (int l = P.nlevels - 1; l >= 0; --l) bq.insert(bq.end(), bw.begin() + D.bwd_ptr[l], bw.begin() + D.bwd_ptr[l + 1]);
-    D.bwd_q.upload(ctx, bq);
-    D.n_fwd = (int)fw.size(); D.n_bwd = (int)bq.size();
-    D.fdone.alloc(ctx, P.nfronts); D.bdone.alloc(ctx, P.nfronts);
-    D.nfs.upload(ctx, nfs);
-  }
   D.gsrc.upload(ctx, gsrc);
   D.w_tiles.upload(ctx, wt); D.s_tiles.upload(ctx, stl); D.ea_slabs.upload(ctx, ea);
-  D.fwd_items.upload(ctx, fw); D.bwd_items.upload(ctx, bw);
   D.pool.alloc(ctx, (size_t)P.foff[P.nfronts]);
   D.status.alloc(ctx, 4);
   // the host vectors above are pageable: make sure the copies are done before they go out of scope
@@ -1304,9 +907,6 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
 void launch_front_load(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, const double* d_sigma_node) {
   PLFEM_CUDA(cudaMemsetAsync(D.pool.p, 0, D.pool.n * sizeof(double), ctx->stream));
   PLFEM_CUDA(cudaMemsetAsync(D.status.p, 0, 4 * sizeof(int32_t), ctx->stream));
-  PLFEM_CUDA(cudaMemsetAsync(D.fdone.p, 0, D.fdone.n * sizeof(int32_t), ctx->stream));
-  PLFEM_CUDA(cudaMemsetAsync(D.bdone.p, 0, D.bdone.n * sizeof(int32_t), ctx->stream));
-  D.epoch = 0;
   const int bs = 256;
   front_load_kernel<<<(unsigned)((pat.nnz + bs - 1) / bs), bs, 0, ctx->stream>>>(pat.nnz, pat.rowidx.p, pat.col.p,
                                                                                  D.sn_of.p, view(D), d_vals, d_sigma_node);
@@ -1350,8 +950,9 @@ void run_factorization(plfem_ctx* ctx, const DevPlan& D) {
       ctx->launches++;
     }
   }
-  pack_kernel<<<D.nfronts, 256, 0, ctx->stream>>>(v, D.lo.p, D.wo.p, D.ldp.p, D.fac.p);
+  pack_kernel<<<D.nfronts, 256, 0, ctx->stream>>>(v, D.lo.p, D.wo.p, D.ldp.p, D.in_sub.p, D.fac.p);
   ctx->launches++;
+  launch_stream_pack(ctx, D);
   PLFEM_CUDA(cudaGetLastError());
 }
 
@@ -1380,10 +981,9 @@ void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double
   const bool pdl = use_pdl();
   bool first = true;     // the first launch follows kernels that are not PDL-aware: plain launch
   const int32_t* gs = D.gsrc.p;
-  if (D.n_subs > 0) {
-    if (nrhs == 1) launch_sweep(forward_subtree_kernel<1, false>, false, D.n_subs, ctx->stream, D.subs.p, D.sub_fptr.p, D.fwd_tasks.p, gs, D.fac.p, rv);
-    else launch_sweep(forward_subtree_kernel<SOLVE_NRHS, false>, false, D.n_subs, ctx->stream, D.subs.p, D.sub_fptr.p, D.fwd_tasks.p, gs, D.fac.p, rv);
-    first = false; ctx->launches++;
+  if (D.st.n_subs > 0) {
+    launch_stream_forward(ctx, D, b, z, nrhs, false);
+    first = false;
   }
   for (int l = 0; l < D.nlevels; ++l) {
     const int nbig = D.fwdb_ptr[l + 1] - D.fwdb_ptr[l];
@@ -1400,46 +1000,17 @@ void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double
 void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs) {
   const PlanView v = sweep_view(D);
   const bool pdl = use_pdl();
+  bool any_level = false;     // the stream kernel may be chained by PDL only to a PDL-aware predecessor
   for (int l = D.nlevels - 1; l >= 0; --l) {
     const int nbig = D.bwdb_ptr[l + 1] - D.bwdb_ptr[l];
     if (nbig == 0) continue;
+    any_level = true;
     const BwdItem* items = D.bwdb_items.p + D.bwdb_ptr[l];
     if (nrhs == 1) { if (pdl) launch_sweep(backward_kernel<1, true>, true, nbig, ctx->stream, items, v, x); else launch_sweep(backward_kernel<1, false>, false, nbig, ctx->stream, items, v, x); }
     else { if (pdl) launch_sweep(backward_kernel<SOLVE_NRHS, true>, true, nbig, ctx->stream, items, v, x); else launch_sweep(backward_kernel<SOLVE_NRHS, false>, false, nbig, ctx->stream, items, v, x); }
     ctx->launches++;
   }
-  if (D.n_subs > 0) {
-    if (nrhs == 1) { if (pdl) launch_sweep(backward_subtree_kernel<1, true>, true, D.n_subs, ctx->stream, D.subs.p, D.sub_bptr.p, D.bwd_tasks.p, D.strct.p, D.fac.p, x); else launch_sweep(backward_subtree_kernel<1, false>, false, D.n_subs, ctx->stream, D.subs.p, D.sub_bptr.p, D.bwd_tasks.p, D.strct.p, D.fac.p, x); }
-    else { if (pdl) launch_sweep(backward_subtree_kernel<SOLVE_NRHS, true>, true, D.n_subs, ctx->stream, D.subs.p, D.sub_bptr.p, D.bwd_tasks.p, D.strct.p, D.fac.p, x); else launch_sweep(backward_subtree_kernel<SOLVE_NRHS, false>, false, D.n_subs, ctx->stream, D.subs.p, D.sub_bptr.p, D.bwd_tasks.p, D.strct.p, D.fac.p, x); }
-    ctx->launches++;
-  }
-}
-
-int op_grid_size(plfem_ctx* ctx, int ctas_per_sm) {
-  static int max_per_sm[64] = {}; static int nsm[64] = {};
-  const int dev = ctx->device < 64 ? ctx->device : 0;
-  if (!nsm[dev]) {
-    int occ = 0, sms = 0;
-    PLFEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, op_kernel, 256, 0));
-    PLFEM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
-    max_per_sm[dev] = std::max(occ, 1); nsm[dev] = sms;
-  }
-  return nsm[dev] * std::max(1, std::min(ctas_per_sm, max_per_sm[dev]));
-}
-
-// x = (A - sigma B)^-1 b with `refine` refinement steps, one cooperative launch (b, x, rt, rdx distinct)
-void run_operator(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, const double* d_sigma_node, const double* b,
-                  double* x, double* rt, double* rdx, int refine, int ctas_per_sm) {
-  OpArgs a;
-  a.P = sweep_view(D);
-  a.fwd_q = D.fwd_items.p; a.bwd_q = D.bwd_q.p; a.gsrc = D.gsrc.p; a.n_fwd = D.n_fwd; a.n_bwd = D.n_bwd;
-  a.fdone = D.fdone.p; a.bdone = D.bdone.p; a.status = D.status.p; a.nfs = D.nfs.p;
-  a.epoch0 = D.epoch; D.epoch += 1 + refine;
-  a.b = b; a.x = x; a.upd = D.upd.p; a.rt = rt; a.rdx = rdx; a.refine = refine;
-  a.n = pat.n; a.rowptr = pat.rowptr.p; a.col = pat.col.p; a.vals = d_vals; a.nnz = pat.nnz; a.sigma_node = d_sigma_node;
-  void* args[] = {&a};
-  PLFEM_CUDA(cudaLaunchCooperativeKernel((const void*)op_kernel, dim3(op_grid_size(ctx, ctas_per_sm)), dim3(256), args, 0, ctx->stream));
-  ctx->launches++;
+  if (D.st.n_subs > 0) launch_stream_backward(ctx, D, x, nrhs, pdl && any_level);
 }
 
 void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x, int nrhs) {

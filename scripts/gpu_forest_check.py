@@ -29,3 +29,7 @@ for nb in sizes:
     print(f"nb={nb:3d} wall={1e3*dt:8.2f} ms  per-solve={1e3*dt/nb:7.2f} ms  {nb/dt:7.1f} solves/s | sym_wall={st['ms_symbolic_wall']:.1f} "
           f"sym_own={st['ms_symbolic']:.1f} asm={st['ms_assemble']:.2f} fac={st['ms_factor']:.2f} lan={st['ms_lanczos']:.2f} "
           f"met={st['ms_metrics']:.2f} entries={st['factor_entries']} levels={st['n_levels']} fronts={st['n_fronts']} launches={st['kernel_launches']} block_ops={st['batch_block_ops']} ok={ok} dev={dev:.1e} resid={st['max_residual']:.1e}", flush=True)
+prof, nbp = ctx.profile_last(repeat=10)
+peak = 6553.6
+for name, (ms, nbytes) in prof.items():
+    print(f"  {name:22s} {ms:9.4f} ms {nbytes / 1e6:9.1f} MB {nbytes / ms / 1e6:8.1f} GB/s ({nbytes / ms / 1e6 / peak:.3f} of HBM peak) [forest of {nbp}]", flush=True)

@@ -204,9 +204,9 @@ def test_single_vector_and_block_lanczos_agree(small_case):
     assert len(a) == len(b)
 
 
-def test_persistent_operator_kernel_matches_per_level_kernels(small_case):
-    """`plfem_debug_solve`: the cooperative dataflow kernel and the per-level kernels give the same solution,
-    and both agree with SuperLU after one refinement step."""
+def test_block_ldlt_solve_matches_superlu(small_case):
+    """`plfem_debug_solve`: the sweeps (TMA-streamed bottom subtrees + per-level kernels) on the block-LDL^T factors agree
+    with SuperLU: raw to 1e-7 (symmetrised pivot-block inverses), to 1e-11 after one refinement step."""
     from scipy.sparse.linalg import splu
     from plfem_b200.solver_fem import sigma_estimate
     g, mesh = small_case
@@ -218,10 +218,9 @@ def test_persistent_operator_kernel_matches_per_level_kernels(small_case):
     pb.solve_modes(mat, sigma, 16)
     b = s["B_int"] @ np.random.default_rng(2).standard_normal(K.shape[0])
     xr = splu(K).solve(b)
-    x_coop, x_lvl = pb.debug_solve(sigma, b, 1), pb.debug_solve(sigma, b, 101)
-    assert np.linalg.norm(x_coop - xr) / np.linalg.norm(xr) < 1e-9
-    assert np.linalg.norm(x_lvl - xr) / np.linalg.norm(xr) < 1e-9
-    assert np.linalg.norm(x_coop - x_lvl) / np.linalg.norm(xr) < 1e-12
+    x_raw, x_ref = pb.debug_solve(sigma, b, 0), pb.debug_solve(sigma, b, 1)
+    assert np.linalg.norm(x_raw - xr) / np.linalg.norm(xr) < 1e-7
+    assert np.linalg.norm(x_ref - xr) / np.linalg.norm(xr) < 1e-11
 
 
 def test_readme_surface(cfg1):
