@@ -8,10 +8,13 @@ declared in ``include/plfem.h``.
 from .geometry import MCFGeometry, PhotonicLanternGeometry, mcf_positions  # noqa: F401
 from .config import SimulationConfig, PhysicalConstants, IPDipCauchy  # noqa: F401
 from .mesh import MeshTri, MeshGenerator  # noqa: F401
+from .losses import (LossCalculator, VectorialLossCalculator, EnhancedLossCalculator,  # noqa: F401
+                     PhotonicLanternDesignParameters)
 
 __all__ = ["MCFGeometry", "PhotonicLanternGeometry", "mcf_positions", "SimulationConfig",
            "PhysicalConstants", "IPDipCauchy", "MeshTri", "MeshGenerator",
-           "TrueVectorialMaxwellSolver", "ModeRecord"]
+           "LossCalculator", "VectorialLossCalculator", "EnhancedLossCalculator", "PhotonicLanternDesignParameters",
+           "TrueVectorialMaxwellSolver", "ScalarHelmholtzSolver", "ModeRecord"]
 
 
 def __getattr__(name):

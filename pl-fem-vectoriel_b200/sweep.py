@@ -7,8 +7,8 @@ round-robin over ranks (one process per GPU), solve locally, and exchange the fi
 records ONCE (`all_gather`).  There is no data-path collective inside a solve.
 
 Record layout (86 float64 slots, the count `README.md:49` names; the README's own table sums to 85,
-slot 85 is spare).  Loss columns (12) belong to `losses.py`, which is outside this hot path; they
-are NaN here.
+slot 85 is spare).  The 12 loss columns come from `losses.LossCalculator` (the reference's closed forms for
+vectorial modes, `losses.py:742-826`, both directions) evaluated on the host from the mode records.
 """
 from __future__ import annotations
 
@@ -35,7 +35,7 @@ RECORD_FIELDS: List[str] = (
     + ["PDL_mean_dB", "PDL_max_dB", "n_hybrid_modes", "n_te_like_modes", "n_tm_like_modes"]      # 5 polarization
     + [f"loss_{k}" for k in ("IL_mux_dB", "MDL_mux_dB", "PDL_mux_dB", "XT_mux_dB", "IL_demux_dB", "MDL_demux_dB",
                              "PDL_demux_dB", "XT_demux_dB", "radiation_dB_per_m", "taper_dB", "mmf_dB",
-                             "polymer_dB")]                                                      # 12 losses (NaN)
+                             "polymer_dB")]                                                      # 12 losses
     + [f"{name}_mode_{k}" for k in range(N_PER_MODE) for name in ("n_eff", "conf", "PDL", "pol", "div")]  # 35
     + ["spare"]
 )
@@ -78,6 +78,18 @@ def design_record(sample_id: int, design: Dict, geometry, mesh, modes: Sequence[
         for k, m in enumerate(modes[:N_PER_MODE]):
             r[f[f"n_eff_mode_{k}"]], r[f[f"conf_mode_{k}"]], r[f[f"PDL_mode_{k}"]] = m["n_eff"], m["confinement"], m["PDL_dB"]
             r[f[f"pol_mode_{k}"]], r[f[f"div_mode_{k}"]] = POL_CODE.get(m["polarization"], np.nan), m["div_ratio"]
+        if g is not None:
+            from .losses import LossCalculator, VectorialLossCalculator
+            wl = 1000.0 * g.wavelength
+            for direction in ("mux", "demux"):
+                L = LossCalculator.calculate_physical_losses(list(modes), g, direction, wl)
+                if L.get("success"):
+                    r[f[f"loss_IL_{direction}_dB"]], r[f[f"loss_MDL_{direction}_dB"]] = L["IL_dB"], L["MDL_dB"]
+                    r[f[f"loss_PDL_{direction}_dB"]], r[f[f"loss_XT_{direction}_dB"]] = L["PDL_dB"], L["crosstalk_dB"]
+                    r[f["loss_radiation_dB_per_m"]] = L["radiation_loss_dB_per_m"]
+            S = VectorialLossCalculator.calculate_vectorial_losses(list(modes), g, LossCalculator._build_design_params(list(modes), g, wl), "mux", wl)
+            if S.get("success"):
+                r[f["loss_taper_dB"]], r[f["loss_mmf_dB"]], r[f["loss_polymer_dB"]] = S["IL_taper"], S["IL_MMF"], S["IL_polymer"]
     elif success:
         r[f["n_modes_found"]] = 0
     return r

@@ -10,6 +10,11 @@ What is frozen and where it comes from
                     scikit-fem + the real SciPy eigsh) on config 1 and on the small 3-core case:
                     sigma, eigenvalues, n_eff, CSR structure digests.  These pin the oracle against
                     regressions; they are NOT reference outputs (parity unpinned, see the oracle header).
+  losses.json     : the REAL reference module losses.py (imported from /root/reference with a stand-in for the absent
+                    `config.PhotonicLanternDesignParameters`: a class that stores its keyword arguments): its own
+                    self-check (XT, PDL of 7 synthetic modes, `losses.py:1228-1259`) and
+                    `LossCalculator.calculate_physical_losses` on synthetic vectorial mode lists for 3 geometries,
+                    both directions, 2 wavelengths.  The mode lists are stored with the outputs.
 """
 import hashlib
 import json
@@ -118,8 +123,63 @@ def golden_oracle():
     return out
 
 
+def synthetic_vectorial_modes(n_modes, seed):
+    """Mode records shaped like the reference's own self-check (`losses.py:1234-1250`)."""
+    rng = np.random.default_rng(seed)
+    modes = []
+    for k in range(n_modes):
+        Px = float(rng.uniform(0.3, 0.7))
+        Py = 1.0 - Px
+        modes.append({"n_eff": float(1.20 - k * 0.003 + rng.normal(0, 1e-4)), "beta": float((2 * np.pi / 1.55) * (1.20 - k * 0.003)),
+                      "P_x": Px, "P_y": Py, "PDL_dB": float(10 * np.log10(max(Px, Py) / min(Px, Py))), "polarization": "Hybrid",
+                      "confinement": float(rng.uniform(0.55, 0.72)), "core_overlap": 0.60, "div_ratio": 0.02,
+                      "is_vectorial": True, "method": "H-field_V18.10"})
+    return modes
+
+
+def golden_losses():
+    sys.path.insert(0, REF)
+    import geometry_unified as G
+
+    class DesignParams:                      # stand-in for the absent config.PhotonicLanternDesignParameters
+        def __init__(self, **kw):
+            self.__dict__.update(kw)
+    config = types.ModuleType("config"); config.PhotonicLanternDesignParameters = DesignParams
+    saved = sys.modules.get("config")
+    sys.modules["config"] = config
+    try:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ref_losses", os.path.join(REF, "losses.py"))
+        L = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(L)
+        out = {}
+        m7 = synthetic_vectorial_modes(7, 42)
+        out["selfcheck"] = dict(xt=L.EnhancedLossCalculator._calculate_crosstalk(m7), pdl=L.EnhancedLossCalculator._calculate_pdl_vectorial(m7))
+        cases = []
+        for n_cores, n_modes, seed in ((7, 7, 42), (19, 23, 5), (3, 2, 9)):
+            g = G.MCFGeometry(n_cores, 8.0, 1.5, 1.535, 1.0)
+            modes = synthetic_vectorial_modes(n_modes, seed)
+            for direction in ("mux", "demux"):
+                for wl in (1550.0, 1490.0):
+                    res = L.LossCalculator.calculate_physical_losses(modes, g, direction, wl)
+                    dp = L.LossCalculator._build_design_params(modes, g, wl)
+                    cases.append(dict(n_cores=n_cores, seed=seed, n_modes=n_modes, direction=direction, wavelength_nm=wl,
+                                      result={k: v for k, v in res.items()},
+                                      design={k: (v if isinstance(v, (str, bool)) else float(v)) for k, v in dp.__dict__.items()}))
+        out["cases"] = cases
+        return out
+    finally:
+        if saved is None:
+            sys.modules.pop("config", None)
+        else:
+            sys.modules["config"] = saved
+
+
 if __name__ == "__main__":
-    for name, fn in (("geometry", golden_geometry), ("mesh_recipe", golden_mesh), ("oracle_cfg", golden_oracle)):
+    only = sys.argv[1:]
+    for name, fn in (("geometry", golden_geometry), ("mesh_recipe", golden_mesh), ("oracle_cfg", golden_oracle), ("losses", golden_losses)):
+        if only and name not in only:
+            continue
         with open(os.path.join(HERE, name + ".json"), "w") as f:
             json.dump(fn(), f, indent=1)
         print("wrote", name)

@@ -102,7 +102,9 @@ def test_two_rank_sweep_matches_single_rank(tmp_path):
     assert list(r0[:, f["success"]]) == [1, 1, 1, 0, 1]                      # the failed design poisons nothing
     assert np.isnan(r0[3, f["n_eff_mean"]]) and r0[2, f["n_modes_found"]] >= 1
     assert r0[2, f["wavelength_nm"]] == 1490 and r0[0, f["n_cores"]] == 1
-    assert np.isnan(r0[:, f["loss_IL_mux_dB"]]).all()                        # loss columns are out of scope
+    ok = r0[:, f["n_modes_found"]] >= 1                                      # loss columns: filled wherever modes were found
+    assert np.isfinite(r0[ok][:, [f["loss_IL_mux_dB"], f["loss_PDL_demux_dB"], f["loss_XT_mux_dB"], f["loss_taper_dB"]]]).all()
+    assert (r0[ok, f["loss_PDL_demux_dB"]] >= r0[ok, f["loss_PDL_mux_dB"]]).all() and np.isnan(r0[3, f["loss_IL_mux_dB"]])
     p = tmp_path / "records.csv"
     sweep.records_to_csv(r0, str(p))
     lines = open(p).read().splitlines()
