@@ -182,6 +182,30 @@ class MeshGenerator:
         cls._cache_hits = cls._cache_misses = 0
 
     @classmethod
+    def _estimate_cache_memory_mb(cls) -> float:
+        return sum(m.p.nbytes + m.t.nbytes for m, _ in cls._cache.values()) / 2 ** 20
+
+    @classmethod
+    def save_cache(cls, filepath):
+        """Persist the mesh cache (`mesh.py:385-396`).  Written as a NumPy archive of plain arrays (p and t per key plus the
+        hit/miss counters), not a pickle of objects: the file can be read back by any version of this package."""
+        arrays = {"keys": np.array(list(cls._cache.keys())), "counters": np.array([cls._cache_hits, cls._cache_misses])}
+        for i, (mesh, _) in enumerate(cls._cache.values()):
+            arrays[f"p{i}"], arrays[f"t{i}"] = mesh.p, mesh.t
+        with open(filepath, "wb") as f:
+            np.savez_compressed(f, **arrays)
+
+    @classmethod
+    def load_cache(cls, filepath):
+        """Load a cache written by `save_cache` (`mesh.py:398-416`); a missing file leaves the cache untouched."""
+        import os
+        if not os.path.exists(filepath):
+            return
+        with np.load(filepath, allow_pickle=False) as z:
+            cls._cache = OrderedDict((str(k), (MeshTri(z[f"p{i}"], z[f"t{i}"]), None)) for i, k in enumerate(z["keys"]))
+            cls._cache_hits, cls._cache_misses = (int(v) for v in z["counters"])
+
+    @classmethod
     def get_cache_stats(cls):
         tot = cls._cache_hits + cls._cache_misses
         return dict(size=len(cls._cache), hits=cls._cache_hits, misses=cls._cache_misses,

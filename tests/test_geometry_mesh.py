@@ -117,3 +117,25 @@ def test_hub_vertices_fit_the_device_pattern_builder(cfg1, cfg2):
         sample.append(P.MeshGenerator.generate(design_geometry(d))[0])
     worst = max(int(np.bincount(np.asarray(m.t).ravel()).max()) for m in sample)
     assert 16 <= worst <= cap // 2, worst
+
+
+def test_mesh_cache_round_trip(tmp_path):
+    """`save_cache` / `load_cache` (`mesh.py:385-416`): same keys, same meshes, counters kept; a hit after reloading."""
+    import plfem_b200 as P
+    P.MeshGenerator.clear_cache()
+    g = P.MCFGeometry(3, 6.0, 1.2, 1.53, 1.0, 1.55)
+    cfg = P.SimulationConfig()
+    cfg.enable_mesh_cache = True
+    m1, _ = P.MeshGenerator.generate(g, 0.4, cfg)
+    path = tmp_path / "mesh_cache.npz"
+    P.MeshGenerator.save_cache(path)
+    before = P.MeshGenerator.get_cache_stats()
+    P.MeshGenerator.clear_cache()
+    P.MeshGenerator.load_cache(tmp_path / "missing.npz")          # no file: nothing happens
+    assert P.MeshGenerator.get_cache_stats()["size"] == 0
+    P.MeshGenerator.load_cache(path)
+    assert P.MeshGenerator.get_cache_stats() == before
+    m2, _ = P.MeshGenerator.generate(g, 0.4, cfg)
+    assert P.MeshGenerator.get_cache_stats()["hits"] == before["hits"] + 1
+    assert np.array_equal(m1.p, m2.p) and np.array_equal(m1.t, m2.t)
+    P.MeshGenerator.clear_cache()
