@@ -62,6 +62,9 @@ typedef struct {
 int plfem_problem_create(plfem_ctx* ctx, const double* p, const int64_t* t, int64_t V, int64_t T,
                          plfem_problem** out);
 void plfem_problem_destroy(plfem_problem* pb);
+/* on = 1 (default): the solve eliminates the boundary DOFs (solver_fem.py:179-184).  on = 0: every DOF is kept, the
+ * natural boundary condition of ScalarHelmholtzSolver (solver_fem.py:245-276), which never calls get_dofs() */
+int plfem_problem_set_dirichlet(plfem_problem* pb, int on);
 int plfem_problem_info(const plfem_problem* pb, plfem_mesh_info* info);
 /* element_dofs (6,T) int64, doflocs (2,N) float64, boundary (n_boundary) int64, interior (n_interior)
  * int64; any pointer may be NULL to skip it */
@@ -78,6 +81,10 @@ typedef struct {
   double alpha_p;              /* divergence penalty, reference uses 1.0 (solver_fem.py:158) */
   const double* eps_at_quad;   /* optional (T,6) Re eps sampled by the caller at plfem_quad_points();
                                   when non-NULL it overrides the disc model */
+  int32_t scalar_mode;         /* 0: vectorial H-field system (solver_fem.py:122-169).  1: the scalar Helmholtz pencil of
+                                  ScalarHelmholtzSolver (solver_fem.py:245-276), (K - k0^2 M_eps, M), carried in the Hx block;
+                                  the Hy block holds (scalar_shift * M, M), whose eigenvalues all equal scalar_shift */
+  double scalar_shift;         /* scalar mode only: pick it far from sigma so that the Hy copy is never wanted */
 } plfem_material;
 
 /* global coordinates of the 6 quadrature points of every element, out_xy is (2,T,6) float64 */

@@ -15,6 +15,7 @@ the reference's post-processing restated line by line:
 * ``assemble_hfield_system``  <- `solver_fem.py:122-169`
 * ``solve_vectorial_modes``   <- `solver_fem.py:171-239`
 * ``polarization_from_interp``<- `solver_fem.py:68-107`
+* ``solve_scalar_modes``      <- ``ScalarHelmholtzSolver.solve``   (`solver_fem.py:245-276`)
 
 PARITY UNPINNED: the reference ships no test, golden vector or stored result
 for this path and scikit-fem (third-party, unpinned,
@@ -289,4 +290,37 @@ def solve_vectorial_modes(geometry, mesh, n_modes_target: int = 20, v0="ones",
     if return_raw:
         return modes, dict(beta_sq=beta_sq, evecs=evecs, sigma=sigma, modes_raw=modes_raw,
                            frac_core=frac_core, system=s)
+    return modes
+
+
+def solve_scalar_modes(geometry, mesh, n_modes_target: int = 20, v0="ones"):
+    """`ScalarHelmholtzSolver.solve` (`solver_fem.py:249-272`), verbatim but for the fixed ``v0``."""
+    basis = P2Basis(mesh)
+    eps = lambda x: np.real(geometry.epsilon(*x))                                        # noqa: E731
+    K = assemble_form(basis, lambda u, gu, v, gv, x: gu[0] * gv[0] + gu[1] * gv[1])
+    M = assemble_form(basis, lambda u, gu, v, gv, x: u * v)
+    Me = assemble_form(basis, lambda u, gu, v, gv, x: eps(x) * u * v)
+    k0 = geometry.k0
+    sigma = -(k0 * (geometry.n_core - 0.008)) ** 2
+    if isinstance(v0, str) and v0 == "ones":
+        v0 = np.ones(basis.N)
+    evals, evecs = eigsh(K - k0 ** 2 * Me, k=min(n_modes_target + 8, basis.N - 4), M=M, sigma=sigma, which="LM", tol=1e-6,
+                         maxiter=6000, v0=v0)
+    x_dof, y_dof = basis.doflocs
+    modes = []
+    for i in range(len(evals)):
+        if evals[i] >= 0:
+            continue
+        ne = np.sqrt(-evals[i]) / k0
+        if ne <= geometry.n_clad or ne >= geometry.n_core * 1.005:
+            continue
+        v = evecs[:, i].copy()
+        v /= np.sqrt(float(v @ (M @ v))) + 1e-30
+        in_core = np.zeros(len(x_dof), dtype=bool)
+        for (cx, cy), r in zip(geometry.positions, geometry.core_radii):
+            in_core |= (x_dof - cx) ** 2 + (y_dof - cy) ** 2 <= r ** 2
+        conf = float(np.sum(v[in_core] ** 2) / np.sum(v ** 2))
+        modes.append({"n_eff": float(ne), "beta": float(k0 * ne), "field_vector": v, "confinement": conf, "core_overlap": conf,
+                      "PDL_dB": 0.0, "polarization": "scalar", "is_vectorial": False})
+    modes.sort(key=lambda m: m["n_eff"], reverse=True)
     return modes

@@ -31,7 +31,7 @@ EIG_TOL = 1e-8
 
 #: every symbol include/plfem.h declares (checked by tests/test_cabi.py)
 SYMBOLS = ["plfem_ctx_create", "plfem_ctx_destroy", "plfem_last_error", "plfem_version",
-           "plfem_problem_create", "plfem_problem_destroy", "plfem_problem_info", "plfem_problem_dofs",
+           "plfem_problem_create", "plfem_problem_destroy", "plfem_problem_set_dirichlet", "plfem_problem_info", "plfem_problem_dofs",
            "plfem_quad_points", "plfem_assemble", "plfem_export_csr", "plfem_spmv_csr", "plfem_solve_modes",
            "plfem_plan_sizes", "plfem_plan_export", "plfem_debug_symeig", "plfem_profile_kernels", "plfem_set_host_threads",
            "plfem_debug_solve", "plfem_solve_modes_batch", "plfem_profile_last", "plfem_host_alloc", "plfem_host_free"]
@@ -43,7 +43,8 @@ class MeshInfo(C.Structure):
 
 class Material(C.Structure):
     _fields_ = [("cores_xy", p_f64), ("cores_r", p_f64), ("n_cores", c_i32), ("eps_core", c_f64),
-                ("eps_clad", c_f64), ("k0", c_f64), ("alpha_p", c_f64), ("eps_at_quad", p_f64)]
+                ("eps_clad", c_f64), ("k0", c_f64), ("alpha_p", c_f64), ("eps_at_quad", p_f64),
+                ("scalar_mode", c_i32), ("scalar_shift", c_f64)]
 
 
 class SolveOpts(C.Structure):
@@ -99,6 +100,7 @@ def load():
         lib.plfem_problem_create.argtypes = [vp, p_f64, p_i64, c_i64, c_i64, C.POINTER(vp)]
         lib.plfem_problem_destroy.argtypes = [vp]
         lib.plfem_problem_destroy.restype = None
+        lib.plfem_problem_set_dirichlet.argtypes = [vp, C.c_int]
         lib.plfem_problem_info.argtypes = [vp, C.POINTER(MeshInfo)]
         lib.plfem_problem_dofs.argtypes = [vp, p_i64, p_f64, p_i64, p_i64]
         lib.plfem_quad_points.argtypes = [vp, p_f64]
@@ -287,6 +289,12 @@ class Problem:
             if self.ctx is None:
                 raise PlfemError(st, "host-only problem")
             self.ctx.check(st)
+
+    def set_dirichlet(self, on: bool):
+        """``False``: keep every DOF (natural boundary condition of the reference's scalar solver, `solver_fem.py:245-276`)."""
+        self._check(self.lib.plfem_problem_set_dirichlet(self.handle, int(bool(on))))
+        self.lib.plfem_problem_info(self.handle, C.byref(self.info))
+        self.n_interior = self.info.n_interior
 
     def dofs(self):
         ed = np.empty((6, self.T), dtype=np.int64)

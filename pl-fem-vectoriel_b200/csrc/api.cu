@@ -168,6 +168,10 @@ void upload_material(plfem_problem* pb, const plfem_material* mat) {
   launch_element_setup(ctx, pb->d_p.p, pb->d_edofs.p, pb->dof.V, pb->dof.T, *mat, pb->d_cores.p, epsq, pb->d_elem.p);
 }
 
+// (k0^2, alpha_p) of the vectorial system or (k0^2, shift of the decoupled Hy copy) of the scalar one
+inline double second_coeff(const plfem_material& m) { return m.scalar_mode ? m.scalar_shift : m.alpha_p; }
+inline int assembly_mode(const plfem_material& m) { return m.scalar_mode ? 2 : 0; }
+
 void upload_pattern(plfem_ctx* ctx, const Pattern& P, DevPattern& D) {
   D.n = P.n; D.nnz = (int64_t)P.col.size();
   D.rowptr.upload(ctx, P.rowptr); D.col.upload(ctx, P.col); D.old_of_new.upload(ctx, P.old_of_new);
@@ -283,6 +287,23 @@ int plfem_problem_create(plfem_ctx* ctx, const double* p, const int64_t* t, int6
   return PLFEM_OK;
 }
 
+int plfem_problem_set_dirichlet(plfem_problem* pb, int on) {
+  if (!pb) return PLFEM_ERR_INVALID;
+  return guarded(pb->ctx, [&] {
+    DofTables& d = pb->dof;
+    d.interior.clear();
+    if (on) {
+      std::vector<uint8_t> is_b(d.N, 0);
+      for (int32_t b : d.boundary) is_b[b] = 1;
+      for (int32_t i = 0; i < d.N; ++i) if (!is_b[i]) d.interior.push_back(i);
+    } else {
+      d.interior.resize(d.N);
+      for (int32_t i = 0; i < d.N; ++i) d.interior[i] = i;
+    }
+    pb->plan_ready = false; pb->adj_ready = false; pb->work.reset();     // everything derived from the interior set is stale
+  });
+}
+
 void plfem_problem_destroy(plfem_problem* pb) {
   if (!pb) return;
   if (pb->ctx) cudaSetDevice(pb->ctx->device);
@@ -338,12 +359,16 @@ int plfem_assemble(plfem_problem* pb, const plfem_material* mat) {
     if (pb->dof.n_degenerate > 0)
       throw StatusError(PLFEM_ERR_DEGENERATE, std::to_string(pb->dof.n_degenerate) + " zero-area triangle(s): the affine map is singular");
     ensure_full_pattern(pb);
+    need(mat != nullptr, "material is NULL");
+    plfem_material vmat = *mat;
+    vmat.scalar_mode = 0;          // the export path always assembles the ten scalar matrices of the H-field forms (M among them)
+    mat = &vmat;
     upload_material(pb, mat);
     const int64_t nnz = pb->dfull.nnz;
     pb->d_full_vals.alloc(ctx, (size_t)NV_EXPORT * nnz);
     pb->d_full_flags.alloc(ctx, (size_t)nnz);
     launch_assemble(ctx, pb->dfull, pb->d_n2e_ptr.p, pb->d_n2e.p, pb->d_edofs.p, pb->d_elem.p, mat->k0 * mat->k0,
-                    mat->alpha_p, true, pb->d_full_vals.p, pb->d_full_flags.p);
+                    mat->alpha_p, 1, pb->d_full_vals.p, pb->d_full_flags.p);
     pb->h_full_vals.resize((size_t)NV_EXPORT * nnz);
     pb->h_full_flags.resize((size_t)nnz);
     pb->d_full_vals.download(pb->h_full_vals.data(), pb->h_full_vals.size());
@@ -577,7 +602,7 @@ static void solve_forest(plfem_ctx* ctx, int nb, plfem_problem* const* pbs, cons
     W.asm_args[b].mat.cores_xy = nullptr; W.asm_args[b].mat.cores_r = nullptr; W.asm_args[b].mat.eps_at_quad = nullptr;
     const int64_t z0 = W.nnz_off[b];
     launch_assemble_slice(ctx, W.nnz_off[b + 1] - z0, W.dpat.rowidx.p + z0, W.dpat.col.p + z0, W.dpat.old_of_new.p, pb->d_n2e_ptr.p,
-                          pb->d_n2e.p, pb->d_edofs.p, pb->d_elem.p, mats[b].k0 * mats[b].k0, mats[b].alpha_p, false,
+                          pb->d_n2e.p, pb->d_edofs.p, pb->d_elem.p, mats[b].k0 * mats[b].k0, second_coeff(mats[b]), assembly_mode(mats[b]),
                           W.d_vals.p + z0, nnz, nullptr);
     std::fill(sig.begin() + bd.noff[b], sig.begin() + bd.noff[b + 1], opts[b].sigma);
     std::copy(masks[b].begin(), masks[b].end(), mask_all.begin() + bd.noff[b]);
@@ -786,7 +811,7 @@ static void profile_work(plfem_ctx* ctx, SolveWork& W, int repeat, double* out_m
       const int64_t z0 = W.nnz_off[d];
       launch_element_setup(ctx, a.d_p, a.d_edofs, a.V, a.T, a.mat, a.d_cores, nullptr, a.d_elem);
       launch_assemble_slice(ctx, W.nnz_off[d + 1] - z0, W.dpat.rowidx.p + z0, W.dpat.col.p + z0, W.dpat.old_of_new.p, a.d_n2e_ptr, a.d_n2e,
-                            a.d_edofs, a.d_elem, a.mat.k0 * a.mat.k0, a.mat.alpha_p, false, W.d_vals.p + z0, nnz, nullptr);
+                            a.d_edofs, a.d_elem, a.mat.k0 * a.mat.k0, second_coeff(a.mat), assembly_mode(a.mat), W.d_vals.p + z0, nnz, nullptr);
     }
   });
   // mesh in (coordinates + 6 DOF ids per element), every assembled value out once

@@ -83,7 +83,7 @@ constexpr int ELEM_STRIDE = 12;  // doubles per element record: i00 i10 i01 i11 
 __global__ void element_setup_kernel(const double* __restrict__ px, const double* __restrict__ py,
                                      const int32_t* __restrict__ edofs, int64_t T, const double* __restrict__ cores,
                                      int ncores, double eps_core, double eps_clad,
-                                     const double* __restrict__ eps_at_quad, double* __restrict__ elem) {
+                                     const double* __restrict__ eps_at_quad, bool store_eps, double* __restrict__ elem) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= T) return;
   const int32_t v0 = edofs[6 * e], v1 = edofs[6 * e + 1], v2 = edofs[6 * e + 2];
@@ -110,7 +110,7 @@ __global__ void element_setup_kernel(const double* __restrict__ px, const double
         if (add(mul(ddx, ddx), mul(ddy, ddy)) <= mul(rr, rr)) eps = eps_core;
       }
     }
-    r[5 + q] = __ddiv_rn(1.0, eps);
+    r[5 + q] = store_eps ? eps : __ddiv_rn(1.0, eps);     // weight of the "w" forms: 1/eps (H-field system) or eps (scalar Helmholtz)
   }
   r[11] = 0.0;
 }
@@ -201,7 +201,9 @@ __global__ void gather_offsets_kernel(const int32_t* __restrict__ rowptr, const 
 }
 
 // ---- K1b/K2 fused: one thread per structural non-zero ---------------------------------------------------
-template <bool EXPORT>
+// MODE 0: the solve's value arrays of the H-field system; 1: the ten scalar matrices for export; 2: scalar Helmholtz pencil
+// (solver_fem.py:245-276) in the same arrays — Hx block (K - k0^2 M_eps, M), Hy block (shift M, M), no coupling
+template <int MODE>
 __global__ void __launch_bounds__(128)
 assemble_kernel(int64_t nnz, const int32_t* __restrict__ rowidx, const int32_t* __restrict__ col,
                 const int32_t* __restrict__ old_of_new, const int32_t* __restrict__ n2e_ptr,
@@ -261,14 +263,24 @@ assemble_kernel(int64_t nnz, const int32_t* __restrict__ rowidx, const int32_t* 
 #pragma unroll
     for (int k = 0; k < 10; ++k) {
       g[k] = add(g[k], l[k]);
-      if (EXPORT && l[k] != 0.0) fl |= (1u << k);   // NaN != 0 is true: a NaN entry is stored, as in SciPy
+      if (MODE == 1 && l[k] != 0.0) fl |= (1u << k);   // NaN != 0 is true: a NaN entry is stored, as in SciPy
     }
   }
 
-  if (EXPORT) {
+  if (MODE == 1) {
 #pragma unroll
     for (int k = 0; k < 10; ++k) vals[(int64_t)k * vstride + z] = g[k];
     flags[z] = fl;
+  } else if (MODE == 2) {
+    // the element records hold eps (not 1/eps) in this mode: g[X_MINV] is M_eps; `alpha` carries the decoupled shift
+    vals[(int64_t)S_AXX * vstride + z] = add(add(g[X_DXX], g[X_DYY]), -mul(k0sq, g[X_MINV]));
+    vals[(int64_t)S_AXY * vstride + z] = 0.0;
+    vals[(int64_t)S_AYX * vstride + z] = 0.0;
+    vals[(int64_t)S_AYY * vstride + z] = mul(alpha, g[X_M]);
+    vals[(int64_t)S_MINV * vstride + z] = g[X_M];
+    vals[(int64_t)S_DXX * vstride + z] = 0.0;
+    vals[(int64_t)S_DXY * vstride + z] = 0.0;
+    vals[(int64_t)S_DYY * vstride + z] = 0.0;
   } else {
     const double km = mul(k0sq, g[X_M]);
     vals[(int64_t)S_AXX * vstride + z] = add(add(g[X_KXX], mul(alpha, g[X_DXX])), -km);
@@ -319,7 +331,7 @@ void launch_element_setup(plfem_ctx* ctx, const double* d_p, const int32_t* d_ed
                           double* d_elem) {
   const int bs = 128;
   element_setup_kernel<<<(unsigned)((T + bs - 1) / bs), bs, 0, ctx->stream>>>(
-      d_p, d_p + V, d_edofs, T, d_cores, mat.n_cores, mat.eps_core, mat.eps_clad, d_eps_at_quad, d_elem);
+      d_p, d_p + V, d_edofs, T, d_cores, mat.n_cores, mat.eps_core, mat.eps_clad, d_eps_at_quad, mat.scalar_mode != 0, d_elem);
   PLFEM_CUDA(cudaGetLastError());
   ctx->launches++;
 }
@@ -391,24 +403,27 @@ void build_device_pattern(plfem_ctx* ctx, int nb, const PatternSource* src, cons
 // vals[k * vstride + z]; row/column ids index old_of_new, whose entries are DOF ids of THIS design's mesh
 void launch_assemble_slice(plfem_ctx* ctx, int64_t nnz, const int32_t* d_rowidx, const int32_t* d_col, const int32_t* d_old_of_new,
                            const int32_t* d_n2e_ptr, const int32_t* d_n2e, const int32_t* d_edofs, const double* d_elem,
-                           double k0sq, double alpha, bool export_mode, double* d_vals, int64_t vstride, uint32_t* d_flags) {
+                           double k0sq, double alpha, int mode, double* d_vals, int64_t vstride, uint32_t* d_flags) {
   const int bs = 128;
   const unsigned grid = (unsigned)((nnz + bs - 1) / bs);
-  if (export_mode)
-    assemble_kernel<true><<<grid, bs, 0, ctx->stream>>>(nnz, d_rowidx, d_col, d_old_of_new, d_n2e_ptr, d_n2e, d_edofs, d_elem, k0sq,
-                                                        alpha, d_vals, vstride, d_flags);
+  if (mode == 1)
+    assemble_kernel<1><<<grid, bs, 0, ctx->stream>>>(nnz, d_rowidx, d_col, d_old_of_new, d_n2e_ptr, d_n2e, d_edofs, d_elem, k0sq,
+                                                     alpha, d_vals, vstride, d_flags);
+  else if (mode == 2)
+    assemble_kernel<2><<<grid, bs, 0, ctx->stream>>>(nnz, d_rowidx, d_col, d_old_of_new, d_n2e_ptr, d_n2e, d_edofs, d_elem, k0sq,
+                                                     alpha, d_vals, vstride, d_flags);
   else
-    assemble_kernel<false><<<grid, bs, 0, ctx->stream>>>(nnz, d_rowidx, d_col, d_old_of_new, d_n2e_ptr, d_n2e, d_edofs, d_elem, k0sq,
-                                                         alpha, d_vals, vstride, d_flags);
+    assemble_kernel<0><<<grid, bs, 0, ctx->stream>>>(nnz, d_rowidx, d_col, d_old_of_new, d_n2e_ptr, d_n2e, d_edofs, d_elem, k0sq,
+                                                     alpha, d_vals, vstride, d_flags);
   PLFEM_CUDA(cudaGetLastError());
   ctx->launches++;
 }
 
 void launch_assemble(plfem_ctx* ctx, const DevPattern& pat, const int32_t* d_n2e_ptr, const int32_t* d_n2e,
-                     const int32_t* d_edofs, const double* d_elem, double k0sq, double alpha, bool export_mode,
+                     const int32_t* d_edofs, const double* d_elem, double k0sq, double alpha, int mode,
                      double* d_vals, uint32_t* d_flags) {
   launch_assemble_slice(ctx, pat.nnz, pat.rowidx.p, pat.col.p, pat.old_of_new.p, d_n2e_ptr, d_n2e, d_edofs, d_elem, k0sq, alpha,
-                        export_mode, d_vals, pat.nnz, d_flags);
+                        mode, d_vals, pat.nnz, d_flags);
 }
 
 void launch_spmv_csr(plfem_ctx* ctx, int64_t rows, const int32_t* rowptr, const int32_t* col, const double* val,

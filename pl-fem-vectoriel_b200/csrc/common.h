@@ -157,11 +157,11 @@ struct PatternSource { const int32_t* n2e_ptr; const int32_t* n2e; const int32_t
 void build_device_pattern(plfem_ctx* ctx, int nb, const PatternSource* src, const std::vector<int32_t>& node_off,
                           const std::vector<int32_t>& old_of_new, DevPattern& D, std::vector<int64_t>& nnz_off);
 void launch_assemble(plfem_ctx* ctx, const DevPattern& pat, const int32_t* d_n2e_ptr, const int32_t* d_n2e,
-                     const int32_t* d_edofs, const double* d_elem, double k0sq, double alpha, bool export_mode,
+                     const int32_t* d_edofs, const double* d_elem, double k0sq, double alpha, int mode /* 0 solve, 1 export, 2 scalar */,
                      double* d_vals, uint32_t* d_flags);
 void launch_assemble_slice(plfem_ctx* ctx, int64_t nnz, const int32_t* d_rowidx, const int32_t* d_col, const int32_t* d_old_of_new,
                            const int32_t* d_n2e_ptr, const int32_t* d_n2e, const int32_t* d_edofs, const double* d_elem,
-                           double k0sq, double alpha, bool export_mode, double* d_vals, int64_t vstride, uint32_t* d_flags);
+                           double k0sq, double alpha, int mode, double* d_vals, int64_t vstride, uint32_t* d_flags);
 void launch_spmv_csr(plfem_ctx* ctx, int64_t rows, const int32_t* rowptr, const int32_t* col, const double* val,
                      const double* x, double* y);
 

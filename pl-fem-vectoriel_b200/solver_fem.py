@@ -212,3 +212,63 @@ class TrueVectorialMaxwellSolver:
         for _, pb in self._problems.values():
             pb.close()
         self._problems.clear()
+
+
+class ScalarHelmholtzSolver:
+    """Drop-in for the reference's scalar P2 solver (`solver_fem.py:245-276`): modes of
+    ``(K - k0^2 M_eps) v = lambda M v`` nearest ``sigma = -(k0 (n_core - 0.008))^2``, ``n_eff = sqrt(-lambda) / k0``.
+
+    Runs on the same CUDA kernels as the vectorial solver: the scalar pencil occupies the Hx block of the two-unknowns-per-node
+    layout (material ``scalar_mode``), the Hy block carries ``(shift M, M)`` whose eigenvalues all equal ``shift``, far from
+    ``sigma``, so it never enters the wanted set; no boundary DOF is eliminated (the reference does not call ``get_dofs``).
+    Records carry the reference's keys: ``n_eff, beta, field_vector, confinement, core_overlap, PDL_dB = 0,
+    polarization = 'scalar', is_vectorial = False``; ``field_vector`` is M-normalised over all N DOFs."""
+
+    def __init__(self, geometry, device: int = 0, ctx=None):
+        _cabi.load()
+        self.geometry = geometry
+        self.k0 = geometry.k0
+        self.device = int(device)
+        self._ctx = ctx
+        self.last_stats: Dict = {}
+
+    def solve(self, mesh, n_modes_target: int = 20) -> List[Dict]:
+        geo = self.geometry
+        pb = _cabi.Problem(mesh, self._ctx or _cabi.Context.get(self.device))
+        try:
+            eps_q = None
+            if not has_disc_epsilon(geo):
+                xy = pb.quad_points()
+                eps_q = np.real(geo.epsilon(xy[0], xy[1]))
+            mat, _keep = _cabi.material_struct(geo, 1.0, eps_q)
+            pb.assemble(mat)
+            M = pb.export_csr("M")                                      # plain mass matrix, all N DOFs (for the M-norm)
+            _, loc, _, _ = pb.dofs()
+            pb.set_dirichlet(False)
+            N = pb.N
+            sigma = -(self.k0 * (geo.n_core - 0.008)) ** 2
+            mat.scalar_mode = 1
+            mat.scalar_shift = 1.0e3 * max(1.0, abs(sigma))
+            k = min(n_modes_target + 8, N - 4)
+            evals, evecs, _met, _nc, stats = pb.solve_modes(mat, sigma, k, tol=_cabi.EIG_TOL, maxiter=6000)
+            self.last_stats = stats.as_dict()
+        finally:
+            pb.close()
+        x_dof, y_dof = loc
+        in_core = np.zeros(N, dtype=bool)
+        for (cx, cy), r in zip(geo.positions, geo.core_radii):
+            in_core |= (x_dof - cx) ** 2 + (y_dof - cy) ** 2 <= r ** 2
+        modes = []
+        for lam, vec in zip(evals, evecs):
+            if lam >= 0:
+                continue
+            ne = np.sqrt(-lam) / self.k0
+            if ne <= geo.n_clad or ne >= geo.n_core * 1.005:
+                continue
+            v = np.array(vec[:N])
+            v /= np.sqrt(float(v @ (M @ v))) + 1e-30
+            conf = float(np.sum(v[in_core] ** 2) / np.sum(v ** 2))
+            modes.append(ModeRecord({"n_eff": float(ne), "beta": float(self.k0 * ne), "field_vector": v, "confinement": conf,
+                                     "core_overlap": conf, "PDL_dB": 0.0, "polarization": "scalar", "is_vectorial": False}))
+        modes.sort(key=lambda m: m["n_eff"], reverse=True)
+        return modes

@@ -29,7 +29,7 @@ def test_struct_layouts_match_header(tmp_path):
     import shutil
     import subprocess
     assert ctypes.sizeof(_cabi.MeshInfo) == 64
-    assert ctypes.sizeof(_cabi.Material) == 64
+    assert ctypes.sizeof(_cabi.Material) == 80
     assert ctypes.sizeof(_cabi.SolveOpts) == 64
     assert ctypes.sizeof(_cabi.SolveStats) == 112
     gcc = shutil.which("gcc")

@@ -405,3 +405,26 @@ def test_structured_mesh_is_solved_without_refinement():
     s = O.interior_system(g, mesh)
     ref = np.sort(eigsh(s["A_int"], k=22, M=s["B_int"], sigma=sigma, which="LM", tol=1e-10)[0])
     assert np.abs(np.sort(vals) / ref - 1).max() < 1e-8
+
+
+@pytest.mark.gpu
+def test_scalar_helmholtz_solver_matches_oracle(small_case):
+    """`ScalarHelmholtzSolver.solve` (`solver_fem.py:245-276`) on the CUDA kernels (scalar pencil in the Hx block, natural
+    boundary condition) against the oracle's restatement with the real eigsh: same modes, n_eff to 1e-8."""
+    from plfem_b200.solver_fem import ScalarHelmholtzSolver
+    g, mesh = small_case
+    ref = O.solve_scalar_modes(g, mesh, 6)
+    s = ScalarHelmholtzSolver(g)
+    got = s.solve(mesh, 6)
+    assert len(got) == len(ref) > 0 and s.last_stats["max_residual"] < 1e-9
+    for a, b in zip(got, ref):
+        assert abs(a["n_eff"] / b["n_eff"] - 1) < 1e-8
+        assert a["polarization"] == "scalar" and a["is_vectorial"] is False and a["PDL_dB"] == 0.0
+        assert a["field_vector"].shape == b["field_vector"].shape
+    ne = np.array([m["n_eff"] for m in ref])
+    lonely = [i for i in range(len(ne)) if np.min(np.abs(np.delete(ne, i) - ne[i])) > 1e-4]     # non-degenerate modes
+    assert lonely
+    for i in lonely:
+        assert abs(got[i]["confinement"] - ref[i]["confinement"]) < 1e-6
+        c = abs(float(got[i]["field_vector"] @ ref[i]["field_vector"])) / (np.linalg.norm(got[i]["field_vector"]) * np.linalg.norm(ref[i]["field_vector"]))
+        assert c > 1 - 1e-8
