@@ -52,6 +52,12 @@ WORKLOADS = {
     # BASELINE.json configs[1]
     "cfg2": dict(name="cfg2: 19-core hex_1plus6plus12 MCF, r=1.5um, pitch 8um, Cauchy IP-Dip/air, 1550nm, n_modes=40",
                  n_cores=19, pitch=8.0, r=1.5, n_core=None, lam=1.55, n_modes=40),
+    # BASELINE.json configs[3]: a fixed sample of the stratified-LHS dataset (all 12 layouts, mixed mesh sizes and k)
+    "cfg4": dict(name="cfg4: fixed sample of the 2,000-design stratified LHS (12 MCF layouts, r 0.5-3um, pitch 3-15um, 4 bands, "
+                      "n_modes=min(3 N_cores, 40)), designs sorted into forests by mesh size"),
+    # BASELINE.json configs[4]: the ~2M-unknown structured stress mesh (real arithmetic: the reference takes Re(eps))
+    "cfg5": dict(name="cfg5: structured stress mesh, 500x500 cells split on one diagonal over a 64um square, cfg-1 cores, 1550nm, "
+                      "n_modes=10 (dim 1,996,002)", n_cores=7, pitch=8.0, r=1.5, n_core=1.535, lam=1.55, n_modes=10, cells=500),
 }
 
 
@@ -60,8 +66,32 @@ def make_case(name):
     w = WORKLOADS[name]
     n_core = w["n_core"] if w["n_core"] is not None else P.IPDipCauchy.n(1000 * w["lam"])
     g = P.MCFGeometry(w["n_cores"], w["pitch"], w["r"], n_core, 1.0, w["lam"])
-    mesh, _ = P.MeshGenerator.generate(g, 1.0)
+    if "cells" in w:
+        mesh = P.MeshTri.init_structured(w["cells"], w["cells"], 32.0)
+    else:
+        mesh, _ = P.MeshGenerator.generate(g, 1.0)
     return w, g, mesh
+
+
+def make_jobs(name, n_jobs, forest):
+    """The (geometry, mesh, n_modes) jobs of ONE step and how they are grouped into forests.  cfg1/cfg2/cfg5: n_jobs copies of
+    the configuration's design.  cfg4: the first n_jobs designs of the seeded LHS sample, sorted by mesh size and cut into
+    forests of `forest` designs — designs of similar size converge and finish together, which keeps the lockstep idle share low
+    (size-sorted partition)."""
+    import plfem_b200 as P
+    if name != "cfg4":
+        w, g, mesh = make_case(name)
+        return w, [(g, mesh, w["n_modes"])] * n_jobs
+    from plfem_b200 import sweep
+    designs = sweep.lhs_designs(max(n_jobs * 2, 48), seed=42)
+    designs = [designs[i] for i in np.random.default_rng(7).permutation(len(designs))[:n_jobs]]      # every layout, fixed order
+    jobs = []
+    for d in designs:
+        g = sweep.design_geometry(d)
+        mesh, _ = P.MeshGenerator.generate(g, 1.0)
+        jobs.append((g, mesh, d["n_modes"]))
+    jobs.sort(key=lambda j: j[1].p.shape[1] * (j[2] + 12))
+    return WORKLOADS[name], jobs
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -157,7 +187,7 @@ def run_reference(args):
     if rank != 0:
         return
     import multiprocessing as mp
-    name = args.workload if args.workload in WORKLOADS else "cfg1"
+    name = args.workload if args.workload in ("cfg1", "cfg2") else "cfg1"
     cores = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     w, g, mesh = make_case(name)
     os.environ.update(_ONE_THREAD)          # inherited by the spawned workers BEFORE they import NumPy
@@ -210,8 +240,12 @@ def run_ours(args):
         pass
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
 
-    w, g, mesh = make_case(args.workload)
-    n_modes = w["n_modes"]
+    # designs per forest / forests in flight: cfg5 is ONE 2M-unknown design per step (a forest of one, one worker)
+    B = 1 if args.workload == "cfg5" else max(1, args.inflight)
+    NW = 1 if args.workload == "cfg5" else max(1, args.workers)
+    w, jobs = make_jobs(args.workload, B * NW, B)
+    forests = [jobs[i * B:(i + 1) * B] for i in range(NW)]          # forest i of a step is worker i's
+    g, mesh, n_modes = forests[-1][-1]                              # the largest design (cfg4: sorted) for latency / sizes
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=f"cuda:{local}")
 
     def sync_all():
@@ -224,45 +258,66 @@ def run_ours(args):
         flush.fill_(1)
         torch.cuda.synchronize(local)
 
-    # ---- value: a step = ONE forest of B designs; mesh + DOF tables resident, everything else inside ------
-    B = max(1, args.inflight)
-    NW = max(1, args.workers)
-    NF = args.steps * NW                                   # forests in the timed region: a step = one forest per worker thread
+    # ---- value: a step = ONE forest of B designs per worker; meshes + DOF tables resident, everything else inside ------
+    K = args.steps
     pool = ForestPool(device=local, batch=B, workers=NW, want_vectors=False)
-    sigma = sigma_estimate(g)
-    mat, keep = _cabi.material_struct(g)
-    by_ctx = {}                                            # B resident problems per worker context
+    resident = {}                                          # worker index -> (problems, materials, shifts, ks) of its forest
 
-    def resident(c):
-        if id(c) not in by_ctx:
-            by_ctx[id(c)] = [_cabi.Problem(mesh, c) for _ in range(B)]   # created during warm-up, outside the timed region
-        return by_ctx[id(c)]
+    def prepare(_pool, c, wi):
+        if wi not in resident:                             # created during warm-up, outside the timed region
+            pbs = [_cabi.Problem(j[1], c) for j in forests[wi]]
+            mk = [_cabi.material_struct(j[0]) for j in forests[wi]]
+            resident[wi] = (pbs, [m for m, _ in mk], [sigma_estimate(j[0]) for j in forests[wi]],
+                            [min(j[2] + 12, 2 * pb.n_interior - 4) for j, pb in zip(forests[wi], pbs)], mk)
+        return resident[wi]
 
-    def forest_resident(_pool, c, _):
-        pbs = resident(c)
-        kk = min(n_modes + 12, 2 * pbs[0].n_interior - 4)
-        return _cabi.solve_modes_batch(c, pbs, [mat] * B, [sigma] * B, [kk] * B, tol=_cabi.EIG_TOL, maxiter=12000, want_vectors=False,
-                                       reuse_symbolic=False)
+    def forest_resident(_pool, c, wi, reps=1):
+        pbs, mats, sig, ks, _keep = prepare(_pool, c, wi)
+        out = []
+        for _ in range(reps):
+            out.append(_cabi.solve_modes_batch(c, pbs, mats, sig, ks, tol=_cabi.EIG_TOL, maxiter=12000, want_vectors=False,
+                                               reuse_symbolic=False))
+        return out
+
+    widx = iter(range(NW))
+    lock = threading.Lock()
+
+    def my_index():
+        with lock:
+            return next(widx)
+    tl = threading.local()
+
+    def on_worker(p_, c, reps):
+        if not hasattr(tl, "wi"):
+            tl.wi = my_index()                             # a worker thread keeps its forest (and its resident problems)
+        return forest_resident(p_, c, tl.wi, reps)
 
     for _ in range(args.warmup):                           # every worker thread gets its context and problems
-        pool.on_every_worker(lambda p_, c: forest_resident(p_, c, 0))
+        pool.on_every_worker(lambda p_, c: on_worker(p_, c, 1))
+    NF = K * NW
     launches, phase = 0, {n: 0.0 for n in ("ms_symbolic", "ms_symbolic_wall", "ms_assemble", "ms_factor", "ms_lanczos", "ms_metrics", "ms_total")}
     records = np.full((NF * B, N_RECORD), np.nan)
+    idle_num = idle_den = 0.0
     flush_l2()
     sync_all()
     with ClockSampler(local) as clocks:
         t0, c0 = time.perf_counter(), time.process_time()
-        outs = pool.map_forests(forest_resident, range(NF))              # K x workers forests, pipelined over the worker threads
+        outs = pool.on_every_worker(lambda p_, c: on_worker(p_, c, K))   # K forests per worker thread, NW threads side by side
         torch.cuda.synchronize(local)
         t_value, cpu_value = time.perf_counter() - t0, time.process_time() - c0
-        for i, forest in enumerate(outs):
-            st = forest[0][4]
-            launches += st.kernel_launches
-            for n in phase:
-                phase[n] += getattr(st, n)
-            for j, f in enumerate(forest):
-                assert f[5] == 0, "a design failed"
-                records[i * B + j, 0], records[i * B + j, 1], records[i * B + j, 3] = (rank * NF + i) * B + j, 1.0, st.ms_total * 1e-3 / B
+        i = 0
+        for per_worker in outs:
+            for forest in per_worker:
+                st = forest[0][4]
+                launches += st.kernel_launches
+                for n in phase:
+                    phase[n] += getattr(st, n)
+                for j, f in enumerate(forest):
+                    assert f[5] == 0, "a design failed"
+                    records[i * B + j, 0], records[i * B + j, 1], records[i * B + j, 3] = (rank * NF + i) * B + j, 1.0, st.ms_total * 1e-3 / B
+                    idle_num += st.batch_block_ops - f[4].n_block_op      # block steps a design was carried after converging
+                    idle_den += st.batch_block_ops
+                i += 1
         if world > 1:          # the sweep's single collective, inside the timed region
             t0 = time.perf_counter()
             allrec = gather_records(records, world * NF * B, rank, world, local)
@@ -272,17 +327,17 @@ def run_ours(args):
     stats = st.as_dict()
 
     # ---- e2e: public API, host buffers in, mode records (with eigenvectors) out -----------------------------
-    pool_e = ForestPool(device=local, batch=B, workers=max(1, args.workers), want_vectors=True)
-    jobs = [(g, mesh, n_modes)] * B
+    pool_e = ForestPool(device=local, batch=B, workers=NW, want_vectors=True)
+    step_jobs = [j for f in forests for j in f]
 
     for _ in range(args.warmup):
-        pool_e.on_every_worker(lambda p_, c: p_.solve_forest(jobs))
+        pool_e.on_every_worker(lambda p_, c: p_.solve_forest(forests[0]))
     flush_l2()
     sync_all()
     with ClockSampler(local) as clocks2:
         t0, c0 = time.perf_counter(), time.process_time()
         n_rec = 0
-        for modes in pool_e.solve_iter(jobs * NF):     # records consumed as they arrive (a dataset writer would
+        for modes in pool_e.solve_iter(step_jobs * K):     # records consumed as they arrive (a dataset writer would
             assert not isinstance(modes, Exception), modes     # reduce each to its 86-slot row here)
             n_rec += len(modes) > 0
         torch.cuda.synchronize(local)
@@ -295,7 +350,7 @@ def run_ours(args):
     lat_stats = {}
     if rank == 0:
         _cabi.load().plfem_set_host_threads(0)
-        for i in range(3 + min(args.steps, 10)):
+        for i in range(3 + min(args.steps, 10 if args.workload != "cfg5" else 2)):
             flush_l2()
             t0 = time.perf_counter()
             s1 = TrueVectorialMaxwellSolver(g, device=local)
@@ -305,11 +360,15 @@ def run_ours(args):
             lat.append(time.perf_counter() - t0)
         lat = lat[3:]
     ctx0 = _cabi.Context.get(local)
-    pbs0 = [_cabi.Problem(mesh, ctx0) for _ in range(B)]
-    n_solve = pbs0[0].n_interior
+    pbs0 = [_cabi.Problem(j[1], ctx0) for j in forests[-1]]
+    n_solve = pbs0[-1].n_interior
     k = min(n_modes + 12, 2 * n_solve - 4)
-    h2d = NW * B * (mesh.p.nbytes + mesh.t.astype(np.int64).nbytes + 8 * (3 * g.n_cores + 4))
-    d2h = NW * B * 8 * (k + k * 2 * n_solve + k * _cabi.NMETRICS)
+    h2d = sum(j[1].p.nbytes + j[1].t.astype(np.int64).nbytes + 8 * (3 * j[0].n_cores + 4) for j in step_jobs)
+    d2h = 0
+    for f, wi in zip(forests, range(NW)):
+        for j, pb in zip(f, resident[wi][0]):
+            kk = min(j[2] + 12, 2 * pb.n_interior - 4)
+            d2h += 8 * (kk + kk * 2 * pb.n_interior + kk * _cabi.NMETRICS)
 
     if world > 1:
         tt = torch.tensor([t_value, t_e2e], dtype=torch.float64, device=f"cuda:{local}")
@@ -326,53 +385,63 @@ def run_ours(args):
         return
 
     # ---- per-kernel roofline of a forest (CUDA events on the library's stream, L2 flushed per repetition) ----
-    fo = _cabi.solve_modes_batch(ctx0, pbs0, [mat] * B, [sigma] * B, [k] * B, want_vectors=False)   # leaves plan + factors on the device
-    fstats = fo[0][4].as_dict()
-    prof, nb_prof = ctx0.profile_last(repeat=10)
+    mk0 = [_cabi.material_struct(j[0]) for j in forests[-1]]
+    fo = _cabi.solve_modes_batch(ctx0, pbs0, [m for m, _ in mk0], [sigma_estimate(j[0]) for j in forests[-1]],
+                                 [min(j[2] + 12, 2 * pb.n_interior - 4) for j, pb in zip(forests[-1], pbs0)], want_vectors=False)   # leaves plan + factors on the device
+    fstats = fo[-1][4].as_dict()
+    prof, nb_prof = ctx0.profile_last(repeat=10 if args.workload != "cfg5" else 3)
     nblk = fstats["batch_block_ops"]
     n_sweeps = nblk * (1 + int(fstats["refine_steps"]))        # block-LDL^T solves per operator application: 1 + refinement steps
     fkey, bkey = "forward_sweep_4rhs", "backward_sweep_4rhs"
     share = {k_: 0.0 for k_ in prof}
     share.update({fkey: n_sweeps * prof[fkey][0], bkey: n_sweeps * prof[bkey][0], "factorize": prof["factorize"][0],
-                  "assemble": prof["assemble"][0], "spmm_B": nblk * prof["spmm_B"][0], "spmv_K_residual": nblk * prof["spmv_K_residual"][0]})
-    dom = max(share, key=share.get)
+                  "assemble": prof["assemble"][0], "spmm_B": nblk * prof["spmm_B"][0],
+                  "spmv_K_residual": nblk * int(fstats["refine_steps"]) * prof["spmv_K_residual"][0]})
+    dom = max((k_ for k_ in share if k_ != "factorize"), key=share.get)      # "factorize" is a phase of five kernels, reported apart
     kernels = {}
     for name, (ms, nbytes) in prof.items():
         gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else None
         kernels[name] = {"ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak if gbs else None,
                          "est_ms_per_forest": share[name]}
+    # FP64 side of the factorisation: flops of the plan (inverse + W + Schur) over the measured factorisation time
+    fl = sum(f[4].factor_flops for f in fo)
+    kernels["factorize"]["fp64_tflops"] = fl / (prof["factorize"][0] * 1e-3) / 1e12
+    kernels["factorize"]["factor_gflop"] = fl / 1e9
     launches_per = fstats["n_levels"] if "sweep" in dom else 1
     ms_dom, bytes_dom = prof[dom]
     traffic = None          # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (same forest size)
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        tr = tj["sweeps"].get(dom)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        tr = tj["sweeps"].get(dom) if tj.get("workload", "cfg1") == args.workload else None
         if tr:      # whole-sweep DRAM bytes of the captured forest, scaled to this forest (traffic is proportional to the
             #         designs) and spread over the same launches `achieved` is quoted per
             traffic = tr["dram_bytes"] * nb_prof / float(tj.get("designs", 12)) / launches_per
     except Exception:
         pass
-    roofline = {"kernel": {"forward_sweep": "forward_subtree_kernel<1> (leaf fronts) + forward_kernel<1> (one launch per level)",
-                           "backward_sweep": "backward_kernel<1> (one launch per level) + backward_subtree_kernel<1> (leaf fronts)",
-                           "forward_sweep_4rhs": "forward_subtree_kernel<4> (leaf fronts) + forward_kernel<4> (one launch per level)",
-                           "backward_sweep_4rhs": "backward_kernel<4> (one launch per level) + backward_subtree_kernel<4> (leaf fronts)",
+    roofline = {"kernel": {"forward_sweep": "stream_forward_kernel<1> (bottom subtrees, TMA-streamed) + forward_kernel<1> (one launch per level above)",
+                           "backward_sweep": "backward_kernel<1> (one launch per level) + stream_backward_kernel<1> (bottom subtrees, TMA-streamed)",
+                           "forward_sweep_4rhs": "stream_forward_kernel<4> (bottom subtrees, TMA-streamed) + forward_kernel<4> (one launch per level above)",
+                           "backward_sweep_4rhs": "backward_kernel<4> (one launch per level) + stream_backward_kernel<4> (bottom subtrees, TMA-streamed)",
                            "factorize": "invert_kernel+gemm",
                            "assemble": "assemble_kernel", "spmm_B": "spmm_b_kernel", "spmv_K_residual": "resid_k_kernel"}[dom],
-                "bound": "hbm", "achieved": bytes_dom / (ms_dom * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "name": dom, "bound": "hbm", "achieved": bytes_dom / (ms_dom * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": bytes_dom / (ms_dom * 1e-3) / 1e9 / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "per_launch": {"launches_per_sweep": launches_per, "avg_launch_us": 1e3 * ms_dom / launches_per,
                                "algorithmic_bytes_per_launch": bytes_dom / launches_per, "designs_per_launch": nb_prof},
-                "note": "one sweep = one launch per elimination-tree level carrying the fronts of all designs of the forest; "
-                        "algorithmic bytes = factor entries of the left block columns (8 B each) + the right-hand sides; L2 flushed before each timed sweep"}
+                "note": "one sweep = one TMA-streamed launch for the bottom subtrees + one launch per elimination-tree level above them, all carrying "
+                        "the fronts of every design of the forest; algorithmic bytes = factor entries of the left block columns (8 B each) + the "
+                        "right-hand sides; L2 flushed before each timed sweep"}
 
-    cpu = cpu_baseline_sample(args.workload, 2) if world == 1 else None
+    cpu = cpu_baseline_sample(args.workload, 2) if (world == 1 and args.workload in ("cfg1", "cfg2")) else None
     pool.close()
     nst = args.steps
     line = {"metric": "modal_solves_per_sec", "value": world * B * NF / t_value, "unit": "solves/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_value / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["name"], "mesh": {"V": int(mesh.p.shape[1]), "T": int(mesh.t.shape[1]), "N_p2": int(pbs0[0].N),
-                                                       "dim": 2 * n_solve, "recipe": "reference point recipe, refinement 1.0, flat hull triangles dropped"},
+            "config": {"workload": w["name"], "mesh": {"V": int(mesh.p.shape[1]), "T": int(mesh.t.shape[1]), "N_p2": int(pbs0[-1].N),
+                                                       "dim": 2 * n_solve, "recipe": "structured cells" if args.workload == "cfg5" else "reference point recipe, refinement 1.0, flat hull triangles dropped",
+                                                       "note": "largest design of the step" if args.workload == "cfg4" else "every design of the step"},
+                       "lockstep_idle_fraction": idle_num / max(idle_den, 1.0),
                        "step": f"{NW} forests (one per host thread / context) of {B} independent modal solves each = {NW * B} solves; the designs "
                                f"of a forest (each with its own symbolic analysis, assembly, factorisation, eigensolve and reductions) share "
                                f"every kernel launch, the {NW} forests in flight overlap host analysis and device work",
@@ -410,7 +479,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg1", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg1", choices=sorted(WORKLOADS),
+                    help="cfg1 (default, the configuration the metric is quoted on), cfg2, cfg4 (heterogeneous LHS sample), cfg5 (2M unknowns)")
     ap.add_argument("--inflight", type=int, default=12, help="designs per forest (= per step)")
     ap.add_argument("--workers", type=int, default=6, help="host threads / contexts, each working on its own forest")
     args = ap.parse_args()
