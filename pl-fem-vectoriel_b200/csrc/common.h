@@ -166,20 +166,6 @@ void launch_spmv_csr(plfem_ctx* ctx, int64_t rows, const int32_t* rowptr, const 
                      const double* x, double* y);
 
 // ---- multifrontal factorisation and solves (factor.cu) ------------------------------------------------
-// one forward work item: (front, slab of rows) with everything the kernel needs, so that no plan metadata
-// has to be chased through dependent loads on the critical path
-struct FwdItem {
-  int32_t f, row0, nrows, G, s2, ld;     // ld = leading dimension of the front's packed left block column
-  int32_t ch0, ch1, tgt0, tgt1;          // first two children and the number of forward items each must complete
-  int32_t uoff, goff, nchild, nf2;       // update-vector offset, gather-table offset, children, rows of the front
-  int64_t foff, g0;                      // packed panel offset, first unknown of the front
-};
-struct BwdItem {
-  int32_t f, col0, ncols, s2, u2, ld, soff, parent;   // ld = leading dimension of the row-major copy of W
-  int32_t tgt_f, tgt_pf, tgt_pb, G;      // forward items of f, forward / backward items of the parent; column groups
-  int64_t foff, g0;                      // offset of the W copy, first unknown of the front
-};
-
 // ---- TMA-streamed bottom subtrees of the sweeps (sweep_stream.cu) --------------------------------------------------
 constexpr int ST_CHUNK_DOUBLES = 512;   // one bulk copy / ring stage: 4 KB
 constexpr int ST_NLOC = 320;            // unknowns of a subtree's local vector: its pivots + the update set of its root
@@ -194,11 +180,26 @@ struct StreamSub {                      // one bottom subtree = one warp
 struct StreamPackRec {                  // where one front of a subtree starts in the two streams (cursor before its items)
   int32_t f, sub, fchunk, fpos, bchunk, bpos, lm_off, pad;
 };
+// one task of a per-level launch (fronts above the bottom subtrees): a slab of a front's left block column (forward) or of its
+// W block (backward), streamed from its own chunk-aligned piece of the level streams
+struct LevelTask {
+  int64_t soff, g0;                     // stream offset (doubles), first unknown of the front
+  int32_t chunks, s2, u2, r0, n;        // chunks of the task's stream; pivot / update unknowns; first row (fwd) or pivot column (bwd), count
+  int32_t goff;                         // forward: the front's gather tables in gsrc; backward: its update set in strct
+  int32_t uoff;                         // forward: the front's update vector in the update pool
+  int32_t nch;                          // forward: children of the front; backward: slab class 8 / 16 (lanes split the contraction) or 0 (wide)
+  int32_t f, pad;
+};
 struct StreamPlan {
   int n_subs = 0, n_fronts = 0;
   int64_t fwd_doubles = 0, bwd_doubles = 0;   // stream lengths including chunk padding
   DevBuf<StreamSub> subs; DevBuf<int4> fronts; DevBuf<StreamPackRec> recs; DevBuf<uint16_t> lmaps;
   DevBuf<double> sfwd, sbwd;
+  // fronts above the subtrees: per-level task lists and their streams
+  DevBuf<LevelTask> ftasks, btasks;
+  std::vector<int32_t> fptr, bptr;            // [nlevels+1]
+  DevBuf<double> lfwd, lbwd;
+  int64_t lfwd_doubles = 0, lbwd_doubles = 0;
 };
 
 struct DevPlan {
@@ -212,14 +213,9 @@ struct DevPlan {
   // per-level work lists (host-built): tiles for the two GEMMs, slabs for extend-add and the sweeps
   DevBuf<int4> w_tiles, s_tiles, ea_slabs;
   DevBuf<int32_t> gsrc;
-  std::vector<int32_t> w_ptr, s_ptr, ea_ptr, fwd_ptr, bwd_ptr;  // [nlevels+1] each
-  // per-level launch lists (CTA items of the fronts above the bottom subtrees) + the subtrees' warp tasks
-  DevBuf<FwdItem> fwdb_items; DevBuf<BwdItem> bwdb_items;
-  std::vector<int32_t> fwdb_ptr, bwdb_ptr;     // [nlevels+1] each
+  std::vector<int32_t> w_ptr, s_ptr, ea_ptr;  // [nlevels+1] each
   StreamPlan st;                     // bottom subtrees: TMA-streamed, one warp each
   DevBuf<uint8_t> in_sub;            // front covered by a bottom subtree
-  DevBuf<int64_t> lo, wo; DevBuf<int32_t> ldp; // packed panels: [F11^-1 ; W^T] (ldp x 2s) and W row-major (s2p x 2u)
-  DevBuf<double> fac;                // packed factor panels: the only matrix data the sweeps read
   DevBuf<double> pool;               // all frontal matrices (factorisation workspace)
   DevBuf<double> upd;                // per-front update vectors of the forward sweep
   DevBuf<int32_t> status;            // [0] = 1 when a pivot block was singular
@@ -227,6 +223,10 @@ struct DevPlan {
 };
 void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D);
 void build_stream_plan(plfem_ctx* ctx, const FrontPlan& P, const std::vector<int32_t>& uoff, std::vector<uint8_t>& in_sub, StreamPlan& S);
+void build_level_plan(plfem_ctx* ctx, const FrontPlan& P, const std::vector<int32_t>& uoff, const std::vector<uint8_t>& in_sub,
+                      const std::vector<int32_t>& goff, StreamPlan& S);
+void launch_level_forward(plfem_ctx* ctx, const DevPlan& D, int level, const double* rhs, double* out, int nrhs, bool pdl);
+void launch_level_backward(plfem_ctx* ctx, const DevPlan& D, int level, double* x, int nrhs, bool pdl);
 void launch_stream_pack(plfem_ctx* ctx, const DevPlan& D);
 void launch_stream_forward(plfem_ctx* ctx, const DevPlan& D, const double* rhs, double* out, int nrhs, bool pdl);
 void launch_stream_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs, bool pdl);

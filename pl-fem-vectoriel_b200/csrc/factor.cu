@@ -269,505 +269,6 @@ __global__ void __launch_bounds__(256) gemm_schur_kernel(const int4* __restrict_
                          F + (int64_t)s2 * ld + s2, ld, u2, u2, s2, t.y, t.z);
 }
 
-// ---- sweep work items --------------------------------------------------------------------------------------
-// A sweep is a chain of ~2 x levels dependent steps, each a handful of microseconds of which most used to be
-// dependent L2 round trips chasing plan metadata (slab -> front -> children -> maps -> values).  Every item
-// now carries all it needs in one 96-byte record, the child->parent maps are flattened per parent row into
-// two source offsets (first and second child), and everything static — the record, the source offsets, the
-// factor entries the thread will multiply — is loaded BEFORE the item waits for its dependencies, so the
-// critical path of a step is: see the flag, one gather of the freshly written values, FMAs from registers,
-// write, signal.
-template <int NR>
-struct SweepSmem {
-  double y[MAX_PIV][NR];          // assembled pivot part of the right-hand sides, [k][rhs] (one 16/32-byte read per k)
-  double part[8][2][NR][32];      // partial sums: [warp][row of the thread][rhs][lane]
-};
-
-// The NR right-hand sides of a sweep are INTERLEAVED: entry i of all of them is rhs[i*NR .. i*NR+NR), one 32-byte
-// sector for NR = 4.  Every gather of the sweeps (children's updates, ancestors' unknowns) fetches all right-hand
-// sides of an index at once, so this costs one sector and two 128-bit loads per index instead of four of each.
-struct RhsView {
-  const double* rhs; double* out; double* upd;
-};
-
-// CG = true: values produced by other CTAs of the SAME launch (dataflow kernel) are read with ld.global.cg,
-// i.e. from L2, never from a possibly stale L1 line.
-template <bool CG>
-__device__ __forceinline__ double ldx(const double* p) { return CG ? __ldcg(p) : *p; }
-
-// all NR right-hand sides of entry idx of an interleaved vector block
-template <bool CG, int NR>
-__device__ __forceinline__ void ldv(const double* base, int64_t idx, double (&v)[NR]) {
-  if constexpr (NR % 2 == 0) {
-    const double2* p = reinterpret_cast<const double2*>(base + idx * NR);
-#pragma unroll
-    for (int r = 0; r < NR / 2; ++r) { const double2 t = CG ? __ldcg(p + r) : p[r]; v[2 * r] = t.x; v[2 * r + 1] = t.y; }
-  } else {
-#pragma unroll
-    for (int r = 0; r < NR; ++r) v[r] = ldx<CG>(base + idx * NR + r);
-  }
-}
-template <int NR>
-__device__ __forceinline__ void stv(double* base, int64_t idx, const double (&v)[NR]) {
-  if constexpr (NR % 2 == 0) {
-    double2* p = reinterpret_cast<double2*>(base + idx * NR);
-#pragma unroll
-    for (int r = 0; r < NR / 2; ++r) p[r] = make_double2(v[2 * r], v[2 * r + 1]);
-  } else {
-#pragma unroll
-    for (int r = 0; r < NR; ++r) base[idx * NR + r] = v[r];
-  }
-}
-
-__device__ __forceinline__ void wait_count(const int32_t* ctr, int32_t target, int32_t* status) {
-  const volatile int32_t* v = ctr;
-  unsigned spins = 0;
-  while (*v < target) {
-    if (++spins > (1u << 22)) { atomicExch(status + 1, 1); break; }   // ~seconds: report instead of hanging
-  }
-}
-
-// Programmatic dependent launch: a kernel launched with the programmatic-serialisation attribute may start
-// while its predecessor in the stream is still running; everything before griddep_wait() (the static
-// prefetch) overlaps the predecessor's tail, everything after it sees the predecessor's writes.
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
-struct Deps {          // dataflow bookkeeping of the persistent kernel (unused by the per-level kernels)
-  int32_t* fdone; int32_t* bdone; int32_t* status; int epoch; const int32_t* nfs;
-};
-
-constexpr int FQ = 16;  // factor entries per thread in flight before the wait
-
-// NR doubles of one row of a [.][NR] shared array: a single 128-bit load per pair of right-hand sides
-template <int NR>
-__device__ __forceinline__ void lds_row(const double (*a)[NR], int k, double (&v)[NR]) {
-  if constexpr (NR % 2 == 0) {
-    const double2* p = reinterpret_cast<const double2*>(a[k]);
-#pragma unroll
-    for (int r = 0; r < NR / 2; ++r) { const double2 t = p[r]; v[2 * r] = t.x; v[2 * r + 1] = t.y; }
-  } else {
-#pragma unroll
-    for (int r = 0; r < NR; ++r) v[r] = a[k][r];
-  }
-}
-
-// forward: one CTA (8 warps) per (front, slab of 32*G*R rows) of the packed left block column.  The 8 warps form G
-// row groups x 8/G slices of the k range (the 2s pivot columns), every thread owns R rows 32 apart; partial sums
-// meet in shared memory.  The loops are lean on purpose — ncu showed the previous version issue-bound at ~80 warp
-// instructions per loaded factor entry: loop bounds are warp-uniform, rows past the end of the slab read row 0
-// (and are discarded) instead of predicating every load, the assembled right-hand sides are read with one 128-bit
-// shared load per pair, pointers advance by a constant stride.
-template <bool CG, int NR, int R, bool PDL>
-__device__ __forceinline__ void forward_item_r(const FwdItem& it, const int32_t* __restrict__ gsrc, const PlanView& P,
-                                               const RhsView& rv, SweepSmem<NR>& sm, const Deps& dp) {
-  constexpr int FQR = FQ / R;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int s2 = it.s2, nrows = it.nrows, row0 = it.row0, G = it.G & 0xff, nf2 = it.nf2;
-  const int64_t ld = it.ld;
-  const int nks = 8 / G, rg = warp % G, ks = warp / G;
-  // ---- static prefetch: gather sources and this thread's factor entries
-  const int32_t* g1 = gsrc + it.goff;       // first child: source offset into upd per front row, -1 = none
-  const int32_t* g2 = g1 + nf2;             // second child
-  int i1 = -1, i2 = -1;
-  if (tid < s2) { i1 = g1[tid]; i2 = g2[tid]; }
-  int lr[R]; bool ok[R]; int j1[R], j2[R];
-#pragma unroll
-  for (int q = 0; q < R; ++q) {
-    lr[q] = (rg * R + q) * 32 + lane;
-    ok[q] = lr[q] < nrows;
-    j1[q] = j2[q] = -1;
-    if (ks == 0 && ok[q] && row0 + lr[q] >= s2) { j1[q] = g1[row0 + lr[q]]; j2[q] = g2[row0 + lr[q]]; }
-  }
-  const int nk = (s2 - ks + nks - 1) / nks;          // k's of this warp's slice: ks, ks + nks, ...  (warp-uniform)
-  const int64_t step = (int64_t)nks * ld;
-  const double* p[R];
-#pragma unroll
-  for (int q = 0; q < R; ++q) p[q] = P.pool + it.foff + row0 + (ok[q] ? lr[q] : 0) + (int64_t)ks * ld;
-  double m[FQR][R];
-#pragma unroll
-  for (int i = 0; i < FQR; ++i) {
-    if (i < nk) {
-#pragma unroll
-      for (int q = 0; q < R; ++q) m[i][q] = p[q][i * step];
-    } else {
-#pragma unroll
-      for (int q = 0; q < R; ++q) m[i][q] = 0.0;
-    }
-  }
-  if (PDL) griddep_wait();                 // the previous level's kernel is complete and visible from here on
-  // ---- wait for the children (dataflow mode)
-  if (CG) {
-    if (tid == 0) {
-      if (it.ch0 >= 0) wait_count(dp.fdone + it.ch0, it.tgt0 * dp.epoch, dp.status);
-      if (it.ch1 >= 0) wait_count(dp.fdone + it.ch1, it.tgt1 * dp.epoch, dp.status);
-      for (int q = 2; q < it.nchild; ++q) { const int ch = P.child[P.cptr[it.f] + q]; wait_count(dp.fdone + ch, dp.nfs[ch] * dp.epoch, dp.status); }
-    }
-    __syncthreads();
-  }
-  // ---- dynamic part: right-hand side + children's updates, fixed order (rhs + first child) + second child
-  if (tid < s2) {
-    double v[NR], w[NR];
-    ldv<CG, NR>(rv.rhs, it.g0 + tid, v);
-    if (i1 >= 0) {
-      ldv<CG, NR>(rv.upd, i1, w);
-#pragma unroll
-      for (int r = 0; r < NR; ++r) v[r] += w[r];
-    }
-    if (i2 >= 0) {
-      ldv<CG, NR>(rv.upd, i2, w);
-#pragma unroll
-      for (int r = 0; r < NR; ++r) v[r] += w[r];
-    }
-#pragma unroll
-    for (int r = 0; r < NR; ++r) sm.y[tid][r] = v[r];
-  }
-  double yt[R][NR];                          // what the children send to this thread's update rows (final-stage threads)
-#pragma unroll
-  for (int q = 0; q < R; ++q) {
-    double w[NR];
-#pragma unroll
-    for (int r = 0; r < NR; ++r) yt[q][r] = 0.0;
-    if (j1[q] >= 0) {
-      ldv<CG, NR>(rv.upd, j1[q], w);
-#pragma unroll
-      for (int r = 0; r < NR; ++r) yt[q][r] += w[r];
-    }
-    if (j2[q] >= 0) {
-      ldv<CG, NR>(rv.upd, j2[q], w);
-#pragma unroll
-      for (int r = 0; r < NR; ++r) yt[q][r] += w[r];
-    }
-  }
-  __syncthreads();
-  if (it.nchild > 2) {                       // rare (a separator that does not disconnect): generic path
-    for (int c = P.cptr[it.f] + 2; c < P.cptr[it.f + 1]; ++c) {
-      const int ch = P.child[c];
-      const int uc2 = 2 * front_u(P, ch);
-      const int32_t* cm = P.cmap + P.cmap_ptr[ch];
-      for (int r = 0; r < NR; ++r) {
-        const double* uv = rv.upd + (int64_t)P.uoff[ch] * NR + r;      // entry k of right-hand side r at uv[k * NR]
-        for (int k = tid; k < uc2; k += 256) {
-          const int t = 2 * cm[k >> 1] + (k & 1);
-          if (t < s2) sm.y[t][r] += ldx<CG>(uv + (int64_t)k * NR);
-        }
-        if (ks == 0) {
-          for (int k = 0; k < uc2; ++k) {
-            const int t = 2 * cm[k >> 1] + (k & 1);
-#pragma unroll
-            for (int q = 0; q < R; ++q) if (ok[q] && t == row0 + lr[q] && t >= s2) yt[q][r] += ldx<CG>(uv + (int64_t)k * NR);
-          }
-        }
-      }
-      __syncthreads();
-    }
-  }
-  double acc[R][NR];
-#pragma unroll
-  for (int q = 0; q < R; ++q)
-#pragma unroll
-    for (int r = 0; r < NR; ++r) acc[q][r] = 0.0;
-#pragma unroll
-  for (int i = 0; i < FQR; ++i) {
-    if (i < nk) {
-      double y[NR];
-      lds_row<NR>(sm.y, ks + i * nks, y);
-#pragma unroll
-      for (int q = 0; q < R; ++q)
-#pragma unroll
-        for (int r = 0; r < NR; ++r) acc[q][r] = fma(m[i][q], y[r], acc[q][r]);
-    }
-  }
-#pragma unroll 4
-  for (int i = FQR; i < nk; ++i) {
-    double mv[R], y[NR];
-#pragma unroll
-    for (int q = 0; q < R; ++q) mv[q] = p[q][i * step];
-    lds_row<NR>(sm.y, ks + i * nks, y);
-#pragma unroll
-    for (int q = 0; q < R; ++q)
-#pragma unroll
-      for (int r = 0; r < NR; ++r) acc[q][r] = fma(mv[q], y[r], acc[q][r]);
-  }
-#pragma unroll
-  for (int q = 0; q < R; ++q)
-#pragma unroll
-    for (int r = 0; r < NR; ++r) sm.part[warp][q][r][lane] = acc[q][r];
-  __syncthreads();
-  if (ks == 0) {
-#pragma unroll
-    for (int q = 0; q < R; ++q) {
-      if (!ok[q]) continue;
-      const int row = row0 + lr[q];
-      double o[NR];
-#pragma unroll
-      for (int r = 0; r < NR; ++r) {
-        double t = 0.0;
-        for (int c = 0; c < nks; ++c) t += sm.part[c * G + rg][q][r][lane];
-        o[r] = row < s2 ? t : yt[q][r] - t;
-      }
-      if (row < s2) stv<NR>(rv.out, it.g0 + row, o);
-      else stv<NR>(rv.upd, (int64_t)it.uoff + (row - s2), o);
-    }
-  }
-}
-
-template <bool CG, int NR, bool PDL = false>
-__device__ __forceinline__ void forward_item(const FwdItem& it, const int32_t* __restrict__ gsrc, const PlanView& P,
-                                             const RhsView& rv, SweepSmem<NR>& sm, const Deps& dp) {
-  if ((it.G >> 8) == 2) forward_item_r<CG, NR, 2, PDL>(it, gsrc, P, rv, sm, dp);
-  else forward_item_r<CG, NR, 1, PDL>(it, gsrc, P, rv, sm, dp);
-}
-
-// backward: one CTA per (front, chunk of 32*R pivot columns) against the row-major copy of W (lanes over pivot
-// columns, coalesced rows).  The update unknowns x2 are gathered ONCE per CTA into shared memory — the gather costs
-// as many loads as the factor chunk itself, so it must not be repeated per column — and the 8 warps take slices of
-// the j range (the 2u update unknowns); partial sums meet in shared memory.  Same lean loops as the forward item.
-constexpr int JT = 512;    // update unknowns staged per pass (one pass for all fronts met so far)
-template <int NR>
-struct BwdSmem {
-  double xs[JT][NR];
-  double part[8][2][NR][32];
-};
-
-template <bool CG, int NR, int R, bool PDL>
-__device__ __forceinline__ void backward_item_r(const BwdItem& it, const PlanView& P, double* x, BwdSmem<NR>& sm,
-                                                const Deps& dp) {
-  constexpr int FQR = FQ / R;
-  constexpr int nks = 8;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int u2 = it.u2, ks = warp;
-  const int64_t s2p = it.ld;
-  const int32_t* st = P.strct + it.soff;
-  int lc[R]; bool ok[R];
-#pragma unroll
-  for (int q = 0; q < R; ++q) { lc[q] = q * 32 + lane; ok[q] = lc[q] < it.ncols; }
-  // ---- static prefetch: gather offsets of the first pass and this thread's factor entries
-  int64_t o0 = -1, o1 = -1;
-  if (tid < u2) o0 = 2 * (int64_t)st[tid >> 1] + (tid & 1);
-  if (tid + 256 < u2) o1 = 2 * (int64_t)st[(tid + 256) >> 1] + (tid & 1);
-  const double* p[R];
-#pragma unroll
-  for (int q = 0; q < R; ++q) p[q] = P.pool + it.foff + it.col0 + (ok[q] ? lc[q] : 0) + (int64_t)ks * s2p;
-  const int64_t step = (int64_t)nks * s2p;
-  const int n0 = (min(u2, JT) - ks + nks - 1) / nks;   // j's of this warp's slice in the first pass (warp-uniform)
-  double m[FQR][R];
-#pragma unroll
-  for (int i = 0; i < FQR; ++i) {
-    if (i < n0) {
-#pragma unroll
-      for (int q = 0; q < R; ++q) m[i][q] = p[q][i * step];
-    } else {
-#pragma unroll
-      for (int q = 0; q < R; ++q) m[i][q] = 0.0;
-    }
-  }
-  if (PDL) griddep_wait();
-  if (CG) {
-    if (tid == 0) {
-      wait_count(dp.fdone + it.f, it.tgt_f * dp.epoch, dp.status);             // z of this front is complete
-      if (it.parent >= 0) { wait_count(dp.fdone + it.parent, it.tgt_pf * dp.epoch, dp.status); wait_count(dp.bdone + it.parent, it.tgt_pb * dp.epoch, dp.status); }
-    }
-    __syncthreads();
-  }
-  double acc[R][NR];
-#pragma unroll
-  for (int q = 0; q < R; ++q)
-#pragma unroll
-    for (int r = 0; r < NR; ++r) acc[q][r] = 0.0;
-  for (int j0 = 0; j0 < u2; j0 += JT) {
-    const int jn = min(JT, u2 - j0);
-    if (j0 > 0) {                             // fronts with more than JT update unknowns: further passes
-      __syncthreads();
-      o0 = o1 = -1;
-      if (tid < jn) o0 = 2 * (int64_t)st[(j0 + tid) >> 1] + (tid & 1);
-      if (tid + 256 < jn) o1 = 2 * (int64_t)st[(j0 + tid + 256) >> 1] + (tid & 1);
-    }
-    if (o0 >= 0) {
-      double v[NR];
-      ldv<CG, NR>(x, o0, v);
-#pragma unroll
-      for (int r = 0; r < NR; ++r) sm.xs[tid][r] = v[r];
-    }
-    if (o1 >= 0) {
-      double v[NR];
-      ldv<CG, NR>(x, o1, v);
-#pragma unroll
-      for (int r = 0; r < NR; ++r) sm.xs[tid + 256][r] = v[r];
-    }
-    __syncthreads();
-    const int nk = (jn - ks + nks - 1) / nks;
-    int i = 0;
-    if (j0 == 0) {
-#pragma unroll
-      for (int ii = 0; ii < FQR; ++ii) {
-        if (ii < nk) {
-          double xv[NR];
-          lds_row<NR>(sm.xs, ks + ii * nks, xv);
-#pragma unroll
-          for (int q = 0; q < R; ++q)
-#pragma unroll
-            for (int r = 0; r < NR; ++r) acc[q][r] = fma(m[ii][q], xv[r], acc[q][r]);
-        }
-      }
-      i = FQR;
-    }
-    const double* const* pp = p;
-#pragma unroll 4
-    for (; i < nk; ++i) {
-      double mv[R], xv[NR];
-#pragma unroll
-      for (int q = 0; q < R; ++q) mv[q] = pp[q][(int64_t)j0 * s2p + i * step];
-      lds_row<NR>(sm.xs, ks + i * nks, xv);
-#pragma unroll
-      for (int q = 0; q < R; ++q)
-#pragma unroll
-        for (int r = 0; r < NR; ++r) acc[q][r] = fma(mv[q], xv[r], acc[q][r]);
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < R; ++q)
-#pragma unroll
-    for (int r = 0; r < NR; ++r) sm.part[warp][q][r][lane] = acc[q][r];
-  __syncthreads();
-  // final stage: warp w sums the partials of right-hand side w % NR for row q = w / NR (all 8 warps share the work)
-  for (int job = warp; job < R * NR; job += 8) {
-    const int q = job / NR, r = job % NR;
-    if (q * 32 + lane < it.ncols) {
-      double t = 0.0;
-#pragma unroll
-      for (int c = 0; c < nks; ++c) t += sm.part[c][q][r][lane];
-      double* xp = x + (it.g0 + it.col0 + q * 32 + lane) * NR + r;
-      *xp = ldx<CG>(xp) - t;
-    }
-  }
-}
-
-// backward, fronts with MANY update unknowns: one warp per pivot column of W^T in the packed left block column
-// (lanes over the update unknowns), 8 columns per CTA.  Parallel over all 2s x 2u entries, every factor entry in
-// flight before the dependency wait — the shape the latency-bound upper levels of the tree need.
-constexpr int BWD_COLS = 8;
-constexpr int BQ = 8;   // factor entries per lane preloaded before the wait
-template <bool CG, int NR, bool PDL>
-__device__ __forceinline__ void backward_item_cols(const BwdItem& it, const PlanView& P, double* x, const Deps& dp) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int u2 = it.u2;
-  const bool active = warp < it.ncols;
-  const int32_t* st = P.strct + it.soff;
-  const double* wc = P.pool + it.foff + it.s2 + (int64_t)(it.col0 + warp) * it.ld;   // W^T(j, col) at col*ld + s2 + j
-  // ---- static prefetch: factor column and gather offsets
-  double wreg[BQ]; int64_t xo[BQ];
-#pragma unroll
-  for (int q = 0; q < BQ; ++q) {
-    const int j = lane + 32 * q;
-    const bool ok = active && j < u2;
-    wreg[q] = ok ? wc[j] : 0.0;
-    xo[q] = ok ? 2 * (int64_t)st[j >> 1] + (j & 1) : -1;
-  }
-  if (PDL) griddep_wait();
-  if (CG) {
-    if (threadIdx.x == 0) {
-      wait_count(dp.fdone + it.f, it.tgt_f * dp.epoch, dp.status);             // z of this front is complete
-      if (it.parent >= 0) { wait_count(dp.fdone + it.parent, it.tgt_pf * dp.epoch, dp.status); wait_count(dp.bdone + it.parent, it.tgt_pb * dp.epoch, dp.status); }
-    }
-    __syncthreads();
-  }
-  if (!active) return;
-  double a[NR];
-#pragma unroll
-  for (int r = 0; r < NR; ++r) a[r] = 0.0;
-#pragma unroll
-  for (int q = 0; q < BQ; ++q) {
-    if (xo[q] >= 0) {
-      double xv[NR];
-      ldv<CG, NR>(x, xo[q], xv);
-#pragma unroll
-      for (int r = 0; r < NR; ++r) a[r] = fma(wreg[q], xv[r], a[r]);
-    }
-  }
-  for (int j = lane + 32 * BQ; j < u2; j += 32) {
-    const double wv = wc[j];
-    const int64_t o = 2 * (int64_t)st[j >> 1] + (j & 1);
-    double xv[NR];
-    ldv<CG, NR>(x, o, xv);
-#pragma unroll
-    for (int r = 0; r < NR; ++r) a[r] = fma(wv, xv[r], a[r]);
-  }
-#pragma unroll
-  for (int r = 0; r < NR; ++r) {
-    double v = a[r];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-    if (lane == 0) { double* xp = x + (it.g0 + it.col0 + warp) * NR + r; *xp = ldx<CG>(xp) - v; }
-  }
-}
-
-template <bool CG, int NR, bool PDL = false>
-__device__ __forceinline__ void backward_item(const BwdItem& it, const PlanView& P, double* x, BwdSmem<NR>& sm,
-                                              const Deps& dp) {
-  if (it.G == 0) backward_item_cols<CG, NR, PDL>(it, P, x, dp);
-  else if (it.G == 2) backward_item_r<CG, NR, 2, PDL>(it, P, x, sm, dp);
-  else backward_item_r<CG, NR, 1, PDL>(it, P, x, sm, dp);
-}
-
-// large fronts: one CTA-cooperative item per CTA
-template <int NR, bool PDL>
-__global__ void __launch_bounds__(256, 4) forward_kernel(const FwdItem* __restrict__ items, const int32_t* __restrict__ gsrc, PlanView P,
-                                                       RhsView rv) {
-  __shared__ SweepSmem<NR> sm;
-  if (PDL) griddep_launch_dependents();    // let the next launch start its static prefetch
-  const Deps none{nullptr, nullptr, nullptr, 0, nullptr};
-  forward_item<false, NR, PDL>(items[blockIdx.x], gsrc, P, rv, sm, none);
-}
-
-template <int NR, bool PDL>
-__global__ void __launch_bounds__(256, 4) backward_kernel(const BwdItem* __restrict__ items, PlanView P, double* x) {
-  __shared__ BwdSmem<NR> sm;
-  if (PDL) griddep_launch_dependents();
-  const Deps none{nullptr, nullptr, nullptr, 0, nullptr};
-  backward_item<false, NR, PDL>(items[blockIdx.x], P, x, sm, none);
-}
-
-// ---- pack: the solve phase reads only the left block column of a front (and W a second time, row-major) ----
-// Copy both into dense, 32-byte aligned panels; the front pool is factorisation workspace only.
-__global__ void __launch_bounds__(256) pack_kernel(PlanView P, const int64_t* __restrict__ lo, const int64_t* __restrict__ wo,
-                                                   const int32_t* __restrict__ ldp, const uint8_t* __restrict__ in_sub,
-                                                   double* __restrict__ fac) {
-  __shared__ double tile[32][33];
-  const int f = blockIdx.x;
-  if (in_sub[f]) return;          // packed into the streams of the bottom subtrees instead
-  const int s2 = 2 * P.s[f], u2 = 2 * front_u(P, f);
-  const int64_t ld = s2 + u2, lp = ldp[f];
-  const double* src = P.pool + P.foff[f];
-  double* dst = fac + lo[f];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int k = warp; k < s2; k += 8)
-    for (int i = lane; i < ld; i += 32) dst[k * lp + i] = src[k * ld + i];
-  if (u2 == 0) return;
-  double* dw = fac + wo[f];
-  const int64_t s2p = (s2 + 3) & ~3;
-  for (int c0 = 0; c0 < s2; c0 += 32)
-    for (int j0 = 0; j0 < u2; j0 += 32) {
-      __syncthreads();
-      for (int w = warp; w < 32; w += 8) {              // column c0+w of W^T, rows j0..j0+31
-        const int c = c0 + w, j = j0 + lane;
-        tile[w][lane] = (c < s2 && j < u2) ? src[(int64_t)c * ld + s2 + j] : 0.0;
-      }
-      __syncthreads();
-      for (int w = warp; w < 32; w += 8) {              // row j0+w of the copy, columns c0..c0+31
-        const int j = j0 + w, c = c0 + lane;
-        if (j < u2 && c < s2) dw[(int64_t)j * s2p + c] = tile[lane][w];
-      }
-    }
-}
-
-PlanView view(const DevPlan& D);
-PlanView sweep_view(const DevPlan& D) {   // the sweeps read the packed panels, never the front pool
-  PlanView v = view(D);
-  v.pool = D.fac.p;
-  return v;
-}
-
 size_t invert_smem(int m) { return ((size_t)(m | 1) * m + 2 * (size_t)m) * sizeof(double); }
 
 PlanView view(const DevPlan& D) {
@@ -812,24 +313,7 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
   build_stream_plan(ctx, P, uoff, in_sub, D.st);
   D.in_sub.upload(ctx, in_sub);
 
-  // packed panels of the solve phase (fronts above the bottom subtrees)
-  std::vector<int64_t> lo(P.nfronts + 1, 0), wo(P.nfronts, 0);
-  std::vector<int32_t> ldp(P.nfronts, 0);
-  {
-    int64_t off = 0;
-    for (int f = 0; f < P.nfronts; ++f) {
-      const int64_t s2 = 2 * (int64_t)P.s[f], u2 = 2 * (int64_t)(P.sptr[f + 1] - P.sptr[f]);
-      ldp[f] = (int32_t)((s2 + u2 + 3) & ~int64_t(3));
-      lo[f] = off; if (!in_sub[f]) off += (int64_t)ldp[f] * s2;
-      wo[f] = off; if (!in_sub[f]) off += ((s2 + 3) & ~int64_t(3)) * u2;
-    }
-    lo[P.nfronts] = off;
-    D.fac.alloc(ctx, (size_t)std::max<int64_t>(off, 1));
-    D.lo.upload(ctx, lo); D.wo.upload(ctx, wo); D.ldp.upload(ctx, ldp);
-  }
   std::vector<int4> wt, stl, ea;
-  std::vector<FwdItem> fwb; std::vector<BwdItem> bwb;     // per-level launches: CTA items of the fronts above the subtrees
-  D.fwdb_ptr.assign(P.nlevels + 1, 0); D.bwdb_ptr = D.fwdb_ptr;
   D.w_ptr.assign(P.nlevels + 1, 0); D.s_ptr = D.ea_ptr = D.w_ptr;
   D.lmax_m.assign(P.nlevels, 0);
   // flattened child -> parent gather: per front above the subtrees, for every front row (2nf unknowns) the offset into the
@@ -850,7 +334,6 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
       }
     }
   }
-  static const int bwd_rows_u2 = [] { const char* e = std::getenv("PLFEM_BWD_ROWS_U2"); return e ? std::max(0, atoi(e)) : 128; }();
   for (int l = 0; l < P.nlevels; ++l) {
     for (int q = P.lptr[l]; q < P.lptr[l + 1]; ++q) {
       const int f = P.lfront[q];
@@ -863,39 +346,10 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
         for (int a0 = 0; a0 < u2; a0 += GT) stl.push_back(make_int4(f, a0, b0, 0));
       if (P.cptr[f + 1] > P.cptr[f])
         for (int c0 = 0; c0 < nf; c0 += EA_COLS) ea.push_back(make_int4(f, c0, std::min(c0 + EA_COLS, nf), 0));
-      if (in_sub[f]) continue;
-      {
-        const int rows = s2 + u2;
-        // row groups x rows per thread: <= 32 rows (1,1), <= 64 (1,2), <= 128 (2,2), larger fronts in slabs of 64 rows (1,2)
-        const int G = (rows > 64 && rows <= 128) ? 2 : 1, Rr = rows <= 32 ? 1 : 2;
-        const int nch = P.cptr[f + 1] - P.cptr[f];
-        for (int r0 = 0; r0 < rows; r0 += 32 * G * Rr) {
-          FwdItem it{};
-          it.f = f; it.row0 = r0; it.nrows = std::min(32 * G * Rr, rows - r0); it.G = G | (Rr << 8); it.s2 = s2; it.ld = ldp[f];
-          it.ch0 = nch > 0 ? P.child[P.cptr[f]] : -1; it.ch1 = nch > 1 ? P.child[P.cptr[f] + 1] : -1;
-          it.uoff = uoff[f]; it.goff = goff[f]; it.nchild = nch; it.nf2 = rows;
-          it.foff = lo[f]; it.g0 = 2 * (int64_t)P.first[f];
-          fwb.push_back(it);
-        }
-      }
-      if (u2 > 0) {
-        const bool rows_style = u2 <= bwd_rows_u2;
-        const int Gb = rows_style ? (s2 <= 32 ? 1 : 2) : 0;   // pivot columns per thread; 0 = one warp per column
-        const int cw = rows_style ? 32 * Gb : BWD_COLS;
-        for (int c0 = 0; c0 < s2; c0 += cw) {
-          BwdItem it{};
-          it.f = f; it.col0 = c0; it.ncols = std::min(cw, s2 - c0); it.s2 = s2; it.u2 = u2; it.soff = P.sptr[f];
-          it.ld = rows_style ? ((s2 + 3) & ~3) : ldp[f];
-          it.parent = P.parent[f]; it.G = Gb;
-          it.foff = rows_style ? wo[f] : lo[f]; it.g0 = 2 * (int64_t)P.first[f];
-          bwb.push_back(it);
-        }
-      }
     }
     D.w_ptr[l + 1] = (int32_t)wt.size(); D.s_ptr[l + 1] = (int32_t)stl.size(); D.ea_ptr[l + 1] = (int32_t)ea.size();
-    D.fwdb_ptr[l + 1] = (int32_t)fwb.size(); D.bwdb_ptr[l + 1] = (int32_t)bwb.size();
   }
-  D.fwdb_items.upload(ctx, fwb); D.bwdb_items.upload(ctx, bwb);
+  build_level_plan(ctx, P, uoff, in_sub, goff, D.st);
   D.gsrc.upload(ctx, gsrc);
   D.w_tiles.upload(ctx, wt); D.s_tiles.upload(ctx, stl); D.ea_slabs.upload(ctx, ea);
   D.pool.alloc(ctx, (size_t)P.foff[P.nfronts]);
@@ -950,9 +404,7 @@ void run_factorization(plfem_ctx* ctx, const DevPlan& D) {
       ctx->launches++;
     }
   }
-  pack_kernel<<<D.nfronts, 256, 0, ctx->stream>>>(v, D.lo.p, D.wo.p, D.ldp.p, D.in_sub.p, D.fac.p);
-  ctx->launches++;
-  launch_stream_pack(ctx, D);
+  launch_stream_pack(ctx, D);       // the solve phase reads only the streams written here; the front pool is workspace
   PLFEM_CUDA(cudaGetLastError());
 }
 
@@ -961,56 +413,31 @@ bool use_pdl() {
   return on;
 }
 
-template <class... KArgs, class... Args>
-void launch_sweep(void (*kernel)(KArgs...), bool pdl, int grid, cudaStream_t st, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-  PLFEM_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
-}
-
 // nrhs right-hand sides (1 or SOLVE_NRHS), INTERLEAVED: entry i of right-hand side r at b[i * nrhs + r].  One launch for the
-// bottom subtrees, then one launch per remaining level (CTA items).
+// bottom subtrees, then one launch per remaining level (sweep_stream.cu).
 void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double* z, int nrhs) {
-  const PlanView v = sweep_view(D);
   if (nrhs != 1 && nrhs != SOLVE_NRHS) throw StatusError(PLFEM_ERR_INTERNAL, "unsupported number of right-hand sides");
-  const RhsView rv{b, z, D.upd.p};
   const bool pdl = use_pdl();
   bool first = true;     // the first launch follows kernels that are not PDL-aware: plain launch
-  const int32_t* gs = D.gsrc.p;
   if (D.st.n_subs > 0) {
     launch_stream_forward(ctx, D, b, z, nrhs, false);
     first = false;
   }
   for (int l = 0; l < D.nlevels; ++l) {
-    const int nbig = D.fwdb_ptr[l + 1] - D.fwdb_ptr[l];
-    if (nbig == 0) continue;
-    const FwdItem* items = D.fwdb_items.p + D.fwdb_ptr[l];
-    const bool p = pdl && !first;
-    if (nrhs == 1) { if (p) launch_sweep(forward_kernel<1, true>, true, nbig, ctx->stream, items, gs, v, rv); else launch_sweep(forward_kernel<1, false>, false, nbig, ctx->stream, items, gs, v, rv); }
-    else { if (p) launch_sweep(forward_kernel<SOLVE_NRHS, true>, true, nbig, ctx->stream, items, gs, v, rv); else launch_sweep(forward_kernel<SOLVE_NRHS, false>, false, nbig, ctx->stream, items, gs, v, rv); }
-    first = false; ctx->launches++;
+    if (D.st.fptr[l + 1] == D.st.fptr[l]) continue;
+    launch_level_forward(ctx, D, l, b, z, nrhs, pdl && !first);
+    first = false;
   }
 }
 
 // must follow run_solve_forward on the same stream (its launches may be PDL-chained to the forward ones)
 void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs) {
-  const PlanView v = sweep_view(D);
   const bool pdl = use_pdl();
-  bool any_level = false;     // the stream kernel may be chained by PDL only to a PDL-aware predecessor
   for (int l = D.nlevels - 1; l >= 0; --l) {
-    const int nbig = D.bwdb_ptr[l + 1] - D.bwdb_ptr[l];
-    if (nbig == 0) continue;
-    any_level = true;
-    const BwdItem* items = D.bwdb_items.p + D.bwdb_ptr[l];
-    if (nrhs == 1) { if (pdl) launch_sweep(backward_kernel<1, true>, true, nbig, ctx->stream, items, v, x); else launch_sweep(backward_kernel<1, false>, false, nbig, ctx->stream, items, v, x); }
-    else { if (pdl) launch_sweep(backward_kernel<SOLVE_NRHS, true>, true, nbig, ctx->stream, items, v, x); else launch_sweep(backward_kernel<SOLVE_NRHS, false>, false, nbig, ctx->stream, items, v, x); }
-    ctx->launches++;
+    if (D.st.bptr[l + 1] == D.st.bptr[l]) continue;
+    launch_level_backward(ctx, D, l, x, nrhs, pdl);
   }
-  if (D.st.n_subs > 0) launch_stream_backward(ctx, D, x, nrhs, pdl && any_level);
+  if (D.st.n_subs > 0) launch_stream_backward(ctx, D, x, nrhs, pdl);
 }
 
 void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x, int nrhs) {

@@ -34,6 +34,7 @@ constexpr int NS = 4;                   // ring stages per warp
 constexpr int NLOC = ST_NLOC;           // local unknowns (pivots of the subtree + update set of its root)
 constexpr int MAXF = 32;                // fronts per subtree: one descriptor per lane
 constexpr int RB = 128;                 // rows of a forward row block (4 rows per lane)
+constexpr int MAX_PIV_UNKNOWNS = 128;   // largest pivot block (unknowns)
 
 __host__ __device__ inline int lm_item(int u) { return ((u + 7) / 8) * 2; }   // doubles holding u uint16 node indices, 16-byte multiple
 
@@ -85,36 +86,37 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// The warp's view of its stream: a ring of NS chunks, refilled by lane 0 as soon as the warp has left a chunk.
-struct Pipe {
+// The warp's view of its stream: a ring of NST chunks, refilled by lane 0 as soon as the warp has left a chunk.
+template <int NST>
+struct PipeT {
   double* ring; uint64_t* bar; const double* src; int32_t* status;
   int nchunks, cur, pos, lane;
   bool dead = false;                                  // a wait timed out: stop waiting, the status flag reports it
   __device__ __forceinline__ void issue(int c) {
-    const int s = c % NS;
+    const int s = c % NST;
     mbar_expect_tx(bar + s, CHD * 8);
     bulk_g2s(ring + s * CHD, src + (int64_t)c * CHD, CHD * 8, bar + s);
   }
   __device__ __forceinline__ void start() {
     if (lane == 0)
-      for (int c = 0; c < NS && c < nchunks; ++c) issue(c);
+      for (int c = 0; c < NST && c < nchunks; ++c) issue(c);
     cur = -1; pos = CHD;
   }
   __device__ __forceinline__ void advance() {
     if (cur >= 0) {
       __syncwarp();                                   // every lane is done with the chunk being left
-      if (lane == 0 && cur + NS < nchunks) issue(cur + NS);
+      if (lane == 0 && cur + NST < nchunks) issue(cur + NST);
     }
     ++cur; pos = 0;
-    uint64_t* b = bar + cur % NS;
-    const uint32_t parity = (cur / NS) & 1;
+    uint64_t* b = bar + cur % NST;
+    const uint32_t parity = (cur / NST) & 1;
     unsigned spins = 0;
     while (!dead && !mbar_try_wait(b, parity))
       if (++spins > (1u << 18)) { atomicExch(status + 1, 2); dead = true; }   // report instead of hanging the GPU
   }
   __device__ __forceinline__ const double* place(int sz) {
     if (pos + sz > CHD) advance();
-    const double* p = ring + (cur % NS) * CHD + pos;
+    const double* p = ring + (cur % NST) * CHD + pos;
     pos += sz;
     return p;
   }
@@ -122,6 +124,8 @@ struct Pipe {
     while (cur + 1 < nchunks) advance();
   }
 };
+
+using Pipe = PipeT<NS>;
 
 template <int NR>
 struct StreamSmem {
@@ -434,6 +438,378 @@ __global__ void __launch_bounds__(256) stream_pack_kernel(const StreamPackRec* _
   }
 }
 
+// ================================================================================================================
+// Fronts ABOVE the bottom subtrees: one launch per elimination-tree level, one warp (a 32-thread CTA) per task.
+//
+// A forward task is a slab of <= 128 rows of a front's left block column [F11^-1 ; W^T], a backward task a slab of
+// pivot columns of W.  Both were laid out at pack time as their own chunk-aligned stream (uniform items: panel columns
+// of the slab / rows of the W slab), so the warp starts its bulk copies before the kernel's dependency wait — a task of
+// up to NS chunks is completely in flight while the previous level is still running — and the critical path of a level
+// is: one gather of freshly written values (children's update vectors / ancestors' unknowns; their indices were
+// prefetched too), FMAs against shared memory, one store.  The task sizes follow the front: small contraction ->
+// wide slabs, long contraction -> narrow slabs with the lanes split over the contraction index, so that a task stays
+// near the ring's capacity; fronts of the 2M-unknown regime get wide slabs again (fewer redundant gathers).
+constexpr int KX = 512;     // contraction entries staged per pass of a backward task
+
+struct RhsView {            // interleaved vectors of a forward sweep: right-hand sides in, pivot solutions out, update pool
+  const double* rhs; double* out; double* upd;
+};
+
+constexpr int NSF = 8;      // ring stages of a forward task (a 32 KB task is completely in flight before the dependency wait)
+constexpr int NSB = 6;      // ring stages of a backward task (its contraction vector takes 16 KB)
+using PipeF = PipeT<NSF>;
+using PipeB = PipeT<NSB>;
+
+template <int NR>
+struct LevelFwdSmem {
+  alignas(128) double ring[NSF * CHD];
+  alignas(16) double cv[MAX_PIV_UNKNOWNS * NR];   // assembled pivot part of the right-hand sides
+  alignas(8) uint64_t bar[NSF];
+};
+template <int NR>
+struct LevelBwdSmem {
+  alignas(128) double ring[NSB * CHD];
+  alignas(16) double cv[KX * NR];                 // gathered x2 of the current pass
+  alignas(8) uint64_t bar[NSB];
+};
+
+// uniform items of size sz, starting chunk-aligned: item i of the task's stream
+__host__ __device__ inline int64_t item_off(int i, int sz) {
+  const int per = CHD / sz;
+  return (int64_t)(i / per) * CHD + (i % per) * sz;
+}
+__host__ __device__ inline int item_chunks(int n, int sz) { return n == 0 ? 0 : (n + CHD / sz - 1) / (CHD / sz); }
+
+template <int NR, int R>
+__device__ __forceinline__ void level_fwd_rows(PipeF& pp, LevelFwdSmem<NR>& sm, const LevelTask& t, const int (&j1)[4], const int (&j2)[4],
+                                               const RhsView& rv) {
+  const int lane = pp.lane;
+  const int ld = (t.n + 3) & ~3;
+  bool valid[R];
+#pragma unroll
+  for (int q = 0; q < R; ++q) valid[q] = lane + 32 * q < t.n;
+  // what the children send to this task's update rows: in flight while the panel is multiplied
+  double yt[R][NR];
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) yt[q][r] = 0.0;
+    double w[NR];
+    if (j1[q] >= 0) {
+      ldg_v<NR>(rv.upd, j1[q], w);
+#pragma unroll
+      for (int r = 0; r < NR; ++r) yt[q][r] += w[r];
+    }
+    if (j2[q] >= 0) {
+      ldg_v<NR>(rv.upd, j2[q], w);
+#pragma unroll
+      for (int r = 0; r < NR; ++r) yt[q][r] += w[r];
+    }
+  }
+  double acc[R][NR];
+#pragma unroll
+  for (int q = 0; q < R; ++q)
+#pragma unroll
+    for (int r = 0; r < NR; ++r) acc[q][r] = 0.0;
+  for (int k = 0; k < t.s2;) {
+    int n = (CHD - pp.pos) / ld;
+    if (n == 0) { pp.advance(); continue; }
+    n = min(n, t.s2 - k);
+    const double* base = pp.ring + (pp.cur % NSF) * CHD + pp.pos + lane;
+    const double* yv = sm.cv + k * NR;
+#pragma unroll 4
+    for (int c = 0; c < n; ++c) {
+      double y[NR];
+      ld_loc<NR>(yv, c, y);
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        const double m = valid[q] ? base[c * ld + 32 * q] : 0.0;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) acc[q][r] = fma(m, y[r], acc[q][r]);
+      }
+    }
+    pp.pos += n * ld; k += n;
+  }
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+    if (!valid[q]) continue;
+    const int row = t.r0 + lane + 32 * q;
+    if (row < t.s2) {
+      stg_v<NR>(rv.out, t.g0 + row, acc[q]);
+    } else {
+      double o[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) o[r] = yt[q][r] - acc[q][r];
+      stg_v<NR>(rv.upd, (int64_t)t.uoff + (row - t.s2), o);
+    }
+  }
+}
+
+template <int NR, bool PDL>
+__global__ void __launch_bounds__(32) level_forward_kernel(const LevelTask* __restrict__ tasks, const int32_t* __restrict__ gsrc,
+                                                           const double* __restrict__ stream, const int32_t* __restrict__ cptr,
+                                                           const int32_t* __restrict__ child, const int32_t* __restrict__ cmap_ptr,
+                                                           const int32_t* __restrict__ cmap, const int32_t* __restrict__ sptr,
+                                                           const int32_t* __restrict__ uoff, RhsView rv, int32_t* status) {
+  __shared__ LevelFwdSmem<NR> sm;
+  const int lane = threadIdx.x;
+  if (PDL) griddep_launch_dependents();
+  const LevelTask t = tasks[blockIdx.x];
+  if (lane == 0) {
+    for (int s = 0; s < NSF; ++s) mbar_init(sm.bar + s, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  PipeF pp{sm.ring, sm.bar, stream + t.soff, status, t.chunks, -1, CHD, lane};
+  pp.start();
+  // static: where the pivot rows and this task's update rows receive their children's updates
+  const int nf2 = t.s2 + t.u2;
+  const int32_t* g1 = gsrc + t.goff;
+  const int32_t* g2 = g1 + nf2;
+  int i1[4], i2[4], j1[4], j2[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int k = lane + 32 * q;
+    i1[q] = i2[q] = j1[q] = j2[q] = -1;
+    if (k < t.s2) { i1[q] = g1[k]; i2[q] = g2[k]; }
+    const int row = t.r0 + k;
+    if (k < t.n && row >= t.s2) { j1[q] = g1[row]; j2[q] = g2[row]; }
+  }
+  if (PDL) griddep_wait();
+  // assembled pivot part of the right-hand sides, fixed order (rhs + first child) + second child
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int k = lane + 32 * q;
+    if (k >= t.s2) continue;
+    double v[NR], w[NR];
+    ldg_v<NR>(rv.rhs, t.g0 + k, v);
+    if (i1[q] >= 0) {
+      ldg_v<NR>(rv.upd, i1[q], w);
+#pragma unroll
+      for (int r = 0; r < NR; ++r) v[r] += w[r];
+    }
+    if (i2[q] >= 0) {
+      ldg_v<NR>(rv.upd, i2[q], w);
+#pragma unroll
+      for (int r = 0; r < NR; ++r) v[r] += w[r];
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) sm.cv[k * NR + r] = v[r];
+  }
+  __syncwarp();
+  if (t.nch > 2) {          // rare (a separator that does not disconnect): the further children, one after the other
+    for (int c = cptr[t.f] + 2; c < cptr[t.f + 1]; ++c) {
+      const int ch = child[c];
+      const int uc2 = 2 * (sptr[ch + 1] - sptr[ch]);
+      const int32_t* cm = cmap + cmap_ptr[ch];
+      for (int k = lane; k < uc2; k += 32) {
+        const int row = 2 * cm[k >> 1] + (k & 1);
+        if (row < t.s2) {
+          double w[NR];
+          ldg_v<NR>(rv.upd, (int64_t)uoff[ch] + k, w);
+#pragma unroll
+          for (int r = 0; r < NR; ++r) sm.cv[row * NR + r] += w[r];
+        }
+      }
+      __syncwarp();
+    }
+  }
+  switch ((t.n + 31) >> 5) {
+    case 1: level_fwd_rows<NR, 1>(pp, sm, t, j1, j2, rv); break;
+    case 2: level_fwd_rows<NR, 2>(pp, sm, t, j1, j2, rv); break;
+    case 3: level_fwd_rows<NR, 3>(pp, sm, t, j1, j2, rv); break;
+    default: level_fwd_rows<NR, 4>(pp, sm, t, j1, j2, rv); break;
+  }
+  if (t.nch > 2) {          // update rows of this task: contributions of the further children (after the first two, fixed order)
+    __syncwarp();
+    for (int c = cptr[t.f] + 2; c < cptr[t.f + 1]; ++c) {
+      const int ch = child[c];
+      const int uc2 = 2 * (sptr[ch + 1] - sptr[ch]);
+      const int32_t* cm = cmap + cmap_ptr[ch];
+      for (int k = lane; k < uc2; k += 32) {
+        const int row = 2 * cm[k >> 1] + (k & 1);
+        if (row >= t.s2 && row >= t.r0 && row < t.r0 + t.n) {
+          double w[NR], o[NR];
+          ldg_v<NR>(rv.upd, (int64_t)uoff[ch] + k, w);
+          ldg_v<NR>(rv.upd, (int64_t)t.uoff + (row - t.s2), o);
+#pragma unroll
+          for (int r = 0; r < NR; ++r) o[r] += w[r];
+          stg_v<NR>(rv.upd, (int64_t)t.uoff + (row - t.s2), o);
+        }
+      }
+      __syncwarp();
+    }
+  }
+  pp.drain();
+}
+
+// backward: G = 32 / W lanes share a pivot column (W = 8, 16: lanes split the contraction index), or R columns per lane (wide)
+template <int NR, int W>
+__device__ __forceinline__ void level_bwd_narrow(PipeB& pp, LevelBwdSmem<NR>& sm, int jn, double (&acc)[NR]) {
+  constexpr int G = 32 / W;
+  const int lane = pp.lane, jg = lane / W;
+  for (int j = 0; j < jn;) {
+    int n = (CHD - pp.pos) / W;                                  // items left in this chunk (a multiple of G by construction)
+    if (n == 0) { pp.advance(); continue; }
+    n = min(n, jn - j);
+    const double* base = pp.ring + (pp.cur % NSB) * CHD + pp.pos + lane;
+#pragma unroll 4
+    for (int c = 0; c < n; c += G) {
+      const bool ok = c + jg < n;
+      double x[NR];
+      ld_loc<NR>(sm.cv, ok ? j + c + jg : 0, x);
+      const double m = ok ? base[c * W] : 0.0;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) acc[r] = fma(m, x[r], acc[r]);
+    }
+    pp.pos += ((n + G - 1) / G) * G * W; j += n;
+  }
+}
+
+template <int NR, int R>
+__device__ __forceinline__ void level_bwd_wide(PipeB& pp, LevelBwdSmem<NR>& sm, const LevelTask& t, int jn, double (&acc)[4][NR],
+                                               const bool (&valid)[4]) {
+  const int lane = pp.lane;
+  const int isz = (t.n + 3) & ~3;
+  for (int j = 0; j < jn;) {
+    int n = (CHD - pp.pos) / isz;
+    if (n == 0) { pp.advance(); continue; }
+    n = min(n, jn - j);
+    const double* base = pp.ring + (pp.cur % NSB) * CHD + pp.pos + lane;
+#pragma unroll 4
+    for (int c = 0; c < n; ++c) {
+      double x[NR];
+      ld_loc<NR>(sm.cv, j + c, x);
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        const double m = valid[q] ? base[c * isz + 32 * q] : 0.0;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) acc[q][r] = fma(m, x[r], acc[q][r]);
+      }
+    }
+    pp.pos += n * isz; j += n;
+  }
+}
+
+template <int NR, bool PDL>
+__global__ void __launch_bounds__(32) level_backward_kernel(const LevelTask* __restrict__ tasks, const double* __restrict__ stream,
+                                                            const int32_t* __restrict__ strct, double* __restrict__ x, int32_t* status) {
+  __shared__ LevelBwdSmem<NR> sm;
+  const int lane = threadIdx.x;
+  if (PDL) griddep_launch_dependents();
+  const LevelTask t = tasks[blockIdx.x];
+  if (lane == 0) {
+    for (int s = 0; s < NSB; ++s) mbar_init(sm.bar + s, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  PipeB pp{sm.ring, sm.bar, stream + t.soff, status, t.chunks, -1, CHD, lane};
+  pp.start();
+  const int32_t* st = strct + t.goff;          // the front's update set
+  // static: positions of the first pass's update unknowns in the solution vector
+  constexpr int NG = KX / 32;
+  int64_t xo[NG];
+#pragma unroll
+  for (int q = 0; q < NG; ++q) {
+    const int j = lane + 32 * q;
+    xo[q] = j < t.u2 ? 2 * (int64_t)st[j >> 1] + (j & 1) : -1;
+  }
+  if (PDL) griddep_wait();
+  const int W = t.nch;                          // slab class: 8, 16 (lanes split the contraction index) or 0 (wide)
+  double accn[NR];
+  double accw[4][NR];
+  bool valid[4];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) accn[r] = 0.0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    valid[q] = lane + 32 * q < t.n;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) accw[q][r] = 0.0;
+  }
+  const int Rw = (t.n + 31) >> 5;
+  for (int j0 = 0; j0 < t.u2; j0 += KX) {
+    const int jn = min(KX, t.u2 - j0);
+    if (j0 > 0) {
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < NG; ++q) {
+        const int j = j0 + lane + 32 * q;
+        xo[q] = j < t.u2 ? 2 * (int64_t)st[j >> 1] + (j & 1) : -1;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NG; ++q) {
+      if (xo[q] < 0) continue;
+      double v[NR];
+      ldg_v<NR>(x, xo[q], v);
+#pragma unroll
+      for (int r = 0; r < NR; ++r) sm.cv[(lane + 32 * q) * NR + r] = v[r];
+    }
+    __syncwarp();
+    if (W == 8) level_bwd_narrow<NR, 8>(pp, sm, jn, accn);
+    else if (W == 16) level_bwd_narrow<NR, 16>(pp, sm, jn, accn);
+    else if (Rw == 1) level_bwd_wide<NR, 1>(pp, sm, t, jn, accw, valid);
+    else if (Rw == 2) level_bwd_wide<NR, 2>(pp, sm, t, jn, accw, valid);
+    else if (Rw == 3) level_bwd_wide<NR, 3>(pp, sm, t, jn, accw, valid);
+    else level_bwd_wide<NR, 4>(pp, sm, t, jn, accw, valid);
+  }
+  if (W == 8 || W == 16) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      double v = accn[r];
+      for (int off = 16; off >= W; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      accn[r] = v;
+    }
+    if (lane < t.n) {       // t.n <= W: lanes 0..n-1 hold the totals of their columns
+      double z[NR];
+      ldg_v<NR>(x, t.g0 + t.r0 + lane, z);
+#pragma unroll
+      for (int r = 0; r < NR; ++r) z[r] -= accn[r];
+      stg_v<NR>(x, t.g0 + t.r0 + lane, z);
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (!valid[q]) continue;
+      double z[NR];
+      ldg_v<NR>(x, t.g0 + t.r0 + lane + 32 * q, z);
+#pragma unroll
+      for (int r = 0; r < NR; ++r) z[r] -= accw[q][r];
+      stg_v<NR>(x, t.g0 + t.r0 + lane + 32 * q, z);
+    }
+  }
+  pp.drain();
+}
+
+// pack of the level tasks: one CTA per task copies its slab from the front pool into its stream
+__global__ void __launch_bounds__(256) level_pack_kernel(const LevelTask* __restrict__ ftasks, int nf_tasks, const LevelTask* __restrict__ btasks,
+                                                         const int64_t* __restrict__ foff, const double* __restrict__ pool,
+                                                         double* __restrict__ lfwd, double* __restrict__ lbwd) {
+  const bool fwd = (int)blockIdx.x < nf_tasks;
+  const LevelTask t = fwd ? ftasks[blockIdx.x] : btasks[blockIdx.x - nf_tasks];
+  const int f = t.f, tid = threadIdx.x;
+  const int s2 = t.s2, u2 = t.u2;
+  const int64_t ld = s2 + u2;
+  const double* src = pool + foff[f];
+  if (fwd) {
+    const int ldb = (t.n + 3) & ~3;
+    double* dst = lfwd + t.soff;
+    for (int idx = tid; idx < s2 * ldb; idx += 256) {
+      const int k = idx / ldb, i = idx - k * ldb;
+      dst[item_off(k, ldb) + i] = i < t.n ? src[k * ld + t.r0 + i] : 0.0;
+    }
+  } else {
+    const int isz = t.nch ? t.nch : ((t.n + 3) & ~3);
+    double* dst = lbwd + t.soff;
+    // W(j, c) = src[(c0 + c) * ld + s2 + j]: read with j fastest (coalesced), write item j, column c
+    for (int64_t idx = tid; idx < (int64_t)u2 * isz; idx += 256) {
+      const int c = (int)(idx / u2), j = (int)(idx - (int64_t)c * u2);
+      dst[item_off(j, isz) + c] = c < t.n ? src[(int64_t)(t.r0 + c) * ld + s2 + j] : 0.0;
+    }
+  }
+}
+
 int stream_nloc() {
   static const int v = [] {
     const char* e = std::getenv("PLFEM_STREAM_NLOC");
@@ -517,18 +893,71 @@ void build_stream_plan(plfem_ctx* ctx, const FrontPlan& P, const std::vector<int
   PLFEM_CUDA(stream_wait(ctx->stream));       // the host vectors above are pageable and local
 }
 
+// Task lists of the fronts above the bottom subtrees, level by level, and the layout of their streams.
+void build_level_plan(plfem_ctx* ctx, const FrontPlan& P, const std::vector<int32_t>& uoff, const std::vector<uint8_t>& in_sub,
+                      const std::vector<int32_t>& goff, StreamPlan& S) {
+  std::vector<LevelTask> ft, bt;
+  S.fptr.assign(P.nlevels + 1, 0); S.bptr.assign(P.nlevels + 1, 0);
+  int64_t fo = 0, bo = 0;     // chunks
+  for (int l = 0; l < P.nlevels; ++l) {
+    for (int q = P.lptr[l]; q < P.lptr[l + 1]; ++q) {
+      const int f = P.lfront[q];
+      if (in_sub[f]) continue;
+      const int s2 = 2 * P.s[f], u2 = 2 * (P.sptr[f + 1] - P.sptr[f]), rows = s2 + u2;
+      LevelTask t{};
+      t.g0 = 2 * (int64_t)P.first[f]; t.s2 = s2; t.u2 = u2; t.f = f;
+      // forward: slabs of rows.  A slab's stream is s2 columns of its height: about 32 KB (the ring) for the latency-bound
+      // fronts, full 128-row slabs for the fronts of the bandwidth-bound regime (fewer redundant gathers of the pivot part)
+      const int nr = rows >= 512 ? 128 : std::max(32, std::min(128, (4096 / s2) & ~31));
+      t.goff = goff[f]; t.uoff = uoff[f]; t.nch = P.cptr[f + 1] - P.cptr[f];
+      for (int r0 = 0; r0 < rows; r0 += nr) {
+        t.r0 = r0; t.n = std::min(nr, rows - r0);
+        t.chunks = item_chunks(s2, (t.n + 3) & ~3);
+        t.soff = fo * CHD; fo += t.chunks;
+        ft.push_back(t);
+      }
+      if (u2 == 0) continue;
+      // backward: slabs of pivot columns; the longer the contraction (u2), the narrower the slab, down to 8 columns with the
+      // lanes split four ways over the contraction index
+      int W, nc;
+      if (u2 <= 128) { W = 0; nc = std::max(32, std::min(128, (4096 / u2) & ~31)); }
+      else if (u2 <= 256) { W = 16; nc = 16; }
+      else if (u2 <= 1024) { W = 8; nc = 8; }
+      else { W = 0; nc = 32; }
+      t.goff = P.sptr[f]; t.uoff = 0; t.nch = W;
+      for (int c0 = 0; c0 < s2; c0 += nc) {
+        t.r0 = c0; t.n = std::min(nc, s2 - c0);
+        t.chunks = item_chunks(u2, W ? W : ((t.n + 3) & ~3));
+        t.soff = bo * CHD; bo += t.chunks;
+        bt.push_back(t);
+      }
+    }
+    S.fptr[l + 1] = (int32_t)ft.size(); S.bptr[l + 1] = (int32_t)bt.size();
+  }
+  S.ftasks.upload(ctx, ft); S.btasks.upload(ctx, bt);
+  S.lfwd.alloc(ctx, (size_t)std::max<int64_t>(fo, 1) * CHD); S.lbwd.alloc(ctx, (size_t)std::max<int64_t>(bo, 1) * CHD);
+  S.lfwd_doubles = fo * CHD; S.lbwd_doubles = bo * CHD;
+  PLFEM_CUDA(stream_wait(ctx->stream));       // the host vectors above are pageable and local
+}
+
 void launch_stream_pack(plfem_ctx* ctx, const DevPlan& D) {
   const StreamPlan& S = D.st;
-  if (S.n_fronts == 0) return;
-  stream_pack_kernel<<<S.n_fronts, 256, 0, ctx->stream>>>(S.recs.p, S.subs.p, D.s.p, D.sptr.p, D.foff.p, D.pool.p, S.lmaps.p, S.sfwd.p, S.sbwd.p);
+  if (S.n_fronts > 0) {
+    stream_pack_kernel<<<S.n_fronts, 256, 0, ctx->stream>>>(S.recs.p, S.subs.p, D.s.p, D.sptr.p, D.foff.p, D.pool.p, S.lmaps.p, S.sfwd.p, S.sbwd.p);
+    ctx->launches++;
+  }
+  const int nf = (int)S.ftasks.n, nb = (int)S.btasks.n;
+  if (nf + nb > 0) {
+    level_pack_kernel<<<nf + nb, 256, 0, ctx->stream>>>(S.ftasks.p, nf, S.btasks.p, D.foff.p, D.pool.p, S.lfwd.p, S.lbwd.p);
+    ctx->launches++;
+  }
   PLFEM_CUDA(cudaGetLastError());
-  ctx->launches++;
 }
 
 namespace {
 template <class... KArgs, class... Args>
 void launch_warp_ctas(void (*kernel)(KArgs...), bool pdl, int grid, cudaStream_t st, Args... args) {
-  static thread_local const void* configured[8] = {};
+  static thread_local const void* configured[16] = {};
   bool seen = false;
   for (const void* k : configured) seen |= (k == (const void*)kernel);
   if (!seen) {      // all of the SM's shared memory for the rings: 8 warps per SM
@@ -558,6 +987,35 @@ void launch_stream_forward(plfem_ctx* ctx, const DevPlan& D, const double* rhs, 
   ctx->launches++;
 }
 
+void launch_level_forward(plfem_ctx* ctx, const DevPlan& D, int level, const double* rhs, double* out, int nrhs, bool pdl) {
+  const StreamPlan& S = D.st;
+  const int n = S.fptr[level + 1] - S.fptr[level];
+  const LevelTask* tasks = S.ftasks.p + S.fptr[level];
+  const RhsView rv{rhs, out, D.upd.p};
+  if (nrhs == 1) {
+    if (pdl) launch_warp_ctas(level_forward_kernel<1, true>, true, n, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p);
+    else launch_warp_ctas(level_forward_kernel<1, false>, false, n, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p);
+  } else {
+    if (pdl) launch_warp_ctas(level_forward_kernel<SOLVE_NRHS, true>, true, n, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p);
+    else launch_warp_ctas(level_forward_kernel<SOLVE_NRHS, false>, false, n, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p);
+  }
+  ctx->launches++;
+}
+
+void launch_level_backward(plfem_ctx* ctx, const DevPlan& D, int level, double* x, int nrhs, bool pdl) {
+  const StreamPlan& S = D.st;
+  const int n = S.bptr[level + 1] - S.bptr[level];
+  const LevelTask* tasks = S.btasks.p + S.bptr[level];
+  if (nrhs == 1) {
+    if (pdl) launch_warp_ctas(level_backward_kernel<1, true>, true, n, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, D.status.p);
+    else launch_warp_ctas(level_backward_kernel<1, false>, false, n, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, D.status.p);
+  } else {
+    if (pdl) launch_warp_ctas(level_backward_kernel<SOLVE_NRHS, true>, true, n, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, D.status.p);
+    else launch_warp_ctas(level_backward_kernel<SOLVE_NRHS, false>, false, n, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, D.status.p);
+  }
+  ctx->launches++;
+}
+
 void launch_stream_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs, bool pdl) {
   const StreamPlan& S = D.st;
   if (S.n_subs == 0) return;
@@ -572,3 +1030,4 @@ void launch_stream_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrh
 }
 
 }  // namespace plfem
+

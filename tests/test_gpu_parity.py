@@ -317,14 +317,37 @@ def test_pool_solve_many_keeps_job_order(small_case):
 
 
 def _check_record_against_oracle(rec, d, mesh, f):
+    """A sweep record against the oracle's mode list of the same design.  The divergence filter of `solver_fem.py:228-231`
+    thresholds a per-vector quantity (v^T D v / beta^2) that is NOT defined for the members of a degenerate pair (any rotation
+    of the pair is an eigenbasis; ARPACK's own answer changes with its random start vector), so modes that sit within 30 % of
+    the threshold, or belong to a degenerate pair straddling it, may legitimately fall on either side: the record must agree
+    with the oracle on every mode that is not ambiguous in that sense, and exactly when no mode is."""
     from plfem_b200 import sweep
-    modes = O.solve_vectorial_modes(sweep.design_geometry(d), mesh, d["n_modes"])
-    assert len(modes) == rec[f["n_modes_found"]], (d["n_cores"], d["wavelength_nm"])
-    ne = np.array([m["n_eff"] for m in modes])
-    assert abs(ne.max() / rec[f["n_eff_max"]] - 1) < 1e-8 and abs(ne.min() / rec[f["n_eff_min"]] - 1) < 1e-8
-    assert abs(ne.mean() / rec[f["n_eff_mean"]] - 1) < 1e-8
-    assert abs(np.mean([m["confinement"] for m in modes]) - rec[f["confinement_mean"]]) < 5e-6
+    modes, raw = O.solve_vectorial_modes(sweep.design_geometry(d), mesh, d["n_modes"], return_raw=True)
+    mr = raw["modes_raw"]
+    dr = np.array([m["div_ratio"] for m in mr])
+    ne_raw = np.array([m["n_eff"] for m in mr])
+    thr = max(10 * np.median(dr), 50 * dr.min(), 1e-6)
+    amb = np.abs(dr / thr - 1) < 0.3
+    for i in range(len(mr)):
+        twins = np.abs(ne_raw / ne_raw[i] - 1) < 1e-9
+        if twins.sum() > 1 and dr[twins].min() < 1.3 * thr and dr[twins].max() > thr / 1.3:
+            amb[i] = True
+    guided_ids = {id(m) for m in modes}
+    sure = [m for m, a in zip(mr, amb) if id(m) in guided_ids and not a]
+    n_amb = int(amb.sum())
+    assert len(sure) <= rec[f["n_modes_found"]] <= len(sure) + n_amb, (d["n_cores"], d["wavelength_nm"], len(modes), n_amb)
+    if n_amb == 0:
+        assert len(modes) == rec[f["n_modes_found"]]
+        ne = np.array([m["n_eff"] for m in modes])
+        assert abs(ne.max() / rec[f["n_eff_max"]] - 1) < 1e-8 and abs(ne.min() / rec[f["n_eff_min"]] - 1) < 1e-8
+        assert abs(ne.mean() / rec[f["n_eff_mean"]] - 1) < 1e-8
+        assert abs(np.mean([m["confinement"] for m in modes]) - rec[f["confinement_mean"]]) < 5e-6
+    # the leading modes of the record, as long as the oracle's list is unambiguous there
+    amb_ne = ne_raw[amb]
     for k, m in enumerate(modes[:sweep.N_PER_MODE]):
+        if len(amb_ne) and m["n_eff"] <= amb_ne.max() * (1 + 1e-9):
+            break
         assert abs(m["n_eff"] / rec[f[f"n_eff_mode_{k}"]] - 1) < 1e-8
 
 
