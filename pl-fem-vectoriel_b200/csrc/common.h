@@ -209,7 +209,7 @@ struct DevPlan {
   DevBuf<int32_t> uoff;              // offset of each front's update vector (in doubles)
   std::vector<int32_t> lptr;         // host copy of the level schedule
   std::vector<int32_t> lmax_m;       // largest pivot block (unknowns) per level
-  std::vector<int32_t> lsplit, lmax_small;   // per level: fronts with a pivot block <= 64 unknowns (listed first in lfront), their largest block
+  std::vector<int32_t> lsplit32, lsplit64;   // per level: fronts with a pivot block <= 32 / <= 64 unknowns (listed first in lfront)
   // per-level work lists (host-built): tiles for the two GEMMs, slabs for extend-add and the sweeps
   DevBuf<int4> w_tiles, s_tiles, ea_slabs;
   DevBuf<int32_t> gsrc;

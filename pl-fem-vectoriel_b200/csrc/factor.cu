@@ -99,87 +99,110 @@ __global__ void __launch_bounds__(256) extend_add_kernel(const int4* __restrict_
   }
 }
 
-// ---- pivot block inverse: Gauss-Jordan with partial pivoting in shared memory, one CTA per front ------
-// Thread layout: i = tid % MP (row), jg = tid / MP (column group), MP = m rounded up to 32/64/128, so the
-// rank-1 update of step k needs no integer division and touches shared memory conflict-free.
-__global__ void __launch_bounds__(1024) invert_kernel(const int32_t* __restrict__ fronts, PlanView P, int32_t* status) {
-  extern __shared__ double sm[];
+// ---- pivot block inverse: Gauss-Jordan with partial pivoting, the block in REGISTERS, one CTA per front -------------
+// The first version kept the block in shared memory and needed three CTA barriers and three passes over the block per
+// elimination step: 430 us of pure latency for a 128 x 128 block, the single largest kernel of a forest once the sweeps had
+// been streamed (14 % of the kernel time).  Here thread (i, jg) owns row i and the columns jg, jg + NG, ... (E of them) in
+// registers; a step publishes only the pivot row and the pivot column (two barriers, ~3 KB of shared traffic), every warp
+// finds the pivot redundantly from the published column, and rows are never swapped: step k pivots on the largest entry of
+// column k among the rows not used before (the same choices as partial pivoting with swaps, the same arithmetic), and the
+// row / column permutation is undone when the result is written back: A^-1[r][c] = a[p_r][step at which row c was used].
+template <int MP, int NG, int E>
+__global__ void __launch_bounds__(MP * NG, MP == 128 ? 1 : (MP == 64 ? 3 : 6)) invert_kernel(const int32_t* __restrict__ fronts, PlanView P, int32_t* status) {
+  extern __shared__ double sB[];          // the finished block for the symmetrised write-back
+  __shared__ double cand[MP], prow[MP], pcol[2 * MP];
+  __shared__ int p_of[MP], step_of[MP];
   const int f = fronts[blockIdx.x];
   const int m = 2 * P.s[f];
   const int64_t ld = 2 * (int64_t)(P.s[f] + front_u(P, f));
   double* F = P.pool + P.foff[f];
-  const int lds = m | 1;
-  double* a = sm;                 // m x m, column-major, leading dimension lds
-  double* colk = a + (size_t)lds * m;
-  double* rowk = colk + m;
-  __shared__ int piv[MAX_PIV];
-  __shared__ int src[MAX_PIV];
-  __shared__ int s_p;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int MP = (m <= 32) ? 32 : (m <= 64 ? 64 : 128);
-  const int i = tid & (MP - 1), jg = tid / MP, ng = nt / MP;
-  if (i < m)
-    for (int j = jg; j < m; j += ng) a[i + j * lds] = F[(int64_t)j * ld + i];
-  __syncthreads();
-  for (int k = 0; k < m; ++k) {
-    if (tid < 32) {
-      double best = -1.0; int bi = k;
-      for (int r = k + tid; r < m; r += 32) {
-        const double v = fabs(a[r + k * lds]);
-        if (v > best) { best = v; bi = r; }   // NaN never wins; an all-NaN column keeps bi = k
-      }
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int i = tid % MP, jg = tid / MP;
+  double a[E];
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const double ob = __shfl_down_sync(0xffffffffu, best, off);
-        const int oi = __shfl_down_sync(0xffffffffu, bi, off);
-        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-      }
-      if (tid == 0) {
-        s_p = bi; piv[k] = bi;
-        if (!(best > 0.0) || !isfinite(best)) { atomicExch(status, 1); atomicExch(status + 3, f); }
-      }
-    }
-    __syncthreads();
-    const int p = s_p;
-    const double inv = 1.0 / a[p + k * lds];
-    // row swap k <-> p fused with the copies of the scaled pivot row (first m threads) and of the
-    // pivot column (last m threads)
-    if (tid < m) {
-      const int j = tid;
-      const double ak = a[k + j * lds], ap = a[p + j * lds];
-      rowk[j] = ap * inv;
-      if (p != k && j != k) a[p + j * lds] = ak;
-    }
-    if (tid >= nt - m) {
-      const int r = tid - (nt - m);
-      double v;
-      if (r == k) v = 0.0;                         // unused
-      else if (r == p) v = a[k + k * lds];         // row p now holds old row k
-      else v = a[r + k * lds];
-      colk[r] = v;
-    }
-    __syncthreads();
-    if (i < m) {
-      const double ci = colk[i];
-      if (i == k) {
-        for (int j = jg; j < m; j += ng) a[i + j * lds] = (j == k) ? inv : rowk[j];
-      } else {
-        for (int j = jg; j < m; j += ng) a[i + j * lds] = (j == k) ? -ci * inv : a[i + j * lds] - ci * rowk[j];
-      }
-    }
-    __syncthreads();
+  for (int t = 0; t < E; ++t) {
+    const int j = jg + NG * t;
+    a[t] = (i < m && j < m) ? F[(int64_t)j * ld + i] : 0.0;
   }
-  if (tid == 0) {
-    for (int j = 0; j < m; ++j) src[j] = j;
-    for (int k = m - 1; k >= 0; --k) { const int t = src[k]; src[k] = src[piv[k]]; src[piv[k]] = t; }
+  bool used = false;
+  // A step costs every thread E (load, FMA) pairs and nothing else: the scaled pivot row is published by the threads that own
+  // it, column k is patched afterwards by the one column group that owns it (jg is uniform within a warp), rows and columns
+  // beyond m hold zeros and take part without predicates, and only the threads that need 1 / pivot compute it.
+  for (int k = 0; k < m; ++k) {
+    const int kt = k / NG, kg = k % NG;
+    double* pc = pcol + (k & 1) * MP;       // double-buffered: rows of the previous step may still be reading theirs
+    if (jg == kg) {
+      double mine = 0.0;                    // a[kt] without a dynamic register index
+#pragma unroll
+      for (int t = 0; t < E; ++t) mine = (t == kt) ? a[t] : mine;
+      // an unused row always beats a used one, also when its entry is NaN (-0.5: it loses against every number, the step is
+      // flagged as singular, and the pivot order stays a permutation)
+      const double am = fabs(mine);
+      cand[i] = (i < m && !used) ? (am == am ? am : -0.5) : -1.0;
+      pc[i] = mine;
+    }
+    __syncthreads();
+    double best = -1.0; int bi = 0;
+#pragma unroll
+    for (int r = lane; r < MP; r += 32) {
+      const double v = cand[r];
+      if (v > best) { best = v; bi = r; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    const int p = bi;                       // the same in every warp
+    if (tid == 0) {
+      p_of[k] = p; step_of[p] = k;
+      if (!(best > 0.0) || !isfinite(best)) { atomicExch(status, 1); atomicExch(status + 3, f); }
+    }
+    const double piv = pc[p];
+    if (i == p) {
+      used = true;
+      const double inv = 1.0 / piv;
+#pragma unroll
+      for (int t = 0; t < E; ++t) prow[jg + NG * t] = a[t] * inv;
+    }
+    __syncthreads();
+    const double ci = pc[i];
+    if (i == p) {
+#pragma unroll
+      for (int t = 0; t < E; ++t) a[t] = prow[jg + NG * t];
+    } else {
+#pragma unroll
+      for (int t = 0; t < E; ++t) a[t] = a[t] - ci * prow[jg + NG * t];
+    }
+    if (jg == kg) {                         // column k of the inverse-in-progress
+      const double inv = 1.0 / piv;
+      const double v = (i == p) ? inv : -ci * inv;
+#pragma unroll
+      for (int t = 0; t < E; ++t) a[t] = (t == kt) ? v : a[t];
+    }
+  }
+  const int lds = m | 1;
+  if (i < m) {
+#pragma unroll
+    for (int t = 0; t < E; ++t) {
+      const int j = jg + NG * t;
+      if (j < m) sB[i + j * lds] = a[t];
+    }
   }
   __syncthreads();
   // The inverse of a symmetric block is symmetric; the computed one only to cond x eps, and the Schur complement
   // S = F22 - F12^T (F11^-1 F12) is formed from the upper block alone, so that antisymmetric part would land in S, then in
   // the parent's pivot block, amplified by |W|^2 level by level (it, not the block-local pivoting, cost
   // the raw solve six digits and made structured meshes diverge).  Write back the average with the transpose.
-  if (i < m)
-    for (int j = jg; j < m; j += ng) F[(int64_t)j * ld + i] = 0.5 * (a[i + src[j] * lds] + a[j + src[i] * lds]);
+  if (i < m) {
+    const int pr = p_of[i], sr = step_of[i];
+#pragma unroll
+    for (int t = 0; t < E; ++t) {
+      const int c = jg + NG * t;
+      if (c < m) F[(int64_t)c * ld + i] = 0.5 * (sB[pr + step_of[c] * lds] + sB[p_of[c] + sr * lds]);
+    }
+  }
 }
 
 // ---- tiled FP64 GEMM used for W^T and the Schur update -------------------------------------------------
@@ -247,6 +270,99 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ Ap, int64_t
   }
 }
 
+// The same tile on the FP64 tensor path: mma.sync m8n8k4 (DMMA).  tcgen05 has no f64 kind, so warp-level DMMA is the tensor
+// path Blackwell offers for this precision; on this B200 it peaks at 37.1 TFLOP/s against 34.1 for CUDA-core FMAs and 35.1
+// for cuBLAS DGEMM (scripts/micro/fp64_peak.cu, profiles/r02_fp64_peak.txt), so what it buys is not peak but issue slots and
+// shared-memory bandwidth: 16 MMAs (4096 FMAs) per 8 fragment loads, where the FMA tile needs 8 loads per 16 FMAs.
+// 128 threads = 2 x 2 warps, each warp a 32 x 32 block of the 64 x 64 tile = 4 x 4 MMA tiles, 32 accumulators per lane.
+// Fragment layout (PTX ISA, m8n8k4 .f64): A[lane >> 2][lane & 3], B[lane & 3][lane >> 2], C[lane >> 2][2 (lane & 3) + {0, 1}].
+constexpr int DK = 16;        // k-slab of the DMMA tile
+constexpr int DLD = GT + 4;   // leading dimension of the k-major slabs: 4 k-rows x 4 row-octets hit 16 distinct bank pairs
+template <bool B_KCONTIG, bool ACCUM>
+__device__ __forceinline__ void gemm_tile_dmma(const double* __restrict__ Ap, int64_t lda, const double* __restrict__ Bp,
+                                               int64_t ldb, double* __restrict__ Cp, int64_t ldc, int M, int N, int K,
+                                               int m0, int n0) {
+  __shared__ double As[DK][DLD];
+  __shared__ double Bs[DK][DLD];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
+  const int fr = lane >> 2, fk = lane & 3;
+  double c[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) c[a][b][0] = c[a][b][1] = 0.0;
+  for (int k0 = 0; k0 < K; k0 += DK) {
+    for (int t = tid; t < GT * DK; t += 128) {
+      const int kk = t % DK, i = t / DK;
+      const int gi = m0 + i, gk = k0 + kk;
+      As[kk][i] = (gi < M && gk < K) ? Ap[(int64_t)gi * lda + gk] : 0.0;
+    }
+    if (B_KCONTIG) {
+      for (int t = tid; t < GT * DK; t += 128) {
+        const int kk = t % DK, j = t / DK;
+        const int gj = n0 + j, gk = k0 + kk;
+        Bs[kk][j] = (gj < N && gk < K) ? Bp[(int64_t)gj * ldb + gk] : 0.0;
+      }
+    } else {
+      for (int t = tid; t < GT * DK; t += 128) {
+        const int j = t % GT, kk = t / GT;
+        const int gj = n0 + j, gk = k0 + kk;
+        Bs[kk][j] = (gj < N && gk < K) ? Bp[(int64_t)gk * ldb + gj] : 0.0;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < DK; kk += 4) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) av[a] = As[kk + fk][wm + 8 * a + fr];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bv[b] = Bs[kk + fk][wn + 8 * b + fr];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(c[a][b][0]), "+d"(c[a][b][1])
+                       : "d"(av[a]), "d"(bv[b]));
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int b = 0; b < 4; ++b)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int gj = n0 + wn + 8 * b + 2 * fk + e;
+      if (gj >= N) continue;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int gi = m0 + wm + 8 * a + fr;
+        if (gi >= M) continue;
+        double* cp = Cp + (int64_t)gj * ldc + gi;
+        if (ACCUM) *cp -= c[a][b][e]; else *cp = c[a][b][e];
+      }
+    }
+}
+
+__global__ void __launch_bounds__(128) gemm_w_dmma_kernel(const int4* __restrict__ tiles, PlanView P) {
+  const int4 t = tiles[blockIdx.x];
+  const int f = t.x;
+  const int s2 = 2 * P.s[f], u2 = 2 * front_u(P, f);
+  const int64_t ld = s2 + u2;
+  double* F = P.pool + P.foff[f];
+  gemm_tile_dmma<true, false>(F + (int64_t)s2 * ld, ld, F, ld, F + s2, ld, u2, s2, s2, t.y, t.z);
+}
+
+__global__ void __launch_bounds__(128) gemm_schur_dmma_kernel(const int4* __restrict__ tiles, PlanView P) {
+  const int4 t = tiles[blockIdx.x];
+  const int f = t.x;
+  const int s2 = 2 * P.s[f], u2 = 2 * front_u(P, f);
+  const int64_t ld = s2 + u2;
+  double* F = P.pool + P.foff[f];
+  gemm_tile_dmma<false, true>(F + (int64_t)s2 * ld, ld, F + s2, ld, F + (int64_t)s2 * ld + s2, ld, u2, u2, s2, t.y, t.z);
+}
+
 // W^T:  F21new(j, i) = sum_k F12(k, j) * F11inv(k, i)      (j over 2u, i over 2s, k over 2s)
 __global__ void __launch_bounds__(256) gemm_w_kernel(const int4* __restrict__ tiles, PlanView P) {
   const int4 t = tiles[blockIdx.x];
@@ -269,7 +385,7 @@ __global__ void __launch_bounds__(256) gemm_schur_kernel(const int4* __restrict_
                          F + (int64_t)s2 * ld + s2, ld, u2, u2, s2, t.y, t.z);
 }
 
-size_t invert_smem(int m) { return ((size_t)(m | 1) * m + 2 * (size_t)m) * sizeof(double); }
+size_t invert_smem(int m) { return (size_t)(m | 1) * m * sizeof(double); }
 
 PlanView view(const DevPlan& D) {
   PlanView v;
@@ -288,15 +404,15 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D) {
   D.sn_of.upload(ctx, P.sn_of); D.parent.upload(ctx, P.parent); D.cptr.upload(ctx, P.cptr); D.child.upload(ctx, P.child);
   D.cmap_ptr.upload(ctx, P.cmap_ptr); D.cmap.upload(ctx, P.cmap);
   {
-    // fronts of a level in two size classes (pivot block <= 64 unknowns first): the pivot-block inverse runs 256-thread
-    // CTAs on the first class and 1024-thread CTAs on the second — one oversized leaf must not put a thousand threads on
-    // each of the thousands of 48 x 48 blocks of its level
+    // fronts of a level in three size classes of their pivot block (<= 32, <= 64, <= 128 unknowns): each class has its own
+    // instantiation of the register-resident inverse (256 / 256 / 512 threads)
     std::vector<int32_t> lf(P.lfront);
-    D.lsplit.assign(P.nlevels, 0); D.lmax_small.assign(P.nlevels, 0);
+    D.lsplit32.assign(P.nlevels, 0); D.lsplit64.assign(P.nlevels, 0);
     for (int l = 0; l < P.nlevels; ++l) {
-      auto mid = std::stable_partition(lf.begin() + P.lptr[l], lf.begin() + P.lptr[l + 1], [&](int32_t f) { return 2 * P.s[f] <= 64; });
-      D.lsplit[l] = (int32_t)(mid - (lf.begin() + P.lptr[l]));
-      for (auto it = lf.begin() + P.lptr[l]; it != mid; ++it) D.lmax_small[l] = std::max(D.lmax_small[l], 2 * P.s[*it]);
+      auto b0 = lf.begin() + P.lptr[l], e0 = lf.begin() + P.lptr[l + 1];
+      auto m32 = std::stable_partition(b0, e0, [&](int32_t f) { return 2 * P.s[f] <= 32; });
+      auto m64 = std::stable_partition(m32, e0, [&](int32_t f) { return 2 * P.s[f] <= 64; });
+      D.lsplit32[l] = (int32_t)(m32 - b0); D.lsplit64[l] = (int32_t)(m64 - b0);
     }
     D.lfront.upload(ctx, lf);
   }
@@ -371,10 +487,12 @@ void launch_front_load(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const 
 void run_factorization(plfem_ctx* ctx, const DevPlan& D) {
   static bool attr_set[64] = {};
   if (!(ctx->device < 64 && attr_set[ctx->device])) {
-    PLFEM_CUDA(cudaFuncSetAttribute(invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)invert_smem(MAX_PIV)));
+    PLFEM_CUDA(cudaFuncSetAttribute(invert_kernel<128, 4, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)invert_smem(MAX_PIV)));
     if (ctx->device < 64) attr_set[ctx->device] = true;
   }
   const PlanView v = view(D);
+  // frontal GEMMs: FP64 tensor path (DMMA) unless PLFEM_GEMM=fma asks for the CUDA-core tile
+  static const bool dmma = [] { const char* e = std::getenv("PLFEM_GEMM"); return !(e && e[0] == 'f'); }();
   for (int l = 0; l < D.nlevels; ++l) {
     const int nea = D.ea_ptr[l + 1] - D.ea_ptr[l];
     if (nea > 0) {
@@ -382,25 +500,21 @@ void run_factorization(plfem_ctx* ctx, const DevPlan& D) {
       ctx->launches++;
     }
     const int nfl = D.lptr[l + 1] - D.lptr[l];
-    // two size classes in separate launches only where the level is throughput-bound (thousands of small blocks, as at the
-    // bottom of a forest); a latency-bound level runs both classes in one launch, concurrently
-    const int nsmall = D.lsplit[l];
-    if (nsmall >= 1500 && nfl > nsmall) {
-      invert_kernel<<<nsmall, 256, invert_smem(D.lmax_small[l]), ctx->stream>>>(D.lfront.p + D.lptr[l], v, D.status.p);
-      invert_kernel<<<nfl - nsmall, 1024, invert_smem(D.lmax_m[l]), ctx->stream>>>(D.lfront.p + D.lptr[l] + nsmall, v, D.status.p);
-      ctx->launches += 2;
-    } else {
-      invert_kernel<<<nfl, D.lmax_m[l] > 64 ? 1024 : 256, invert_smem(D.lmax_m[l]), ctx->stream>>>(D.lfront.p + D.lptr[l], v, D.status.p);
-      ctx->launches++;
-    }
+    const int n32 = D.lsplit32[l], n64 = D.lsplit64[l] - D.lsplit32[l], n128 = nfl - D.lsplit64[l];
+    const int32_t* lf = D.lfront.p + D.lptr[l];
+    if (n32 > 0) { invert_kernel<32, 8, 4><<<n32, 256, invert_smem(32), ctx->stream>>>(lf, v, D.status.p); ctx->launches++; }
+    if (n64 > 0) { invert_kernel<64, 4, 16><<<n64, 256, invert_smem(64), ctx->stream>>>(lf + n32, v, D.status.p); ctx->launches++; }
+    if (n128 > 0) { invert_kernel<128, 4, 32><<<n128, 512, invert_smem(128), ctx->stream>>>(lf + n32 + n64, v, D.status.p); ctx->launches++; }
     const int nw = D.w_ptr[l + 1] - D.w_ptr[l];
     if (nw > 0) {
-      gemm_w_kernel<<<nw, 256, 0, ctx->stream>>>(D.w_tiles.p + D.w_ptr[l], v);
+      if (dmma) gemm_w_dmma_kernel<<<nw, 128, 0, ctx->stream>>>(D.w_tiles.p + D.w_ptr[l], v);
+      else gemm_w_kernel<<<nw, 256, 0, ctx->stream>>>(D.w_tiles.p + D.w_ptr[l], v);
       ctx->launches++;
     }
     const int ns = D.s_ptr[l + 1] - D.s_ptr[l];
     if (ns > 0) {
-      gemm_schur_kernel<<<ns, 256, 0, ctx->stream>>>(D.s_tiles.p + D.s_ptr[l], v);
+      if (dmma) gemm_schur_dmma_kernel<<<ns, 128, 0, ctx->stream>>>(D.s_tiles.p + D.s_ptr[l], v);
+      else gemm_schur_kernel<<<ns, 256, 0, ctx->stream>>>(D.s_tiles.p + D.s_ptr[l], v);
       ctx->launches++;
     }
   }

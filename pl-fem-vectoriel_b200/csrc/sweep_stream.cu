@@ -906,9 +906,9 @@ void build_level_plan(plfem_ctx* ctx, const FrontPlan& P, const std::vector<int3
       const int s2 = 2 * P.s[f], u2 = 2 * (P.sptr[f + 1] - P.sptr[f]), rows = s2 + u2;
       LevelTask t{};
       t.g0 = 2 * (int64_t)P.first[f]; t.s2 = s2; t.u2 = u2; t.f = f;
-      // forward: slabs of rows.  A slab's stream is s2 columns of its height: about 32 KB (the ring) for the latency-bound
-      // fronts, full 128-row slabs for the fronts of the bandwidth-bound regime (fewer redundant gathers of the pivot part)
-      const int nr = rows >= 512 ? 128 : std::max(32, std::min(128, (4096 / s2) & ~31));
+      // forward: slabs of rows.  A slab's stream is s2 columns of its height: about 32 KB, the capacity of the ring, so that a
+      // task is completely in flight before its dependencies resolve
+      const int nr = std::max(32, std::min(128, (4096 / s2) & ~31));
       t.goff = goff[f]; t.uoff = uoff[f]; t.nch = P.cptr[f + 1] - P.cptr[f];
       for (int r0 = 0; r0 < rows; r0 += nr) {
         t.r0 = r0; t.n = std::min(nr, rows - r0);
@@ -922,8 +922,7 @@ void build_level_plan(plfem_ctx* ctx, const FrontPlan& P, const std::vector<int3
       int W, nc;
       if (u2 <= 128) { W = 0; nc = std::max(32, std::min(128, (4096 / u2) & ~31)); }
       else if (u2 <= 256) { W = 16; nc = 16; }
-      else if (u2 <= 1024) { W = 8; nc = 8; }
-      else { W = 0; nc = 32; }
+      else { W = 8; nc = 8; }
       t.goff = P.sptr[f]; t.uoff = 0; t.nch = W;
       for (int c0 = 0; c0 < s2; c0 += nc) {
         t.r0 = c0; t.n = std::min(nc, s2 - c0);
