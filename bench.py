@@ -260,7 +260,7 @@ def run_ours(args):
 
     # ---- value: a step = ONE forest of B designs per worker; meshes + DOF tables resident, everything else inside ------
     K = args.steps
-    pool = ForestPool(device=local, batch=B, workers=NW, want_vectors=False)
+    pool = ForestPool(device=local, batch=B, workers=NW, want_vectors=False, share_analysis=False)
     resident = {}                                          # worker index -> (problems, materials, shifts, ks) of its forest
 
     def prepare(_pool, c, wi):
@@ -327,7 +327,8 @@ def run_ours(args):
     stats = st.as_dict()
 
     # ---- e2e: public API, host buffers in, mode records (with eigenvectors) out -----------------------------
-    pool_e = ForestPool(device=local, batch=B, workers=NW, want_vectors=True)
+    # share_analysis off: the designs of this synthetic step sit on ONE mesh, a real sweep's do not — every design pays its own analysis
+    pool_e = ForestPool(device=local, batch=B, workers=NW, want_vectors=True, share_analysis=False)
     step_jobs = [j for f in forests for j in f]
 
     for _ in range(args.warmup):
@@ -446,6 +447,7 @@ def run_ours(args):
                                f"of a forest (each with its own symbolic analysis, assembly, factorisation, eigensolve and reductions) share "
                                f"every kernel launch, the {NW} forests in flight overlap host analysis and device work",
                        "designs_per_forest": B, "forests_in_flight": NW, "solves_per_step": NW * B,
+                       "analysis_shared_between_designs": False,
                        "k": k, "lanczos": "thick-restart block Lanczos, 4 vectors per operator application, basis 3k, designs in lockstep", "tol": _cabi.EIG_TOL,
                        "start_vector": "ones (+3 fixed pseudo-random)", "refine_steps": int(fstats["refine_steps"]),
                        "l2": f"inputs larger than L2: one forest streams {B * fstats['factor_entries'] * 8 / 1e6:.0f} MB of factor panels per sweep "

@@ -123,7 +123,9 @@ typedef struct {
   const double* v0;    /* optional start vector, reference ordering, length 2 N_solve; NULL = ones */
   int32_t leaf_nodes;  /* nested-dissection leaf size (0 = default) */
   int32_t max_sn_nodes;/* supernode width limit in nodes (0 = default) */
-  int32_t reuse_symbolic; /* 1 = keep ordering/front plan from the previous solve on this problem */
+  int32_t reuse_symbolic; /* 1 = the ordering / front plan may be reused: the one of the previous solve on this problem, or, inside
+                             a forest, the one of another design with reuse_symbolic = 1 on an identical mesh (the bands of a
+                             wavelength sweep share their mesh); 0 = analyse this design on its own */
   int32_t refine;      /* iterative-refinement steps per operator application: 0 = chosen by probing one raw solve
                           (1 for the reference's meshes), n > 0 = n, -1 = none.  Environment PLFEM_RELAX_AT=x (default
                           0 = off) applies one step fewer once every wanted Ritz pair is within x of convergence */

@@ -31,9 +31,12 @@ from .solver_fem import TrueVectorialMaxwellSolver, modes_from_solution, sigma_e
 class ForestPool:
     """``solve_many(jobs)`` with jobs = ``(geometry, mesh, n_modes_target)`` -> list of mode lists."""
 
-    def __init__(self, device: int = 0, batch: int = 8, workers: int = 2, want_vectors: bool = True, host_threads: int = 0):
+    def __init__(self, device: int = 0, batch: int = 8, workers: int = 2, want_vectors: bool = True, host_threads: int = 0,
+                 share_analysis: bool = True):
         self.device, self.batch, self.workers = int(device), max(1, int(batch)), max(1, int(workers))
         self.want_vectors = want_vectors
+        #: designs of a forest that sit on an identical mesh (the bands of a wavelength sweep) share ONE ordering / front plan
+        self.share_analysis = bool(share_analysis)
         lib = _cabi.load()
         # host threads per forest: the cores this process may count on (its share of the node under torchrun), spread
         # over the forests in flight with some oversubscription — hundreds of runnable threads per core cost more than
@@ -83,7 +86,7 @@ class ForestPool:
                 live.append(j); mats.append(m); keep.append(k_); sigmas.append(sg); ks.append(kk)
             if live:
                 res = _cabi.solve_modes_batch(ctx, [problems[j] for j in live], mats, sigmas, ks, tol=_cabi.EIG_TOL,
-                                              maxiter=12000, want_vectors=self.want_vectors)
+                                              maxiter=12000, want_vectors=self.want_vectors, reuse_symbolic=self.share_analysis)
                 for j, (vals, vecs, met, ncore, st, status) in zip(live, res):
                     geo, pb = jobs[j][0], problems[j]
                     stats[j] = st.as_dict()
@@ -98,6 +101,7 @@ class ForestPool:
                     out[j] = (guided, dict(beta_sq=vals, evecs=vecs, metrics=met, modes_raw=raw, frac_core=frac,
                                            stats=stats[j])) if return_raw else guided
             self.last_stats = stats
+            self._local.last_stats = stats          # per worker thread: `last_stats` is whichever forest finished last
             return out
         finally:
             if own:

@@ -117,6 +117,7 @@ struct plfem_problem {
   // interior solve path (host side; the device side of a solve lives in a SolveWork)
   Pattern adj;  bool adj_ready = false;        // interior nodes, interior-index numbering (for dissection)
   FrontPlan plan; bool plan_ready = false; SymbolicOptions plan_opt;
+  uint64_t mesh_print = 0;                     // fingerprint of (p, t): designs of one forest with equal meshes can share one analysis
   std::shared_ptr<SolveWork> work;             // device state of the last single-design solve (profile / debug hooks, reuse)
   int plan_serial = 0;                         // bumped whenever the front plan is rebuilt
 };
@@ -145,6 +146,12 @@ int guarded(plfem_ctx* ctx, F&& fn) {
 
 void need(bool ok, const char* msg) {
   if (!ok) throw StatusError(PLFEM_ERR_INVALID, msg);
+}
+
+double cpu_ms() {      // CPU time of the whole process (all threads): what a forest costs the host, not how long it waits
+  timespec ts;
+  clock_gettime(CLOCK_PROCESS_CPUTIME_ID, &ts);
+  return 1e3 * ts.tv_sec + 1e-6 * ts.tv_nsec;
 }
 
 double now_ms() {
@@ -275,6 +282,15 @@ int plfem_problem_create(plfem_ctx* ctx, const double* p, const int64_t* t, int6
     need(V + 3 * T < (int64_t(1) << 31), "mesh too large for 32-bit DOF ids");
     build_dof_tables(p, t, V, T, pb->dof);
     pb->p_host.assign(p, p + 2 * V);
+    {
+      uint64_t h = 1469598103934665603ull;     // FNV-1a over the raw bytes of p and t
+      auto mix = [&](const void* data, size_t bytes) {
+        const uint64_t* w = static_cast<const uint64_t*>(data);
+        for (size_t i = 0; i < bytes / 8; ++i) { h ^= w[i]; h *= 1099511628211ull; h ^= h >> 29; }
+      };
+      mix(p, sizeof(double) * 2 * (size_t)V); mix(t, sizeof(int64_t) * 3 * (size_t)T);
+      pb->mesh_print = h;
+    }
     if (!ctx) return;   // host-only problem: DOF tables and front plan only (tests of the host logic)
     PLFEM_CUDA(cudaSetDevice(ctx->device));
     pb->d_p.upload(ctx, pb->p_host);
@@ -509,54 +525,82 @@ static void solve_forest(plfem_ctx* ctx, int nb, plfem_problem* const* pbs, cons
   need(nb == 1 || block == SOLVE_NRHS, "a batch of designs needs the block eigensolver");
   ctx->launches = 0;
   const double t0 = now_ms();
+  static const bool cpu_timing = std::getenv("PLFEM_TIMING") != nullptr;
+  double c_[6] = {cpu_ms(), 0, 0, 0, 0, 0};
 
   // -- symbolic (host), designs in parallel -------------------------------------------------------------
   std::vector<double> ms_sym(nb, 0.0);
   std::vector<std::vector<uint8_t>> masks(nb);
   const bool have_work = reuse_work && W.ready;
+  // Designs that allow it (reuse_symbolic = 1) and sit on the SAME mesh — the bands of a wavelength sweep, README.md:226-243:
+  // the mesh depends on the geometry only, mesh.py:232-289 — share one analysis: the first of them is analysed, the others
+  // copy its front plan (ordering, fronts, update sets: integers only, nothing numerical is shared).
+  std::vector<int> donor(nb, -1);
+  for (int b = 0; b < nb; ++b) {
+    if (!opts[b].reuse_symbolic || pbs[b]->plan_ready) continue;
+    for (int c = 0; c < b; ++c)
+      if (opts[c].reuse_symbolic && donor[c] < 0 && pbs[c]->mesh_print == pbs[b]->mesh_print && pbs[c]->dof.N == pbs[b]->dof.N &&
+          pbs[c]->dof.T == pbs[b]->dof.T && pbs[c]->dof.interior.size() == pbs[b]->dof.interior.size() &&
+          opts[c].leaf_nodes == opts[b].leaf_nodes && opts[c].max_sn_nodes == opts[b].max_sn_nodes) { donor[b] = c; break; }
+  }
   {
     const int hw = host_thread_budget();      // threads this call may occupy (lowered when several forests / ranks share the host)
     const int outer = std::min(nb, hw);
     std::atomic<int> next{0};
     std::exception_ptr err; std::mutex mu;
-    auto work = [&] {
-      if (nb > 1) set_host_threads_local(std::max(1, std::min(8, hw / outer)));
-      for (int b; (b = next.fetch_add(1)) < nb;) {
-        try {
-          const double ta = now_ms();
-          plfem_problem* pb = pbs[b];
-          ensure_plan(pb, opts[b].leaf_nodes, opts[b].max_sn_nodes, opts[b].reuse_symbolic != 0);
-          // core mask of the permuted interior nodes (solver_fem.py:200-203)
-          const plfem_material* mat = &mats[b];
-          const int64_t n = nint[b];
-          std::vector<uint8_t>& mask = masks[b];
-          mask.assign(n, 0);
-          const double* Xc = pb->dof.doflocs.data();
-          const double* Yc = Xc + pb->dof.N;
-          int32_t cnt = 0;
-          for (int64_t r = 0; r < n; ++r) {
-            const int32_t node = pb->dof.interior[pb->plan.perm[r]];
-            bool in = false;
-            for (int c = 0; c < mat->n_cores && mat->cores_xy; ++c) {
-              volatile double dx = Xc[node] - mat->cores_xy[2 * c], dy = Yc[node] - mat->cores_xy[2 * c + 1];
-              volatile double dx2 = dx * dx, dy2 = dy * dy, rr = mat->cores_r[c] * mat->cores_r[c];
-              volatile double d2 = dx2 + dy2;
-              if (d2 <= rr) in = true;
-            }
-            mask[r] = in; cnt += in;
-          }
-          if (core_counts) core_counts[b] = cnt;
-          ms_sym[b] = now_ms() - ta;
-        } catch (...) { std::lock_guard<std::mutex> g(mu); if (!err) err = std::current_exception(); }
-      }
-      set_host_threads_local(0);
+    auto run_parallel = [&](auto&& body) {
+      next = 0;
+      auto work = [&] {
+        if (nb > 1) set_host_threads_local(std::max(1, std::min(8, hw / outer)));
+        for (int b; (b = next.fetch_add(1)) < nb;) {
+          try { body(b); } catch (...) { std::lock_guard<std::mutex> g(mu); if (!err) err = std::current_exception(); }
+        }
+        set_host_threads_local(0);
+      };
+      std::vector<std::thread> th;
+      for (int t = 1; t < outer; ++t) th.emplace_back(work);
+      work();
+      for (auto& t : th) t.join();
+      if (err) std::rethrow_exception(err);
     };
-    std::vector<std::thread> th;
-    for (int t = 1; t < outer; ++t) th.emplace_back(work);
-    work();
-    for (auto& t : th) t.join();
-    if (err) std::rethrow_exception(err);
+    run_parallel([&](int b) {            // ordering + front plan of every design that does not borrow one
+      if (donor[b] >= 0) return;
+      const double ta = now_ms();
+      ensure_plan(pbs[b], opts[b].leaf_nodes, opts[b].max_sn_nodes, opts[b].reuse_symbolic != 0);
+      ms_sym[b] = now_ms() - ta;
+    });
+    for (int b = 0; b < nb; ++b) {
+      if (donor[b] < 0) continue;
+      plfem_problem* pb = pbs[b];
+      pb->plan = pbs[donor[b]]->plan; pb->plan_opt = pbs[donor[b]]->plan_opt;
+      pb->plan_ready = true; pb->plan_serial++;
+    }
+    run_parallel([&](int b) {            // core mask of the permuted interior nodes (solver_fem.py:200-203)
+      const double ta = now_ms();
+      plfem_problem* pb = pbs[b];
+      const plfem_material* mat = &mats[b];
+      const int64_t n = nint[b];
+      std::vector<uint8_t>& mask = masks[b];
+      mask.assign(n, 0);
+      const double* Xc = pb->dof.doflocs.data();
+      const double* Yc = Xc + pb->dof.N;
+      int32_t cnt = 0;
+      for (int64_t r = 0; r < n; ++r) {
+        const int32_t node = pb->dof.interior[pb->plan.perm[r]];
+        bool in = false;
+        for (int c = 0; c < mat->n_cores && mat->cores_xy; ++c) {
+          volatile double dx = Xc[node] - mat->cores_xy[2 * c], dy = Yc[node] - mat->cores_xy[2 * c + 1];
+          volatile double dx2 = dx * dx, dy2 = dy * dy, rr = mat->cores_r[c] * mat->cores_r[c];
+          volatile double d2 = dx2 + dy2;
+          if (d2 <= rr) in = true;
+        }
+        mask[r] = in; cnt += in;
+      }
+      if (core_counts) core_counts[b] = cnt;
+      ms_sym[b] += now_ms() - ta;
+    });
   }
+  c_[1] = cpu_ms();
   if (!have_work) {
     std::vector<const FrontPlan*> plans(nb);
     for (int b = 0; b < nb; ++b) plans[b] = &pbs[b]->plan;
@@ -587,6 +631,7 @@ static void solve_forest(plfem_ctx* ctx, int nb, plfem_problem* const* pbs, cons
   const BatchDims& bd = W.bd;
   const int64_t n_tot = bd.noff[nb];
   const double t1 = now_ms();
+  c_[2] = cpu_ms();
 
   // -- assembly: one slice of the concatenated value arrays per design ----------------------------------------
   PLFEM_CUDA(cudaEventRecord(ctx->ev[0], st));
@@ -627,6 +672,7 @@ static void solve_forest(plfem_ctx* ctx, int nb, plfem_problem* const* pbs, cons
   }
 
   // -- eigensolver ----------------------------------------------------------------------------------
+  c_[3] = cpu_ms();
   DevBuf<double> d_v0;
   const double* v0p = nullptr;
   bool any_v0 = false;
@@ -666,6 +712,7 @@ static void solve_forest(plfem_ctx* ctx, int nb, plfem_problem* const* pbs, cons
     }
     des[0].n_block_op = 0; des[0].n_restart = er.n_restart;
   }
+  c_[4] = cpu_ms();
   PLFEM_CUDA(cudaEventRecord(ctx->ev[3], st));
   W.dplan.status.download(fstat, 4);
   PLFEM_CUDA(stream_wait(st));
@@ -690,6 +737,11 @@ static void solve_forest(plfem_ctx* ctx, int nb, plfem_problem* const* pbs, cons
   PLFEM_CUDA(cudaEventRecord(ctx->ev[4], st));
   PLFEM_CUDA(stream_wait(st));
   const double t2 = now_ms();
+  c_[5] = cpu_ms();
+  if (cpu_timing)
+    fprintf(stderr, "[plfem] process CPU ms of a forest of %d: analysis %.1f, merge + device plans %.1f, assembly + factorisation issue %.1f, "
+                    "eigensolver (launches + convergence checks) %.1f, reductions + copies %.1f; total %.1f = %.2f per design\n",
+            nb, c_[1] - c_[0], c_[2] - c_[1], c_[3] - c_[2], c_[4] - c_[3], c_[5] - c_[4], c_[5] - c_[0], (c_[5] - c_[0]) / nb);
 
   float ms_asm = 0, ms_fac = 0, ms_lan = 0, ms_met = 0;
   cudaEventElapsedTime(&ms_asm, ctx->ev[0], ctx->ev[1]);

@@ -897,6 +897,7 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
     bool done = false, newly = false;
     int q_want = 0;
     double worst = 1e300;            // largest relative residual bound among the wanted Ritz pairs at the last check
+    double prev_worst = 1e300;       // ... at the check before, `steps_between` block steps earlier
     int best_nconv = -1, stalled = 0; // restarts since the number of converged pairs last grew
   };
   std::vector<Host> hs(B);
@@ -912,6 +913,12 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
   const double eps23 = std::pow(2.220446049250313e-16, 2.0 / 3.0);
   static const int check_every = [] { const char* e = std::getenv("PLFEM_CHECK_EVERY"); return e ? std::max(1, atoi(e)) : 2; }();
   int since_check = 0;
+  // A convergence check costs every unfinished design a dense eigensolve on the host (~0.5 ms for a 60 x 60 projection) and
+  // the device an idle gap; checking every second block step from 2k basis vectors on was a third of the host time per
+  // design.  The worst residual bound of a design falls geometrically between checks, so the next check is scheduled at 60 %
+  // of the steps the slowest design is predicted to need (never less than `check_every`, never more than 8).
+  int next_gap = check_every, steps_between = 0, n_checks = 0;
+  double ms_checks = 0.0;
   auto check_from = [&](int k) { return std::min(ncvp, ((2 * k + P - 1) / P) * P); };
   for (;;) {
     // ---- one block step: image of the last P basis vectors
@@ -938,10 +945,13 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
     const bool full = (c >= ncvp);
     bool due = false;
     for (int b = 0; b < B; ++b) if (!hs[b].done && c >= check_from(des[b].k)) due = true;
-    if (!full && !(due && since_check >= check_every)) continue;
+    if (!full && !(due && since_check >= next_gap)) continue;
+    steps_between = since_check;
     since_check = 0;
 
     // ---- convergence check on the c x c projected matrix of every unfinished design
+    const auto t_check0 = std::chrono::steady_clock::now();
+    ++n_checks;
     PLFEM_CUDA(cudaGetLastError());
     Hs.download(Hh.data(), Hh.size());
     Lall.download(Lh.data(), Lh.size());
@@ -989,6 +999,7 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
         if (bnd <= de.tol * ref) nconv++;
         worst = std::max(worst, bnd / ref);
       }
+      h.prev_worst = h.worst;
       h.worst = worst;
       de.nconv = nconv;
       if (nconv >= k || last_chance) {
@@ -1034,7 +1045,25 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
     }
     ndone = 0;
     for (const Host& h : hs) ndone += h.done;
-    if (ndone == B) return;
+    ms_checks += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_check0).count();
+    if (ndone == B) {
+      static const bool timing = std::getenv("PLFEM_TIMING") != nullptr;
+      if (timing) fprintf(stderr, "[plfem] block Lanczos: %d block steps, %d convergence checks, %.2f ms of host wall time in them\n", res.n_block_op, n_checks, ms_checks);
+      return;
+    }
+    next_gap = check_every;
+    if (!full) {                     // (a restart changes the basis: start predicting afresh after it)
+      int need = 0;
+      bool known = true;
+      for (int b = 0; b < B; ++b) {
+        const Host& h = hs[b];
+        if (h.done) continue;
+        if (!(h.worst < h.prev_worst) || h.prev_worst > 1e299 || steps_between <= 0) { known = false; break; }
+        const double rate = std::log(h.worst / h.prev_worst) / steps_between;      // < 0
+        need = std::max(need, (int)std::ceil(std::log(des[b].tol / std::max(h.worst, 1e-300)) / rate));
+      }
+      if (known) next_gap = std::max(check_every, std::min(8, (int)(0.6 * need)));
+    }
     if (!relaxed && gexec_lo) {
       double w = 0.0;
       for (const Host& h : hs) if (!h.done) w = std::max(w, h.worst);

@@ -16,6 +16,7 @@ keyed like `mesh.py:132-165`).
 from __future__ import annotations
 
 import hashlib
+import threading
 from collections import OrderedDict
 from typing import Optional
 
@@ -130,6 +131,7 @@ class MeshGenerator:
     _cache: "OrderedDict[str, tuple]" = OrderedDict()
     _cache_hits = 0
     _cache_misses = 0
+    _cache_lock = threading.Lock()      # the sweep driver meshes on several threads (the reference's cache is not thread-safe)
     MAX_REFINEMENT_ITERATIONS = 5
 
     @classmethod
@@ -146,16 +148,18 @@ class MeshGenerator:
                  config: Optional[SimulationConfig] = None):
         config = config or SimulationConfig()
         key = cls._key(geometry, refinement) + f"{config.mesh_min_points}:{config.mesh_target_points}"
-        if config.enable_mesh_cache and key in cls._cache:
-            cls._cache_hits += 1
-            cls._cache.move_to_end(key)
-            return cls._cache[key]
-        cls._cache_misses += 1
+        with cls._cache_lock:
+            if config.enable_mesh_cache and key in cls._cache:
+                cls._cache_hits += 1
+                cls._cache.move_to_end(key)
+                return cls._cache[key]
+            cls._cache_misses += 1
         out = cls._generate_mesh(geometry, refinement, config)
         if config.enable_mesh_cache:
-            while len(cls._cache) >= max(config.cache_max_size, 1):
-                cls._cache.popitem(last=False)
-            cls._cache[key] = out
+            with cls._cache_lock:
+                while len(cls._cache) >= max(config.cache_max_size, 1):
+                    cls._cache.popitem(last=False)
+                cls._cache[key] = out
         return out
 
     @classmethod

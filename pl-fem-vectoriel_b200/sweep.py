@@ -162,40 +162,56 @@ def solve_design_gpu(d: Dict, device: int = 0, refinement: float = 1.0):
     return g, mesh, modes, st, time.perf_counter() - t0
 
 
-def solve_forest_gpu(ds: Sequence[Dict], pool, refinement: float = 1.0) -> List:
+def prepare_design(d: Dict, refinement: float = 1.0):
+    """Host side of one design: geometry + mesh (Qhull).  Returns ``(geometry, mesh, n_modes)`` or the Exception."""
+    try:
+        g = design_geometry(d)
+        mesh, _ = MeshGenerator.generate(g, refinement)
+        return g, mesh, d.get("n_modes", 10)
+    except Exception as e:                                  # noqa: BLE001 — a bad design must not stop the forest
+        return e
+
+
+def solve_forest_gpu(ds: Sequence[Dict], pool, refinement: float = 1.0, prepared: Optional[Sequence] = None) -> List:
     """Default worker of the forest mode: meshes on the host, ONE forest solve on the GPU for all of ``ds``.
+    ``prepared[j]`` (optional) is the result of `prepare_design(ds[j])` or a Future of it (meshing pipelined on other threads).
     Returns one ``(geometry, mesh, modes, stats, seconds)`` or ``Exception`` per design."""
     import time
     from .solver_fem import sigma_estimate
-    prepared, out = [], [None] * len(ds)
+    ready, out = [], [None] * len(ds)
     for j, d in enumerate(ds):
-        try:
-            g = design_geometry(d)
-            mesh, _ = MeshGenerator.generate(g, refinement)
-            prepared.append((j, g, mesh, d.get("n_modes", 10)))
-        except Exception as e:                              # noqa: BLE001 — a bad design must not stop the forest
-            out[j] = e
-    if prepared:
+        p = prepared[j] if prepared is not None else prepare_design(d, refinement)
+        p = p.result() if hasattr(p, "result") else p
+        if isinstance(p, Exception):
+            out[j] = p
+        else:
+            ready.append((j,) + tuple(p))
+    if ready:
         t0 = time.perf_counter()
-        res = pool.solve_forest([(g, mesh, n) for _, g, mesh, n in prepared])
-        secs = (time.perf_counter() - t0) / len(prepared)
-        for (j, g, mesh, _), modes, st in zip(prepared, res, pool.last_stats):
+        res = pool.solve_forest([(g, mesh, n) for _, g, mesh, n in ready])
+        secs = (time.perf_counter() - t0) / len(ready)
+        stats = list(getattr(pool._local, "last_stats", None) or pool.last_stats)
+        for (j, g, mesh, _), modes, st in zip(ready, res, stats):
             if isinstance(modes, Exception):
                 out[j] = modes
             else:
                 n_dofs = 2 * len(modes[0]["Ex_dofs"]) if modes and modes[0]["Ex_dofs"] is not None else np.nan
-                out[j] = (g, mesh, modes, dict(st, sigma=sigma_estimate(g), n_dofs=n_dofs), secs)
+                out[j] = (g, mesh, modes, dict(st or {}, sigma=sigma_estimate(g), n_dofs=n_dofs), secs)
     return out
 
 
 def run_sweep(designs: Sequence[Dict], rank: int = 0, world: int = 1, device: int = 0,
               solve_fn: Optional[Callable] = None, gather: bool = True, forest: int = 0,
-              forest_fn: Optional[Callable] = None) -> np.ndarray:
+              forest_fn: Optional[Callable] = None, workers: int = 2, mesh_threads: int = 4) -> np.ndarray:
     """Solve this rank's shard and return ALL records, (len(designs), 86), on every rank.
 
     ``forest = B > 0`` is the production mode on GPUs: the shard is cut into forests of ``B`` designs, each solved by
-    one `plfem_solve_modes_batch` call (``forest_fn(list of designs) -> list of results or Exceptions``; default
-    `solve_forest_gpu` on a `ForestPool`).  ``forest = 0`` solves design by design with ``solve_fn``.
+    one `plfem_solve_modes_batch` call.  With the default worker the forests are pipelined: ``mesh_threads`` host threads
+    build geometries and Delaunay meshes ahead, ``workers`` forest threads (each with its own CUDA context) take the
+    forests in order, so meshing, the host analysis of one forest and the device work of another overlap; designs of a
+    forest on an identical mesh (the bands of a wavelength sweep) share one analysis.  A custom
+    ``forest_fn(list of designs) -> list of results or Exceptions`` is called forest by forest.
+    ``forest = 0`` solves design by design with ``solve_fn``.
 
     A failed design yields a record with ``success = 0`` and never poisons the others
     (the reference wraps each sample in try/except, `main.py:346,384-386`).
@@ -203,28 +219,39 @@ def run_sweep(designs: Sequence[Dict], rank: int = 0, world: int = 1, device: in
     """
     mine = shard(len(designs), rank, world)
     local = np.full((len(mine), N_RECORD), np.nan)
-    if forest > 0:
-        pool = None
-        if forest_fn is None:
-            from .batch import ForestPool
-            pool = ForestPool(device=device, batch=forest, workers=1)
-            forest_fn = lambda ds: solve_forest_gpu(ds, pool)                     # noqa: E731
-        try:
-            for j0 in range(0, len(mine), forest):
-                idx = mine[j0:j0 + forest]
+
+    def put(j0, idx, results):
+        for j, i, r in zip(range(j0, j0 + len(idx)), idx, results):
+            if isinstance(r, Exception) or r is None:
+                local[j] = design_record(i, designs[i], None, None, [], None, 0.0, False)
+            else:
+                g, mesh, modes, st, secs = r
+                local[j] = design_record(i, designs[i], g, mesh, modes, st, secs, True)
+
+    if forest > 0 and forest_fn is None:
+        from concurrent.futures import ThreadPoolExecutor
+        from .batch import ForestPool
+        chunks = [(j0, mine[j0:j0 + forest]) for j0 in range(0, len(mine), forest)]
+        with ForestPool(device=device, batch=forest, workers=max(1, workers)) as pool, \
+                ThreadPoolExecutor(max_workers=max(1, mesh_threads), thread_name_prefix="plfem-mesh") as mesher:
+            prepared = {i: mesher.submit(prepare_design, designs[i]) for _, idx in chunks for i in idx}   # in sweep order
+
+            def one(chunk):
+                j0, idx = chunk
                 try:
-                    results = forest_fn([designs[i] for i in idx])
+                    return solve_forest_gpu([designs[i] for i in idx], pool, prepared=[prepared[i] for i in idx])
                 except Exception as e:                      # noqa: BLE001 — the whole forest failed
-                    results = [e] * len(idx)
-                for j, i, r in zip(range(j0, j0 + len(idx)), idx, results):
-                    if isinstance(r, Exception) or r is None:
-                        local[j] = design_record(i, designs[i], None, None, [], None, 0.0, False)
-                    else:
-                        g, mesh, modes, st, secs = r
-                        local[j] = design_record(i, designs[i], g, mesh, modes, st, secs, True)
-        finally:
-            if pool is not None:
-                pool.close()
+                    return [e] * len(idx)
+            for (j0, idx), results in zip(chunks, pool._pool.map(one, chunks)):
+                put(j0, idx, results)
+    elif forest > 0:
+        for j0 in range(0, len(mine), forest):
+            idx = mine[j0:j0 + forest]
+            try:
+                results = forest_fn([designs[i] for i in idx])
+            except Exception as e:                          # noqa: BLE001 — the whole forest failed
+                results = [e] * len(idx)
+            put(j0, idx, results)
     else:
         solve_fn = solve_fn or (lambda d: solve_design_gpu(d, device))
         for j, i in enumerate(mine):

@@ -492,3 +492,23 @@ def test_config5_two_million_unknowns():
     cvals, *_ = coarse.solve_modes(mat, sigma, 22, want_vectors=False)
     assert np.abs(np.sort(vals) / np.sort(cvals) - 1).max() < 2e-2          # h-convergence: the same cluster of modes
     pb.close(); coarse.close()
+
+
+@pytest.mark.gpu
+def test_bands_on_one_mesh_share_one_analysis(cfg1):
+    """The four bands of config 3 sit on ONE mesh (the recipe uses the geometry only, `mesh.py:232-289`): inside a forest they
+    share the ordering and the front plan of the first — same results as analysing each on its own, a fraction of the host time."""
+    import plfem_b200 as P
+    from plfem_b200.batch import ForestPool
+    g0, mesh = cfg1
+    jobs = [(P.MCFGeometry(7, 8.0, 1.5, P.IPDipCauchy.n(w), 1.0, w / 1000.0), mesh, 10) for w in (1490, 1550, 1600, 1650)]
+    with ForestPool(batch=4, workers=1, share_analysis=True) as pool:
+        shared = pool.solve_forest(jobs, return_raw=True)
+        st_shared = [r[1]["stats"] for r in shared]
+    with ForestPool(batch=4, workers=1, share_analysis=False) as pool:
+        own = pool.solve_forest(jobs, return_raw=True)
+        st_own = [r[1]["stats"] for r in own]
+    for (ma, ra), (mb, rb) in zip(shared, own):
+        assert np.array_equal(ra["beta_sq"], rb["beta_sq"]) and len(ma) == len(mb)
+    assert all(s["ms_symbolic"] < 0.5 * o["ms_symbolic"] for s, o in zip(st_shared[1:], st_own[1:]))
+    assert st_shared[0]["n_fronts"] == st_shared[3]["n_fronts"] == st_own[3]["n_fronts"]
