@@ -18,6 +18,12 @@ out = _cabi.solve_modes_batch(ctx, pbs, [mat] * nb, [sigma] * nb, [k] * nb, want
 st = out[0][4].as_dict()
 print("forest", nb, "block_ops", st["batch_block_ops"], "refine", st["refine_steps"], "launches", st["kernel_launches"], "resid", st["max_residual"], flush=True)
 print("PROFILE_BEGIN", flush=True)
+rng = os.environ.get("NCU_RANGE")          # under `ncu --profile-from-start off`: capture only the isolated sweeps below
+if rng:
+    import torch
+    torch.cuda.cudart().cudaProfilerStart()
 prof, nbp = ctx.profile_last(repeat=int(os.environ.get("REPEAT", 1)))
 for n_, (ms, nbytes) in prof.items():
     print(f"  {n_:22s} {ms:9.4f} ms {nbytes / 1e6:9.1f} MB {nbytes / ms / 1e6:8.1f} GB/s ({nbytes / ms / 1e6 / 6553.6:.3f})", flush=True)
+if rng:
+    torch.cuda.cudart().cudaProfilerStop()
