@@ -468,7 +468,7 @@ def run_ours(args):
                      "cpu_ms_per_solve_value": 1e3 * cpu_value / (B * NF), "cpu_ms_per_solve_e2e": 1e3 * cpu_e2e / (B * NF),
                      "note": "process CPU time of rank 0 inside the two timed regions / designs solved"},
             "solver": {kk: stats[kk] for kk in ("nconv", "n_op", "n_block_op", "n_restart", "n_fronts", "n_levels", "max_front_nodes", "factor_entries",
-                                                "front_pool_doubles", "factor_flops", "max_residual", "batch_size", "batch_block_ops")},
+                                                "front_pool_doubles", "factor_flops", "max_residual", "batch_size", "batch_block_ops", "probe_rho")},
             "kernels": kernels}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -42,7 +42,9 @@ class ForestPool:
         # over the forests in flight with some oversubscription — hundreds of runnable threads per core cost more than
         # the idle cores they could fill
         cores = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
-        self.host_threads = host_threads or max(1, min(self.batch, -(-3 * cores // (2 * self.workers))))
+        # (a forest of ONE design — the 2M-unknown stress mesh — runs its own dissection on all of them: halves on separate threads)
+        share = -(-3 * cores // (2 * self.workers))
+        self.host_threads = host_threads or max(1, min(self.batch if self.batch > 1 else cores // self.workers, share))
         lib.plfem_set_host_threads(self.host_threads)
         self._local = threading.local()
         self._contexts: list = []                     # every context a worker thread created (destroyed in close())

@@ -645,10 +645,8 @@ static void solve_forest(plfem_ctx* ctx, int nb, plfem_problem* const* pbs, cons
     upload_material(pb, &mats[b]);
     W.asm_args[b] = {pb->d_p.p, pb->d_edofs.p, pb->d_n2e_ptr.p, pb->d_n2e.p, pb->d_elem.p, pb->d_cores.p, pb->dof.V, pb->dof.T, mats[b]};
     W.asm_args[b].mat.cores_xy = nullptr; W.asm_args[b].mat.cores_r = nullptr; W.asm_args[b].mat.eps_at_quad = nullptr;
-    const int64_t z0 = W.nnz_off[b];
-    launch_assemble_slice(ctx, W.nnz_off[b + 1] - z0, W.dpat.rowidx.p + z0, W.dpat.col.p + z0, W.dpat.old_of_new.p, pb->d_n2e_ptr.p,
-                          pb->d_n2e.p, pb->d_edofs.p, pb->d_elem.p, mats[b].k0 * mats[b].k0, second_coeff(mats[b]), assembly_mode(mats[b]),
-                          W.d_vals.p + z0, nnz, nullptr);
+    launch_assemble_slice(ctx, bd.noff[b], bd.noff[b + 1] - bd.noff[b], W.dpat, pb->d_n2e_ptr.p, pb->d_n2e.p, pb->d_edofs.p, pb->d_elem.p,
+                          mats[b].k0 * mats[b].k0, second_coeff(mats[b]), assembly_mode(mats[b]), W.d_vals.p, nnz, nullptr);
     std::fill(sig.begin() + bd.noff[b], sig.begin() + bd.noff[b + 1], opts[b].sigma);
     std::copy(masks[b].begin(), masks[b].end(), mask_all.begin() + bd.noff[b]);
   }
@@ -860,10 +858,9 @@ static void profile_work(plfem_ctx* ctx, SolveWork& W, int repeat, double* out_m
   out_ms[0] = timed([&] {
     for (int d = 0; d < nb; ++d) {
       const SolveWork::AsmArgs& a = W.asm_args[d];
-      const int64_t z0 = W.nnz_off[d];
       launch_element_setup(ctx, a.d_p, a.d_edofs, a.V, a.T, a.mat, a.d_cores, nullptr, a.d_elem);
-      launch_assemble_slice(ctx, W.nnz_off[d + 1] - z0, W.dpat.rowidx.p + z0, W.dpat.col.p + z0, W.dpat.old_of_new.p, a.d_n2e_ptr, a.d_n2e,
-                            a.d_edofs, a.d_elem, a.mat.k0 * a.mat.k0, second_coeff(a.mat), assembly_mode(a.mat), W.d_vals.p + z0, nnz, nullptr);
+      launch_assemble_slice(ctx, W.bd.noff[d], W.bd.noff[d + 1] - W.bd.noff[d], W.dpat, a.d_n2e_ptr, a.d_n2e, a.d_edofs, a.d_elem,
+                            a.mat.k0 * a.mat.k0, second_coeff(a.mat), assembly_mode(a.mat), W.d_vals.p, nnz, nullptr);
     }
   });
   // mesh in (coordinates + 6 DOF ids per element), every assembled value out once

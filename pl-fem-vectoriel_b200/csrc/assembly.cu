@@ -200,77 +200,76 @@ __global__ void gather_offsets_kernel(const int32_t* __restrict__ rowptr, const 
   if (i < nb1) out[i] = rowptr[node_off[i]];
 }
 
-// ---- K1b/K2 fused: one thread per structural non-zero ---------------------------------------------------
+// ---- K1b/K2 fused: quadrature per (row node, element) pair, combined per structural non-zero inside the CTA ---------------
 // MODE 0: the solve's value arrays of the H-field system; 1: the ten scalar matrices for export; 2: scalar Helmholtz pencil
-// (solver_fem.py:245-276) in the same arrays — Hx block (K - k0^2 M_eps, M), Hy block (shift M, M), no coupling
-template <int MODE>
-__global__ void __launch_bounds__(128)
-assemble_kernel(int64_t nnz, const int32_t* __restrict__ rowidx, const int32_t* __restrict__ col,
-                const int32_t* __restrict__ old_of_new, const int32_t* __restrict__ n2e_ptr,
-                const int32_t* __restrict__ n2e, const int32_t* __restrict__ edofs, const double* __restrict__ elem,
-                double k0sq, double alpha, double* __restrict__ vals, int64_t vstride, uint32_t* __restrict__ flags) {
-  __shared__ double s_phi[36], s_dx[36], s_dy[36], s_w[6];
-  for (int i = threadIdx.x; i < 36; i += blockDim.x) { s_phi[i] = c_tab.phi[i]; s_dx[i] = c_tab.dx[i]; s_dy[i] = c_tab.dy[i]; }
-  if (threadIdx.x < 6) s_w[threadIdx.x] = c_tab.w[threadIdx.x];
-  __syncthreads();
-  const int64_t z = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (z >= nnz) return;
-  const int32_t orow = old_of_new[rowidx[z]];
-  const int32_t ocol = old_of_new[col[z]];
+// (solver_fem.py:245-276) in the same arrays — Hx block (K - k0^2 M_eps, M), Hy block (shift M, M), no coupling.
+//
+// Round 1 gave every structural non-zero (r, c) a thread that walked the elements around r looking for c: 0.044 of the HBM
+// peak, because the thread of a diagonal entry integrates over ALL elements around its node (6 for a vertex) while its
+// warp-mates integrate over one or two, and every thread repeats the search.  Now a CTA takes ASM_RPB consecutive pattern rows:
+//   phase 1  one thread per (row node r, element e around r): the test-function side (gradients and value of r's shape function
+//            at the 6 quadrature points) is computed once, then the 10 forms against each of the element's 6 trial functions —
+//            36 T uniform work items per mesh, no search, no divergence; the 6 x 10 element-level values go to shared memory;
+//   phase 2  one thread per structural non-zero of those rows: adds the staged values of its column over the row's elements in
+//            ascending element id (the same fixed order, operation for operation, as the walk: bit-identical results), applies
+//            the block formulas and writes each assembled value once, coalesced.
+// DRAM traffic stays the mesh in and every value out once; the element-level values never leave the SM.  A CTA whose rows have
+// more than ASM_CAP pairs (a hub node of a ring of 100+ elements) takes the old per-entry walk.
+constexpr int ASM_T = 128;       // threads per CTA
+constexpr int ASM_RPB = 30;      // pattern rows per CTA: 3 elements around a P2 node on average -> ~90 pairs
+constexpr int ASM_CAP = 128;     // (row, element) pairs staged per CTA (60 doubles each: 61 KB)
 
-  double g[10];
-#pragma unroll
-  for (int k = 0; k < 10; ++k) g[k] = 0.0;
-  uint32_t fl = 0;
+struct AsmArgs {
+  int32_t row0, nrows;                               // this design's rows of the (possibly concatenated) pattern
+  const int32_t *rowptr, *col, *old_of_new;          // pattern (global row / non-zero ids)
+  const int32_t *n2e_ptr, *n2e, *edofs;              // this design's mesh tables
+  const double* elem;
+  double k0sq, alpha;
+  double* vals; int64_t vstride; uint32_t* flags;
+};
 
-  for (int32_t q = n2e_ptr[orow]; q < n2e_ptr[orow + 1]; ++q) {
-    const int32_t e = n2e[q];
-    const int32_t* ed = edofs + 6 * (int64_t)e;
-    int li = -1, lj = -1;
+struct AsmSmem {
+  double l[60 * ASM_CAP];        // [(j * 10 + k) * ASM_CAP + pair]
+  int32_t key[6 * ASM_CAP];      // DOF id of trial function j of the pair's element
+  double phi[36], dx[36], dy[36], w[6];
+  int32_t o[ASM_RPB], q0[ASM_RPB], pp[ASM_RPB + 1], rp[ASM_RPB + 1];
+};
+
+// the 10 element-level forms of (test i, trial j) of one element, oracle operation order
+__device__ __forceinline__ void element_forms(const AsmSmem& sm, const double* __restrict__ r, int li, int lj, double (&l)[10]) {
+  const double i00 = r[0], i10 = r[1], i01 = r[2], i11 = r[3], adet = r[4];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const int32_t d = ed[k];
-      if (d == orow) li = k;
-      if (d == ocol) lj = k;
-    }
-    if (lj < 0) continue;
-    const double* r = elem + (int64_t)e * ELEM_STRIDE;
-    const double i00 = r[0], i10 = r[1], i01 = r[2], i11 = r[3], adet = r[4];
-    double l[10];
+  for (int k = 0; k < 10; ++k) l[k] = 0.0;
 #pragma unroll
-    for (int k = 0; k < 10; ++k) l[k] = 0.0;
-#pragma unroll
-    for (int qp = 0; qp < 6; ++qp) {
-      const double w = r[5 + qp];
-      const double dxq = mul(adet, s_w[qp]);
-      // test function v = row node (i), trial function u = column node (j)
-      const double gxi = add(mul(i00, s_dx[li * 6 + qp]), mul(i10, s_dy[li * 6 + qp]));
-      const double gyi = add(mul(i01, s_dx[li * 6 + qp]), mul(i11, s_dy[li * 6 + qp]));
-      const double gxj = add(mul(i00, s_dx[lj * 6 + qp]), mul(i10, s_dy[lj * 6 + qp]));
-      const double gyj = add(mul(i01, s_dx[lj * 6 + qp]), mul(i11, s_dy[lj * 6 + qp]));
-      const double pi = s_phi[li * 6 + qp], pj = s_phi[lj * 6 + qp];
-      l[X_KXX] = add(l[X_KXX], mul(mul(mul(w, gyj), gyi), dxq));
-      l[X_KYY] = add(l[X_KYY], mul(mul(mul(w, gxj), gxi), dxq));
-      l[X_KXY] = add(l[X_KXY], mul(mul(mul(-w, gyj), gxi), dxq));
-      l[X_KYX] = add(l[X_KYX], mul(mul(mul(-w, gxj), gyi), dxq));
-      l[X_DXX] = add(l[X_DXX], mul(mul(gxj, gxi), dxq));
-      l[X_DYY] = add(l[X_DYY], mul(mul(gyj, gyi), dxq));
-      l[X_DXY] = add(l[X_DXY], mul(mul(gxj, gyi), dxq));
-      l[X_DYX] = add(l[X_DYX], mul(mul(gxi, gyj), dxq));   // Dxy(c, r): trial = row node, test = column node
-      l[X_M] = add(l[X_M], mul(mul(pj, pi), dxq));
-      l[X_MINV] = add(l[X_MINV], mul(mul(mul(w, pj), pi), dxq));
-    }
-#pragma unroll
-    for (int k = 0; k < 10; ++k) {
-      g[k] = add(g[k], l[k]);
-      if (MODE == 1 && l[k] != 0.0) fl |= (1u << k);   // NaN != 0 is true: a NaN entry is stored, as in SciPy
-    }
+  for (int qp = 0; qp < 6; ++qp) {
+    const double w = r[5 + qp];
+    const double dxq = mul(adet, sm.w[qp]);
+    // test function v = row node (i), trial function u = column node (j)
+    const double gxi = add(mul(i00, sm.dx[li * 6 + qp]), mul(i10, sm.dy[li * 6 + qp]));
+    const double gyi = add(mul(i01, sm.dx[li * 6 + qp]), mul(i11, sm.dy[li * 6 + qp]));
+    const double gxj = add(mul(i00, sm.dx[lj * 6 + qp]), mul(i10, sm.dy[lj * 6 + qp]));
+    const double gyj = add(mul(i01, sm.dx[lj * 6 + qp]), mul(i11, sm.dy[lj * 6 + qp]));
+    const double pi = sm.phi[li * 6 + qp], pj = sm.phi[lj * 6 + qp];
+    l[X_KXX] = add(l[X_KXX], mul(mul(mul(w, gyj), gyi), dxq));
+    l[X_KYY] = add(l[X_KYY], mul(mul(mul(w, gxj), gxi), dxq));
+    l[X_KXY] = add(l[X_KXY], mul(mul(mul(-w, gyj), gxi), dxq));
+    l[X_KYX] = add(l[X_KYX], mul(mul(mul(-w, gxj), gyi), dxq));
+    l[X_DXX] = add(l[X_DXX], mul(mul(gxj, gxi), dxq));
+    l[X_DYY] = add(l[X_DYY], mul(mul(gyj, gyi), dxq));
+    l[X_DXY] = add(l[X_DXY], mul(mul(gxj, gyi), dxq));
+    l[X_DYX] = add(l[X_DYX], mul(mul(gxi, gyj), dxq));   // Dxy(c, r): trial = row node, test = column node
+    l[X_M] = add(l[X_M], mul(mul(pj, pi), dxq));
+    l[X_MINV] = add(l[X_MINV], mul(mul(mul(w, pj), pi), dxq));
   }
+}
 
+template <int MODE>
+__device__ __forceinline__ void store_entry(const AsmArgs& a, int64_t z, const double (&g)[10], uint32_t fl) {
+  double* vals = a.vals; const int64_t vstride = a.vstride; const double k0sq = a.k0sq, alpha = a.alpha;
   if (MODE == 1) {
 #pragma unroll
     for (int k = 0; k < 10; ++k) vals[(int64_t)k * vstride + z] = g[k];
-    flags[z] = fl;
+    a.flags[z] = fl;
   } else if (MODE == 2) {
     // the element records hold eps (not 1/eps) in this mode: g[X_MINV] is M_eps; `alpha` carries the decoupled shift
     vals[(int64_t)S_AXX * vstride + z] = add(add(g[X_DXX], g[X_DYY]), -mul(k0sq, g[X_MINV]));
@@ -291,6 +290,141 @@ assemble_kernel(int64_t nnz, const int32_t* __restrict__ rowidx, const int32_t* 
     vals[(int64_t)S_DXX * vstride + z] = g[X_DXX];
     vals[(int64_t)S_DXY * vstride + z] = g[X_DXY];
     vals[(int64_t)S_DYY * vstride + z] = g[X_DYY];
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(ASM_T) assemble_rows_kernel(AsmArgs a) {
+  extern __shared__ __align__(16) unsigned char asm_smem_raw[];
+  AsmSmem& sm = *reinterpret_cast<AsmSmem*>(asm_smem_raw);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 36; i += ASM_T) { sm.phi[i] = c_tab.phi[i]; sm.dx[i] = c_tab.dx[i]; sm.dy[i] = c_tab.dy[i]; }
+  if (tid < 6) sm.w[tid] = c_tab.w[tid];
+  const int32_t R0 = a.row0 + blockIdx.x * ASM_RPB;
+  const int nr = min(ASM_RPB, a.row0 + a.nrows - R0);
+  if (tid < nr) {
+    const int32_t o = a.old_of_new[R0 + tid];
+    sm.o[tid] = o; sm.q0[tid] = a.n2e_ptr[o];
+    sm.pp[tid + 1] = a.n2e_ptr[o + 1] - a.n2e_ptr[o];
+  }
+  if (tid <= nr) sm.rp[tid] = a.rowptr[R0 + tid];
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0; sm.pp[0] = 0;
+    for (int i = 0; i < nr; ++i) { acc += sm.pp[i + 1]; sm.pp[i + 1] = acc; }
+  }
+  __syncthreads();
+  const int npairs = sm.pp[nr];
+  const int32_t zb = sm.rp[0], ze = sm.rp[nr];
+  if (npairs > ASM_CAP) {
+    // a hub node among these rows: per-entry walk over the elements around the row node (the round-1 scheme)
+    for (int32_t z = zb + tid; z < ze; z += ASM_T) {
+      int lo = 0, hi = nr;
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sm.rp[mid] <= z) lo = mid; else hi = mid; }
+      const int32_t orow = sm.o[lo], ocol = a.old_of_new[a.col[z]];
+      double g[10];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) g[k] = 0.0;
+      uint32_t fl = 0;
+      for (int32_t q = a.n2e_ptr[orow]; q < a.n2e_ptr[orow + 1]; ++q) {
+        const int32_t e = a.n2e[q];
+        const int32_t* ed = a.edofs + 6 * (int64_t)e;
+        int li = -1, lj = -1;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const int32_t d = ed[k];
+          if (d == orow) li = k;
+          if (d == ocol) lj = k;
+        }
+        if (lj < 0) continue;
+        double l[10];
+        element_forms(sm, a.elem + (int64_t)e * ELEM_STRIDE, li, lj, l);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+          g[k] = add(g[k], l[k]);
+          if (MODE == 1 && l[k] != 0.0) fl |= (1u << k);   // NaN != 0 is true: a NaN entry is stored, as in SciPy
+        }
+      }
+      store_entry<MODE>(a, z, g, fl);
+    }
+    return;
+  }
+  // phase 1: one (row node, element) pair per thread
+  for (int p = tid; p < npairs; p += ASM_T) {
+    int lo = 0, hi = nr;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sm.pp[mid] <= p) lo = mid; else hi = mid; }
+    const int32_t orow = sm.o[lo];
+    const int32_t e = a.n2e[sm.q0[lo] + (p - sm.pp[lo])];
+    const int32_t* ed = a.edofs + 6 * (int64_t)e;
+    int li = 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int32_t d = ed[k];
+      sm.key[k * ASM_CAP + p] = d;
+      if (d == orow) li = k;
+    }
+    const double* r = a.elem + (int64_t)e * ELEM_STRIDE;
+    const double i00 = r[0], i10 = r[1], i01 = r[2], i11 = r[3], adet = r[4];
+    // test-function side and weights at the 6 quadrature points: once per pair (same operations as element_forms)
+    double gxi[6], gyi[6], pi[6], wq[6], dxq[6];
+#pragma unroll
+    for (int qp = 0; qp < 6; ++qp) {
+      wq[qp] = r[5 + qp];
+      dxq[qp] = mul(adet, sm.w[qp]);
+      gxi[qp] = add(mul(i00, sm.dx[li * 6 + qp]), mul(i10, sm.dy[li * 6 + qp]));
+      gyi[qp] = add(mul(i01, sm.dx[li * 6 + qp]), mul(i11, sm.dy[li * 6 + qp]));
+      pi[qp] = sm.phi[li * 6 + qp];
+    }
+#pragma unroll 1
+    for (int lj = 0; lj < 6; ++lj) {
+      double l[10];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) l[k] = 0.0;
+#pragma unroll
+      for (int qp = 0; qp < 6; ++qp) {
+        const double w = wq[qp];
+        const double gxj = add(mul(i00, sm.dx[lj * 6 + qp]), mul(i10, sm.dy[lj * 6 + qp]));
+        const double gyj = add(mul(i01, sm.dx[lj * 6 + qp]), mul(i11, sm.dy[lj * 6 + qp]));
+        const double pj = sm.phi[lj * 6 + qp];
+        const double wgy = mul(w, gyj), wgx = mul(w, gxj);       // mul(-w, g) == -mul(w, g) exactly
+        l[X_KXX] = add(l[X_KXX], mul(mul(wgy, gyi[qp]), dxq[qp]));
+        l[X_KYY] = add(l[X_KYY], mul(mul(wgx, gxi[qp]), dxq[qp]));
+        l[X_KXY] = add(l[X_KXY], mul(mul(-wgy, gxi[qp]), dxq[qp]));
+        l[X_KYX] = add(l[X_KYX], mul(mul(-wgx, gyi[qp]), dxq[qp]));
+        l[X_DXX] = add(l[X_DXX], mul(mul(gxj, gxi[qp]), dxq[qp]));
+        l[X_DYY] = add(l[X_DYY], mul(mul(gyj, gyi[qp]), dxq[qp]));
+        l[X_DXY] = add(l[X_DXY], mul(mul(gxj, gyi[qp]), dxq[qp]));
+        l[X_DYX] = add(l[X_DYX], mul(mul(gxi[qp], gyj), dxq[qp]));
+        l[X_M] = add(l[X_M], mul(mul(pj, pi[qp]), dxq[qp]));
+        l[X_MINV] = add(l[X_MINV], mul(mul(mul(w, pj), pi[qp]), dxq[qp]));
+      }
+#pragma unroll
+      for (int k = 0; k < 10; ++k) sm.l[(lj * 10 + k) * ASM_CAP + p] = l[k];
+    }
+  }
+  __syncthreads();
+  // phase 2: one structural non-zero per thread
+  for (int32_t z = zb + tid; z < ze; z += ASM_T) {
+    int lo = 0, hi = nr;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sm.rp[mid] <= z) lo = mid; else hi = mid; }
+    const int32_t ocol = a.old_of_new[a.col[z]];
+    double g[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) g[k] = 0.0;
+    uint32_t fl = 0;
+    for (int p = sm.pp[lo]; p < sm.pp[lo + 1]; ++p) {      // the row's elements, ascending id
+      int lj = -1;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) lj = (sm.key[k * ASM_CAP + p] == ocol) ? k : lj;
+      if (lj < 0) continue;
+#pragma unroll
+      for (int k = 0; k < 10; ++k) {
+        const double l = sm.l[(lj * 10 + k) * ASM_CAP + p];
+        g[k] = add(g[k], l);
+        if (MODE == 1 && l != 0.0) fl |= (1u << k);
+      }
+    }
+    store_entry<MODE>(a, z, g, fl);
   }
 }
 
@@ -399,22 +533,24 @@ void build_device_pattern(plfem_ctx* ctx, int nb, const PatternSource* src, cons
   // the scratch buffers return to the context's arena here; it serves this stream only, so reuse is stream-ordered
 }
 
-// one design's slice of a (possibly concatenated) pattern: nnz entries starting at rowidx/col, values written to
-// vals[k * vstride + z]; row/column ids index old_of_new, whose entries are DOF ids of THIS design's mesh
-void launch_assemble_slice(plfem_ctx* ctx, int64_t nnz, const int32_t* d_rowidx, const int32_t* d_col, const int32_t* d_old_of_new,
-                           const int32_t* d_n2e_ptr, const int32_t* d_n2e, const int32_t* d_edofs, const double* d_elem,
-                           double k0sq, double alpha, int mode, double* d_vals, int64_t vstride, uint32_t* d_flags) {
-  const int bs = 128;
-  const unsigned grid = (unsigned)((nnz + bs - 1) / bs);
-  if (mode == 1)
-    assemble_kernel<1><<<grid, bs, 0, ctx->stream>>>(nnz, d_rowidx, d_col, d_old_of_new, d_n2e_ptr, d_n2e, d_edofs, d_elem, k0sq,
-                                                     alpha, d_vals, vstride, d_flags);
-  else if (mode == 2)
-    assemble_kernel<2><<<grid, bs, 0, ctx->stream>>>(nnz, d_rowidx, d_col, d_old_of_new, d_n2e_ptr, d_n2e, d_edofs, d_elem, k0sq,
-                                                     alpha, d_vals, vstride, d_flags);
-  else
-    assemble_kernel<0><<<grid, bs, 0, ctx->stream>>>(nnz, d_rowidx, d_col, d_old_of_new, d_n2e_ptr, d_n2e, d_edofs, d_elem, k0sq,
-                                                     alpha, d_vals, vstride, d_flags);
+// one design's rows [row0, row0 + nrows) of a (possibly concatenated) pattern; values written to vals[k * vstride + z] with z
+// the global non-zero id; old_of_new maps pattern rows / columns to DOF ids of THIS design's mesh
+void launch_assemble_slice(plfem_ctx* ctx, int32_t row0, int32_t nrows, const DevPattern& pat, const int32_t* d_n2e_ptr,
+                           const int32_t* d_n2e, const int32_t* d_edofs, const double* d_elem, double k0sq, double alpha, int mode,
+                           double* d_vals, int64_t vstride, uint32_t* d_flags) {
+  if (nrows <= 0) return;
+  static thread_local bool configured = false;
+  if (!configured) {
+    PLFEM_CUDA(cudaFuncSetAttribute(assemble_rows_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AsmSmem)));
+    PLFEM_CUDA(cudaFuncSetAttribute(assemble_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AsmSmem)));
+    PLFEM_CUDA(cudaFuncSetAttribute(assemble_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AsmSmem)));
+    configured = true;
+  }
+  const AsmArgs a{row0, nrows, pat.rowptr.p, pat.col.p, pat.old_of_new.p, d_n2e_ptr, d_n2e, d_edofs, d_elem, k0sq, alpha, d_vals, vstride, d_flags};
+  const unsigned grid = (unsigned)((nrows + ASM_RPB - 1) / ASM_RPB);
+  if (mode == 1) assemble_rows_kernel<1><<<grid, ASM_T, sizeof(AsmSmem), ctx->stream>>>(a);
+  else if (mode == 2) assemble_rows_kernel<2><<<grid, ASM_T, sizeof(AsmSmem), ctx->stream>>>(a);
+  else assemble_rows_kernel<0><<<grid, ASM_T, sizeof(AsmSmem), ctx->stream>>>(a);
   PLFEM_CUDA(cudaGetLastError());
   ctx->launches++;
 }
@@ -422,8 +558,7 @@ void launch_assemble_slice(plfem_ctx* ctx, int64_t nnz, const int32_t* d_rowidx,
 void launch_assemble(plfem_ctx* ctx, const DevPattern& pat, const int32_t* d_n2e_ptr, const int32_t* d_n2e,
                      const int32_t* d_edofs, const double* d_elem, double k0sq, double alpha, int mode,
                      double* d_vals, uint32_t* d_flags) {
-  launch_assemble_slice(ctx, pat.nnz, pat.rowidx.p, pat.col.p, pat.old_of_new.p, d_n2e_ptr, d_n2e, d_edofs, d_elem, k0sq, alpha,
-                        mode, d_vals, pat.nnz, d_flags);
+  launch_assemble_slice(ctx, 0, pat.n, pat, d_n2e_ptr, d_n2e, d_edofs, d_elem, k0sq, alpha, mode, d_vals, pat.nnz, d_flags);
 }
 
 void launch_spmv_csr(plfem_ctx* ctx, int64_t rows, const int32_t* rowptr, const int32_t* col, const double* val,

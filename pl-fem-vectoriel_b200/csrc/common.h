@@ -159,9 +159,9 @@ void build_device_pattern(plfem_ctx* ctx, int nb, const PatternSource* src, cons
 void launch_assemble(plfem_ctx* ctx, const DevPattern& pat, const int32_t* d_n2e_ptr, const int32_t* d_n2e,
                      const int32_t* d_edofs, const double* d_elem, double k0sq, double alpha, int mode /* 0 solve, 1 export, 2 scalar */,
                      double* d_vals, uint32_t* d_flags);
-void launch_assemble_slice(plfem_ctx* ctx, int64_t nnz, const int32_t* d_rowidx, const int32_t* d_col, const int32_t* d_old_of_new,
-                           const int32_t* d_n2e_ptr, const int32_t* d_n2e, const int32_t* d_edofs, const double* d_elem,
-                           double k0sq, double alpha, int mode, double* d_vals, int64_t vstride, uint32_t* d_flags);
+void launch_assemble_slice(plfem_ctx* ctx, int32_t row0, int32_t nrows, const DevPattern& pat, const int32_t* d_n2e_ptr,
+                           const int32_t* d_n2e, const int32_t* d_edofs, const double* d_elem, double k0sq, double alpha, int mode,
+                           double* d_vals, int64_t vstride, uint32_t* d_flags);
 void launch_spmv_csr(plfem_ctx* ctx, int64_t rows, const int32_t* rowptr, const int32_t* col, const double* val,
                      const double* x, double* y);
 
