@@ -213,10 +213,12 @@ __global__ void gather_offsets_kernel(const int32_t* __restrict__ rowptr, const 
 //   phase 2  one thread per structural non-zero of those rows: adds the staged values of its column over the row's elements in
 //            ascending element id (the same fixed order, operation for operation, as the walk: bit-identical results), applies
 //            the block formulas and writes each assembled value once, coalesced.
-// DRAM traffic stays the mesh in and every value out once; the element-level values never leave the SM.  A CTA whose rows have
-// more than ASM_CAP pairs (a hub node of a ring of 100+ elements) takes the old per-entry walk.
+// DRAM traffic stays the mesh in and every value out once; the element-level values never leave the SM.  The CTA's rows are
+// taken in batches of at most ASM_CAP pairs (vertex nodes cluster in the elimination order: 6 elements each against 2 for an
+// edge node, so a fixed row count per batch either overflows the staging area or leaves the threads idle); a single row with
+// more than ASM_CAP elements (a hub node of a ring of 100+ elements) takes the old per-entry walk.
 constexpr int ASM_T = 128;       // threads per CTA
-constexpr int ASM_RPB = 30;      // pattern rows per CTA: 3 elements around a P2 node on average -> ~90 pairs
+constexpr int ASM_RPB = 80;      // pattern rows per CTA: 3 elements around a P2 node on average -> two batches of <= ASM_CAP pairs
 constexpr int ASM_CAP = 128;     // (row, element) pairs staged per CTA (60 doubles each: 61 KB)
 
 struct AsmArgs {
@@ -293,6 +295,40 @@ __device__ __forceinline__ void store_entry(const AsmArgs& a, int64_t z, const d
   }
 }
 
+// where pair q keeps its value (trial function lj, form k): rotated by 3 lj so that the six columns of one element, read by six
+// threads of phase 2 in the same cycle, sit in six different banks; a warp of phase 1 still writes 32 consecutive doubles
+__device__ __forceinline__ int stage_at(int lj, int k, int q) { return (lj * 10 + k) * ASM_CAP + ((q + 3 * lj) & (ASM_CAP - 1)); }
+
+// per-entry walk over the elements around the row node (the round-1 scheme): only for a row with more than ASM_CAP elements
+template <int MODE>
+__device__ __forceinline__ void walk_entry(const AsmArgs& a, const AsmSmem& sm, int32_t orow, int32_t z) {
+  const int32_t ocol = a.old_of_new[a.col[z]];
+  double g[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) g[k] = 0.0;
+  uint32_t fl = 0;
+  for (int32_t q = a.n2e_ptr[orow]; q < a.n2e_ptr[orow + 1]; ++q) {
+    const int32_t e = a.n2e[q];
+    const int32_t* ed = a.edofs + 6 * (int64_t)e;
+    int li = -1, lj = -1;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int32_t d = ed[k];
+      if (d == orow) li = k;
+      if (d == ocol) lj = k;
+    }
+    if (lj < 0) continue;
+    double l[10];
+    element_forms(sm, a.elem + (int64_t)e * ELEM_STRIDE, li, lj, l);
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      g[k] = add(g[k], l[k]);
+      if (MODE == 1 && l[k] != 0.0) fl |= (1u << k);   // NaN != 0 is true: a NaN entry is stored, as in SciPy
+    }
+  }
+  store_entry<MODE>(a, z, g, fl);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(ASM_T) assemble_rows_kernel(AsmArgs a) {
   extern __shared__ __align__(16) unsigned char asm_smem_raw[];
@@ -314,117 +350,98 @@ __global__ void __launch_bounds__(ASM_T) assemble_rows_kernel(AsmArgs a) {
     for (int i = 0; i < nr; ++i) { acc += sm.pp[i + 1]; sm.pp[i + 1] = acc; }
   }
   __syncthreads();
-  const int npairs = sm.pp[nr];
-  const int32_t zb = sm.rp[0], ze = sm.rp[nr];
-  if (npairs > ASM_CAP) {
-    // a hub node among these rows: per-entry walk over the elements around the row node (the round-1 scheme)
+  // the CTA's rows in batches of at most ASM_CAP (row, element) pairs: every thread derives the same batches
+  for (int rb = 0; rb < nr;) {
+    int re = rb + 1;
+    const int p0 = sm.pp[rb];
+    while (re < nr && sm.pp[re + 1] - p0 <= ASM_CAP) ++re;
+    const int npairs = sm.pp[re] - p0;
+    const int32_t zb = sm.rp[rb], ze = sm.rp[re];
+    if (npairs > ASM_CAP) {       // one hub row on its own
+      for (int32_t z = zb + tid; z < ze; z += ASM_T) walk_entry<MODE>(a, sm, sm.o[rb], z);
+      rb = re;
+      continue;
+    }
+    // phase 1: one (row node, element) pair per thread
+    for (int q = tid; q < npairs; q += ASM_T) {
+      const int p = p0 + q;
+      int lo = rb, hi = re;
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sm.pp[mid] <= p) lo = mid; else hi = mid; }
+      const int32_t orow = sm.o[lo];
+      const int32_t e = a.n2e[sm.q0[lo] + (p - sm.pp[lo])];
+      const int32_t* ed = a.edofs + 6 * (int64_t)e;
+      int li = 0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const int32_t d = ed[k];
+        sm.key[k * ASM_CAP + q] = d;
+        if (d == orow) li = k;
+      }
+      const double* r = a.elem + (int64_t)e * ELEM_STRIDE;
+      const double i00 = r[0], i10 = r[1], i01 = r[2], i11 = r[3], adet = r[4];
+      // test-function side and weights at the 6 quadrature points: once per pair (same operations as element_forms)
+      double gxi[6], gyi[6], pi[6], wq[6], dxq[6];
+#pragma unroll
+      for (int qp = 0; qp < 6; ++qp) {
+        wq[qp] = r[5 + qp];
+        dxq[qp] = mul(adet, sm.w[qp]);
+        gxi[qp] = add(mul(i00, sm.dx[li * 6 + qp]), mul(i10, sm.dy[li * 6 + qp]));
+        gyi[qp] = add(mul(i01, sm.dx[li * 6 + qp]), mul(i11, sm.dy[li * 6 + qp]));
+        pi[qp] = sm.phi[li * 6 + qp];
+      }
+#pragma unroll 1
+      for (int lj = 0; lj < 6; ++lj) {
+        double l[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) l[k] = 0.0;
+#pragma unroll
+        for (int qp = 0; qp < 6; ++qp) {
+          const double w = wq[qp];
+          const double gxj = add(mul(i00, sm.dx[lj * 6 + qp]), mul(i10, sm.dy[lj * 6 + qp]));
+          const double gyj = add(mul(i01, sm.dx[lj * 6 + qp]), mul(i11, sm.dy[lj * 6 + qp]));
+          const double pj = sm.phi[lj * 6 + qp];
+          const double wgy = mul(w, gyj), wgx = mul(w, gxj);       // mul(-w, g) == -mul(w, g) exactly
+          l[X_KXX] = add(l[X_KXX], mul(mul(wgy, gyi[qp]), dxq[qp]));
+          l[X_KYY] = add(l[X_KYY], mul(mul(wgx, gxi[qp]), dxq[qp]));
+          l[X_KXY] = add(l[X_KXY], mul(mul(-wgy, gxi[qp]), dxq[qp]));
+          l[X_KYX] = add(l[X_KYX], mul(mul(-wgx, gyi[qp]), dxq[qp]));
+          l[X_DXX] = add(l[X_DXX], mul(mul(gxj, gxi[qp]), dxq[qp]));
+          l[X_DYY] = add(l[X_DYY], mul(mul(gyj, gyi[qp]), dxq[qp]));
+          l[X_DXY] = add(l[X_DXY], mul(mul(gxj, gyi[qp]), dxq[qp]));
+          l[X_DYX] = add(l[X_DYX], mul(mul(gxi[qp], gyj), dxq[qp]));
+          l[X_M] = add(l[X_M], mul(mul(pj, pi[qp]), dxq[qp]));
+          l[X_MINV] = add(l[X_MINV], mul(mul(mul(w, pj), pi[qp]), dxq[qp]));
+        }
+#pragma unroll
+        for (int k = 0; k < 10; ++k) sm.l[stage_at(lj, k, q)] = l[k];
+      }
+    }
+    __syncthreads();
+    // phase 2: one structural non-zero per thread
     for (int32_t z = zb + tid; z < ze; z += ASM_T) {
-      int lo = 0, hi = nr;
+      int lo = rb, hi = re;
       while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sm.rp[mid] <= z) lo = mid; else hi = mid; }
-      const int32_t orow = sm.o[lo], ocol = a.old_of_new[a.col[z]];
+      const int32_t ocol = a.old_of_new[a.col[z]];
       double g[10];
 #pragma unroll
       for (int k = 0; k < 10; ++k) g[k] = 0.0;
       uint32_t fl = 0;
-      for (int32_t q = a.n2e_ptr[orow]; q < a.n2e_ptr[orow + 1]; ++q) {
-        const int32_t e = a.n2e[q];
-        const int32_t* ed = a.edofs + 6 * (int64_t)e;
-        int li = -1, lj = -1;
+      for (int q = sm.pp[lo] - p0; q < sm.pp[lo + 1] - p0; ++q) {      // the row's elements, ascending id
+        int lj = -1;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          const int32_t d = ed[k];
-          if (d == orow) li = k;
-          if (d == ocol) lj = k;
-        }
+        for (int k = 0; k < 6; ++k) lj = (sm.key[k * ASM_CAP + q] == ocol) ? k : lj;
         if (lj < 0) continue;
-        double l[10];
-        element_forms(sm, a.elem + (int64_t)e * ELEM_STRIDE, li, lj, l);
 #pragma unroll
         for (int k = 0; k < 10; ++k) {
-          g[k] = add(g[k], l[k]);
-          if (MODE == 1 && l[k] != 0.0) fl |= (1u << k);   // NaN != 0 is true: a NaN entry is stored, as in SciPy
+          const double l = sm.l[stage_at(lj, k, q)];
+          g[k] = add(g[k], l);
+          if (MODE == 1 && l != 0.0) fl |= (1u << k);
         }
       }
       store_entry<MODE>(a, z, g, fl);
     }
-    return;
-  }
-  // phase 1: one (row node, element) pair per thread
-  for (int p = tid; p < npairs; p += ASM_T) {
-    int lo = 0, hi = nr;
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sm.pp[mid] <= p) lo = mid; else hi = mid; }
-    const int32_t orow = sm.o[lo];
-    const int32_t e = a.n2e[sm.q0[lo] + (p - sm.pp[lo])];
-    const int32_t* ed = a.edofs + 6 * (int64_t)e;
-    int li = 0;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const int32_t d = ed[k];
-      sm.key[k * ASM_CAP + p] = d;
-      if (d == orow) li = k;
-    }
-    const double* r = a.elem + (int64_t)e * ELEM_STRIDE;
-    const double i00 = r[0], i10 = r[1], i01 = r[2], i11 = r[3], adet = r[4];
-    // test-function side and weights at the 6 quadrature points: once per pair (same operations as element_forms)
-    double gxi[6], gyi[6], pi[6], wq[6], dxq[6];
-#pragma unroll
-    for (int qp = 0; qp < 6; ++qp) {
-      wq[qp] = r[5 + qp];
-      dxq[qp] = mul(adet, sm.w[qp]);
-      gxi[qp] = add(mul(i00, sm.dx[li * 6 + qp]), mul(i10, sm.dy[li * 6 + qp]));
-      gyi[qp] = add(mul(i01, sm.dx[li * 6 + qp]), mul(i11, sm.dy[li * 6 + qp]));
-      pi[qp] = sm.phi[li * 6 + qp];
-    }
-#pragma unroll 1
-    for (int lj = 0; lj < 6; ++lj) {
-      double l[10];
-#pragma unroll
-      for (int k = 0; k < 10; ++k) l[k] = 0.0;
-#pragma unroll
-      for (int qp = 0; qp < 6; ++qp) {
-        const double w = wq[qp];
-        const double gxj = add(mul(i00, sm.dx[lj * 6 + qp]), mul(i10, sm.dy[lj * 6 + qp]));
-        const double gyj = add(mul(i01, sm.dx[lj * 6 + qp]), mul(i11, sm.dy[lj * 6 + qp]));
-        const double pj = sm.phi[lj * 6 + qp];
-        const double wgy = mul(w, gyj), wgx = mul(w, gxj);       // mul(-w, g) == -mul(w, g) exactly
-        l[X_KXX] = add(l[X_KXX], mul(mul(wgy, gyi[qp]), dxq[qp]));
-        l[X_KYY] = add(l[X_KYY], mul(mul(wgx, gxi[qp]), dxq[qp]));
-        l[X_KXY] = add(l[X_KXY], mul(mul(-wgy, gxi[qp]), dxq[qp]));
-        l[X_KYX] = add(l[X_KYX], mul(mul(-wgx, gyi[qp]), dxq[qp]));
-        l[X_DXX] = add(l[X_DXX], mul(mul(gxj, gxi[qp]), dxq[qp]));
-        l[X_DYY] = add(l[X_DYY], mul(mul(gyj, gyi[qp]), dxq[qp]));
-        l[X_DXY] = add(l[X_DXY], mul(mul(gxj, gyi[qp]), dxq[qp]));
-        l[X_DYX] = add(l[X_DYX], mul(mul(gxi[qp], gyj), dxq[qp]));
-        l[X_M] = add(l[X_M], mul(mul(pj, pi[qp]), dxq[qp]));
-        l[X_MINV] = add(l[X_MINV], mul(mul(mul(w, pj), pi[qp]), dxq[qp]));
-      }
-#pragma unroll
-      for (int k = 0; k < 10; ++k) sm.l[(lj * 10 + k) * ASM_CAP + p] = l[k];
-    }
-  }
-  __syncthreads();
-  // phase 2: one structural non-zero per thread
-  for (int32_t z = zb + tid; z < ze; z += ASM_T) {
-    int lo = 0, hi = nr;
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sm.rp[mid] <= z) lo = mid; else hi = mid; }
-    const int32_t ocol = a.old_of_new[a.col[z]];
-    double g[10];
-#pragma unroll
-    for (int k = 0; k < 10; ++k) g[k] = 0.0;
-    uint32_t fl = 0;
-    for (int p = sm.pp[lo]; p < sm.pp[lo + 1]; ++p) {      // the row's elements, ascending id
-      int lj = -1;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) lj = (sm.key[k * ASM_CAP + p] == ocol) ? k : lj;
-      if (lj < 0) continue;
-#pragma unroll
-      for (int k = 0; k < 10; ++k) {
-        const double l = sm.l[(lj * 10 + k) * ASM_CAP + p];
-        g[k] = add(g[k], l);
-        if (MODE == 1 && l != 0.0) fl |= (1u << k);
-      }
-    }
-    store_entry<MODE>(a, z, g, fl);
+    __syncthreads();              // the staging area is reused by the next batch
+    rb = re;
   }
 }
 

@@ -188,7 +188,12 @@ struct LevelTask {
   int32_t goff;                         // forward: the front's gather tables in gsrc; backward: its update set in strct
   int32_t uoff;                         // forward: the front's update vector in the update pool
   int32_t nch;                          // forward: children of the front; backward: slab class 8 / 16 (lanes split the contraction) or 0 (wide)
-  int32_t f, pad;
+  int32_t f;
+  // dataflow launch (all levels in one grid): the counter this task waits on, the count it waits for, the counter it bumps
+  // when its results are visible.  Forward: dep = its own front (tasks of its children above the subtrees), sig = its parent.
+  // Backward: dep = its parent (all of the parent's tasks), sig = its own front.  -1 = none.
+  int32_t dep, need, sig;
+  int32_t pad[2];
 };
 struct StreamPlan {
   int n_subs = 0, n_fronts = 0;
@@ -197,8 +202,10 @@ struct StreamPlan {
   DevBuf<double> sfwd, sbwd;
   // fronts above the subtrees: per-level task lists and their streams
   DevBuf<LevelTask> ftasks, btasks;
-  std::vector<int32_t> fptr, bptr;            // [nlevels+1]
+  std::vector<int32_t> fptr, bptr;            // [nlevels+1]; backward tasks are stored top level first: level l is [bptr[l+1], bptr[l])
   DevBuf<double> lfwd, lbwd;
+  DevBuf<int32_t> sync;                       // dataflow counters: [0] forward ticket, [1] backward ticket, [2 + f] forward, [2 + nfronts + f] backward
+  int32_t nfronts = 0;
   int64_t lfwd_doubles = 0, lbwd_doubles = 0;
 };
 
@@ -227,6 +234,10 @@ void build_level_plan(plfem_ctx* ctx, const FrontPlan& P, const std::vector<int3
                       const std::vector<int32_t>& goff, StreamPlan& S);
 void launch_level_forward(plfem_ctx* ctx, const DevPlan& D, int level, const double* rhs, double* out, int nrhs, bool pdl);
 void launch_level_backward(plfem_ctx* ctx, const DevPlan& D, int level, double* x, int nrhs, bool pdl);
+// every level above the bottom subtrees in ONE launch: tasks take tickets in level order and wait on per-front counters
+void reset_sweep_counters(plfem_ctx* ctx, const DevPlan& D);
+void launch_fused_forward(plfem_ctx* ctx, const DevPlan& D, const double* rhs, double* out, int nrhs, bool pdl);
+void launch_fused_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs, bool pdl);
 void launch_stream_pack(plfem_ctx* ctx, const DevPlan& D);
 void launch_stream_forward(plfem_ctx* ctx, const DevPlan& D, const double* rhs, double* out, int nrhs, bool pdl);
 void launch_stream_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs, bool pdl);
@@ -238,7 +249,7 @@ void run_factorization(plfem_ctx* ctx, const DevPlan& D);
 constexpr int SOLVE_NRHS = 4;   // block size of the multi-right-hand-side sweeps (block Lanczos)
 void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x, int nrhs = 1);
 void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double* z, int nrhs = 1);
-void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs = 1);
+void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs = 1, bool reset_counters = true);
 
 // ---- Lanczos + mode reductions (eigen.cu) ----------------------------------------------------------
 struct EigenResult {

@@ -527,15 +527,28 @@ bool use_pdl() {
   return on;
 }
 
+bool use_fused_sweeps() {      // PLFEM_SWEEP=levels: one launch per elimination-tree level (the round-2 scheme, kept for A/B runs)
+  static const bool on = [] { const char* e = std::getenv("PLFEM_SWEEP"); return !(e && e[0] == 'l'); }();
+  return on;
+}
+
 // nrhs right-hand sides (1 or SOLVE_NRHS), INTERLEAVED: entry i of right-hand side r at b[i * nrhs + r].  One launch for the
-// bottom subtrees, then one launch per remaining level (sweep_stream.cu).
+// bottom subtrees, then ONE dataflow launch for everything above them (sweep_stream.cu): its tasks take tickets in level
+// order and wait on per-front counters, so a front starts as soon as its own children are done and no launch boundary
+// (12 us each, fifteen of them per sweep of a 7-core design) separates the levels.
 void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double* z, int nrhs) {
   if (nrhs != 1 && nrhs != SOLVE_NRHS) throw StatusError(PLFEM_ERR_INTERNAL, "unsupported number of right-hand sides");
   const bool pdl = use_pdl();
+  const bool fused = use_fused_sweeps();
+  if (fused) reset_sweep_counters(ctx, D);     // forward and backward counters, before the first launch of the solve
   bool first = true;     // the first launch follows kernels that are not PDL-aware: plain launch
   if (D.st.n_subs > 0) {
     launch_stream_forward(ctx, D, b, z, nrhs, false);
     first = false;
+  }
+  if (fused) {
+    launch_fused_forward(ctx, D, b, z, nrhs, pdl && !first);
+    return;
   }
   for (int l = 0; l < D.nlevels; ++l) {
     if (D.st.fptr[l + 1] == D.st.fptr[l]) continue;
@@ -544,19 +557,25 @@ void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double
   }
 }
 
-// must follow run_solve_forward on the same stream (its launches may be PDL-chained to the forward ones)
-void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs) {
+// must follow run_solve_forward on the same stream (its launches may be PDL-chained to the forward ones); reset_counters =
+// false when that forward sweep has just cleared the dataflow counters (run_solve)
+void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs, bool reset_counters) {
   const bool pdl = use_pdl();
-  for (int l = D.nlevels - 1; l >= 0; --l) {
-    if (D.st.bptr[l + 1] == D.st.bptr[l]) continue;
-    launch_level_backward(ctx, D, l, x, nrhs, pdl);
+  if (use_fused_sweeps()) {
+    if (reset_counters) reset_sweep_counters(ctx, D);
+    launch_fused_backward(ctx, D, x, nrhs, pdl && !reset_counters);
+  } else {
+    for (int l = D.nlevels - 1; l >= 0; --l) {
+      if (D.st.bptr[l] == D.st.bptr[l + 1]) continue;
+      launch_level_backward(ctx, D, l, x, nrhs, pdl);
+    }
   }
   if (D.st.n_subs > 0) launch_stream_backward(ctx, D, x, nrhs, pdl);
 }
 
 void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x, int nrhs) {
   run_solve_forward(ctx, D, b, x, nrhs);
-  run_solve_backward(ctx, D, x, nrhs);
+  run_solve_backward(ctx, D, x, nrhs, false);
 }
 
 }  // namespace plfem

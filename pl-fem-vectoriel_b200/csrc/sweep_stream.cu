@@ -157,6 +157,41 @@ __device__ __forceinline__ void ldg_v(const double* base, int64_t idx, double (&
     for (int r = 0; r < NR; ++r) v[r] = base[idx * NR + r];
   }
 }
+// the same through L2 only (ld.global.cg): values another CTA of the SAME launch has just written (dataflow sweeps)
+template <int NR>
+__device__ __forceinline__ void ldcg_v(const double* base, int64_t idx, double (&v)[NR]) {
+  if constexpr (NR % 2 == 0) {
+    const double2* p = reinterpret_cast<const double2*>(base + idx * NR);
+#pragma unroll
+    for (int r = 0; r < NR / 2; ++r) { const double2 t = __ldcg(p + r); v[2 * r] = t.x; v[2 * r + 1] = t.y; }
+  } else {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) v[r] = __ldcg(base + idx * NR + r);
+  }
+}
+__device__ __forceinline__ int ld_acquire(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// lane 0 waits until counter c has reached `need`; gives up (and says so) instead of hanging the GPU
+__device__ __forceinline__ void wait_counter(const int32_t* c, int need, int lane, int32_t* status) {
+  if (lane == 0) {
+    unsigned spins = 0;
+    while (ld_acquire(c) < need) {
+      __nanosleep(64);
+      if (++spins > (1u << 22)) { atomicExch(status + 1, 3); break; }
+    }
+  }
+  __syncwarp();
+}
+// every lane's stores first, then one increment
+__device__ __forceinline__ void signal_counter(int32_t* c, int lane) {
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) atomicAdd(c, 1);
+}
+
 template <int NR>
 __device__ __forceinline__ void stg_v(double* base, int64_t idx, const double (&v)[NR]) {
   if constexpr (NR % 2 == 0) {
@@ -496,12 +531,12 @@ __device__ __forceinline__ void level_fwd_rows(PipeF& pp, LevelFwdSmem<NR>& sm, 
     for (int r = 0; r < NR; ++r) yt[q][r] = 0.0;
     double w[NR];
     if (j1[q] >= 0) {
-      ldg_v<NR>(rv.upd, j1[q], w);
+      ldcg_v<NR>(rv.upd, j1[q], w);
 #pragma unroll
       for (int r = 0; r < NR; ++r) yt[q][r] += w[r];
     }
     if (j2[q] >= 0) {
-      ldg_v<NR>(rv.upd, j2[q], w);
+      ldcg_v<NR>(rv.upd, j2[q], w);
 #pragma unroll
       for (int r = 0; r < NR; ++r) yt[q][r] += w[r];
     }
@@ -545,16 +580,23 @@ __device__ __forceinline__ void level_fwd_rows(PipeF& pp, LevelFwdSmem<NR>& sm, 
   }
 }
 
-template <int NR, bool PDL>
+template <int NR, bool PDL, bool FUSED>
 __global__ void __launch_bounds__(32) level_forward_kernel(const LevelTask* __restrict__ tasks, const int32_t* __restrict__ gsrc,
                                                            const double* __restrict__ stream, const int32_t* __restrict__ cptr,
                                                            const int32_t* __restrict__ child, const int32_t* __restrict__ cmap_ptr,
                                                            const int32_t* __restrict__ cmap, const int32_t* __restrict__ sptr,
-                                                           const int32_t* __restrict__ uoff, RhsView rv, int32_t* status) {
+                                                           const int32_t* __restrict__ uoff, RhsView rv, int32_t* status, int32_t* sync) {
   __shared__ LevelFwdSmem<NR> sm;
   const int lane = threadIdx.x;
   if (PDL) griddep_launch_dependents();
-  const LevelTask t = tasks[blockIdx.x];
+  // dataflow launch: tasks are handed out in level order by a ticket, so whatever a running task waits for belongs to a
+  // task that has started before it — progress does not depend on the order in which the hardware dispatches CTAs
+  int ti = blockIdx.x;
+  if (FUSED) {
+    if (lane == 0) ti = atomicAdd(sync, 1);
+    ti = __shfl_sync(0xffffffffu, ti, 0);
+  }
+  const LevelTask t = tasks[ti];
   if (lane == 0) {
     for (int s = 0; s < NSF; ++s) mbar_init(sm.bar + s, 1);
     fence_mbar_init();
@@ -576,6 +618,7 @@ __global__ void __launch_bounds__(32) level_forward_kernel(const LevelTask* __re
     if (k < t.n && row >= t.s2) { j1[q] = g1[row]; j2[q] = g2[row]; }
   }
   if (PDL) griddep_wait();
+  if (FUSED && t.need > 0) wait_counter(sync + 2 + t.dep, t.need, lane, status);     // the children's update vectors are complete
   // assembled pivot part of the right-hand sides, fixed order (rhs + first child) + second child
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -584,12 +627,12 @@ __global__ void __launch_bounds__(32) level_forward_kernel(const LevelTask* __re
     double v[NR], w[NR];
     ldg_v<NR>(rv.rhs, t.g0 + k, v);
     if (i1[q] >= 0) {
-      ldg_v<NR>(rv.upd, i1[q], w);
+      ldcg_v<NR>(rv.upd, i1[q], w);
 #pragma unroll
       for (int r = 0; r < NR; ++r) v[r] += w[r];
     }
     if (i2[q] >= 0) {
-      ldg_v<NR>(rv.upd, i2[q], w);
+      ldcg_v<NR>(rv.upd, i2[q], w);
 #pragma unroll
       for (int r = 0; r < NR; ++r) v[r] += w[r];
     }
@@ -606,7 +649,7 @@ __global__ void __launch_bounds__(32) level_forward_kernel(const LevelTask* __re
         const int row = 2 * cm[k >> 1] + (k & 1);
         if (row < t.s2) {
           double w[NR];
-          ldg_v<NR>(rv.upd, (int64_t)uoff[ch] + k, w);
+          ldcg_v<NR>(rv.upd, (int64_t)uoff[ch] + k, w);
 #pragma unroll
           for (int r = 0; r < NR; ++r) sm.cv[row * NR + r] += w[r];
         }
@@ -630,8 +673,8 @@ __global__ void __launch_bounds__(32) level_forward_kernel(const LevelTask* __re
         const int row = 2 * cm[k >> 1] + (k & 1);
         if (row >= t.s2 && row >= t.r0 && row < t.r0 + t.n) {
           double w[NR], o[NR];
-          ldg_v<NR>(rv.upd, (int64_t)uoff[ch] + k, w);
-          ldg_v<NR>(rv.upd, (int64_t)t.uoff + (row - t.s2), o);
+          ldcg_v<NR>(rv.upd, (int64_t)uoff[ch] + k, w);
+          ldcg_v<NR>(rv.upd, (int64_t)t.uoff + (row - t.s2), o);
 #pragma unroll
           for (int r = 0; r < NR; ++r) o[r] += w[r];
           stg_v<NR>(rv.upd, (int64_t)t.uoff + (row - t.s2), o);
@@ -640,6 +683,7 @@ __global__ void __launch_bounds__(32) level_forward_kernel(const LevelTask* __re
       __syncwarp();
     }
   }
+  if (FUSED && t.sig >= 0) signal_counter(sync + 2 + t.sig, lane);
   pp.drain();
 }
 
@@ -691,13 +735,18 @@ __device__ __forceinline__ void level_bwd_wide(PipeB& pp, LevelBwdSmem<NR>& sm, 
   }
 }
 
-template <int NR, bool PDL>
+template <int NR, bool PDL, bool FUSED>
 __global__ void __launch_bounds__(32) level_backward_kernel(const LevelTask* __restrict__ tasks, const double* __restrict__ stream,
-                                                            const int32_t* __restrict__ strct, double* __restrict__ x, int32_t* status) {
+                                                            const int32_t* __restrict__ strct, double* __restrict__ x, int32_t* status, int32_t* sync, int nfronts) {
   __shared__ LevelBwdSmem<NR> sm;
   const int lane = threadIdx.x;
   if (PDL) griddep_launch_dependents();
-  const LevelTask t = tasks[blockIdx.x];
+  int ti = blockIdx.x;
+  if (FUSED) {            // tickets in level order, top level first (see level_forward_kernel)
+    if (lane == 0) ti = atomicAdd(sync + 1, 1);
+    ti = __shfl_sync(0xffffffffu, ti, 0);
+  }
+  const LevelTask t = tasks[ti];
   if (lane == 0) {
     for (int s = 0; s < NSB; ++s) mbar_init(sm.bar + s, 1);
     fence_mbar_init();
@@ -715,6 +764,7 @@ __global__ void __launch_bounds__(32) level_backward_kernel(const LevelTask* __r
     xo[q] = j < t.u2 ? 2 * (int64_t)st[j >> 1] + (j & 1) : -1;
   }
   if (PDL) griddep_wait();
+  if (FUSED && t.need > 0) wait_counter(sync + 2 + nfronts + t.dep, t.need, lane, status);   // the parent's unknowns are final
   const int W = t.nch;                          // slab class: 8, 16 (lanes split the contraction index) or 0 (wide)
   double accn[NR];
   double accw[4][NR];
@@ -742,7 +792,7 @@ __global__ void __launch_bounds__(32) level_backward_kernel(const LevelTask* __r
     for (int q = 0; q < NG; ++q) {
       if (xo[q] < 0) continue;
       double v[NR];
-      ldg_v<NR>(x, xo[q], v);
+      ldcg_v<NR>(x, xo[q], v);
 #pragma unroll
       for (int r = 0; r < NR; ++r) sm.cv[(lane + 32 * q) * NR + r] = v[r];
     }
@@ -779,6 +829,7 @@ __global__ void __launch_bounds__(32) level_backward_kernel(const LevelTask* __r
       stg_v<NR>(x, t.g0 + t.r0 + lane + 32 * q, z);
     }
   }
+  if (FUSED && t.sig >= 0) signal_counter(sync + 2 + nfronts + t.sig, lane);
   pp.drain();
 }
 
@@ -893,11 +944,30 @@ void build_stream_plan(plfem_ctx* ctx, const FrontPlan& P, const std::vector<int
   PLFEM_CUDA(stream_wait(ctx->stream));       // the host vectors above are pageable and local
 }
 
-// Task lists of the fronts above the bottom subtrees, level by level, and the layout of their streams.
+// Task lists of the fronts above the bottom subtrees, level by level, and the layout of their streams.  Forward tasks are
+// stored bottom level first, backward tasks top level first: the order in which the dataflow launches hand them out.
 void build_level_plan(plfem_ctx* ctx, const FrontPlan& P, const std::vector<int32_t>& uoff, const std::vector<uint8_t>& in_sub,
                       const std::vector<int32_t>& goff, StreamPlan& S) {
   std::vector<LevelTask> ft, bt;
   S.fptr.assign(P.nlevels + 1, 0); S.bptr.assign(P.nlevels + 1, 0);
+  S.nfronts = P.nfronts;
+  // slab sizes depend on the front alone (a design's arithmetic is the same alone and inside a forest)
+  auto fwd_rows = [](int s2) { return std::max(32, std::min(128, (4096 / s2) & ~31)); };
+  auto bwd_class = [](int u2, int& W, int& nc) {
+    if (u2 <= 128) { W = 0; nc = std::max(32, std::min(128, (4096 / u2) & ~31)); }
+    else if (u2 <= 256) { W = 16; nc = 16; }
+    else { W = 8; nc = 8; }
+  };
+  std::vector<int32_t> nft(P.nfronts, 0), nbt(P.nfronts, 0);      // tasks per front
+  for (int f = 0; f < P.nfronts; ++f) {
+    if (in_sub[f]) continue;
+    const int s2 = 2 * P.s[f], u2 = 2 * (P.sptr[f + 1] - P.sptr[f]);
+    nft[f] = (s2 + u2 + fwd_rows(s2) - 1) / fwd_rows(s2);
+    if (u2 > 0) { int W, nc; bwd_class(u2, W, nc); nbt[f] = (s2 + nc - 1) / nc; }
+  }
+  std::vector<int32_t> fneed(P.nfronts, 0);                        // forward: tasks of the children above the subtrees
+  for (int f = 0; f < P.nfronts; ++f)
+    if (!in_sub[f] && P.parent[f] >= 0) fneed[P.parent[f]] += nft[f];
   int64_t fo = 0, bo = 0;     // chunks
   for (int l = 0; l < P.nlevels; ++l) {
     for (int q = P.lptr[l]; q < P.lptr[l + 1]; ++q) {
@@ -908,22 +978,33 @@ void build_level_plan(plfem_ctx* ctx, const FrontPlan& P, const std::vector<int3
       t.g0 = 2 * (int64_t)P.first[f]; t.s2 = s2; t.u2 = u2; t.f = f;
       // forward: slabs of rows.  A slab's stream is s2 columns of its height: about 32 KB, the capacity of the ring, so that a
       // task is completely in flight before its dependencies resolve
-      const int nr = std::max(32, std::min(128, (4096 / s2) & ~31));
+      const int nr = fwd_rows(s2);
       t.goff = goff[f]; t.uoff = uoff[f]; t.nch = P.cptr[f + 1] - P.cptr[f];
+      t.dep = f; t.need = fneed[f]; t.sig = P.parent[f];
       for (int r0 = 0; r0 < rows; r0 += nr) {
         t.r0 = r0; t.n = std::min(nr, rows - r0);
         t.chunks = item_chunks(s2, (t.n + 3) & ~3);
         t.soff = fo * CHD; fo += t.chunks;
         ft.push_back(t);
       }
+    }
+    S.fptr[l + 1] = (int32_t)ft.size();
+  }
+  for (int l = P.nlevels - 1; l >= 0; --l) {
+    for (int q = P.lptr[l]; q < P.lptr[l + 1]; ++q) {
+      const int f = P.lfront[q];
+      if (in_sub[f]) continue;
+      const int s2 = 2 * P.s[f], u2 = 2 * (P.sptr[f + 1] - P.sptr[f]);
       if (u2 == 0) continue;
+      LevelTask t{};
+      t.g0 = 2 * (int64_t)P.first[f]; t.s2 = s2; t.u2 = u2; t.f = f;
       // backward: slabs of pivot columns; the longer the contraction (u2), the narrower the slab, down to 8 columns with the
       // lanes split four ways over the contraction index
       int W, nc;
-      if (u2 <= 128) { W = 0; nc = std::max(32, std::min(128, (4096 / u2) & ~31)); }
-      else if (u2 <= 256) { W = 16; nc = 16; }
-      else { W = 8; nc = 8; }
+      bwd_class(u2, W, nc);
       t.goff = P.sptr[f]; t.uoff = 0; t.nch = W;
+      const int par = P.parent[f];
+      t.dep = par; t.need = par >= 0 ? nbt[par] : 0; t.sig = f;   // a root above (no update set) has no tasks: nothing to wait for
       for (int c0 = 0; c0 < s2; c0 += nc) {
         t.r0 = c0; t.n = std::min(nc, s2 - c0);
         t.chunks = item_chunks(u2, W ? W : ((t.n + 3) & ~3));
@@ -931,11 +1012,13 @@ void build_level_plan(plfem_ctx* ctx, const FrontPlan& P, const std::vector<int3
         bt.push_back(t);
       }
     }
-    S.fptr[l + 1] = (int32_t)ft.size(); S.bptr[l + 1] = (int32_t)bt.size();
+    S.bptr[l] = (int32_t)bt.size();           // level l: [bptr[l + 1], bptr[l])
   }
+  S.bptr[P.nlevels] = 0;
   S.ftasks.upload(ctx, ft); S.btasks.upload(ctx, bt);
   S.lfwd.alloc(ctx, (size_t)std::max<int64_t>(fo, 1) * CHD); S.lbwd.alloc(ctx, (size_t)std::max<int64_t>(bo, 1) * CHD);
   S.lfwd_doubles = fo * CHD; S.lbwd_doubles = bo * CHD;
+  S.sync.alloc(ctx, 2 + 2 * (size_t)P.nfronts);
   PLFEM_CUDA(stream_wait(ctx->stream));       // the host vectors above are pageable and local
 }
 
@@ -956,7 +1039,7 @@ void launch_stream_pack(plfem_ctx* ctx, const DevPlan& D) {
 namespace {
 template <class... KArgs, class... Args>
 void launch_warp_ctas(void (*kernel)(KArgs...), bool pdl, int grid, cudaStream_t st, Args... args) {
-  static thread_local const void* configured[16] = {};
+  static thread_local const void* configured[64] = {};
   bool seen = false;
   for (const void* k : configured) seen |= (k == (const void*)kernel);
   if (!seen) {      // all of the SM's shared memory for the rings: 8 warps per SM
@@ -970,6 +1053,33 @@ void launch_warp_ctas(void (*kernel)(KArgs...), bool pdl, int grid, cudaStream_t
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
   PLFEM_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+}
+
+template <bool FUSED>
+void launch_forward_tasks(plfem_ctx* ctx, const DevPlan& D, const LevelTask* tasks, int n, const double* rhs, double* out, int nrhs, bool pdl) {
+  const StreamPlan& S = D.st;
+  const RhsView rv{rhs, out, D.upd.p};
+  if (nrhs == 1) {
+    if (pdl) launch_warp_ctas(level_forward_kernel<1, true, FUSED>, true, n, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p);
+    else launch_warp_ctas(level_forward_kernel<1, false, FUSED>, false, n, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p);
+  } else {
+    if (pdl) launch_warp_ctas(level_forward_kernel<SOLVE_NRHS, true, FUSED>, true, n, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p);
+    else launch_warp_ctas(level_forward_kernel<SOLVE_NRHS, false, FUSED>, false, n, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p);
+  }
+  ctx->launches++;
+}
+
+template <bool FUSED>
+void launch_backward_tasks(plfem_ctx* ctx, const DevPlan& D, const LevelTask* tasks, int n, double* x, int nrhs, bool pdl) {
+  const StreamPlan& S = D.st;
+  if (nrhs == 1) {
+    if (pdl) launch_warp_ctas(level_backward_kernel<1, true, FUSED>, true, n, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, D.status.p, S.sync.p, S.nfronts);
+    else launch_warp_ctas(level_backward_kernel<1, false, FUSED>, false, n, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, D.status.p, S.sync.p, S.nfronts);
+  } else {
+    if (pdl) launch_warp_ctas(level_backward_kernel<SOLVE_NRHS, true, FUSED>, true, n, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, D.status.p, S.sync.p, S.nfronts);
+    else launch_warp_ctas(level_backward_kernel<SOLVE_NRHS, false, FUSED>, false, n, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, D.status.p, S.sync.p, S.nfronts);
+  }
+  ctx->launches++;
 }
 }  // namespace
 
@@ -988,31 +1098,26 @@ void launch_stream_forward(plfem_ctx* ctx, const DevPlan& D, const double* rhs, 
 
 void launch_level_forward(plfem_ctx* ctx, const DevPlan& D, int level, const double* rhs, double* out, int nrhs, bool pdl) {
   const StreamPlan& S = D.st;
-  const int n = S.fptr[level + 1] - S.fptr[level];
-  const LevelTask* tasks = S.ftasks.p + S.fptr[level];
-  const RhsView rv{rhs, out, D.upd.p};
-  if (nrhs == 1) {
-    if (pdl) launch_warp_ctas(level_forward_kernel<1, true>, true, n, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p);
-    else launch_warp_ctas(level_forward_kernel<1, false>, false, n, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p);
-  } else {
-    if (pdl) launch_warp_ctas(level_forward_kernel<SOLVE_NRHS, true>, true, n, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p);
-    else launch_warp_ctas(level_forward_kernel<SOLVE_NRHS, false>, false, n, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p);
-  }
-  ctx->launches++;
+  launch_forward_tasks<false>(ctx, D, S.ftasks.p + S.fptr[level], S.fptr[level + 1] - S.fptr[level], rhs, out, nrhs, pdl);
 }
 
 void launch_level_backward(plfem_ctx* ctx, const DevPlan& D, int level, double* x, int nrhs, bool pdl) {
   const StreamPlan& S = D.st;
-  const int n = S.bptr[level + 1] - S.bptr[level];
-  const LevelTask* tasks = S.btasks.p + S.bptr[level];
-  if (nrhs == 1) {
-    if (pdl) launch_warp_ctas(level_backward_kernel<1, true>, true, n, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, D.status.p);
-    else launch_warp_ctas(level_backward_kernel<1, false>, false, n, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, D.status.p);
-  } else {
-    if (pdl) launch_warp_ctas(level_backward_kernel<SOLVE_NRHS, true>, true, n, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, D.status.p);
-    else launch_warp_ctas(level_backward_kernel<SOLVE_NRHS, false>, false, n, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, D.status.p);
-  }
-  ctx->launches++;
+  launch_backward_tasks<false>(ctx, D, S.btasks.p + S.bptr[level + 1], S.bptr[level] - S.bptr[level + 1], x, nrhs, pdl);
+}
+
+void reset_sweep_counters(plfem_ctx* ctx, const DevPlan& D) {
+  if (D.st.sync.n) PLFEM_CUDA(cudaMemsetAsync(D.st.sync.p, 0, D.st.sync.n * sizeof(int32_t), ctx->stream));
+}
+
+void launch_fused_forward(plfem_ctx* ctx, const DevPlan& D, const double* rhs, double* out, int nrhs, bool pdl) {
+  const StreamPlan& S = D.st;
+  if (S.ftasks.n > 0) launch_forward_tasks<true>(ctx, D, S.ftasks.p, (int)S.ftasks.n, rhs, out, nrhs, pdl);
+}
+
+void launch_fused_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs, bool pdl) {
+  const StreamPlan& S = D.st;
+  if (S.btasks.n > 0) launch_backward_tasks<true>(ctx, D, S.btasks.p, (int)S.btasks.n, x, nrhs, pdl);
 }
 
 void launch_stream_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs, bool pdl) {
@@ -1029,4 +1134,3 @@ void launch_stream_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrh
 }
 
 }  // namespace plfem
-
