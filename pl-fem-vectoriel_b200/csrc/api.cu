@@ -887,6 +887,27 @@ static void profile_work(plfem_ctx* ctx, SolveWork& W, int repeat, double* out_m
     out_bytes[6] = out_bytes[2] + 16.0 * m * (SOLVE_NRHS - 1);
     out_ms[7] = timed([&] { run_solve_backward(ctx, W.dplan, x4.p, SOLVE_NRHS); });
     out_bytes[7] = out_bytes[3] + 16.0 * m * (SOLVE_NRHS - 1);
+    if (const char* tf = std::getenv("PLFEM_TRACE_FILE")) {
+      // stage clock of one dataflow forward sweep: [int64 ntasks, nlevels][int32 fptr[nlevels + 1]][int64 stamps[ntasks][8]]
+      const int64_t nt = (int64_t)W.dplan.st.ftasks.n, nl = W.dplan.nlevels;
+      DevBuf<long long> tr;
+      tr.alloc(ctx, (size_t)std::max<int64_t>(nt, 1) * 8); tr.zero();
+      PLFEM_CUDA(stream_wait(st));
+      set_sweep_trace(tr.p);
+      PLFEM_CUDA(cudaMemsetAsync(flush.p, 1, flush.n * sizeof(double), st));
+      run_solve_forward(ctx, W.dplan, b4.p, x4.p, SOLVE_NRHS);
+      PLFEM_CUDA(stream_wait(st));
+      set_sweep_trace(nullptr);
+      std::vector<long long> h((size_t)nt * 8);
+      tr.download(h.data(), h.size());
+      PLFEM_CUDA(stream_wait(st));
+      if (FILE* fh = std::fopen(tf, "wb")) {
+        std::fwrite(&nt, 8, 1, fh); std::fwrite(&nl, 8, 1, fh);
+        std::fwrite(W.dplan.st.fptr.data(), 4, (size_t)nl + 1, fh);
+        std::fwrite(h.data(), 8, h.size(), fh);
+        std::fclose(fh);
+      }
+    }
   }
 }
 

@@ -187,7 +187,8 @@ struct LevelTask {
   int32_t chunks, s2, u2, r0, n;        // chunks of the task's stream; pivot / update unknowns; first row (fwd) or pivot column (bwd), count
   int32_t goff;                         // forward: the front's gather tables in gsrc; backward: its update set in strct
   int32_t uoff;                         // forward: the front's update vector in the update pool
-  int32_t nch;                          // forward: children of the front; backward: slab class 8 / 16 (lanes split the contraction) or 0 (wide)
+  int32_t nch;                          // forward: children of the front; backward: slabs of the front (r0 = first update unknown, n = count,
+                                        // uoff = the front's partial sums, pad[0] = slab length)
   int32_t f;
   // dataflow launch (all levels in one grid): the counter this task waits on, the count it waits for, the counter it bumps
   // when its results are visible.  Forward: dep = its own front (tasks of its children above the subtrees), sig = its parent.
@@ -204,7 +205,9 @@ struct StreamPlan {
   DevBuf<LevelTask> ftasks, btasks;
   std::vector<int32_t> fptr, bptr;            // [nlevels+1]; backward tasks are stored top level first: level l is [bptr[l+1], bptr[l])
   DevBuf<double> lfwd, lbwd;
-  DevBuf<int32_t> sync;                       // dataflow counters: [0] forward ticket, [1] backward ticket, [2 + f] forward, [2 + nfronts + f] backward
+  DevBuf<int32_t> sync;                       // counters: [0] forward ticket, [1] backward ticket, [2 + f] forward, [2 + nfronts + f] backward,
+                                              // [2 + 2 nfronts + f] backward slabs of front f that have left their partial sums
+  DevBuf<double> bpart;                       // partial sums of the backward slabs
   int32_t nfronts = 0;
   int64_t lfwd_doubles = 0, lbwd_doubles = 0;
 };
@@ -236,6 +239,7 @@ void launch_level_forward(plfem_ctx* ctx, const DevPlan& D, int level, const dou
 void launch_level_backward(plfem_ctx* ctx, const DevPlan& D, int level, double* x, int nrhs, bool pdl);
 // every level above the bottom subtrees in ONE launch: tasks take tickets in level order and wait on per-front counters
 void reset_sweep_counters(plfem_ctx* ctx, const DevPlan& D);
+void set_sweep_trace(long long* p);   // measurement only: stage clock of the dataflow forward sweep (null = off)
 void launch_fused_forward(plfem_ctx* ctx, const DevPlan& D, const double* rhs, double* out, int nrhs, bool pdl);
 void launch_fused_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs, bool pdl);
 void launch_stream_pack(plfem_ctx* ctx, const DevPlan& D);

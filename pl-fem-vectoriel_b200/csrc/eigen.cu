@@ -289,30 +289,31 @@ constexpr int DCOLS = 8;    // basis columns per CTA of the projection kernel: t
 constexpr int RSPLIT = 8;   // row slices per design (fixed: the summation order does not depend on the forest)
 
 // Hp_b[s][c + r*ldh] = <Q_b[rows of slice s, c], R_b[rows of slice s, r]> for c < ncols, r < P;
-// one CTA per (group of DCOLS columns, row slice s, design b)
+// one CTA per (group of DCOLS columns, row slice s, design b).  Rows are taken in PAIRS (128-bit loads: the design's rows
+// start at an even offset and the slices are cut at even rows), two pairs in flight per thread.
 __global__ void __launch_bounds__(256) dots_block_kernel(const double* __restrict__ Q, int64_t ld, const double* __restrict__ R,
                                                          const int64_t* __restrict__ moff, int ncols, double* __restrict__ Hp, int ldh,
                                                          int64_t hstride) {
   __shared__ double sh[DCOLS * P * 8];
   const int b = blockIdx.z, sl = blockIdx.y, c0 = blockIdx.x * DCOLS;
   const int64_t m0 = moff[b], mlen = moff[b + 1] - m0;
-  const int64_t chunk = (mlen + RSPLIT - 1) / RSPLIT;
+  const int64_t chunk = 2 * ((mlen / 2 + RSPLIT - 1) / RSPLIT);
   const int64_t i0 = m0 + sl * chunk, i1 = min(m0 + mlen, i0 + chunk);
   const int nc = min(DCOLS, ncols - c0);
   const double* q = Q + (int64_t)c0 * ld;
   double acc[DCOLS * P];
 #pragma unroll
   for (int a = 0; a < DCOLS * P; ++a) acc[a] = 0.0;
-  for (int64_t i = i0 + threadIdx.x; i < i1; i += 256) {
-    double rv[P], qv[DCOLS];
+  for (int64_t i = i0 + 2 * threadIdx.x; i < i1; i += 512) {
+    double2 rv[P], qv[DCOLS];
 #pragma unroll
-    for (int r = 0; r < P; ++r) rv[r] = R[r * ld + i];
+    for (int r = 0; r < P; ++r) rv[r] = *reinterpret_cast<const double2*>(R + r * ld + i);
 #pragma unroll
-    for (int c = 0; c < DCOLS; ++c) qv[c] = c < nc ? q[c * ld + i] : 0.0;
+    for (int c = 0; c < DCOLS; ++c) qv[c] = c < nc ? *reinterpret_cast<const double2*>(q + c * ld + i) : make_double2(0.0, 0.0);
 #pragma unroll
     for (int c = 0; c < DCOLS; ++c)
 #pragma unroll
-      for (int r = 0; r < P; ++r) acc[c * P + r] = fma(qv[c], rv[r], acc[c * P + r]);
+      for (int r = 0; r < P; ++r) acc[c * P + r] = fma(qv[c].y, rv[r].y, fma(qv[c].x, rv[r].x, acc[c * P + r]));
   }
   const double t = block_sum_n<DCOLS * P>(acc, sh);
   const int c = threadIdx.x / P, r = threadIdx.x % P;
@@ -333,24 +334,41 @@ __global__ void sum_slices_kernel(const double* __restrict__ Hp, int ldh, int64_
   }
 }
 
-// R_b[:, r] -= V_b[:, 0..ncols) H_b[:, r]
+// R_b[:, r] -= V_b[:, 0..ncols) H_b[:, r]; a thread owns a PAIR of rows (128-bit loads), the coefficients sit in shared memory
+constexpr int UPD_MAXC = 384;      // basis columns the shared copy of H holds (the basis has ncv + P <= 3 (n_modes + 12) + 8)
 __global__ void __launch_bounds__(256) update_block_kernel(const double* __restrict__ V, int64_t ld, const double* __restrict__ H,
                                                            int ldh, int64_t hstride, int ncols, const int64_t* __restrict__ moff,
                                                            double* __restrict__ R) {
+  __shared__ double sh[UPD_MAXC * P];     // [c][r]
   const int b = blockIdx.y;
-  const int64_t i = moff[b] + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= moff[b + 1]) return;
   const double* Hb = H + b * hstride;
-  double acc[P];
+  const int nsh = min(ncols, UPD_MAXC);
+  for (int t = threadIdx.x; t < nsh * P; t += 256) sh[t] = Hb[(t / P) + (t % P) * ldh];
+  __syncthreads();
+  const int64_t i = moff[b] + 2 * (blockIdx.x * (int64_t)blockDim.x + threadIdx.x);
+  if (i >= moff[b + 1]) return;
+  double2 acc[P];
 #pragma unroll
-  for (int r = 0; r < P; ++r) acc[r] = 0.0;
-  for (int c = 0; c < ncols; ++c) {
-    const double v = V[(int64_t)c * ld + i];
+  for (int r = 0; r < P; ++r) acc[r] = make_double2(0.0, 0.0);
+  int c = 0;
+#pragma unroll 8
+  for (; c < nsh; ++c) {
+    const double2 v = *reinterpret_cast<const double2*>(V + (int64_t)c * ld + i);
 #pragma unroll
-    for (int r = 0; r < P; ++r) acc[r] = fma(v, __ldg(Hb + c + r * ldh), acc[r]);
+    for (int r = 0; r < P; ++r) { const double h = sh[c * P + r]; acc[r].x = fma(v.x, h, acc[r].x); acc[r].y = fma(v.y, h, acc[r].y); }
+  }
+  for (; c < ncols; ++c) {           // beyond the shared copy (never with the basis sizes of this solver)
+    const double2 v = *reinterpret_cast<const double2*>(V + (int64_t)c * ld + i);
+#pragma unroll
+    for (int r = 0; r < P; ++r) { const double h = __ldg(Hb + c + r * ldh); acc[r].x = fma(v.x, h, acc[r].x); acc[r].y = fma(v.y, h, acc[r].y); }
   }
 #pragma unroll
-  for (int r = 0; r < P; ++r) R[r * ld + i] -= acc[r];
+  for (int r = 0; r < P; ++r) {
+    double2* p = reinterpret_cast<double2*>(R + r * ld + i);
+    double2 o = *p;
+    o.x -= acc[r].x; o.y -= acc[r].y;
+    *p = o;
+  }
 }
 
 // Hs_b[0..ncols, r] = h1 + h2 (the projected-matrix column block kept for the host)
@@ -801,6 +819,7 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
   cstat.alloc(ctx, B); cstat.zero();
   const unsigned gm = (unsigned)((m + 255) / 256);
   const dim3 grows((unsigned)((bd.mmax + 255) / 256), B);
+  const dim3 gpairs((unsigned)((bd.mmax / 2 + 255) / 256), B);      // kernels whose threads own a pair of rows
 
   // operator application on P right-hand sides, captured once into a CUDA graph: R = OP(opin)
   // Two versions: the accurate one (rsteps refinement steps) and a RELAXED one with one step fewer.  Inexact-Krylov
@@ -932,10 +951,10 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
     const dim3 gdots((nb + DCOLS - 1) / DCOLS, RSPLIT, B), gsum((nb + 127) / 128, B);
     dots_block_kernel<<<gdots, 256, 0, st>>>(BVc, ld, R.p, moff, nb, hp.p, ldh, hstride);          // CGS pass 1
     sum_slices_kernel<<<gsum, 128, 0, st>>>(hp.p, ldh, hstride, nb, h1.p);
-    update_block_kernel<<<grows, 256, 0, st>>>(Vc, ld, h1.p, ldh, hstride, nb, moff, R.p);
+    update_block_kernel<<<gpairs, 256, 0, st>>>(Vc, ld, h1.p, ldh, hstride, nb, moff, R.p);
     dots_block_kernel<<<gdots, 256, 0, st>>>(BVc, ld, R.p, moff, nb, hp.p, ldh, hstride);          // CGS pass 2
     sum_slices_kernel<<<gsum, 128, 0, st>>>(hp.p, ldh, hstride, nb, h2.p);
-    update_block_kernel<<<grows, 256, 0, st>>>(Vc, ld, h2.p, ldh, hstride, nb, moff, R.p);
+    update_block_kernel<<<gpairs, 256, 0, st>>>(Vc, ld, h2.p, ldh, hstride, nb, moff, R.p);
     store_h_kernel<<<gsum, 128, 0, st>>>(h1.p, h2.p, ldh, hstride, nb, Hs.p + (size_t)j0 * ldh, ldh, sstride);
     ctx->launches += 7;
     orthonormalize(Vc + (int64_t)nb * ld, BVc + (int64_t)nb * ld, j0 / P);

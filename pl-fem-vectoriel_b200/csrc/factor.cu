@@ -540,7 +540,7 @@ void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double
   if (nrhs != 1 && nrhs != SOLVE_NRHS) throw StatusError(PLFEM_ERR_INTERNAL, "unsupported number of right-hand sides");
   const bool pdl = use_pdl();
   const bool fused = use_fused_sweeps();
-  if (fused) reset_sweep_counters(ctx, D);     // forward and backward counters, before the first launch of the solve
+  reset_sweep_counters(ctx, D);                // forward and backward counters, before the first launch of the solve
   bool first = true;     // the first launch follows kernels that are not PDL-aware: plain launch
   if (D.st.n_subs > 0) {
     launch_stream_forward(ctx, D, b, z, nrhs, false);
@@ -561,13 +561,14 @@ void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double
 // false when that forward sweep has just cleared the dataflow counters (run_solve)
 void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs, bool reset_counters) {
   const bool pdl = use_pdl();
+  if (reset_counters) reset_sweep_counters(ctx, D);
   if (use_fused_sweeps()) {
-    if (reset_counters) reset_sweep_counters(ctx, D);
     launch_fused_backward(ctx, D, x, nrhs, pdl && !reset_counters);
   } else {
     for (int l = D.nlevels - 1; l >= 0; --l) {
       if (D.st.bptr[l] == D.st.bptr[l + 1]) continue;
-      launch_level_backward(ctx, D, l, x, nrhs, pdl);
+      launch_level_backward(ctx, D, l, x, nrhs, pdl && !reset_counters);
+      reset_counters = false;
     }
   }
   if (D.st.n_subs > 0) launch_stream_backward(ctx, D, x, nrhs, pdl);

@@ -127,6 +127,17 @@ struct PipeT {
 
 using Pipe = PipeT<NS>;
 
+// Optional stage clock of the dataflow forward sweep (PLFEM_TRACE_FILE, see profile_work in api.cu): eight %globaltimer
+// stamps per task.  A null pointer (always, outside that measurement) costs one uniform load per task.
+__device__ long long* g_sweep_trace = nullptr;
+__device__ __forceinline__ void trace_stamp(long long* tr, int ti, int stage, int lane) {
+  if (tr && lane == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    tr[(int64_t)ti * 8 + stage] = t;
+  }
+}
+
 template <int NR>
 struct StreamSmem {
   alignas(128) double ring[NS * CHD];
@@ -484,14 +495,14 @@ __global__ void __launch_bounds__(256) stream_pack_kernel(const StreamPackRec* _
 // prefetched too), FMAs against shared memory, one store.  The task sizes follow the front: small contraction ->
 // wide slabs, long contraction -> narrow slabs with the lanes split over the contraction index, so that a task stays
 // near the ring's capacity; fronts of the 2M-unknown regime get wide slabs again (fewer redundant gathers).
-constexpr int KX = 512;     // contraction entries staged per pass of a backward task
+constexpr int KSMAX = 256;  // contraction entries of a backward task (a slab of the update set)
 
 struct RhsView {            // interleaved vectors of a forward sweep: right-hand sides in, pivot solutions out, update pool
   const double* rhs; double* out; double* upd;
 };
 
 constexpr int NSF = 8;      // ring stages of a forward task (a 32 KB task is completely in flight before the dependency wait)
-constexpr int NSB = 6;      // ring stages of a backward task (its contraction vector takes 16 KB)
+constexpr int NSB = 6;      // ring stages of a backward task (its contraction vector takes 8 KB)
 using PipeF = PipeT<NSF>;
 using PipeB = PipeT<NSB>;
 
@@ -504,7 +515,7 @@ struct LevelFwdSmem {
 template <int NR>
 struct LevelBwdSmem {
   alignas(128) double ring[NSB * CHD];
-  alignas(16) double cv[KX * NR];                 // gathered x2 of the current pass
+  alignas(16) double cv[KSMAX * NR];              // gathered x2 of the task's slab of the update set
   alignas(8) uint64_t bar[NSB];
 };
 
@@ -592,11 +603,14 @@ __global__ void __launch_bounds__(32) level_forward_kernel(const LevelTask* __re
   // dataflow launch: tasks are handed out in level order by a ticket, so whatever a running task waits for belongs to a
   // task that has started before it — progress does not depend on the order in which the hardware dispatches CTAs
   int ti = blockIdx.x;
+  long long* const tr = FUSED ? g_sweep_trace : nullptr;
+  trace_stamp(tr, blockIdx.x, 0, lane);        // entry, by CTA index (the ticket is not known yet)
   if (FUSED) {
     if (lane == 0) ti = atomicAdd(sync, 1);
     ti = __shfl_sync(0xffffffffu, ti, 0);
   }
   const LevelTask t = tasks[ti];
+  trace_stamp(tr, ti, 1, lane);
   if (lane == 0) {
     for (int s = 0; s < NSF; ++s) mbar_init(sm.bar + s, 1);
     fence_mbar_init();
@@ -618,7 +632,9 @@ __global__ void __launch_bounds__(32) level_forward_kernel(const LevelTask* __re
     if (k < t.n && row >= t.s2) { j1[q] = g1[row]; j2[q] = g2[row]; }
   }
   if (PDL) griddep_wait();
+  trace_stamp(tr, ti, 2, lane);
   if (FUSED && t.need > 0) wait_counter(sync + 2 + t.dep, t.need, lane, status);     // the children's update vectors are complete
+  trace_stamp(tr, ti, 3, lane);
   // assembled pivot part of the right-hand sides, fixed order (rhs + first child) + second child
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -640,6 +656,7 @@ __global__ void __launch_bounds__(32) level_forward_kernel(const LevelTask* __re
     for (int r = 0; r < NR; ++r) sm.cv[k * NR + r] = v[r];
   }
   __syncwarp();
+  trace_stamp(tr, ti, 4, lane);
   if (t.nch > 2) {          // rare (a separator that does not disconnect): the further children, one after the other
     for (int c = cptr[t.f] + 2; c < cptr[t.f + 1]; ++c) {
       const int ch = child[c];
@@ -683,40 +700,19 @@ __global__ void __launch_bounds__(32) level_forward_kernel(const LevelTask* __re
       __syncwarp();
     }
   }
+  trace_stamp(tr, ti, 5, lane);
   if (FUSED && t.sig >= 0) signal_counter(sync + 2 + t.sig, lane);
+  trace_stamp(tr, ti, 6, lane);
   pp.drain();
+  trace_stamp(tr, ti, 7, lane);
 }
 
-// backward: G = 32 / W lanes share a pivot column (W = 8, 16: lanes split the contraction index), or R columns per lane (wide)
-template <int NR, int W>
-__device__ __forceinline__ void level_bwd_narrow(PipeB& pp, LevelBwdSmem<NR>& sm, int jn, double (&acc)[NR]) {
-  constexpr int G = 32 / W;
-  const int lane = pp.lane, jg = lane / W;
-  for (int j = 0; j < jn;) {
-    int n = (CHD - pp.pos) / W;                                  // items left in this chunk (a multiple of G by construction)
-    if (n == 0) { pp.advance(); continue; }
-    n = min(n, jn - j);
-    const double* base = pp.ring + (pp.cur % NSB) * CHD + pp.pos + lane;
-#pragma unroll 4
-    for (int c = 0; c < n; c += G) {
-      const bool ok = c + jg < n;
-      double x[NR];
-      ld_loc<NR>(sm.cv, ok ? j + c + jg : 0, x);
-      const double m = ok ? base[c * W] : 0.0;
-#pragma unroll
-      for (int r = 0; r < NR; ++r) acc[r] = fma(m, x[r], acc[r]);
-    }
-    pp.pos += ((n + G - 1) / G) * G * W; j += n;
-  }
-}
-
+// backward, one slab of the contraction: acc += W(slab, :)^T x2(slab); lanes over the pivot columns (R per lane)
 template <int NR, int R>
-__device__ __forceinline__ void level_bwd_wide(PipeB& pp, LevelBwdSmem<NR>& sm, const LevelTask& t, int jn, double (&acc)[4][NR],
-                                               const bool (&valid)[4]) {
+__device__ __forceinline__ void level_bwd_slab(PipeB& pp, LevelBwdSmem<NR>& sm, int s2p, int jn, double (&acc)[4][NR], const bool (&valid)[4]) {
   const int lane = pp.lane;
-  const int isz = (t.n + 3) & ~3;
   for (int j = 0; j < jn;) {
-    int n = (CHD - pp.pos) / isz;
+    int n = (CHD - pp.pos) / s2p;
     if (n == 0) { pp.advance(); continue; }
     n = min(n, jn - j);
     const double* base = pp.ring + (pp.cur % NSB) * CHD + pp.pos + lane;
@@ -726,18 +722,23 @@ __device__ __forceinline__ void level_bwd_wide(PipeB& pp, LevelBwdSmem<NR>& sm, 
       ld_loc<NR>(sm.cv, j + c, x);
 #pragma unroll
       for (int q = 0; q < R; ++q) {
-        const double m = valid[q] ? base[c * isz + 32 * q] : 0.0;
+        const double m = valid[q] ? base[c * s2p + 32 * q] : 0.0;
 #pragma unroll
         for (int r = 0; r < NR; ++r) acc[q][r] = fma(m, x[r], acc[q][r]);
       }
     }
-    pp.pos += n * isz; j += n;
+    pp.pos += n * s2p; j += n;
   }
 }
 
+// A backward task is a slab of the CONTRACTION: all pivot columns of a front against <= KSMAX of its update unknowns, so no
+// two tasks gather the same ancestors' values (the first version split the pivot columns: sixteen tasks of a front with
+// 3 800 update unknowns each gathered all of them, and each ran for 50 us).  The slabs of a front leave their partial sums in
+// `part`; whichever arrives last adds them IN SLAB ORDER (the result does not depend on who that is) and subtracts from z1.
 template <int NR, bool PDL, bool FUSED>
 __global__ void __launch_bounds__(32) level_backward_kernel(const LevelTask* __restrict__ tasks, const double* __restrict__ stream,
-                                                            const int32_t* __restrict__ strct, double* __restrict__ x, int32_t* status, int32_t* sync, int nfronts) {
+                                                            const int32_t* __restrict__ strct, double* __restrict__ x,
+                                                            double* __restrict__ part, int32_t* status, int32_t* sync, int nfronts) {
   __shared__ LevelBwdSmem<NR> sm;
   const int lane = threadIdx.x;
   if (PDL) griddep_launch_dependents();
@@ -754,82 +755,85 @@ __global__ void __launch_bounds__(32) level_backward_kernel(const LevelTask* __r
   __syncwarp();
   PipeB pp{sm.ring, sm.bar, stream + t.soff, status, t.chunks, -1, CHD, lane};
   pp.start();
+  const int k0 = t.r0, kn = t.n, nk = t.nch;   // this task's slab of the update unknowns; slabs of the front
   const int32_t* st = strct + t.goff;          // the front's update set
-  // static: positions of the first pass's update unknowns in the solution vector
-  constexpr int NG = KX / 32;
+  // static: positions of the slab's update unknowns in the solution vector
+  constexpr int NG = KSMAX / 32;
   int64_t xo[NG];
 #pragma unroll
   for (int q = 0; q < NG; ++q) {
     const int j = lane + 32 * q;
-    xo[q] = j < t.u2 ? 2 * (int64_t)st[j >> 1] + (j & 1) : -1;
+    xo[q] = j < kn ? 2 * (int64_t)st[(k0 + j) >> 1] + ((k0 + j) & 1) : -1;
   }
   if (PDL) griddep_wait();
   if (FUSED && t.need > 0) wait_counter(sync + 2 + nfronts + t.dep, t.need, lane, status);   // the parent's unknowns are final
-  const int W = t.nch;                          // slab class: 8, 16 (lanes split the contraction index) or 0 (wide)
-  double accn[NR];
-  double accw[4][NR];
+#pragma unroll
+  for (int q = 0; q < NG; ++q) {
+    if (xo[q] < 0) continue;
+    double v[NR];
+    ldcg_v<NR>(x, xo[q], v);
+#pragma unroll
+    for (int r = 0; r < NR; ++r) sm.cv[(lane + 32 * q) * NR + r] = v[r];
+  }
+  __syncwarp();
+  const int s2p = (t.s2 + 3) & ~3;
+  double acc[4][NR];
   bool valid[4];
 #pragma unroll
-  for (int r = 0; r < NR; ++r) accn[r] = 0.0;
-#pragma unroll
   for (int q = 0; q < 4; ++q) {
-    valid[q] = lane + 32 * q < t.n;
+    valid[q] = lane + 32 * q < t.s2;
 #pragma unroll
-    for (int r = 0; r < NR; ++r) accw[q][r] = 0.0;
+    for (int r = 0; r < NR; ++r) acc[q][r] = 0.0;
   }
-  const int Rw = (t.n + 31) >> 5;
-  for (int j0 = 0; j0 < t.u2; j0 += KX) {
-    const int jn = min(KX, t.u2 - j0);
-    if (j0 > 0) {
-      __syncwarp();
+  switch ((t.s2 + 31) >> 5) {
+    case 1: level_bwd_slab<NR, 1>(pp, sm, s2p, kn, acc, valid); break;
+    case 2: level_bwd_slab<NR, 2>(pp, sm, s2p, kn, acc, valid); break;
+    case 3: level_bwd_slab<NR, 3>(pp, sm, s2p, kn, acc, valid); break;
+    default: level_bwd_slab<NR, 4>(pp, sm, s2p, kn, acc, valid); break;
+  }
+  bool finish = true;
+  if (nk > 1) {
+    double* mine = part + ((int64_t)t.uoff + (int64_t)(k0 / t.pad[0]) * s2p) * NR;    // pad[0]: slab length of this front
 #pragma unroll
-      for (int q = 0; q < NG; ++q) {
-        const int j = j0 + lane + 32 * q;
-        xo[q] = j < t.u2 ? 2 * (int64_t)st[j >> 1] + (j & 1) : -1;
+    for (int q = 0; q < 4; ++q)
+      if (valid[q]) stg_v<NR>(mine, lane + 32 * q, acc[q]);
+    __threadfence();
+    __syncwarp();
+    int old = 0;
+    if (lane == 0) old = atomicAdd(sync + 2 + 2 * nfronts + t.f, 1);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    finish = (old == nk - 1);
+    if (finish) {
+      __threadfence();                          // the other slabs' partial sums are visible now
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int r = 0; r < NR; ++r) acc[q][r] = 0.0;
+      const double* all = part + (int64_t)t.uoff * NR;
+      for (int kk = 0; kk < nk; ++kk) {         // slab order, whoever finishes
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (!valid[q]) continue;
+          double w[NR];
+          ldcg_v<NR>(all, (int64_t)kk * s2p + lane + 32 * q, w);
+#pragma unroll
+          for (int r = 0; r < NR; ++r) acc[q][r] += w[r];
+        }
       }
     }
-#pragma unroll
-    for (int q = 0; q < NG; ++q) {
-      if (xo[q] < 0) continue;
-      double v[NR];
-      ldcg_v<NR>(x, xo[q], v);
-#pragma unroll
-      for (int r = 0; r < NR; ++r) sm.cv[(lane + 32 * q) * NR + r] = v[r];
-    }
-    __syncwarp();
-    if (W == 8) level_bwd_narrow<NR, 8>(pp, sm, jn, accn);
-    else if (W == 16) level_bwd_narrow<NR, 16>(pp, sm, jn, accn);
-    else if (Rw == 1) level_bwd_wide<NR, 1>(pp, sm, t, jn, accw, valid);
-    else if (Rw == 2) level_bwd_wide<NR, 2>(pp, sm, t, jn, accw, valid);
-    else if (Rw == 3) level_bwd_wide<NR, 3>(pp, sm, t, jn, accw, valid);
-    else level_bwd_wide<NR, 4>(pp, sm, t, jn, accw, valid);
   }
-  if (W == 8 || W == 16) {
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      double v = accn[r];
-      for (int off = 16; off >= W; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-      accn[r] = v;
-    }
-    if (lane < t.n) {       // t.n <= W: lanes 0..n-1 hold the totals of their columns
-      double z[NR];
-      ldg_v<NR>(x, t.g0 + t.r0 + lane, z);
-#pragma unroll
-      for (int r = 0; r < NR; ++r) z[r] -= accn[r];
-      stg_v<NR>(x, t.g0 + t.r0 + lane, z);
-    }
-  } else {
+  if (finish) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       if (!valid[q]) continue;
       double z[NR];
-      ldg_v<NR>(x, t.g0 + t.r0 + lane + 32 * q, z);
+      ldg_v<NR>(x, t.g0 + lane + 32 * q, z);
 #pragma unroll
-      for (int r = 0; r < NR; ++r) z[r] -= accw[q][r];
-      stg_v<NR>(x, t.g0 + t.r0 + lane + 32 * q, z);
+      for (int r = 0; r < NR; ++r) z[r] -= acc[q][r];
+      stg_v<NR>(x, t.g0 + lane + 32 * q, z);
     }
+    if (FUSED && t.sig >= 0) signal_counter(sync + 2 + nfronts + t.sig, lane);
   }
-  if (FUSED && t.sig >= 0) signal_counter(sync + 2 + nfronts + t.sig, lane);
   pp.drain();
 }
 
@@ -851,12 +855,12 @@ __global__ void __launch_bounds__(256) level_pack_kernel(const LevelTask* __rest
       dst[item_off(k, ldb) + i] = i < t.n ? src[k * ld + t.r0 + i] : 0.0;
     }
   } else {
-    const int isz = t.nch ? t.nch : ((t.n + 3) & ~3);
+    const int isz = (s2 + 3) & ~3, k0 = t.r0, kn = t.n;
     double* dst = lbwd + t.soff;
-    // W(j, c) = src[(c0 + c) * ld + s2 + j]: read with j fastest (coalesced), write item j, column c
-    for (int64_t idx = tid; idx < (int64_t)u2 * isz; idx += 256) {
-      const int c = (int)(idx / u2), j = (int)(idx - (int64_t)c * u2);
-      dst[item_off(j, isz) + c] = c < t.n ? src[(int64_t)(t.r0 + c) * ld + s2 + j] : 0.0;
+    // W(j, c) = src[c * ld + s2 + j]: read with j fastest (coalesced), write item j - k0, column c
+    for (int64_t idx = tid; idx < (int64_t)kn * isz; idx += 256) {
+      const int c = (int)(idx / kn), j = (int)(idx - (int64_t)c * kn);
+      dst[item_off(j, isz) + c] = c < s2 ? src[(int64_t)c * ld + s2 + k0 + j] : 0.0;
     }
   }
 }
@@ -953,22 +957,20 @@ void build_level_plan(plfem_ctx* ctx, const FrontPlan& P, const std::vector<int3
   S.nfronts = P.nfronts;
   // slab sizes depend on the front alone (a design's arithmetic is the same alone and inside a forest)
   auto fwd_rows = [](int s2) { return std::max(32, std::min(128, (4096 / s2) & ~31)); };
-  auto bwd_class = [](int u2, int& W, int& nc) {
-    if (u2 <= 128) { W = 0; nc = std::max(32, std::min(128, (4096 / u2) & ~31)); }
-    else if (u2 <= 256) { W = 16; nc = 16; }
-    else { W = 8; nc = 8; }
-  };
+  // backward: slabs of the contraction index of about 32 KB of W (all pivot columns x ks update unknowns)
+  auto bwd_ks = [](int s2) { return std::max(32, std::min(KSMAX, (4096 / ((s2 + 3) & ~3)) & ~31)); };
   std::vector<int32_t> nft(P.nfronts, 0), nbt(P.nfronts, 0);      // tasks per front
   for (int f = 0; f < P.nfronts; ++f) {
     if (in_sub[f]) continue;
     const int s2 = 2 * P.s[f], u2 = 2 * (P.sptr[f + 1] - P.sptr[f]);
     nft[f] = (s2 + u2 + fwd_rows(s2) - 1) / fwd_rows(s2);
-    if (u2 > 0) { int W, nc; bwd_class(u2, W, nc); nbt[f] = (s2 + nc - 1) / nc; }
+    if (u2 > 0) nbt[f] = (u2 + bwd_ks(s2) - 1) / bwd_ks(s2);
   }
   std::vector<int32_t> fneed(P.nfronts, 0);                        // forward: tasks of the children above the subtrees
   for (int f = 0; f < P.nfronts; ++f)
     if (!in_sub[f] && P.parent[f] >= 0) fneed[P.parent[f]] += nft[f];
   int64_t fo = 0, bo = 0;     // chunks
+  int64_t po = 0;             // partial sums of the backward slabs (vector entries)
   for (int l = 0; l < P.nlevels; ++l) {
     for (int q = P.lptr[l]; q < P.lptr[l + 1]; ++q) {
       const int f = P.lfront[q];
@@ -998,16 +1000,19 @@ void build_level_plan(plfem_ctx* ctx, const FrontPlan& P, const std::vector<int3
       if (u2 == 0) continue;
       LevelTask t{};
       t.g0 = 2 * (int64_t)P.first[f]; t.s2 = s2; t.u2 = u2; t.f = f;
-      // backward: slabs of pivot columns; the longer the contraction (u2), the narrower the slab, down to 8 columns with the
-      // lanes split four ways over the contraction index
-      int W, nc;
-      bwd_class(u2, W, nc);
-      t.goff = P.sptr[f]; t.uoff = 0; t.nch = W;
+      // backward: one task per slab of the update set; a front with several slabs owns nk x s2p partial sums in `part`
+      const int ks = bwd_ks(s2), nk = nbt[f], s2p = (s2 + 3) & ~3;
+      t.goff = P.sptr[f]; t.nch = nk; t.pad[0] = ks;
+      t.uoff = (int32_t)po;
+      if (nk > 1) po += (int64_t)nk * s2p;
+      if (po > INT32_MAX) throw StatusError(PLFEM_ERR_INVALID, "backward partial sums exceed the 32-bit offsets of the task records");
       const int par = P.parent[f];
-      t.dep = par; t.need = par >= 0 ? nbt[par] : 0; t.sig = f;   // a root above (no update set) has no tasks: nothing to wait for
-      for (int c0 = 0; c0 < s2; c0 += nc) {
-        t.r0 = c0; t.n = std::min(nc, s2 - c0);
-        t.chunks = item_chunks(u2, W ? W : ((t.n + 3) & ~3));
+      // exactly ONE signal per front (its single task, or whichever slab finishes): a child waits for 1; a root above has no
+      // update set and no tasks — nothing to wait for
+      t.dep = par; t.need = (par >= 0 && nbt[par] > 0) ? 1 : 0; t.sig = f;
+      for (int k0 = 0; k0 < u2; k0 += ks) {
+        t.r0 = k0; t.n = std::min(ks, u2 - k0);
+        t.chunks = item_chunks(t.n, s2p);
         t.soff = bo * CHD; bo += t.chunks;
         bt.push_back(t);
       }
@@ -1018,7 +1023,8 @@ void build_level_plan(plfem_ctx* ctx, const FrontPlan& P, const std::vector<int3
   S.ftasks.upload(ctx, ft); S.btasks.upload(ctx, bt);
   S.lfwd.alloc(ctx, (size_t)std::max<int64_t>(fo, 1) * CHD); S.lbwd.alloc(ctx, (size_t)std::max<int64_t>(bo, 1) * CHD);
   S.lfwd_doubles = fo * CHD; S.lbwd_doubles = bo * CHD;
-  S.sync.alloc(ctx, 2 + 2 * (size_t)P.nfronts);
+  S.sync.alloc(ctx, 2 + 3 * (size_t)P.nfronts);
+  S.bpart.alloc(ctx, (size_t)std::max<int64_t>(po, 1) * SOLVE_NRHS);
   PLFEM_CUDA(stream_wait(ctx->stream));       // the host vectors above are pageable and local
 }
 
@@ -1073,11 +1079,11 @@ template <bool FUSED>
 void launch_backward_tasks(plfem_ctx* ctx, const DevPlan& D, const LevelTask* tasks, int n, double* x, int nrhs, bool pdl) {
   const StreamPlan& S = D.st;
   if (nrhs == 1) {
-    if (pdl) launch_warp_ctas(level_backward_kernel<1, true, FUSED>, true, n, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, D.status.p, S.sync.p, S.nfronts);
-    else launch_warp_ctas(level_backward_kernel<1, false, FUSED>, false, n, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, D.status.p, S.sync.p, S.nfronts);
+    if (pdl) launch_warp_ctas(level_backward_kernel<1, true, FUSED>, true, n, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts);
+    else launch_warp_ctas(level_backward_kernel<1, false, FUSED>, false, n, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts);
   } else {
-    if (pdl) launch_warp_ctas(level_backward_kernel<SOLVE_NRHS, true, FUSED>, true, n, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, D.status.p, S.sync.p, S.nfronts);
-    else launch_warp_ctas(level_backward_kernel<SOLVE_NRHS, false, FUSED>, false, n, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, D.status.p, S.sync.p, S.nfronts);
+    if (pdl) launch_warp_ctas(level_backward_kernel<SOLVE_NRHS, true, FUSED>, true, n, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts);
+    else launch_warp_ctas(level_backward_kernel<SOLVE_NRHS, false, FUSED>, false, n, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts);
   }
   ctx->launches++;
 }
@@ -1105,6 +1111,8 @@ void launch_level_backward(plfem_ctx* ctx, const DevPlan& D, int level, double* 
   const StreamPlan& S = D.st;
   launch_backward_tasks<false>(ctx, D, S.btasks.p + S.bptr[level + 1], S.bptr[level] - S.bptr[level + 1], x, nrhs, pdl);
 }
+
+void set_sweep_trace(long long* p) { PLFEM_CUDA(cudaMemcpyToSymbol(g_sweep_trace, &p, sizeof(p))); }
 
 void reset_sweep_counters(plfem_ctx* ctx, const DevPlan& D) {
   if (D.st.sync.n) PLFEM_CUDA(cudaMemsetAsync(D.st.sync.p, 0, D.st.sync.n * sizeof(int32_t), ctx->stream));
