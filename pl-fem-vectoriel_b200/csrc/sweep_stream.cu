@@ -180,6 +180,42 @@ __device__ __forceinline__ void ldcg_v(const double* base, int64_t idx, double (
     for (int r = 0; r < NR; ++r) v[r] = __ldcg(base + idx * NR + r);
   }
 }
+// predicated vector load: zeros when idx < 0.  Written so that a run of them compiles into loads issued back to back — ONE
+// memory round trip for the batch instead of one per load (measured with the stage clock: the chained version spent
+// 2.5-4 us gathering and 1.6 us more before the first FMA of every task)
+template <int NR>
+__device__ __forceinline__ void ldcg_opt(const double* base, int64_t idx, double (&v)[NR]) {
+  const bool ok = idx >= 0;
+  if constexpr (NR % 2 == 0) {
+    const double2* p = reinterpret_cast<const double2*>(base + (ok ? idx : 0) * NR);
+#pragma unroll
+    for (int r = 0; r < NR / 2; ++r) {
+      double2 t = make_double2(0.0, 0.0);
+      if (ok) t = __ldcg(p + r);
+      v[2 * r] = t.x; v[2 * r + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) v[r] = ok ? __ldcg(base + idx * NR + r) : 0.0;
+  }
+}
+
+// n consecutive vectors src[g0 ..) into shared memory, four loads of a lane in flight at a time
+template <int NR>
+__device__ __forceinline__ void load_run(const double* src, int64_t g0, int n, double* dst, int lane) {
+  for (int i0 = 0; i0 < n; i0 += 128) {
+    double v[4][NR];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const int i = i0 + lane + 32 * q; ldcg_opt<NR>(src, i < n ? g0 + i : -1, v[q]); }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = i0 + lane + 32 * q;
+      if (i >= n) continue;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) dst[i * NR + r] = v[q][r];
+    }
+  }
+}
 __device__ __forceinline__ int ld_acquire(const int32_t* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -215,6 +251,61 @@ __device__ __forceinline__ void stg_v(double* base, int64_t idx, const double (&
   }
 }
 
+// The multiply of every sweep task: acc(row, rhs) += panel(row, c) * y(c, rhs) over n columns of a chunk in shared memory.
+// A lane's FMAs on one accumulator are a dependent chain, and the FP64 pipe of this part returns a result only after tens of
+// cycles (stage clock: 36 ns per column with one accumulator set, whatever the row count): the columns are dealt round-robin
+// to U accumulator sets, added pairwise at the end (the order is fixed by the task's layout, so results stay reproducible).
+template <int R> struct AccSets { static constexpr int U = R == 1 ? 4 : 2; };
+
+template <int NR, int R, int U, class YF>
+__device__ __forceinline__ void fma_columns(const double* __restrict__ base, int ld, int n, const bool (&valid)[R], YF&& yf,
+                                            double (&acc)[U][R][NR]) {
+  int c = 0;
+#pragma unroll 2
+  for (; c + U <= n; c += U) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      double y[NR];
+      yf(c + u, y);
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        const double m = valid[q] ? base[(c + u) * ld + 32 * q] : 0.0;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) acc[u][q][r] = fma(m, y[r], acc[u][q][r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U - 1; ++u) {
+    if (c + u >= n) break;
+    double y[NR];
+    yf(c + u, y);
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      const double m = valid[q] ? base[(c + u) * ld + 32 * q] : 0.0;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) acc[u][q][r] = fma(m, y[r], acc[u][q][r]);
+    }
+  }
+}
+template <int NR, int R, int U>
+__device__ __forceinline__ void zero_sets(double (&acc)[U][R][NR]) {
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+#pragma unroll
+    for (int q = 0; q < R; ++q)
+#pragma unroll
+      for (int r = 0; r < NR; ++r) acc[u][q][r] = 0.0;
+}
+template <int NR, int R, int U>
+__device__ __forceinline__ void fold_sets(const double (&acc)[U][R][NR], int q, double (&out)[NR]) {
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    if constexpr (U == 4) out[r] = (acc[0][q][r] + acc[1][q][r]) + (acc[2][q][r] + acc[3][q][r]);
+    else out[r] = acc[0][q][r] + acc[1][q][r];
+  }
+}
+
 // forward, one row block (<= 128 rows, R per lane) of one front: acc = block * y1, y1 = loc[p0 ..) in place
 template <int NR, int R>
 __device__ __forceinline__ void fwd_block(Pipe& pp, StreamSmem<NR>& sm, int s2, int p0, int r0, int nrb, double* __restrict__ out,
@@ -224,41 +315,31 @@ __device__ __forceinline__ void fwd_block(Pipe& pp, StreamSmem<NR>& sm, int s2, 
   bool valid[R];
 #pragma unroll
   for (int q = 0; q < R; ++q) valid[q] = lane + 32 * q < nrb;
-  double acc[R][NR];
-#pragma unroll
-  for (int q = 0; q < R; ++q)
-#pragma unroll
-    for (int r = 0; r < NR; ++r) acc[q][r] = 0.0;
+  constexpr int U = AccSets<R>::U;
+  double accs[U][R][NR];
+  zero_sets<NR, R, U>(accs);
   for (int k = 0; k < s2;) {
     int n = (CHD - pp.pos) / ld;
     if (n == 0) { pp.advance(); continue; }
     n = min(n, s2 - k);
     const double* base = pp.ring + (pp.cur % NS) * CHD + pp.pos + lane;
     const double* yv = sm.loc + (p0 + k) * NR;
-#pragma unroll 4
-    for (int c = 0; c < n; ++c) {
-      double y[NR];
-      ld_loc<NR>(yv, c, y);
-#pragma unroll
-      for (int q = 0; q < R; ++q) {
-        const double m = valid[q] ? base[c * ld + 32 * q] : 0.0;
-#pragma unroll
-        for (int r = 0; r < NR; ++r) acc[q][r] = fma(m, y[r], acc[q][r]);
-      }
-    }
+    fma_columns<NR, R, U>(base, ld, n, valid, [&](int c, double (&y)[NR]) { ld_loc<NR>(yv, c, y); }, accs);
     pp.pos += n * ld; k += n;
   }
 #pragma unroll
   for (int q = 0; q < R; ++q) {
     if (!valid[q]) continue;
+    double acc[1][NR];
+    fold_sets<NR, R, U>(accs, q, acc[0]);
     const int row = r0 + lane + 32 * q;
     if (row < s2) {
-      stg_v<NR>(out, gpiv + row, acc[q]);                        // z1 = F11^-1 y1
+      stg_v<NR>(out, gpiv + row, acc[0]);                        // z1 = F11^-1 y1
     } else {
       const int j = row - s2;
       double* t = sm.loc + (2 * (int)sm.lm[j >> 1] + (j & 1)) * NR;   // the ancestor's local position: y -= W^T y1
 #pragma unroll
-      for (int r = 0; r < NR; ++r) t[r] -= acc[q][r];
+      for (int r = 0; r < NR; ++r) t[r] -= acc[0][r];
     }
   }
 }
@@ -282,17 +363,10 @@ __global__ void __launch_bounds__(32) stream_forward_kernel(const StreamSub* __r
   if (lane < sb.nfronts) fd = fronts[sb.front0 + lane];
   if (PDL) griddep_wait();
   // local vector: right-hand side of the subtree's pivots, zeros for the root's update set
-  for (int i = lane; i < sb.nI + sb.next; i += 32) {
-    double v[NR];
-    if (i < sb.nI) {
-      ldg_v<NR>(rhs, (int64_t)sb.g0 + i, v);
-    } else {
+  load_run<NR>(rhs, sb.g0, sb.nI, sm.loc, lane);
+  for (int i = sb.nI + lane; i < sb.nI + sb.next; i += 32)
 #pragma unroll
-      for (int r = 0; r < NR; ++r) v[r] = 0.0;
-    }
-#pragma unroll
-    for (int r = 0; r < NR; ++r) sm.loc[i * NR + r] = v[r];
-  }
+    for (int r = 0; r < NR; ++r) sm.loc[i * NR + r] = 0.0;
   __syncwarp();
   for (int i = 0; i < sb.nfronts; ++i) {
     const int su = __shfl_sync(0xffffffffu, fd.x, i), p0 = __shfl_sync(0xffffffffu, fd.y, i);
@@ -331,36 +405,28 @@ __device__ __forceinline__ void bwd_front(Pipe& pp, StreamSmem<NR>& sm, int s2, 
   bool valid[R];
 #pragma unroll
   for (int q = 0; q < R; ++q) valid[q] = lane + 32 * q < s2;
-  double acc[R][NR];
-#pragma unroll
-  for (int q = 0; q < R; ++q)
-#pragma unroll
-    for (int r = 0; r < NR; ++r) acc[q][r] = 0.0;
+  constexpr int U = AccSets<R>::U;
+  double accs[U][R][NR];
+  zero_sets<NR, R, U>(accs);
   for (int j = 0; j < u2;) {
     int n = (CHD - pp.pos) / s2p;
     if (n == 0) { pp.advance(); continue; }
     n = min(n, u2 - j);
     const double* base = pp.ring + (pp.cur % NS) * CHD + pp.pos + lane;
-#pragma unroll 4
-    for (int c = 0; c < n; ++c) {
+    fma_columns<NR, R, U>(base, s2p, n, valid, [&](int c, double (&x)[NR]) {
       const int jj = j + c;
-      double x[NR];
       ld_loc<NR>(sm.loc, 2 * (int)sm.lm[jj >> 1] + (jj & 1), x);
-#pragma unroll
-      for (int q = 0; q < R; ++q) {
-        const double m = valid[q] ? base[c * s2p + 32 * q] : 0.0;
-#pragma unroll
-        for (int r = 0; r < NR; ++r) acc[q][r] = fma(m, x[r], acc[q][r]);
-      }
-    }
+    }, accs);
     pp.pos += n * s2p; j += n;
   }
 #pragma unroll
   for (int q = 0; q < R; ++q) {
     if (!valid[q]) continue;
+    double a[NR];
+    fold_sets<NR, R, U>(accs, q, a);
     double* t = sm.loc + (p0 + lane + 32 * q) * NR;
 #pragma unroll
-    for (int r = 0; r < NR; ++r) t[r] -= acc[q][r];
+    for (int r = 0; r < NR; ++r) t[r] -= a[r];
   }
 }
 
@@ -390,20 +456,21 @@ __global__ void __launch_bounds__(32) stream_backward_kernel(const StreamSub* __
     xo[t] = e < sb.next ? 2 * (int64_t)strct[sb.soff + (e >> 1)] + (e & 1) : -1;
   }
   if (PDL) griddep_wait();
-  for (int i = lane; i < sb.nI; i += 32) {                        // z of the subtree's pivots (forward sweep)
-    double v[NR];
-    ldg_v<NR>(x, (int64_t)sb.g0 + i, v);
+  load_run<NR>(x, sb.g0, sb.nI, sm.loc, lane);                    // z of the subtree's pivots (forward sweep)
+  constexpr int NEH = (NE + 1) / 2;                               // x of the ancestors above the subtree (final): two batches
 #pragma unroll
-    for (int r = 0; r < NR; ++r) sm.loc[i * NR + r] = v[r];
-  }
+  for (int h = 0; h < 2; ++h) {
+    double v[NEH][NR];
 #pragma unroll
-  for (int t = 0; t < NE; ++t) {                                  // x of the ancestors above the subtree (final)
-    if (xo[t] < 0) continue;
-    double v[NR];
-    ldg_v<NR>(x, xo[t], v);
-    const int e = lane + 32 * t;
+    for (int t = 0; t < NEH; ++t) ldcg_opt<NR>(x, h * NEH + t < NE ? xo[(h * NEH + t) % NE] : -1, v[t]);
 #pragma unroll
-    for (int r = 0; r < NR; ++r) sm.loc[(sb.nI + e) * NR + r] = v[r];
+    for (int t = 0; t < NEH; ++t) {
+      const int tt = h * NEH + t;
+      if (tt >= NE || xo[tt % NE] < 0) continue;
+      const int e = lane + 32 * tt;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) sm.loc[(sb.nI + e) * NR + r] = v[t][r];
+    }
   }
   __syncwarp();
   for (int i = sb.nfronts - 1; i >= 0; --i) {                     // the root first
@@ -526,29 +593,9 @@ __host__ __device__ inline int64_t item_off(int i, int sz) {
 }
 __host__ __device__ inline int item_chunks(int n, int sz) { return n == 0 ? 0 : (n + CHD / sz - 1) / (CHD / sz); }
 
-// predicated vector load: zeros when idx < 0.  Written so that a run of them compiles into loads issued back to back — ONE
-// memory round trip for the batch instead of one per load (measured with the stage clock: the chained version spent
-// 2.5-4 us gathering and 1.6 us more before the first FMA of every task)
-template <int NR>
-__device__ __forceinline__ void ldcg_opt(const double* base, int64_t idx, double (&v)[NR]) {
-  const bool ok = idx >= 0;
-  if constexpr (NR % 2 == 0) {
-    const double2* p = reinterpret_cast<const double2*>(base + (ok ? idx : 0) * NR);
-#pragma unroll
-    for (int r = 0; r < NR / 2; ++r) {
-      double2 t = make_double2(0.0, 0.0);
-      if (ok) t = __ldcg(p + r);
-      v[2 * r] = t.x; v[2 * r + 1] = t.y;
-    }
-  } else {
-#pragma unroll
-    for (int r = 0; r < NR; ++r) v[r] = ok ? __ldcg(base + idx * NR + r) : 0.0;
-  }
-}
-
 template <int NR, int R>
 __device__ __forceinline__ void level_fwd_rows(PipeF& pp, LevelFwdSmem<NR>& sm, const LevelTask& t, const int (&j1)[4], const int (&j2)[4],
-                                               const RhsView& rv) {
+                                               const RhsView& rv, long long* tr, int ti) {
   const int lane = pp.lane;
   const int ld = (t.n + 3) & ~3;
   bool valid[R];
@@ -558,40 +605,31 @@ __device__ __forceinline__ void level_fwd_rows(PipeF& pp, LevelFwdSmem<NR>& sm, 
   double y1[R][NR], y2[R][NR];
 #pragma unroll
   for (int q = 0; q < R; ++q) { ldcg_opt<NR>(rv.upd, j1[q], y1[q]); ldcg_opt<NR>(rv.upd, j2[q], y2[q]); }
-  double acc[R][NR];
-#pragma unroll
-  for (int q = 0; q < R; ++q)
-#pragma unroll
-    for (int r = 0; r < NR; ++r) acc[q][r] = 0.0;
+  constexpr int U = AccSets<R>::U;
+  double accs[U][R][NR];
+  zero_sets<NR, R, U>(accs);
   for (int k = 0; k < t.s2;) {
     int n = (CHD - pp.pos) / ld;
-    if (n == 0) { pp.advance(); continue; }
+    if (n == 0) { pp.advance(); if (pp.cur == 0) trace_stamp(tr, ti, 0, lane); continue; }
     n = min(n, t.s2 - k);
     const double* base = pp.ring + (pp.cur % NSF) * CHD + pp.pos + lane;
     const double* yv = sm.cv + k * NR;
-#pragma unroll 4
-    for (int c = 0; c < n; ++c) {
-      double y[NR];
-      ld_loc<NR>(yv, c, y);
-#pragma unroll
-      for (int q = 0; q < R; ++q) {
-        const double m = valid[q] ? base[c * ld + 32 * q] : 0.0;
-#pragma unroll
-        for (int r = 0; r < NR; ++r) acc[q][r] = fma(m, y[r], acc[q][r]);
-      }
-    }
+    fma_columns<NR, R, U>(base, ld, n, valid, [&](int c, double (&y)[NR]) { ld_loc<NR>(yv, c, y); }, accs);
     pp.pos += n * ld; k += n;
   }
+  trace_stamp(tr, ti, 7, lane);
 #pragma unroll
   for (int q = 0; q < R; ++q) {
     if (!valid[q]) continue;
     const int row = t.r0 + lane + 32 * q;
+    double a[NR];
+    fold_sets<NR, R, U>(accs, q, a);
     if (row < t.s2) {
-      stg_v<NR>(rv.out, t.g0 + row, acc[q]);
+      stg_v<NR>(rv.out, t.g0 + row, a);
     } else {
       double o[NR];
 #pragma unroll
-      for (int r = 0; r < NR; ++r) o[r] = (y1[q][r] + y2[q][r]) - acc[q][r];      // first child, second child (fixed order)
+      for (int r = 0; r < NR; ++r) o[r] = (y1[q][r] + y2[q][r]) - a[r];      // first child, second child (fixed order)
       stg_v<NR>(rv.upd, (int64_t)t.uoff + (row - t.s2), o);
     }
   }
@@ -610,7 +648,6 @@ __global__ void __launch_bounds__(32) level_forward_kernel(const LevelTask* __re
   // task that has started before it — progress does not depend on the order in which the hardware dispatches CTAs
   int ti = blockIdx.x;
   long long* const tr = FUSED ? g_sweep_trace : nullptr;
-  trace_stamp(tr, blockIdx.x, 0, lane);        // entry, by CTA index (the ticket is not known yet)
   if (FUSED) {
     if (lane == 0) ti = atomicAdd(sync, 1);
     ti = __shfl_sync(0xffffffffu, ti, 0);
@@ -687,10 +724,10 @@ __global__ void __launch_bounds__(32) level_forward_kernel(const LevelTask* __re
     }
   }
   switch ((t.n + 31) >> 5) {
-    case 1: level_fwd_rows<NR, 1>(pp, sm, t, j1, j2, rv); break;
-    case 2: level_fwd_rows<NR, 2>(pp, sm, t, j1, j2, rv); break;
-    case 3: level_fwd_rows<NR, 3>(pp, sm, t, j1, j2, rv); break;
-    default: level_fwd_rows<NR, 4>(pp, sm, t, j1, j2, rv); break;
+    case 1: level_fwd_rows<NR, 1>(pp, sm, t, j1, j2, rv, tr, ti); break;
+    case 2: level_fwd_rows<NR, 2>(pp, sm, t, j1, j2, rv, tr, ti); break;
+    case 3: level_fwd_rows<NR, 3>(pp, sm, t, j1, j2, rv, tr, ti); break;
+    default: level_fwd_rows<NR, 4>(pp, sm, t, j1, j2, rv, tr, ti); break;
   }
   if (t.nch > 2) {          // update rows of this task: contributions of the further children (after the first two, fixed order)
     __syncwarp();
@@ -716,31 +753,28 @@ __global__ void __launch_bounds__(32) level_forward_kernel(const LevelTask* __re
   if (FUSED && t.sig >= 0) signal_counter(sync + 2 + t.sig, lane);
   trace_stamp(tr, ti, 6, lane);
   pp.drain();
-  trace_stamp(tr, ti, 7, lane);
 }
 
 // backward, one slab of the contraction: acc += W(slab, :)^T x2(slab); lanes over the pivot columns (R per lane)
 template <int NR, int R>
-__device__ __forceinline__ void level_bwd_slab(PipeB& pp, LevelBwdSmem<NR>& sm, int s2p, int jn, double (&acc)[4][NR], const bool (&valid)[4]) {
+__device__ __forceinline__ void level_bwd_slab(PipeB& pp, LevelBwdSmem<NR>& sm, int s2p, int jn, double (&acc)[4][NR], const bool (&valid4)[4]) {
   const int lane = pp.lane;
+  constexpr int U = AccSets<R>::U;
+  bool valid[R];
+#pragma unroll
+  for (int q = 0; q < R; ++q) valid[q] = valid4[q];
+  double accs[U][R][NR];
+  zero_sets<NR, R, U>(accs);
   for (int j = 0; j < jn;) {
     int n = (CHD - pp.pos) / s2p;
     if (n == 0) { pp.advance(); continue; }
     n = min(n, jn - j);
     const double* base = pp.ring + (pp.cur % NSB) * CHD + pp.pos + lane;
-#pragma unroll 4
-    for (int c = 0; c < n; ++c) {
-      double x[NR];
-      ld_loc<NR>(sm.cv, j + c, x);
-#pragma unroll
-      for (int q = 0; q < R; ++q) {
-        const double m = valid[q] ? base[c * s2p + 32 * q] : 0.0;
-#pragma unroll
-        for (int r = 0; r < NR; ++r) acc[q][r] = fma(m, x[r], acc[q][r]);
-      }
-    }
+    fma_columns<NR, R, U>(base, s2p, n, valid, [&](int c, double (&x)[NR]) { ld_loc<NR>(sm.cv, j + c, x); }, accs);
     pp.pos += n * s2p; j += n;
   }
+#pragma unroll
+  for (int q = 0; q < R; ++q) fold_sets<NR, R, U>(accs, q, acc[q]);
 }
 
 // A backward task is a slab of the CONTRACTION: all pivot columns of a front against <= KSMAX of its update unknowns, so no

@@ -1,6 +1,5 @@
 #!/bin/bash
 O=gpurun_out; mkdir -p $O
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > $O/smi.txt 2>&1
 timeout 1500 python -m pytest tests -m gpu -x -q --durations=5 > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_gpu.log
 PLFEM_TRACE_FILE=$O/trace_cfg1.bin timeout 300 python scripts/gpu_sweep_profile.py cfg1 12 > $O/trace_cfg1.log 2>&1; echo "trace cfg1 rc=$?"
 python scripts/sweep_trace.py $O/trace_cfg1.bin > $O/trace_cfg1.txt 2>&1
