@@ -552,350 +552,291 @@ __global__ void __launch_bounds__(256) stream_pack_kernel(const StreamPackRec* _
 }
 
 // ================================================================================================================
-// Fronts ABOVE the bottom subtrees: one launch per elimination-tree level, one warp (a 32-thread CTA) per task.
+// Fronts ABOVE the bottom subtrees: tasks of FOUR warps (a 128-thread CTA), one thread per row (forward) or per pivot
+// column (backward).
 //
-// A forward task is a slab of <= 128 rows of a front's left block column [F11^-1 ; W^T], a backward task a slab of
-// pivot columns of W.  Both were laid out at pack time as their own chunk-aligned stream (uniform items: panel columns
-// of the slab / rows of the W slab), so the warp starts its bulk copies before the kernel's dependency wait — a task of
-// up to NS chunks is completely in flight while the previous level is still running — and the critical path of a level
-// is: one gather of freshly written values (children's update vectors / ancestors' unknowns; their indices were
-// prefetched too), FMAs against shared memory, one store.  The task sizes follow the front: small contraction ->
-// wide slabs, long contraction -> narrow slabs with the lanes split over the contraction index, so that a task stays
-// near the ring's capacity; fronts of the 2M-unknown regime get wide slabs again (fewer redundant gathers).
+// Why four warps: one warp of this part issues an FP64 FMA (or a shared load) only every 4-5 cycles, whatever the number of
+// independent accumulators (scripts/micro/panel_fma.cu: 26 cycles per panel column with 32 rows, 65-75 with 128 rows), so
+// a one-warp task of 32 KB spent 4-5 us in its multiply — more than in all its memory round trips together (stage clock,
+// scripts/sweep_trace.py) — and held 170 registers per thread for its 4 x 4 accumulators, which capped an SM at 11 warps.
+// Here every thread owns ONE row: a forward task is a slab of <= 128 rows of a front's left block column
+// [F11^-1 ; W^T], a backward task a slab of <= 128 ... 256 update unknowns against all pivot columns of W; warp w streams
+// its own quarter (rows / pivot columns 32 w ...) from its own chunk-aligned sub-stream through its own ring of bulk copies
+// (started before the dependency wait), the four warps share only the assembled contraction vector, and the task takes a
+// quarter of the time with half the registers (24 warps per SM).
+// Backward tasks split the CONTRACTION: no two tasks gather the same ancestors' values (the first version split the pivot
+// columns: sixteen tasks of a front with 3 800 update unknowns each gathered all of them, and each ran for 50 us).  The slabs
+// of a front leave partial sums in `part`; whichever arrives last adds them IN SLAB ORDER — the result does not depend on
+// who that is — and subtracts from z1.
 constexpr int KSMAX = 256;  // contraction entries of a backward task (a slab of the update set)
+constexpr int TW = 4;       // warps per task
+constexpr int NSW = 2;      // ring stages per warp: 8 KB in flight per warp, 32 KB per task
 
 struct RhsView {            // interleaved vectors of a forward sweep: right-hand sides in, pivot solutions out, update pool
   const double* rhs; double* out; double* upd;
 };
 
-constexpr int NSF = 4;      // ring stages of a forward task: 16 KB in flight, the rest streams while the first chunks are multiplied (11 tasks per SM)
-constexpr int NSB = 4;      // ring stages of a backward task (its contraction vector takes 8 KB: 9 tasks per SM)
-using PipeF = PipeT<NSF>;
-using PipeB = PipeT<NSB>;
+using PipeW = PipeT<NSW>;
 
 template <int NR>
 struct LevelFwdSmem {
-  alignas(128) double ring[NSF * CHD];
+  alignas(128) double ring[TW][NSW * CHD];
   alignas(16) double cv[MAX_PIV_UNKNOWNS * NR];   // assembled pivot part of the right-hand sides
-  alignas(8) uint64_t bar[NSF];
+  alignas(8) uint64_t bar[TW][NSW];
+  int ticket;
 };
 template <int NR>
 struct LevelBwdSmem {
-  alignas(128) double ring[NSB * CHD];
+  alignas(128) double ring[TW][NSW * CHD];
   alignas(16) double cv[KSMAX * NR];              // gathered x2 of the task's slab of the update set
-  alignas(8) uint64_t bar[NSB];
+  alignas(8) uint64_t bar[TW][NSW];
+  int ticket, last;
 };
 
-// uniform items of size sz, starting chunk-aligned: item i of the task's stream
+// uniform items of size sz, starting chunk-aligned: item i of a sub-stream
 __host__ __device__ inline int64_t item_off(int i, int sz) {
   const int per = CHD / sz;
   return (int64_t)(i / per) * CHD + (i % per) * sz;
 }
 __host__ __device__ inline int item_chunks(int n, int sz) { return n == 0 ? 0 : (n + CHD / sz - 1) / (CHD / sz); }
 
-template <int NR, int R>
-__device__ __forceinline__ void level_fwd_rows(PipeF& pp, LevelFwdSmem<NR>& sm, const LevelTask& t, const int (&j1)[4], const int (&j2)[4],
-                                               const RhsView& rv, long long* tr, int ti) {
-  const int lane = pp.lane;
-  const int ld = (t.n + 3) & ~3;
-  bool valid[R];
-#pragma unroll
-  for (int q = 0; q < R; ++q) valid[q] = lane + 32 * q < t.n;
-  // what the children send to this task's update rows: requested now, used after the panel has been multiplied
-  double y1[R][NR], y2[R][NR];
-#pragma unroll
-  for (int q = 0; q < R; ++q) { ldcg_opt<NR>(rv.upd, j1[q], y1[q]); ldcg_opt<NR>(rv.upd, j2[q], y2[q]); }
-  constexpr int U = AccSets<R>::U;
-  double accs[U][R][NR];
-  zero_sets<NR, R, U>(accs);
-  for (int k = 0; k < t.s2;) {
-    int n = (CHD - pp.pos) / ld;
-    if (n == 0) { pp.advance(); if (pp.cur == 0) trace_stamp(tr, ti, 0, lane); continue; }
-    n = min(n, t.s2 - k);
-    const double* base = pp.ring + (pp.cur % NSF) * CHD + pp.pos + lane;
-    const double* yv = sm.cv + k * NR;
-    fma_columns<NR, R, U>(base, ld, n, valid, [&](int c, double (&y)[NR]) { ld_loc<NR>(yv, c, y); }, accs);
-    pp.pos += n * ld; k += n;
+// one warp's multiply: its 32 rows (or pivot columns) against n items of 32 doubles, y(c) from shared memory
+template <int NR, class YF>
+__device__ __forceinline__ void warp_multiply(PipeW& pp, int n, bool valid, YF&& yf, double (&out)[NR]) {
+  const bool v1[1] = {valid};
+  double accs[4][1][NR];
+  zero_sets<NR, 1, 4>(accs);
+  for (int k = 0; k < n;) {
+    int m = (CHD - pp.pos) / 32;
+    if (m == 0) { pp.advance(); continue; }
+    m = min(m, n - k);
+    const double* base = pp.ring + (pp.cur % NSW) * CHD + pp.pos + pp.lane;
+    fma_columns<NR, 1, 4>(base, 32, m, v1, [&](int c, double (&y)[NR]) { yf(k + c, y); }, accs);
+    pp.pos += m * 32; k += m;
   }
-  trace_stamp(tr, ti, 7, lane);
-#pragma unroll
-  for (int q = 0; q < R; ++q) {
-    if (!valid[q]) continue;
-    const int row = t.r0 + lane + 32 * q;
-    double a[NR];
-    fold_sets<NR, R, U>(accs, q, a);
-    if (row < t.s2) {
-      stg_v<NR>(rv.out, t.g0 + row, a);
-    } else {
-      double o[NR];
-#pragma unroll
-      for (int r = 0; r < NR; ++r) o[r] = (y1[q][r] + y2[q][r]) - a[r];      // first child, second child (fixed order)
-      stg_v<NR>(rv.upd, (int64_t)t.uoff + (row - t.s2), o);
-    }
-  }
+  fold_sets<NR, 1, 4>(accs, 0, out);
 }
 
 template <int NR, bool PDL, bool FUSED>
-__global__ void __launch_bounds__(32) level_forward_kernel(const LevelTask* __restrict__ tasks, const int32_t* __restrict__ gsrc,
-                                                           const double* __restrict__ stream, const int32_t* __restrict__ cptr,
-                                                           const int32_t* __restrict__ child, const int32_t* __restrict__ cmap_ptr,
-                                                           const int32_t* __restrict__ cmap, const int32_t* __restrict__ sptr,
-                                                           const int32_t* __restrict__ uoff, RhsView rv, int32_t* status, int32_t* sync) {
+__global__ void __launch_bounds__(32 * TW) level_forward_kernel(const LevelTask* __restrict__ tasks, const int32_t* __restrict__ gsrc,
+                                                                const double* __restrict__ stream, const int32_t* __restrict__ cptr,
+                                                                const int32_t* __restrict__ child, const int32_t* __restrict__ cmap_ptr,
+                                                                const int32_t* __restrict__ cmap, const int32_t* __restrict__ sptr,
+                                                                const int32_t* __restrict__ uoff, RhsView rv, int32_t* status, int32_t* sync) {
   __shared__ LevelFwdSmem<NR> sm;
-  const int lane = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (PDL) griddep_launch_dependents();
   // dataflow launch: tasks are handed out in level order by a ticket, so whatever a running task waits for belongs to a
   // task that has started before it — progress does not depend on the order in which the hardware dispatches CTAs
   int ti = blockIdx.x;
   long long* const tr = FUSED ? g_sweep_trace : nullptr;
   if (FUSED) {
-    if (lane == 0) ti = atomicAdd(sync, 1);
-    ti = __shfl_sync(0xffffffffu, ti, 0);
+    if (tid == 0) sm.ticket = atomicAdd(sync, 1);
+    __syncthreads();
+    ti = sm.ticket;
   }
   const LevelTask t = tasks[ti];
-  trace_stamp(tr, ti, 1, lane);
-  if (lane == 0) {
-    for (int s = 0; s < NSF; ++s) mbar_init(sm.bar + s, 1);
+  trace_stamp(tr, ti, 1, tid);
+  const int nw = (t.n + 31) >> 5;              // warps with rows
+  if (warp < nw && lane == 0) {
+    for (int s = 0; s < NSW; ++s) mbar_init(sm.bar[warp] + s, 1);
     fence_mbar_init();
   }
   __syncwarp();
-  PipeF pp{sm.ring, sm.bar, stream + t.soff, status, t.chunks, -1, CHD, lane};
-  pp.start();
-  // static: where the pivot rows and this task's update rows receive their children's updates
+  PipeW pp{sm.ring[warp], sm.bar[warp], stream + t.soff + (int64_t)warp * t.chunks * CHD, status, warp < nw ? t.chunks : 0, -1, CHD, lane};
+  if (warp < nw) pp.start();
+  // static: where this thread's pivot row and its row of the slab receive their children's updates
   const int nf2 = t.s2 + t.u2;
   const int32_t* g1 = gsrc + t.goff;
   const int32_t* g2 = g1 + nf2;
-  int i1[4], i2[4], j1[4], j2[4];
+  int i1 = -1, i2 = -1, j1 = -1, j2 = -1;
+  double v[NR];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int k = lane + 32 * q;
-    i1[q] = i2[q] = j1[q] = j2[q] = -1;
-    if (k < t.s2) { i1[q] = g1[k]; i2[q] = g2[k]; }
-    const int row = t.r0 + k;
-    if (k < t.n && row >= t.s2) { j1[q] = g1[row]; j2[q] = g2[row]; }
+  for (int r = 0; r < NR; ++r) v[r] = 0.0;
+  if (tid < t.s2) {          // the right-hand sides are input of the whole solve: final before the first sweep kernel started
+    i1 = g1[tid]; i2 = g2[tid];
+    ldg_v<NR>(rv.rhs, t.g0 + tid, v);
   }
-  // the right-hand sides of the pivot rows are input of the whole solve: final before the first sweep kernel started
-  double v[4][NR];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int k = lane + 32 * q;
-    if (k < t.s2) {
-      ldg_v<NR>(rv.rhs, t.g0 + k, v[q]);
-    } else {
-#pragma unroll
-      for (int r = 0; r < NR; ++r) v[q][r] = 0.0;
-    }
-  }
+  const int row = t.r0 + tid;
+  const bool has_row = tid < t.n;
+  if (has_row && row >= t.s2) { j1 = g1[row]; j2 = g2[row]; }
   if (PDL) griddep_wait();
-  trace_stamp(tr, ti, 2, lane);
-  if (FUSED && t.need > 0) wait_counter(sync + 2 + t.dep, t.need, lane, status);     // the children's update vectors are complete
-  trace_stamp(tr, ti, 3, lane);
-  // assembled pivot part of the right-hand sides, fixed order (rhs + first child) + second child; the eight gathers of a lane
-  // are one batch
+  trace_stamp(tr, ti, 2, tid);
+  if (FUSED && t.need > 0) {                   // the children's update vectors are complete
+    if (warp == 0) wait_counter(sync + 2 + t.dep, t.need, lane, status);
+    __syncthreads();
+  }
+  trace_stamp(tr, ti, 3, tid);
+  // assembled pivot part of the right-hand sides, fixed order (rhs + first child) + second child; both gathers in flight at once
   {
-    double w1[4][NR], w2[4][NR];
+    double w1[NR], w2[NR];
+    ldcg_opt<NR>(rv.upd, i1, w1); ldcg_opt<NR>(rv.upd, i2, w2);
+    if (tid < t.s2) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { ldcg_opt<NR>(rv.upd, i1[q], w1[q]); ldcg_opt<NR>(rv.upd, i2[q], w2[q]); }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int k = lane + 32 * q;
-      if (k >= t.s2) continue;
-#pragma unroll
-      for (int r = 0; r < NR; ++r) sm.cv[k * NR + r] = (v[q][r] + w1[q][r]) + w2[q][r];
+      for (int r = 0; r < NR; ++r) sm.cv[tid * NR + r] = (v[r] + w1[r]) + w2[r];
     }
   }
-  __syncwarp();
-  trace_stamp(tr, ti, 4, lane);
+  __syncthreads();
   if (t.nch > 2) {          // rare (a separator that does not disconnect): the further children, one after the other
     for (int c = cptr[t.f] + 2; c < cptr[t.f + 1]; ++c) {
       const int ch = child[c];
       const int uc2 = 2 * (sptr[ch + 1] - sptr[ch]);
       const int32_t* cm = cmap + cmap_ptr[ch];
-      for (int k = lane; k < uc2; k += 32) {
-        const int row = 2 * cm[k >> 1] + (k & 1);
-        if (row < t.s2) {
+      for (int k = tid; k < uc2; k += 32 * TW) {
+        const int prow = 2 * cm[k >> 1] + (k & 1);
+        if (prow < t.s2) {
           double w[NR];
           ldcg_v<NR>(rv.upd, (int64_t)uoff[ch] + k, w);
 #pragma unroll
-          for (int r = 0; r < NR; ++r) sm.cv[row * NR + r] += w[r];
+          for (int r = 0; r < NR; ++r) sm.cv[prow * NR + r] += w[r];
         }
       }
-      __syncwarp();
+      __syncthreads();
     }
   }
-  switch ((t.n + 31) >> 5) {
-    case 1: level_fwd_rows<NR, 1>(pp, sm, t, j1, j2, rv, tr, ti); break;
-    case 2: level_fwd_rows<NR, 2>(pp, sm, t, j1, j2, rv, tr, ti); break;
-    case 3: level_fwd_rows<NR, 3>(pp, sm, t, j1, j2, rv, tr, ti); break;
-    default: level_fwd_rows<NR, 4>(pp, sm, t, j1, j2, rv, tr, ti); break;
+  trace_stamp(tr, ti, 4, tid);
+  if (warp < nw) {
+    // what the children send to this thread's update row: requested now, used after the panel has been multiplied
+    double y1[NR], y2[NR], a[NR];
+    ldcg_opt<NR>(rv.upd, j1, y1); ldcg_opt<NR>(rv.upd, j2, y2);
+    warp_multiply<NR>(pp, t.s2, has_row, [&](int c, double (&y)[NR]) { ld_loc<NR>(sm.cv, c, y); }, a);
+    if (warp == 0) trace_stamp(tr, ti, 7, tid);
+    if (has_row) {
+      if (row < t.s2) {
+        stg_v<NR>(rv.out, t.g0 + row, a);                            // z1 = F11^-1 y1
+      } else {
+        double o[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) o[r] = (y1[r] + y2[r]) - a[r];   // first child, second child (fixed order), minus W^T y1
+        stg_v<NR>(rv.upd, (int64_t)t.uoff + (row - t.s2), o);
+      }
+    }
   }
   if (t.nch > 2) {          // update rows of this task: contributions of the further children (after the first two, fixed order)
-    __syncwarp();
+    __syncthreads();
     for (int c = cptr[t.f] + 2; c < cptr[t.f + 1]; ++c) {
       const int ch = child[c];
       const int uc2 = 2 * (sptr[ch + 1] - sptr[ch]);
       const int32_t* cm = cmap + cmap_ptr[ch];
-      for (int k = lane; k < uc2; k += 32) {
-        const int row = 2 * cm[k >> 1] + (k & 1);
-        if (row >= t.s2 && row >= t.r0 && row < t.r0 + t.n) {
+      for (int k = tid; k < uc2; k += 32 * TW) {
+        const int prow = 2 * cm[k >> 1] + (k & 1);
+        if (prow >= t.s2 && prow >= t.r0 && prow < t.r0 + t.n) {
           double w[NR], o[NR];
           ldcg_v<NR>(rv.upd, (int64_t)uoff[ch] + k, w);
-          ldcg_v<NR>(rv.upd, (int64_t)t.uoff + (row - t.s2), o);
+          ldcg_v<NR>(rv.upd, (int64_t)t.uoff + (prow - t.s2), o);
 #pragma unroll
           for (int r = 0; r < NR; ++r) o[r] += w[r];
-          stg_v<NR>(rv.upd, (int64_t)t.uoff + (row - t.s2), o);
+          stg_v<NR>(rv.upd, (int64_t)t.uoff + (prow - t.s2), o);
         }
       }
-      __syncwarp();
+      __syncthreads();
     }
   }
-  trace_stamp(tr, ti, 5, lane);
-  if (FUSED && t.sig >= 0) signal_counter(sync + 2 + t.sig, lane);
-  trace_stamp(tr, ti, 6, lane);
-  pp.drain();
-}
-
-// backward, one slab of the contraction: acc += W(slab, :)^T x2(slab); lanes over the pivot columns (R per lane)
-template <int NR, int R>
-__device__ __forceinline__ void level_bwd_slab(PipeB& pp, LevelBwdSmem<NR>& sm, int s2p, int jn, double (&acc)[4][NR], const bool (&valid4)[4]) {
-  const int lane = pp.lane;
-  constexpr int U = AccSets<R>::U;
-  bool valid[R];
-#pragma unroll
-  for (int q = 0; q < R; ++q) valid[q] = valid4[q];
-  double accs[U][R][NR];
-  zero_sets<NR, R, U>(accs);
-  for (int j = 0; j < jn;) {
-    int n = (CHD - pp.pos) / s2p;
-    if (n == 0) { pp.advance(); continue; }
-    n = min(n, jn - j);
-    const double* base = pp.ring + (pp.cur % NSB) * CHD + pp.pos + lane;
-    fma_columns<NR, R, U>(base, s2p, n, valid, [&](int c, double (&x)[NR]) { ld_loc<NR>(sm.cv, j + c, x); }, accs);
-    pp.pos += n * s2p; j += n;
+  trace_stamp(tr, ti, 5, tid);
+  if (FUSED && t.sig >= 0) {                   // every thread's stores first, then one increment
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicAdd(sync + 2 + t.sig, 1);
   }
-#pragma unroll
-  for (int q = 0; q < R; ++q) fold_sets<NR, R, U>(accs, q, acc[q]);
+  trace_stamp(tr, ti, 6, tid);
+  if (warp < nw) pp.drain();
 }
 
-// A backward task is a slab of the CONTRACTION: all pivot columns of a front against <= KSMAX of its update unknowns, so no
-// two tasks gather the same ancestors' values (the first version split the pivot columns: sixteen tasks of a front with
-// 3 800 update unknowns each gathered all of them, and each ran for 50 us).  The slabs of a front leave their partial sums in
-// `part`; whichever arrives last adds them IN SLAB ORDER (the result does not depend on who that is) and subtracts from z1.
 template <int NR, bool PDL, bool FUSED>
-__global__ void __launch_bounds__(32) level_backward_kernel(const LevelTask* __restrict__ tasks, const double* __restrict__ stream,
-                                                            const int32_t* __restrict__ strct, double* __restrict__ x,
-                                                            double* __restrict__ part, int32_t* status, int32_t* sync, int nfronts) {
+__global__ void __launch_bounds__(32 * TW) level_backward_kernel(const LevelTask* __restrict__ tasks, const double* __restrict__ stream,
+                                                                 const int32_t* __restrict__ strct, double* __restrict__ x,
+                                                                 double* __restrict__ part, int32_t* status, int32_t* sync, int nfronts) {
   __shared__ LevelBwdSmem<NR> sm;
-  const int lane = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (PDL) griddep_launch_dependents();
   int ti = blockIdx.x;
   if (FUSED) {            // tickets in level order, top level first (see level_forward_kernel)
-    if (lane == 0) ti = atomicAdd(sync + 1, 1);
-    ti = __shfl_sync(0xffffffffu, ti, 0);
+    if (tid == 0) sm.ticket = atomicAdd(sync + 1, 1);
+    __syncthreads();
+    ti = sm.ticket;
   }
   const LevelTask t = tasks[ti];
-  if (lane == 0) {
-    for (int s = 0; s < NSB; ++s) mbar_init(sm.bar + s, 1);
+  const int k0 = t.r0, kn = t.n, nk = t.nch;   // this task's slab of the update unknowns; slabs of the front
+  const int nw = (t.s2 + 31) >> 5;             // warps with pivot columns
+  if (warp < nw && lane == 0) {
+    for (int s = 0; s < NSW; ++s) mbar_init(sm.bar[warp] + s, 1);
     fence_mbar_init();
   }
   __syncwarp();
-  PipeB pp{sm.ring, sm.bar, stream + t.soff, status, t.chunks, -1, CHD, lane};
-  pp.start();
-  const int k0 = t.r0, kn = t.n, nk = t.nch;   // this task's slab of the update unknowns; slabs of the front
+  PipeW pp{sm.ring[warp], sm.bar[warp], stream + t.soff + (int64_t)warp * t.chunks * CHD, status, warp < nw ? t.chunks : 0, -1, CHD, lane};
+  if (warp < nw) pp.start();
   const int32_t* st = strct + t.goff;          // the front's update set
-  // static: positions of the slab's update unknowns in the solution vector
-  constexpr int NG = KSMAX / 32;
-  int64_t xo[NG];
+  // static: positions of the slab's update unknowns in the solution vector (two per thread)
+  int64_t xo[KSMAX / (32 * TW)];
 #pragma unroll
-  for (int q = 0; q < NG; ++q) {
-    const int j = lane + 32 * q;
+  for (int q = 0; q < KSMAX / (32 * TW); ++q) {
+    const int j = tid + 32 * TW * q;
     xo[q] = j < kn ? 2 * (int64_t)st[(k0 + j) >> 1] + ((k0 + j) & 1) : -1;
   }
   if (PDL) griddep_wait();
-  // z1 of this front's pivots (forward sweep): requested before the dependency wait, used at the very end
-  double z[4][NR];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    if (lane + 32 * q < t.s2) {
-      ldcg_v<NR>(x, t.g0 + lane + 32 * q, z[q]);
-    } else {
-#pragma unroll
-      for (int r = 0; r < NR; ++r) z[q][r] = 0.0;
-    }
+  const bool has_col = tid < t.s2;
+  // z1 of this thread's pivot (forward sweep): requested before the dependency wait, used at the very end
+  double z[NR];
+  ldcg_opt<NR>(x, has_col ? t.g0 + tid : -1, z);
+  if (FUSED && t.need > 0) {                   // the parent's unknowns are final
+    if (warp == 0) wait_counter(sync + 2 + nfronts + t.dep, t.need, lane, status);
+    __syncthreads();
   }
-  if (FUSED && t.need > 0) wait_counter(sync + 2 + nfronts + t.dep, t.need, lane, status);   // the parent's unknowns are final
   {
-    double g[NG][NR];        // the slab of x2: one batch of gathers
+    double g[KSMAX / (32 * TW)][NR];           // the slab of x2: one batch of gathers
 #pragma unroll
-    for (int q = 0; q < NG; ++q) ldcg_opt<NR>(x, xo[q], g[q]);
+    for (int q = 0; q < KSMAX / (32 * TW); ++q) ldcg_opt<NR>(x, xo[q], g[q]);
 #pragma unroll
-    for (int q = 0; q < NG; ++q) {
+    for (int q = 0; q < KSMAX / (32 * TW); ++q) {
       if (xo[q] < 0) continue;
 #pragma unroll
-      for (int r = 0; r < NR; ++r) sm.cv[(lane + 32 * q) * NR + r] = g[q][r];
+      for (int r = 0; r < NR; ++r) sm.cv[(tid + 32 * TW * q) * NR + r] = g[q][r];
     }
   }
-  __syncwarp();
-  const int s2p = (t.s2 + 3) & ~3;
-  double acc[4][NR];
-  bool valid[4];
+  __syncthreads();
+  double a[NR];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    valid[q] = lane + 32 * q < t.s2;
-#pragma unroll
-    for (int r = 0; r < NR; ++r) acc[q][r] = 0.0;
-  }
-  switch ((t.s2 + 31) >> 5) {
-    case 1: level_bwd_slab<NR, 1>(pp, sm, s2p, kn, acc, valid); break;
-    case 2: level_bwd_slab<NR, 2>(pp, sm, s2p, kn, acc, valid); break;
-    case 3: level_bwd_slab<NR, 3>(pp, sm, s2p, kn, acc, valid); break;
-    default: level_bwd_slab<NR, 4>(pp, sm, s2p, kn, acc, valid); break;
-  }
+  for (int r = 0; r < NR; ++r) a[r] = 0.0;
+  if (warp < nw) warp_multiply<NR>(pp, kn, has_col, [&](int c, double (&y)[NR]) { ld_loc<NR>(sm.cv, c, y); }, a);
   bool finish = true;
   if (nk > 1) {
-    double* mine = part + ((int64_t)t.uoff + (int64_t)(k0 / t.pad[0]) * s2p) * NR;    // pad[0]: slab length of this front
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (valid[q]) stg_v<NR>(mine, lane + 32 * q, acc[q]);
+    const int s2p = (t.s2 + 3) & ~3;
+    if (has_col) stg_v<NR>(part + ((int64_t)t.uoff + (int64_t)(k0 / t.pad[0]) * s2p) * NR, tid, a);    // pad[0]: slab length of this front
     __threadfence();
-    __syncwarp();
-    int old = 0;
-    if (lane == 0) old = atomicAdd(sync + 2 + 2 * nfronts + t.f, 1);
-    old = __shfl_sync(0xffffffffu, old, 0);
-    finish = (old == nk - 1);
+    __syncthreads();
+    if (tid == 0) sm.last = (atomicAdd(sync + 2 + 2 * nfronts + t.f, 1) == nk - 1);
+    __syncthreads();
+    finish = sm.last != 0;
     if (finish) {
       __threadfence();                          // the other slabs' partial sums are visible now
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int r = 0; r < NR; ++r) acc[q][r] = 0.0;
+      for (int r = 0; r < NR; ++r) a[r] = 0.0;
       const double* all = part + (int64_t)t.uoff * NR;
-      for (int kk = 0; kk < nk; ++kk) {         // slab order, whoever finishes
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (!valid[q]) continue;
+      if (has_col)
+        for (int kk = 0; kk < nk; ++kk) {       // slab order, whoever finishes
           double w[NR];
-          ldcg_v<NR>(all, (int64_t)kk * s2p + lane + 32 * q, w);
+          ldcg_v<NR>(all, (int64_t)kk * s2p + tid, w);
 #pragma unroll
-          for (int r = 0; r < NR; ++r) acc[q][r] += w[r];
+          for (int r = 0; r < NR; ++r) a[r] += w[r];
         }
-      }
     }
   }
   if (finish) {
+    if (has_col) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (!valid[q]) continue;
-#pragma unroll
-      for (int r = 0; r < NR; ++r) z[q][r] -= acc[q][r];
-      stg_v<NR>(x, t.g0 + lane + 32 * q, z[q]);
+      for (int r = 0; r < NR; ++r) z[r] -= a[r];
+      stg_v<NR>(x, t.g0 + tid, z);
     }
-    if (FUSED && t.sig >= 0) signal_counter(sync + 2 + nfronts + t.sig, lane);
+    if (FUSED && t.sig >= 0) {
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) atomicAdd(sync + 2 + nfronts + t.sig, 1);
+    }
   }
-  pp.drain();
+  if (warp < nw) pp.drain();
 }
 
-// pack of the level tasks: one CTA per task copies its slab from the front pool into its stream
+// pack of the level tasks: one CTA per task copies its slab from the front pool into the sub-streams of its warps
 __global__ void __launch_bounds__(256) level_pack_kernel(const LevelTask* __restrict__ ftasks, int nf_tasks, const LevelTask* __restrict__ btasks,
                                                          const int64_t* __restrict__ foff, const double* __restrict__ pool,
                                                          double* __restrict__ lfwd, double* __restrict__ lbwd) {
@@ -905,20 +846,23 @@ __global__ void __launch_bounds__(256) level_pack_kernel(const LevelTask* __rest
   const int s2 = t.s2, u2 = t.u2;
   const int64_t ld = s2 + u2;
   const double* src = pool + foff[f];
+  const int64_t wstride = (int64_t)t.chunks * CHD;      // one warp's sub-stream
   if (fwd) {
-    const int ldb = (t.n + 3) & ~3;
+    // rows r0 .. r0 + n of the left block column: warp w owns rows 32 w ..., item k = column k of its 32 rows
     double* dst = lfwd + t.soff;
-    for (int idx = tid; idx < s2 * ldb; idx += 256) {
-      const int k = idx / ldb, i = idx - k * ldb;
-      dst[item_off(k, ldb) + i] = i < t.n ? src[k * ld + t.r0 + i] : 0.0;
+    const int nwr = ((t.n + 31) >> 5) * 32;
+    for (int idx = tid; idx < s2 * nwr; idx += 256) {
+      const int k = idx / nwr, i = idx - k * nwr;
+      dst[(i >> 5) * wstride + item_off(k, 32) + (i & 31)] = i < t.n ? src[k * ld + t.r0 + i] : 0.0;
     }
   } else {
-    const int isz = (s2 + 3) & ~3, k0 = t.r0, kn = t.n;
+    // W(j, c) = src[c * ld + s2 + j] for the slab j = k0 .. k0 + kn: warp w owns pivot columns 32 w ..., item j - k0 = row j of its 32
+    // columns; read with j fastest (coalesced)
     double* dst = lbwd + t.soff;
-    // W(j, c) = src[c * ld + s2 + j]: read with j fastest (coalesced), write item j - k0, column c
-    for (int64_t idx = tid; idx < (int64_t)kn * isz; idx += 256) {
+    const int k0 = t.r0, kn = t.n, ncw = ((s2 + 31) >> 5) * 32;
+    for (int64_t idx = tid; idx < (int64_t)kn * ncw; idx += 256) {
       const int c = (int)(idx / kn), j = (int)(idx - (int64_t)c * kn);
-      dst[item_off(j, isz) + c] = c < s2 ? src[(int64_t)c * ld + s2 + k0 + j] : 0.0;
+      dst[(c >> 5) * wstride + item_off(j, 32) + (c & 31)] = c < s2 ? src[(int64_t)c * ld + s2 + k0 + j] : 0.0;
     }
   }
 }
@@ -1014,9 +958,9 @@ void build_level_plan(plfem_ctx* ctx, const FrontPlan& P, const std::vector<int3
   S.fptr.assign(P.nlevels + 1, 0); S.bptr.assign(P.nlevels + 1, 0);
   S.nfronts = P.nfronts;
   // slab sizes depend on the front alone (a design's arithmetic is the same alone and inside a forest)
-  auto fwd_rows = [](int s2) { return std::max(32, std::min(128, (4096 / s2) & ~31)); };
-  // backward: slabs of the contraction index of about 32 KB of W (all pivot columns x ks update unknowns)
-  auto bwd_ks = [](int s2) { return std::max(32, std::min(KSMAX, (4096 / ((s2 + 3) & ~3)) & ~31)); };
+  auto fwd_rows = [](int) { return 32 * TW; };        // a forward task: 128 rows, one per thread
+  // backward: slabs of the contraction index of about 128 KB of W (all pivot columns x ks update unknowns)
+  auto bwd_ks = [](int s2) { return std::max(32, std::min(KSMAX, (16384 / ((s2 + 3) & ~3)) & ~31)); };
   std::vector<int32_t> nft(P.nfronts, 0), nbt(P.nfronts, 0);      // tasks per front
   for (int f = 0; f < P.nfronts; ++f) {
     if (in_sub[f]) continue;
@@ -1036,15 +980,14 @@ void build_level_plan(plfem_ctx* ctx, const FrontPlan& P, const std::vector<int3
       const int s2 = 2 * P.s[f], u2 = 2 * (P.sptr[f + 1] - P.sptr[f]), rows = s2 + u2;
       LevelTask t{};
       t.g0 = 2 * (int64_t)P.first[f]; t.s2 = s2; t.u2 = u2; t.f = f;
-      // forward: slabs of rows.  A slab's stream is s2 columns of its height: about 32 KB, the capacity of the ring, so that a
-      // task is completely in flight before its dependencies resolve
+      // forward: slabs of 128 rows, four sub-streams (one per warp: s2 columns of 32 rows each)
       const int nr = fwd_rows(s2);
       t.goff = goff[f]; t.uoff = uoff[f]; t.nch = P.cptr[f + 1] - P.cptr[f];
       t.dep = f; t.need = fneed[f]; t.sig = P.parent[f];
       for (int r0 = 0; r0 < rows; r0 += nr) {
         t.r0 = r0; t.n = std::min(nr, rows - r0);
-        t.chunks = item_chunks(s2, (t.n + 3) & ~3);
-        t.soff = fo * CHD; fo += t.chunks;
+        t.chunks = item_chunks(s2, 32);                        // per warp
+        t.soff = fo * CHD; fo += (int64_t)t.chunks * ((t.n + 31) >> 5);
         ft.push_back(t);
       }
     }
@@ -1070,8 +1013,8 @@ void build_level_plan(plfem_ctx* ctx, const FrontPlan& P, const std::vector<int3
       t.dep = par; t.need = (par >= 0 && nbt[par] > 0) ? 1 : 0; t.sig = f;
       for (int k0 = 0; k0 < u2; k0 += ks) {
         t.r0 = k0; t.n = std::min(ks, u2 - k0);
-        t.chunks = item_chunks(t.n, s2p);
-        t.soff = bo * CHD; bo += t.chunks;
+        t.chunks = item_chunks(t.n, 32);                       // per warp
+        t.soff = bo * CHD; bo += (int64_t)t.chunks * ((s2 + 31) >> 5);
         bt.push_back(t);
       }
     }
@@ -1102,7 +1045,7 @@ void launch_stream_pack(plfem_ctx* ctx, const DevPlan& D) {
 
 namespace {
 template <class... KArgs, class... Args>
-void launch_warp_ctas(void (*kernel)(KArgs...), bool pdl, int grid, cudaStream_t st, Args... args) {
+void launch_warp_ctas(void (*kernel)(KArgs...), bool pdl, int grid, int threads, cudaStream_t st, Args... args) {
   static thread_local const void* configured[64] = {};
   bool seen = false;
   for (const void* k : configured) seen |= (k == (const void*)kernel);
@@ -1111,7 +1054,7 @@ void launch_warp_ctas(void (*kernel)(KArgs...), bool pdl, int grid, cudaStream_t
     for (const void*& k : configured) if (!k) { k = (const void*)kernel; break; }
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(32); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -1124,11 +1067,11 @@ void launch_forward_tasks(plfem_ctx* ctx, const DevPlan& D, const LevelTask* tas
   const StreamPlan& S = D.st;
   const RhsView rv{rhs, out, D.upd.p};
   if (nrhs == 1) {
-    if (pdl) launch_warp_ctas(level_forward_kernel<1, true, FUSED>, true, n, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p);
-    else launch_warp_ctas(level_forward_kernel<1, false, FUSED>, false, n, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p);
+    if (pdl) launch_warp_ctas(level_forward_kernel<1, true, FUSED>, true, n, 32 * TW, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p);
+    else launch_warp_ctas(level_forward_kernel<1, false, FUSED>, false, n, 32 * TW, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p);
   } else {
-    if (pdl) launch_warp_ctas(level_forward_kernel<SOLVE_NRHS, true, FUSED>, true, n, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p);
-    else launch_warp_ctas(level_forward_kernel<SOLVE_NRHS, false, FUSED>, false, n, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p);
+    if (pdl) launch_warp_ctas(level_forward_kernel<SOLVE_NRHS, true, FUSED>, true, n, 32 * TW, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p);
+    else launch_warp_ctas(level_forward_kernel<SOLVE_NRHS, false, FUSED>, false, n, 32 * TW, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p);
   }
   ctx->launches++;
 }
@@ -1137,11 +1080,11 @@ template <bool FUSED>
 void launch_backward_tasks(plfem_ctx* ctx, const DevPlan& D, const LevelTask* tasks, int n, double* x, int nrhs, bool pdl) {
   const StreamPlan& S = D.st;
   if (nrhs == 1) {
-    if (pdl) launch_warp_ctas(level_backward_kernel<1, true, FUSED>, true, n, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts);
-    else launch_warp_ctas(level_backward_kernel<1, false, FUSED>, false, n, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts);
+    if (pdl) launch_warp_ctas(level_backward_kernel<1, true, FUSED>, true, n, 32 * TW, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts);
+    else launch_warp_ctas(level_backward_kernel<1, false, FUSED>, false, n, 32 * TW, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts);
   } else {
-    if (pdl) launch_warp_ctas(level_backward_kernel<SOLVE_NRHS, true, FUSED>, true, n, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts);
-    else launch_warp_ctas(level_backward_kernel<SOLVE_NRHS, false, FUSED>, false, n, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts);
+    if (pdl) launch_warp_ctas(level_backward_kernel<SOLVE_NRHS, true, FUSED>, true, n, 32 * TW, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts);
+    else launch_warp_ctas(level_backward_kernel<SOLVE_NRHS, false, FUSED>, false, n, 32 * TW, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts);
   }
   ctx->launches++;
 }
@@ -1151,11 +1094,11 @@ void launch_stream_forward(plfem_ctx* ctx, const DevPlan& D, const double* rhs, 
   const StreamPlan& S = D.st;
   if (S.n_subs == 0) return;
   if (nrhs == 1) {
-    if (pdl) launch_warp_ctas(stream_forward_kernel<1, true>, true, S.n_subs, ctx->stream, S.subs.p, S.fronts.p, S.sfwd.p, rhs, out, D.upd.p, D.status.p);
-    else launch_warp_ctas(stream_forward_kernel<1, false>, false, S.n_subs, ctx->stream, S.subs.p, S.fronts.p, S.sfwd.p, rhs, out, D.upd.p, D.status.p);
+    if (pdl) launch_warp_ctas(stream_forward_kernel<1, true>, true, S.n_subs, 32, ctx->stream, S.subs.p, S.fronts.p, S.sfwd.p, rhs, out, D.upd.p, D.status.p);
+    else launch_warp_ctas(stream_forward_kernel<1, false>, false, S.n_subs, 32, ctx->stream, S.subs.p, S.fronts.p, S.sfwd.p, rhs, out, D.upd.p, D.status.p);
   } else {
-    if (pdl) launch_warp_ctas(stream_forward_kernel<SOLVE_NRHS, true>, true, S.n_subs, ctx->stream, S.subs.p, S.fronts.p, S.sfwd.p, rhs, out, D.upd.p, D.status.p);
-    else launch_warp_ctas(stream_forward_kernel<SOLVE_NRHS, false>, false, S.n_subs, ctx->stream, S.subs.p, S.fronts.p, S.sfwd.p, rhs, out, D.upd.p, D.status.p);
+    if (pdl) launch_warp_ctas(stream_forward_kernel<SOLVE_NRHS, true>, true, S.n_subs, 32, ctx->stream, S.subs.p, S.fronts.p, S.sfwd.p, rhs, out, D.upd.p, D.status.p);
+    else launch_warp_ctas(stream_forward_kernel<SOLVE_NRHS, false>, false, S.n_subs, 32, ctx->stream, S.subs.p, S.fronts.p, S.sfwd.p, rhs, out, D.upd.p, D.status.p);
   }
   ctx->launches++;
 }
@@ -1190,11 +1133,11 @@ void launch_stream_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrh
   const StreamPlan& S = D.st;
   if (S.n_subs == 0) return;
   if (nrhs == 1) {
-    if (pdl) launch_warp_ctas(stream_backward_kernel<1, true>, true, S.n_subs, ctx->stream, S.subs.p, S.fronts.p, S.sbwd.p, D.strct.p, x, D.status.p);
-    else launch_warp_ctas(stream_backward_kernel<1, false>, false, S.n_subs, ctx->stream, S.subs.p, S.fronts.p, S.sbwd.p, D.strct.p, x, D.status.p);
+    if (pdl) launch_warp_ctas(stream_backward_kernel<1, true>, true, S.n_subs, 32, ctx->stream, S.subs.p, S.fronts.p, S.sbwd.p, D.strct.p, x, D.status.p);
+    else launch_warp_ctas(stream_backward_kernel<1, false>, false, S.n_subs, 32, ctx->stream, S.subs.p, S.fronts.p, S.sbwd.p, D.strct.p, x, D.status.p);
   } else {
-    if (pdl) launch_warp_ctas(stream_backward_kernel<SOLVE_NRHS, true>, true, S.n_subs, ctx->stream, S.subs.p, S.fronts.p, S.sbwd.p, D.strct.p, x, D.status.p);
-    else launch_warp_ctas(stream_backward_kernel<SOLVE_NRHS, false>, false, S.n_subs, ctx->stream, S.subs.p, S.fronts.p, S.sbwd.p, D.strct.p, x, D.status.p);
+    if (pdl) launch_warp_ctas(stream_backward_kernel<SOLVE_NRHS, true>, true, S.n_subs, 32, ctx->stream, S.subs.p, S.fronts.p, S.sbwd.p, D.strct.p, x, D.status.p);
+    else launch_warp_ctas(stream_backward_kernel<SOLVE_NRHS, false>, false, S.n_subs, 32, ctx->stream, S.subs.p, S.fronts.p, S.sbwd.p, D.strct.p, x, D.status.p);
   }
   ctx->launches++;
 }
