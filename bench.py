@@ -408,7 +408,10 @@ def run_ours(args):
     fl = sum(f[4].factor_flops for f in fo)
     kernels["factorize"]["fp64_tflops"] = fl / (prof["factorize"][0] * 1e-3) / 1e12
     kernels["factorize"]["factor_gflop"] = fl / 1e9
-    launches_per = fstats["n_levels"] if "sweep" in dom else 1
+    fused = not os.environ.get("PLFEM_SWEEP", "").startswith("l")
+    # launches of one sweep: the TMA-streamed bottom subtrees + ONE dataflow launch for every level above them (or, with
+    # PLFEM_SWEEP=levels, one launch per elimination-tree level)
+    launches_per = (2 if fused else fstats["n_levels"]) if "sweep" in dom else 1
     ms_dom, bytes_dom = prof[dom]
     traffic = None          # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (same forest size)
     try:
@@ -419,19 +422,18 @@ def run_ours(args):
             traffic = tr["dram_bytes"] * nb_prof / float(tj.get("designs", 12)) / launches_per
     except Exception:
         pass
-    roofline = {"kernel": {"forward_sweep": "stream_forward_kernel<1> (bottom subtrees, TMA-streamed) + forward_kernel<1> (one launch per level above)",
-                           "backward_sweep": "backward_kernel<1> (one launch per level) + stream_backward_kernel<1> (bottom subtrees, TMA-streamed)",
-                           "forward_sweep_4rhs": "stream_forward_kernel<4> (bottom subtrees, TMA-streamed) + forward_kernel<4> (one launch per level above)",
-                           "backward_sweep_4rhs": "backward_kernel<4> (one launch per level) + stream_backward_kernel<4> (bottom subtrees, TMA-streamed)",
-                           "factorize": "invert_kernel+gemm",
-                           "assemble": "assemble_kernel", "spmm_B": "spmm_b_kernel", "spmv_K_residual": "resid_k_kernel"}[dom],
+    above = ("level_forward_kernel<NR> / level_backward_kernel<NR> (every front above them: four-warp tasks, one dataflow launch with tickets and "
+             "per-front counters)" if fused else "level_forward_kernel<NR> / level_backward_kernel<NR> (one launch per level above them)")
+    roofline = {"kernel": ("stream_forward_kernel<NR> / stream_backward_kernel<NR> (bottom subtrees, one warp each, TMA-streamed) + " + above)
+                          if "sweep" in dom else {"factorize": "invert_kernel + gemm_w_dmma_kernel + gemm_schur_dmma_kernel + extend_add_kernel",
+                                                  "assemble": "assemble_rows_kernel", "spmm_B": "spmm_b_kernel", "spmv_K_residual": "resid_k_kernel"}[dom],
                 "name": dom, "bound": "hbm", "achieved": bytes_dom / (ms_dom * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": bytes_dom / (ms_dom * 1e-3) / 1e9 / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "per_launch": {"launches_per_sweep": launches_per, "avg_launch_us": 1e3 * ms_dom / launches_per,
                                "algorithmic_bytes_per_launch": bytes_dom / launches_per, "designs_per_launch": nb_prof},
-                "note": "one sweep = one TMA-streamed launch for the bottom subtrees + one launch per elimination-tree level above them, all carrying "
+                "note": "one sweep = one TMA-streamed launch for the bottom subtrees + the launch(es) for the fronts above them, all carrying "
                         "the fronts of every design of the forest; algorithmic bytes = factor entries of the left block columns (8 B each) + the "
-                        "right-hand sides; L2 flushed before each timed sweep"}
+                        "right-hand sides; CUDA events on the library's stream around the whole sweep, L2 flushed before each timed sweep"}
 
     cpu = cpu_baseline_sample(args.workload, 2) if (world == 1 and args.workload in ("cfg1", "cfg2")) else None
     pool.close()
@@ -450,6 +452,7 @@ def run_ours(args):
                        "analysis_shared_between_designs": False,
                        "k": k, "lanczos": "thick-restart block Lanczos, 4 vectors per operator application, basis 3k, designs in lockstep", "tol": _cabi.EIG_TOL,
                        "start_vector": "ones (+3 fixed pseudo-random)", "refine_steps": int(fstats["refine_steps"]),
+                       "sweeps": "dataflow launch above the bottom subtrees" if not os.environ.get("PLFEM_SWEEP", "").startswith("l") else "one launch per level",
                        "l2": f"inputs larger than L2: one forest streams {B * fstats['factor_entries'] * 8 / 1e6:.0f} MB of factor panels per sweep "
                              f"(front pools {B * fstats['front_pool_doubles'] * 8 / 1e9:.2f} GB); L2 also flushed (512 MiB write) before the timed region",
                        "timing": "wall clock around the K steps (forests) submitted to the worker threads, cuda synchronize + barrier on both sides, max over ranks",

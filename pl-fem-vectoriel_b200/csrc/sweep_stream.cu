@@ -75,6 +75,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(b))
                : "memory");
 }
+// the rest of a task's sub-stream on its way into L2 while the ring holds only NSW chunks: the refills then cost an L2 round
+// trip instead of a DRAM one (a 32 KB sub-stream through an 8 KB ring took 4-6 us, four DRAM latencies)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(src)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
   uint32_t ok;
   asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
@@ -97,9 +102,11 @@ struct PipeT {
     mbar_expect_tx(bar + s, CHD * 8);
     bulk_g2s(ring + s * CHD, src + (int64_t)c * CHD, CHD * 8, bar + s);
   }
-  __device__ __forceinline__ void start() {
-    if (lane == 0)
+  __device__ __forceinline__ void start(bool prefetch_rest = false) {
+    if (lane == 0) {
       for (int c = 0; c < NST && c < nchunks; ++c) issue(c);
+      if (prefetch_rest && nchunks > NST) bulk_prefetch_l2(src + (int64_t)NST * CHD, (uint32_t)(nchunks - NST) * CHD * 8);
+    }
     cur = -1; pos = CHD;
   }
   __device__ __forceinline__ void advance() {
@@ -644,7 +651,7 @@ __global__ void __launch_bounds__(32 * TW) level_forward_kernel(const LevelTask*
   }
   __syncwarp();
   PipeW pp{sm.ring[warp], sm.bar[warp], stream + t.soff + (int64_t)warp * t.chunks * CHD, status, warp < nw ? t.chunks : 0, -1, CHD, lane};
-  if (warp < nw) pp.start();
+  if (warp < nw) pp.start(true);
   // static: where this thread's pivot row and its row of the slab receive their children's updates
   const int nf2 = t.s2 + t.u2;
   const int32_t* g1 = gsrc + t.goff;
@@ -764,7 +771,7 @@ __global__ void __launch_bounds__(32 * TW) level_backward_kernel(const LevelTask
   }
   __syncwarp();
   PipeW pp{sm.ring[warp], sm.bar[warp], stream + t.soff + (int64_t)warp * t.chunks * CHD, status, warp < nw ? t.chunks : 0, -1, CHD, lane};
-  if (warp < nw) pp.start();
+  if (warp < nw) pp.start(true);
   const int32_t* st = strct + t.goff;          // the front's update set
   // static: positions of the slab's update unknowns in the solution vector (two per thread)
   int64_t xo[KSMAX / (32 * TW)];
