@@ -331,8 +331,9 @@ def run_ours(args):
     pool_e = ForestPool(device=local, batch=B, workers=NW, want_vectors=True, share_analysis=False)
     step_jobs = [j for f in forests for j in f]
 
-    for _ in range(args.warmup):
-        pool_e.on_every_worker(lambda p_, c: p_.solve_forest(forests[0]))
+    for _ in range(args.warmup):                            # whole steps through the same pipeline: contexts, device arenas and the
+        for modes in pool_e.solve_iter(step_jobs):          # pool of page-locked result blocks reach their steady state before timing
+            assert not isinstance(modes, Exception), modes
     flush_l2()
     sync_all()
     with ClockSampler(local) as clocks2:
