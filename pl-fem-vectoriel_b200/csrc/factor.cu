@@ -110,7 +110,8 @@ __global__ void __launch_bounds__(256) extend_add_kernel(const int4* __restrict_
 template <int MP, int NG, int E>
 __global__ void __launch_bounds__(MP * NG, MP == 128 ? 1 : (MP == 64 ? 3 : 6)) invert_kernel(const int32_t* __restrict__ fronts, PlanView P, int32_t* status) {
   extern __shared__ double sB[];          // the finished block for the symmetrised write-back
-  __shared__ double cand[MP], prow[MP], pcol[2 * MP];
+  __shared__ __align__(16) double prow[MP];
+  __shared__ double cand[MP], pcol[2 * MP], sinv;
   __shared__ int p_of[MP], step_of[MP];
   const int f = fronts[blockIdx.x];
   const int m = 2 * P.s[f];
@@ -118,88 +119,89 @@ __global__ void __launch_bounds__(MP * NG, MP == 128 ? 1 : (MP == 64 ? 3 : 6)) i
   double* F = P.pool + P.foff[f];
   const int tid = threadIdx.x, lane = tid & 31;
   const int i = tid % MP, jg = tid / MP;
+  // thread (i, jg) owns row i and the E CONTIGUOUS columns jg E ... jg E + E - 1: the column of step k = g E + kt belongs to
+  // group g at the STATIC register index kt once the step loop is unrolled over kt (the first version dealt the columns
+  // round-robin and paid ~200 select instructions per warp and step to read and patch a[k / NG] without a dynamic index)
   double a[E];
 #pragma unroll
   for (int t = 0; t < E; ++t) {
-    const int j = jg + NG * t;
+    const int j = jg * E + t;
     a[t] = (i < m && j < m) ? F[(int64_t)j * ld + i] : 0.0;
   }
   bool used = false;
-  // A step costs every thread E (load, FMA) pairs and nothing else: the scaled pivot row is published by the threads that own
+  // A step costs every thread E (load, FMA) pairs and little else: the scaled pivot row is published by the threads that own
   // it, column k is patched afterwards by the one column group that owns it (jg is uniform within a warp), rows and columns
-  // beyond m hold zeros and take part without predicates, and only the threads that need 1 / pivot compute it.
-  for (int k = 0; k < m; ++k) {
-    const int kt = k / NG, kg = k % NG;
-    double* pc = pcol + (k & 1) * MP;       // double-buffered: rows of the previous step may still be reading theirs
-    if (jg == kg) {
-      double mine = 0.0;                    // a[kt] without a dynamic register index
+  // beyond m hold zeros and take part without predicates, 1 / pivot is computed by the four threads of the pivot row only.
+  for (int g = 0; g < NG; ++g) {
 #pragma unroll
-      for (int t = 0; t < E; ++t) mine = (t == kt) ? a[t] : mine;
-      // an unused row always beats a used one, also when its entry is NaN (-0.5: it loses against every number, the step is
-      // flagged as singular, and the pivot order stays a permutation)
-      const double am = fabs(mine);
-      cand[i] = (i < m && !used) ? (am == am ? am : -0.5) : -1.0;
-      pc[i] = mine;
-    }
-    __syncthreads();
-    double best = -1.0; int bi = 0;
+    for (int kt = 0; kt < E; ++kt) {
+      const int k = g * E + kt;
+      if (k >= m) break;                      // uniform
+      double* pc = pcol + (k & 1) * MP;       // double-buffered: rows of the previous step may still be reading theirs
+      if (jg == g) {
+        // an unused row always beats a used one, also when its entry is NaN (-0.5: it loses against every number, the step is
+        // flagged as singular, and the pivot order stays a permutation)
+        const double mine = a[kt];
+        const double am = fabs(mine);
+        cand[i] = (i < m && !used) ? (am == am ? am : -0.5) : -1.0;
+        pc[i] = mine;
+      }
+      __syncthreads();
+      double best = -1.0; int bi = 0;
 #pragma unroll
-    for (int r = lane; r < MP; r += 32) {
-      const double v = cand[r];
-      if (v > best) { best = v; bi = r; }
-    }
+      for (int r = lane; r < MP; r += 32) {
+        const double v = cand[r];
+        if (v > best) { best = v; bi = r; }
+      }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, best, off);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-    }
-    const int p = bi;                       // the same in every warp
-    if (tid == 0) {
-      p_of[k] = p; step_of[p] = k;
-      if (!(best > 0.0) || !isfinite(best)) { atomicExch(status, 1); atomicExch(status + 3, f); }
-    }
-    const double piv = pc[p];
-    if (i == p) {
-      used = true;
-      const double inv = 1.0 / piv;
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      const int p = bi;                       // the same in every warp
+      if (tid == 0) {
+        p_of[k] = p; step_of[p] = k;
+        if (!(best > 0.0) || !isfinite(best)) { atomicExch(status, 1); atomicExch(status + 3, f); }
+      }
+      if (i == p) {
+        used = true;
+        const double inv = 1.0 / pc[p];
+        if (jg == g) sinv = inv;
 #pragma unroll
-      for (int t = 0; t < E; ++t) prow[jg + NG * t] = a[t] * inv;
-    }
-    __syncthreads();
-    const double ci = pc[i];
-    if (i == p) {
+        for (int t = 0; t < E; ++t) prow[jg * E + t] = a[t] * inv;
+      }
+      __syncthreads();
+      const double ci = pc[i];
+      const double2* pr = reinterpret_cast<const double2*>(prow + jg * E);
+      if (i == p) {
 #pragma unroll
-      for (int t = 0; t < E; ++t) a[t] = prow[jg + NG * t];
-    } else {
+        for (int t = 0; t < E; t += 2) { const double2 q = pr[t >> 1]; a[t] = q.x; a[t + 1] = q.y; }
+      } else {
 #pragma unroll
-      for (int t = 0; t < E; ++t) a[t] = a[t] - ci * prow[jg + NG * t];
-    }
-    if (jg == kg) {                         // column k of the inverse-in-progress
-      const double inv = 1.0 / piv;
-      const double v = (i == p) ? inv : -ci * inv;
-#pragma unroll
-      for (int t = 0; t < E; ++t) a[t] = (t == kt) ? v : a[t];
+        for (int t = 0; t < E; t += 2) { const double2 q = pr[t >> 1]; a[t] = a[t] - ci * q.x; a[t + 1] = a[t + 1] - ci * q.y; }
+      }
+      if (jg == g) a[kt] = (i == p) ? sinv : -ci * sinv;    // column k of the inverse-in-progress
     }
   }
   const int lds = m | 1;
   if (i < m) {
 #pragma unroll
     for (int t = 0; t < E; ++t) {
-      const int j = jg + NG * t;
+      const int j = jg * E + t;
       if (j < m) sB[i + j * lds] = a[t];
     }
   }
   __syncthreads();
   // The inverse of a symmetric block is symmetric; the computed one only to cond x eps, and the Schur complement
   // S = F22 - F12^T (F11^-1 F12) is formed from the upper block alone, so that antisymmetric part would land in S, then in
-  // the parent's pivot block, amplified by |W|^2 level by level (DESIGN.md 4.4a: it, not the block-local pivoting, cost
+  // the parent's pivot block, amplified by |W|^2 level by level (DESIGN.md 4.4: it, not the block-local pivoting, cost
   // the raw solve six digits and made structured meshes diverge).  Write back the average with the transpose.
   if (i < m) {
     const int pr = p_of[i], sr = step_of[i];
 #pragma unroll
     for (int t = 0; t < E; ++t) {
-      const int c = jg + NG * t;
+      const int c = jg * E + t;
       if (c < m) F[(int64_t)c * ld + i] = 0.5 * (sB[pr + step_of[c] * lds] + sB[p_of[c] + sr * lds]);
     }
   }

@@ -966,8 +966,10 @@ void build_level_plan(plfem_ctx* ctx, const FrontPlan& P, const std::vector<int3
   S.nfronts = P.nfronts;
   // slab sizes depend on the front alone (a design's arithmetic is the same alone and inside a forest)
   auto fwd_rows = [](int) { return 32 * TW; };        // a forward task: 128 rows, one per thread
-  // backward: slabs of the contraction index of about 128 KB of W (all pivot columns x ks update unknowns)
-  auto bwd_ks = [](int s2) { return std::max(32, std::min(KSMAX, (16384 / ((s2 + 3) & ~3)) & ~31)); };
+  // backward: slabs of the contraction index of about 64 KB of W (all pivot columns x ks update unknowns; 32 / 64 / 128 KB measured
+  // within 3 % of each other on cfg1 and cfg5)
+  static const int slab_doubles = [] { const char* e = std::getenv("PLFEM_BWD_SLAB_KB"); return 128 * std::max(8, std::min(256, e ? atoi(e) : 64)); }();
+  auto bwd_ks = [](int s2) { return std::max(32, std::min(KSMAX, (slab_doubles / ((s2 + 3) & ~3)) & ~31)); };
   std::vector<int32_t> nft(P.nfronts, 0), nbt(P.nfronts, 0);      // tasks per front
   for (int f = 0; f < P.nfronts; ++f) {
     if (in_sub[f]) continue;

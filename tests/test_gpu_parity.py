@@ -274,9 +274,14 @@ def test_forest_matches_single_solves(small_case):
         assert raw["stats"]["nconv"] >= len(raw["beta_sq"]) and raw["stats"]["max_residual"] < 1e-9
         assert np.abs(raw["beta_sq"] / araw["beta_sq"] - 1).max() < 1e-9   # lockstep may stop a step later: same pairs
         assert len(modes) == len(alone)
-        for m, a in zip(modes, alone):
-            assert abs(m["n_eff"] / a["n_eff"] - 1) < 1e-9 and m["polarization"] == a["polarization"]
-            assert abs(m["confinement"] - a["confinement"]) < 1e-6
+        ne = np.array([a["n_eff"] for a in alone])
+        for i, (m, a) in enumerate(zip(modes, alone)):
+            assert abs(m["n_eff"] / a["n_eff"] - 1) < 1e-9
+            # polarization label and confinement are properties of the VECTOR, and inside a (near-)degenerate pair the vector is
+            # any rotation of the eigenspace: a forest may stop a block step later than the single solve and return another one
+            if len(ne) == 1 or np.min(np.abs(np.delete(ne, i) - ne[i])) > 1e-6:
+                assert m["polarization"] == a["polarization"]
+                assert abs(m["confinement"] - a["confinement"]) < 1e-6
 
 
 def test_forest_of_identical_designs_is_bit_identical_to_single(small_case):
