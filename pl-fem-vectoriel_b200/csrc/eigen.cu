@@ -236,27 +236,44 @@ __global__ void __launch_bounds__(128) rotate_kernel(const double* __restrict__ 
   }
 }
 
-// Out_b[:, c] = sum_j In_b[:, j] * S_b[j, c]  for c < nout, every design of the forest in one launch (S_b at S + b*sstride)
+// Out_b[:, c] = sum_j In_b[:, j] * S_b[j, c]  for c < nout, every design of the forest in one launch (S_b at S + b*sstride).
+// A thread owns a PAIR of rows (128-bit loads) and 16 output columns at a time; the 16 columns of S sit in shared memory as
+// [j][16], read as broadcast 128-bit loads: 32 FMAs per 9 loads (the first version: 8 FMAs per 9 loads, In re-read per 8 columns).
+constexpr int ROT_C = 16;        // output columns per pass
+constexpr int ROT_MAXIN = 256;   // basis columns the shared tile of S holds (ncv + P <= 3 (n_modes + 12) + 8)
 __global__ void __launch_bounds__(128) rotate_forest_kernel(const double* __restrict__ In, int64_t ld, int nin,
                                                             const double* __restrict__ S, int64_t sstride, int nout,
                                                             const int64_t* __restrict__ moff, double* __restrict__ Out, int64_t ldo) {
+  __shared__ __align__(16) double sh[ROT_MAXIN * ROT_C];
   const int b = blockIdx.y;
-  const int64_t i = moff[b] + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= moff[b + 1]) return;
+  const int64_t i = moff[b] + 2 * (blockIdx.x * (int64_t)blockDim.x + threadIdx.x);
+  const bool live = i < moff[b + 1];
   const double* Sb = S + b * sstride;
-  for (int c0 = 0; c0 < nout; c0 += 8) {
-    double acc[8];
+  for (int c0 = 0; c0 < nout; c0 += ROT_C) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < nin * ROT_C; t += blockDim.x) {
+      const int c = t / nin, j = t - c * nin;
+      sh[j * ROT_C + c] = c0 + c < nout ? Sb[(int64_t)(c0 + c) * nin + j] : 0.0;
+    }
+    __syncthreads();
+    if (!live) continue;
+    double2 acc[ROT_C];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = 0.0;
+    for (int c = 0; c < ROT_C; ++c) acc[c] = make_double2(0.0, 0.0);
+#pragma unroll 2
     for (int j = 0; j < nin; ++j) {
-      const double v = In[(int64_t)j * ld + i];
+      const double2 v = *reinterpret_cast<const double2*>(In + (int64_t)j * ld + i);
+      const double2* sj = reinterpret_cast<const double2*>(sh + j * ROT_C);
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        if (c0 + c < nout) acc[c] = fma(v, __ldg(Sb + (int64_t)(c0 + c) * nin + j), acc[c]);
+      for (int c = 0; c < ROT_C; c += 2) {
+        const double2 w = sj[c >> 1];
+        acc[c].x = fma(v.x, w.x, acc[c].x); acc[c].y = fma(v.y, w.x, acc[c].y);
+        acc[c + 1].x = fma(v.x, w.y, acc[c + 1].x); acc[c + 1].y = fma(v.y, w.y, acc[c + 1].y);
+      }
     }
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-      if (c0 + c < nout) Out[(int64_t)(c0 + c) * ldo + i] = acc[c];
+    for (int c = 0; c < ROT_C; ++c)
+      if (c0 + c < nout) *reinterpret_cast<double2*>(Out + (int64_t)(c0 + c) * ldo + i) = acc[c];
   }
 }
 
@@ -488,53 +505,99 @@ __global__ void fill_kernel(double* v, int64_t m, double val) {
 constexpr int NRED = 10;  // norm2, e_core, px_core, py_core, px_all, py_all, div, res2, ||B||_F^2, ||A||_F^2
 constexpr int MROWS = 2048;  // rows (nodes) per CTA in the mode reduction
 
+// Four threads per row (consecutive non-zeros across the lanes: coalesced value loads, no divergence between vertex rows of 19
+// and edge rows of 9 entries) and TWO modes per pass over the matrix (the eight value arrays are read once for both; the first
+// version read them once per mode with one thread per row: 154 us per 7-core design).
+constexpr int MODE_TPR = 4, MODE_PAIR = 2;
 __global__ void __launch_bounds__(256) mode_partial_kernel(int32_t row0, int32_t row1, const int32_t* __restrict__ rowptr,
                                                            const int32_t* __restrict__ col, const double* __restrict__ vals,
                                                            int64_t nnz, const uint8_t* __restrict__ in_core,
                                                            const double2* __restrict__ X, int64_t ldx /* in double2 */,
-                                                           const double* __restrict__ lambda, double* __restrict__ part,
+                                                           const double* __restrict__ lambda, int nmodes, double* __restrict__ part,
                                                            int nchunks) {
   __shared__ double sh[32];
-  const int mode = blockIdx.y, chunk = blockIdx.x;
-  const double2* x = X + (int64_t)mode * ldx;
-  const double lam = lambda[mode];
-  double acc[NRED];
+  const int mode0 = blockIdx.y * MODE_PAIR, chunk = blockIdx.x;
+  const int sub = threadIdx.x % MODE_TPR;
+  double acc[MODE_PAIR][NRED];
 #pragma unroll
-  for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
-  const int r0 = row0 + chunk * MROWS, r1 = min(row1, r0 + MROWS);   // rows of ONE design of the forest
-  for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
-    const double2 v = x[r];
-    const double ex = v.x * v.x, ey = v.y * v.y;
-    acc[0] += ex + ey;
-    acc[4] += ex; acc[5] += ey;
-    if (in_core[r]) { acc[1] += ex + ey; acc[2] += ex; acc[3] += ey; }
-    double dx = 0.0, dy = 0.0, axv = 0.0, ayv = 0.0, bx = 0.0, by = 0.0, fa = 0.0, fb = 0.0;
-    for (int32_t z = rowptr[r]; z < rowptr[r + 1]; ++z) {
-      const double2 c = x[col[z]];
-      dx = fma(vals[(int64_t)S_DXX * nnz + z], c.x, dx);
-      dx = fma(2.0 * vals[(int64_t)S_DXY * nnz + z], c.y, dx);
-      dy = fma(vals[(int64_t)S_DYY * nnz + z], c.y, dy);
-      axv = fma(vals[(int64_t)S_AXX * nnz + z], c.x, axv);
-      axv = fma(vals[(int64_t)S_AXY * nnz + z], c.y, axv);
-      ayv = fma(vals[(int64_t)S_AYX * nnz + z], c.x, ayv);
-      ayv = fma(vals[(int64_t)S_AYY * nnz + z], c.y, ayv);
-      const double mi = vals[(int64_t)S_MINV * nnz + z];
-      bx = fma(mi, c.x, bx); by = fma(mi, c.y, by);
-      // squared Frobenius norms of A and B for the normwise backward error
-      const double a0 = vals[(int64_t)S_AXX * nnz + z], a1 = vals[(int64_t)S_AXY * nnz + z];
-      const double a2 = vals[(int64_t)S_AYX * nnz + z], a3 = vals[(int64_t)S_AYY * nnz + z];
-      fa += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
-      fb += 2.0 * mi * mi;
-    }
-    acc[6] += v.x * dx + v.y * dy;
-    const double rx = axv - lam * bx, ry = ayv - lam * by;
-    acc[7] += rx * rx + ry * ry;
-    acc[8] += fb;
-    acc[9] += fa;
+  for (int q = 0; q < MODE_PAIR; ++q)
+#pragma unroll
+    for (int k = 0; k < NRED; ++k) acc[q][k] = 0.0;
+  const double2* x[MODE_PAIR];
+  double lam[MODE_PAIR];
+#pragma unroll
+  for (int q = 0; q < MODE_PAIR; ++q) {
+    const int md = min(mode0 + q, nmodes - 1);          // an odd count: the last pass computes its mode twice, stores it once
+    x[q] = X + (int64_t)md * ldx; lam[q] = lambda[md];
   }
-  for (int k = 0; k < NRED; ++k) {
-    const double t = block_sum(acc[k], sh);
-    if (threadIdx.x == 0) part[((int64_t)mode * nchunks + chunk) * NRED + k] = t;
+  const int r0 = row0 + chunk * MROWS, r1 = min(row1, r0 + MROWS);   // rows of ONE design of the forest
+  for (int rb = r0 + (int)threadIdx.x / MODE_TPR; rb - (int)threadIdx.x / MODE_TPR < r1; rb += 256 / MODE_TPR) {
+    const int r = rb;
+    const bool live = r < r1;                             // whole groups of four stay in the shuffles below
+    double s[MODE_PAIR][6];                               // dx dy ax ay bx by of this lane's share of the row
+#pragma unroll
+    for (int q = 0; q < MODE_PAIR; ++q)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s[q][k] = 0.0;
+    double fa = 0.0, fb = 0.0;
+    if (live) {
+      for (int32_t z = rowptr[r] + sub; z < rowptr[r + 1]; z += MODE_TPR) {
+        const int32_t cz = col[z];
+        const double dxx = vals[(int64_t)S_DXX * nnz + z], dxy = vals[(int64_t)S_DXY * nnz + z], dyy = vals[(int64_t)S_DYY * nnz + z];
+        const double a0 = vals[(int64_t)S_AXX * nnz + z], a1 = vals[(int64_t)S_AXY * nnz + z];
+        const double a2 = vals[(int64_t)S_AYX * nnz + z], a3 = vals[(int64_t)S_AYY * nnz + z];
+        const double mi = vals[(int64_t)S_MINV * nnz + z];
+        // squared Frobenius norms of A and B for the normwise backward error
+        fa += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+        fb += 2.0 * mi * mi;
+#pragma unroll
+        for (int q = 0; q < MODE_PAIR; ++q) {
+          const double2 c = x[q][cz];
+          s[q][0] = fma(dxx, c.x, s[q][0]);
+          s[q][0] = fma(2.0 * dxy, c.y, s[q][0]);
+          s[q][1] = fma(dyy, c.y, s[q][1]);
+          s[q][2] = fma(a0, c.x, s[q][2]);
+          s[q][2] = fma(a1, c.y, s[q][2]);
+          s[q][3] = fma(a2, c.x, s[q][3]);
+          s[q][3] = fma(a3, c.y, s[q][3]);
+          s[q][4] = fma(mi, c.x, s[q][4]); s[q][5] = fma(mi, c.y, s[q][5]);
+        }
+      }
+    }
+    // the row's sums (the residual is squared per ROW): fixed butterfly over the four lanes
+#pragma unroll
+    for (int q = 0; q < MODE_PAIR; ++q)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        s[q][k] += __shfl_xor_sync(0xffffffffu, s[q][k], 1);
+        s[q][k] += __shfl_xor_sync(0xffffffffu, s[q][k], 2);
+      }
+    if (live && sub == 0) {
+      const bool core = in_core[r];
+#pragma unroll
+      for (int q = 0; q < MODE_PAIR; ++q) {
+        const double2 v = x[q][r];
+        const double ex = v.x * v.x, ey = v.y * v.y;
+        acc[q][0] += ex + ey;
+        acc[q][4] += ex; acc[q][5] += ey;
+        if (core) { acc[q][1] += ex + ey; acc[q][2] += ex; acc[q][3] += ey; }
+        acc[q][6] += v.x * s[q][0] + v.y * s[q][1];
+        const double rx = s[q][2] - lam[q] * s[q][4], ry = s[q][3] - lam[q] * s[q][5];
+        acc[q][7] += rx * rx + ry * ry;
+      }
+    }
+    if (live) {                                           // every lane's share of the Frobenius norms
+#pragma unroll
+      for (int q = 0; q < MODE_PAIR; ++q) { acc[q][8] += fb; acc[q][9] += fa; }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < MODE_PAIR; ++q) {
+    if (mode0 + q >= nmodes) break;
+    for (int k = 0; k < NRED; ++k) {
+      const double t = block_sum(acc[q][k], sh);
+      if (threadIdx.x == 0) part[((int64_t)(mode0 + q) * nchunks + chunk) * NRED + k] = t;
+    }
   }
 }
 
@@ -1056,11 +1119,12 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
     for (int b = 0; b < B; ++b) {
       if (!hs[b].newly) continue;
       const int k = des[b].k;
-      PLFEM_CUDA(cudaMemcpyAsync(Sdev.p, hs[b].S.data(), hs[b].S.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+      if (c > ROT_MAXIN || hs[b].S.size() > (size_t)ncvp * ncvp) throw StatusError(PLFEM_ERR_INTERNAL, "rotation tile too small");
+      double* Sb = Sdev.p + (size_t)b * ncvp * ncvp;      // the design's own slot: no wait between the designs
+      PLFEM_CUDA(cudaMemcpyAsync(Sb, hs[b].S.data(), hs[b].S.size() * sizeof(double), cudaMemcpyHostToDevice, st));
       const int64_t mb = bd.moff[b + 1] - bd.moff[b];
-      rotate_kernel<<<(unsigned)((mb + 127) / 128), 128, 0, st>>>(V[cur].p + bd.moff[b], ld, c, Sdev.p, k, mb, X.p + bd.moff[b], m);
+      rotate_forest_kernel<<<dim3((unsigned)((mb / 2 + 127) / 128), 1), 128, 0, st>>>(V[cur].p, ld, c, Sb, 0, k, moff + b, X.p, m);
       ctx->launches++;
-      PLFEM_CUDA(stream_wait(st));   // Sdev is reused by the next design
     }
     ndone = 0;
     for (const Host& h : hs) ndone += h.done;
@@ -1111,7 +1175,8 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
         }
       }
       PLFEM_CUDA(cudaMemcpyAsync(Sdev.p, S.data(), S.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-      const dim3 grot((unsigned)((bd.mmax + 127) / 128), B);
+      if (ncvp > ROT_MAXIN) throw StatusError(PLFEM_ERR_INVALID, "Lanczos basis larger than the rotation kernel's shared tile");
+      const dim3 grot((unsigned)((bd.mmax / 2 + 127) / 128), B);
       rotate_forest_kernel<<<grot, 128, 0, st>>>(V[cur].p, ld, ncvp, Sdev.p, sst, q, moff, V[nxt].p, ld);
       rotate_forest_kernel<<<grot, 128, 0, st>>>(BV[cur].p, ld, ncvp, Sdev.p, sst, q, moff, BV[nxt].p, ld);
       ctx->launches += 2;
@@ -1134,8 +1199,8 @@ void run_mode_metrics(plfem_ctx* ctx, const DevPattern& pat, const double* d_val
   part.alloc(ctx, (size_t)k * nchunks * NRED);
   lam.upload(ctx, lambda.data(), k);
   scale.alloc(ctx, k);
-  mode_partial_kernel<<<dim3(nchunks, k), 256, 0, st>>>(row0, row0 + n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz, d_in_core,
-                                                        (const double2*)X, ldx / 2, lam.p, part.p, nchunks);
+  mode_partial_kernel<<<dim3(nchunks, (k + MODE_PAIR - 1) / MODE_PAIR), 256, 0, st>>>(row0, row0 + n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz,
+                                                                                     d_in_core, (const double2*)X, ldx / 2, lam.p, k, part.p, nchunks);
   mode_final_kernel<<<(k + 63) / 64, 64, 0, st>>>(part.p, nchunks, k, lam.p, d_metrics, d_resid, scale.p);
   ctx->launches += 2;
   if (d_out_evecs) {

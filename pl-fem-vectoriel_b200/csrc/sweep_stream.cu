@@ -30,7 +30,7 @@ namespace plfem {
 namespace {
 
 constexpr int CHD = ST_CHUNK_DOUBLES;   // doubles per chunk
-constexpr int NS = 4;                   // ring stages per warp
+constexpr int NS = 2;                   // ring stages per warp
 constexpr int NLOC = ST_NLOC;           // local unknowns (pivots of the subtree + update set of its root)
 constexpr int MAXF = 32;                // fronts per subtree: one descriptor per lane
 constexpr int RB = 128;                 // rows of a forward row block (4 rows per lane)
