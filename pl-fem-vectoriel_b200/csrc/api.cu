@@ -888,24 +888,40 @@ static void profile_work(plfem_ctx* ctx, SolveWork& W, int repeat, double* out_m
     out_ms[7] = timed([&] { run_solve_backward(ctx, W.dplan, x4.p, SOLVE_NRHS); });
     out_bytes[7] = out_bytes[3] + 16.0 * m * (SOLVE_NRHS - 1);
     if (const char* tf = std::getenv("PLFEM_TRACE_FILE")) {
-      // stage clock of one dataflow forward sweep: [int64 ntasks, nlevels][int32 fptr[nlevels + 1]][int64 stamps[ntasks][8]]
-      const int64_t nt = (int64_t)W.dplan.st.ftasks.n, nl = W.dplan.nlevels;
-      DevBuf<long long> tr;
-      tr.alloc(ctx, (size_t)std::max<int64_t>(nt, 1) * 8); tr.zero();
-      PLFEM_CUDA(stream_wait(st));
-      set_sweep_trace(tr.p);
-      PLFEM_CUDA(cudaMemsetAsync(flush.p, 1, flush.n * sizeof(double), st));
-      run_solve_forward(ctx, W.dplan, b4.p, x4.p, SOLVE_NRHS);
-      PLFEM_CUDA(stream_wait(st));
-      set_sweep_trace(nullptr);
-      std::vector<long long> h((size_t)nt * 8);
-      tr.download(h.data(), h.size());
-      PLFEM_CUDA(stream_wait(st));
-      if (FILE* fh = std::fopen(tf, "wb")) {
-        std::fwrite(&nt, 8, 1, fh); std::fwrite(&nl, 8, 1, fh);
-        std::fwrite(W.dplan.st.fptr.data(), 4, (size_t)nl + 1, fh);
-        std::fwrite(h.data(), 8, h.size(), fh);
-        std::fclose(fh);
+      // stage clock of one dataflow forward sweep (file `tf`) and of the backward sweep that follows it (`tf`.bwd):
+      // [int64 ntasks, nlevels][int32 level ranges[nlevels + 1]][int64 stamps[ntasks][8]]
+      for (int dir = 0; dir < 2; ++dir) {
+        const StreamPlan& SP = W.dplan.st;
+        const int64_t nt = (int64_t)(dir == 0 ? SP.ftasks.n : SP.btasks.n), nl = W.dplan.nlevels;
+        DevBuf<long long> tr;
+        tr.alloc(ctx, (size_t)std::max<int64_t>(nt, 1) * 8); tr.zero();
+        PLFEM_CUDA(stream_wait(st));
+        PLFEM_CUDA(cudaMemsetAsync(flush.p, 1, flush.n * sizeof(double), st));
+        if (dir == 0) {
+          set_sweep_trace(tr.p);
+          run_solve_forward(ctx, W.dplan, b4.p, x4.p, SOLVE_NRHS);
+        } else {
+          run_solve_forward(ctx, W.dplan, b4.p, x4.p, SOLVE_NRHS);
+          PLFEM_CUDA(stream_wait(st));
+          PLFEM_CUDA(cudaMemsetAsync(flush.p, 2, flush.n * sizeof(double), st));
+          set_sweep_trace(tr.p);
+          run_solve_backward(ctx, W.dplan, x4.p, SOLVE_NRHS);
+        }
+        PLFEM_CUDA(stream_wait(st));
+        set_sweep_trace(nullptr);
+        std::vector<long long> h((size_t)nt * 8);
+        tr.download(h.data(), h.size());
+        PLFEM_CUDA(stream_wait(st));
+        // level ranges in task order: forward bottom level first; backward top level first (stored reversed: see build_level_plan)
+        std::vector<int32_t> ranges(nl + 1);
+        for (int l = 0; l <= nl; ++l) ranges[l] = dir == 0 ? SP.fptr[l] : SP.bptr[nl - l];
+        const std::string name = std::string(tf) + (dir == 0 ? "" : ".bwd");
+        if (FILE* fh = std::fopen(name.c_str(), "wb")) {
+          std::fwrite(&nt, 8, 1, fh); std::fwrite(&nl, 8, 1, fh);
+          std::fwrite(ranges.data(), 4, (size_t)nl + 1, fh);
+          std::fwrite(h.data(), 8, h.size(), fh);
+          std::fclose(fh);
+        }
       }
     }
   }

@@ -763,6 +763,8 @@ __global__ void __launch_bounds__(32 * TW) level_backward_kernel(const LevelTask
     ti = sm.ticket;
   }
   const LevelTask t = tasks[ti];
+  long long* const tr = FUSED ? g_sweep_trace : nullptr;
+  trace_stamp(tr, ti, 1, tid);
   const int k0 = t.r0, kn = t.n, nk = t.nch;   // this task's slab of the update unknowns; slabs of the front
   const int nw = (t.s2 + 31) >> 5;             // warps with pivot columns
   if (warp < nw && lane == 0) {
@@ -785,10 +787,12 @@ __global__ void __launch_bounds__(32 * TW) level_backward_kernel(const LevelTask
   // z1 of this thread's pivot (forward sweep): requested before the dependency wait, used at the very end
   double z[NR];
   ldcg_opt<NR>(x, has_col ? t.g0 + tid : -1, z);
+  trace_stamp(tr, ti, 2, tid);
   if (FUSED && t.need > 0) {                   // the parent's unknowns are final
     if (warp == 0) wait_counter(sync + 2 + nfronts + t.dep, t.need, lane, status);
     __syncthreads();
   }
+  trace_stamp(tr, ti, 3, tid);
   {
     double g[KSMAX / (32 * TW)][NR];           // the slab of x2: one batch of gathers
 #pragma unroll
@@ -801,10 +805,12 @@ __global__ void __launch_bounds__(32 * TW) level_backward_kernel(const LevelTask
     }
   }
   __syncthreads();
+  trace_stamp(tr, ti, 4, tid);
   double a[NR];
 #pragma unroll
   for (int r = 0; r < NR; ++r) a[r] = 0.0;
   if (warp < nw) warp_multiply<NR>(pp, kn, has_col, [&](int c, double (&y)[NR]) { ld_loc<NR>(sm.cv, c, y); }, a);
+  trace_stamp(tr, ti, 7, tid);
   bool finish = true;
   if (nk > 1) {
     const int s2p = (t.s2 + 3) & ~3;
@@ -834,12 +840,14 @@ __global__ void __launch_bounds__(32 * TW) level_backward_kernel(const LevelTask
       for (int r = 0; r < NR; ++r) z[r] -= a[r];
       stg_v<NR>(x, t.g0 + tid, z);
     }
+    trace_stamp(tr, ti, 5, tid);
     if (FUSED && t.sig >= 0) {
       __threadfence();
       __syncthreads();
       if (tid == 0) atomicAdd(sync + 2 + nfronts + t.sig, 1);
     }
   }
+  trace_stamp(tr, ti, 6, tid);
   if (warp < nw) pp.drain();
 }
 
