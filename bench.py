@@ -408,6 +408,11 @@ def run_ours(args):
     # FP64 side of the factorisation: flops of the plan (inverse + W + Schur) over the measured factorisation time
     fl = sum(f[4].factor_flops for f in fo)
     kernels["factorize"]["fp64_tflops"] = fl / (prof["factorize"][0] * 1e-3) / 1e12
+    # against the FP64 ceilings measured on this pool's B200 (scripts/micro/fp64_peak.cu, profiles/r02_fp64_peak.txt): DMMA
+    # mma.sync m8n8k4 37.0, CUDA-core FMA 34.1, cuBLAS DGEMM 35.1 TFLOP/s.  The phase is inverse + extend-add + two GEMMs + packs
+    kernels["factorize"]["fp64_peak_tflops"] = 37.0
+    kernels["factorize"]["fp64_peak_source"] = "measured: mma.sync.m8n8k4.f64 chain, profiles/r02_fp64_peak.txt"
+    kernels["factorize"]["frac_of_fp64_peak"] = kernels["factorize"]["fp64_tflops"] / 37.0
     kernels["factorize"]["factor_gflop"] = fl / 1e9
     fused = not os.environ.get("PLFEM_SWEEP", "").startswith("l")
     # launches of one sweep: the TMA-streamed bottom subtrees + ONE dataflow launch for every level above them (or, with

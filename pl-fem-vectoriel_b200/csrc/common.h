@@ -235,25 +235,27 @@ void build_dev_plan(plfem_ctx* ctx, const FrontPlan& P, DevPlan& D);
 void build_stream_plan(plfem_ctx* ctx, const FrontPlan& P, const std::vector<int32_t>& uoff, std::vector<uint8_t>& in_sub, StreamPlan& S);
 void build_level_plan(plfem_ctx* ctx, const FrontPlan& P, const std::vector<int32_t>& uoff, const std::vector<uint8_t>& in_sub,
                       const std::vector<int32_t>& goff, StreamPlan& S);
-void launch_level_forward(plfem_ctx* ctx, const DevPlan& D, int level, const double* rhs, double* out, int nrhs, bool pdl);
-void launch_level_backward(plfem_ctx* ctx, const DevPlan& D, int level, double* x, int nrhs, bool pdl);
+void launch_level_forward(plfem_ctx* ctx, const DevPlan& D, int level, const double* rhs, double* out, int nrhs, bool pdl, const uint8_t* active);
+void launch_level_backward(plfem_ctx* ctx, const DevPlan& D, int level, double* x, int nrhs, bool pdl, const uint8_t* active);
 // every level above the bottom subtrees in ONE launch: tasks take tickets in level order and wait on per-front counters
 void reset_sweep_counters(plfem_ctx* ctx, const DevPlan& D);
 void set_sweep_trace(long long* p);   // measurement only: stage clock of the dataflow forward sweep (null = off)
-void launch_fused_forward(plfem_ctx* ctx, const DevPlan& D, const double* rhs, double* out, int nrhs, bool pdl);
-void launch_fused_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs, bool pdl);
+void launch_fused_forward(plfem_ctx* ctx, const DevPlan& D, const double* rhs, double* out, int nrhs, bool pdl, const uint8_t* active);
+void launch_fused_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs, bool pdl, const uint8_t* active);
 void launch_stream_pack(plfem_ctx* ctx, const DevPlan& D);
-void launch_stream_forward(plfem_ctx* ctx, const DevPlan& D, const double* rhs, double* out, int nrhs, bool pdl);
-void launch_stream_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs, bool pdl);
+void launch_stream_forward(plfem_ctx* ctx, const DevPlan& D, const double* rhs, double* out, int nrhs, bool pdl, const uint8_t* active);
+void launch_stream_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs, bool pdl, const uint8_t* active);
 // d_sigma_node: the shift of the design each (permuted) node belongs to — a forest of designs is one problem
 void launch_front_load(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, const double* d_vals, const double* d_sigma_node);
 void run_factorization(plfem_ctx* ctx, const DevPlan& D);
 // solves (A - sigma B) x = b in the permuted layout (Hx, Hy of a node adjacent), b and x of length 2n (must not alias);
 // with nrhs = SOLVE_NRHS the right-hand sides are interleaved: entry i of right-hand side r at b[i * nrhs + r]
 constexpr int SOLVE_NRHS = 4;   // block size of the multi-right-hand-side sweeps (block Lanczos)
-void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x, int nrhs = 1);
-void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double* z, int nrhs = 1);
-void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs = 1, bool reset_counters = true);
+// active_node (optional): one flag per permuted node of the forest — fronts of designs whose flag is 0 are skipped (their rows of x
+// are left untouched): the refinement solve of a forest in which only some designs need it
+void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x, int nrhs = 1, const uint8_t* active_node = nullptr);
+void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double* z, int nrhs = 1, const uint8_t* active_node = nullptr);
+void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs = 1, bool reset_counters = true, const uint8_t* active_node = nullptr);
 
 // ---- Lanczos + mode reductions (eigen.cu) ----------------------------------------------------------
 struct EigenResult {
@@ -261,6 +263,7 @@ struct EigenResult {
   int nconv = 0, n_op = 0, n_restart = 0, n_block_op = 0;
   int refine_steps = 0;       // refinement steps per operator application actually used
   int relaxed_from = -1;      // block step from which the relaxed operator (one refinement step fewer) was applied
+  int refine_skipped = 0;     // designs of the forest that skip the refinement solve the others need
 };
 // A forest of independent designs laid out as one block-diagonal problem: design b owns the permuted nodes
 // [noff[b], noff[b+1]) and the vector rows [moff[b], moff[b+1]) (two unknowns per node).
@@ -301,7 +304,7 @@ void launch_spmm_b(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, 
                    int64_t ld = 0);
 // t = b - (A - sigma B) x, x / b / t with nrhs interleaved right-hand sides
 void launch_resid_k(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, const double* d_sigma_node, const double* x,
-                    const double* b, double* t, int nrhs = 1);
+                    const double* b, double* t, int nrhs = 1, const uint8_t* active_node = nullptr);
 
 void launch_axpy(plfem_ctx* ctx, double* x, const double* dx, int64_t m);
 void symmetric_eigen(int n, std::vector<double>& a /* n*n col-major in, eigenvectors out */, std::vector<double>& w);

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) resid_k_kernel(int32_t n, const int32_t* 
                                                       const int32_t* __restrict__ col, const double* __restrict__ vals,
                                                       int64_t nnz, const double* __restrict__ sigma_node,
                                                       const double* __restrict__ x, const double* __restrict__ b,
-                                                      double* __restrict__ t) {
+                                                      double* __restrict__ t, const uint8_t* __restrict__ active) {
   constexpr int TPR = 4;
   const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t row = gid / TPR;
@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(256) resid_k_kernel(int32_t n, const int32_t* 
   double ax[NR], ay[NR];
 #pragma unroll
   for (int r = 0; r < NR; ++r) { ax[r] = 0.0; ay[r] = 0.0; }
-  if (row < n) {
+  const bool live = row < n && (!active || active[row]);    // rows of a design that takes no part: nothing read, nothing written
+  if (live) {
     const double sigma = sigma_node[row];
     for (int32_t z = rowptr[row] + lane; z < rowptr[row + 1]; z += TPR) {
       const double sm = sigma * vals[(int64_t)S_MINV * nnz + z];
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(256) resid_k_kernel(int32_t n, const int32_t* 
       ax[r] += __shfl_down_sync(0xffffffffu, ax[r], off, TPR);
       ay[r] += __shfl_down_sync(0xffffffffu, ay[r], off, TPR);
     }
-    if (row < n && lane == 0) {
+    if (live && lane == 0) {
       const int64_t o = 2 * row * NR + r;
       t[o] = b[o] - ax[r];
       t[o + NR] = b[o + NR] - ay[r];
@@ -151,11 +152,12 @@ __global__ void __launch_bounds__(256) interleave_kernel(const double* __restric
 
 // out (P columns, leading dimension ld) = interleaved x (+ interleaved dx when given)
 __global__ void __launch_bounds__(256) deinterleave_add_kernel(const double* __restrict__ x, const double* __restrict__ dx, int64_t ld,
-                                                               int64_t m, double* __restrict__ out) {
+                                                               int64_t m, double* __restrict__ out, const uint8_t* __restrict__ active) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= m) return;
+  const bool corr = dx && (!active || active[i >> 1]);     // the refinement correction exists only for the designs that took part
 #pragma unroll
-  for (int r = 0; r < SOLVE_NRHS; ++r) out[r * ld + i] = x[i * SOLVE_NRHS + r] + (dx ? dx[i * SOLVE_NRHS + r] : 0.0);
+  for (int r = 0; r < SOLVE_NRHS; ++r) out[r * ld + i] = x[i * SOLVE_NRHS + r] + (corr ? dx[i * SOLVE_NRHS + r] : 0.0);
 }
 
 __global__ void __launch_bounds__(256) add_kernel(double* __restrict__ x, const double* __restrict__ dx, int64_t m) {
@@ -646,12 +648,12 @@ void launch_spmm_b(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, 
 }
 
 void launch_resid_k(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals, const double* d_sigma_node, const double* x,
-                    const double* b, double* t, int nrhs) {
+                    const double* b, double* t, int nrhs, const uint8_t* active) {
   const unsigned g = (unsigned)(((int64_t)pat.n * 4 + 255) / 256);
   if (nrhs == 1)
-    resid_k_kernel<1><<<g, 256, 0, ctx->stream>>>(pat.n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz, d_sigma_node, x, b, t);
+    resid_k_kernel<1><<<g, 256, 0, ctx->stream>>>(pat.n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz, d_sigma_node, x, b, t, active);
   else
-    resid_k_kernel<SOLVE_NRHS><<<g, 256, 0, ctx->stream>>>(pat.n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz, d_sigma_node, x, b, t);
+    resid_k_kernel<SOLVE_NRHS><<<g, 256, 0, ctx->stream>>>(pat.n, pat.rowptr.p, pat.col.p, d_vals, pat.nnz, d_sigma_node, x, b, t, active);
   PLFEM_CUDA(cudaGetLastError());
   ctx->launches++;
 }
@@ -891,18 +893,22 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
   // applications use the relaxed operator (PLFEM_RELAX_AT, 0 = never).
   cudaGraph_t graph = nullptr, graph_lo = nullptr; cudaGraphExec_t gexec = nullptr, gexec_lo = nullptr; int graph_nodes = 0, graph_nodes_lo = 0;
   struct GraphGuard { cudaGraph_t* g; cudaGraphExec_t* e; ~GraphGuard() { if (*e) cudaGraphExecDestroy(*e); if (*g) cudaGraphDestroy(*g); } } guard{&graph, &gexec}, guard_lo{&graph_lo, &gexec_lo};
+  DevBuf<uint8_t> refine_node;      // per node: its design takes part in the refinement solve (only set when some designs do not)
+  const uint8_t* d_refine = nullptr;
   auto capture_operator = [&](int rsteps, cudaGraph_t& graph, cudaGraphExec_t& gexec, int& graph_nodes) {
     const int before = ctx->launches;
+    // designs whose probe found the raw solve accurate skip the (single) refinement solve of the others
+    const uint8_t* act = rsteps == 1 ? d_refine : nullptr;
     PLFEM_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     try {
       // interleaved right-hand sides inside the solve: opin -> xi (+ refinement) -> R (columns again)
       run_solve(ctx, D, opin.p, xi.p, P);
       for (int it = 0; it < rsteps; ++it) {
-        launch_resid_k(ctx, pat, d_vals, d_sigma_node, xi.p, opin.p, rt.p, P);
-        run_solve(ctx, D, rt.p, rdx.p, P);
+        launch_resid_k(ctx, pat, d_vals, d_sigma_node, xi.p, opin.p, rt.p, P, act);
+        run_solve(ctx, D, rt.p, rdx.p, P, act);
         if (it + 1 < rsteps) launch_axpy(ctx, xi.p, rdx.p, m * P);
       }
-      deinterleave_add_kernel<<<gm, 256, 0, st>>>(xi.p, rsteps > 0 ? rdx.p : nullptr, ld, m, R.p);
+      deinterleave_add_kernel<<<gm, 256, 0, st>>>(xi.p, rsteps > 0 ? rdx.p : nullptr, ld, m, R.p, act);
       ctx->launches++;
     } catch (...) {
       cudaGraph_t dead = nullptr; cudaStreamEndCapture(st, &dead); if (dead) cudaGraphDestroy(dead);
@@ -950,6 +956,7 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
     nrm.download(hn.data(), hn.size());
     PLFEM_CUDA(stream_wait(st));
     rsteps = 0;
+    std::vector<int> need(B, 0);
     for (int b = 0; b < B; ++b) {
       double nr = 0.0, nbv = 0.0;
       for (int sl = 0; sl < RSPLIT; ++sl) { nr += hn[((size_t)b * RSPLIT + sl) * 2]; nbv += hn[((size_t)b * RSPLIT + sl) * 2 + 1]; }
@@ -964,7 +971,25 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
       }
       // rho <= 1e-9: the raw solve is already three decades below the Lanczos tolerance (symmetrised pivot-block inverses
       // give 1e-10 on the reference's meshes): no refinement solve at all
-      rsteps = std::max(rsteps, rho <= 1e-9 ? 0 : (rho <= 1e-4 ? 1 : (rho <= 2e-3 ? 2 : (rho <= 1e-2 ? 3 : 5))));
+      const int mine = rho <= 1e-9 ? 0 : (rho <= 1e-4 ? 1 : (rho <= 2e-3 ? 2 : (rho <= 1e-2 ? 3 : 5)));
+      need[b] = mine;
+      rsteps = std::max(rsteps, mine);
+    }
+    // a forest in which the step count is ONE for some designs and zero for others: the refinement solve skips the fronts,
+    // rows and corrections of the designs that do not need it (one poorly conditioned mesh doubled the sweeps of
+    // the other eleven).  With two or more steps every design takes them all.
+    if (rsteps == 1) {
+      int nskip = 0;
+      for (int b = 0; b < B; ++b) nskip += (need[b] == 0 && des[b].status == PLFEM_OK);
+      if (nskip > 0) {
+        std::vector<uint8_t> flag((size_t)(m / 2), 1);
+        for (int b = 0; b < B; ++b)
+          if (need[b] == 0) std::fill(flag.begin() + bd.moff[b] / 2, flag.begin() + bd.moff[b + 1] / 2, (uint8_t)0);
+        refine_node.upload(ctx, flag);
+        PLFEM_CUDA(stream_wait(st));
+        d_refine = refine_node.p;
+        res.refine_skipped = nskip;
+      }
     }
   }
   res.refine_steps = rsteps;

@@ -538,47 +538,47 @@ bool use_fused_sweeps() {      // PLFEM_SWEEP=levels: one launch per elimination
 // bottom subtrees, then ONE dataflow launch for everything above them (sweep_stream.cu): its tasks take tickets in level
 // order and wait on per-front counters, so a front starts as soon as its own children are done and no launch boundary
 // (12 us each, fifteen of them per sweep of a 7-core design) separates the levels.
-void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double* z, int nrhs) {
+void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double* z, int nrhs, const uint8_t* active) {
   if (nrhs != 1 && nrhs != SOLVE_NRHS) throw StatusError(PLFEM_ERR_INTERNAL, "unsupported number of right-hand sides");
   const bool pdl = use_pdl();
   const bool fused = use_fused_sweeps();
   reset_sweep_counters(ctx, D);                // forward and backward counters, before the first launch of the solve
   bool first = true;     // the first launch follows kernels that are not PDL-aware: plain launch
   if (D.st.n_subs > 0) {
-    launch_stream_forward(ctx, D, b, z, nrhs, false);
+    launch_stream_forward(ctx, D, b, z, nrhs, false, active);
     first = false;
   }
   if (fused) {
-    launch_fused_forward(ctx, D, b, z, nrhs, pdl && !first);
+    launch_fused_forward(ctx, D, b, z, nrhs, pdl && !first, active);
     return;
   }
   for (int l = 0; l < D.nlevels; ++l) {
     if (D.st.fptr[l + 1] == D.st.fptr[l]) continue;
-    launch_level_forward(ctx, D, l, b, z, nrhs, pdl && !first);
+    launch_level_forward(ctx, D, l, b, z, nrhs, pdl && !first, active);
     first = false;
   }
 }
 
 // must follow run_solve_forward on the same stream (its launches may be PDL-chained to the forward ones); reset_counters =
 // false when that forward sweep has just cleared the dataflow counters (run_solve)
-void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs, bool reset_counters) {
+void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs, bool reset_counters, const uint8_t* active) {
   const bool pdl = use_pdl();
   if (reset_counters) reset_sweep_counters(ctx, D);
   if (use_fused_sweeps()) {
-    launch_fused_backward(ctx, D, x, nrhs, pdl && !reset_counters);
+    launch_fused_backward(ctx, D, x, nrhs, pdl && !reset_counters, active);
   } else {
     for (int l = D.nlevels - 1; l >= 0; --l) {
       if (D.st.bptr[l] == D.st.bptr[l + 1]) continue;
-      launch_level_backward(ctx, D, l, x, nrhs, pdl && !reset_counters);
+      launch_level_backward(ctx, D, l, x, nrhs, pdl && !reset_counters, active);
       reset_counters = false;
     }
   }
-  if (D.st.n_subs > 0) launch_stream_backward(ctx, D, x, nrhs, pdl);
+  if (D.st.n_subs > 0) launch_stream_backward(ctx, D, x, nrhs, pdl, active);
 }
 
-void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x, int nrhs) {
-  run_solve_forward(ctx, D, b, x, nrhs);
-  run_solve_backward(ctx, D, x, nrhs, false);
+void run_solve(plfem_ctx* ctx, const DevPlan& D, const double* b, double* x, int nrhs, const uint8_t* active) {
+  run_solve_forward(ctx, D, b, x, nrhs, active);
+  run_solve_backward(ctx, D, x, nrhs, false, active);
 }
 
 }  // namespace plfem

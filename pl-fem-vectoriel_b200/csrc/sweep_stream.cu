@@ -354,11 +354,13 @@ __device__ __forceinline__ void fwd_block(Pipe& pp, StreamSmem<NR>& sm, int s2, 
 template <int NR, bool PDL>
 __global__ void __launch_bounds__(32) stream_forward_kernel(const StreamSub* __restrict__ subs, const int4* __restrict__ fronts,
                                                             const double* __restrict__ stream, const double* __restrict__ rhs,
-                                                            double* __restrict__ out, double* __restrict__ upd, int32_t* status) {
+                                                            double* __restrict__ out, double* __restrict__ upd, int32_t* status,
+                                                            const uint8_t* __restrict__ active) {
   __shared__ StreamSmem<NR> sm;
   const int lane = threadIdx.x;
   if (PDL) griddep_launch_dependents();
   const StreamSub sb = subs[blockIdx.x];
+  if (active && !active[sb.g0 >> 1]) return;        // a design of the forest that takes no part in this solve (refinement it does not need)
   if (lane == 0) {
     for (int s = 0; s < NS; ++s) mbar_init(sm.bar + s, 1);
     fence_mbar_init();
@@ -440,11 +442,12 @@ __device__ __forceinline__ void bwd_front(Pipe& pp, StreamSmem<NR>& sm, int s2, 
 template <int NR, bool PDL>
 __global__ void __launch_bounds__(32) stream_backward_kernel(const StreamSub* __restrict__ subs, const int4* __restrict__ fronts,
                                                              const double* __restrict__ stream, const int32_t* __restrict__ strct,
-                                                             double* __restrict__ x, int32_t* status) {
+                                                             double* __restrict__ x, int32_t* status, const uint8_t* __restrict__ active) {
   __shared__ StreamSmem<NR> sm;
   const int lane = threadIdx.x;
   if (PDL) griddep_launch_dependents();
   const StreamSub sb = subs[blockIdx.x];
+  if (active && !active[sb.g0 >> 1]) return;
   if (lane == 0) {
     for (int s = 0; s < NS; ++s) mbar_init(sm.bar + s, 1);
     fence_mbar_init();
@@ -629,7 +632,8 @@ __global__ void __launch_bounds__(32 * TW) level_forward_kernel(const LevelTask*
                                                                 const double* __restrict__ stream, const int32_t* __restrict__ cptr,
                                                                 const int32_t* __restrict__ child, const int32_t* __restrict__ cmap_ptr,
                                                                 const int32_t* __restrict__ cmap, const int32_t* __restrict__ sptr,
-                                                                const int32_t* __restrict__ uoff, RhsView rv, int32_t* status, int32_t* sync) {
+                                                                const int32_t* __restrict__ uoff, RhsView rv, int32_t* status, int32_t* sync,
+                                                                const uint8_t* __restrict__ active) {
   __shared__ LevelFwdSmem<NR> sm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (PDL) griddep_launch_dependents();
@@ -643,6 +647,8 @@ __global__ void __launch_bounds__(32 * TW) level_forward_kernel(const LevelTask*
     ti = sm.ticket;
   }
   const LevelTask t = tasks[ti];
+  // a design that takes no part in this solve: all fronts of its tree are skipped, so nobody waits for this task's signal
+  if (active && !active[t.g0 >> 1]) return;
   trace_stamp(tr, ti, 1, tid);
   const int nw = (t.n + 31) >> 5;              // warps with rows
   if (warp < nw && lane == 0) {
@@ -752,7 +758,8 @@ __global__ void __launch_bounds__(32 * TW) level_forward_kernel(const LevelTask*
 template <int NR, bool PDL, bool FUSED>
 __global__ void __launch_bounds__(32 * TW) level_backward_kernel(const LevelTask* __restrict__ tasks, const double* __restrict__ stream,
                                                                  const int32_t* __restrict__ strct, double* __restrict__ x,
-                                                                 double* __restrict__ part, int32_t* status, int32_t* sync, int nfronts) {
+                                                                 double* __restrict__ part, int32_t* status, int32_t* sync, int nfronts,
+                                                                 const uint8_t* __restrict__ active) {
   __shared__ LevelBwdSmem<NR> sm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (PDL) griddep_launch_dependents();
@@ -763,6 +770,7 @@ __global__ void __launch_bounds__(32 * TW) level_backward_kernel(const LevelTask
     ti = sm.ticket;
   }
   const LevelTask t = tasks[ti];
+  if (active && !active[t.g0 >> 1]) return;   // see level_forward_kernel
   long long* const tr = FUSED ? g_sweep_trace : nullptr;
   trace_stamp(tr, ti, 1, tid);
   const int k0 = t.r0, kn = t.n, nk = t.nch;   // this task's slab of the update unknowns; slabs of the front
@@ -1080,54 +1088,54 @@ void launch_warp_ctas(void (*kernel)(KArgs...), bool pdl, int grid, int threads,
 }
 
 template <bool FUSED>
-void launch_forward_tasks(plfem_ctx* ctx, const DevPlan& D, const LevelTask* tasks, int n, const double* rhs, double* out, int nrhs, bool pdl) {
+void launch_forward_tasks(plfem_ctx* ctx, const DevPlan& D, const LevelTask* tasks, int n, const double* rhs, double* out, int nrhs, bool pdl, const uint8_t* active) {
   const StreamPlan& S = D.st;
   const RhsView rv{rhs, out, D.upd.p};
   if (nrhs == 1) {
-    if (pdl) launch_warp_ctas(level_forward_kernel<1, true, FUSED>, true, n, 32 * TW, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p);
-    else launch_warp_ctas(level_forward_kernel<1, false, FUSED>, false, n, 32 * TW, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p);
+    if (pdl) launch_warp_ctas(level_forward_kernel<1, true, FUSED>, true, n, 32 * TW, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p, active);
+    else launch_warp_ctas(level_forward_kernel<1, false, FUSED>, false, n, 32 * TW, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p, active);
   } else {
-    if (pdl) launch_warp_ctas(level_forward_kernel<SOLVE_NRHS, true, FUSED>, true, n, 32 * TW, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p);
-    else launch_warp_ctas(level_forward_kernel<SOLVE_NRHS, false, FUSED>, false, n, 32 * TW, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p);
+    if (pdl) launch_warp_ctas(level_forward_kernel<SOLVE_NRHS, true, FUSED>, true, n, 32 * TW, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p, active);
+    else launch_warp_ctas(level_forward_kernel<SOLVE_NRHS, false, FUSED>, false, n, 32 * TW, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p, active);
   }
   ctx->launches++;
 }
 
 template <bool FUSED>
-void launch_backward_tasks(plfem_ctx* ctx, const DevPlan& D, const LevelTask* tasks, int n, double* x, int nrhs, bool pdl) {
+void launch_backward_tasks(plfem_ctx* ctx, const DevPlan& D, const LevelTask* tasks, int n, double* x, int nrhs, bool pdl, const uint8_t* active) {
   const StreamPlan& S = D.st;
   if (nrhs == 1) {
-    if (pdl) launch_warp_ctas(level_backward_kernel<1, true, FUSED>, true, n, 32 * TW, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts);
-    else launch_warp_ctas(level_backward_kernel<1, false, FUSED>, false, n, 32 * TW, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts);
+    if (pdl) launch_warp_ctas(level_backward_kernel<1, true, FUSED>, true, n, 32 * TW, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts, active);
+    else launch_warp_ctas(level_backward_kernel<1, false, FUSED>, false, n, 32 * TW, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts, active);
   } else {
-    if (pdl) launch_warp_ctas(level_backward_kernel<SOLVE_NRHS, true, FUSED>, true, n, 32 * TW, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts);
-    else launch_warp_ctas(level_backward_kernel<SOLVE_NRHS, false, FUSED>, false, n, 32 * TW, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts);
+    if (pdl) launch_warp_ctas(level_backward_kernel<SOLVE_NRHS, true, FUSED>, true, n, 32 * TW, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts, active);
+    else launch_warp_ctas(level_backward_kernel<SOLVE_NRHS, false, FUSED>, false, n, 32 * TW, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts, active);
   }
   ctx->launches++;
 }
 }  // namespace
 
-void launch_stream_forward(plfem_ctx* ctx, const DevPlan& D, const double* rhs, double* out, int nrhs, bool pdl) {
+void launch_stream_forward(plfem_ctx* ctx, const DevPlan& D, const double* rhs, double* out, int nrhs, bool pdl, const uint8_t* active) {
   const StreamPlan& S = D.st;
   if (S.n_subs == 0) return;
   if (nrhs == 1) {
-    if (pdl) launch_warp_ctas(stream_forward_kernel<1, true>, true, S.n_subs, 32, ctx->stream, S.subs.p, S.fronts.p, S.sfwd.p, rhs, out, D.upd.p, D.status.p);
-    else launch_warp_ctas(stream_forward_kernel<1, false>, false, S.n_subs, 32, ctx->stream, S.subs.p, S.fronts.p, S.sfwd.p, rhs, out, D.upd.p, D.status.p);
+    if (pdl) launch_warp_ctas(stream_forward_kernel<1, true>, true, S.n_subs, 32, ctx->stream, S.subs.p, S.fronts.p, S.sfwd.p, rhs, out, D.upd.p, D.status.p, active);
+    else launch_warp_ctas(stream_forward_kernel<1, false>, false, S.n_subs, 32, ctx->stream, S.subs.p, S.fronts.p, S.sfwd.p, rhs, out, D.upd.p, D.status.p, active);
   } else {
-    if (pdl) launch_warp_ctas(stream_forward_kernel<SOLVE_NRHS, true>, true, S.n_subs, 32, ctx->stream, S.subs.p, S.fronts.p, S.sfwd.p, rhs, out, D.upd.p, D.status.p);
-    else launch_warp_ctas(stream_forward_kernel<SOLVE_NRHS, false>, false, S.n_subs, 32, ctx->stream, S.subs.p, S.fronts.p, S.sfwd.p, rhs, out, D.upd.p, D.status.p);
+    if (pdl) launch_warp_ctas(stream_forward_kernel<SOLVE_NRHS, true>, true, S.n_subs, 32, ctx->stream, S.subs.p, S.fronts.p, S.sfwd.p, rhs, out, D.upd.p, D.status.p, active);
+    else launch_warp_ctas(stream_forward_kernel<SOLVE_NRHS, false>, false, S.n_subs, 32, ctx->stream, S.subs.p, S.fronts.p, S.sfwd.p, rhs, out, D.upd.p, D.status.p, active);
   }
   ctx->launches++;
 }
 
-void launch_level_forward(plfem_ctx* ctx, const DevPlan& D, int level, const double* rhs, double* out, int nrhs, bool pdl) {
+void launch_level_forward(plfem_ctx* ctx, const DevPlan& D, int level, const double* rhs, double* out, int nrhs, bool pdl, const uint8_t* active) {
   const StreamPlan& S = D.st;
-  launch_forward_tasks<false>(ctx, D, S.ftasks.p + S.fptr[level], S.fptr[level + 1] - S.fptr[level], rhs, out, nrhs, pdl);
+  launch_forward_tasks<false>(ctx, D, S.ftasks.p + S.fptr[level], S.fptr[level + 1] - S.fptr[level], rhs, out, nrhs, pdl, active);
 }
 
-void launch_level_backward(plfem_ctx* ctx, const DevPlan& D, int level, double* x, int nrhs, bool pdl) {
+void launch_level_backward(plfem_ctx* ctx, const DevPlan& D, int level, double* x, int nrhs, bool pdl, const uint8_t* active) {
   const StreamPlan& S = D.st;
-  launch_backward_tasks<false>(ctx, D, S.btasks.p + S.bptr[level + 1], S.bptr[level] - S.bptr[level + 1], x, nrhs, pdl);
+  launch_backward_tasks<false>(ctx, D, S.btasks.p + S.bptr[level + 1], S.bptr[level] - S.bptr[level + 1], x, nrhs, pdl, active);
 }
 
 void set_sweep_trace(long long* p) { PLFEM_CUDA(cudaMemcpyToSymbol(g_sweep_trace, &p, sizeof(p))); }
@@ -1136,25 +1144,25 @@ void reset_sweep_counters(plfem_ctx* ctx, const DevPlan& D) {
   if (D.st.sync.n) PLFEM_CUDA(cudaMemsetAsync(D.st.sync.p, 0, D.st.sync.n * sizeof(int32_t), ctx->stream));
 }
 
-void launch_fused_forward(plfem_ctx* ctx, const DevPlan& D, const double* rhs, double* out, int nrhs, bool pdl) {
+void launch_fused_forward(plfem_ctx* ctx, const DevPlan& D, const double* rhs, double* out, int nrhs, bool pdl, const uint8_t* active) {
   const StreamPlan& S = D.st;
-  if (S.ftasks.n > 0) launch_forward_tasks<true>(ctx, D, S.ftasks.p, (int)S.ftasks.n, rhs, out, nrhs, pdl);
+  if (S.ftasks.n > 0) launch_forward_tasks<true>(ctx, D, S.ftasks.p, (int)S.ftasks.n, rhs, out, nrhs, pdl, active);
 }
 
-void launch_fused_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs, bool pdl) {
+void launch_fused_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs, bool pdl, const uint8_t* active) {
   const StreamPlan& S = D.st;
-  if (S.btasks.n > 0) launch_backward_tasks<true>(ctx, D, S.btasks.p, (int)S.btasks.n, x, nrhs, pdl);
+  if (S.btasks.n > 0) launch_backward_tasks<true>(ctx, D, S.btasks.p, (int)S.btasks.n, x, nrhs, pdl, active);
 }
 
-void launch_stream_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs, bool pdl) {
+void launch_stream_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs, bool pdl, const uint8_t* active) {
   const StreamPlan& S = D.st;
   if (S.n_subs == 0) return;
   if (nrhs == 1) {
-    if (pdl) launch_warp_ctas(stream_backward_kernel<1, true>, true, S.n_subs, 32, ctx->stream, S.subs.p, S.fronts.p, S.sbwd.p, D.strct.p, x, D.status.p);
-    else launch_warp_ctas(stream_backward_kernel<1, false>, false, S.n_subs, 32, ctx->stream, S.subs.p, S.fronts.p, S.sbwd.p, D.strct.p, x, D.status.p);
+    if (pdl) launch_warp_ctas(stream_backward_kernel<1, true>, true, S.n_subs, 32, ctx->stream, S.subs.p, S.fronts.p, S.sbwd.p, D.strct.p, x, D.status.p, active);
+    else launch_warp_ctas(stream_backward_kernel<1, false>, false, S.n_subs, 32, ctx->stream, S.subs.p, S.fronts.p, S.sbwd.p, D.strct.p, x, D.status.p, active);
   } else {
-    if (pdl) launch_warp_ctas(stream_backward_kernel<SOLVE_NRHS, true>, true, S.n_subs, 32, ctx->stream, S.subs.p, S.fronts.p, S.sbwd.p, D.strct.p, x, D.status.p);
-    else launch_warp_ctas(stream_backward_kernel<SOLVE_NRHS, false>, false, S.n_subs, 32, ctx->stream, S.subs.p, S.fronts.p, S.sbwd.p, D.strct.p, x, D.status.p);
+    if (pdl) launch_warp_ctas(stream_backward_kernel<SOLVE_NRHS, true>, true, S.n_subs, 32, ctx->stream, S.subs.p, S.fronts.p, S.sbwd.p, D.strct.p, x, D.status.p, active);
+    else launch_warp_ctas(stream_backward_kernel<SOLVE_NRHS, false>, false, S.n_subs, 32, ctx->stream, S.subs.p, S.fronts.p, S.sbwd.p, D.strct.p, x, D.status.p, active);
   }
   ctx->launches++;
 }
