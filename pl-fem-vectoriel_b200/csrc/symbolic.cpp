@@ -9,6 +9,7 @@
 #include <atomic>
 #include <cstring>
 #include <thread>
+#include <type_traits>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -310,22 +311,28 @@ struct Dissector {
         for (int32_t r = 0; r < n; ++r) rank4[Ld[r]].r[d] = r;
         sc.dl[d].assign(n + 2, 0); sc.dr[d].assign(n + 2, 0);
       }
-      for (int32_t i = 0; i < n; ++i) {
-        const int32_t v = L0[i];
-        const Rk rv = rank4[v];
-        int32_t hi[ND], lo[ND];
-        for (int d = 0; d < ND; ++d) hi[d] = lo[d] = rv.r[d];
-        for (int32_t q = adj.rowptr[v]; q < adj.rowptr[v + 1]; ++q) {
-          const int32_t w = adj.col[q];
-          if (side[w] != cur) continue;
-          const Rk rw = rank4[w];
-          for (int d = 0; d < ND; ++d) { hi[d] = std::max(hi[d], rw.r[d]); lo[d] = std::min(lo[d], rw.r[d]); }
+      // (small subsets examine two directions only: most of the nodes sit in such subsets, and the pass over their
+      // neighbours is the hot loop of the whole analysis)
+      auto neighbour_pass = [&](auto nd_tag) {
+        constexpr int NDIR = decltype(nd_tag)::value;
+        for (int32_t i = 0; i < n; ++i) {
+          const int32_t v = L0[i];
+          const Rk rv = rank4[v];
+          int32_t hi[NDIR], lo[NDIR];
+          for (int d = 0; d < NDIR; ++d) hi[d] = lo[d] = rv.r[d];
+          for (int32_t q = adj.rowptr[v]; q < adj.rowptr[v + 1]; ++q) {
+            const int32_t w = adj.col[q];
+            if (side[w] != cur) continue;
+            const Rk& rw = rank4[w];
+            for (int d = 0; d < NDIR; ++d) { hi[d] = std::max(hi[d], rw.r[d]); lo[d] = std::min(lo[d], rw.r[d]); }
+          }
+          for (int d = 0; d < NDIR; ++d) {
+            sc.dl[d][rv.r[d] + 1]++; sc.dl[d][hi[d] + 1]--;   // left-boundary member for h in (r, hi]
+            sc.dr[d][lo[d] + 1]++; sc.dr[d][rv.r[d] + 1]--;   // right-boundary member for h in (lo, r]
+          }
         }
-        for (int d = 0; d < ndir; ++d) {
-          sc.dl[d][rv.r[d] + 1]++; sc.dl[d][hi[d] + 1]--;   // left-boundary member for h in (r, hi]
-          sc.dr[d][lo[d] + 1]++; sc.dr[d][rv.r[d] + 1]--;   // right-boundary member for h in (lo, r]
-        }
-      }
+      };
+      if (ndir == ND) neighbour_pass(std::integral_constant<int, ND>{}); else neighbour_pass(std::integral_constant<int, 2>{});
       for (int d = 0; d < ndir; ++d) {
         const int32_t* dl = sc.dl[d].data(); const int32_t* dr = sc.dr[d].data();
         int32_t cl = 0, cr = 0;
@@ -359,7 +366,7 @@ struct Dissector {
     // stable three-way partition of every direction list: [left | right | separator]
     int32_t nl = 0, nr = 0;
     sc.tmp.resize(n);
-    for (int d = 0; d < ND; ++d) {
+    for (int d = 0; d < ndir; ++d) {           // a subset that examines two directions has only smaller subsets below it
       int32_t* Ld = lists[d].data() + off;
       int32_t a = 0, b = 0;
       for (int32_t i = 0; i < n; ++i) {
