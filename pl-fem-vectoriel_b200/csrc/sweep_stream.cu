@@ -96,9 +96,11 @@ template <int NST>
 struct PipeT {
   double* ring; uint64_t* bar; const double* src; int32_t* status;
   int nchunks, cur, pos, lane;
+  int base = 0;                                       // chunks this ring has carried before (persistent CTAs: stage and parity run on)
   bool dead = false;                                  // a wait timed out: stop waiting, the status flag reports it
+  __device__ __forceinline__ int stage() const { return (base + cur) % NST; }
   __device__ __forceinline__ void issue(int c) {
-    const int s = c % NST;
+    const int s = (base + c) % NST;
     mbar_expect_tx(bar + s, CHD * 8);
     bulk_g2s(ring + s * CHD, src + (int64_t)c * CHD, CHD * 8, bar + s);
   }
@@ -115,15 +117,15 @@ struct PipeT {
       if (lane == 0 && cur + NST < nchunks) issue(cur + NST);
     }
     ++cur; pos = 0;
-    uint64_t* b = bar + cur % NST;
-    const uint32_t parity = (cur / NST) & 1;
+    uint64_t* b = bar + (base + cur) % NST;
+    const uint32_t parity = ((base + cur) / NST) & 1;
     unsigned spins = 0;
     while (!dead && !mbar_try_wait(b, parity))
       if (++spins > (1u << 18)) { atomicExch(status + 1, 2); dead = true; }   // report instead of hanging the GPU
   }
   __device__ __forceinline__ const double* place(int sz) {
     if (pos + sz > CHD) advance();
-    const double* p = ring + (cur % NST) * CHD + pos;
+    const double* p = ring + stage() * CHD + pos;
     pos += sz;
     return p;
   }
@@ -329,7 +331,7 @@ __device__ __forceinline__ void fwd_block(Pipe& pp, StreamSmem<NR>& sm, int s2, 
     int n = (CHD - pp.pos) / ld;
     if (n == 0) { pp.advance(); continue; }
     n = min(n, s2 - k);
-    const double* base = pp.ring + (pp.cur % NS) * CHD + pp.pos + lane;
+    const double* base = pp.ring + pp.stage() * CHD + pp.pos + lane;
     const double* yv = sm.loc + (p0 + k) * NR;
     fma_columns<NR, R, U>(base, ld, n, valid, [&](int c, double (&y)[NR]) { ld_loc<NR>(yv, c, y); }, accs);
     pp.pos += n * ld; k += n;
@@ -421,7 +423,7 @@ __device__ __forceinline__ void bwd_front(Pipe& pp, StreamSmem<NR>& sm, int s2, 
     int n = (CHD - pp.pos) / s2p;
     if (n == 0) { pp.advance(); continue; }
     n = min(n, u2 - j);
-    const double* base = pp.ring + (pp.cur % NS) * CHD + pp.pos + lane;
+    const double* base = pp.ring + pp.stage() * CHD + pp.pos + lane;
     fma_columns<NR, R, U>(base, s2p, n, valid, [&](int c, double (&x)[NR]) {
       const int jj = j + c;
       ld_loc<NR>(sm.loc, 2 * (int)sm.lm[jj >> 1] + (jj & 1), x);
@@ -620,7 +622,7 @@ __device__ __forceinline__ void warp_multiply(PipeW& pp, int n, bool valid, YF&&
     int m = (CHD - pp.pos) / 32;
     if (m == 0) { pp.advance(); continue; }
     m = min(m, n - k);
-    const double* base = pp.ring + (pp.cur % NSW) * CHD + pp.pos + pp.lane;
+    const double* base = pp.ring + pp.stage() * CHD + pp.pos + pp.lane;
     fma_columns<NR, 1, 4>(base, 32, m, v1, [&](int c, double (&y)[NR]) { yf(k + c, y); }, accs);
     pp.pos += m * 32; k += m;
   }
@@ -633,30 +635,39 @@ __global__ void __launch_bounds__(32 * TW) level_forward_kernel(const LevelTask*
                                                                 const int32_t* __restrict__ child, const int32_t* __restrict__ cmap_ptr,
                                                                 const int32_t* __restrict__ cmap, const int32_t* __restrict__ sptr,
                                                                 const int32_t* __restrict__ uoff, RhsView rv, int32_t* status, int32_t* sync,
-                                                                const uint8_t* __restrict__ active) {
+                                                                const uint8_t* __restrict__ active, int ntasks) {
   __shared__ LevelFwdSmem<NR> sm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (PDL) griddep_launch_dependents();
-  // dataflow launch: tasks are handed out in level order by a ticket, so whatever a running task waits for belongs to a
-  // task that has started before it — progress does not depend on the order in which the hardware dispatches CTAs
-  int ti = blockIdx.x;
-  long long* const tr = FUSED ? g_sweep_trace : nullptr;
-  if (FUSED) {
-    if (tid == 0) sm.ticket = atomicAdd(sync, 1);
-    __syncthreads();
-    ti = sm.ticket;
-  }
-  const LevelTask t = tasks[ti];
-  // a design that takes no part in this solve: all fronts of its tree are skipped, so nobody waits for this task's signal
-  if (active && !active[t.g0 >> 1]) return;
-  trace_stamp(tr, ti, 1, tid);
-  const int nw = (t.n + 31) >> 5;              // warps with rows
-  if (warp < nw && lane == 0) {
+  if (lane == 0) {
     for (int s = 0; s < NSW; ++s) mbar_init(sm.bar[warp] + s, 1);
     fence_mbar_init();
   }
   __syncwarp();
-  PipeW pp{sm.ring[warp], sm.bar[warp], stream + t.soff + (int64_t)warp * t.chunks * CHD, status, warp < nw ? t.chunks : 0, -1, CHD, lane};
+  int ring_base = 0;                           // chunks this warp's ring has carried in earlier tasks of this CTA
+  bool pdl_pending = PDL;
+  long long* const tr = FUSED ? g_sweep_trace : nullptr;
+  // Dataflow launch: a bounded number of PERSISTENT CTAs; each takes the next task by a ticket, in level order, so whatever
+  // a running task waits for belongs to a task taken before it — by a CTA that is running — and progress does not depend
+  // on how many CTAs the hardware has made resident or in which order.  (One CTA per task let thousands of waiting tasks of
+  // one forest occupy the shared memory that runnable tasks of the other forests in flight needed.)
+  for (bool once = true;; once = false) {
+  int ti = blockIdx.x;
+  if (FUSED) {
+    __syncthreads();                           // the previous task of this CTA is done with the shared contraction vector
+    if (tid == 0) sm.ticket = atomicAdd(sync, 1);
+    __syncthreads();
+    ti = sm.ticket;
+    if (ti >= ntasks) break;
+  } else if (!once) {
+    break;
+  }
+  const LevelTask t = tasks[ti];
+  // a design that takes no part in this solve: all fronts of its tree are skipped, so nobody waits for this task's signal
+  if (active && !active[t.g0 >> 1]) continue;
+  trace_stamp(tr, ti, 1, tid);
+  const int nw = (t.n + 31) >> 5;              // warps with rows
+  PipeW pp{sm.ring[warp], sm.bar[warp], stream + t.soff + (int64_t)warp * t.chunks * CHD, status, warp < nw ? t.chunks : 0, -1, CHD, lane, ring_base};
   if (warp < nw) pp.start(true);
   // static: where this thread's pivot row and its row of the slab receive their children's updates
   const int nf2 = t.s2 + t.u2;
@@ -673,7 +684,7 @@ __global__ void __launch_bounds__(32 * TW) level_forward_kernel(const LevelTask*
   const int row = t.r0 + tid;
   const bool has_row = tid < t.n;
   if (has_row && row >= t.s2) { j1 = g1[row]; j2 = g2[row]; }
-  if (PDL) griddep_wait();
+  if (pdl_pending) { griddep_wait(); pdl_pending = false; }
   trace_stamp(tr, ti, 2, tid);
   if (FUSED && t.need > 0) {                   // the children's update vectors are complete
     if (warp == 0) wait_counter(sync + 2 + t.dep, t.need, lane, status);
@@ -752,35 +763,43 @@ __global__ void __launch_bounds__(32 * TW) level_forward_kernel(const LevelTask*
     if (tid == 0) atomicAdd(sync + 2 + t.sig, 1);
   }
   trace_stamp(tr, ti, 6, tid);
-  if (warp < nw) pp.drain();
+  if (warp < nw) { pp.drain(); ring_base += t.chunks; }
+  }
 }
 
 template <int NR, bool PDL, bool FUSED>
 __global__ void __launch_bounds__(32 * TW) level_backward_kernel(const LevelTask* __restrict__ tasks, const double* __restrict__ stream,
                                                                  const int32_t* __restrict__ strct, double* __restrict__ x,
                                                                  double* __restrict__ part, int32_t* status, int32_t* sync, int nfronts,
-                                                                 const uint8_t* __restrict__ active) {
+                                                                 const uint8_t* __restrict__ active, int ntasks) {
   __shared__ LevelBwdSmem<NR> sm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (PDL) griddep_launch_dependents();
-  int ti = blockIdx.x;
-  if (FUSED) {            // tickets in level order, top level first (see level_forward_kernel)
-    if (tid == 0) sm.ticket = atomicAdd(sync + 1, 1);
-    __syncthreads();
-    ti = sm.ticket;
-  }
-  const LevelTask t = tasks[ti];
-  if (active && !active[t.g0 >> 1]) return;   // see level_forward_kernel
-  long long* const tr = FUSED ? g_sweep_trace : nullptr;
-  trace_stamp(tr, ti, 1, tid);
-  const int k0 = t.r0, kn = t.n, nk = t.nch;   // this task's slab of the update unknowns; slabs of the front
-  const int nw = (t.s2 + 31) >> 5;             // warps with pivot columns
-  if (warp < nw && lane == 0) {
+  if (lane == 0) {
     for (int s = 0; s < NSW; ++s) mbar_init(sm.bar[warp] + s, 1);
     fence_mbar_init();
   }
   __syncwarp();
-  PipeW pp{sm.ring[warp], sm.bar[warp], stream + t.soff + (int64_t)warp * t.chunks * CHD, status, warp < nw ? t.chunks : 0, -1, CHD, lane};
+  int ring_base = 0;
+  bool pdl_pending = PDL;
+  long long* const tr = FUSED ? g_sweep_trace : nullptr;
+  for (bool once = true;; once = false) {      // persistent CTAs, tickets in level order, top level first (see level_forward_kernel)
+  int ti = blockIdx.x;
+  if (FUSED) {
+    __syncthreads();
+    if (tid == 0) sm.ticket = atomicAdd(sync + 1, 1);
+    __syncthreads();
+    ti = sm.ticket;
+    if (ti >= ntasks) break;
+  } else if (!once) {
+    break;
+  }
+  const LevelTask t = tasks[ti];
+  if (active && !active[t.g0 >> 1]) continue;  // see level_forward_kernel
+  trace_stamp(tr, ti, 1, tid);
+  const int k0 = t.r0, kn = t.n, nk = t.nch;   // this task's slab of the update unknowns; slabs of the front
+  const int nw = (t.s2 + 31) >> 5;             // warps with pivot columns
+  PipeW pp{sm.ring[warp], sm.bar[warp], stream + t.soff + (int64_t)warp * t.chunks * CHD, status, warp < nw ? t.chunks : 0, -1, CHD, lane, ring_base};
   if (warp < nw) pp.start(true);
   const int32_t* st = strct + t.goff;          // the front's update set
   // static: positions of the slab's update unknowns in the solution vector (two per thread)
@@ -790,7 +809,7 @@ __global__ void __launch_bounds__(32 * TW) level_backward_kernel(const LevelTask
     const int j = tid + 32 * TW * q;
     xo[q] = j < kn ? 2 * (int64_t)st[(k0 + j) >> 1] + ((k0 + j) & 1) : -1;
   }
-  if (PDL) griddep_wait();
+  if (pdl_pending) { griddep_wait(); pdl_pending = false; }
   const bool has_col = tid < t.s2;
   // z1 of this thread's pivot (forward sweep): requested before the dependency wait, used at the very end
   double z[NR];
@@ -856,7 +875,8 @@ __global__ void __launch_bounds__(32 * TW) level_backward_kernel(const LevelTask
     }
   }
   trace_stamp(tr, ti, 6, tid);
-  if (warp < nw) pp.drain();
+  if (warp < nw) { pp.drain(); ring_base += t.chunks; }
+  }
 }
 
 // pack of the level tasks: one CTA per task copies its slab from the front pool into the sub-streams of its warps
@@ -1087,16 +1107,24 @@ void launch_warp_ctas(void (*kernel)(KArgs...), bool pdl, int grid, int threads,
   PLFEM_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
 }
 
+// CTAs of a dataflow launch: PLFEM_SWEEP_CTAS_PER_SM (default 5, what the shared memory of the four rings allows) x SMs
+int persistent_ctas(plfem_ctx* ctx) {
+  static const int per_sm = [] { const char* e = std::getenv("PLFEM_SWEEP_CTAS_PER_SM"); return e ? std::max(1, std::min(16, atoi(e))) : 5; }();
+  static thread_local int sms = 0;
+  if (sms == 0) PLFEM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+  return per_sm * sms;
+}
+
 template <bool FUSED>
 void launch_forward_tasks(plfem_ctx* ctx, const DevPlan& D, const LevelTask* tasks, int n, const double* rhs, double* out, int nrhs, bool pdl, const uint8_t* active) {
   const StreamPlan& S = D.st;
   const RhsView rv{rhs, out, D.upd.p};
   if (nrhs == 1) {
-    if (pdl) launch_warp_ctas(level_forward_kernel<1, true, FUSED>, true, n, 32 * TW, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p, active);
-    else launch_warp_ctas(level_forward_kernel<1, false, FUSED>, false, n, 32 * TW, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p, active);
+    if (pdl) launch_warp_ctas(level_forward_kernel<1, true, FUSED>, true, FUSED ? std::min(n, persistent_ctas(ctx)) : n, 32 * TW, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p, active, n);
+    else launch_warp_ctas(level_forward_kernel<1, false, FUSED>, false, FUSED ? std::min(n, persistent_ctas(ctx)) : n, 32 * TW, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p, active, n);
   } else {
-    if (pdl) launch_warp_ctas(level_forward_kernel<SOLVE_NRHS, true, FUSED>, true, n, 32 * TW, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p, active);
-    else launch_warp_ctas(level_forward_kernel<SOLVE_NRHS, false, FUSED>, false, n, 32 * TW, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p, active);
+    if (pdl) launch_warp_ctas(level_forward_kernel<SOLVE_NRHS, true, FUSED>, true, FUSED ? std::min(n, persistent_ctas(ctx)) : n, 32 * TW, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p, active, n);
+    else launch_warp_ctas(level_forward_kernel<SOLVE_NRHS, false, FUSED>, false, FUSED ? std::min(n, persistent_ctas(ctx)) : n, 32 * TW, ctx->stream, tasks, D.gsrc.p, S.lfwd.p, D.cptr.p, D.child.p, D.cmap_ptr.p, D.cmap.p, D.sptr.p, D.uoff.p, rv, D.status.p, S.sync.p, active, n);
   }
   ctx->launches++;
 }
@@ -1105,11 +1133,11 @@ template <bool FUSED>
 void launch_backward_tasks(plfem_ctx* ctx, const DevPlan& D, const LevelTask* tasks, int n, double* x, int nrhs, bool pdl, const uint8_t* active) {
   const StreamPlan& S = D.st;
   if (nrhs == 1) {
-    if (pdl) launch_warp_ctas(level_backward_kernel<1, true, FUSED>, true, n, 32 * TW, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts, active);
-    else launch_warp_ctas(level_backward_kernel<1, false, FUSED>, false, n, 32 * TW, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts, active);
+    if (pdl) launch_warp_ctas(level_backward_kernel<1, true, FUSED>, true, FUSED ? std::min(n, persistent_ctas(ctx)) : n, 32 * TW, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts, active, n);
+    else launch_warp_ctas(level_backward_kernel<1, false, FUSED>, false, FUSED ? std::min(n, persistent_ctas(ctx)) : n, 32 * TW, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts, active, n);
   } else {
-    if (pdl) launch_warp_ctas(level_backward_kernel<SOLVE_NRHS, true, FUSED>, true, n, 32 * TW, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts, active);
-    else launch_warp_ctas(level_backward_kernel<SOLVE_NRHS, false, FUSED>, false, n, 32 * TW, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts, active);
+    if (pdl) launch_warp_ctas(level_backward_kernel<SOLVE_NRHS, true, FUSED>, true, FUSED ? std::min(n, persistent_ctas(ctx)) : n, 32 * TW, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts, active, n);
+    else launch_warp_ctas(level_backward_kernel<SOLVE_NRHS, false, FUSED>, false, FUSED ? std::min(n, persistent_ctas(ctx)) : n, 32 * TW, ctx->stream, tasks, S.lbwd.p, D.strct.p, x, S.bpart.p, D.status.p, S.sync.p, S.nfronts, active, n);
   }
   ctx->launches++;
 }
