@@ -1,9 +1,5 @@
 #!/bin/bash
 O=gpurun_out; mkdir -p $O
+PLFEM_TIMING=1 PLFEM_HOST_THREADS=1 timeout 300 python scripts/gpu_forest_once.py 12 3 > $O/forest_timing.log 2>&1
 timeout 900 python -m pytest tests -m gpu -q -x --durations=3 > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_gpu.log
-for c in 5 3 2 1; do
-PLFEM_SWEEP_CTAS_PER_SM=$c timeout 300 python scripts/gpu_sweep_profile.py cfg1 12 2>&1 | tail -2 > $O/pers${c}_cfg1.log
-PLFEM_SWEEP_CTAS_PER_SM=$c timeout 600 python bench.py --steps 8 --warmup 3 > $O/bench_pers${c}.json 2> /dev/null; echo "bench $c rc=$?"
-done
-PLFEM_SWEEP_CTAS_PER_SM=5 timeout 300 python scripts/gpu_sweep_profile.py cfg5 1 2>&1 | tail -2 > $O/pers5_cfg5.log
-PLFEM_SWEEP_CTAS_PER_SM=5 timeout 300 python scripts/gpu_sweep_profile.py cfg1 1 2>&1 | tail -2 > $O/pers5_cfg1s.log
+timeout 600 python bench.py --steps 10 --warmup 3 > $O/bench_cfg1.json 2> $O/bench_cfg1.err; echo "bench cfg1 rc=$?"

@@ -6,6 +6,8 @@ largest magnitude in its row: entries that are pure round-off of cancelling elem
 (e.g. the vertex / adjacent-edge mass entries, exactly 0 in exact arithmetic) have no meaningful
 relative error of their own, and SciPy's own summation order for duplicates is unspecified.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -14,6 +16,7 @@ from plfem_b200.solver_fem import TrueVectorialMaxwellSolver, ModeRecord
 from oracle import fem_oracle as O
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def rowwise_rel_err(M, R, row_scale=None):
@@ -517,3 +520,48 @@ def test_bands_on_one_mesh_share_one_analysis(cfg1):
         assert np.array_equal(ra["beta_sq"], rb["beta_sq"]) and len(ma) == len(mb)
     assert all(s["ms_symbolic"] < 0.5 * o["ms_symbolic"] for s, o in zip(st_shared[1:], st_own[1:]))
     assert st_shared[0]["n_fronts"] == st_shared[3]["n_fronts"] == st_own[3]["n_fronts"]
+
+
+@pytest.mark.gpu
+def test_refinement_is_per_design_inside_a_forest(small_case, cfg1):
+    """A forest mixing a design whose raw block-LDL^T solve is accurate (the recipe mesh of config 1: probe rho ~ 6e-11, no
+    refinement alone) with one that needs a refinement step (a coarse structured mesh: rho > 1e-9): the forest's refinement solve
+    must skip the first design's fronts, rows and correction — and both must still give their single-solve eigenvalues and pass
+    the backward-error bar."""
+    import plfem_b200 as P
+    from plfem_b200.batch import ForestPool
+    g, mesh = cfg1
+    coarse = P.MeshTri.init_structured(60, 60, 32.0)
+    jobs = [(g, mesh, 10), (g, coarse, 10), (g, mesh, 10)]
+    alone = []
+    for gg, mm, n in jobs[:2]:
+        modes, raw = TrueVectorialMaxwellSolver(gg).solve_vectorial_modes(mm, n, return_raw=True)
+        alone.append(raw)
+    assert alone[0]["stats"]["refine_steps"] == 0 and alone[1]["stats"]["refine_steps"] >= 1, \
+        (alone[0]["stats"]["probe_rho"], alone[1]["stats"]["probe_rho"])
+    with ForestPool(batch=3, workers=1) as pool:
+        out = pool.solve_forest(jobs, return_raw=True)
+    for (modes, raw), ref in zip(out, (alone[0], alone[1], alone[0])):
+        assert raw["stats"]["max_residual"] < 1e-9
+        assert np.abs(raw["beta_sq"] / ref["beta_sq"] - 1).max() < 1e-9
+    assert out[0][1]["stats"]["refine_steps"] == alone[1]["stats"]["refine_steps"]      # the forest reports the maximum
+    assert np.array_equal(out[0][1]["beta_sq"], out[2][1]["beta_sq"])                     # identical designs, identical results
+
+
+@pytest.mark.gpu
+def test_dataflow_and_per_level_sweeps_are_bit_identical(tmp_path):
+    """`PLFEM_SWEEP=levels` launches the same sweep tasks level by level instead of as one dataflow launch per direction: the
+    eigenvalues must agree bit for bit (the variable is read once per process, hence two subprocesses)."""
+    import subprocess
+    import sys as _sys
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); import plfem_b200 as P; "
+            "from plfem_b200.solver_fem import TrueVectorialMaxwellSolver as S; "
+            "g = P.MCFGeometry(3, 6.0, 1.2, 1.53, 1.0, 1.55); mesh, _ = P.MeshGenerator.generate(g, refinement=0.4); "
+            "m, raw = S(g).solve_vectorial_modes(mesh, 4, return_raw=True); np.save(sys.argv[1], raw['beta_sq'])" % ROOT)
+    outs = []
+    for mode in ("", "levels"):
+        f = str(tmp_path / f"beta_{mode or 'dataflow'}.npy")
+        env = dict(os.environ, PLFEM_SWEEP=mode)
+        subprocess.run([_sys.executable, "-c", code, f], env=env, check=True, timeout=300)
+        outs.append(np.load(f))
+    assert np.array_equal(outs[0], outs[1])
