@@ -203,6 +203,8 @@ int plfem_plan_export(plfem_problem* pb, int32_t* perm, int32_t* first, int32_t*
 int plfem_debug_solve(plfem_problem* pb, double sigma, const double* b, double* x, int refine);
 /* dense symmetric eigensolver used at Lanczos restarts: a is n*n column-major, overwritten by eigenvectors */
 int plfem_debug_symeig(int32_t n, double* a, double* w);
+/* the convergence checks' variant: eigenvalues (ascending) and only the last p rows of the eigenvector matrix, tail[j*p + r] = Z(n-p+r, j) */
+int plfem_debug_symeig_tail(int32_t n, const double* a, double* w, int32_t p, double* tail);
 
 #ifdef __cplusplus
 }

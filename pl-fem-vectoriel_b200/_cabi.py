@@ -33,7 +33,7 @@ EIG_TOL = 1e-8
 SYMBOLS = ["plfem_ctx_create", "plfem_ctx_destroy", "plfem_last_error", "plfem_version",
            "plfem_problem_create", "plfem_problem_destroy", "plfem_problem_set_dirichlet", "plfem_problem_info", "plfem_problem_dofs",
            "plfem_quad_points", "plfem_assemble", "plfem_export_csr", "plfem_spmv_csr", "plfem_solve_modes",
-           "plfem_plan_sizes", "plfem_plan_export", "plfem_debug_symeig", "plfem_profile_kernels", "plfem_set_host_threads",
+           "plfem_plan_sizes", "plfem_plan_export", "plfem_debug_symeig", "plfem_debug_symeig_tail", "plfem_profile_kernels", "plfem_set_host_threads",
            "plfem_debug_solve", "plfem_solve_modes_batch", "plfem_profile_last", "plfem_host_alloc", "plfem_host_free"]
 
 
@@ -116,6 +116,7 @@ def load():
         lib.plfem_plan_sizes.argtypes = [vp, c_i32, c_i32, p_i64]
         lib.plfem_plan_export.argtypes = [vp] + [p_i32] * 9 + [p_i64]
         lib.plfem_debug_symeig.argtypes = [c_i32, p_f64, p_f64]
+        lib.plfem_debug_symeig_tail.argtypes = [c_i32, p_f64, p_f64, c_i32, p_f64]
         lib.plfem_debug_solve.argtypes = [vp, c_f64, p_f64, p_f64, C.c_int]
         lib.plfem_set_host_threads.argtypes = [C.c_int]
         lib.plfem_set_host_threads.restype = None
@@ -438,3 +439,16 @@ def symeig(a: np.ndarray):
     if st != 0:
         raise PlfemError(st, "symeig")
     return w, buf
+
+
+def symeig_tail(a: np.ndarray, p: int):
+    """Test hook for the convergence checks' eigensolver: (w ascending, last p rows of the eigenvector matrix, shape (p, n))."""
+    lib = load()
+    n = a.shape[0]
+    buf = np.asfortranarray(a, dtype=np.float64).copy(order="F")
+    w = np.empty(n)
+    tail = np.empty((p, n), order="F")
+    st = lib.plfem_debug_symeig_tail(n, buf.ctypes.data_as(p_f64), _ptr(w, p_f64), p, tail.ctypes.data_as(p_f64))
+    if st != 0:
+        raise PlfemError(st, "symeig_tail")
+    return w, tail

@@ -15,7 +15,7 @@ OBJ = HERE / "build"
 
 SOURCES = ["symbolic.cpp", "symeig.cpp", "assembly.cu", "factor.cu", "sweep_stream.cu", "eigen.cu", "api.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "--expt-relaxed-constexpr"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-mavx2", "--expt-relaxed-constexpr"]
 # assembly.cu: products and sums must round like the NumPy oracle, never contract into FMAs
 PER_FILE = {"assembly.cu": ["-fmad=false"]}
 

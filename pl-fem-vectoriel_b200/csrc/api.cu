@@ -589,6 +589,10 @@ static void solve_forest(plfem_ctx* ctx, int nb, plfem_problem* const* pbs, cons
         const int32_t node = pb->dof.interior[pb->plan.perm[r]];
         bool in = false;
         for (int c = 0; c < mat->n_cores && mat->cores_xy; ++c) {
+          // (outside the core's bounding square, widened by 1e-9 relative so that no rounding of the test below can matter:
+          //  |dx| > r (1 + 1e-9) implies fl(dx*dx) > fl(r*r), and fl(dx2 + dy2) >= dx2)
+          const double rb = std::fabs(mat->cores_r[c]) * (1.0 + 1e-9);
+          if (std::fabs(Xc[node] - mat->cores_xy[2 * c]) > rb || std::fabs(Yc[node] - mat->cores_xy[2 * c + 1]) > rb) continue;
           volatile double dx = Xc[node] - mat->cores_xy[2 * c], dy = Yc[node] - mat->cores_xy[2 * c + 1];
           volatile double dx2 = dx * dx, dy2 = dy * dy, rr = mat->cores_r[c] * mat->cores_r[c];
           volatile double d2 = dx2 + dy2;
@@ -1018,6 +1022,16 @@ int plfem_debug_symeig(int32_t n, double* a, double* w) {
   symmetric_eigen(n, A, W);
   std::copy(A.begin(), A.end(), a);
   std::copy(W.begin(), W.end(), w);
+  return PLFEM_OK;
+}
+
+// test hook: eigenvalues + the last p rows of the eigenvector matrix (what a convergence check reads); tail is p*n, column-major
+int plfem_debug_symeig_tail(int32_t n, const double* a, double* w, int32_t p, double* tail) {
+  if (!a || !w || !tail || n < 1 || p < 1 || p > n) return PLFEM_ERR_INVALID;
+  std::vector<double> A(a, a + (size_t)n * n), W, T;
+  symmetric_eigen_tail(n, A, W, p, T);
+  std::copy(W.begin(), W.end(), w);
+  std::copy(T.begin(), T.end(), tail);
   return PLFEM_OK;
 }
 

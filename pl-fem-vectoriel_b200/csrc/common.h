@@ -308,5 +308,7 @@ void launch_resid_k(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals,
 
 void launch_axpy(plfem_ctx* ctx, double* x, const double* dx, int64_t m);
 void symmetric_eigen(int n, std::vector<double>& a /* n*n col-major in, eigenvectors out */, std::vector<double>& w);
+// eigenvalues + the last p rows of the eigenvector matrix only (tail[j*p + r] = Z(n-p+r, j)); a is destroyed
+void symmetric_eigen_tail(int n, std::vector<double>& a, std::vector<double>& w, int p, std::vector<double>& tail);
 
 }  // namespace plfem

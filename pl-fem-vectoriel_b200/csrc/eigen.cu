@@ -999,7 +999,8 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
   if (relax_at > 0.0 && rsteps >= 1) capture_operator(rsteps - 1, graph_lo, gexec_lo, graph_nodes_lo);
 
   struct Host {                      // per-design host state of the projected problem
-    std::vector<double> Th, T, w, S;
+    std::vector<double> Th, T, w, S, Ttail, tail;
+    bool expect_final = false;       // the decay of its bounds predicts that the next check finds it converged
     std::vector<int> order;
     bool done = false, newly = false;
     int q_want = 0;
@@ -1084,27 +1085,43 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
           de.status = PLFEM_ERR_SINGULAR; de.err = "Lanczos recurrence produced a non-finite value (shifted operator singular?)";
           h.done = true; return;
         }
-      symmetric_eigen(c, h.T, h.w);        // T now holds eigenvectors in columns
-      h.order.resize(c);
-      std::iota(h.order.begin(), h.order.end(), 0);
-      std::stable_sort(h.order.begin(), h.order.end(), [&](int a, int bb) { return std::fabs(h.w[a]) > std::fabs(h.w[bb]); });
+      // The residual bounds read only the last P rows of the eigenvector matrix.  A check that is neither a restart nor
+      // expected to be the design's last one asks for just those (symmetric_eigen_tail: no accumulation of the
+      // tridiagonalising reflectors, rotations on P rows instead of c — about half the cost); if every wanted pair
+      // turns out to be converged after all, the full decomposition follows.
       const double* L = Lh.data() + ((size_t)b * nslots + (c - P) / P) * P * P;     // R_last = V_next L^T
-      auto bound = [&](int col) {
-        double s2 = 0.0;
-        for (int a = 0; a < P; ++a) {
-          double t = 0.0;
-          for (int bb = a; bb < P; ++bb) t += L[bb + a * P] * h.T[(size_t)col * c + (c - P + bb)];
-          s2 += t * t;
-        }
-        return std::sqrt(s2);
-      };
       const int k = de.k;
       int nconv = 0;
       double worst = 0.0;
-      for (int i = 0; i < k; ++i) {
-        const double bnd = bound(h.order[i]), ref = std::max(eps23, std::fabs(h.w[h.order[i]]));
-        if (bnd <= de.tol * ref) nconv++;
-        worst = std::max(worst, bnd / ref);
+      auto examine = [&](const double* tail, int ldt, int row0) {       // tail(r, col) = Z(c - P + r, col)
+        h.order.resize(c);
+        std::iota(h.order.begin(), h.order.end(), 0);
+        std::stable_sort(h.order.begin(), h.order.end(), [&](int a, int bb) { return std::fabs(h.w[a]) > std::fabs(h.w[bb]); });
+        nconv = 0; worst = 0.0;
+        for (int i = 0; i < k; ++i) {
+          const double* z = tail + (size_t)h.order[i] * ldt + row0;
+          double s2 = 0.0;
+          for (int a = 0; a < P; ++a) {
+            double t = 0.0;
+            for (int bb = a; bb < P; ++bb) t += L[bb + a * P] * z[bb];
+            s2 += t * t;
+          }
+          const double bnd = std::sqrt(s2), ref = std::max(eps23, std::fabs(h.w[h.order[i]]));
+          if (bnd <= de.tol * ref) nconv++;
+          worst = std::max(worst, bnd / ref);
+        }
+      };
+      bool have_vectors = full || last_chance || h.expect_final;
+      if (!have_vectors) {
+        h.Ttail = h.T;
+        symmetric_eigen_tail(c, h.Ttail, h.w, P, h.tail);
+        examine(h.tail.data(), P, 0);
+        have_vectors = false;
+        if (nconv >= k) have_vectors = true;      // converged earlier than predicted: the vectors are needed now
+      }
+      if (have_vectors) {
+        symmetric_eigen(c, h.T, h.w);        // T now holds eigenvectors in columns
+        examine(h.T.data(), c, c - P);
       }
       h.prev_worst = h.worst;
       h.worst = worst;
@@ -1173,6 +1190,13 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
         need = std::max(need, (int)std::ceil(std::log(des[b].tol / std::max(h.worst, 1e-300)) / rate));
       }
       if (known) next_gap = std::max(check_every, std::min(8, (int)(0.6 * need)));
+      for (int b = 0; b < B; ++b) {
+        Host& h = hs[b];
+        h.expect_final = false;
+        if (h.done || !(h.worst < h.prev_worst) || h.prev_worst > 1e299 || steps_between <= 0) continue;
+        const double rate = std::log(h.worst / h.prev_worst) / steps_between;
+        h.expect_final = std::ceil(std::log(des[b].tol / std::max(h.worst, 1e-300)) / rate) <= next_gap;
+      }
     }
     if (!relaxed && gexec_lo) {
       double w = 0.0;

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <thread>
 #include <type_traits>
+#include <smmintrin.h>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -251,8 +252,10 @@ struct Dissector {
   const double* y;
   const SymbolicOptions& opt;
   std::vector<int32_t> side;   // per node: stamp of the subset/half it currently belongs to
-  struct Rk { int32_t r[4]; };
+  struct alignas(16) Rk { int32_t r[4]; };
   std::vector<Rk> rank4;       // per node: position in each direction list of the subset being examined
+  struct alignas(16) Ext { int32_t hi[4], lo[4]; };
+  std::vector<Ext> ext;        // per node: extreme ranks among its neighbours inside the subset (and itself)
   std::vector<uint8_t> insep;  // per node: chosen as separator in the current call
   std::atomic<int32_t> stamp{0};
   std::vector<int32_t> lists[ND];  // the node set of the current call, sorted along each direction
@@ -260,7 +263,7 @@ struct Dissector {
   struct Scratch { std::vector<int32_t> tmp, dl[ND], dr[ND]; };
 
   Dissector(const Pattern& a, const double* x_, const double* y_, const SymbolicOptions& o)
-      : adj(a), x(x_), y(y_), opt(o), side(a.n, -1), rank4(a.n, Rk{{0, 0, 0, 0}}), insep(a.n, 0) {
+      : adj(a), x(x_), y(y_), opt(o), side(a.n, -1), rank4(a.n, Rk{{0, 0, 0, 0}}), ext(a.n), insep(a.n, 0) {
     const int32_t n = a.n;
     auto one = [&](int d) {
       std::vector<double> key(n);
@@ -313,22 +316,32 @@ struct Dissector {
       }
       // (small subsets examine two directions only: most of the nodes sit in such subsets, and the pass over their
       // neighbours is the hot loop of the whole analysis)
+      // Branch-free over the neighbours: the four ranks of a node are one 128-bit lane set, a neighbour outside the subset
+      // contributes 0 to the maxima (ranks are >= 0 and a node's own rank takes part) and INT32_MAX to the minima.  The extreme
+      // ranks are kept per node (ext[v]): the separator of the chosen cut is read off them below without a second pass over
+      // the adjacency.
       auto neighbour_pass = [&](auto nd_tag) {
         constexpr int NDIR = decltype(nd_tag)::value;
+        const __m128i big = _mm_set1_epi32(INT32_MAX);
+        const int32_t* rp = adj.rowptr.data(); const int32_t* cl = adj.col.data(); const int32_t* sd = side.data();
         for (int32_t i = 0; i < n; ++i) {
           const int32_t v = L0[i];
-          const Rk rv = rank4[v];
-          int32_t hi[NDIR], lo[NDIR];
-          for (int d = 0; d < NDIR; ++d) hi[d] = lo[d] = rv.r[d];
-          for (int32_t q = adj.rowptr[v]; q < adj.rowptr[v + 1]; ++q) {
-            const int32_t w = adj.col[q];
-            if (side[w] != cur) continue;
-            const Rk& rw = rank4[w];
-            for (int d = 0; d < NDIR; ++d) { hi[d] = std::max(hi[d], rw.r[d]); lo[d] = std::min(lo[d], rw.r[d]); }
+          const __m128i rv = _mm_load_si128((const __m128i*)&rank4[v]);
+          __m128i hi = rv, lo = rv;
+          for (int32_t q = rp[v], qe = rp[v + 1]; q < qe; ++q) {
+            const int32_t w = cl[q];
+            const __m128i in = _mm_set1_epi32(-(int32_t)(sd[w] == cur));
+            const __m128i rw = _mm_load_si128((const __m128i*)&rank4[w]);
+            hi = _mm_max_epi32(hi, _mm_and_si128(rw, in));
+            lo = _mm_min_epi32(lo, _mm_or_si128(rw, _mm_andnot_si128(in, big)));
           }
+          alignas(16) int32_t h4[4], l4[4];
+          _mm_store_si128((__m128i*)h4, hi); _mm_store_si128((__m128i*)l4, lo);
+          _mm_store_si128((__m128i*)&ext[v].hi, hi); _mm_store_si128((__m128i*)&ext[v].lo, lo);
+          const int32_t* r4 = rank4[v].r;
           for (int d = 0; d < NDIR; ++d) {
-            sc.dl[d][rv.r[d] + 1]++; sc.dl[d][hi[d] + 1]--;   // left-boundary member for h in (r, hi]
-            sc.dr[d][lo[d] + 1]++; sc.dr[d][rv.r[d] + 1]--;   // right-boundary member for h in (lo, r]
+            sc.dl[d][r4[d] + 1]++; sc.dl[d][h4[d] + 1]--;   // left-boundary member for h in (r, hi]
+            sc.dr[d][l4[d] + 1]++; sc.dr[d][r4[d] + 1]--;   // right-boundary member for h in (lo, r]
           }
         }
       };
@@ -355,13 +368,10 @@ struct Dissector {
     for (int32_t i = 0; i < h; ++i) side[Lb[i]] = sl;
     for (int32_t i = h; i < n; ++i) side[Lb[i]] = sr;
     std::vector<int32_t> sep;
-    {
-      const int32_t b = best_left ? 0 : h, e = best_left ? h : n, other = best_left ? sr : sl;
-      for (int32_t i = b; i < e; ++i) {
-        const int32_t v = Lb[i];
-        for (int32_t q = adj.rowptr[v]; q < adj.rowptr[v + 1]; ++q)
-          if (side[adj.col[q]] == other) { sep.push_back(v); insep[v] = 1; break; }
-      }
+    if (best_left) {          // left half: members with a neighbour of rank >= h
+      for (int32_t i = 0; i < h; ++i) { const int32_t v = Lb[i]; if (ext[v].hi[best_dir] >= h) { sep.push_back(v); insep[v] = 1; } }
+    } else {                  // right half: members with a neighbour of rank < h
+      for (int32_t i = h; i < n; ++i) { const int32_t v = Lb[i]; if (ext[v].lo[best_dir] < h) { sep.push_back(v); insep[v] = 1; } }
     }
     // stable three-way partition of every direction list: [left | right | separator]
     int32_t nl = 0, nr = 0;

@@ -106,6 +106,31 @@ def test_restart_eigensolver():
     assert np.allclose(w, np.linalg.eigvalsh(a), atol=1e-13) and np.abs(a @ v - v * w).max() < 1e-13
 
 
+def test_convergence_check_eigensolver_returns_the_last_rows():
+    """`symmetric_eigen_tail` (eigenvalues + the last p rows of the eigenvector matrix, what a Lanczos convergence check reads)
+    against LAPACK: eigenvalues, and — sign- and rotation-invariant inside a degenerate cluster — the norm of the tail of every
+    eigenvalue cluster; the p rows of an orthogonal matrix are orthonormal."""
+    rng = np.random.default_rng(3)
+    cases = [(1, 1), (2, 2), (5, 4), (44, 4), (70, 4), (45, 4)]
+    for n, p in cases:
+        a = rng.standard_normal((n, n)); a = a + a.T
+        if n == 45:        # a thick-restart projection: diagonal block with degenerate pairs, arrow row, block tridiagonal rest
+            q = 22
+            a = np.diag(np.repeat(rng.standard_normal((n + 1) // 2), 2)[:n])
+            a[q, :q] = a[:q, q] = 1e-4 * rng.standard_normal(q)
+            for j in range(q, n - 1):
+                a[j, j + 1] = a[j + 1, j] = rng.standard_normal()
+        w, t = _cabi.symeig_tail(a, p)
+        wr, vr = np.linalg.eigh(a)
+        assert np.allclose(w, wr, atol=2e-13 * max(1.0, np.abs(wr).max()))
+        assert np.abs(t @ t.T - np.eye(p)).max() < 1e-13
+        for j in range(n):
+            cl = np.where(np.abs(wr - wr[j]) < 1e-9)[0]
+            assert abs(np.linalg.norm(t[:, cl]) - np.linalg.norm(vr[n - p:, cl])) < 1e-12
+        wf, vf = _cabi.symeig(a)
+        assert np.allclose(wf, wr, atol=2e-13 * max(1.0, np.abs(wr).max())) and np.abs(a @ vf - vf * wf).max() < 1e-12 * max(1.0, np.abs(wr).max())
+
+
 @pytest.mark.parametrize("leaf,sn", [(24, 64), (8, 16)])
 def test_front_plan_solves_the_shifted_system(small_case, leaf, sn):
     """The host-built plan (ordering, update sets, child maps), executed with dense NumPy, must solve
