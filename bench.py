@@ -219,7 +219,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from plfem_b200 import _cabi
-    from plfem_b200.batch import ForestPool
+    from plfem_b200.batch import ForestPool, default_workers
     from plfem_b200.solver_fem import TrueVectorialMaxwellSolver, sigma_estimate
     from plfem_b200.sweep import gather_records, N_RECORD
 
@@ -242,7 +242,7 @@ def run_ours(args):
 
     # designs per forest / forests in flight: cfg5 is ONE 2M-unknown design per step (a forest of one, one worker)
     B = 1 if args.workload == "cfg5" else max(1, args.inflight)
-    NW = 1 if args.workload == "cfg5" else max(1, args.workers)
+    NW = 1 if args.workload == "cfg5" else (args.workers if args.workers > 0 else default_workers())
     w, jobs = make_jobs(args.workload, B * NW, B)
     forests = [jobs[i * B:(i + 1) * B] for i in range(NW)]          # forest i of a step is worker i's
     g, mesh, n_modes = forests[-1][-1]                              # the largest design (cfg4: sorted) for latency / sizes
@@ -498,7 +498,8 @@ def main():
     ap.add_argument("--workload", default="cfg1", choices=sorted(WORKLOADS),
                     help="cfg1 (default, the configuration the metric is quoted on), cfg2, cfg4 (heterogeneous LHS sample), cfg5 (2M unknowns)")
     ap.add_argument("--inflight", type=int, default=12, help="designs per forest (= per step)")
-    ap.add_argument("--workers", type=int, default=6, help="host threads / contexts, each working on its own forest")
+    ap.add_argument("--workers", type=int, default=0, help="host threads / contexts, each working on its own forest "
+                    "(0 = batch.default_workers(): 6, or 9 when this rank has fewer than 8 host cores)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     if args.impl == "reference":

@@ -364,9 +364,6 @@ struct Dissector {
       if (cand[d].cost < best_cost) { best_cost = cand[d].cost; best_dir = d; best_h = cand[d].h; best_left = cand[d].left; }
     const int32_t h = best_h;
     const int32_t* Lb = lists[best_dir].data() + off;
-    const int32_t sl = ++stamp, sr = ++stamp;
-    for (int32_t i = 0; i < h; ++i) side[Lb[i]] = sl;
-    for (int32_t i = h; i < n; ++i) side[Lb[i]] = sr;
     std::vector<int32_t> sep;
     if (best_left) {          // left half: members with a neighbour of rank >= h
       for (int32_t i = 0; i < h; ++i) { const int32_t v = Lb[i]; if (ext[v].hi[best_dir] >= h) { sep.push_back(v); insep[v] = 1; } }
@@ -382,7 +379,7 @@ struct Dissector {
       for (int32_t i = 0; i < n; ++i) {
         const int32_t v = Ld[i];
         if (insep[v]) continue;
-        if (side[v] == sl) Ld[a++] = v; else sc.tmp[b++] = v;
+        if (rank4[v].r[best_dir] < h) Ld[a++] = v; else sc.tmp[b++] = v;      // left of the cut along the chosen direction
       }
       std::copy(sc.tmp.begin(), sc.tmp.begin() + b, Ld + a);
       nl = a; nr = b;
