@@ -509,6 +509,14 @@ void dissect_vertex_graph(const DofTables& d, const std::vector<int32_t>& interi
   }
   // order separators along their cut, split them into chains of <= max_sn_nodes supernodes
   auto proj = [&](int dd, int32_t v) { switch (dd) { case 0: return x[v]; case 1: return y[v]; case 2: return x[v] + y[v]; default: return x[v] - y[v]; } };
+  // (keys gathered once per node and sorted as (key, node) pairs: the same order as comparing proj(odir, .) with ties by node id)
+  std::vector<std::pair<double, int32_t>> keyed;
+  auto sort_along = [&](std::vector<int32_t>& o, int odir) {
+    keyed.resize(o.size());
+    for (size_t i = 0; i < o.size(); ++i) keyed[i] = {proj(odir, o[i]), o[i]};
+    std::sort(keyed.begin(), keyed.end());
+    for (size_t i = 0; i < o.size(); ++i) o[i] = keyed[i].second;
+  };
   out = Forest(); out_roots.clear();
   std::vector<int32_t> head(nt, -1);          // tree node of `out` heading (last chain link of) vertex-tree node t
   // children before parents: process in reverse DFS order
@@ -524,7 +532,7 @@ void dissect_vertex_graph(const DofTables& d, const std::vector<int32_t>& interi
     for (int32_t c : vf.nodes[t].children) kids.push_back(head[c]);
     const int odir = vf.nodes[t].od;
     if (odir < 0 || (int32_t)o.size() <= opt.max_sn_nodes) {
-      if (odir >= 0) std::sort(o.begin(), o.end(), [&](int32_t a, int32_t b) { const double pa = proj(odir, a), pb = proj(odir, b); return pa < pb || (pa == pb && a < b); });
+      if (odir >= 0) sort_along(o, odir);
       // a leaf larger than the supernode limit (many edge nodes) is split as well
       const int32_t ns = (int32_t)o.size();
       const int32_t nchunks = std::max(1, (ns + opt.max_sn_nodes - 1) / opt.max_sn_nodes);
@@ -540,7 +548,7 @@ void dissect_vertex_graph(const DofTables& d, const std::vector<int32_t>& interi
       head[t] = prev;
       continue;
     }
-    std::sort(o.begin(), o.end(), [&](int32_t a, int32_t b) { const double pa = proj(odir, a), pb = proj(odir, b); return pa < pb || (pa == pb && a < b); });
+    sort_along(o, odir);
     const int32_t ns = (int32_t)o.size();
     const int32_t nchunks = (ns + opt.max_sn_nodes - 1) / opt.max_sn_nodes;
     int32_t prev = -1, pos = 0;
@@ -640,7 +648,30 @@ void build_front_plan(const DofTables& dof, const Pattern* adj_p, const double* 
   // (read from the element tables: the node adjacency pattern is never built on this path).
   P.sptr.assign(nf + 1, 0);
   P.strct.clear(); P.strct.reserve((size_t)n * 8);
-  std::vector<int32_t> mark(n, -1);
+  // The update set of a front is collected in a two-level bitmap over the new ids (a word of the upper level has a bit per
+  // word of the lower one) and read back in ascending order: no duplicates to test for, no sort (sorting the ~30-entry
+  // sets front by front was half of this pass).
+  std::vector<uint64_t> bm0(((size_t)n + 63) / 64 + 1, 0), bm1((bm0.size() + 63) / 64 + 1, 0);
+  int32_t w1lo = INT32_MAX, w1hi = -1;
+  auto bm_add = [&](int32_t c) {
+    const int32_t w = c >> 6;
+    if (!bm0[w]) { const int32_t w1 = w >> 6; bm1[w1] |= 1ull << (w & 63); w1lo = std::min(w1lo, w1); w1hi = std::max(w1hi, w1); }
+    bm0[w] |= 1ull << (c & 63);
+  };
+  auto bm_drain = [&](std::vector<int32_t>& out) {
+    for (int32_t w1 = w1lo; w1 <= w1hi; ++w1) {
+      uint64_t m1 = bm1[w1];
+      bm1[w1] = 0;
+      while (m1) {
+        const int32_t w = (w1 << 6) + __builtin_ctzll(m1);
+        m1 &= m1 - 1;
+        uint64_t m0 = bm0[w];
+        bm0[w] = 0;
+        while (m0) { out.push_back((w << 6) + __builtin_ctzll(m0)); m0 &= m0 - 1; }
+      }
+    }
+    w1lo = INT32_MAX; w1hi = -1;
+  };
   // Without the adjacency pattern: an element is a clique of its 6 nodes, and in a valid elimination forest they lie on one
   // root path — so it is enough to hand the element to the front of its FIRST eliminated node (the later nodes reach the
   // fronts further up through the children's update sets).  One pass over the elements instead of one over every node's
@@ -675,28 +706,25 @@ void build_front_plan(const DofTables& dof, const Pattern* adj_p, const double* 
         const int32_t v = P.perm[r];
         for (int32_t q = adj_p->rowptr[v]; q < adj_p->rowptr[v + 1]; ++q) {
           const int32_t c = new_of[adj_p->col[q]];
-          if (c > last && mark[c] != f) { mark[c] = f; P.strct.push_back(c); }
+          if (c > last) bm_add(c);
         }
       }
     } else {
       for (int32_t q = eptr[f]; q < eptr[f + 1]; ++q) {
         const int32_t* en = &enew[6 * (int64_t)elist[q]];
-        for (int k = 0; k < 6; ++k) {
-          const int32_t c = en[k];
-          if (c > last && mark[c] != f) { mark[c] = f; P.strct.push_back(c); }
-        }
+        for (int k = 0; k < 6; ++k) if (en[k] > last) bm_add(en[k]);
       }
     }
     for (int32_t q = P.cptr[f]; q < P.cptr[f + 1]; ++q) {
       const int32_t ch = P.child[q];
       for (int32_t k = P.sptr[ch]; k < P.sptr[ch + 1]; ++k) {
         const int32_t c = P.strct[k];
-        if (c > last && mark[c] != f) { mark[c] = f; P.strct.push_back(c); }
+        if (c > last) bm_add(c);
         else if (c < P.first[f]) throw std::runtime_error("front plan: child update set escapes its parent");
       }
       P.level[f] = std::max(P.level[f], P.level[ch] + 1);
     }
-    std::sort(P.strct.begin() + b, P.strct.end());
+    bm_drain(P.strct);
     P.sptr[f + 1] = (int32_t)P.strct.size();
     if (P.parent[f] < 0 && P.sptr[f + 1] != (int32_t)b) throw std::runtime_error("front plan: root front has an update set");
   }
