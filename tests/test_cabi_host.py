@@ -263,3 +263,34 @@ def test_front_plan_is_the_frozen_one(cfg1, small_case):
     assert digest(cfg1[1], (0, 0)) == gold["cfg1_default"]
     assert digest(cfg1[1], (8, 16)) == gold["cfg1_leaf8_sn16"]
     assert digest(small_case[1], (0, 0)) == gold["small_default"]
+
+
+def test_solve_iter_keeps_job_order_and_bounds_the_forests_in_flight():
+    """`ForestPool.solve_iter` (host logic only: the forest solve is replaced): results come back in job order while at most
+    2 * workers + 2 forests are submitted and not yet consumed, however slowly the first one finishes."""
+    import threading
+    import time
+    from plfem_b200.batch import ForestPool, default_workers
+    assert default_workers(16) == 6 and default_workers(4) == 9
+    pool = ForestPool(batch=3, workers=2)
+    lock = threading.Lock()
+    state = {"started": 0, "consumed": 0, "max_ahead": 0}
+
+    def fake_forest(jobs):
+        with lock:
+            state["started"] += 1
+            state["max_ahead"] = max(state["max_ahead"], state["started"] - state["consumed"])
+        time.sleep(0.2 if jobs[0] == 0 else 0.002)          # the first forest is the slow one
+        return [j * 10 for j in jobs]
+    pool.solve_forest = fake_forest
+    try:
+        out = []
+        for r in pool.solve_iter(list(range(60))):
+            out.append(r)
+            if len(out) % 3 == 0:
+                with lock:
+                    state["consumed"] += 1
+        assert out == [10 * j for j in range(60)]
+        assert state["started"] == 20 and state["max_ahead"] <= 2 * 2 + 2
+    finally:
+        pool.close()
