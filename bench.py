@@ -331,9 +331,10 @@ def run_ours(args):
     pool_e = ForestPool(device=local, batch=B, workers=NW, want_vectors=True, share_analysis=False)
     step_jobs = [j for f in forests for j in f]
 
-    for _ in range(args.warmup):                            # whole steps through the same pipeline: contexts, device arenas and the
-        for modes in pool_e.solve_iter(step_jobs):          # pool of page-locked result blocks reach their steady state before timing
-            assert not isinstance(modes, Exception), modes
+    # whole steps through the same pipeline, as ONE stream of forests like the timed region (the same number of forests in
+    # flight): contexts, device arenas and the pool of page-locked result blocks reach their steady state before timing
+    for modes in pool_e.solve_iter(step_jobs * args.warmup):
+        assert not isinstance(modes, Exception), modes
     flush_l2()
     sync_all()
     with ClockSampler(local) as clocks2:
@@ -391,7 +392,17 @@ def run_ours(args):
     fo = _cabi.solve_modes_batch(ctx0, pbs0, [m for m, _ in mk0], [sigma_estimate(j[0]) for j in forests[-1]],
                                  [min(j[2] + 12, 2 * pb.n_interior - 4) for j, pb in zip(forests[-1], pbs0)], want_vectors=False)   # leaves plan + factors on the device
     fstats = fo[-1][4].as_dict()
+    # the sweeps are timed in the schedule the timed region ran with (a pool with several workers asks its contexts for one
+    # launch per level, a single solve uses the dataflow launch); the other schedule is measured too and reported beside it
+    pooled = NW > 1 and not os.environ.get("PLFEM_SWEEP")
+    prof_alone = None
+    if pooled:
+        prof_alone, _ = ctx0.profile_last(repeat=10)
+        ctx0.set_sweep_schedule(_cabi.Context.SWEEPS_PER_LEVEL)
     prof, nb_prof = ctx0.profile_last(repeat=10 if args.workload != "cfg5" else 3)
+    sweep_schedule = ctx0.sweep_schedule
+    if pooled:
+        ctx0.set_sweep_schedule(-1)
     nblk = fstats["batch_block_ops"]
     n_sweeps = nblk * (1 + int(fstats["refine_steps"]))        # block-LDL^T solves per operator application: 1 + refinement steps
     fkey, bkey = "forward_sweep_4rhs", "backward_sweep_4rhs"
@@ -419,7 +430,7 @@ def run_ours(args):
     kernels["factorize"]["fp64_peak_source"] = "measured: mma.sync.m8n8k4.f64 chain, profiles/r02_fp64_peak.txt"
     kernels["factorize"]["frac_of_fp64_peak"] = kernels["factorize"]["fp64_tflops"] / 37.0
     kernels["factorize"]["factor_gflop"] = fl / 1e9
-    fused = not os.environ.get("PLFEM_SWEEP", "").startswith("l")
+    fused = sweep_schedule.startswith("dataflow")
     # launches of one sweep: the TMA-streamed bottom subtrees + ONE dataflow launch for every level above them (or, with
     # PLFEM_SWEEP=levels, one launch per elimination-tree level)
     launches_per = (2 if fused else fstats["n_levels"]) if "sweep" in dom else 1
@@ -446,6 +457,12 @@ def run_ours(args):
                         "the fronts of every design of the forest; algorithmic bytes = factor entries of the left block columns (8 B each) + the "
                         "right-hand sides; CUDA events on the library's stream around the whole sweep, L2 flushed before each timed sweep"}
 
+    if prof_alone is not None:      # the same sweep as ONE dataflow launch above the subtrees (what a solve alone on the device runs)
+        ms_a, by_a = prof_alone[dom]
+        roofline["single_solve_schedule"] = {"sweeps": "dataflow launch", "ms": ms_a, "achieved": by_a / (ms_a * 1e-3) / 1e9,
+                                             "frac": by_a / (ms_a * 1e-3) / 1e9 / hbm_peak}
+        if traffic is not None:
+            roofline["traffic_note"] = "ncu --set full capture of the dataflow schedule (profiles/r02_traffic.json), spread over this schedule's launches"
     cpu = cpu_baseline_sample(args.workload, 2) if (world == 1 and args.workload in ("cfg1", "cfg2")) else None
     pool.close()
     nst = args.steps
@@ -463,7 +480,7 @@ def run_ours(args):
                        "analysis_shared_between_designs": False,
                        "k": k, "lanczos": "thick-restart block Lanczos, 4 vectors per operator application, basis 3k, designs in lockstep", "tol": _cabi.EIG_TOL,
                        "start_vector": "ones (+3 fixed pseudo-random)", "refine_steps": int(fstats["refine_steps"]),
-                       "sweeps": "dataflow launch above the bottom subtrees" if not os.environ.get("PLFEM_SWEEP", "").startswith("l") else "one launch per level",
+                       "sweeps": sweep_schedule + " above the bottom subtrees (timed region and roofline; a single solve uses the dataflow launch)",
                        "l2": f"inputs larger than L2: one forest streams {B * fstats['factor_entries'] * 8 / 1e6:.0f} MB of factor panels per sweep "
                              f"(front pools {B * fstats['front_pool_doubles'] * 8 / 1e9:.2f} GB); L2 also flushed (512 MiB write) before the timed region",
                        "timing": "wall clock around the K steps (forests) submitted to the worker threads, cuda synchronize + barrier on both sides, max over ranks",

@@ -46,6 +46,16 @@ const char* plfem_last_error(const plfem_ctx* ctx);
 /* host threads the symbolic analysis of ONE call (a solve, or a whole forest) may use (0 = default: min(cores, 8) for a
  * single solve, every core for a forest); lower it when several contexts / processes share the host */
 void plfem_set_host_threads(int n);
+/* How the forward / backward sweeps run above the bottom subtrees: PLFEM_SWEEPS_DATAFLOW (default) = one persistent launch per
+ * direction whose tasks wait on per-front counters — fastest for a solve that has the device to itself; PLFEM_SWEEPS_PER_LEVEL =
+ * one launch per elimination-tree level — nothing waits on the device, better when several contexts keep forests in flight on
+ * one GPU (the forest pool of the host package asks for it).  Results are bit-identical.  -1 restores the default; the
+ * environment variable PLFEM_SWEEP=levels|dataflow overrides every context (A/B runs).  Set it before the first solve. */
+#define PLFEM_SWEEPS_DATAFLOW 0
+#define PLFEM_SWEEPS_PER_LEVEL 1
+int plfem_ctx_set_sweep_schedule(plfem_ctx* ctx, int schedule);
+/* the schedule in effect for this context (environment override included) */
+int plfem_ctx_sweep_schedule(const plfem_ctx* ctx);
 /* abi / build identification: "plfem <version> sm_100a" */
 const char* plfem_version(void);
 

@@ -33,7 +33,7 @@ EIG_TOL = 1e-8
 SYMBOLS = ["plfem_ctx_create", "plfem_ctx_destroy", "plfem_last_error", "plfem_version",
            "plfem_problem_create", "plfem_problem_destroy", "plfem_problem_set_dirichlet", "plfem_problem_info", "plfem_problem_dofs",
            "plfem_quad_points", "plfem_assemble", "plfem_export_csr", "plfem_spmv_csr", "plfem_solve_modes",
-           "plfem_plan_sizes", "plfem_plan_export", "plfem_debug_symeig", "plfem_debug_symeig_tail", "plfem_profile_kernels", "plfem_set_host_threads",
+           "plfem_plan_sizes", "plfem_plan_export", "plfem_debug_symeig", "plfem_debug_symeig_tail", "plfem_profile_kernels", "plfem_set_host_threads", "plfem_ctx_set_sweep_schedule", "plfem_ctx_sweep_schedule",
            "plfem_debug_solve", "plfem_solve_modes_batch", "plfem_profile_last", "plfem_host_alloc", "plfem_host_free"]
 
 
@@ -120,6 +120,8 @@ def load():
         lib.plfem_debug_solve.argtypes = [vp, c_f64, p_f64, p_f64, C.c_int]
         lib.plfem_set_host_threads.argtypes = [C.c_int]
         lib.plfem_set_host_threads.restype = None
+        lib.plfem_ctx_set_sweep_schedule.argtypes = [vp, C.c_int]
+        lib.plfem_ctx_sweep_schedule.argtypes = [vp]
         lib.plfem_profile_kernels.argtypes = [vp, C.POINTER(Material), c_f64, C.c_int, p_f64, p_f64]
         lib.plfem_profile_last.argtypes = [vp, C.c_int, p_f64, p_f64, p_i32]
         lib.plfem_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
@@ -208,6 +210,17 @@ class Context:
         if device not in cls._cache:
             cls._cache[device] = cls(device)
         return cls._cache[device]
+
+    SWEEPS_DATAFLOW, SWEEPS_PER_LEVEL = 0, 1
+
+    def set_sweep_schedule(self, schedule: int):
+        """``SWEEPS_DATAFLOW`` (default: one persistent launch per sweep direction, best for a solve alone on the device) or
+        ``SWEEPS_PER_LEVEL`` (one launch per elimination-tree level, best with several forests in flight); before the first solve."""
+        self.check(self.lib.plfem_ctx_set_sweep_schedule(self.handle, int(schedule)))
+
+    @property
+    def sweep_schedule(self) -> str:
+        return "one launch per level" if self.lib.plfem_ctx_sweep_schedule(self.handle) == 1 else "dataflow launch"
 
     def check(self, st: int):
         if st != 0:

@@ -231,6 +231,14 @@ const char* plfem_version(void) { return "plfem 0.1 sm_100a"; }
 
 void plfem_set_host_threads(int n) { plfem::set_host_threads(n); }
 
+int plfem_ctx_set_sweep_schedule(plfem_ctx* ctx, int schedule) {
+  if (!ctx || schedule < -1 || schedule > 1) return PLFEM_ERR_INVALID;
+  ctx->sweep_schedule = schedule;
+  return PLFEM_OK;
+}
+
+int plfem_ctx_sweep_schedule(const plfem_ctx* ctx) { return ctx ? (plfem::use_fused_sweeps(ctx) ? 0 : 1) : -1; }
+
 int plfem_ctx_create(int device, plfem_ctx** out) {
   if (!out) return PLFEM_ERR_INVALID;
   *out = nullptr;

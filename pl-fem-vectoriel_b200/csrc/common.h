@@ -84,6 +84,7 @@ struct plfem_ctx {
   std::string err;
   plfem::DeviceArena arena;
   int launches = 0;          // kernels launched since the counter was last reset
+  int sweep_schedule = -1;   // PLFEM_SWEEPS_*: -1 = follow $PLFEM_SWEEP (default: dataflow), see plfem_ctx_set_sweep_schedule
   cudaEvent_t ev[8] = {};
   std::shared_ptr<plfem::SolveWork> last_work;   // what the last solve left on the device (measurement hook)
   void* pinned = nullptr;    // pinned staging buffer for small device->host reads
@@ -307,6 +308,7 @@ void launch_resid_k(plfem_ctx* ctx, const DevPattern& pat, const double* d_vals,
                     const double* b, double* t, int nrhs = 1, const uint8_t* active_node = nullptr);
 
 void launch_axpy(plfem_ctx* ctx, double* x, const double* dx, int64_t m);
+bool use_fused_sweeps(const plfem_ctx* ctx);   // factor.cu: dataflow launch (true) or one launch per level above the bottom subtrees
 void symmetric_eigen(int n, std::vector<double>& a /* n*n col-major in, eigenvectors out */, std::vector<double>& w);
 // eigenvalues + the last p rows of the eigenvector matrix only (tail[j*p + r] = Z(n-p+r, j)); a is destroyed
 void symmetric_eigen_tail(int n, std::vector<double>& a, std::vector<double>& w, int p, std::vector<double>& tail);

@@ -529,9 +529,15 @@ bool use_pdl() {
   return on;
 }
 
-bool use_fused_sweeps() {      // PLFEM_SWEEP=levels: one launch per elimination-tree level (the round-2 scheme, kept for A/B runs)
-  static const bool on = [] { const char* e = std::getenv("PLFEM_SWEEP"); return !(e && e[0] == 'l'); }();
-  return on;
+// Above the bottom subtrees a sweep is either ONE dataflow launch (persistent CTAs taking tickets, waiting on per-front
+// counters: fastest for a sweep that has the device to itself, 0.195 vs 0.227 ms on a config-1 forest) or one launch per
+// elimination-tree level (nothing ever waits on the device: with several forests in flight on one GPU their launches
+// interleave better, 502 vs 456 solves/s).  A context says which it wants (plfem_ctx_set_sweep_schedule: the forest pool
+// asks for per-level launches when it runs more than one worker); $PLFEM_SWEEP=levels|dataflow overrides for A/B runs.
+bool use_fused_sweeps(const plfem_ctx* ctx) {
+  static const int env = [] { const char* e = std::getenv("PLFEM_SWEEP"); return !e || !e[0] ? -1 : (e[0] == 'l' ? 1 : 0); }();
+  const int mode = env >= 0 ? env : (ctx->sweep_schedule >= 0 ? ctx->sweep_schedule : 0);
+  return mode == 0;
 }
 
 // nrhs right-hand sides (1 or SOLVE_NRHS), INTERLEAVED: entry i of right-hand side r at b[i * nrhs + r].  One launch for the
@@ -541,7 +547,7 @@ bool use_fused_sweeps() {      // PLFEM_SWEEP=levels: one launch per elimination
 void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double* z, int nrhs, const uint8_t* active) {
   if (nrhs != 1 && nrhs != SOLVE_NRHS) throw StatusError(PLFEM_ERR_INTERNAL, "unsupported number of right-hand sides");
   const bool pdl = use_pdl();
-  const bool fused = use_fused_sweeps();
+  const bool fused = use_fused_sweeps(ctx);
   reset_sweep_counters(ctx, D);                // forward and backward counters, before the first launch of the solve
   bool first = true;     // the first launch follows kernels that are not PDL-aware: plain launch
   if (D.st.n_subs > 0) {
@@ -564,7 +570,7 @@ void run_solve_forward(plfem_ctx* ctx, const DevPlan& D, const double* b, double
 void run_solve_backward(plfem_ctx* ctx, const DevPlan& D, double* x, int nrhs, bool reset_counters, const uint8_t* active) {
   const bool pdl = use_pdl();
   if (reset_counters) reset_sweep_counters(ctx, D);
-  if (use_fused_sweeps()) {
+  if (use_fused_sweeps(ctx)) {
     launch_fused_backward(ctx, D, x, nrhs, pdl && !reset_counters, active);
   } else {
     for (int l = D.nlevels - 1; l >= 0; --l) {
