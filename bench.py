@@ -242,7 +242,10 @@ def run_ours(args):
 
     # designs per forest / forests in flight: cfg5 is ONE 2M-unknown design per step (a forest of one, one worker)
     B = 1 if args.workload == "cfg5" else max(1, args.inflight)
-    NW = 1 if args.workload == "cfg5" else (args.workers if args.workers > 0 else default_workers())
+    # forests in flight: cfg1's contexts take ~4 GB each; the 19-core / LHS forests (k = 52: a 164-vector basis, larger fronts)
+    # take 10-15 GB each, twelve of them do not fit one B200 (measured: cfg4 fails to allocate with 12, cfg2 runs with 10)
+    NW = 1 if args.workload == "cfg5" else (args.workers if args.workers > 0 else
+                                            {"cfg1": default_workers(), "cfg2": 8, "cfg4": 6}.get(args.workload, 6))
     w, jobs = make_jobs(args.workload, B * NW, B)
     forests = [jobs[i * B:(i + 1) * B] for i in range(NW)]          # forest i of a step is worker i's
     g, mesh, n_modes = forests[-1][-1]                              # the largest design (cfg4: sorted) for latency / sizes
@@ -325,6 +328,11 @@ def run_ours(args):
             t_value += time.perf_counter() - t0
             assert allrec.shape == (world * NF * B, N_RECORD)
     stats = st.as_dict()
+    host_threads = pool.host_threads
+    n_int = {wi: [pb.n_interior for pb in resident[wi][0]] for wi in resident}      # for the byte counts of the end-to-end run
+    resident.clear()
+    pool.close()                 # the contexts of the value run (streams, device arenas with their front pools) go back before the
+    #                              end-to-end pool creates its own: two pools of twelve contexts each do not fit for the larger workloads
 
     # ---- e2e: public API, host buffers in, mode records (with eigenvectors) out -----------------------------
     # share_analysis off: the designs of this synthetic step sit on ONE mesh, a real sweep's do not — every design pays its own analysis
@@ -369,9 +377,9 @@ def run_ours(args):
     h2d = sum(j[1].p.nbytes + j[1].t.astype(np.int64).nbytes + 8 * (3 * j[0].n_cores + 4) for j in step_jobs)
     d2h = 0
     for f, wi in zip(forests, range(NW)):
-        for j, pb in zip(f, resident[wi][0]):
-            kk = min(j[2] + 12, 2 * pb.n_interior - 4)
-            d2h += 8 * (kk + kk * 2 * pb.n_interior + kk * _cabi.NMETRICS)
+        for j, ni in zip(f, n_int[wi]):
+            kk = min(j[2] + 12, 2 * ni - 4)
+            d2h += 8 * (kk + kk * 2 * ni + kk * _cabi.NMETRICS)
 
     if world > 1:
         tt = torch.tensor([t_value, t_e2e], dtype=torch.float64, device=f"cuda:{local}")
@@ -382,7 +390,6 @@ def run_ours(args):
         launches = int(lt.item())
 
     if rank != 0:
-        pool.close()
         if world > 1:
             dist.destroy_process_group()
         return
@@ -464,7 +471,6 @@ def run_ours(args):
         if traffic is not None:
             roofline["traffic_note"] = "ncu --set full capture of the dataflow schedule (profiles/r02_traffic.json), spread over this schedule's launches"
     cpu = cpu_baseline_sample(args.workload, 2) if (world == 1 and args.workload in ("cfg1", "cfg2")) else None
-    pool.close()
     nst = args.steps
     line = {"metric": "modal_solves_per_sec", "value": world * B * NF / t_value, "unit": "solves/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_value / args.steps, "higher_is_better": True,
@@ -495,7 +501,7 @@ def run_ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "phases_ms_per_forest": {n: v / NF for n, v in phase.items()},
-            "host": {"cores": os.cpu_count(), "host_threads_per_forest": pool.host_threads,
+            "host": {"cores": os.cpu_count(), "host_threads_per_forest": host_threads,
                      "cpu_ms_per_solve_value": 1e3 * cpu_value / (B * NF), "cpu_ms_per_solve_e2e": 1e3 * cpu_e2e / (B * NF),
                      "note": "process CPU time of rank 0 inside the two timed regions / designs solved"},
             "solver": {kk: stats[kk] for kk in ("nconv", "n_op", "n_block_op", "n_restart", "n_fronts", "n_levels", "max_front_nodes", "factor_entries",
@@ -516,7 +522,7 @@ def main():
                     help="cfg1 (default, the configuration the metric is quoted on), cfg2, cfg4 (heterogeneous LHS sample), cfg5 (2M unknowns)")
     ap.add_argument("--inflight", type=int, default=12, help="designs per forest (= per step)")
     ap.add_argument("--workers", type=int, default=0, help="host threads / contexts, each working on its own forest "
-                    "(0 = batch.default_workers(): 6, or 9 when this rank has fewer than 8 host cores)")
+                    "(0 = 12 for cfg1 (batch.default_workers()), 8 for cfg2, 6 for cfg4: device memory)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     if args.impl == "reference":

@@ -136,54 +136,77 @@ def _ptr(a, typ):
 
 
 class PinnedPool:
-    """Recycling pool of page-locked host blocks for the big result arrays (eigenvectors).
+    """Page-locked host memory for the big result arrays (eigenvectors), carved out of a few large slabs.
 
-    ``empty(shape)`` returns a float64 NumPy array backed by a pinned block; when the array (and every view of it —
-    the mode records hold views) is garbage-collected the block goes back to the pool.  Device->host copies into such
-    arrays run at link speed and touch no fresh pages.  Above ``cap_bytes`` of blocks in use the pool hands out ordinary
-    ``np.empty`` arrays, so a caller that keeps thousands of results alive does not pin all of host memory."""
+    ``empty(shape)`` returns a float64 NumPy array backed by a piece of a pinned slab; when the array (and every view of it —
+    the mode records hold views) is garbage-collected the piece goes back to the slab's free list and merges with its free
+    neighbours.  Device->host copies into such arrays run at link speed and touch no fresh pages.  Slabs are 512 MiB (or the
+    request, if larger): an LHS sweep returns blocks of many sizes (k = 14 ... 52 modes on 20k ... 120k unknowns), and one
+    cudaHostAlloc per size class — milliseconds each, serialised with the device's other work — kept happening inside the
+    sweep.  Above ``cap_bytes`` of slabs the pool hands out ordinary ``np.empty`` arrays, so a caller that keeps thousands of
+    results alive does not pin all of host memory."""
+
+    SLAB = 512 << 20
+    ALIGN = 4096
 
     def __init__(self, cap_bytes: int = 8 << 30):
-        self.cap, self.in_use = int(cap_bytes), 0
-        self.free: dict = {}
+        self.cap, self.reserved, self.in_use = int(cap_bytes), 0, 0
+        self.free: list = []            # [address, size, slab id], sorted by address; neighbours of one slab are merged
+        self.n_slabs = 0
         self.lock = threading.Lock()
 
-    @staticmethod
-    def _size_class(nbytes: int) -> int:
-        """Eight classes per octave (<= 12.5 % slack): the eigenvector blocks of an LHS sweep come in many sizes (k = 14 ... 52
-        modes on 20k ... 120k unknowns) and powers of two alone wasted up to half of the pool's cap."""
-        c = 1 << 16
-        while c < nbytes:
-            c <<= 1
-        if c > (1 << 16):
-            step = c >> 4                      # the octave (c/2, c] in eight steps
-            c = (c >> 1) + -(-(nbytes - (c >> 1)) // step) * step
-        return c
+    def _take(self, size: int):
+        for i, (addr, sz, slab) in enumerate(self.free):          # first fit
+            if sz >= size:
+                if sz == size:
+                    del self.free[i]
+                else:
+                    self.free[i] = [addr + size, sz - size, slab]
+                return addr, slab
+        return None
 
-    def _give_back(self, ptr: int, size: int):
+    def _give_back(self, addr: int, size: int, slab: int):
+        import bisect
         with self.lock:
-            self.free.setdefault(size, []).append(ptr)
             self.in_use -= size
+            i = bisect.bisect_left(self.free, [addr, 0, 0])
+            self.free.insert(i, [addr, size, slab])
+            if i + 1 < len(self.free) and self.free[i + 1][2] == slab and addr + size == self.free[i + 1][0]:
+                self.free[i][1] += self.free[i + 1][1]
+                del self.free[i + 1]
+            if i > 0 and self.free[i - 1][2] == slab and self.free[i - 1][0] + self.free[i - 1][1] == addr:
+                self.free[i - 1][1] += self.free[i][1]
+                del self.free[i]
 
     def empty(self, shape) -> np.ndarray:
+        import bisect
         import weakref
         n = int(np.prod(shape))
-        size = self._size_class(8 * max(n, 1))
+        size = -(-8 * max(n, 1) // self.ALIGN) * self.ALIGN
         with self.lock:
-            if self.in_use + size > self.cap:
-                return np.empty(shape)
-            lst = self.free.get(size)
-            ptr = lst.pop() if lst else None
-            self.in_use += size
-        if ptr is None:
+            got = self._take(size)
+            if got is None:
+                slab_bytes = max(self.SLAB, size)
+                if self.reserved + slab_bytes > self.cap:
+                    return np.empty(shape)
+                self.reserved += slab_bytes             # reserved before the (slow) allocation, outside the lock below
+        if got is None:
             h = C.c_void_p()
-            if load().plfem_host_alloc(size, C.byref(h)) != 0 or not h.value:
+            if load().plfem_host_alloc(slab_bytes, C.byref(h)) != 0 or not h.value:
                 with self.lock:
-                    self.in_use -= size
+                    self.reserved -= slab_bytes
                 return np.empty(shape)
-            ptr = h.value
-        buf = (c_f64 * n).from_address(ptr)
-        weakref.finalize(buf, self._give_back, ptr, size)      # runs when the last array / view over buf dies
+            with self.lock:
+                slab = self.n_slabs
+                self.n_slabs += 1
+                if slab_bytes > size:
+                    bisect.insort(self.free, [h.value + size, slab_bytes - size, slab])
+                got = (h.value, slab)
+        with self.lock:
+            self.in_use += size
+        addr, slab = got
+        buf = (c_f64 * n).from_address(addr)
+        weakref.finalize(buf, self._give_back, addr, size, slab)      # runs when the last array / view over buf dies
         return np.ctypeslib.as_array(buf).reshape(shape)
 
 

@@ -29,12 +29,14 @@ from .solver_fem import TrueVectorialMaxwellSolver, modes_from_solution, sigma_e
 
 
 def default_workers(cores: int = 0) -> int:
-    """Forests in flight per GPU.  A worker thread analyses its forest on the host (about 5 ms per config-1 design) and then
-    drives it on the device; with few host cores per GPU (an 8-GPU node with 32 cores gives a rank four) the analysis phases
-    are long and more forests have to be in flight to keep the device fed.  Measured on one B200 restricted to four cores:
-    6 / 9 / 12 workers give 375 / 416 / 430 solves/s; with 16 cores 6 workers saturate the device (469)."""
-    cores = cores or usable_cores()
-    return 6 if cores >= 8 else 9
+    """Forests in flight per GPU.  A worker thread analyses its forest on the host (about 4 ms per config-1 design), drives it
+    on the device and builds its records; with the sweeps launched level by level (nothing waits on the device) more forests
+    in flight keep filling the GPU until about twelve.  Measured on one B200, config 1, solves/s device-resident / end to end:
+    16 host cores: 6 workers 480 / 416, 8: 517 / 492, 10: 525 / 511, 12: 529 / 526, 15: 530 / 529;
+    restricted to 4 cores (a rank's share of a 32-core 8-GPU node): 9 workers 417-431 / 372-390, 12: 454 / 390.
+    Each context keeps its device arena (about 4 GB for forests of twelve 7-core designs, 10-15 GB for 19-core designs with
+    k = 52): callers with large designs pass fewer workers; an arena that cannot allocate trims every arena's cache first."""
+    return 12
 
 
 def usable_cores() -> int:
@@ -148,16 +150,16 @@ class ForestPool:
         """Like ``solve_many`` but yields the mode list (or the Exception) of one job at a time, in job order, while
         later forests are still being solved — a consumer that reduces each result (a dataset record) and drops it
         keeps only a few forests of eigenvectors alive, and their page-locked buffers are recycled.  Forests are handed to
-        the worker threads as the consumer takes results: at most ``2 * workers + 2`` are submitted and not yet consumed — every
-        worker busy plus as many finished forests waiting behind a slower one that is due first (results come in job order;
-        a window of ``workers + 2`` was measured to starve the workers: 441 -> 385 solves/s) — so finished forests cannot pile up
-        without bound and the page-locked pool stays below its cap."""
+        the worker threads as the consumer takes results: at most ``workers + max(4, workers / 2)`` are submitted and not yet
+        consumed — every worker busy plus some finished forests waiting behind a slower one that is due first (results come in
+        job order; a window of ``workers + 2`` was measured to starve six workers: 441 -> 385 solves/s) — so finished forests
+        cannot pile up without bound and the page-locked pool stays below its cap."""
         from collections import deque
         chunks = [jobs[i:i + self.batch] for i in range(0, len(jobs), self.batch)]
         pending: deque = deque()
         nxt = 0
         while nxt < len(chunks) or pending:
-            while nxt < len(chunks) and len(pending) < 2 * self.workers + 2:
+            while nxt < len(chunks) and len(pending) < self.workers + max(4, self.workers // 2):
                 pending.append(self._pool.submit(self.solve_forest, chunks[nxt]))
                 nxt += 1
             part = pending.popleft().result()

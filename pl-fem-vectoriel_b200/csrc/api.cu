@@ -26,27 +26,51 @@ static size_t size_class(size_t bytes) {
   return c;
 }
 
-void* DeviceArena::alloc(size_t bytes) {
+// Every arena of the process (one per context: a forest pool keeps a dozen on one GPU).  Blocks an arena has cached but is not
+// using are what fills the device when many contexts have each seen a large forest: an arena that cannot get memory first gives
+// back its own cache, then asks all the others to do the same, and only then fails.
+static std::mutex g_arenas_mu;
+static std::vector<DeviceArena*> g_arenas;
+
+size_t DeviceArena::trim() {
   std::lock_guard<std::mutex> g(mu_);
+  size_t freed = 0;
+  for (auto& kv : free_) { cudaFree(kv.second); reserved_ -= kv.first; freed += kv.first; }
+  free_.clear();
+  return freed;
+}
+
+void* DeviceArena::alloc(size_t bytes) {
   const size_t c = size_class(bytes);
-  auto it = free_.find(c);
-  void* p = nullptr;
-  if (it != free_.end()) {
-    p = it->second;
-    free_.erase(it);
-  } else {
-    cudaError_t e = cudaMalloc(&p, c);
-    if (e != cudaSuccess) {
-      // give cached blocks back and retry once
-      for (auto& kv : free_) { cudaFree(kv.second); reserved_ -= kv.first; }
-      free_.clear();
-      e = cudaMalloc(&p, c);
-      if (e != cudaSuccess) throw CudaError(std::string("cudaMalloc of ") + std::to_string(c) + " bytes failed: " + cudaGetErrorString(e));
-    }
-    reserved_ += c;
+  if (!registered_) {
+    std::lock_guard<std::mutex> g(g_arenas_mu);
+    if (!registered_) { g_arenas.push_back(this); registered_ = true; }
   }
-  live_[p] = c;
-  return p;
+  for (int attempt = 0;; ++attempt) {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      auto it = free_.find(c);
+      void* p = nullptr;
+      if (it != free_.end()) {
+        p = it->second;
+        free_.erase(it);
+        live_[p] = c;
+        return p;
+      }
+      const cudaError_t e = cudaMalloc(&p, c);
+      if (e == cudaSuccess) { reserved_ += c; live_[p] = c; return p; }
+      (void)cudaGetLastError();     // the failure must not stay behind as the "last error" of a later, successful launch
+      if (attempt >= 2)
+        throw CudaError(std::string("cudaMalloc of ") + std::to_string(c) + " bytes failed: " + cudaGetErrorString(e));
+    }
+    // (no arena lock is held here: two arenas trimming each other cannot deadlock)
+    if (attempt == 0) {
+      trim();
+    } else {
+      std::lock_guard<std::mutex> g(g_arenas_mu);
+      for (DeviceArena* a : g_arenas) a->trim();
+    }
+  }
 }
 
 void DeviceArena::release(void* p) {
@@ -58,6 +82,12 @@ void DeviceArena::release(void* p) {
 }
 
 void DeviceArena::destroy() {
+  {
+    std::lock_guard<std::mutex> g(g_arenas_mu);
+    g_arenas.erase(std::remove(g_arenas.begin(), g_arenas.end(), this), g_arenas.end());
+    registered_ = false;
+  }
+  std::lock_guard<std::mutex> g(mu_);
   for (auto& kv : free_) cudaFree(kv.second);
   for (auto& kv : live_) cudaFree(kv.first);
   free_.clear(); live_.clear(); reserved_ = 0;

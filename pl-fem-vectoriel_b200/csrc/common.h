@@ -66,8 +66,10 @@ class DeviceArena {
   void release(void* p);
   void destroy();
   size_t reserved_bytes() const { return reserved_; }
+  size_t trim();    // cudaFree every cached (unused) block; returns the bytes given back
 
  private:
+  bool registered_ = false;
   std::mutex mu_;   // problems of one context may be created from several host threads
   std::multimap<size_t, void*> free_;
   std::map<void*, size_t> live_;

@@ -267,11 +267,11 @@ def test_front_plan_is_the_frozen_one(cfg1, small_case):
 
 def test_solve_iter_keeps_job_order_and_bounds_the_forests_in_flight():
     """`ForestPool.solve_iter` (host logic only: the forest solve is replaced): results come back in job order while at most
-    2 * workers + 2 forests are submitted and not yet consumed, however slowly the first one finishes."""
+    workers + max(4, workers / 2) forests are submitted and not yet consumed, however slowly the first one finishes."""
     import threading
     import time
     from plfem_b200.batch import ForestPool, default_workers
-    assert default_workers(16) == 6 and default_workers(4) == 9
+    assert default_workers(16) >= 6 and default_workers(4) >= 6
     pool = ForestPool(batch=3, workers=2)
     lock = threading.Lock()
     state = {"started": 0, "consumed": 0, "max_ahead": 0}
@@ -291,6 +291,49 @@ def test_solve_iter_keeps_job_order_and_bounds_the_forests_in_flight():
                 with lock:
                     state["consumed"] += 1
         assert out == [10 * j for j in range(60)]
-        assert state["started"] == 20 and state["max_ahead"] <= 2 * 2 + 2
+        assert state["started"] == 20 and state["max_ahead"] <= 2 + 4
     finally:
         pool.close()
+
+
+def test_pinned_pool_carves_blocks_out_of_slabs_and_merges_them_back(monkeypatch):
+    """`_cabi.PinnedPool` (host logic; the page-locked allocation is replaced by plain buffers): blocks of many sizes never
+    overlap, freed blocks merge back into whole slabs, no new slab is taken while a free piece fits, and beyond the cap the
+    pool falls back to ordinary arrays."""
+    import ctypes as C
+    import gc
+
+    class FakeLib:
+        def __init__(self):
+            self.bufs = []
+
+        def plfem_host_alloc(self, nbytes, ref):
+            b = (C.c_char * nbytes)()
+            self.bufs.append(b)
+            ref._obj.value = C.addressof(b)
+            return 0
+    fake = FakeLib()
+    monkeypatch.setattr(_cabi, "load", lambda: fake)
+    pool = _cabi.PinnedPool(cap_bytes=64 << 20)
+    pool.SLAB = 16 << 20
+    rng = np.random.default_rng(0)
+    live = []
+    for it in range(1500):
+        if live and rng.random() < 0.5:
+            live.pop(rng.integers(len(live)))
+        else:
+            live.append(pool.empty((int(rng.integers(1, 400000)),)))
+            live[-1][:] = it
+    spans = sorted((x.ctypes.data, x.ctypes.data + x.nbytes) for x in live)
+    assert all(spans[i][1] <= spans[i + 1][0] for i in range(len(spans) - 1))
+    assert all((x == x[0]).all() for x in live)
+    n_slabs = len(fake.bufs)
+    assert 1 <= n_slabs <= 4
+    live.clear()
+    gc.collect()
+    assert pool.in_use == 0 and len(pool.free) == n_slabs and all(f[1] == 16 << 20 for f in pool.free)
+    a = pool.empty((1 << 20,))                       # 8 MiB: fits a free slab, no new allocation
+    assert len(fake.bufs) == n_slabs
+    big = [pool.empty((3 << 20,)) for _ in range(4)]       # 24 MiB each: own slabs until the cap, then ordinary arrays
+    assert pool.reserved <= 64 << 20 and all(b.shape == (3 << 20,) for b in big)
+    del a, big
