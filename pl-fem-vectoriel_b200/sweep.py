@@ -207,7 +207,8 @@ def run_sweep(designs: Sequence[Dict], rank: int = 0, world: int = 1, device: in
 
     ``forest = B > 0`` is the production mode on GPUs: the shard is cut into forests of ``B`` designs, each solved by
     one `plfem_solve_modes_batch` call.  With the default worker the forests are pipelined: ``mesh_threads`` host threads
-    build geometries and Delaunay meshes ahead, ``workers`` forest threads (0 = `batch.default_workers()`; each with its own CUDA context) take the
+    build geometries and Delaunay meshes ahead, ``workers`` forest threads (0 = 6: the device arenas of six contexts hold forests of the largest LHS designs — 19 cores, k = 52 —
+    on one B200, `batch.default_workers()` = 12 suits 7-core designs; each with its own CUDA context) take the
     forests in order, so meshing, the host analysis of one forest and the device work of another overlap; designs of a
     forest on an identical mesh (the bands of a wavelength sweep) share one analysis.  A custom
     ``forest_fn(list of designs) -> list of results or Exceptions`` is called forest by forest.
@@ -230,9 +231,9 @@ def run_sweep(designs: Sequence[Dict], rank: int = 0, world: int = 1, device: in
 
     if forest > 0 and forest_fn is None:
         from concurrent.futures import ThreadPoolExecutor
-        from .batch import ForestPool, default_workers
+        from .batch import ForestPool
         chunks = [(j0, mine[j0:j0 + forest]) for j0 in range(0, len(mine), forest)]
-        with ForestPool(device=device, batch=forest, workers=workers if workers > 0 else default_workers()) as pool, \
+        with ForestPool(device=device, batch=forest, workers=workers if workers > 0 else 6) as pool, \
                 ThreadPoolExecutor(max_workers=max(1, mesh_threads), thread_name_prefix="plfem-mesh") as mesher:
             prepared = {i: mesher.submit(prepare_design, designs[i]) for _, idx in chunks for i in idx}   # in sweep order
 
