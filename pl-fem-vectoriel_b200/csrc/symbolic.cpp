@@ -448,23 +448,23 @@ void dissect_vertex_graph(const DofTables& d, const std::vector<int32_t>& interi
   std::vector<int32_t> vid(V, -1), vdof;
   for (int64_t v = 0; v < V; ++v) if (int_of[v] >= 0) { vid[v] = (int32_t)vdof.size(); vdof.push_back((int32_t)v); }
   const int32_t nv = (int32_t)vdof.size();
+  // two vertices share an element iff they share a mesh edge: the adjacency comes straight from the facet table (two
+  // counting passes over the edges; rows are unsorted and carry no self entry — the dissection only asks for the extreme
+  // neighbour ranks, and a node's own rank always takes part)
   Pattern vadj;
   vadj.n = nv;
   vadj.rowptr.assign(nv + 1, 0);
+  for (int64_t f = 0; f < d.E; ++f) {
+    const int32_t a = vid[d.facets[2 * f]], b = vid[d.facets[2 * f + 1]];
+    if (a >= 0 && b >= 0) { vadj.rowptr[a + 1]++; vadj.rowptr[b + 1]++; }
+  }
+  for (int32_t a = 0; a < nv; ++a) vadj.rowptr[a + 1] += vadj.rowptr[a];
+  vadj.col.resize(vadj.rowptr[nv]);
   {
-    std::vector<int32_t> stamp(nv, -1);
-    vadj.col.reserve((size_t)nv * 8);
-    for (int32_t a = 0; a < nv; ++a) {
-      const int32_t va = vdof[a];
-      stamp[a] = a; vadj.col.push_back(a);
-      for (int32_t q = d.n2e_ptr[va]; q < d.n2e_ptr[va + 1]; ++q) {
-        const int32_t* ed = &d.edofs[6 * (int64_t)d.n2e[q]];
-        for (int k = 0; k < 3; ++k) {
-          const int32_t c = vid[ed[k]];
-          if (c >= 0 && stamp[c] != a) { stamp[c] = a; vadj.col.push_back(c); }
-        }
-      }
-      vadj.rowptr[a + 1] = (int32_t)vadj.col.size();     // (rows stay unsorted: the dissection only asks "any/extreme neighbour")
+    std::vector<int32_t> fill(vadj.rowptr.begin(), vadj.rowptr.end() - 1);
+    for (int64_t f = 0; f < d.E; ++f) {
+      const int32_t a = vid[d.facets[2 * f]], b = vid[d.facets[2 * f + 1]];
+      if (a >= 0 && b >= 0) { vadj.col[fill[a]++] = b; vadj.col[fill[b]++] = a; }
     }
   }
   std::vector<double> vx(nv), vy(nv);
@@ -518,6 +518,7 @@ void dissect_vertex_graph(const DofTables& d, const std::vector<int32_t>& interi
     for (size_t i = 0; i < o.size(); ++i) o[i] = keyed[i].second;
   };
   out = Forest(); out_roots.clear();
+  out.nodes.reserve((size_t)nt + nt / 4 + 16);
   std::vector<int32_t> head(nt, -1);          // tree node of `out` heading (last chain link of) vertex-tree node t
   // children before parents: process in reverse DFS order
   std::vector<int32_t> order; order.reserve(nt);
