@@ -391,13 +391,15 @@ __global__ void __launch_bounds__(256) update_block_kernel(const double* __restr
 }
 
 // Hs_b[0..ncols, r] = h1 + h2 (the projected-matrix column block kept for the host)
-__global__ void store_h_kernel(const double* __restrict__ h1, const double* __restrict__ h2, int ldh, int64_t hstride, int ncols,
+// (the first pass covered the columns c >= c1 only: h1 counts from there)
+__global__ void store_h_kernel(const double* __restrict__ h1, const double* __restrict__ h2, int ldh, int64_t hstride, int ncols, int c1,
                                double* __restrict__ Hs, int lds, int64_t sstride) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (c >= ncols) return;
 #pragma unroll
-  for (int r = 0; r < P; ++r) Hs[b * sstride + c + r * lds] = h1[b * hstride + c + r * ldh] + h2[b * hstride + c + r * ldh];
+  for (int r = 0; r < P; ++r)
+    Hs[b * sstride + c + r * lds] = (c >= c1 ? h1[b * hstride + c + r * ldh] : 0.0) + h2[b * hstride + c + r * ldh];
 }
 
 // Gp_b[s][r + q*P] = <R_b[slice s, r], U_b[slice s, q]>, one CTA per (row slice, design): R and U are read once
@@ -1037,14 +1039,24 @@ void run_eigensolver_block(plfem_ctx* ctx, const DevPattern& pat, DevPlan& D, co
     PLFEM_CUDA(cudaGraphLaunch(relaxed ? gexec_lo : gexec, st));
     ctx->launches += relaxed ? graph_nodes_lo : graph_nodes;
     res.n_op += P; res.n_block_op++;
+    // Two Gram-Schmidt passes.  In exact arithmetic the image of the last block is B-orthogonal to every basis vector except
+    // the last two blocks (three-term recurrence) — or, right after a thick restart (j0 == q), the kept Ritz vectors, which
+    // couple to the first new block.  The FIRST pass therefore projects against those columns only: it removes the O(1)
+    // components (the ones whose removal cancels digits); the SECOND pass runs over the whole basis and removes what
+    // rounding left anywhere, now without cancellation — the orthogonality of two full passes for the memory traffic of
+    // little more than one (the passes stream the whole basis: 8.4 + 6.4 % of a forest's kernel time for two of them).
+    static const bool local_first = [] { const char* e = std::getenv("PLFEM_CGS"); return !(e && e[0] == 'f'); }();    // PLFEM_CGS=full: two full passes
+    const int jA = (!local_first || j0 == q) ? 0 : std::max(0, j0 - P);
+    const int nA = nb - jA;
     const dim3 gdots((nb + DCOLS - 1) / DCOLS, RSPLIT, B), gsum((nb + 127) / 128, B);
-    dots_block_kernel<<<gdots, 256, 0, st>>>(BVc, ld, R.p, moff, nb, hp.p, ldh, hstride);          // CGS pass 1
-    sum_slices_kernel<<<gsum, 128, 0, st>>>(hp.p, ldh, hstride, nb, h1.p);
-    update_block_kernel<<<gpairs, 256, 0, st>>>(Vc, ld, h1.p, ldh, hstride, nb, moff, R.p);
+    const dim3 gdotsA((nA + DCOLS - 1) / DCOLS, RSPLIT, B), gsumA((nA + 127) / 128, B);
+    dots_block_kernel<<<gdotsA, 256, 0, st>>>(BVc + (int64_t)jA * ld, ld, R.p, moff, nA, hp.p + jA, ldh, hstride);   // CGS pass 1
+    sum_slices_kernel<<<gsumA, 128, 0, st>>>(hp.p + jA, ldh, hstride, nA, h1.p + jA);
+    update_block_kernel<<<gpairs, 256, 0, st>>>(Vc + (int64_t)jA * ld, ld, h1.p + jA, ldh, hstride, nA, moff, R.p);
     dots_block_kernel<<<gdots, 256, 0, st>>>(BVc, ld, R.p, moff, nb, hp.p, ldh, hstride);          // CGS pass 2
     sum_slices_kernel<<<gsum, 128, 0, st>>>(hp.p, ldh, hstride, nb, h2.p);
     update_block_kernel<<<gpairs, 256, 0, st>>>(Vc, ld, h2.p, ldh, hstride, nb, moff, R.p);
-    store_h_kernel<<<gsum, 128, 0, st>>>(h1.p, h2.p, ldh, hstride, nb, Hs.p + (size_t)j0 * ldh, ldh, sstride);
+    store_h_kernel<<<gsum, 128, 0, st>>>(h1.p, h2.p, ldh, hstride, nb, jA, Hs.p + (size_t)j0 * ldh, ldh, sstride);
     ctx->launches += 7;
     orthonormalize(Vc + (int64_t)nb * ld, BVc + (int64_t)nb * ld, j0 / P);
     nb += P;
