@@ -565,3 +565,29 @@ def test_dataflow_and_per_level_sweeps_are_bit_identical(tmp_path):
         subprocess.run([_sys.executable, "-c", code, f], env=env, check=True, timeout=300)
         outs.append(np.load(f))
     assert np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.gpu
+def test_local_first_orthogonalisation_matches_two_full_passes(tmp_path):
+    """The block Lanczos step projects first against the last two blocks only (the kept Ritz vectors right after a restart) and
+    then against the whole basis; `PLFEM_CGS=full` runs two full passes.  Same number of block steps, eigenvalues equal to
+    1e-11 relative, backward errors under the bar in both (the variable is read once per process: two subprocesses)."""
+    import json
+    import subprocess
+    import sys as _sys
+    code = ("import sys, json, numpy as np; sys.path.insert(0, %r); import plfem_b200 as P; "
+            "from plfem_b200.solver_fem import TrueVectorialMaxwellSolver as S; "
+            "g = P.MCFGeometry(7, 8.0, 1.5, 1.535, 1.0, 1.55); mesh, _ = P.MeshGenerator.generate(g, refinement=0.7); "
+            "m, raw = S(g).solve_vectorial_modes(mesh, 10, return_raw=True); np.save(sys.argv[1], raw['beta_sq']); "
+            "print(json.dumps({k: raw['stats'][k] for k in ('n_block_op', 'n_restart', 'max_residual')}))" % ROOT)
+    outs, stats = [], []
+    for mode in ("", "full"):
+        f = str(tmp_path / f"beta_cgs_{mode or 'local'}.npy")
+        env = dict(os.environ, PLFEM_CGS=mode)
+        r = subprocess.run([_sys.executable, "-c", code, f], env=env, check=True, timeout=300, capture_output=True, text=True)
+        stats.append(json.loads(r.stdout.strip().splitlines()[-1]))
+        outs.append(np.load(f))
+    assert stats[0]["n_restart"] >= 1, stats                      # the case exercises the step right after a thick restart
+    assert stats[0]["n_block_op"] == stats[1]["n_block_op"], stats
+    assert max(s["max_residual"] for s in stats) < 1e-9, stats
+    assert np.abs(outs[0] / outs[1] - 1).max() < 1e-11
