@@ -509,14 +509,20 @@ void dissect_vertex_graph(const DofTables& d, const std::vector<int32_t>& interi
   }
   // order separators along their cut, split them into chains of <= max_sn_nodes supernodes
   auto proj = [&](int dd, int32_t v) { switch (dd) { case 0: return x[v]; case 1: return y[v]; case 2: return x[v] + y[v]; default: return x[v] - y[v]; } };
-  // (keys gathered once per node and sorted as (key, node) pairs: the same order as comparing proj(odir, .) with ties by node id)
-  std::vector<std::pair<double, int32_t>> keyed;
-  auto sort_along = [&](std::vector<int32_t>& o, int odir) {
-    keyed.resize(o.size());
-    for (size_t i = 0; i < o.size(); ++i) keyed[i] = {proj(odir, o[i]), o[i]};
-    std::sort(keyed.begin(), keyed.end());
-    for (size_t i = 0; i < o.size(); ++i) o[i] = keyed[i].second;
-  };
+  // (keys gathered once per node and sorted as (key, node) pairs: the same order as comparing proj(odir, .) with ties by node
+  //  id; the tree nodes are independent — large trees (the 2M-unknown mesh: 60 k of them) sort on the call's host threads)
+  parallel_for(nt, 4096, [&](int64_t b, int64_t e) {
+    std::vector<std::pair<double, int32_t>> keyed;
+    for (int64_t t = b; t < e; ++t) {
+      const int odir = vf.nodes[t].od;
+      if (odir < 0) continue;
+      std::vector<int32_t>& o = own[t];
+      keyed.resize(o.size());
+      for (size_t i = 0; i < o.size(); ++i) keyed[i] = {proj(odir, o[i]), o[i]};
+      std::sort(keyed.begin(), keyed.end());
+      for (size_t i = 0; i < o.size(); ++i) o[i] = keyed[i].second;
+    }
+  });
   out = Forest(); out_roots.clear();
   out.nodes.reserve((size_t)nt + nt / 4 + 16);
   std::vector<int32_t> head(nt, -1);          // tree node of `out` heading (last chain link of) vertex-tree node t
@@ -528,30 +534,13 @@ void dissect_vertex_graph(const DofTables& d, const std::vector<int32_t>& interi
     std::reverse(order.begin(), order.end());
   }
   for (int32_t t : order) {
-    std::vector<int32_t>& o = own[t];
+    const std::vector<int32_t>& o = own[t];
     std::vector<int32_t> kids;
     for (int32_t c : vf.nodes[t].children) kids.push_back(head[c]);
     const int odir = vf.nodes[t].od;
-    if (odir < 0 || (int32_t)o.size() <= opt.max_sn_nodes) {
-      if (odir >= 0) sort_along(o, odir);
-      // a leaf larger than the supernode limit (many edge nodes) is split as well
-      const int32_t ns = (int32_t)o.size();
-      const int32_t nchunks = std::max(1, (ns + opt.max_sn_nodes - 1) / opt.max_sn_nodes);
-      int32_t prev = -1, pos = 0;
-      for (int32_t k = 0; k < nchunks; ++k) {
-        const int32_t len = ns / nchunks + (k < ns % nchunks ? 1 : 0);
-        TreeNode tn; tn.own.assign(o.begin() + pos, o.begin() + pos + len); tn.od = odir;
-        pos += len;
-        if (k == 0) tn.children = kids; else tn.children = {prev};
-        out.nodes.push_back(std::move(tn));
-        prev = (int32_t)out.nodes.size() - 1;
-      }
-      head[t] = prev;
-      continue;
-    }
-    sort_along(o, odir);
+    // chains of <= max_sn_nodes supernodes (a leaf larger than the limit — many edge nodes — is split as well)
     const int32_t ns = (int32_t)o.size();
-    const int32_t nchunks = (ns + opt.max_sn_nodes - 1) / opt.max_sn_nodes;
+    const int32_t nchunks = std::max(1, (ns + opt.max_sn_nodes - 1) / opt.max_sn_nodes);
     int32_t prev = -1, pos = 0;
     for (int32_t k = 0; k < nchunks; ++k) {
       const int32_t len = ns / nchunks + (k < ns % nchunks ? 1 : 0);
