@@ -43,33 +43,50 @@ void build_dof_tables(const double* p, const int64_t* t, int64_t V, int64_t T, D
     }
   }
   for (int64_t v = 0; v < V; ++v) cnt[v + 1] += cnt[v];
-  std::vector<int32_t> slot(3 * T);           // half-edge ids grouped by min vertex
+  // half-edges grouped by min vertex as (max vertex, half-edge id) in one 64-bit key; a bucket (~6 entries) is sorted by
+  // counting, for every key, the smaller ones (no data-dependent branch: comparison sorts of such buckets spend their
+  // time in mispredictions)
+  std::vector<int64_t> slot(3 * T);
   {
     std::vector<int32_t> fill(cnt.begin(), cnt.end() - 1);
-    for (int64_t h = 0; h < 3 * T; ++h) slot[fill[emin[h]]++] = (int32_t)h;
+    for (int64_t h = 0; h < 3 * T; ++h) slot[fill[emin[h]]++] = ((int64_t)emax[h] << 32) | (int64_t)h;
   }
   d.t2f.assign(3 * T, -1);
-  d.facets.clear(); d.facets.reserve(3 * T + 2 * V);
-  std::vector<int32_t> fcount; fcount.reserve(3 * T / 2 + V);
+  d.facets.resize(6 * T);                     // trimmed to 2 E below
+  std::vector<int32_t> fcount(3 * T + 1);
+  int32_t* fac = d.facets.data();
+  int32_t* fc = fcount.data();
+  int32_t* t2f = d.t2f.data();
+  int64_t nf = 0;
   for (int64_t v = 0; v < V; ++v) {
     int32_t b = cnt[v], e = cnt[v + 1];
-    std::sort(slot.begin() + b, slot.begin() + e,
-              [&](int32_t h1, int32_t h2) { return emax[h1] < emax[h2] || (emax[h1] == emax[h2] && h1 < h2); });
+    const int32_t m = e - b;
+    if (m > 32) std::sort(slot.begin() + b, slot.begin() + e);
+    else if (m > 1) {
+      int64_t key[32];
+      for (int32_t i = 0; i < m; ++i) key[i] = slot[b + i];
+      for (int32_t i = 0; i < m; ++i) {
+        int32_t r = 0;
+        for (int32_t j = 0; j < m; ++j) r += key[j] < key[i];
+        slot[b + r] = key[i];
+      }
+    }
     int32_t last = -1;
     for (int32_t i = b; i < e; ++i) {
-      int32_t h = slot[i];
-      if (emax[h] != last) {
-        last = emax[h];
-        d.facets.push_back((int32_t)v); d.facets.push_back(last);
-        fcount.push_back(0);
-      }
-      int32_t f = (int32_t)fcount.size() - 1;
-      fcount[f]++;
+      const int32_t h = (int32_t)(slot[i] & 0xffffffff), hmax = (int32_t)(slot[i] >> 32);
+      // a new facet starts where the max vertex changes (stores without a branch: a repeated facet rewrites its own entry)
+      const int32_t isnew = hmax != last;
+      last = hmax;
+      nf += isnew;
+      const int64_t f = nf - 1;
+      fac[2 * f] = (int32_t)v; fac[2 * f + 1] = hmax;
+      fc[f] = (isnew ? 0 : fc[f]) + 1;
       // slot h = 3*e + k  ->  element-major t2f
-      d.t2f[h] = f;
+      t2f[h] = (int32_t)f;
     }
   }
-  d.E = (int64_t)fcount.size();
+  d.facets.resize(2 * nf); fcount.resize(nf);
+  d.E = nf;
   d.N = V + d.E;
 
   d.edofs.resize(6 * T);
@@ -205,27 +222,45 @@ void build_pattern(const DofTables& d, const std::vector<int32_t>& new_of_old, i
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-// order[r] = index of the r-th smallest key; stable (ties keep ascending index). LSD radix on the
-// order-preserving integer image of the doubles.
+// order[r] = index of the r-th smallest key; stable (ties keep ascending index).  LSD radix (three 11-bit digits, the three
+// histograms from one read) on the upper 32 bits of the order-preserving integer image of the doubles, then one insertion
+// pass over the full keys: entries that agree in their upper 32 bits (relative distance < 2^-20: exact ties of a symmetric
+// mesh, hardly anything else) arrive in index order and leave sorted by (key, index) — the order a stable sort of the full
+// keys gives.
 void argsort_doubles(const std::vector<double>& key, std::vector<int32_t>& order) {
   const int32_t n = (int32_t)key.size();
-  std::vector<uint64_t> k(n), k2(n);
+  std::vector<uint64_t> k(n);
+  std::vector<uint32_t> hk(n), hk2(n);
   std::vector<int32_t> a(n), b(n);
+  constexpr int B = 11, R = 1 << B;
+  std::vector<int32_t> cnt(3 * (R + 1), 0);
+  int32_t* c0 = cnt.data(); int32_t* c1 = c0 + R + 1; int32_t* c2 = c1 + R + 1;
   for (int32_t i = 0; i < n; ++i) {
     uint64_t u; std::memcpy(&u, &key[i], 8);
-    k[i] = (u >> 63) ? ~u : (u | 0x8000000000000000ull);
-    a[i] = i;
+    u = (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+    k[i] = u;
+    const uint32_t h = (uint32_t)(u >> 32);
+    hk[i] = h; a[i] = i;
+    c0[(h & (R - 1)) + 1]++; c1[((h >> B) & (R - 1)) + 1]++; c2[(h >> (2 * B)) + 1]++;
   }
-  for (int pass = 0; pass < 8; ++pass) {
-    const int sh = 8 * pass;
-    int32_t cnt[257] = {0};
-    for (int32_t i = 0; i < n; ++i) cnt[((k[i] >> sh) & 0xff) + 1]++;
+  for (int pass = 0; pass < 3; ++pass) {
+    int32_t* c = cnt.data() + pass * (R + 1);
+    const int sh = B * pass;
+    const int nb = pass == 2 ? (1 << (32 - 2 * B)) : R;
     bool single = false;
-    for (int c = 1; c <= 256; ++c) if (cnt[c] == n) single = true;
+    for (int j = 1; j <= nb; ++j) if (c[j] == n) { single = true; break; }
     if (single) continue;
-    for (int c = 0; c < 256; ++c) cnt[c + 1] += cnt[c];
-    for (int32_t i = 0; i < n; ++i) { const int32_t d = cnt[(k[i] >> sh) & 0xff]++; k2[d] = k[i]; b[d] = a[i]; }
-    k.swap(k2); a.swap(b);
+    for (int j = 0; j < nb; ++j) c[j + 1] += c[j];
+    for (int32_t i = 0; i < n; ++i) { const int32_t d = c[(hk[i] >> sh) & (R - 1)]++; hk2[d] = hk[i]; b[d] = a[i]; }
+    hk.swap(hk2); a.swap(b);
+  }
+  for (int32_t i = 1; i < n; ++i) {
+    if (hk[i] != hk[i - 1]) continue;
+    const int32_t v = a[i];
+    const uint64_t kv = k[v];
+    int32_t j = i;
+    while (j > 0 && hk[j - 1] == hk[i] && (k[a[j - 1]] > kv || (k[a[j - 1]] == kv && a[j - 1] > v))) { a[j] = a[j - 1]; --j; }
+    a[j] = v;
   }
   order.swap(a);
 }
@@ -251,24 +286,27 @@ struct Dissector {
   const double* x;
   const double* y;
   const SymbolicOptions& opt;
-  std::vector<int32_t> side;   // per node: stamp of the subset/half it currently belongs to
+  // Per node: its position in each direction list (lists[d][pos4[v].r[d]] == v).  A subset under examination occupies the
+  // same range [off, off + n) of every list, so "w belongs to the subset" is a range test on w's position — the partition
+  // below moves the nodes AND writes their new positions, which keeps the positions current for every node that is still
+  // to be dissected (nodes of other subsets lie in other ranges; a separator gets INT32_MAX for good).
   struct alignas(16) Rk { int32_t r[4]; };
-  std::vector<Rk> rank4;       // per node: position in each direction list of the subset being examined
+  std::vector<Rk> pos4;
   struct alignas(16) Ext { int32_t hi[4], lo[4]; };
-  std::vector<Ext> ext;        // per node: extreme ranks among its neighbours inside the subset (and itself)
-  std::vector<uint8_t> insep;  // per node: chosen as separator in the current call
-  std::atomic<int32_t> stamp{0};
+  std::vector<Ext> ext;        // per node: extreme positions among its neighbours inside the subset (and itself)
   std::vector<int32_t> lists[ND];  // the node set of the current call, sorted along each direction
   bool split_chains = true;        // cut separators into chains of <= max_sn_nodes supernodes here (false: the caller does)
-  struct Scratch { std::vector<int32_t> tmp, dl[ND], dr[ND]; };
+  struct Scratch { std::vector<int32_t> tmp, nhi[ND], nlo[ND]; std::vector<double> fac; };
 
   Dissector(const Pattern& a, const double* x_, const double* y_, const SymbolicOptions& o)
-      : adj(a), x(x_), y(y_), opt(o), side(a.n, -1), rank4(a.n, Rk{{0, 0, 0, 0}}), ext(a.n), insep(a.n, 0) {
+      : adj(a), x(x_), y(y_), opt(o), pos4(a.n, Rk{{0, 0, 0, 0}}), ext(a.n) {
     const int32_t n = a.n;
     auto one = [&](int d) {
       std::vector<double> key(n);
       for (int32_t v = 0; v < n; ++v) key[v] = proj(d, v);
       argsort_doubles(key, lists[d]);
+      const int32_t* Ld = lists[d].data();
+      for (int32_t r = 0; r < n; ++r) pos4[Ld[r]].r[d] = r;
     };
     if (host_threads() >= ND && n > 4096) {
       std::vector<std::thread> th;
@@ -297,65 +335,72 @@ struct Dissector {
     }
     // Candidate cuts: ND directions x every split position in the middle 40%.  Along a direction a
     // node of rank r is in the left-boundary separator of split h iff r < h <= (highest neighbour
-    // rank), so the separator size for EVERY h comes from one difference array.  Pick the
+    // rank), so the separator sizes for EVERY h come from the histograms of the extreme neighbour ranks:
+    // left boundary of h = h - #{hi < h}, right boundary = #{lo < h} - h.  Pick the
     // (direction, h, side) with the smallest separator, mildly penalising imbalance.
-    const int32_t cur = ++stamp;
-    for (int32_t i = 0; i < n; ++i) side[L0[i]] = cur;
     const int ndir = (n >= opt.search_min_nodes) ? ND : 2;
     double best_cost = 1e300; int best_dir = 0; int32_t best_h = n / 2; bool best_left = true;
     const int32_t h0 = std::max<int32_t>(1, (int32_t)(0.3 * n)), h1 = std::min<int32_t>(n - 1, (int32_t)(0.7 * n));
     struct Cand { double cost = 1e300; int32_t h = 0; bool left = true; };
     Cand cand[ND];
     {
-      // ranks of every node along every direction, then ONE pass over the adjacency: the extreme neighbour ranks along
-      // all directions at once
-      for (int d = 0; d < ndir; ++d) {
-        const int32_t* Ld = lists[d].data() + off;
-        for (int32_t r = 0; r < n; ++r) rank4[Ld[r]].r[d] = r;
-        sc.dl[d].assign(n + 2, 0); sc.dr[d].assign(n + 2, 0);
-      }
+      for (int d = 0; d < ndir; ++d) { sc.nhi[d].assign(n, 0); sc.nlo[d].assign(n, 0); }
+      // ONE pass over the adjacency: the extreme neighbour positions along all directions at once.
       // (small subsets examine two directions only: most of the nodes sit in such subsets, and the pass over their
       // neighbours is the hot loop of the whole analysis)
-      // Branch-free over the neighbours: the four ranks of a node are one 128-bit lane set, a neighbour outside the subset
-      // contributes 0 to the maxima (ranks are >= 0 and a node's own rank takes part) and INT32_MAX to the minima.  The extreme
-      // ranks are kept per node (ext[v]): the separator of the chosen cut is read off them below without a second pass over
-      // the adjacency.
+      // Branch-free over the neighbours: the four positions of a node are one 128-bit lane set, a neighbour outside the subset
+      // contributes 0 to the maxima (positions are >= 0 and a node's own takes part) and INT32_MAX to the minima.  The range
+      // test runs per lane ((p - off) <u n as a signed compare of biased values): a node outside the subset is outside the
+      // range in EVERY list this subset looks at (lanes 2, 3 of a node stop being updated below its last four-direction
+      // ancestor and stay inside that ancestor's half — disjoint from any subset that still reads them).  The
+      // extremes are kept per node (ext[v]): the separator of the chosen cut is read off them below without a second pass
+      // over the adjacency.
       auto neighbour_pass = [&](auto nd_tag) {
         constexpr int NDIR = decltype(nd_tag)::value;
         const __m128i big = _mm_set1_epi32(INT32_MAX);
-        const int32_t* rp = adj.rowptr.data(); const int32_t* cl = adj.col.data(); const int32_t* sd = side.data();
+        const __m128i bias = _mm_set1_epi32((int32_t)(0x80000000u - (uint32_t)off)), nb = _mm_set1_epi32((int32_t)(0x80000000u + (uint32_t)n));
+        const int32_t* rp = adj.rowptr.data(); const int32_t* cl = adj.col.data();
+        const Rk* ps = pos4.data();
+        int32_t* nh[ND]; int32_t* nl_[ND];
+        for (int d = 0; d < NDIR; ++d) { nh[d] = sc.nhi[d].data() - off; nl_[d] = sc.nlo[d].data() - off; }
         for (int32_t i = 0; i < n; ++i) {
           const int32_t v = L0[i];
-          const __m128i rv = _mm_load_si128((const __m128i*)&rank4[v]);
+          const __m128i rv = _mm_load_si128((const __m128i*)&ps[v]);
           __m128i hi = rv, lo = rv;
           for (int32_t q = rp[v], qe = rp[v + 1]; q < qe; ++q) {
-            const int32_t w = cl[q];
-            const __m128i in = _mm_set1_epi32(-(int32_t)(sd[w] == cur));
-            const __m128i rw = _mm_load_si128((const __m128i*)&rank4[w]);
+            const __m128i rw = _mm_load_si128((const __m128i*)&ps[cl[q]]);
+            const __m128i in = _mm_cmpgt_epi32(nb, _mm_add_epi32(rw, bias));
             hi = _mm_max_epi32(hi, _mm_and_si128(rw, in));
-            lo = _mm_min_epi32(lo, _mm_or_si128(rw, _mm_andnot_si128(in, big)));
+            lo = _mm_min_epi32(lo, _mm_blendv_epi8(big, rw, in));
           }
-          alignas(16) int32_t h4[4], l4[4];
-          _mm_store_si128((__m128i*)h4, hi); _mm_store_si128((__m128i*)l4, lo);
           _mm_store_si128((__m128i*)&ext[v].hi, hi); _mm_store_si128((__m128i*)&ext[v].lo, lo);
-          const int32_t* r4 = rank4[v].r;
-          for (int d = 0; d < NDIR; ++d) {
-            sc.dl[d][r4[d] + 1]++; sc.dl[d][h4[d] + 1]--;   // left-boundary member for h in (r, hi]
-            sc.dr[d][l4[d] + 1]++; sc.dr[d][r4[d] + 1]--;   // right-boundary member for h in (lo, r]
-          }
+          const int32_t* h4 = ext[v].hi; const int32_t* l4 = ext[v].lo;
+          for (int d = 0; d < NDIR; ++d) { nh[d][h4[d]]++; nl_[d][l4[d]]++; }
         }
       };
       if (ndir == ND) neighbour_pass(std::integral_constant<int, ND>{}); else neighbour_pass(std::integral_constant<int, 2>{});
+      // the imbalance factor of a split position is the same along every direction: once per call (a loop of divisions the
+      // compiler vectorises; same IEEE operations as one by one)
+      sc.fac.resize(h1 - h0 + 1);
+      {
+        double* fac = sc.fac.data();
+        const double dn = n;
+        for (int32_t h = h0; h <= h1; ++h) fac[h - h0] = 1.0 + 1.5 * std::fabs(2.0 * h / dn - 1.0);
+      }
       for (int d = 0; d < ndir; ++d) {
-        const int32_t* dl = sc.dl[d].data(); const int32_t* dr = sc.dr[d].data();
-        int32_t cl = 0, cr = 0;
+        const int32_t* nh = sc.nhi[d].data(); const int32_t* nlo = sc.nlo[d].data();
+        const double* fac = sc.fac.data() - h0;
+        int32_t chi = 0, clo = 0;
+        for (int32_t h = 1; h < h0; ++h) { chi += nh[h - 1]; clo += nlo[h - 1]; }
         Cand c;
-        for (int32_t h = 1; h <= h1; ++h) {
-          cl += dl[h]; cr += dr[h];
-          if (h < h0) continue;
-          const double imb = std::fabs(2.0 * h / n - 1.0);
-          const double cost = (std::min(cl, cr) + 1.0) * (1.0 + 1.5 * imb);
-          if (cost < c.cost) { c.cost = cost; c.h = h; c.left = cl <= cr; }
+        int32_t lim = INT32_MAX;                          // a split can only win with min(cl, cr) + 1 < best cost so far
+        for (int32_t h = h0; h <= h1; ++h) {
+          chi += nh[h - 1]; clo += nlo[h - 1];
+          const int32_t cl = h - chi, cr = clo - h;       // members of the left / right boundary of split h
+          const int32_t m = std::min(cl, cr);
+          if (m >= lim) continue;                         // (the imbalance factor is >= 1, the product rounds monotonically)
+          const double cost = (m + 1.0) * fac[h];
+          if (cost < c.cost) { c.cost = cost; c.h = h; c.left = cl <= cr; lim = (int32_t)std::min(std::ceil(cost), 2.0e9) - 1; }
         }
         cand[d] = c;
       }
@@ -366,25 +411,31 @@ struct Dissector {
     const int32_t* Lb = lists[best_dir].data() + off;
     std::vector<int32_t> sep;
     if (best_left) {          // left half: members with a neighbour of rank >= h
-      for (int32_t i = 0; i < h; ++i) { const int32_t v = Lb[i]; if (ext[v].hi[best_dir] >= h) { sep.push_back(v); insep[v] = 1; } }
+      for (int32_t i = 0; i < h; ++i) { const int32_t v = Lb[i]; if (ext[v].hi[best_dir] >= off + h) sep.push_back(v); }
     } else {                  // right half: members with a neighbour of rank < h
-      for (int32_t i = h; i < n; ++i) { const int32_t v = Lb[i]; if (ext[v].lo[best_dir] < h) { sep.push_back(v); insep[v] = 1; } }
+      for (int32_t i = h; i < n; ++i) { const int32_t v = Lb[i]; if (ext[v].lo[best_dir] < off + h) sep.push_back(v); }
     }
-    // stable three-way partition of every direction list: [left | right | separator]
-    int32_t nl = 0, nr = 0;
+    // stable three-way partition of every direction list: [left | right | (separator: dropped)], the new positions written
+    // as the nodes move.  The side of a node is its position along the chosen direction, so that list goes last.
+    const int32_t nsep = (int32_t)sep.size();
+    const int32_t nl = best_left ? h - nsep : h, nr = n - nsep - nl;
+    for (int32_t v : sep) pos4[v] = Rk{{INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX}};
     sc.tmp.resize(n);
-    for (int d = 0; d < ndir; ++d) {           // a subset that examines two directions has only smaller subsets below it
+    for (int dd = 0; dd < ndir; ++dd) {         // a subset that examines two directions has only smaller subsets below it
+      const int d = dd == ndir - 1 ? best_dir : (dd < best_dir ? dd : dd + 1);
       int32_t* Ld = lists[d].data() + off;
+      int32_t* tmp = sc.tmp.data();
+      const int32_t cut = off + h;
       int32_t a = 0, b = 0;
       for (int32_t i = 0; i < n; ++i) {
         const int32_t v = Ld[i];
-        if (insep[v]) continue;
-        if (rank4[v].r[best_dir] < h) Ld[a++] = v; else sc.tmp[b++] = v;      // left of the cut along the chosen direction
+        int32_t* pv = pos4[v].r;
+        const int32_t pb = pv[best_dir];
+        if (pb == INT32_MAX) continue;
+        if (pb < cut) { Ld[a] = v; pv[d] = off + a; ++a; } else { tmp[b] = v; pv[d] = off + nl + b; ++b; }
       }
-      std::copy(sc.tmp.begin(), sc.tmp.begin() + b, Ld + a);
-      nl = a; nr = b;
+      std::copy(tmp, tmp + b, Ld + a);
     }
-    for (int32_t v : sep) { insep[v] = 0; side[v] = -1; }
     std::vector<int32_t> kids;
     if (par_budget > 1 && std::min(nl, nr) >= 1024) {
       // the two halves are independent: left half on a new thread with its own forest and scratch
@@ -404,11 +455,13 @@ struct Dissector {
       return;
     }
     // order the separator along the cut so that chain links are spatially compact
+    // (a caller that splits the chains itself sorts the lifted separators: nothing to order here)
     const int od = (best_dir == 0) ? 1 : (best_dir == 1 ? 0 : (best_dir == 2 ? 3 : 2));
-    std::sort(sep.begin(), sep.end(), [&](int32_t a, int32_t b) {
-      const double pa = proj(od, a), pb = proj(od, b);
-      return pa < pb || (pa == pb && a < b);
-    });
+    if (split_chains)
+      std::sort(sep.begin(), sep.end(), [&](int32_t a, int32_t b) {
+        const double pa = proj(od, a), pb = proj(od, b);
+        return pa < pb || (pa == pb && a < b);
+      });
     const int32_t ns = (int32_t)sep.size();
     const int32_t nchunks = split_chains ? (ns + opt.max_sn_nodes - 1) / opt.max_sn_nodes : 1;
     int32_t prev = -1, pos = 0;
@@ -644,11 +697,20 @@ void build_front_plan(const DofTables& dof, const Pattern* adj_p, const double* 
   std::vector<uint64_t> bm0(((size_t)n + 63) / 64 + 1, 0), bm1((bm0.size() + 63) / 64 + 1, 0);
   int32_t w1lo = INT32_MAX, w1hi = -1;
   auto bm_add = [&](int32_t c) {
-    const int32_t w = c >> 6;
-    if (!bm0[w]) { const int32_t w1 = w >> 6; bm1[w1] |= 1ull << (w & 63); w1lo = std::min(w1lo, w1); w1hi = std::max(w1hi, w1); }
+    const int32_t w = c >> 6, w1 = w >> 6;             // (both levels marked without asking: no data-dependent branch)
+    bm1[w1] |= 1ull << (w & 63); w1lo = std::min(w1lo, w1); w1hi = std::max(w1hi, w1);
     bm0[w] |= 1ull << (c & 63);
   };
+  // a whole word of the lower level at once (the children's sets arrive sorted: their entries are gathered per word in a
+  // register — back-to-back updates of one word in memory wait for each other's store)
+  auto bm_add_word = [&](int32_t w, uint64_t m) {
+    const int32_t w1 = w >> 6;
+    bm1[w1] |= 1ull << (w & 63); w1lo = std::min(w1lo, w1); w1hi = std::max(w1hi, w1);
+    bm0[w] |= m;
+  };
+  std::vector<int32_t> drained((size_t)n + 1);
   auto bm_drain = [&](std::vector<int32_t>& out) {
+    int32_t* o = drained.data();
     for (int32_t w1 = w1lo; w1 <= w1hi; ++w1) {
       uint64_t m1 = bm1[w1];
       bm1[w1] = 0;
@@ -657,9 +719,10 @@ void build_front_plan(const DofTables& dof, const Pattern* adj_p, const double* 
         m1 &= m1 - 1;
         uint64_t m0 = bm0[w];
         bm0[w] = 0;
-        while (m0) { out.push_back((w << 6) + __builtin_ctzll(m0)); m0 &= m0 - 1; }
+        while (m0) { *o++ = (w << 6) + __builtin_ctzll(m0); m0 &= m0 - 1; }
       }
     }
+    out.insert(out.end(), drained.data(), o);
     w1lo = INT32_MAX; w1hi = -1;
   };
   // Without the adjacency pattern: an element is a clique of its 6 nodes, and in a valid elimination forest they lie on one
@@ -707,10 +770,15 @@ void build_front_plan(const DofTables& dof, const Pattern* adj_p, const double* 
     }
     for (int32_t q = P.cptr[f]; q < P.cptr[f + 1]; ++q) {
       const int32_t ch = P.child[q];
-      for (int32_t k = P.sptr[ch]; k < P.sptr[ch + 1]; ++k) {
-        const int32_t c = P.strct[k];
-        if (c > last) bm_add(c);
-        else if (c < P.first[f]) throw std::runtime_error("front plan: child update set escapes its parent");
+      int32_t k = P.sptr[ch];
+      const int32_t ke = P.sptr[ch + 1];
+      if (k < ke && P.strct[k] < P.first[f]) throw std::runtime_error("front plan: child update set escapes its parent");
+      while (k < ke && P.strct[k] <= last) ++k;           // (sorted: the parent's own nodes come first)
+      while (k < ke) {
+        const int32_t w = P.strct[k] >> 6;
+        uint64_t m = 0;
+        do { m |= 1ull << (P.strct[k] & 63); ++k; } while (k < ke && (P.strct[k] >> 6) == w);
+        bm_add_word(w, m);
       }
       P.level[f] = std::max(P.level[f], P.level[ch] + 1);
     }
