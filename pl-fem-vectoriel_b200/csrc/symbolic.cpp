@@ -851,27 +851,41 @@ void merge_front_plans(const std::vector<const FrontPlan*>& parts, FrontPlan& M,
   }
   if (n_tot >= (int64_t(1) << 30) || ns_tot >= (int64_t(1) << 30)) throw std::runtime_error("batch too large for 32-bit plan indices");
   M.n = (int32_t)n_tot; M.nfronts = (int32_t)nf_tot;
-  M.perm.reserve(n_tot); M.sn_of.reserve(n_tot);
-  M.first.reserve(nf_tot); M.s.reserve(nf_tot); M.parent.reserve(nf_tot); M.level.reserve(nf_tot);
-  M.sptr.assign(1, 0); M.cptr.assign(1, 0); M.cmap_ptr.assign(1, 0); M.foff.assign(1, 0);
-  M.sptr.reserve(nf_tot + 1); M.cptr.reserve(nf_tot + 1); M.cmap_ptr.reserve(nf_tot + 1); M.foff.reserve(nf_tot + 1);
-  M.strct.reserve(ns_tot); M.cmap.reserve(nc_tot); M.child.reserve(nch_tot);
+  // every array sized once and filled through plain pointers (copies with an offset added: loops the compiler vectorises)
+  M.perm.resize(n_tot); M.sn_of.resize(n_tot);
+  M.first.resize(nf_tot); M.s.resize(nf_tot); M.parent.resize(nf_tot); M.level.resize(nf_tot);
+  M.sptr.resize(nf_tot + 1); M.cptr.resize(nf_tot + 1); M.cmap_ptr.resize(nf_tot + 1); M.foff.resize(nf_tot + 1);
+  M.sptr[0] = 0; M.cptr[0] = 0; M.cmap_ptr[0] = 0; M.foff[0] = 0;
+  M.strct.resize(ns_tot); M.cmap.resize(nc_tot); M.child.resize(nch_tot);
+  auto shifted = [](const int32_t* src, int64_t cnt, int32_t add, int32_t* dst) { for (int64_t i = 0; i < cnt; ++i) dst[i] = src[i] + add; };
+  int32_t so = 0, co = 0, mo = 0;
+  int64_t po = 0;
   for (int b = 0; b < nb; ++b) {
     const FrontPlan& P = *parts[b];
-    const int32_t no = node_off[b], fo = front_off[b];
-    const int32_t so = M.sptr.back(), co = M.cptr.back(), mo = M.cmap_ptr.back();
-    const int64_t po = M.foff.back();
-    M.perm.insert(M.perm.end(), P.perm.begin(), P.perm.end());
-    for (int32_t v : P.sn_of) M.sn_of.push_back(v + fo);
-    for (int32_t f = 0; f < P.nfronts; ++f) {
-      M.first.push_back(P.first[f] + no); M.s.push_back(P.s[f]);
-      M.parent.push_back(P.parent[f] >= 0 ? P.parent[f] + fo : -1); M.level.push_back(P.level[f]);
-      M.sptr.push_back(P.sptr[f + 1] + so); M.cptr.push_back(P.cptr[f + 1] + co);
-      M.cmap_ptr.push_back(P.cmap_ptr[f + 1] + mo); M.foff.push_back(P.foff[f + 1] + po);
+    const int32_t no = node_off[b], fo = front_off[b], nf = P.nfronts;
+    std::copy(P.perm.begin(), P.perm.end(), M.perm.begin() + no);
+    shifted(P.sn_of.data(), P.n, fo, M.sn_of.data() + no);
+    shifted(P.first.data(), nf, no, M.first.data() + fo);
+    std::copy(P.s.begin(), P.s.end(), M.s.begin() + fo);
+    std::copy(P.level.begin(), P.level.end(), M.level.begin() + fo);
+    {
+      const int32_t* pp = P.parent.data();
+      int32_t* mp = M.parent.data() + fo;
+      for (int32_t f = 0; f < nf; ++f) mp[f] = pp[f] >= 0 ? pp[f] + fo : -1;
     }
-    for (int32_t v : P.strct) M.strct.push_back(v + no);
-    for (int32_t v : P.child) M.child.push_back(v + fo);
-    M.cmap.insert(M.cmap.end(), P.cmap.begin(), P.cmap.end());
+    shifted(P.sptr.data() + 1, nf, so, M.sptr.data() + fo + 1);
+    shifted(P.cptr.data() + 1, nf, co, M.cptr.data() + fo + 1);
+    shifted(P.cmap_ptr.data() + 1, nf, mo, M.cmap_ptr.data() + fo + 1);
+    {
+      const int64_t* pf = P.foff.data() + 1;
+      int64_t* mf = M.foff.data() + fo + 1;
+      for (int32_t f = 0; f < nf; ++f) mf[f] = pf[f] + po;
+    }
+    shifted(P.strct.data(), (int64_t)P.strct.size(), no, M.strct.data() + so);
+    shifted(P.child.data(), (int64_t)P.child.size(), fo, M.child.data() + co);
+    std::copy(P.cmap.begin(), P.cmap.end(), M.cmap.begin() + mo);
+    so += (int32_t)P.strct.size(); co += (int32_t)P.child.size(); mo += (int32_t)P.cmap.size();
+    po += P.foff[nf];
   }
   M.lptr.assign(M.nlevels + 1, 0);
   for (int32_t f = 0; f < M.nfronts; ++f) M.lptr[M.level[f] + 1]++;
