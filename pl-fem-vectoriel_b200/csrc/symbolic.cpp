@@ -265,18 +265,33 @@ void argsort_doubles(const std::vector<double>& key, std::vector<int32_t>& order
   order.swap(a);
 }
 
-struct TreeNode {
-  std::vector<int32_t> own;       // interior indices, elimination order inside the node
-  std::vector<int32_t> children;  // tree node ids (within the same Forest)
-  int od = -1;                    // separators: projection direction along which `own` is ordered (-1: leaf)
-};
-
+// A forest of tree nodes in flat storage: the own list and the child list of a node are slices of two pools — the analysis
+// creates thousands of small nodes per design, and an allocation per list was a fifth of its time (more with a dozen analyses
+// side by side in one allocator).
 struct Forest {
-  std::vector<TreeNode> nodes;
-  void absorb(Forest&& o, std::vector<int32_t>& heads, const std::vector<int32_t>& oheads) {
-    const int32_t off = (int32_t)nodes.size();
-    for (auto& tn : o.nodes) { for (auto& c : tn.children) c += off; nodes.push_back(std::move(tn)); }
-    for (int32_t h : oheads) heads.push_back(h + off);
+  struct Node {
+    int32_t own_b, own_n;   // slice of `own`: interior indices, elimination order inside the node
+    int32_t ch_b, ch_n;     // slice of `child`: tree node ids (within the same Forest)
+    int od;                 // separators: projection direction along which the own list is ordered (-1: leaf)
+  };
+  std::vector<Node> nodes;
+  std::vector<int32_t> own, child;
+  // (o and c must not point into this forest's pools)
+  int32_t add(const int32_t* o, int32_t no, const int32_t* c, int32_t nc, int od) {
+    nodes.push_back(Node{(int32_t)own.size(), no, (int32_t)child.size(), nc, od});
+    own.insert(own.end(), o, o + no);
+    child.insert(child.end(), c, c + nc);
+    return (int32_t)nodes.size() - 1;
+  }
+  const int32_t* own_of(int32_t t) const { return own.data() + nodes[t].own_b; }
+  const int32_t* children_of(int32_t t) const { return child.data() + nodes[t].ch_b; }
+  // appends the nodes of `o`; returns the offset its node ids got
+  int32_t absorb(const Forest& o) {
+    const int32_t off = (int32_t)nodes.size(), oo = (int32_t)own.size(), co = (int32_t)child.size();
+    for (Node nd : o.nodes) { nd.own_b += oo; nd.ch_b += co; nodes.push_back(nd); }
+    own.insert(own.end(), o.own.begin(), o.own.end());
+    for (int32_t c : o.child) child.push_back(c + off);
+    return off;
   }
 };
 
@@ -296,7 +311,7 @@ struct Dissector {
   std::vector<Ext> ext;        // per node: extreme positions among its neighbours inside the subset (and itself)
   std::vector<int32_t> lists[ND];  // the node set of the current call, sorted along each direction
   bool split_chains = true;        // cut separators into chains of <= max_sn_nodes supernodes here (false: the caller does)
-  struct Scratch { std::vector<int32_t> tmp, nhi[ND], nlo[ND]; std::vector<double> fac; };
+  struct Scratch { std::vector<int32_t> tmp, nhi[ND], nlo[ND], sep; std::vector<double> fac; };   // sep: a stack over the recursion
 
   Dissector(const Pattern& a, const double* x_, const double* y_, const SymbolicOptions& o)
       : adj(a), x(x_), y(y_), opt(o), pos4(a.n, Rk{{0, 0, 0, 0}}), ext(a.n) {
@@ -323,14 +338,13 @@ struct Dissector {
   }
 
   // Dissect the node set stored (in ND different orders) at lists[d][off .. off+n).
-  // Appends tree nodes to `F` and the ids of the nodes heading the resulting sub-forest to `heads`.
+  // Appends tree nodes to `F` and the ids of the nodes heading the resulting sub-forest to `heads` (which doubles as the
+  // stack of the recursion: the heads the two halves append are the children of this call's separator).
   void dissect(int32_t off, int32_t n, Forest& F, std::vector<int32_t>& heads, Scratch& sc, int par_budget) {
     if (n == 0) return;
     int32_t* L0 = lists[0].data() + off;
     if (n <= opt.leaf_nodes) {
-      TreeNode leaf; leaf.own.assign(L0, L0 + n);
-      F.nodes.push_back(std::move(leaf));
-      heads.push_back((int32_t)F.nodes.size() - 1);
+      heads.push_back(F.add(L0, n, nullptr, 0, -1));
       return;
     }
     // Candidate cuts: ND directions x every split position in the middle 40%.  Along a direction a
@@ -409,17 +423,17 @@ struct Dissector {
       if (cand[d].cost < best_cost) { best_cost = cand[d].cost; best_dir = d; best_h = cand[d].h; best_left = cand[d].left; }
     const int32_t h = best_h;
     const int32_t* Lb = lists[best_dir].data() + off;
-    std::vector<int32_t> sep;
+    const size_t sep_mark = sc.sep.size();
     if (best_left) {          // left half: members with a neighbour of rank >= h
-      for (int32_t i = 0; i < h; ++i) { const int32_t v = Lb[i]; if (ext[v].hi[best_dir] >= off + h) sep.push_back(v); }
+      for (int32_t i = 0; i < h; ++i) { const int32_t v = Lb[i]; if (ext[v].hi[best_dir] >= off + h) sc.sep.push_back(v); }
     } else {                  // right half: members with a neighbour of rank < h
-      for (int32_t i = h; i < n; ++i) { const int32_t v = Lb[i]; if (ext[v].lo[best_dir] < off + h) sep.push_back(v); }
+      for (int32_t i = h; i < n; ++i) { const int32_t v = Lb[i]; if (ext[v].lo[best_dir] < off + h) sc.sep.push_back(v); }
     }
     // stable three-way partition of every direction list: [left | right | (separator: dropped)], the new positions written
     // as the nodes move.  The side of a node is its position along the chosen direction, so that list goes last.
-    const int32_t nsep = (int32_t)sep.size();
+    const int32_t nsep = (int32_t)(sc.sep.size() - sep_mark);
     const int32_t nl = best_left ? h - nsep : h, nr = n - nsep - nl;
-    for (int32_t v : sep) pos4[v] = Rk{{INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX}};
+    for (int32_t q = 0; q < nsep; ++q) pos4[sc.sep[sep_mark + q]] = Rk{{INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX}};
     sc.tmp.resize(n);
     for (int dd = 0; dd < ndir; ++dd) {         // a subset that examines two directions has only smaller subsets below it
       const int d = dd == ndir - 1 ? best_dir : (dd < best_dir ? dd : dd + 1);
@@ -436,44 +450,41 @@ struct Dissector {
       }
       std::copy(tmp, tmp + b, Ld + a);
     }
-    std::vector<int32_t> kids;
+    const size_t kid_mark = heads.size();
     if (par_budget > 1 && std::min(nl, nr) >= 1024) {
       // the two halves are independent: left half on a new thread with its own forest and scratch
       Forest FL; std::vector<int32_t> hl;
       std::thread th([&] { Scratch s2; dissect(off, nl, FL, hl, s2, par_budget / 2); });
-      dissect(off + nl, nr, F, kids, sc, par_budget - par_budget / 2);
+      dissect(off + nl, nr, F, heads, sc, par_budget - par_budget / 2);
       th.join();
-      std::vector<int32_t> right_kids; right_kids.swap(kids);
-      F.absorb(std::move(FL), kids, hl);
-      kids.insert(kids.end(), right_kids.begin(), right_kids.end());
+      const int32_t shift = F.absorb(FL);
+      for (int32_t& hd : hl) hd += shift;
+      heads.insert(heads.begin() + kid_mark, hl.begin(), hl.end());      // left heads first
     } else {
-      dissect(off, nl, F, kids, sc, 1);
-      dissect(off + nl, nr, F, kids, sc, 1);
+      dissect(off, nl, F, heads, sc, 1);
+      dissect(off + nl, nr, F, heads, sc, 1);
     }
-    if (sep.empty()) {  // disconnected halves: no front of its own, children go up
-      heads.insert(heads.end(), kids.begin(), kids.end());
-      return;
-    }
+    if (nsep == 0) return;  // disconnected halves: no front of its own, the children's heads go up
     // order the separator along the cut so that chain links are spatially compact
     // (a caller that splits the chains itself sorts the lifted separators: nothing to order here)
     const int od = (best_dir == 0) ? 1 : (best_dir == 1 ? 0 : (best_dir == 2 ? 3 : 2));
+    int32_t* sep = sc.sep.data() + sep_mark;
     if (split_chains)
-      std::sort(sep.begin(), sep.end(), [&](int32_t a, int32_t b) {
+      std::sort(sep, sep + nsep, [&](int32_t a, int32_t b) {
         const double pa = proj(od, a), pb = proj(od, b);
         return pa < pb || (pa == pb && a < b);
       });
-    const int32_t ns = (int32_t)sep.size();
+    const int32_t ns = nsep;
     const int32_t nchunks = split_chains ? (ns + opt.max_sn_nodes - 1) / opt.max_sn_nodes : 1;
     int32_t prev = -1, pos = 0;
     for (int32_t k = 0; k < nchunks; ++k) {
       const int32_t len = ns / nchunks + (k < ns % nchunks ? 1 : 0);
-      TreeNode tn; tn.own.assign(sep.begin() + pos, sep.begin() + pos + len);
-      tn.od = od;
+      prev = k == 0 ? F.add(sep + pos, len, heads.data() + kid_mark, (int32_t)(heads.size() - kid_mark), od)
+                    : F.add(sep + pos, len, &prev, 1, od);
       pos += len;
-      if (k == 0) tn.children = kids; else tn.children = {prev};
-      F.nodes.push_back(std::move(tn));
-      prev = (int32_t)F.nodes.size() - 1;
     }
+    sc.sep.resize(sep_mark);
+    heads.resize(kid_mark);
     heads.push_back(prev);
   }
 };
@@ -543,22 +554,29 @@ void dissect_vertex_graph(const DofTables& d, const std::vector<int32_t>& interi
     std::vector<int32_t> st(vroots.begin(), vroots.end());
     while (!st.empty()) {
       const int32_t t = st.back(); st.pop_back();
-      for (int32_t c : vf.nodes[t].children) { depth[c] = depth[t] + 1; st.push_back(c); }
+      const int32_t* ch = vf.children_of(t);
+      for (int32_t q = 0; q < vf.nodes[t].ch_n; ++q) { depth[ch[q]] = depth[t] + 1; st.push_back(ch[q]); }
     }
-    for (int32_t t = 0; t < nt; ++t) for (int32_t a : vf.nodes[t].own) tn_of[a] = t;
+    for (int32_t t = 0; t < nt; ++t) { const int32_t* o = vf.own_of(t); for (int32_t q = 0; q < vf.nodes[t].own_n; ++q) tn_of[o[q]] = t; }
   }
-  // lift: own lists in interior P2 indices
-  std::vector<std::vector<int32_t>> own(nt);
-  std::vector<int32_t> orphans;
-  for (int32_t t = 0; t < nt; ++t) { own[t].reserve(vf.nodes[t].own.size() * 4); for (int32_t a : vf.nodes[t].own) own[t].push_back(int_of[vdof[a]]); }
+  // lift: own lists in interior P2 indices (one pool, a slice per tree node: its vertices, then its edge nodes by facet id)
+  std::vector<int32_t> lptr(nt + 1, 0), lown, orphans, tn_of_facet(d.E, -1);
+  for (int32_t t = 0; t < nt; ++t) lptr[t + 1] = vf.nodes[t].own_n;
   for (int64_t f = 0; f < d.E; ++f) {
-    const int32_t i = int_of[V + f];
-    if (i < 0) continue;
+    if (int_of[V + f] < 0) continue;
     const int32_t a = vid[d.facets[2 * f]], b = vid[d.facets[2 * f + 1]];
     const int32_t ta = a >= 0 ? tn_of[a] : -1, tb = b >= 0 ? tn_of[b] : -1;
     int32_t t = ta;
     if (ta < 0 || (tb >= 0 && depth[tb] > depth[ta])) t = tb;
-    if (t < 0) orphans.push_back(i); else own[t].push_back(i);
+    if (t < 0) { orphans.push_back(int_of[V + f]); continue; }
+    tn_of_facet[f] = t; lptr[t + 1]++;
+  }
+  for (int32_t t = 0; t < nt; ++t) lptr[t + 1] += lptr[t];
+  lown.resize(lptr[nt]);
+  {
+    std::vector<int32_t> fill(lptr.begin(), lptr.end() - 1);
+    for (int32_t t = 0; t < nt; ++t) { const int32_t* o = vf.own_of(t); for (int32_t q = 0; q < vf.nodes[t].own_n; ++q) lown[fill[t]++] = int_of[vdof[o[q]]]; }
+    for (int64_t f = 0; f < d.E; ++f) if (tn_of_facet[f] >= 0) lown[fill[tn_of_facet[f]]++] = int_of[V + f];
   }
   // order separators along their cut, split them into chains of <= max_sn_nodes supernodes
   auto proj = [&](int dd, int32_t v) { switch (dd) { case 0: return x[v]; case 1: return y[v]; case 2: return x[v] + y[v]; default: return x[v] - y[v]; } };
@@ -569,55 +587,57 @@ void dissect_vertex_graph(const DofTables& d, const std::vector<int32_t>& interi
     for (int64_t t = b; t < e; ++t) {
       const int odir = vf.nodes[t].od;
       if (odir < 0) continue;
-      std::vector<int32_t>& o = own[t];
-      keyed.resize(o.size());
-      for (size_t i = 0; i < o.size(); ++i) keyed[i] = {proj(odir, o[i]), o[i]};
+      int32_t* o = lown.data() + lptr[t];
+      const int32_t no = lptr[t + 1] - lptr[t];
+      keyed.resize(no);
+      for (int32_t i = 0; i < no; ++i) keyed[i] = {proj(odir, o[i]), o[i]};
       std::sort(keyed.begin(), keyed.end());
-      for (size_t i = 0; i < o.size(); ++i) o[i] = keyed[i].second;
+      for (int32_t i = 0; i < no; ++i) o[i] = keyed[i].second;
     }
   });
   out = Forest(); out_roots.clear();
-  out.nodes.reserve((size_t)nt + nt / 4 + 16);
+  out.nodes.reserve((size_t)nt + nt / 4 + 16); out.own.reserve((size_t)n); out.child.reserve((size_t)nt + nt / 4 + 16);
   std::vector<int32_t> head(nt, -1);          // tree node of `out` heading (last chain link of) vertex-tree node t
   // children before parents: process in reverse DFS order
   std::vector<int32_t> order; order.reserve(nt);
   {
     std::vector<int32_t> st(vroots.begin(), vroots.end());
-    while (!st.empty()) { const int32_t t = st.back(); st.pop_back(); order.push_back(t); for (int32_t c : vf.nodes[t].children) st.push_back(c); }
+    while (!st.empty()) {
+      const int32_t t = st.back(); st.pop_back(); order.push_back(t);
+      const int32_t* ch = vf.children_of(t);
+      for (int32_t q = 0; q < vf.nodes[t].ch_n; ++q) st.push_back(ch[q]);
+    }
     std::reverse(order.begin(), order.end());
   }
+  std::vector<int32_t> kids;
   for (int32_t t : order) {
-    const std::vector<int32_t>& o = own[t];
-    std::vector<int32_t> kids;
-    for (int32_t c : vf.nodes[t].children) kids.push_back(head[c]);
+    const int32_t* o = lown.data() + lptr[t];
+    kids.clear();
+    { const int32_t* ch = vf.children_of(t); for (int32_t q = 0; q < vf.nodes[t].ch_n; ++q) kids.push_back(head[ch[q]]); }
     const int odir = vf.nodes[t].od;
     // chains of <= max_sn_nodes supernodes (a leaf larger than the limit — many edge nodes — is split as well)
-    const int32_t ns = (int32_t)o.size();
+    const int32_t ns = lptr[t + 1] - lptr[t];
     const int32_t nchunks = std::max(1, (ns + opt.max_sn_nodes - 1) / opt.max_sn_nodes);
     int32_t prev = -1, pos = 0;
     for (int32_t k = 0; k < nchunks; ++k) {
       const int32_t len = ns / nchunks + (k < ns % nchunks ? 1 : 0);
-      TreeNode tn; tn.own.assign(o.begin() + pos, o.begin() + pos + len); tn.od = odir;
+      prev = k == 0 ? out.add(o + pos, len, kids.data(), (int32_t)kids.size(), odir) : out.add(o + pos, len, &prev, 1, odir);
       pos += len;
-      if (k == 0) tn.children = kids; else tn.children = {prev};
-      out.nodes.push_back(std::move(tn));
-      prev = (int32_t)out.nodes.size() - 1;
     }
     head[t] = prev;
   }
   for (int32_t r : vroots) out_roots.push_back(head[r]);
   if (timing) fprintf(stderr, "[plfem] vertex dissection: graph %.2f ms, presort %.2f ms, dissect %.2f ms, lift %.2f ms (nv=%d)\n", t1 - t0, t1b - t1, t2 - t1b, clk() - t2, nv);
   if (!orphans.empty()) {
-    TreeNode tn; tn.own = orphans; tn.children = out_roots;
-    // keep the supernode limit: chain if needed
-    while ((int32_t)tn.own.size() > opt.max_sn_nodes) {
-      TreeNode part; part.own.assign(tn.own.end() - opt.max_sn_nodes, tn.own.end()); tn.own.resize(tn.own.size() - opt.max_sn_nodes);
-      part.children = tn.children;
-      out.nodes.push_back(std::move(part));
-      tn.children = {(int32_t)out.nodes.size() - 1};
+    // one more node above all roots; keep the supernode limit: chain if needed (the last max_sn_nodes orphans first)
+    std::vector<int32_t> ch(out_roots);
+    int32_t left = (int32_t)orphans.size();
+    while (left > opt.max_sn_nodes) {
+      const int32_t id = out.add(orphans.data() + left - opt.max_sn_nodes, opt.max_sn_nodes, ch.data(), (int32_t)ch.size(), -1);
+      left -= opt.max_sn_nodes;
+      ch.assign(1, id);
     }
-    out.nodes.push_back(std::move(tn));
-    out_roots.assign(1, (int32_t)out.nodes.size() - 1);
+    out_roots.assign(1, out.add(orphans.data(), left, ch.data(), (int32_t)ch.size(), -1));
   }
 }
 
@@ -659,7 +679,7 @@ void build_front_plan(const DofTables& dof, const Pattern* adj_p, const double* 
       st.emplace_back(r, 0);
       while (!st.empty()) {
         auto& [v, k] = st.back();
-        if (k < forest.nodes[v].children.size()) { int32_t ch = forest.nodes[v].children[k++]; st.emplace_back(ch, 0); }
+        if (k < (size_t)forest.nodes[v].ch_n) { int32_t ch = forest.children_of(v)[k++]; st.emplace_back(ch, 0); }
         else { front_of[v] = (int32_t)order.size(); order.push_back(v); st.pop_back(); }
       }
     }
@@ -671,10 +691,12 @@ void build_front_plan(const DofTables& dof, const Pattern* adj_p, const double* 
   std::vector<int32_t> new_of(n, -1);
   int32_t next = 0;
   for (int32_t f = 0; f < nf; ++f) {
-    const TreeNode& tn = forest.nodes[order[f]];
-    P.first[f] = next; P.s[f] = (int32_t)tn.own.size();
-    for (int32_t v : tn.own) { P.perm[next] = v; new_of[v] = next; P.sn_of[next] = f; ++next; }
-    for (int32_t ch : tn.children) P.parent[front_of[ch]] = f;
+    const Forest::Node& tn = forest.nodes[order[f]];
+    const int32_t* own = forest.own_of(order[f]);
+    const int32_t* kids = forest.children_of(order[f]);
+    P.first[f] = next; P.s[f] = tn.own_n;
+    for (int32_t q = 0; q < tn.own_n; ++q) { const int32_t v = own[q]; P.perm[next] = v; new_of[v] = next; P.sn_of[next] = f; ++next; }
+    for (int32_t q = 0; q < tn.ch_n; ++q) P.parent[front_of[kids[q]]] = f;
   }
   if (next != n) throw std::runtime_error("nested dissection lost nodes");
   P.cptr.assign(nf + 1, 0);
