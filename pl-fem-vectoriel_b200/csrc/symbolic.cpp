@@ -10,7 +10,7 @@
 #include <cstring>
 #include <thread>
 #include <type_traits>
-#include <smmintrin.h>
+#include <immintrin.h>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -311,7 +311,7 @@ struct Dissector {
   std::vector<Ext> ext;        // per node: extreme positions among its neighbours inside the subset (and itself)
   std::vector<int32_t> lists[ND];  // the node set of the current call, sorted along each direction
   bool split_chains = true;        // cut separators into chains of <= max_sn_nodes supernodes here (false: the caller does)
-  struct Scratch { std::vector<int32_t> tmp, nhi[ND], nlo[ND], sep; std::vector<double> fac; };   // sep: a stack over the recursion
+  struct Scratch { std::vector<int32_t> tmp, hist, sep, mm; std::vector<double> fac, cost; };   // sep: a stack over the recursion
 
   Dissector(const Pattern& a, const double* x_, const double* y_, const SymbolicOptions& o)
       : adj(a), x(x_), y(y_), opt(o), pos4(a.n, Rk{{0, 0, 0, 0}}), ext(a.n) {
@@ -358,7 +358,7 @@ struct Dissector {
     struct Cand { double cost = 1e300; int32_t h = 0; bool left = true; };
     Cand cand[ND];
     {
-      for (int d = 0; d < ndir; ++d) { sc.nhi[d].assign(n, 0); sc.nlo[d].assign(n, 0); }
+      sc.hist.assign((size_t)2 * ndir * n, 0);      // per direction: n counters of the highest, n of the lowest neighbour positions
       // ONE pass over the adjacency: the extreme neighbour positions along all directions at once.
       // (small subsets examine two directions only: most of the nodes sit in such subsets, and the pass over their
       // neighbours is the hot loop of the whole analysis)
@@ -376,7 +376,7 @@ struct Dissector {
         const int32_t* rp = adj.rowptr.data(); const int32_t* cl = adj.col.data();
         const Rk* ps = pos4.data();
         int32_t* nh[ND]; int32_t* nl_[ND];
-        for (int d = 0; d < NDIR; ++d) { nh[d] = sc.nhi[d].data() - off; nl_[d] = sc.nlo[d].data() - off; }
+        for (int d = 0; d < NDIR; ++d) { nh[d] = sc.hist.data() + (size_t)(2 * d) * n - off; nl_[d] = sc.hist.data() + (size_t)(2 * d + 1) * n - off; }
         for (int32_t i = 0; i < n; ++i) {
           const int32_t v = L0[i];
           const __m128i rv = _mm_load_si128((const __m128i*)&ps[v]);
@@ -401,21 +401,39 @@ struct Dissector {
         const double dn = n;
         for (int32_t h = h0; h <= h1; ++h) fac[h - h0] = 1.0 + 1.5 * std::fabs(2.0 * h / dn - 1.0);
       }
+      // Per direction: the boundary sizes of every split position (two running sums), their costs four at a time, then the
+      // FIRST position attaining the smallest cost — what comparing them one by one with "<" selects, without a
+      // data-dependent branch per position (the sizes hover around their minimum: such a branch mispredicts all along).
+      const int32_t nh_ = h1 - h0 + 1;
+      sc.mm.resize(nh_ + 4); sc.cost.resize(nh_ + 4);
       for (int d = 0; d < ndir; ++d) {
-        const int32_t* nh = sc.nhi[d].data(); const int32_t* nlo = sc.nlo[d].data();
-        const double* fac = sc.fac.data() - h0;
+        const int32_t* nh = sc.hist.data() + (size_t)(2 * d) * n; const int32_t* nlo = nh + n;
+        const double* fac = sc.fac.data();
+        int32_t* mm = sc.mm.data();            // min(cl, cr) + 1, sign bit of the word below = "left boundary is the smaller one"
+        double* cost = sc.cost.data();
         int32_t chi = 0, clo = 0;
         for (int32_t h = 1; h < h0; ++h) { chi += nh[h - 1]; clo += nlo[h - 1]; }
-        Cand c;
-        int32_t lim = INT32_MAX;                          // a split can only win with min(cl, cr) + 1 < best cost so far
         for (int32_t h = h0; h <= h1; ++h) {
           chi += nh[h - 1]; clo += nlo[h - 1];
           const int32_t cl = h - chi, cr = clo - h;       // members of the left / right boundary of split h
-          const int32_t m = std::min(cl, cr);
-          if (m >= lim) continue;                         // (the imbalance factor is >= 1, the product rounds monotonically)
-          const double cost = (m + 1.0) * fac[h];
-          if (cost < c.cost) { c.cost = cost; c.h = h; c.left = cl <= cr; lim = (int32_t)std::min(std::ceil(cost), 2.0e9) - 1; }
+          mm[h - h0] = cl <= cr ? cl + 1 : -(cr + 1);     // (both >= 0: the sign carries the side)
         }
+        __m256d vmin = _mm256_set1_pd(1e300);
+        int32_t i = 0;
+        for (; i + 4 <= nh_; i += 4) {
+          const __m128i m4 = _mm_abs_epi32(_mm_loadu_si128((const __m128i*)(mm + i)));
+          const __m256d c4 = _mm256_mul_pd(_mm256_cvtepi32_pd(m4), _mm256_loadu_pd(fac + i));
+          _mm256_storeu_pd(cost + i, c4);
+          vmin = _mm256_min_pd(vmin, c4);
+        }
+        alignas(32) double lane[4];
+        _mm256_store_pd(lane, vmin);
+        double best = std::min(std::min(lane[0], lane[1]), std::min(lane[2], lane[3]));
+        for (; i < nh_; ++i) { cost[i] = (double)std::abs(mm[i]) * fac[i]; best = std::min(best, cost[i]); }
+        int32_t at = 0;
+        while (at < nh_ - 1 && cost[at] != best) ++at;
+        Cand c;
+        c.cost = best; c.h = h0 + at; c.left = mm[at] > 0;
         cand[d] = c;
       }
     }
