@@ -470,7 +470,9 @@ struct Dissector {
     }
     const size_t kid_mark = heads.size();
     if (par_budget > 1 && std::min(nl, nr) >= 1024) {
-      // the two halves are independent: left half on a new thread with its own forest and scratch
+      // the two halves are independent: left half on a new thread with its own forest and scratch.  (Each side reads the
+      // positions of neighbours that belong to the other side while that side rewrites them: whatever it reads lies in the
+      // other half's range of the lists or is the separator mark — "not a member" either way.)
       Forest FL; std::vector<int32_t> hl;
       std::thread th([&] { Scratch s2; dissect(off, nl, FL, hl, s2, par_budget / 2); });
       dissect(off + nl, nr, F, heads, sc, par_budget - par_budget / 2);
