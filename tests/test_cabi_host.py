@@ -265,6 +265,36 @@ def test_front_plan_is_the_frozen_one(cfg1, small_case):
     assert digest(small_case[1], (0, 0)) == gold["small_default"]
 
 
+def test_host_analysis_digests_of_the_micro_benchmark(cfg1, small_case, tmp_path):
+    """The stand-alone harness of the host analysis (scripts/micro/host_analysis.cpp: DOF tables, front plan and the MERGE of a
+    forest's plans, which no C-ABI entry exposes without a GPU) must reproduce the digests taken before the host code was
+    reworked for speed: the merged plan of a forest is what the device factorises."""
+    import json
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no host compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "host_analysis"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-mavx2", "-ffp-contract=off", "-I" + os.path.join(root, "pl-fem-vectoriel_b200", "csrc"),
+                    os.path.join(root, "scripts", "micro", "host_analysis.cpp"),
+                    os.path.join(root, "pl-fem-vectoriel_b200", "csrc", "symbolic.cpp"), "-o", str(exe), "-lpthread"], check=True,
+                   capture_output=True)
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "front_plan.json")))
+    for name, mesh in (("small", small_case[1]), ("cfg1", cfg1[1])):
+        f = tmp_path / (name + ".mesh")
+        p_ = np.ascontiguousarray(mesh.p, dtype=np.float64)
+        t_ = np.ascontiguousarray(mesh.t, dtype=np.int64)
+        with open(f, "wb") as fh:
+            np.array([p_.shape[1], t_.shape[1]], dtype=np.int64).tofile(fh)
+            p_.tofile(fh)
+            t_.tofile(fh)
+        for threads in ("1", "4"):
+            out = subprocess.run([str(exe), str(f), "2", threads], check=True, capture_output=True, text=True).stdout
+            got = dict(re.findall(r"(dof|plan|merge) ([0-9a-f]{16})", out))
+            assert got == gold["host_analysis_" + name], (name, threads, out)
+
+
 def test_solve_iter_keeps_job_order_and_bounds_the_forests_in_flight():
     """`ForestPool.solve_iter` (host logic only: the forest solve is replaced): results come back in job order while at most
     workers + max(4, workers / 2) forests are submitted and not yet consumed, however slowly the first one finishes."""
