@@ -53,7 +53,9 @@ inline cudaError_t stream_wait(cudaStream_t st) {
     if (e != cudaErrorNotReady) return e;
     const auto waited = std::chrono::duration_cast<std::chrono::nanoseconds>(clk::now() - t0).count();
     if (waited < 40000) continue;
-    timespec ts{0, (long)std::min<int64_t>(100000, std::max<int64_t>(30000, waited / 16))};   // naps grow with the wait, <= 0.1 ms
+    // naps grow with the wait (1/16 of it: the overshoot stays near 3 %), <= 0.4 ms.  A nap costs ~5 us of CPU (timer, two
+    // context switches, the query): a dozen pool threads waiting on their forests at 0.1 ms naps were half a core
+    timespec ts{0, (long)std::min<int64_t>(400000, std::max<int64_t>(30000, waited / 16))};
     nanosleep(&ts, nullptr);
   }
 }
