@@ -53,9 +53,12 @@ inline cudaError_t stream_wait(cudaStream_t st) {
     if (e != cudaErrorNotReady) return e;
     const auto waited = std::chrono::duration_cast<std::chrono::nanoseconds>(clk::now() - t0).count();
     if (waited < 40000) continue;
-    // naps grow with the wait (1/16 of it: the overshoot stays near 3 %), <= 0.4 ms.  A nap costs ~5 us of CPU (timer, two
-    // context switches, the query): a dozen pool threads waiting on their forests at 0.1 ms naps were half a core
-    timespec ts{0, (long)std::min<int64_t>(400000, std::max<int64_t>(30000, waited / 16))};
+    // naps grow with the wait: 1/16 of it up to 0.1 ms (a solve alone: its waits last a few milliseconds); a wait that has
+    // lasted 8 ms is a pool thread waiting for its forest behind the others' — 1/32 of the wait up to 0.4 ms.  A nap costs ~5 us
+    // of CPU (timer, two context switches, the query): a dozen pool threads at 0.1 ms naps were half a core of a rank's four.
+    const int64_t nap = waited < 8000000 ? std::min<int64_t>(100000, std::max<int64_t>(30000, waited / 16))
+                                         : std::min<int64_t>(400000, waited / 32);
+    timespec ts{0, (long)nap};
     nanosleep(&ts, nullptr);
   }
 }
