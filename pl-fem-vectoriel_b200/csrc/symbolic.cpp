@@ -222,13 +222,43 @@ void build_pattern(const DofTables& d, const std::vector<int32_t>& new_of_old, i
 // ------------------------------------------------------------------------------------------------
 namespace {
 
+// The same order by six 11-bit passes over the whole 64-bit keys (all histograms from one read, uniform digits skipped): for
+// large inputs, see below.
+void argsort_doubles_wide(const std::vector<double>& key, std::vector<int32_t>& order) {
+  const int32_t n = (int32_t)key.size();
+  constexpr int B = 11, R = 1 << B, NP = 6;                 // 6 x 11 = 66 bits >= 64
+  std::vector<uint64_t> k(n), k2(n);
+  std::vector<int32_t> a(n), b(n);
+  std::vector<int32_t> cnt((size_t)NP * (R + 1), 0);
+  for (int32_t i = 0; i < n; ++i) {
+    uint64_t u; std::memcpy(&u, &key[i], 8);
+    u = (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+    k[i] = u; a[i] = i;
+    for (int pass = 0; pass < NP; ++pass) cnt[(size_t)pass * (R + 1) + ((u >> (B * pass)) & (R - 1)) + 1]++;
+  }
+  for (int pass = 0; pass < NP; ++pass) {
+    int32_t* c = cnt.data() + (size_t)pass * (R + 1);
+    const int sh = B * pass;
+    bool single = false;
+    for (int j = 1; j <= R; ++j) if (c[j] == n) { single = true; break; }
+    if (single) continue;
+    for (int j = 0; j < R; ++j) c[j + 1] += c[j];
+    for (int32_t i = 0; i < n; ++i) { const int32_t d = c[(k[i] >> sh) & (R - 1)]++; k2[d] = k[i]; b[d] = a[i]; }
+    k.swap(k2); a.swap(b);
+  }
+  order.swap(a);
+}
+
 // order[r] = index of the r-th smallest key; stable (ties keep ascending index).  LSD radix (three 11-bit digits, the three
 // histograms from one read) on the upper 32 bits of the order-preserving integer image of the doubles, then one insertion
 // pass over the full keys: entries that agree in their upper 32 bits (relative distance < 2^-20: exact ties of a symmetric
 // mesh, hardly anything else) arrive in index order and leave sorted by (key, index) — the order a stable sort of the full
 // keys gives.
+// Large inputs take the plain 64-bit passes: on a structured grid nearly every entry sits in a run of equal upper halves, and the
+// insertion pass then reads the full keys through the index — two cache misses per entry once they have outgrown the cache.
 void argsort_doubles(const std::vector<double>& key, std::vector<int32_t>& order) {
   const int32_t n = (int32_t)key.size();
+  if (n > 100000) { argsort_doubles_wide(key, order); return; }
   std::vector<uint64_t> k(n);
   std::vector<uint32_t> hk(n), hk2(n);
   std::vector<int32_t> a(n), b(n);
