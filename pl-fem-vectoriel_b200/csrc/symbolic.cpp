@@ -350,8 +350,6 @@ struct Dissector {
       std::vector<double> key(n);
       for (int32_t v = 0; v < n; ++v) key[v] = proj(d, v);
       argsort_doubles(key, lists[d]);
-      const int32_t* Ld = lists[d].data();
-      for (int32_t r = 0; r < n; ++r) pos4[Ld[r]].r[d] = r;
     };
     if (host_threads() >= ND && n > 4096) {
       std::vector<std::thread> th;
@@ -360,6 +358,11 @@ struct Dissector {
       for (auto& t : th) t.join();
     } else {
       for (int d = 0; d < ND; ++d) one(d);
+    }
+    // (on one thread: the four positions of a node share a cache line — threads filling a lane each would fight over it)
+    for (int d = 0; d < ND; ++d) {
+      const int32_t* Ld = lists[d].data();
+      for (int32_t r = 0; r < n; ++r) pos4[Ld[r]].r[d] = r;
     }
   }
 
