@@ -139,3 +139,15 @@ def test_mesh_cache_round_trip(tmp_path):
     assert P.MeshGenerator.get_cache_stats()["hits"] == before["hits"] + 1
     assert np.array_equal(m1.p, m2.p) and np.array_equal(m1.t, m2.t)
     P.MeshGenerator.clear_cache()
+
+
+def test_recipe_meshes_stay_below_the_device_valence_cap():
+    """The device pattern builder serves nodes that belong to at most 128 elements (README.md, known limits).  The recipe's
+    hub is a core centre: it meets one triangle per direction of the polar rings, 16 * refinement of them (`mesh.py:232-297`) —
+    34 elements at refinement 1, 40 at 2; the cap is reached beyond refinement 8 (105 there, a 300 k-vertex mesh)."""
+    import plfem_b200 as P
+    g = P.MCFGeometry(7, 8.0, 1.5, 1.535, 1.0, 1.55)
+    for ref, bound in ((1.0, 48), (2.0, 64)):
+        mesh, _ = P.MeshGenerator.generate(g, refinement=ref)
+        valence = np.bincount(np.asarray(mesh.t).ravel(), minlength=mesh.p.shape[1])
+        assert valence.max() <= bound < 128
