@@ -3,12 +3,12 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg1|cfg2]
 
-A *step* is ``--workers`` (default 6) FORESTS of ``--inflight`` (default 12) independent modal solves of the workload's
-cross-section each (72 solves): the designs of a forest are solved together as one block-diagonal problem by one C-ABI call
+A *step* is ``--workers`` (default 12 for cfg1, 8 for cfg2, 6 for cfg4, 1 for cfg5) FORESTS of ``--inflight`` (default 12) independent
+modal solves of the workload's cross-section each (cfg1: 144 solves): the designs of a forest are solved together as one block-diagonal problem by one C-ABI call
 (`plfem_solve_modes_batch`), sharing every kernel launch — the sweep's production mode.  A modal
 solve is `solve_vectorial_modes`: DOF tables -> assembly -> Dirichlet elimination -> ordering +
 factorisation of A - sigma*B -> eigensolve -> per-mode reductions, all of it done per design (nothing
-is reused between the designs of a forest).  ``--workers`` (default 6) host threads each drive their
+is reused between the designs of a forest).  ``--workers`` host threads each drive their
 own forest, so the host-side symbolic analysis of one forest overlaps the device work of another.
 The mesh is given (built on the host before timing, as in the reference where `MeshGenerator` runs
 first).  ``latency`` in the JSON line is one solve run alone.
